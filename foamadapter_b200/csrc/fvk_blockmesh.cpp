@@ -1,0 +1,405 @@
+// Host-side synthetic block-hex mesh in OpenFOAM blockMesh ordering.
+//
+// Stand-in for `blockMesh` + FoamAdapter::readOpenFOAMMesh (reference
+// src/datastructures/meshAdapter.cpp:59-136), which need OpenFOAM. Topology/ordering follows the
+// polyMesh fixtures the reference commits (test/setup_*/constant/polyMesh);
+// geometry follows OpenFOAM's primitiveMesh (triangle-fan face centres/areas, pyramid cell
+// centres/volumes) evaluated on points+faces, so it also holds for non-uniform point sets.
+#include "fvk_internal.hpp"
+
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace
+{
+
+struct BlockMeshStore
+{
+    fvk_mesh_desc desc {};
+    std::vector<double> points, V, C, Sf, Cf, magSf;
+    std::vector<int32_t> owner, neighbour, faceCells, patchOffsets;
+    std::vector<double> bCf, bCn, bSf, bMagSf, bNf, bDelta, bWeights, bDeltaCoeffs;
+    // poly (all faces incl. empty patches)
+    std::vector<int32_t> polyFaces, polyOwner;
+    int32_t nPolyFaces = 0;
+};
+
+inline void cross3(const double* a, const double* b, double* c)
+{
+    c[0] = a[1] * b[2] - a[2] * b[1];
+    c[1] = a[2] * b[0] - a[0] * b[2];
+    c[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+// quad face centre and area vector, OpenFOAM primitiveMeshFaceCentresAndAreas.C
+inline void quadGeometry(const double* p, const int32_t* f, double* cf, double* sf)
+{
+    double fc[3];
+    for (int d = 0; d < 3; ++d)
+    {
+        double s = p[3 * f[0] + d];
+        for (int k = 1; k < 4; ++k) s += p[3 * f[k] + d];
+        fc[d] = s / 4;
+    }
+    double sumN[3] = {0, 0, 0}, sumAc[3] = {0, 0, 0}, sumA = 0.0;
+    for (int k = 0; k < 4; ++k)
+    {
+        const double* cur = p + 3 * f[k];
+        const double* nxt = p + 3 * f[(k + 1) & 3];
+        double e1[3], e2[3], n[3], c[3];
+        for (int d = 0; d < 3; ++d)
+        {
+            c[d] = cur[d] + nxt[d] + fc[d];
+            e1[d] = nxt[d] - cur[d];
+            e2[d] = fc[d] - cur[d];
+        }
+        cross3(e1, e2, n);
+        const double a = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+        sumA += a;
+        for (int d = 0; d < 3; ++d)
+        {
+            sumN[d] += n[d];
+            sumAc[d] += a * c[d];
+        }
+    }
+    if (sumA < 1e-150)
+    {
+        for (int d = 0; d < 3; ++d) { cf[d] = fc[d]; sf[d] = 0.0; }
+    }
+    else
+    {
+        for (int d = 0; d < 3; ++d)
+        {
+            cf[d] = (1.0 / 3.0) * sumAc[d] / sumA;
+            sf[d] = 0.5 * sumN[d];
+        }
+    }
+}
+
+} // namespace
+
+extern "C" int fvk_blockmesh_create(int32_t nx, int32_t ny, int32_t nz, double lx, double ly,
+                                    double lz, int32_t nPatches, const int32_t* patchNSides,
+                                    const int32_t* patchSides, const int32_t* patchIsEmpty,
+                                    int32_t withPoints, fvk_mesh_desc** out)
+{
+    if (!out || nx < 1 || ny < 1 || nz < 1 || nPatches < 0 || (nPatches && (!patchNSides || !patchSides)))
+        return fvk_fail(FVK_EINVAL, "fvk_blockmesh_create: bad arguments");
+    const int64_t nC64 = int64_t(nx) * ny * nz;
+    const int64_t nI64 = int64_t(nx - 1) * ny * nz + int64_t(nx) * (ny - 1) * nz + int64_t(nx) * ny * (nz - 1);
+    const int64_t sideSize[6] = {int64_t(ny) * nz, int64_t(ny) * nz, int64_t(nx) * nz,
+                                 int64_t(nx) * nz, int64_t(nx) * ny, int64_t(nx) * ny};
+    int64_t nPolyB = 0, nB64 = 0;
+    {
+        int s = 0;
+        bool used[6] = {false, false, false, false, false, false};
+        for (int p = 0; p < nPatches; ++p)
+            for (int q = 0; q < patchNSides[p]; ++q, ++s)
+            {
+                const int side = patchSides[s];
+                if (side < 0 || side > 5 || used[side])
+                    return fvk_fail(FVK_EINVAL, "fvk_blockmesh_create: bad/duplicate side");
+                used[side] = true;
+                nPolyB += sideSize[side];
+                if (!(patchIsEmpty && patchIsEmpty[p])) nB64 += sideSize[side];
+            }
+        for (int side = 0; side < 6; ++side)
+            if (!used[side]) return fvk_fail(FVK_EINVAL, "fvk_blockmesh_create: every block side needs a patch");
+    }
+    if (nI64 + nPolyB >= (int64_t(1) << 30) || nC64 >= (int64_t(1) << 30))
+        return fvk_fail(FVK_EUNSUPPORTED, "fvk_blockmesh_create: mesh too large for int32 labels");
+
+    BlockMeshStore* st = new (std::nothrow) BlockMeshStore;
+    if (!st) return fvk_fail(FVK_ENOMEM, "fvk_blockmesh_create: out of memory");
+    try
+    {
+        const int32_t nC = int32_t(nC64), nI = int32_t(nI64), nB = int32_t(nB64);
+        const int32_t nPoly = int32_t(nI64 + nPolyB);
+        const int32_t nF = nI + nB;
+        const int64_t npx = nx + 1, npy = ny + 1, npz = nz + 1;
+        const int64_t nP = npx * npy * npz;
+        auto vtx = [=](int64_t i, int64_t j, int64_t k) { return int32_t(i + npx * (j + npy * k)); };
+        auto cell = [=](int64_t i, int64_t j, int64_t k) { return int32_t(i + int64_t(nx) * (j + int64_t(ny) * k)); };
+
+        st->points.resize(3 * nP);
+#pragma omp parallel for schedule(static)
+        for (int64_t k = 0; k < npz; ++k)
+            for (int64_t j = 0; j < npy; ++j)
+                for (int64_t i = 0; i < npx; ++i)
+                {
+                    double* p = &st->points[3 * (i + npx * (j + npy * k))];
+                    p[0] = lx * (double(i) / nx);
+                    p[1] = ly * (double(j) / ny);
+                    p[2] = lz * (double(k) / nz);
+                }
+
+        // ---- poly faces -------------------------------------------------------------------
+        st->polyFaces.resize(4 * int64_t(nPoly));
+        st->polyOwner.resize(nPoly);
+        st->neighbour.resize(nI);
+        st->nPolyFaces = nPoly;
+        // internal faces: owner ascending, then +x, +y, +z. First face id of each cell by scan.
+        std::vector<int32_t> ownStart(size_t(nC) + 1);
+        {
+            // faces owned by cell (i,j,k) = (i<nx-1)+(j<ny-1)+(k<nz-1); closed form per row
+            int64_t run = 0;
+            for (int64_t k = 0; k < nz; ++k)
+                for (int64_t j = 0; j < ny; ++j)
+                {
+                    const int base = (j < ny - 1) + (k < nz - 1);
+                    int32_t* o = &ownStart[cell(0, j, k)];
+                    for (int64_t i = 0; i < nx; ++i)
+                    {
+                        o[i] = int32_t(run);
+                        run += base + (i < nx - 1);
+                    }
+                }
+            ownStart[nC] = int32_t(run);
+        }
+#pragma omp parallel for schedule(static)
+        for (int64_t k = 0; k < nz; ++k)
+            for (int64_t j = 0; j < ny; ++j)
+                for (int64_t i = 0; i < nx; ++i)
+                {
+                    const int32_t c = cell(i, j, k);
+                    int32_t f = ownStart[c];
+                    if (i < nx - 1)
+                    {
+                        int32_t* q = &st->polyFaces[4 * int64_t(f)];
+                        q[0] = vtx(i + 1, j, k); q[1] = vtx(i + 1, j + 1, k);
+                        q[2] = vtx(i + 1, j + 1, k + 1); q[3] = vtx(i + 1, j, k + 1);
+                        st->polyOwner[f] = c; st->neighbour[f] = cell(i + 1, j, k); ++f;
+                    }
+                    if (j < ny - 1)
+                    {
+                        int32_t* q = &st->polyFaces[4 * int64_t(f)];
+                        q[0] = vtx(i, j + 1, k); q[1] = vtx(i, j + 1, k + 1);
+                        q[2] = vtx(i + 1, j + 1, k + 1); q[3] = vtx(i + 1, j + 1, k);
+                        st->polyOwner[f] = c; st->neighbour[f] = cell(i, j + 1, k); ++f;
+                    }
+                    if (k < nz - 1)
+                    {
+                        int32_t* q = &st->polyFaces[4 * int64_t(f)];
+                        q[0] = vtx(i, j, k + 1); q[1] = vtx(i + 1, j, k + 1);
+                        q[2] = vtx(i + 1, j + 1, k + 1); q[3] = vtx(i, j + 1, k + 1);
+                        st->polyOwner[f] = c; st->neighbour[f] = cell(i, j, k + 1); ++f;
+                    }
+                }
+        // boundary faces: patches in dictionary order, sides in listed order
+        // (blockMesh block::createBoundary loop nests)
+        std::vector<int32_t> keepStart; // poly start of each kept (non-empty-type) side run
+        std::vector<int32_t> keepSize;
+        st->patchOffsets.assign(1, 0);
+        {
+            int64_t f = nI;
+            int s = 0;
+            for (int p = 0; p < nPatches; ++p)
+            {
+                const bool isEmpty = patchIsEmpty && patchIsEmpty[p];
+                int32_t patchSize = 0;
+                for (int q = 0; q < patchNSides[p]; ++q, ++s)
+                {
+                    const int side = patchSides[s];
+                    const int64_t f0 = f;
+                    auto put = [&](int32_t a, int32_t b, int32_t c, int32_t d, int32_t own) {
+                        int32_t* r = &st->polyFaces[4 * f];
+                        r[0] = a; r[1] = b; r[2] = c; r[3] = d;
+                        st->polyOwner[f] = own;
+                        ++f;
+                    };
+                    switch (side)
+                    {
+                        case 0:
+                            for (int64_t k = 0; k < nz; ++k) for (int64_t j = 0; j < ny; ++j)
+                                put(vtx(0, j, k), vtx(0, j, k + 1), vtx(0, j + 1, k + 1), vtx(0, j + 1, k), cell(0, j, k));
+                            break;
+                        case 1:
+                            for (int64_t k = 0; k < nz; ++k) for (int64_t j = 0; j < ny; ++j)
+                                put(vtx(nx, j, k), vtx(nx, j + 1, k), vtx(nx, j + 1, k + 1), vtx(nx, j, k + 1), cell(nx - 1, j, k));
+                            break;
+                        case 2:
+                            for (int64_t i = 0; i < nx; ++i) for (int64_t k = 0; k < nz; ++k)
+                                put(vtx(i, 0, k), vtx(i + 1, 0, k), vtx(i + 1, 0, k + 1), vtx(i, 0, k + 1), cell(i, 0, k));
+                            break;
+                        case 3:
+                            for (int64_t i = 0; i < nx; ++i) for (int64_t k = 0; k < nz; ++k)
+                                put(vtx(i, ny, k), vtx(i, ny, k + 1), vtx(i + 1, ny, k + 1), vtx(i + 1, ny, k), cell(i, ny - 1, k));
+                            break;
+                        case 4:
+                            for (int64_t i = 0; i < nx; ++i) for (int64_t j = 0; j < ny; ++j)
+                                put(vtx(i, j, 0), vtx(i, j + 1, 0), vtx(i + 1, j + 1, 0), vtx(i + 1, j, 0), cell(i, j, 0));
+                            break;
+                        default:
+                            for (int64_t i = 0; i < nx; ++i) for (int64_t j = 0; j < ny; ++j)
+                                put(vtx(i, j, nz), vtx(i + 1, j, nz), vtx(i + 1, j + 1, nz), vtx(i, j + 1, nz), cell(i, j, nz - 1));
+                            break;
+                    }
+                    if (!isEmpty)
+                    {
+                        keepStart.push_back(int32_t(f0));
+                        keepSize.push_back(int32_t(f - f0));
+                        patchSize += int32_t(f - f0);
+                    }
+                }
+                if (!isEmpty) st->patchOffsets.push_back(st->patchOffsets.back() + patchSize);
+            }
+        }
+        const int32_t nKeptPatches = int32_t(st->patchOffsets.size()) - 1;
+
+        // ---- geometry on all poly faces ---------------------------------------------------
+        std::vector<double> pCf(3 * size_t(nPoly)), pSf(3 * size_t(nPoly));
+#pragma omp parallel for schedule(static)
+        for (int64_t f = 0; f < nPoly; ++f)
+            quadGeometry(st->points.data(), &st->polyFaces[4 * f], &pCf[3 * f], &pSf[3 * f]);
+
+        // cell centre estimate = mean of face centres (own faces then nei faces, OpenFOAM order)
+        std::vector<double> cEst(3 * size_t(nC), 0.0);
+        std::vector<int32_t> cnt(nC, 0);
+        for (int64_t f = 0; f < nPoly; ++f)
+        {
+            const int32_t o = st->polyOwner[f];
+            for (int d = 0; d < 3; ++d) cEst[3 * size_t(o) + d] += pCf[3 * f + d];
+            ++cnt[o];
+        }
+        for (int64_t f = 0; f < nI; ++f)
+        {
+            const int32_t n = st->neighbour[f];
+            for (int d = 0; d < 3; ++d) cEst[3 * size_t(n) + d] += pCf[3 * f + d];
+            ++cnt[n];
+        }
+#pragma omp parallel for schedule(static)
+        for (int64_t c = 0; c < nC; ++c)
+            for (int d = 0; d < 3; ++d) cEst[3 * c + d] /= cnt[c];
+
+        st->C.assign(3 * size_t(nC), 0.0);
+        st->V.assign(nC, 0.0);
+        for (int64_t f = 0; f < nPoly; ++f)
+        {
+            const size_t o = size_t(st->polyOwner[f]);
+            double pyr3 = 0.0;
+            for (int d = 0; d < 3; ++d) pyr3 += pSf[3 * f + d] * (pCf[3 * f + d] - cEst[3 * o + d]);
+            for (int d = 0; d < 3; ++d)
+                st->C[3 * o + d] += pyr3 * ((3.0 / 4.0) * pCf[3 * f + d] + (1.0 / 4.0) * cEst[3 * o + d]);
+            st->V[o] += pyr3;
+        }
+        for (int64_t f = 0; f < nI; ++f)
+        {
+            const size_t n = size_t(st->neighbour[f]);
+            double pyr3 = 0.0;
+            for (int d = 0; d < 3; ++d) pyr3 += pSf[3 * f + d] * (cEst[3 * n + d] - pCf[3 * f + d]);
+            for (int d = 0; d < 3; ++d)
+                st->C[3 * n + d] += pyr3 * ((3.0 / 4.0) * pCf[3 * f + d] + (1.0 / 4.0) * cEst[3 * n + d]);
+            st->V[n] += pyr3;
+        }
+#pragma omp parallel for schedule(static)
+        for (int64_t c = 0; c < nC; ++c)
+        {
+            for (int d = 0; d < 3; ++d) st->C[3 * c + d] /= st->V[c];
+            st->V[c] *= (1.0 / 3.0);
+        }
+        std::vector<double>().swap(cEst);
+        std::vector<int32_t>().swap(cnt);
+
+        // ---- NeoN view: internal faces + kept boundary faces ------------------------------
+        st->owner.resize(nF);
+        st->Sf.resize(3 * size_t(nF));
+        st->Cf.resize(3 * size_t(nF));
+        st->magSf.resize(nF);
+        std::memcpy(st->owner.data(), st->polyOwner.data(), sizeof(int32_t) * size_t(nI));
+        std::memcpy(st->Sf.data(), pSf.data(), sizeof(double) * 3 * size_t(nI));
+        std::memcpy(st->Cf.data(), pCf.data(), sizeof(double) * 3 * size_t(nI));
+        {
+            int64_t dst = nI;
+            for (size_t r = 0; r < keepStart.size(); ++r)
+            {
+                std::memcpy(&st->owner[dst], &st->polyOwner[keepStart[r]], sizeof(int32_t) * size_t(keepSize[r]));
+                std::memcpy(&st->Sf[3 * dst], &pSf[3 * size_t(keepStart[r])], sizeof(double) * 3 * size_t(keepSize[r]));
+                std::memcpy(&st->Cf[3 * dst], &pCf[3 * size_t(keepStart[r])], sizeof(double) * 3 * size_t(keepSize[r]));
+                dst += keepSize[r];
+            }
+        }
+        std::vector<double>().swap(pSf);
+        std::vector<double>().swap(pCf);
+#pragma omp parallel for schedule(static)
+        for (int64_t f = 0; f < nF; ++f)
+        {
+            const double* s = &st->Sf[3 * f];
+            st->magSf[f] = std::sqrt(s[0] * s[0] + s[1] * s[1] + s[2] * s[2]);
+        }
+        // BoundaryMesh arrays (fvPatch: Cf, Cn, Sf, magSf, nf = Sf/magSf, delta = Cf - Cn,
+        // weights = 1 and deltaCoeffs = 1/|delta| on non-coupled patches)
+        st->faceCells.resize(nB);
+        st->bCf.resize(3 * size_t(nB)); st->bCn.resize(3 * size_t(nB)); st->bSf.resize(3 * size_t(nB));
+        st->bNf.resize(3 * size_t(nB)); st->bDelta.resize(3 * size_t(nB));
+        st->bMagSf.resize(nB); st->bWeights.resize(nB); st->bDeltaCoeffs.resize(nB);
+#pragma omp parallel for schedule(static)
+        for (int64_t b = 0; b < nB; ++b)
+        {
+            const int64_t f = nI + b;
+            const int32_t o = st->owner[f];
+            st->faceCells[b] = o;
+            double d2 = 0.0;
+            for (int d = 0; d < 3; ++d)
+            {
+                st->bCf[3 * b + d] = st->Cf[3 * f + d];
+                st->bCn[3 * b + d] = st->C[3 * size_t(o) + d];
+                st->bSf[3 * b + d] = st->Sf[3 * f + d];
+                st->bNf[3 * b + d] = st->Sf[3 * f + d] / st->magSf[f];
+                const double dl = st->Cf[3 * f + d] - st->C[3 * size_t(o) + d];
+                st->bDelta[3 * b + d] = dl;
+                d2 += dl * dl;
+            }
+            st->bMagSf[b] = st->magSf[f];
+            st->bWeights[b] = 1.0;
+            st->bDeltaCoeffs[b] = 1.0 / std::sqrt(d2);
+        }
+        if (!withPoints)
+        {
+            std::vector<double>().swap(st->points);
+            std::vector<int32_t>().swap(st->polyFaces);
+            std::vector<int32_t>().swap(st->polyOwner);
+            st->nPolyFaces = 0;
+        }
+
+        fvk_mesh_desc& d = st->desc;
+        d.nCells = nC; d.nInternalFaces = nI; d.nBoundaryFaces = nB; d.nPatches = nKeptPatches;
+        d.nPoints = withPoints ? int32_t(nP) : 0;
+        d.points = withPoints ? st->points.data() : nullptr;
+        d.cellVolumes = st->V.data(); d.cellCentres = st->C.data();
+        d.faceAreas = st->Sf.data(); d.faceCentres = st->Cf.data(); d.magFaceAreas = st->magSf.data();
+        d.faceOwner = st->owner.data(); d.faceNeighbour = st->neighbour.data();
+        d.faceCells = st->faceCells.data();
+        d.bCf = st->bCf.data(); d.bCn = st->bCn.data(); d.bSf = st->bSf.data();
+        d.bMagSf = st->bMagSf.data(); d.bNf = st->bNf.data(); d.bDelta = st->bDelta.data();
+        d.bWeights = st->bWeights.data(); d.bDeltaCoeffs = st->bDeltaCoeffs.data();
+        d.patchOffsets = st->patchOffsets.data();
+    }
+    catch (const std::bad_alloc&)
+    {
+        delete st;
+        return fvk_fail(FVK_ENOMEM, "fvk_blockmesh_create: out of memory");
+    }
+    static_assert(offsetof(BlockMeshStore, desc) == 0, "desc must be first");
+    *out = &st->desc;
+    return FVK_OK;
+}
+
+extern "C" int fvk_blockmesh_destroy(fvk_mesh_desc* desc)
+{
+    if (desc) delete reinterpret_cast<BlockMeshStore*>(desc);
+    return FVK_OK;
+}
+
+extern "C" int fvk_blockmesh_poly(const fvk_mesh_desc* desc, int32_t* nPolyFaces,
+                                  const int32_t** facePoints, const int32_t** polyOwner)
+{
+    if (!desc) return fvk_fail(FVK_EINVAL, "fvk_blockmesh_poly: null mesh");
+    const BlockMeshStore* st = reinterpret_cast<const BlockMeshStore*>(desc);
+    if (st->nPolyFaces == 0) return fvk_fail(FVK_EINVAL, "fvk_blockmesh_poly: created without points");
+    if (nPolyFaces) *nPolyFaces = st->nPolyFaces;
+    if (facePoints) *facePoints = st->polyFaces.data();
+    if (polyOwner) *polyOwner = st->polyOwner.data();
+    return FVK_OK;
+}

@@ -1,0 +1,593 @@
+// Explicit finite-volume operators: fused, deterministic, cell-centric gather kernels for sm_100a.
+//
+// The reference computes each operator as (1) a face loop writing a face-sized temporary phi_f,
+// (2) a face loop scattering flux to owner/neighbour with atomics, (3) a cell loop scaling by
+// coeff/V (src/NeoN/src/finiteVolume/cellCentred/operators/gaussGreen{Div,Grad,Laplacian}.cpp,
+// surfaceIntegrate.cpp, interpolation/{linear,upwind}.cpp, faceNormalGradient/uncorrected.cpp).
+// Here one kernel per operator walks, for every cell, its faces in ascending face id (the
+// summation order of the reference's SerialExecutor), recomputes the face value on the fly, and
+// writes the scaled result once. No atomics, no temporaries, bit-reproducible.
+//
+// Per-face arithmetic is written exactly as in the reference and the library is compiled with
+// -fmad=false, so results are bit-identical to the Serial executor built without FP contraction.
+#include "fvk_device.cuh"
+
+namespace
+{
+
+// ---- value-type helpers ------------------------------------------------------------------------
+struct S1 // scalar field
+{
+    using T = double;
+    static __device__ __forceinline__ T zero() { return 0.0; }
+    static __device__ __forceinline__ T ld(const double* __restrict__ p, int64_t i) { return p[i]; }
+    static __device__ __forceinline__ void st(double* __restrict__ p, int64_t i, T v) { p[i] = v; }
+    static __device__ __forceinline__ T add(T a, T b) { return a + b; }
+    static __device__ __forceinline__ T sub(T a, T b) { return a - b; }
+    static __device__ __forceinline__ T mul(double s, T a) { return s * a; } // scalar * value
+};
+struct S3 // Vec3 field, AoS
+{
+    using T = Vec3d;
+    static __device__ __forceinline__ T zero() { return Vec3d {0.0, 0.0, 0.0}; }
+    static __device__ __forceinline__ T ld(const double* __restrict__ p, int64_t i) { return ld3(p, i); }
+    static __device__ __forceinline__ void st(double* __restrict__ p, int64_t i, T v) { st3(p, i, v); }
+    static __device__ __forceinline__ T add(T a, T b) { return Vec3d {a.x + b.x, a.y + b.y, a.z + b.z}; }
+    static __device__ __forceinline__ T sub(T a, T b) { return Vec3d {a.x - b.x, a.y - b.y, a.z - b.z}; }
+    // NeoN: operator*(scalar, Vec3) is rhs *= s  ->  component * s (vec3.hpp)
+    static __device__ __forceinline__ T mul(double s, T a) { return Vec3d {a.x * s, a.y * s, a.z * s}; }
+};
+
+// ---- per-face flux functors --------------------------------------------------------------------
+// internal(f, own, nei) is the value the reference adds to res[own] and subtracts from res[nei];
+// boundary(f, b, own) is the value added to res[own] for boundary face f = nI + b.
+
+template <class VT, int SCHEME>
+struct DivOp // gaussGreenDiv.cpp:46-67 with linear.cpp:30-45 / upwind.cpp:32-55
+{
+    using V = VT;
+    using T = typename VT::T;
+    const double* __restrict__ faceFlux;
+    const double* __restrict__ w;
+    const double* __restrict__ phi;
+    const double* __restrict__ phiB;
+    __device__ __forceinline__ T internal(int f, int own, int nei) const
+    {
+        const double F = faceFlux[f];
+        T phif;
+        if (SCHEME == FVK_LINEAR)
+        {
+            const double wf = w[f];
+            phif = VT::add(VT::mul(wf, VT::ld(phi, own)), VT::mul(1 - wf, VT::ld(phi, nei)));
+        }
+        else
+        {
+            phif = (F >= 0) ? VT::ld(phi, own) : VT::ld(phi, nei);
+        }
+        return VT::mul(F, phif);
+    }
+    __device__ __forceinline__ T boundary(int f, int b, int) const
+    {
+        // phif = weights[f] * bvalue[b]; the geometric boundary weight is exactly 1
+        return VT::mul(faceFlux[f], VT::ld(phiB, b));
+    }
+};
+
+struct GradOp // gaussGreenGrad.cpp:46-64 with linear.cpp:30-45
+{
+    using V = S3;
+    using T = Vec3d;
+    const double* __restrict__ Sf;
+    const double* __restrict__ w;
+    const double* __restrict__ phi;
+    const double* __restrict__ phiB;
+    __device__ __forceinline__ T internal(int f, int own, int nei) const
+    {
+        const double wf = w[f];
+        const double phif = wf * phi[own] + (1 - wf) * phi[nei];
+        const Vec3d s = ld3(Sf, f);
+        return Vec3d {s.x * phif, s.y * phif, s.z * phif};
+    }
+    __device__ __forceinline__ T boundary(int f, int b, int) const
+    {
+        const double phif = phiB[b];
+        const Vec3d s = ld3(Sf, f);
+        return Vec3d {s.x * phif, s.y * phif, s.z * phif};
+    }
+};
+
+template <class VT>
+struct LaplacianOp // gaussGreenLaplacian.cpp:34-52 with uncorrected.cpp:34-51
+{
+    using V = VT;
+    using T = typename VT::T;
+    const double* __restrict__ magSf;
+    const double* __restrict__ dc; // nonOrthDeltaCoeffs
+    const double* __restrict__ phi;
+    const double* __restrict__ phiB;
+    __device__ __forceinline__ T internal(int f, int own, int nei) const
+    {
+        const T sn = VT::mul(dc[f], VT::sub(VT::ld(phi, nei), VT::ld(phi, own)));
+        return VT::mul(magSf[f], sn);
+    }
+    __device__ __forceinline__ T boundary(int f, int b, int own) const
+    {
+        const T sn = VT::mul(dc[f], VT::sub(VT::ld(phiB, b), VT::ld(phi, own)));
+        return VT::mul(magSf[f], sn);
+    }
+};
+
+template <class VT>
+struct SurfIntOp // surfaceIntegrate.cpp:26-41
+{
+    using V = VT;
+    using T = typename VT::T;
+    const double* __restrict__ flux;
+    __device__ __forceinline__ T internal(int f, int, int) const { return VT::ld(flux, f); }
+    __device__ __forceinline__ T boundary(int f, int, int) const { return VT::ld(flux, f); }
+};
+
+// ---- scaling + store ---------------------------------------------------------------------------
+struct Scaling
+{
+    const double* __restrict__ V;    // cell volumes
+    const double* __restrict__ view; // Coeff view or nullptr
+    double coeff;
+    bool invVolOnly; // grad: res *= 1 / V
+    __device__ __forceinline__ double at(int c) const
+    {
+        if (invVolOnly) return 1 / V[c];
+        const double os = view ? view[c] * coeff : coeff; // dsl/coeff.hpp:35
+        return os / V[c];
+    }
+};
+
+template <class VT>
+__device__ __forceinline__ void finish(double* __restrict__ out, int c, typename VT::T acc, double s, int mode)
+{
+    if (mode == FVK_ADD)
+        VT::st(out, c, VT::add(VT::ld(out, c), VT::mul(s, acc)));
+    else
+        VT::st(out, c, VT::mul(s, acc));
+}
+// NOTE: res[c] *= s in the reference is (res * s); mul(s, acc) is the same product (commutative).
+
+// ---- variant 0: unified sorted stencil ------------------------------------------------------------
+template <class Op>
+__global__ void __launch_bounds__(256)
+k_gather_stencil(Op op, Scaling sc, int nC, int nI, const int* __restrict__ seg,
+                 const int* __restrict__ ent, const int* __restrict__ owner,
+                 const int* __restrict__ neighbour, double* __restrict__ out, int mode)
+{
+    using VT = typename Op::V;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nC) return;
+    typename VT::T acc = (mode == FVK_ACC_SCALE) ? VT::ld(out, c) : VT::zero();
+    const int e1 = seg[c + 1];
+    for (int e = seg[c]; e < e1; ++e)
+    {
+        const int code = ent[e];
+        const int f = code >> 1;
+        if (f < nI)
+        {
+            if (code & 1)
+                acc = VT::sub(acc, op.internal(f, owner[f], c));
+            else
+                acc = VT::add(acc, op.internal(f, c, neighbour[f]));
+        }
+        else
+        {
+            acc = VT::add(acc, op.boundary(f, f - nI, c));
+        }
+    }
+    finish<VT>(out, c, acc, sc.at(c), mode);
+}
+
+// ---- variant 1: split plan for owner-sorted meshes -------------------------------------------------
+// lower faces (cell is neighbour; ids below every owned face) ascending, then the contiguous owned
+// faces, then boundary faces -- together again ascending face id.
+template <class Op>
+__global__ void __launch_bounds__(256)
+k_gather_split(Op op, Scaling sc, int nC, int nI, const int* __restrict__ lowSeg,
+               const int* __restrict__ lowFace, const int* __restrict__ lowOwner,
+               const int* __restrict__ ownStart, const int* __restrict__ neighbour,
+               const unsigned* __restrict__ hasBnd, int nBndCells, const int* __restrict__ bndCell,
+               const int* __restrict__ bndSeg, const int* __restrict__ bndFace,
+               double* __restrict__ out, int mode)
+{
+    using VT = typename Op::V;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nC) return;
+    typename VT::T acc = (mode == FVK_ACC_SCALE) ? VT::ld(out, c) : VT::zero();
+    const int l0 = lowSeg[c], l1 = lowSeg[c + 1];
+    const int f0 = ownStart[c], f1 = ownStart[c + 1];
+    for (int e = l0; e < l1; ++e) acc = VT::sub(acc, op.internal(lowFace[e], lowOwner[e], c));
+    for (int f = f0; f < f1; ++f) acc = VT::add(acc, op.internal(f, c, neighbour[f]));
+    if ((hasBnd[c >> 5] >> (c & 31)) & 1u)
+    {
+        int lo = 0, hi = nBndCells - 1;
+        while (lo < hi)
+        {
+            const int mid = (lo + hi) >> 1;
+            if (bndCell[mid] < c) lo = mid + 1; else hi = mid;
+        }
+        const int b1 = bndSeg[lo + 1];
+        for (int e = bndSeg[lo]; e < b1; ++e)
+        {
+            const int f = bndFace[e];
+            acc = VT::add(acc, op.boundary(f, f - nI, c));
+        }
+    }
+    finish<VT>(out, c, acc, sc.at(c), mode);
+}
+
+template <class Op>
+int launch_gather(const fvk_mesh* m, Op op, Scaling sc, double* out, int mode, fvk_stream stream)
+{
+    if (mode != FVK_SET && mode != FVK_ACC_SCALE && mode != FVK_ADD)
+        return fvk_fail(FVK_EINVAL, "bad mode %d", mode);
+    const int nC = m->nCells;
+    const int grid = (nC + 255) / 256;
+    const int variant = fvk_variant();
+    if (variant == 0 && m->ownerSorted)
+        k_gather_split<Op><<<grid, 256, 0, fvk_cu(stream)>>>(
+            op, sc, nC, m->nInternalFaces, m->lowSeg, m->lowFace, m->lowOwner, m->ownStart,
+            m->neighbour, m->hasBnd, m->nBndCells, m->bndCell, m->bndSeg, m->bndFace, out, mode);
+    else
+        k_gather_stencil<Op><<<grid, 256, 0, fvk_cu(stream)>>>(
+            op, sc, nC, m->nInternalFaces, m->stencilSeg, m->gatherEnt, m->owner, m->neighbour, out, mode);
+    FVK_LAUNCH_CHECK();
+    return FVK_OK;
+}
+
+#define REQUIRE(cond, msg)                                                                         \
+    do { if (!(cond)) return fvk_fail(FVK_EINVAL, "%s: %s", __func__, msg); } while (0)
+
+// ---- face kernels (interpolate / snGrad / weights) -----------------------------------------------
+template <class VT, int SCHEME>
+__global__ void __launch_bounds__(256)
+k_interpolate(int nI, int nF, const int* __restrict__ owner, const int* __restrict__ neighbour,
+              const double* __restrict__ w, const double* __restrict__ faceFlux,
+              const double* __restrict__ phi, const double* __restrict__ phiB, double* __restrict__ out)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nF) return;
+    typename VT::T r;
+    if (f < nI)
+    {
+        if (SCHEME == FVK_LINEAR)
+        {
+            const double wf = w[f];
+            r = VT::add(VT::mul(wf, VT::ld(phi, owner[f])), VT::mul(1 - wf, VT::ld(phi, neighbour[f])));
+        }
+        else
+            r = (faceFlux[f] >= 0) ? VT::ld(phi, owner[f]) : VT::ld(phi, neighbour[f]);
+    }
+    else
+        r = VT::mul(w[f], VT::ld(phiB, f - nI));
+    VT::st(out, f, r);
+}
+
+template <class VT>
+__global__ void __launch_bounds__(256)
+k_sngrad(int nI, int nF, const int* __restrict__ owner, const int* __restrict__ neighbour,
+         const double* __restrict__ dc, const double* __restrict__ phi, const double* __restrict__ phiB,
+         double* __restrict__ out)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nF) return;
+    const typename VT::T a = (f < nI) ? VT::ld(phi, neighbour[f]) : VT::ld(phiB, f - nI);
+    VT::st(out, f, VT::mul(dc[f], VT::sub(a, VT::ld(phi, owner[f]))));
+}
+
+__global__ void __launch_bounds__(256)
+k_weights(int scheme, int nI, int nF, const double* __restrict__ geomW, const double* __restrict__ faceFlux,
+          double* __restrict__ wFace, double* __restrict__ wB)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nF) return;
+    if (f < nI)
+        wFace[f] = (scheme == FVK_LINEAR) ? geomW[f] : (faceFlux[f] >= 0 ? 1.0 : 0.0);
+    else
+    {
+        const double v = (scheme == FVK_LINEAR) ? geomW[f] : 1.0;
+        wFace[f] = v;
+        if (wB) wB[f - nI] = v;
+    }
+}
+
+// ---- CoNum -------------------------------------------------------------------------------------
+// stage 1: per cell sumPhi = sum_f |F_f| (own and nei both +), block partials of
+// max(sumPhi/V), sum(sumPhi), sum(V); stage 2: one block folds the partials in fixed order.
+struct CoNumOp
+{
+    const double* __restrict__ faceFlux;
+    __device__ __forceinline__ double at(int f) const { const double F = faceFlux[f]; return sqrt(F * F); }
+};
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__global__ void __launch_bounds__(256)
+k_conum_stage1(CoNumOp op, int nC, const int* __restrict__ seg, const int* __restrict__ ent,
+               const double* __restrict__ V, double* __restrict__ partial /* [3*gridDim.x] */)
+{
+    __shared__ double sMax[8], sPhi[8], sVol[8];
+    double lmax = -1.7976931348623157e308, lphi = 0.0, lvol = 0.0;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nC; c += gridDim.x * blockDim.x)
+    {
+        double acc = 0.0;
+        const int e1 = seg[c + 1];
+        for (int e = seg[c]; e < e1; ++e) acc += op.at(ent[e] >> 1);
+        const double v = V[c];
+        lmax = fmax(lmax, acc / v);
+        lphi += acc;
+        lvol += v;
+    }
+    lmax = warp_max(lmax); lphi = warp_sum(lphi); lvol = warp_sum(lvol);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { sMax[wid] = lmax; sPhi[wid] = lphi; sVol[wid] = lvol; }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        for (int i = 1; i < 8; ++i) { lmax = fmax(lmax, sMax[i]); lphi += sPhi[i]; lvol += sVol[i]; }
+        partial[3 * blockIdx.x] = lmax; partial[3 * blockIdx.x + 1] = lphi; partial[3 * blockIdx.x + 2] = lvol;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_conum_stage2(int nPartial, const double* __restrict__ partial, double dt, double* __restrict__ result)
+{
+    __shared__ double sMax[8], sPhi[8], sVol[8];
+    double lmax = -1.7976931348623157e308, lphi = 0.0, lvol = 0.0;
+    for (int i = threadIdx.x; i < nPartial; i += blockDim.x)
+    {
+        lmax = fmax(lmax, partial[3 * i]); lphi += partial[3 * i + 1]; lvol += partial[3 * i + 2];
+    }
+    lmax = warp_max(lmax); lphi = warp_sum(lphi); lvol = warp_sum(lvol);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { sMax[wid] = lmax; sPhi[wid] = lphi; sVol[wid] = lvol; }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        for (int i = 1; i < 8; ++i) { lmax = fmax(lmax, sMax[i]); lphi += sPhi[i]; lvol += sVol[i]; }
+        result[0] = lmax * 0.5 * dt;            // coNum.cpp:89
+        result[1] = 0.5 * (lphi / lvol) * dt;   // coNum.cpp:90
+    }
+}
+
+// ---- boundary conditions -------------------------------------------------------------------------
+struct BcPlan
+{
+    int nPatches;
+    int offsets[FVK_MAX_PATCHES + 1];
+    int kind[FVK_MAX_PATCHES];
+    double value[FVK_MAX_PATCHES * 3];
+};
+
+template <class VT, int NC>
+__global__ void __launch_bounds__(256)
+k_correct_bcs(BcPlan plan, int nB, const int* __restrict__ faceCells, const double* __restrict__ bDeltaCoeffs,
+              const double* __restrict__ internal, double* __restrict__ value, double* __restrict__ refValue,
+              double* __restrict__ valueFraction, double* __restrict__ refGrad)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nB) return;
+    int p = 0;
+    while (p + 1 < plan.nPatches && b >= plan.offsets[p + 1]) ++p;
+    const int kind = plan.kind[p];
+    const typename VT::T cst = VT::ld(plan.value, p);
+    if (kind == FVK_BC_FIXED_VALUE)
+    { // fixedValue.hpp:33-42
+        VT::st(refValue, b, cst); VT::st(value, b, cst); valueFraction[b] = 1.0; VT::st(refGrad, b, cst);
+    }
+    else if (kind == FVK_BC_FIXED_GRADIENT)
+    { // fixedGradient.hpp:42-53: value = internal + grad * (1/deltaCoeffs)
+        VT::st(refGrad, b, cst);
+        const double inv = 1 / bDeltaCoeffs[b];
+        VT::st(value, b, VT::add(VT::ld(internal, faceCells[b]), VT::mul(inv, cst)));
+        valueFraction[b] = 0.0; VT::st(refValue, b, VT::zero());
+    }
+    else if (kind == FVK_BC_EXTRAPOLATED)
+    { // extrapolated.hpp:40-52
+        const typename VT::T v = VT::ld(internal, faceCells[b]);
+        VT::st(value, b, v); valueFraction[b] = 1.0; VT::st(refValue, b, v); VT::st(refGrad, b, VT::zero());
+    }
+}
+
+} // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+template <class VT>
+static int div_impl(const fvk_mesh* m, int scheme, const double* faceFlux, const double* phi,
+                    const double* phiB, double coeff, const double* view, double* out, int mode, fvk_stream s)
+{
+    if (!m || !faceFlux || !phi || !out || (m->nBoundaryFaces && !phiB))
+        return fvk_fail(FVK_EINVAL, "fvk_div: null argument");
+    Scaling sc {m->V, view, coeff, false};
+    if (scheme == FVK_LINEAR)
+        return launch_gather(m, DivOp<VT, FVK_LINEAR> {faceFlux, m->weights, phi, phiB}, sc, out, mode, s);
+    if (scheme == FVK_UPWIND)
+        return launch_gather(m, DivOp<VT, FVK_UPWIND> {faceFlux, m->weights, phi, phiB}, sc, out, mode, s);
+    return fvk_fail(FVK_EINVAL, "fvk_div: unknown scheme %d", scheme);
+}
+
+extern "C" int fvk_div_s(const fvk_mesh* m, int scheme, const double* faceFlux, const double* phi,
+                         const double* phiB, double coeff, const double* view, double* out, int mode, fvk_stream s)
+{
+    return div_impl<S1>(m, scheme, faceFlux, phi, phiB, coeff, view, out, mode, s);
+}
+extern "C" int fvk_div_v(const fvk_mesh* m, int scheme, const double* faceFlux, const double* phi,
+                         const double* phiB, double coeff, const double* view, double* out, int mode, fvk_stream s)
+{
+    return div_impl<S3>(m, scheme, faceFlux, phi, phiB, coeff, view, out, mode, s);
+}
+
+extern "C" int fvk_grad_s(const fvk_mesh* m, const double* phi, const double* phiB, double* out, int mode, fvk_stream s)
+{
+    if (!m || !phi || !out || (m->nBoundaryFaces && !phiB)) return fvk_fail(FVK_EINVAL, "fvk_grad_s: null argument");
+    if (mode == FVK_ADD) return fvk_fail(FVK_EINVAL, "fvk_grad_s: mode FVK_ADD not defined for grad");
+    Scaling sc {m->V, nullptr, 1.0, true};
+    return launch_gather(m, GradOp {m->Sf, m->weights, phi, phiB}, sc, out, mode, s);
+}
+
+extern "C" int fvk_laplacian_s(const fvk_mesh* m, const double* phi, const double* phiB, double coeff,
+                               const double* view, double* out, int mode, fvk_stream s)
+{
+    if (!m || !phi || !out || (m->nBoundaryFaces && !phiB)) return fvk_fail(FVK_EINVAL, "fvk_laplacian_s: null argument");
+    Scaling sc {m->V, view, coeff, false};
+    return launch_gather(m, LaplacianOp<S1> {m->magSf, m->nonOrthDeltaCoeffs, phi, phiB}, sc, out, mode, s);
+}
+extern "C" int fvk_laplacian_v(const fvk_mesh* m, const double* phi, const double* phiB, double coeff,
+                               const double* view, double* out, int mode, fvk_stream s)
+{
+    if (!m || !phi || !out || (m->nBoundaryFaces && !phiB)) return fvk_fail(FVK_EINVAL, "fvk_laplacian_v: null argument");
+    Scaling sc {m->V, view, coeff, false};
+    return launch_gather(m, LaplacianOp<S3> {m->magSf, m->nonOrthDeltaCoeffs, phi, phiB}, sc, out, mode, s);
+}
+
+extern "C" int fvk_surface_integrate_s(const fvk_mesh* m, const double* flux, double coeff, const double* view,
+                                       double* out, int mode, fvk_stream s)
+{
+    if (!m || !flux || !out) return fvk_fail(FVK_EINVAL, "fvk_surface_integrate_s: null argument");
+    Scaling sc {m->V, view, coeff, false};
+    return launch_gather(m, SurfIntOp<S1> {flux}, sc, out, mode, s);
+}
+extern "C" int fvk_surface_integrate_v(const fvk_mesh* m, const double* flux, double coeff, const double* view,
+                                       double* out, int mode, fvk_stream s)
+{
+    if (!m || !flux || !out) return fvk_fail(FVK_EINVAL, "fvk_surface_integrate_v: null argument");
+    Scaling sc {m->V, view, coeff, false};
+    return launch_gather(m, SurfIntOp<S3> {flux}, sc, out, mode, s);
+}
+
+template <class VT>
+static int interpolate_impl(const fvk_mesh* m, int scheme, const double* faceFlux, const double* phi,
+                            const double* phiB, double* outFace, fvk_stream s)
+{
+    if (!m || !phi || !outFace || (m->nBoundaryFaces && !phiB)) return fvk_fail(FVK_EINVAL, "fvk_interpolate: null argument");
+    const int nF = m->nInternalFaces + m->nBoundaryFaces;
+    const int grid = (nF + 255) / 256;
+    if (grid == 0) return FVK_OK;
+    if (scheme == FVK_LINEAR)
+        k_interpolate<VT, FVK_LINEAR><<<grid, 256, 0, fvk_cu(s)>>>(m->nInternalFaces, nF, m->owner, m->neighbour,
+                                                                   m->weights, faceFlux, phi, phiB, outFace);
+    else if (scheme == FVK_UPWIND)
+    {
+        if (!faceFlux) return fvk_fail(FVK_EINVAL, "fvk_interpolate: upwind requires a faceFlux"); // upwind.hpp:66-72
+        k_interpolate<VT, FVK_UPWIND><<<grid, 256, 0, fvk_cu(s)>>>(m->nInternalFaces, nF, m->owner, m->neighbour,
+                                                                   m->weights, faceFlux, phi, phiB, outFace);
+    }
+    else
+        return fvk_fail(FVK_EINVAL, "fvk_interpolate: unknown scheme %d", scheme);
+    FVK_LAUNCH_CHECK();
+    return FVK_OK;
+}
+extern "C" int fvk_interpolate_s(const fvk_mesh* m, int scheme, const double* faceFlux, const double* phi,
+                                 const double* phiB, double* outFace, fvk_stream s)
+{
+    return interpolate_impl<S1>(m, scheme, faceFlux, phi, phiB, outFace, s);
+}
+extern "C" int fvk_interpolate_v(const fvk_mesh* m, int scheme, const double* faceFlux, const double* phi,
+                                 const double* phiB, double* outFace, fvk_stream s)
+{
+    return interpolate_impl<S3>(m, scheme, faceFlux, phi, phiB, outFace, s);
+}
+
+extern "C" int fvk_interpolation_weights(const fvk_mesh* m, int scheme, const double* faceFlux, double* wFace,
+                                         double* wB, fvk_stream s)
+{
+    if (!m || !wFace) return fvk_fail(FVK_EINVAL, "fvk_interpolation_weights: null argument");
+    if (scheme != FVK_LINEAR && scheme != FVK_UPWIND) return fvk_fail(FVK_EINVAL, "fvk_interpolation_weights: unknown scheme");
+    if (scheme == FVK_UPWIND && !faceFlux) return fvk_fail(FVK_EINVAL, "fvk_interpolation_weights: upwind requires a faceFlux");
+    const int nF = m->nInternalFaces + m->nBoundaryFaces;
+    const int grid = (nF + 255) / 256;
+    if (grid == 0) return FVK_OK;
+    k_weights<<<grid, 256, 0, fvk_cu(s)>>>(scheme, m->nInternalFaces, nF, m->weights, faceFlux, wFace, wB);
+    FVK_LAUNCH_CHECK();
+    return FVK_OK;
+}
+
+template <class VT>
+static int sngrad_impl(const fvk_mesh* m, const double* phi, const double* phiB, double* outFace, fvk_stream s)
+{
+    if (!m || !phi || !outFace || (m->nBoundaryFaces && !phiB)) return fvk_fail(FVK_EINVAL, "fvk_face_normal_grad: null argument");
+    const int nF = m->nInternalFaces + m->nBoundaryFaces;
+    const int grid = (nF + 255) / 256;
+    if (grid == 0) return FVK_OK;
+    k_sngrad<VT><<<grid, 256, 0, fvk_cu(s)>>>(m->nInternalFaces, nF, m->owner, m->neighbour, m->nonOrthDeltaCoeffs,
+                                              phi, phiB, outFace);
+    FVK_LAUNCH_CHECK();
+    return FVK_OK;
+}
+extern "C" int fvk_face_normal_grad_s(const fvk_mesh* m, const double* phi, const double* phiB, double* outFace, fvk_stream s)
+{
+    return sngrad_impl<S1>(m, phi, phiB, outFace, s);
+}
+extern "C" int fvk_face_normal_grad_v(const fvk_mesh* m, const double* phi, const double* phiB, double* outFace, fvk_stream s)
+{
+    return sngrad_impl<S3>(m, phi, phiB, outFace, s);
+}
+
+static int conum_grid(const fvk_mesh* m)
+{
+    const int want = (m->nCells + 255) / 256;
+    const int cap = fvk_sm_count() * 8;
+    return want < cap ? (want > 0 ? want : 1) : cap;
+}
+extern "C" size_t fvk_conum_scratch_bytes(const fvk_mesh* m)
+{
+    if (!m) return 0;
+    return sizeof(double) * 3 * size_t(148 * 8 > conum_grid(m) ? 148 * 8 : conum_grid(m));
+}
+extern "C" int fvk_conum(const fvk_mesh* m, const double* faceFlux, double dt, double* result_d, void* scratch_d, fvk_stream s)
+{
+    if (!m || !faceFlux || !result_d || !scratch_d) return fvk_fail(FVK_EINVAL, "fvk_conum: null argument");
+    const int grid = conum_grid(m);
+    double* partial = static_cast<double*>(scratch_d);
+    k_conum_stage1<<<grid, 256, 0, fvk_cu(s)>>>(CoNumOp {faceFlux}, m->nCells, m->stencilSeg, m->gatherEnt, m->V, partial);
+    FVK_LAUNCH_CHECK();
+    k_conum_stage2<<<1, 256, 0, fvk_cu(s)>>>(grid, partial, dt, result_d);
+    FVK_LAUNCH_CHECK();
+    return FVK_OK;
+}
+
+extern "C" int fvk_correct_boundary_conditions(const fvk_mesh* m, int ncomp, const int32_t* kind_h, const double* value_h,
+                                               const double* internal, double* bValue, double* bRefValue,
+                                               double* bValueFraction, double* bRefGrad, fvk_stream s)
+{
+    if (!m || !kind_h || !value_h || !internal || !bValue || !bRefValue || !bValueFraction || !bRefGrad)
+        return fvk_fail(FVK_EINVAL, "fvk_correct_boundary_conditions: null argument");
+    if (ncomp != 1 && ncomp != 3) return fvk_fail(FVK_EINVAL, "fvk_correct_boundary_conditions: ncomp must be 1 or 3");
+    const int nB = m->nBoundaryFaces;
+    if (nB == 0) return FVK_OK;
+    BcPlan plan;
+    plan.nPatches = m->nPatches;
+    for (int p = 0; p <= m->nPatches; ++p) plan.offsets[p] = m->patchOffsets[p];
+    for (int p = 0; p < m->nPatches; ++p)
+    {
+        plan.kind[p] = kind_h[p];
+        if (kind_h[p] < FVK_BC_CALCULATED || kind_h[p] > FVK_BC_EMPTY)
+            return fvk_fail(FVK_EINVAL, "fvk_correct_boundary_conditions: unknown kind %d on patch %d", kind_h[p], p);
+        if (kind_h[p] == FVK_BC_FIXED_GRADIENT && !m->bDeltaCoeffs)
+            return fvk_fail(FVK_EINVAL, "fvk_correct_boundary_conditions: mesh has no boundary deltaCoeffs");
+        for (int k = 0; k < ncomp; ++k) plan.value[ncomp * p + k] = value_h[ncomp * p + k];
+    }
+    const int grid = (nB + 255) / 256;
+    if (ncomp == 1)
+        k_correct_bcs<S1, 1><<<grid, 256, 0, fvk_cu(s)>>>(plan, nB, m->faceCells, m->bDeltaCoeffs, internal, bValue, bRefValue, bValueFraction, bRefGrad);
+    else
+        k_correct_bcs<S3, 3><<<grid, 256, 0, fvk_cu(s)>>>(plan, nB, m->faceCells, m->bDeltaCoeffs, internal, bValue, bRefValue, bValueFraction, bRefGrad);
+    FVK_LAUNCH_CHECK();
+    return FVK_OK;
+}

@@ -1,0 +1,465 @@
+// Mesh handle: upload, geometry scheme (device kernels), cell->face stencil, sparsity pattern.
+//
+// Reference behaviour restated here (not copied): NeoN::UnstructuredMesh / BoundaryMesh layout
+// (src/NeoN/include/NeoN/mesh/unstructured/*.hpp), BasicGeometryScheme
+// (src/NeoN/src/finiteVolume/cellCentred/stencil/basicGeometryScheme.cpp:15-136),
+// CellToFaceStencil (stencil/cellToFaceStencil.cpp:14-96), SparsityPattern
+// (src/NeoN/src/linearAlgebra/sparsityPattern.cpp:21-143; like the reference the pattern is
+// assembled once per mesh on the host and uploaded).
+#include "fvk_device.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+// ------------------------------------------------------------------------------------------------
+// errors, device management
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+static int g_variant = 0;
+
+int fvk_fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+extern "C" int fvk_version(void) { return FVK_VERSION; }
+extern "C" const char* fvk_last_error(void) { return g_err; }
+extern "C" int fvk_set_variant(int v)
+{
+    g_variant = v;
+    return FVK_OK;
+}
+int fvk_variant() { return g_variant; }
+
+int fvk_sm_count()
+{
+    static int sms[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (sms[dev] == 0)
+    {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+        sms[dev] = n;
+    }
+    return sms[dev];
+}
+
+extern "C" int fvk_device_count(int* n)
+{
+    if (!n) return fvk_fail(FVK_EINVAL, "fvk_device_count: null");
+    *n = 0;
+    cudaError_t e = cudaGetDeviceCount(n);
+    if (e != cudaSuccess)
+    {
+        *n = 0;
+        return fvk_fail(FVK_ENODEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    return FVK_OK;
+}
+extern "C" int fvk_set_device(int device)
+{
+    FVK_CUDA(cudaSetDevice(device));
+    return FVK_OK;
+}
+extern "C" int fvk_malloc(void** dptr, size_t bytes)
+{
+    if (!dptr) return fvk_fail(FVK_EINVAL, "fvk_malloc: null");
+    *dptr = nullptr;
+    if (bytes == 0) return FVK_OK;
+    FVK_CUDA(cudaMalloc(dptr, bytes));
+    return FVK_OK;
+}
+extern "C" int fvk_free(void* dptr)
+{
+    if (dptr) FVK_CUDA(cudaFree(dptr));
+    return FVK_OK;
+}
+extern "C" int fvk_malloc_host(void** hptr, size_t bytes)
+{
+    if (!hptr) return fvk_fail(FVK_EINVAL, "fvk_malloc_host: null");
+    *hptr = nullptr;
+    if (bytes == 0) return FVK_OK;
+    FVK_CUDA(cudaMallocHost(hptr, bytes));
+    return FVK_OK;
+}
+extern "C" int fvk_free_host(void* hptr)
+{
+    if (hptr) FVK_CUDA(cudaFreeHost(hptr));
+    return FVK_OK;
+}
+extern "C" int fvk_memcpy_h2d(void* dst, const void* src, size_t bytes, fvk_stream s)
+{
+    if (bytes) FVK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, fvk_cu(s)));
+    return FVK_OK;
+}
+extern "C" int fvk_memcpy_d2h(void* dst, const void* src, size_t bytes, fvk_stream s)
+{
+    if (bytes) FVK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, fvk_cu(s)));
+    return FVK_OK;
+}
+extern "C" int fvk_memcpy_d2d(void* dst, const void* src, size_t bytes, fvk_stream s)
+{
+    if (bytes) FVK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, fvk_cu(s)));
+    return FVK_OK;
+}
+extern "C" int fvk_memset(void* dst, int byte, size_t bytes, fvk_stream s)
+{
+    if (bytes) FVK_CUDA(cudaMemsetAsync(dst, byte, bytes, fvk_cu(s)));
+    return FVK_OK;
+}
+extern "C" int fvk_stream_create(fvk_stream* s)
+{
+    if (!s) return fvk_fail(FVK_EINVAL, "fvk_stream_create: null");
+    cudaStream_t st;
+    FVK_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    *s = st;
+    return FVK_OK;
+}
+extern "C" int fvk_stream_destroy(fvk_stream s)
+{
+    if (s) FVK_CUDA(cudaStreamDestroy(fvk_cu(s)));
+    return FVK_OK;
+}
+extern "C" int fvk_stream_sync(fvk_stream s)
+{
+    FVK_CUDA(cudaStreamSynchronize(fvk_cu(s)));
+    return FVK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// geometry scheme kernels (K31-K34)
+// ------------------------------------------------------------------------------------------------
+namespace
+{
+constexpr double ROOTVSMALL = 1e-18; // src/NeoN/include/NeoN/core/primitives/scalar.hpp
+
+__global__ void __launch_bounds__(256)
+k_geometry_scheme(int nI, int nF, const int* __restrict__ owner, const int* __restrict__ neighbour,
+                  const double* __restrict__ C, const double* __restrict__ Cf,
+                  const double* __restrict__ Sf, const double* __restrict__ magSf,
+                  double* __restrict__ w, double* __restrict__ dc, double* __restrict__ nodc)
+{
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nF; f += gridDim.x * blockDim.x)
+    {
+        const Vec3d sf = ld3(Sf, f), cf = ld3(Cf, f);
+        const Vec3d cp = ld3(C, owner[f]);
+        Vec3d d; // cell-to-cell (internal) or cell-to-face (boundary) distance
+        if (f < nI)
+        {
+            const Vec3d cn = ld3(C, neighbour[f]);
+            // basicGeometryScheme.cpp:27-43
+            const double sfdOwn = fabs(sf.x * (cf.x - cp.x) + sf.y * (cf.y - cp.y) + sf.z * (cf.z - cp.z));
+            const double sfdNei = fabs(sf.x * (cn.x - cf.x) + sf.y * (cn.y - cf.y) + sf.z * (cn.z - cf.z));
+            w[f] = (fabs(sfdOwn + sfdNei) > ROOTVSMALL) ? sfdNei / (sfdOwn + sfdNei) : 0.5;
+            d = Vec3d {cn.x - cp.x, cn.y - cp.y, cn.z - cp.z};
+        }
+        else
+        {
+            w[f] = 1.0; // :45-53
+            d = Vec3d {cf.x - cp.x, cf.y - cp.y, cf.z - cp.z};
+        }
+        const double magD = sqrt(d.x * d.x + d.y * d.y + d.z * d.z);
+        dc[f] = 1.0 / magD; // :68-88
+        // :108-135  faceNormal = (1/|Sf|) * Sf ; orthoDist = faceNormal & d
+        const double inv = 1 / magSf[f];
+        const double ortho = (inv * sf.x) * d.x + (inv * sf.y) * d.y + (inv * sf.z) * d.z;
+        nodc[f] = 1.0 / fmax(ortho, 0.05 * magD);
+    }
+}
+
+template <class T>
+int upload(T** dst, const T* src, size_t n)
+{
+    *dst = nullptr;
+    if (n == 0) return FVK_OK;
+    FVK_CUDA(cudaMalloc(reinterpret_cast<void**>(dst), n * sizeof(T)));
+    FVK_CUDA(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    return FVK_OK;
+}
+#define UP(field, src, n)                                                                          \
+    do                                                                                             \
+    {                                                                                              \
+        int rc_ = upload(&m->field, src, size_t(n));                                               \
+        if (rc_) { fvk_mesh_destroy(m); return rc_; }                                              \
+    } while (0)
+} // namespace
+
+extern "C" int fvk_mesh_destroy(fvk_mesh* m)
+{
+    if (!m) return FVK_OK;
+    void* ptrs[] = {m->V, m->C, m->Sf, m->Cf, m->magSf, m->owner, m->neighbour, m->faceCells, m->bCf,
+                    m->bCn, m->bSf, m->bMagSf, m->bNf, m->bDelta, m->bWeights, m->bDeltaCoeffs,
+                    m->weights, m->deltaCoeffs, m->nonOrthDeltaCoeffs, m->stencilSeg, m->stencilVal,
+                    m->gatherEnt, m->rowOffs, m->colIdxs, m->ownerOffset, m->neighbourOffset,
+                    m->diagOffset, m->ownStart, m->lowSeg, m->lowFace, m->lowOwner, m->bndCell,
+                    m->bndSeg, m->bndFace, m->hasBnd};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    delete m;
+    return FVK_OK;
+}
+
+extern "C" int fvk_mesh_create(const fvk_mesh_desc* d, fvk_mesh** out)
+{
+    if (!d || !out) return fvk_fail(FVK_EINVAL, "fvk_mesh_create: null argument");
+    *out = nullptr;
+    const int32_t nC = d->nCells, nI = d->nInternalFaces, nB = d->nBoundaryFaces;
+    if (nC <= 0 || nI < 0 || nB < 0 || d->nPatches < 0 || d->nPatches > FVK_MAX_PATCHES)
+        return fvk_fail(FVK_EINVAL, "fvk_mesh_create: bad sizes (nCells=%d nI=%d nB=%d nPatches=%d)",
+                        nC, nI, nB, d->nPatches);
+    if (!d->cellVolumes || !d->cellCentres || !d->faceAreas || !d->faceCentres || !d->magFaceAreas
+        || !d->faceOwner || (nI && !d->faceNeighbour) || (nB && (!d->faceCells || !d->patchOffsets)))
+        return fvk_fail(FVK_EINVAL, "fvk_mesh_create: missing array");
+    const int64_t nF = int64_t(nI) + nB;
+    if (nF >= (int64_t(1) << 30)) return fvk_fail(FVK_EUNSUPPORTED, "fvk_mesh_create: > 2^30 faces");
+    {
+        int n = 0;
+        int rc = fvk_device_count(&n);
+        if (rc || n == 0) return fvk_fail(FVK_ENODEVICE, "fvk_mesh_create: no CUDA device (no CPU fallback)");
+    }
+    for (int32_t f = 0; f < nI; ++f)
+    {
+        const int32_t o = d->faceOwner[f], n = d->faceNeighbour[f];
+        if (o < 0 || o >= nC || n < 0 || n >= nC || o == n)
+            return fvk_fail(FVK_EINVAL, "fvk_mesh_create: face %d has bad owner/neighbour", f);
+    }
+    for (int32_t b = 0; b < nB; ++b)
+        if (d->faceCells[b] < 0 || d->faceCells[b] >= nC)
+            return fvk_fail(FVK_EINVAL, "fvk_mesh_create: boundary face %d has bad faceCell", b);
+
+    fvk_mesh* m = new fvk_mesh;
+    m->nCells = nC; m->nInternalFaces = nI; m->nBoundaryFaces = nB; m->nPatches = d->nPatches;
+    m->nnz = int64_t(nC) + 2 * int64_t(nI);
+    cudaGetDevice(&m->device);
+    for (int p = 0; p <= d->nPatches; ++p) m->patchOffsets[p] = nB ? d->patchOffsets[p] : 0;
+
+    UP(V, d->cellVolumes, nC);
+    UP(C, d->cellCentres, 3 * size_t(nC));
+    UP(Sf, d->faceAreas, 3 * size_t(nF));
+    UP(Cf, d->faceCentres, 3 * size_t(nF));
+    UP(magSf, d->magFaceAreas, nF);
+    {
+        // faceOwner over all nF faces: boundary part = faceCells
+        std::vector<int32_t> own(static_cast<size_t>(nF));
+        std::memcpy(own.data(), d->faceOwner, sizeof(int32_t) * size_t(nI));
+        for (int32_t b = 0; b < nB; ++b) own[size_t(nI) + b] = d->faceCells[b];
+        UP(owner, own.data(), nF);
+    }
+    UP(neighbour, d->faceNeighbour, nI);
+    UP(faceCells, d->faceCells, nB);
+    if (d->bCf) UP(bCf, d->bCf, 3 * size_t(nB));
+    if (d->bCn) UP(bCn, d->bCn, 3 * size_t(nB));
+    if (d->bSf) UP(bSf, d->bSf, 3 * size_t(nB));
+    if (d->bMagSf) UP(bMagSf, d->bMagSf, nB);
+    if (d->bNf) UP(bNf, d->bNf, 3 * size_t(nB));
+    if (d->bDelta) UP(bDelta, d->bDelta, 3 * size_t(nB));
+    if (d->bWeights) UP(bWeights, d->bWeights, nB);
+    if (d->bDeltaCoeffs) UP(bDeltaCoeffs, d->bDeltaCoeffs, nB);
+
+    // ---- cell->face stencil + gather plan: visiting faces in ascending id appends ascending ids
+    const int32_t* own = d->faceOwner;
+    const int32_t* nei = d->faceNeighbour;
+    {
+        std::vector<int32_t> seg(size_t(nC) + 1, 0);
+        for (int32_t f = 0; f < nI; ++f) { ++seg[size_t(own[f]) + 1]; ++seg[size_t(nei[f]) + 1]; }
+        for (int32_t b = 0; b < nB; ++b) ++seg[size_t(d->faceCells[b]) + 1];
+        for (int32_t c = 0; c < nC; ++c) seg[size_t(c) + 1] += seg[c];
+        const size_t nEnt = size_t(seg[nC]);
+        std::vector<int32_t> val(nEnt), ent(nEnt), pos(seg.begin(), seg.end() - 1);
+        for (int32_t f = 0; f < nI; ++f)
+        {
+            int32_t k = pos[own[f]]++;
+            val[k] = f; ent[k] = f << 1;
+            k = pos[nei[f]]++;
+            val[k] = f; ent[k] = (f << 1) | 1;
+        }
+        for (int32_t b = 0; b < nB; ++b)
+        {
+            const int32_t k = pos[d->faceCells[b]]++;
+            val[k] = nI + b; ent[k] = (nI + b) << 1;
+        }
+        UP(stencilSeg, seg.data(), seg.size());
+        UP(stencilVal, val.data(), nEnt);
+        UP(gatherEnt, ent.data(), nEnt);
+    }
+    // ---- sparsity pattern: row = [lower (face order) | diag | upper (face order)]
+    {
+        std::vector<int32_t> rowOffs(size_t(nC) + 1, 0), cnt(nC, 0);
+        for (int32_t c = 0; c < nC; ++c) rowOffs[size_t(c) + 1] = 1;
+        for (int32_t f = 0; f < nI; ++f) { ++rowOffs[size_t(own[f]) + 1]; ++rowOffs[size_t(nei[f]) + 1]; }
+        for (int32_t c = 0; c < nC; ++c)
+        {
+            if (rowOffs[size_t(c) + 1] > 255)
+            {
+                fvk_mesh_destroy(m);
+                return fvk_fail(FVK_EUNSUPPORTED, "fvk_mesh_create: cell %d has > 255 row entries (uint8 offsets)", c);
+            }
+            rowOffs[size_t(c) + 1] += rowOffs[c];
+        }
+        std::vector<int32_t> col(size_t(m->nnz));
+        std::vector<uint8_t> ownOff(nI), neiOff(nI), diagOff(nC);
+        for (int32_t f = 0; f < nI; ++f)
+        {
+            const int32_t r = nei[f];
+            const int32_t k = cnt[r]++;
+            neiOff[f] = uint8_t(k);
+            col[size_t(rowOffs[r]) + k] = own[f];
+        }
+        for (int32_t c = 0; c < nC; ++c)
+        {
+            const int32_t k = cnt[c]++;
+            diagOff[c] = uint8_t(k);
+            col[size_t(rowOffs[c]) + k] = c;
+        }
+        for (int32_t f = 0; f < nI; ++f)
+        {
+            const int32_t r = own[f];
+            const int32_t k = cnt[r]++;
+            ownOff[f] = uint8_t(k);
+            col[size_t(rowOffs[r]) + k] = nei[f];
+        }
+        UP(rowOffs, rowOffs.data(), rowOffs.size());
+        UP(colIdxs, col.data(), col.size());
+        UP(ownerOffset, ownOff.data(), nI);
+        UP(neighbourOffset, neiOff.data(), nI);
+        UP(diagOffset, diagOff.data(), nC);
+    }
+    // ---- split plan for owner-sorted meshes (OpenFOAM upper-triangular face order)
+    {
+        bool sorted = true;
+        for (int32_t f = 1; f < nI && sorted; ++f) sorted = own[f - 1] <= own[f];
+        for (int32_t f = 0; f < nI && sorted; ++f) sorted = own[f] < nei[f];
+        m->ownerSorted = sorted;
+        std::vector<int32_t> seg(size_t(nC) + 1, 0);
+        if (sorted)
+        {
+            for (int32_t f = 0; f < nI; ++f) ++seg[size_t(own[f]) + 1];
+            for (int32_t c = 0; c < nC; ++c) seg[size_t(c) + 1] += seg[c];
+            UP(ownStart, seg.data(), seg.size());
+        }
+        std::fill(seg.begin(), seg.end(), 0);
+        for (int32_t f = 0; f < nI; ++f) ++seg[size_t(nei[f]) + 1];
+        for (int32_t c = 0; c < nC; ++c) seg[size_t(c) + 1] += seg[c];
+        std::vector<int32_t> lf(nI), lo(nI), pos(seg.begin(), seg.end() - 1);
+        for (int32_t f = 0; f < nI; ++f)
+        {
+            const int32_t k = pos[nei[f]]++;
+            lf[k] = f; lo[k] = own[f];
+        }
+        UP(lowSeg, seg.data(), seg.size());
+        UP(lowFace, lf.data(), nI);
+        UP(lowOwner, lo.data(), nI);
+        // boundary cells
+        std::vector<int32_t> bcnt(nC, 0);
+        for (int32_t b = 0; b < nB; ++b) ++bcnt[d->faceCells[b]];
+        std::vector<int32_t> bcell, bseg(1, 0);
+        std::vector<uint32_t> mask((size_t(nC) + 31) / 32, 0u);
+        for (int32_t c = 0; c < nC; ++c)
+            if (bcnt[c])
+            {
+                bcell.push_back(c);
+                bseg.push_back(bseg.back() + bcnt[c]);
+                mask[size_t(c) >> 5] |= 1u << (c & 31);
+            }
+        std::vector<int32_t> bface(nB), slot(nC, -1);
+        for (size_t i = 0; i < bcell.size(); ++i) slot[bcell[i]] = bseg[i];
+        for (int32_t b = 0; b < nB; ++b) bface[slot[d->faceCells[b]]++] = nI + b;
+        m->nBndCells = int32_t(bcell.size());
+        UP(bndCell, bcell.data(), bcell.size());
+        UP(bndSeg, bseg.data(), bseg.size());
+        UP(bndFace, bface.data(), nB);
+        UP(hasBnd, mask.data(), mask.size());
+    }
+    // ---- geometry scheme on device
+    {
+        cudaError_t e = cudaSuccess;
+        for (double** p : {&m->weights, &m->deltaCoeffs, &m->nonOrthDeltaCoeffs})
+            if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(p), sizeof(double) * size_t(nF));
+        if (e == cudaSuccess)
+        {
+            const int grid = int((nF + 255) / 256 < 148 * 16 ? (nF + 255) / 256 : 148 * 16);
+            k_geometry_scheme<<<grid > 0 ? grid : 1, 256>>>(nI, int(nF), m->owner, m->neighbour, m->C, m->Cf, m->Sf,
+                                                            m->magSf, m->weights, m->deltaCoeffs, m->nonOrthDeltaCoeffs);
+            e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        }
+        if (e != cudaSuccess)
+        {
+            fvk_mesh_destroy(m);
+            return fvk_fail(FVK_ECUDA, "fvk_mesh_create: geometry scheme: %s", cudaGetErrorString(e));
+        }
+    }
+    *out = m;
+    return FVK_OK;
+}
+
+extern "C" int fvk_mesh_size(const fvk_mesh* m, int field, int64_t* value)
+{
+    if (!m || !value) return fvk_fail(FVK_EINVAL, "fvk_mesh_size: null");
+    switch (field)
+    {
+        case FVK_N_CELLS: *value = m->nCells; break;
+        case FVK_N_INTERNAL_FACES: *value = m->nInternalFaces; break;
+        case FVK_N_BOUNDARY_FACES: *value = m->nBoundaryFaces; break;
+        case FVK_N_PATCHES: *value = m->nPatches; break;
+        case FVK_NNZ: *value = m->nnz; break;
+        default: return fvk_fail(FVK_EINVAL, "fvk_mesh_size: unknown field %d", field);
+    }
+    return FVK_OK;
+}
+
+extern "C" int fvk_mesh_array(const fvk_mesh* m, int field, const void** dptr, int64_t* count)
+{
+    if (!m || !dptr || !count) return fvk_fail(FVK_EINVAL, "fvk_mesh_array: null");
+    const int64_t nC = m->nCells, nI = m->nInternalFaces, nB = m->nBoundaryFaces, nF = nI + nB;
+    const void* p = nullptr;
+    int64_t n = 0;
+    switch (field)
+    {
+        case FVK_CELL_VOLUMES: p = m->V; n = nC; break;
+        case FVK_CELL_CENTRES: p = m->C; n = 3 * nC; break;
+        case FVK_FACE_AREAS: p = m->Sf; n = 3 * nF; break;
+        case FVK_FACE_CENTRES: p = m->Cf; n = 3 * nF; break;
+        case FVK_MAG_FACE_AREAS: p = m->magSf; n = nF; break;
+        case FVK_FACE_OWNER: p = m->owner; n = nF; break;
+        case FVK_FACE_NEIGHBOUR: p = m->neighbour; n = nI; break;
+        case FVK_FACE_CELLS: p = m->faceCells; n = nB; break;
+        case FVK_B_CF: p = m->bCf; n = 3 * nB; break;
+        case FVK_B_CN: p = m->bCn; n = 3 * nB; break;
+        case FVK_B_SF: p = m->bSf; n = 3 * nB; break;
+        case FVK_B_MAGSF: p = m->bMagSf; n = nB; break;
+        case FVK_B_NF: p = m->bNf; n = 3 * nB; break;
+        case FVK_B_DELTA: p = m->bDelta; n = 3 * nB; break;
+        case FVK_B_WEIGHTS: p = m->bWeights; n = nB; break;
+        case FVK_B_DELTACOEFFS: p = m->bDeltaCoeffs; n = nB; break;
+        case FVK_WEIGHTS: p = m->weights; n = nF; break;
+        case FVK_DELTACOEFFS: p = m->deltaCoeffs; n = nF; break;
+        case FVK_NONORTH_DELTACOEFFS: p = m->nonOrthDeltaCoeffs; n = nF; break;
+        case FVK_STENCIL_SEGMENTS: p = m->stencilSeg; n = nC + 1; break;
+        case FVK_STENCIL_VALUES: p = m->stencilVal; n = 2 * nI + nB; break;
+        case FVK_ROW_OFFS: p = m->rowOffs; n = nC + 1; break;
+        case FVK_COL_IDXS: p = m->colIdxs; n = m->nnz; break;
+        case FVK_OWNER_OFFSET: p = m->ownerOffset; n = nI; break;
+        case FVK_NEIGHBOUR_OFFSET: p = m->neighbourOffset; n = nI; break;
+        case FVK_DIAG_OFFSET: p = m->diagOffset; n = nC; break;
+        default: return fvk_fail(FVK_EINVAL, "fvk_mesh_array: unknown field %d", field);
+    }
+    *dptr = p;
+    *count = p ? n : 0;
+    return FVK_OK;
+}
+
+extern "C" int fvk_mesh_patch_offsets(const fvk_mesh* m, int32_t* offsets_h)
+{
+    if (!m || !offsets_h) return fvk_fail(FVK_EINVAL, "fvk_mesh_patch_offsets: null");
+    for (int p = 0; p <= m->nPatches; ++p) offsets_h[p] = m->patchOffsets[p];
+    return FVK_OK;
+}

@@ -1,0 +1,242 @@
+/* fvk.h -- C ABI of the B200 (sm_100a) finite-volume kernel library `libfvk.so`.
+ *
+ * This is the drop-in boundary for the data-parallel hot path of FoamAdapter/NeoN.
+ * The reference has no FFI: its "kernels" are C++ lambdas handed to NeoN::parallelFor
+ * (src/NeoN/include/NeoN/core/parallelAlgorithms.hpp:29-54) from the bodies of the fvcc operators.
+ * Every entry point below replaces the body of one such reference function (cited per function);
+ * the C++ host classes in include/NeoN (same names as the reference) call these.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all array pointers are DEVICE pointers unless the name ends in
+ *     `_h` / the comment says host; memory is caller-owned;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); no entry point
+ *     synchronises unless documented;
+ *   - return value: 0 = success, otherwise an FVK_E* code; fvk_last_error() gives the text;
+ *   - there is no CPU fallback: every compute entry point fails with FVK_ENODEVICE without a GPU;
+ *   - types follow the reference: scalar = double, label/localIdx = int32_t, Vec3 = 3 contiguous
+ *     doubles (AoS, 24 B), sparsity offsets = uint8_t
+ *     (src/NeoN/include/NeoN/core/primitives/{scalar,label,vec3}.hpp);
+ *   - all fields are in REFERENCE ORDER: cell fields [nCells], face fields [nInternalFaces +
+ *     nBoundaryFaces] (internal faces first, then boundary faces in patch order), boundary fields
+ *     [nBoundaryFaces].
+ */
+#ifndef FVK_H
+#define FVK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FVK_VERSION 100
+
+enum {
+    FVK_OK = 0,
+    FVK_EINVAL = 1,    /* bad argument */
+    FVK_ENODEVICE = 2, /* no CUDA device / driver */
+    FVK_ECUDA = 3,     /* CUDA runtime error, see fvk_last_error */
+    FVK_ENOMEM = 4,
+    FVK_EUNSUPPORTED = 5,
+    FVK_ENCCL = 6
+};
+
+typedef void* fvk_stream; /* cudaStream_t */
+typedef struct fvk_mesh fvk_mesh;
+
+int fvk_version(void);
+/* thread-local text of the last error */
+const char* fvk_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Device memory and copies. Replaces GPUExecutor::alloc/free/realloc (Kokkos::kokkos_malloc,
+ * src/NeoN/include/NeoN/core/executor/GPUExecutor.hpp:26-50) and the deep copies behind
+ * Vector::copyToHost / copyToExecutor (src/NeoN/src/core/vector/vector.cpp).
+ * ---------------------------------------------------------------------------------------------- */
+int fvk_device_count(int* n);
+int fvk_set_device(int device);
+int fvk_malloc(void** dptr, size_t bytes);
+int fvk_free(void* dptr);
+int fvk_malloc_host(void** hptr, size_t bytes); /* pinned */
+int fvk_free_host(void* hptr);
+int fvk_memcpy_h2d(void* dst, const void* src_h, size_t bytes, fvk_stream stream);
+int fvk_memcpy_d2h(void* dst_h, const void* src, size_t bytes, fvk_stream stream);
+int fvk_memcpy_d2d(void* dst, const void* src, size_t bytes, fvk_stream stream);
+int fvk_memset(void* dst, int byte, size_t bytes, fvk_stream stream);
+int fvk_stream_create(fvk_stream* stream);
+int fvk_stream_destroy(fvk_stream stream);
+int fvk_stream_sync(fvk_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Mesh description (HOST arrays). This is what readOpenFOAMMesh hands to NeoN::UnstructuredMesh
+ * and NeoN::BoundaryMesh (src/datastructures/meshAdapter.cpp:59-136;
+ * src/NeoN/include/NeoN/mesh/unstructured/{unstructuredMesh,boundaryMesh}.hpp).
+ * nFaces = nInternalFaces + nBoundaryFaces (faces of `empty` patches are dropped, as fvPatch::size()
+ * is 0 for them).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct fvk_mesh_desc {
+    int32_t nCells;
+    int32_t nInternalFaces;
+    int32_t nBoundaryFaces;
+    int32_t nPatches;
+    int32_t nPoints;              /* may be 0 */
+    const double* points;         /* [nPoints*3] or NULL */
+    const double* cellVolumes;    /* [nCells] */
+    const double* cellCentres;    /* [nCells*3] */
+    const double* faceAreas;      /* Sf [nFaces*3] */
+    const double* faceCentres;    /* Cf [nFaces*3] */
+    const double* magFaceAreas;   /* [nFaces] */
+    const int32_t* faceOwner;     /* [nFaces] (boundary part == faceCells) */
+    const int32_t* faceNeighbour; /* [nInternalFaces] */
+    /* BoundaryMesh, all [nBoundaryFaces] (x3 for vectors), patch order */
+    const int32_t* faceCells;
+    const double* bCf;
+    const double* bCn;
+    const double* bSf;
+    const double* bMagSf;
+    const double* bNf;
+    const double* bDelta;
+    const double* bWeights;
+    const double* bDeltaCoeffs;
+    const int32_t* patchOffsets; /* [nPatches+1] */
+} fvk_mesh_desc;
+
+/* ------------------------------------------------------------------------------------------------
+ * Synthetic single-block hex mesh in OpenFOAM blockMesh ordering with OpenFOAM primitiveMesh
+ * geometry -- the stand-in for `blockMesh` + readOpenFOAMMesh, which need OpenFOAM
+ * (block (nx ny nz), box lx x ly x lz, simpleGrading 1).
+ * Sides: 0 x-min, 1 x-max, 2 y-min, 3 y-max, 4 z-min, 5 z-max. Patches are given in blockMeshDict
+ * order, each as an ordered list of sides; `patchIsEmpty[p] != 0` marks an `empty` patch (its faces
+ * enter the geometry but not the NeoN mesh). Host only; arrays owned by the returned object.
+ * ---------------------------------------------------------------------------------------------- */
+int fvk_blockmesh_create(int32_t nx, int32_t ny, int32_t nz, double lx, double ly, double lz,
+                         int32_t nPatches, const int32_t* patchNSides, const int32_t* patchSides,
+                         const int32_t* patchIsEmpty, int32_t withPoints, fvk_mesh_desc** out);
+int fvk_blockmesh_destroy(fvk_mesh_desc* desc);
+/* poly faces of the generated mesh (4 point labels per face, all patches incl. empty), for parity
+ * checks against polyMesh/faces; valid only if created withPoints. */
+int fvk_blockmesh_poly(const fvk_mesh_desc* desc, int32_t* nPolyFaces, const int32_t** facePoints,
+                       const int32_t** polyOwner);
+
+/* ------------------------------------------------------------------------------------------------
+ * Device mesh handle. Uploads the description and builds, once per mesh:
+ *   - BasicGeometryScheme weights / deltaCoeffs / nonOrthDeltaCoeffs
+ *     (src/NeoN/src/finiteVolume/cellCentred/stencil/basicGeometryScheme.cpp:15-136),
+ *   - the cell->face CSR of CellToFaceStencil::computeStencil
+ *     (src/NeoN/src/finiteVolume/cellCentred/stencil/cellToFaceStencil.cpp:14-96),
+ *   - the SparsityPattern (src/NeoN/src/linearAlgebra/sparsityPattern.cpp:21-143), bit-exact.
+ * ---------------------------------------------------------------------------------------------- */
+int fvk_mesh_create(const fvk_mesh_desc* desc_h, fvk_mesh** out);
+int fvk_mesh_destroy(fvk_mesh* mesh);
+
+enum fvk_mesh_field {
+    /* sizes */
+    FVK_N_CELLS = 0, FVK_N_INTERNAL_FACES, FVK_N_BOUNDARY_FACES, FVK_N_PATCHES, FVK_NNZ,
+    /* device arrays, reference order */
+    FVK_CELL_VOLUMES = 16, FVK_CELL_CENTRES, FVK_FACE_AREAS, FVK_FACE_CENTRES, FVK_MAG_FACE_AREAS,
+    FVK_FACE_OWNER, FVK_FACE_NEIGHBOUR, FVK_FACE_CELLS,
+    FVK_B_CF, FVK_B_CN, FVK_B_SF, FVK_B_MAGSF, FVK_B_NF, FVK_B_DELTA, FVK_B_WEIGHTS,
+    FVK_B_DELTACOEFFS,
+    FVK_WEIGHTS = 48, FVK_DELTACOEFFS, FVK_NONORTH_DELTACOEFFS,  /* [nFaces] */
+    FVK_STENCIL_SEGMENTS = 64, /* int32 [nCells+1] */
+    FVK_STENCIL_VALUES,        /* int32 [2*nI+nB], sorted face ids per cell */
+    FVK_ROW_OFFS = 80,         /* int32 [nCells+1] */
+    FVK_COL_IDXS,              /* int32 [nnz] */
+    FVK_OWNER_OFFSET,          /* uint8 [nI]  -> entry (row own, col nei) */
+    FVK_NEIGHBOUR_OFFSET,      /* uint8 [nI]  -> entry (row nei, col own) */
+    FVK_DIAG_OFFSET            /* uint8 [nCells] */
+};
+/* integer properties (FVK_N_*, FVK_NNZ) */
+int fvk_mesh_size(const fvk_mesh* mesh, int field, int64_t* value);
+/* device pointer + element count of an array field */
+int fvk_mesh_array(const fvk_mesh* mesh, int field, const void** dptr, int64_t* count);
+/* host copy of patchOffsets [nPatches+1] */
+int fvk_mesh_patch_offsets(const fvk_mesh* mesh, int32_t* offsets_h);
+
+/* ------------------------------------------------------------------------------------------------
+ * Explicit operators. One fused, deterministic, cell-centric gather kernel
+ * per operator: no atomics, no face-sized temporary, per-cell summation in ascending face id = the
+ * order of the reference's SerialExecutor.
+ *
+ * coeff, coeffView : dsl::Coeff (src/NeoN/include/NeoN/dsl/coeff.hpp:35); operatorScaling[c] =
+ *                    coeffView ? coeffView[c]*coeff : coeff.
+ * mode             : FVK_SET        out[c]  = sum * s[c]           (out assumed zero on entry)
+ *                    FVK_ACC_SCALE  out[c]  = (out[c] + sum) * s[c] (computeDiv on a non-zero `res`)
+ *                    FVK_ADD        out[c] += sum * s[c]            (Operator::explicitOperation:
+ *                                   tmp=0; op(tmp); source += tmp,  operators/divOperator.hpp:133-140)
+ *                    with s[c] = operatorScaling[c] / V[c].
+ * ---------------------------------------------------------------------------------------------- */
+enum { FVK_SET = 0, FVK_ACC_SCALE = 1, FVK_ADD = 2 };
+enum { FVK_LINEAR = 0, FVK_UPWIND = 1 };
+
+/* GaussGreenDiv<scalar|Vec3>::div -> computeDivExp + computeDiv
+ * (src/NeoN/src/finiteVolume/cellCentred/operators/gaussGreenDiv.cpp:29-140) fused with the face
+ * interpolation (interpolation/linear.cpp:12-46, upwind.cpp:12-56). */
+int fvk_div_s(const fvk_mesh* mesh, int scheme, const double* faceFlux, const double* phi,
+              const double* phiBValue, double coeff, const double* coeffView, double* out, int mode,
+              fvk_stream stream);
+int fvk_div_v(const fvk_mesh* mesh, int scheme, const double* faceFlux, const double* phi,
+              const double* phiBValue, double coeff, const double* coeffView, double* out, int mode,
+              fvk_stream stream);
+/* GaussGreenGrad::grad -> computeGrad (operators/gaussGreenGrad.cpp:18-71); always linear, scale 1/V.
+ * mode FVK_SET or FVK_ACC_SCALE. out is Vec3[nCells]. */
+int fvk_grad_s(const fvk_mesh* mesh, const double* phi, const double* phiBValue, double* out,
+               int mode, fvk_stream stream);
+/* GaussGreenLaplacian::laplacian -> computeLaplacianExp (operators/gaussGreenLaplacian.cpp:11-61)
+ * fused with computeFaceNormalGrad (faceNormalGradient/uncorrected.cpp:11-52). gamma is ignored by
+ * the reference (parameter unnamed, gaussGreenLaplacian.cpp:14) and therefore not an argument. */
+int fvk_laplacian_s(const fvk_mesh* mesh, const double* phi, const double* phiBValue, double coeff,
+                    const double* coeffView, double* out, int mode, fvk_stream stream);
+int fvk_laplacian_v(const fvk_mesh* mesh, const double* phi, const double* phiBValue, double coeff,
+                    const double* coeffView, double* out, int mode, fvk_stream stream);
+/* surfaceIntegrate (operators/surfaceIntegrate.cpp:11-49): scatter of a given face flux. */
+int fvk_surface_integrate_s(const fvk_mesh* mesh, const double* flux, double coeff,
+                            const double* coeffView, double* out, int mode, fvk_stream stream);
+int fvk_surface_integrate_v(const fvk_mesh* mesh, const double* flux, double coeff,
+                            const double* coeffView, double* out, int mode, fvk_stream stream);
+
+/* SurfaceInterpolation::interpolate (interpolation/linear.cpp:12-46, upwind.cpp:12-56).
+ * faceFlux may be NULL for FVK_LINEAR. outFace is [nFaces] (x3 for _v). */
+int fvk_interpolate_s(const fvk_mesh* mesh, int scheme, const double* faceFlux, const double* phi,
+                      const double* phiBValue, double* outFace, fvk_stream stream);
+int fvk_interpolate_v(const fvk_mesh* mesh, int scheme, const double* faceFlux, const double* phi,
+                      const double* phiBValue, double* outFace, fvk_stream stream);
+/* SurfaceInterpolation::weight (linear.hpp:76-96 copy of the geometric weights; upwind.cpp:59-93).
+ * wFace [nFaces], wBoundary [nBoundaryFaces]. */
+int fvk_interpolation_weights(const fvk_mesh* mesh, int scheme, const double* faceFlux,
+                              double* wFace, double* wBoundary, fvk_stream stream);
+/* FaceNormalGradient Uncorrected::faceNormalGrad (faceNormalGradient/uncorrected.cpp:11-52). */
+int fvk_face_normal_grad_s(const fvk_mesh* mesh, const double* phi, const double* phiBValue,
+                           double* outFace, fvk_stream stream);
+int fvk_face_normal_grad_v(const fvk_mesh* mesh, const double* phi, const double* phiBValue,
+                           double* outFace, fvk_stream stream);
+
+/* computeCoNum (src/NeoN/src/finiteVolume/cellCentred/auxiliary/coNum.cpp:18-96).
+ * result_d[0] = maxCoNum, result_d[1] = meanCoNum (device, 2 doubles). scratch_d: >= fvk_conum_scratch
+ * bytes. Deterministic two-stage reduction; no host sync. */
+size_t fvk_conum_scratch_bytes(const fvk_mesh* mesh);
+int fvk_conum(const fvk_mesh* mesh, const double* faceFlux, double dt, double* result_d,
+              void* scratch_d, fvk_stream stream);
+
+/* Volume boundary conditions, one launch for all patches of a field
+ * (boundary/volume/fixedValue.hpp:21-43, fixedGradient.hpp:22-54, extrapolated.hpp:22-53,
+ * calculated/empty: no-op). Per patch p: kind[p], and value[p*ncomp..] = the fixedValue /
+ * fixedGradient constant. Arrays kind_h/value_h are HOST (tiny, copied as kernel arguments;
+ * nPatches <= FVK_MAX_PATCHES). ncomp = 1 (scalar) or 3 (Vec3). */
+enum { FVK_BC_CALCULATED = 0, FVK_BC_FIXED_VALUE = 1, FVK_BC_FIXED_GRADIENT = 2,
+       FVK_BC_EXTRAPOLATED = 3, FVK_BC_EMPTY = 4 };
+#define FVK_MAX_PATCHES 16
+int fvk_correct_boundary_conditions(const fvk_mesh* mesh, int ncomp, const int32_t* kind_h,
+                                    const double* value_h, const double* internal, double* bValue,
+                                    double* bRefValue, double* bValueFraction, double* bRefGrad,
+                                    fvk_stream stream);
+
+/* experiment switch: selects the kernel variant used by the gather operators
+ * (0 = default). Used by the roofline harness only. */
+int fvk_set_variant(int variant);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FVK_H */
