@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""Benchmark of the finite-volume hot path on B200 (contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--mesh 128]
+
+Workload (BASELINE.json configs[1], reference benchmarks/bench_explicitOperators.cpp): one step =
+Gauss-Green div (linear) + grad + laplacian (uncorrected), fp64, on a synthetic N^3 block-hex mesh
+(N=128 by default) with T ~ U(1,2) (seed 42), phi[f] = f on internal faces / 0 on the boundary,
+fixedValue top/bottom + zeroGradient sides. metric = fp64 face-ops/s = 3*(nI+nB) per step.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "fp64_face_ops_per_s"
+UNIT = "face-ops/s"
+
+
+def mesh_counts(n):
+    nC = n ** 3
+    nI = 3 * n * n * (n - 1)
+    nB = 6 * n * n
+    return nC, nI, nB
+
+
+def algorithmic_bytes(n):
+    """BASELINE.md §4 / SURVEY.md §8(d): per internal face, per cell, per boundary face."""
+    nC, nI, nB = mesh_counts(n)
+    return {
+        "div": 24 * nI + 24 * nC + 28 * nB,
+        "grad": 40 * nI + 40 * nC + 44 * nB,
+        "laplacian": 24 * nI + 24 * nC + 28 * nB,
+    }
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) >= 6 and r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU arms (the oracle): cpu_baseline leg of the native arm, and --impl reference
+# ----------------------------------------------------------------------------------------------------
+def host_workload(n):
+    from foamadapter_b200.mesh import MeshDesc
+    d = MeshDesc.block(n, n, n, 0.1, 0.1, 0.01)
+    nC, nI, nB = d.nCells, d.nInternalFaces, d.nBoundaryFaces
+    rng = np.random.Generator(np.random.MT19937(42))
+    T = rng.uniform(1.0, 2.0, nC)
+    flux = np.concatenate([np.arange(nI, dtype=np.float64), np.zeros(nB)])
+    return d, T, flux
+
+
+def cpu_step_time(n, d, T, flux, par, reps):
+    """Seconds per step (div+grad+laplacian) of the CPU restatement; best of `reps`."""
+    from oracle.cpu import Mesh as OMesh
+    om = OMesh.from_desc(d)
+    off = om.patchOffsets
+    bd = om.correct_bcs([1, 1, 2], [10.5, 1.5, 0.0], T)
+    phib = bd["value"]
+    best = float("inf")
+    for _ in range(reps):
+        r1, r2, r3 = np.zeros(om.nC), np.zeros((om.nC, 3)), np.zeros(om.nC)
+        t0 = time.perf_counter()
+        om.div(flux, T, phib, 0, par=par, res=r1)
+        om.grad(T, phib, par=par, res=r2)
+        om.laplacian(T, phib, par=par, res=r3)
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import cpu as ocpu
+    n = args.mesh
+    d, T, flux = host_workload(n)
+    nC, nI, nB = d.nCells, d.nInternalFaces, d.nBoundaryFaces
+    cores = ocpu.max_threads()
+    from oracle.cpu import Mesh as OMesh
+    om = OMesh.from_desc(d)
+    phib = om.correct_bcs([1, 1, 2], [10.5, 1.5, 0.0], T)["value"]
+    r1, r2, r3 = np.zeros(nC), np.zeros((nC, 3)), np.zeros(nC)
+
+    def step():
+        r1[:] = 0; r2[:] = 0; r3[:] = 0
+        om.div(flux, T, phib, 0, par=1, res=r1)
+        om.grad(T, phib, par=1, res=r2)
+        om.laplacian(T, phib, par=1, res=r3)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    value = 3.0 * (nI + nB) / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"explicit div+grad+laplacian, {n}^3 block-hex mesh (BASELINE configs[1])"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"full {n}^3 step, OpenMP+atomics restatement of the NeoN CPU executor (oracle/fvo.cpp); "
+                                   "the reference itself needs OpenFOAM/Kokkos/Ginkgo and cannot be built here"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+# native arm
+# ----------------------------------------------------------------------------------------------------
+def run_native(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from foamadapter_b200 import fvcc, ops
+    from foamadapter_b200._capi import lib, ptr
+    from foamadapter_b200.mesh import UnstructuredMesh
+
+    n = args.mesh
+    d, T_h, flux_h = host_workload(n)
+    nC, nI, nB = d.nCells, d.nInternalFaces, d.nBoundaryFaces
+    nF = nI + nB
+    mesh = UnstructuredMesh(d)
+    dev = torch.device("cuda", local_rank)
+    bcs = [("fixedValue", 10.5), ("fixedValue", 1.5), ("zeroGradient", 0.0)]
+    # distinct phi per operator so no operator finds its input in L2 from the previous one
+    fields = []
+    for i in range(3):
+        f = fvcc.VolumeField(mesh, f"T{i}", 1, bcs, device=dev)
+        f.internal.copy_(torch.from_numpy(T_h + 0.0 * i))
+        f.correctBoundaryConditions()
+        fields.append(f)
+    flux = torch.from_numpy(flux_h).to(dev)
+    out_div = torch.zeros(nC, dtype=torch.float64, device=dev)
+    out_grad = torch.zeros((nC, 3), dtype=torch.float64, device=dev)
+    out_lap = torch.zeros(nC, dtype=torch.float64, device=dev)
+    L = lib()
+    stream = torch.cuda.current_stream()
+    s = C.c_void_p(stream.cuda_stream)
+    one = C.c_double(1.0)
+    a_div = (mesh.handle, C.c_int(0), ptr(flux), ptr(fields[0].internal), ptr(fields[0].boundary.value), one, None,
+             ptr(out_div), C.c_int(0), s)
+    a_grad = (mesh.handle, ptr(fields[1].internal), ptr(fields[1].boundary.value), ptr(out_grad), C.c_int(0), s)
+    a_lap = (mesh.handle, ptr(fields[2].internal), ptr(fields[2].boundary.value), one, None, ptr(out_lap), C.c_int(0), s)
+
+    def step(ev=None):
+        if ev is not None:
+            ev[0].record(stream)
+        rc = L.fvk_div_s(*a_div)
+        if ev is not None:
+            ev[1].record(stream)
+        rc |= L.fvk_grad_s(*a_grad)
+        if ev is not None:
+            ev[2].record(stream)
+        rc |= L.fvk_laplacian_s(*a_lap)
+        if ev is not None:
+            ev[3].record(stream)
+        if rc:
+            raise RuntimeError(L.fvk_last_error().decode())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e_start.record(stream)
+    for k in range(args.steps):
+        step(evs[k])
+    e_end.record(stream)
+    barrier()
+    total_ms = e_start.elapsed_time(e_end)
+    clocks = sampler.summary() if rank == 0 else None
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = 3.0 * nF * world / (ms_per_step * 1e-3)
+    kern_ms = {name: float(np.mean([evs[k][i].elapsed_time(evs[k][i + 1]) for k in range(args.steps)]))
+               for i, name in enumerate(("div", "grad", "laplacian"))}
+
+    # ---- e2e: host (pinned) buffers in, results out, every step ---------------------------------
+    pin = lambda a: torch.from_numpy(a).pin_memory()
+    T_pin, flux_pin = pin(T_h), pin(flux_h)
+    r_div, r_grad, r_lap = (torch.empty_like(x, device="cpu").pin_memory() for x in (out_div, out_grad, out_lap))
+    h2d = T_pin.numel() * 8 + flux_pin.numel() * 8
+    d2h = (r_div.numel() + r_grad.numel() + r_lap.numel()) * 8
+    f0 = fields[0]
+
+    def e2e_step():
+        f0.internal.copy_(T_pin, non_blocking=True)
+        flux.copy_(flux_pin, non_blocking=True)
+        f0.correctBoundaryConditions()
+        rc = L.fvk_div_s(*a_div)
+        rc |= L.fvk_grad_s(mesh.handle, ptr(f0.internal), ptr(f0.boundary.value), ptr(out_grad), C.c_int(0), s)
+        rc |= L.fvk_laplacian_s(mesh.handle, ptr(f0.internal), ptr(f0.boundary.value), one, None, ptr(out_lap), C.c_int(0), s)
+        if rc:
+            raise RuntimeError(L.fvk_last_error().decode())
+        r_div.copy_(out_div, non_blocking=True)
+        r_grad.copy_(out_grad, non_blocking=True)
+        r_lap.copy_(out_lap, non_blocking=True)
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e_start.record(stream)
+    for _ in range(e2e_steps):
+        e2e_step()
+    e_end.record(stream)
+    barrier()
+    t = torch.tensor([e_start.elapsed_time(e_end)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item()) / e2e_steps
+    e2e_value = 3.0 * nF * world / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        peak, peak_kind = peaks()
+        ab = algorithmic_bytes(n)
+        kernels = {k: {"ms": kern_ms[k], "algorithmic_bytes": ab[k], "achieved_gbs": ab[k] / (kern_ms[k] * 1e-3) / 1e9,
+                       "frac": ab[k] / (kern_ms[k] * 1e-3) / 1e9 / peak} for k in kern_ms}
+        dom = max(kern_ms, key=kern_ms.get)
+        traffic = None
+        tp = ROOT / "profiles" / "traffic.json"
+        if tp.exists():
+            try:
+                traffic = json.loads(tp.read_text()).get(f"{dom}_{n}")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"explicit div+grad+laplacian, {n}^3 block-hex mesh (BASELINE configs[1])",
+                       "cells": nC, "internal_faces": nI, "boundary_faces": nB,
+                       "l2": "inputs larger than L2: each operator streams 203/338/203 MB (>126 MB L2) and reads its own phi array",
+                       "parallelism": "1 GPU" if world == 1 else f"{world} independent sub-domain replicas (halo exchange not in this bench yet)"},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                         "frac": kernels[dom]["frac"], "traffic": traffic, "peak_kind": peak_kind},
+            "kernels": kernels,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
+            "gpu_launches": 3 * args.steps,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            from oracle import cpu as ocpu
+            cores = ocpu.max_threads()
+            t_par = cpu_step_time(n, d, T_h, flux_h, par=1, reps=3)
+            t_ser = cpu_step_time(n, d, T_h, flux_h, par=0, reps=1)
+            line["cpu_baseline"] = {
+                "value": 3.0 * nF / t_par, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"full {n}^3 step (div+grad+laplacian), best of 3, OpenMP+atomics restatement of the NeoN CPU "
+                          f"executor on {cores} threads; Serial executor restatement on 1 core: {3.0 * nF / t_ser:.4g} {UNIT}",
+                "serial_value": 3.0 * nF / t_ser,
+            }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--mesh", type=int, default=128)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_native(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -183,42 +183,105 @@ k_gather_stencil(Op op, Scaling sc, int nC, int nI, const int* __restrict__ seg,
     finish<VT>(out, c, acc, sc.at(c), mode);
 }
 
-// ---- variant 1: split plan for owner-sorted meshes -------------------------------------------------
-// lower faces (cell is neighbour; ids below every owned face) ascending, then the contiguous owned
-// faces, then boundary faces -- together again ascending face id.
+// ---- split plan for owner-sorted meshes (OpenFOAM upper-triangular order) --------------------------
+// lower faces (cell is the neighbour; their ids are below every owned face) ascending, then the
+// contiguous owned faces, then boundary faces -- together ascending face id.
+struct SplitPlan
+{
+    const int* __restrict__ lowSeg;
+    const int* __restrict__ lowFace;
+    const int* __restrict__ lowOwner;
+    const int* __restrict__ ownStart;
+    const int* __restrict__ neighbour;
+    const unsigned* __restrict__ hasBnd;
+    int nBndCells;
+    const int* __restrict__ bndCell;
+    const int* __restrict__ bndSeg;
+    const int* __restrict__ bndFace;
+};
+
+template <class Op>
+__device__ __forceinline__ typename Op::T boundary_sum(const Op& op, const SplitPlan& pl, int c, int nI, typename Op::T acc)
+{
+    using VT = typename Op::V;
+    if ((pl.hasBnd[c >> 5] >> (c & 31)) & 1u)
+    {
+        int lo = 0, hi = pl.nBndCells - 1;
+        while (lo < hi)
+        {
+            const int mid = (lo + hi) >> 1;
+            if (pl.bndCell[mid] < c) lo = mid + 1; else hi = mid;
+        }
+        const int b1 = pl.bndSeg[lo + 1];
+        for (int e = pl.bndSeg[lo]; e < b1; ++e)
+        {
+            const int f = pl.bndFace[e];
+            acc = VT::add(acc, op.boundary(f, f - nI, c));
+        }
+    }
+    return acc;
+}
+
+// variant 2: plain loops (one face in flight per thread)
 template <class Op>
 __global__ void __launch_bounds__(256)
-k_gather_split(Op op, Scaling sc, int nC, int nI, const int* __restrict__ lowSeg,
-               const int* __restrict__ lowFace, const int* __restrict__ lowOwner,
-               const int* __restrict__ ownStart, const int* __restrict__ neighbour,
-               const unsigned* __restrict__ hasBnd, int nBndCells, const int* __restrict__ bndCell,
-               const int* __restrict__ bndSeg, const int* __restrict__ bndFace,
-               double* __restrict__ out, int mode)
+k_gather_split_simple(Op op, Scaling sc, int nC, int nI, SplitPlan pl, double* __restrict__ out, int mode)
 {
     using VT = typename Op::V;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nC) return;
     typename VT::T acc = (mode == FVK_ACC_SCALE) ? VT::ld(out, c) : VT::zero();
-    const int l0 = lowSeg[c], l1 = lowSeg[c + 1];
-    const int f0 = ownStart[c], f1 = ownStart[c + 1];
-    for (int e = l0; e < l1; ++e) acc = VT::sub(acc, op.internal(lowFace[e], lowOwner[e], c));
-    for (int f = f0; f < f1; ++f) acc = VT::add(acc, op.internal(f, c, neighbour[f]));
-    if ((hasBnd[c >> 5] >> (c & 31)) & 1u)
-    {
-        int lo = 0, hi = nBndCells - 1;
-        while (lo < hi)
-        {
-            const int mid = (lo + hi) >> 1;
-            if (bndCell[mid] < c) lo = mid + 1; else hi = mid;
-        }
-        const int b1 = bndSeg[lo + 1];
-        for (int e = bndSeg[lo]; e < b1; ++e)
-        {
-            const int f = bndFace[e];
-            acc = VT::add(acc, op.boundary(f, f - nI, c));
-        }
-    }
+    const int l0 = pl.lowSeg[c], l1 = pl.lowSeg[c + 1];
+    const int f0 = pl.ownStart[c], f1 = pl.ownStart[c + 1];
+    for (int e = l0; e < l1; ++e) acc = VT::sub(acc, op.internal(pl.lowFace[e], pl.lowOwner[e], c));
+    for (int f = f0; f < f1; ++f) acc = VT::add(acc, op.internal(f, c, pl.neighbour[f]));
+    acc = boundary_sum(op, pl, c, nI, acc);
     finish<VT>(out, c, acc, sc.at(c), mode);
+}
+
+// variant 0 (default): the first CH lower and CH owned faces are fetched as one batch of independent,
+// predicated loads (memory-level parallelism: all index loads, then all data loads in flight
+// together), then folded in ascending face order; longer lists fall back to chunked loops.
+template <class Op, int CH>
+__global__ void __launch_bounds__(256)
+k_gather_split(Op op, Scaling sc, int nC, int nI, SplitPlan pl, double* __restrict__ out, int mode)
+{
+    using VT = typename Op::V;
+    using T = typename VT::T;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nC) return;
+    T acc = (mode == FVK_ACC_SCALE) ? VT::ld(out, c) : VT::zero();
+    const int l0 = pl.lowSeg[c], l1 = pl.lowSeg[c + 1];
+    const int f0 = pl.ownStart[c], f1 = pl.ownStart[c + 1];
+    const double s = sc.at(c);
+    // straight-line, branch-free batch: indices first, then data. Padding lanes read a clamped,
+    // valid (and cached) entry whose flux is computed but never summed.
+    const int last = nI - 1; // nI > 0 guaranteed by the launcher
+    T fl[CH], fo[CH];
+    int lf[CH], lo[CH], ff[CH], nn[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k)
+    {
+        const int e = min(l0 + k, last);
+        lf[k] = pl.lowFace[e];
+        lo[k] = pl.lowOwner[e];
+        ff[k] = min(f0 + k, last);
+        nn[k] = pl.neighbour[ff[k]];
+    }
+#pragma unroll
+    for (int k = 0; k < CH; ++k) fl[k] = op.internal(lf[k], lo[k], c);
+#pragma unroll
+    for (int k = 0; k < CH; ++k) fo[k] = op.internal(ff[k], c, nn[k]);
+#pragma unroll
+    for (int k = 0; k < CH; ++k)
+        if (l0 + k < l1) acc = VT::sub(acc, fl[k]);
+    for (int e = l0 + CH; e < l1; ++e) acc = VT::sub(acc, op.internal(pl.lowFace[e], pl.lowOwner[e], c));
+#pragma unroll
+    for (int k = 0; k < CH; ++k)
+        if (f0 + k < f1) acc = VT::add(acc, fo[k]);
+    for (int f = f0 + CH; f < f1; ++f) acc = VT::add(acc, op.internal(f, c, pl.neighbour[f]));
+    acc = boundary_sum(op, pl, c, nI, acc);
+    finish<VT>(out, c, acc, s, mode);
 }
 
 template <class Op>
@@ -229,10 +292,17 @@ int launch_gather(const fvk_mesh* m, Op op, Scaling sc, double* out, int mode, f
     const int nC = m->nCells;
     const int grid = (nC + 255) / 256;
     const int variant = fvk_variant();
-    if (variant == 0 && m->ownerSorted)
-        k_gather_split<Op><<<grid, 256, 0, fvk_cu(stream)>>>(
-            op, sc, nC, m->nInternalFaces, m->lowSeg, m->lowFace, m->lowOwner, m->ownStart,
-            m->neighbour, m->hasBnd, m->nBndCells, m->bndCell, m->bndSeg, m->bndFace, out, mode);
+    const SplitPlan pl {m->lowSeg, m->lowFace, m->lowOwner, m->ownStart, m->neighbour, m->hasBnd,
+                        m->nBndCells, m->bndCell, m->bndSeg, m->bndFace};
+    if (m->ownerSorted && m->nInternalFaces > 0 && (variant == 0 || variant == 3))
+    {
+        if (variant == 0)
+            k_gather_split<Op, 3><<<grid, 256, 0, fvk_cu(stream)>>>(op, sc, nC, m->nInternalFaces, pl, out, mode);
+        else
+            k_gather_split<Op, 4><<<grid, 256, 0, fvk_cu(stream)>>>(op, sc, nC, m->nInternalFaces, pl, out, mode);
+    }
+    else if (m->ownerSorted && (variant == 2 || (m->nInternalFaces == 0 && variant != 1)))
+        k_gather_split_simple<Op><<<grid, 256, 0, fvk_cu(stream)>>>(op, sc, nC, m->nInternalFaces, pl, out, mode);
     else
         k_gather_stencil<Op><<<grid, 256, 0, fvk_cu(stream)>>>(
             op, sc, nC, m->nInternalFaces, m->stencilSeg, m->gatherEnt, m->owner, m->neighbour, out, mode);

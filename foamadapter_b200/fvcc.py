@@ -1,0 +1,175 @@
+"""Python mirror of NeoN::finiteVolume::cellCentred (the reference's operator/plugin interface for
+the hot path), with the same class and method names and argument meaning; bodies call the C ABI.
+
+Reference: src/NeoN/include/NeoN/finiteVolume/cellCentred/{fields,operators,interpolation,
+faceNormalGradient,boundary}/*.hpp. The C++ twin lives in include/NeoN/.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from . import ops
+from .mesh import UnstructuredMesh
+
+
+@dataclass
+class Coeff:
+    """dsl::Coeff (src/NeoN/include/NeoN/dsl/coeff.hpp:21-54): scalar x optional per-cell view."""
+    value: float = 1.0
+    view: torch.Tensor | None = None
+
+    def __mul__(self, rhs):
+        if isinstance(rhs, Coeff):
+            if rhs.view is not None and self.view is not None:
+                return Coeff(self.value * rhs.value, self.view * rhs.view)
+            return Coeff(self.value * rhs.value, self.view if self.view is not None else rhs.view)
+        return Coeff(self.value * float(rhs), self.view)
+
+    __rmul__ = __mul__
+
+
+class BoundaryData:
+    """fields/boundaryData.hpp:32-215: value/refValue/refGrad T[nB], valueFraction double[nB]."""
+
+    def __init__(self, mesh, ncomp, device):
+        shp = (mesh.nBoundaryFaces, 3) if ncomp == 3 else (mesh.nBoundaryFaces,)
+        z = lambda s: torch.zeros(s, dtype=torch.float64, device=device)
+        self.value, self.refValue, self.refGrad = z(shp), z(shp), z(shp)
+        self.valueFraction = z((mesh.nBoundaryFaces,))
+
+
+_BC_KINDS = {"calculated": ops.BC_CALCULATED, "fixedValue": ops.BC_FIXED_VALUE, "fixedGradient": ops.BC_FIXED_GRADIENT,
+             "extrapolated": ops.BC_EXTRAPOLATED, "empty": ops.BC_EMPTY,
+             # readers.hpp:43-95 maps zeroGradient -> fixedGradient 0 and noSlip -> fixedValue 0
+             "zeroGradient": ops.BC_FIXED_GRADIENT, "noSlip": ops.BC_FIXED_VALUE}
+
+
+class VolumeField:
+    """VolumeField<scalar|Vec3> (fields/volumeField.hpp). bcs: one (type, constant) per patch."""
+
+    def __init__(self, mesh: UnstructuredMesh, name: str, ncomp: int = 1, bcs=None, device="cuda"):
+        self.mesh, self.name, self.ncomp = mesh, name, ncomp
+        shp = (mesh.nCells, 3) if ncomp == 3 else (mesh.nCells,)
+        self.internal = torch.zeros(shp, dtype=torch.float64, device=device)
+        self.boundary = BoundaryData(mesh, ncomp, device)
+        bcs = bcs if bcs is not None else [("calculated", 0.0)] * mesh.nPatches
+        if len(bcs) != mesh.nPatches:
+            raise ValueError(f"{name}: {len(bcs)} boundary conditions for {mesh.nPatches} patches")
+        self.bcs = []
+        for kind, cst in bcs:
+            if kind not in _BC_KINDS:
+                raise KeyError(f"unknown boundary condition '{kind}'")  # RuntimeSelectionFactory::keyExistsOrError
+            if kind in ("zeroGradient", "noSlip", "calculated", "extrapolated", "empty"):
+                cst = (0.0, 0.0, 0.0) if ncomp == 3 else 0.0
+            self.bcs.append((kind, cst))
+
+    def internalVector(self):
+        return self.internal
+
+    def boundaryData(self):
+        return self.boundary
+
+    def assignable(self, patch: int) -> bool:
+        # fixedValue is the only non-assignable BC (fixedValue.hpp:56 vs fixedGradient/extrapolated)
+        return _BC_KINDS[self.bcs[patch][0]] != ops.BC_FIXED_VALUE
+
+    def correctBoundaryConditions(self):
+        b = self.boundary
+        ops.correct_boundary_conditions(self.mesh, [_BC_KINDS[k] for k, _ in self.bcs], [c for _, c in self.bcs],
+                                        self.internal, b.value, b.refValue, b.valueFraction, b.refGrad)
+
+
+class SurfaceField:
+    """SurfaceField<T>: internalVector has nInternalFaces + nBoundaryFaces entries
+    (fields/surfaceField.hpp:38-53); boundary value duplicates the boundary slice."""
+
+    def __init__(self, mesh, name, ncomp=1, device="cuda"):
+        self.mesh, self.name, self.ncomp = mesh, name, ncomp
+        shp = (mesh.nFaces, 3) if ncomp == 3 else (mesh.nFaces,)
+        self.internal = torch.zeros(shp, dtype=torch.float64, device=device)
+        self.bvalue = torch.zeros((mesh.nBoundaryFaces,) + shp[1:], dtype=torch.float64, device=device)
+
+    def internalVector(self):
+        return self.internal
+
+
+class SurfaceInterpolation:
+    """interpolation/surfaceInterpolation.hpp:54-69; keys "linear" | "upwind"."""
+
+    def __init__(self, mesh, scheme: str):
+        if scheme not in ops.SCHEMES:
+            raise KeyError(f"unknown interpolation scheme '{scheme}'")
+        self.mesh, self.scheme = mesh, ops.SCHEMES[scheme]
+
+    def interpolate(self, src: VolumeField, dst: SurfaceField | None = None, faceFlux: SurfaceField | None = None):
+        if self.scheme == ops.UPWIND and faceFlux is None:
+            raise ValueError("limited scheme require a faceFlux")  # upwind.hpp:66-72
+        dst = dst or SurfaceField(self.mesh, "phif", src.ncomp, src.internal.device)
+        ops.interpolate(self.mesh, src.internal, src.boundary.value, dst.internal, self.scheme,
+                        None if faceFlux is None else faceFlux.internal)
+        return dst
+
+    def weight(self, faceFlux: SurfaceField | None = None, dst: SurfaceField | None = None):
+        dst = dst or SurfaceField(self.mesh, "weight", 1)
+        ops.interpolation_weights(self.mesh, dst.internal, dst.bvalue, self.scheme,
+                                  None if faceFlux is None else faceFlux.internal)
+        return dst
+
+
+class FaceNormalGradient:
+    """faceNormalGradient/faceNormalGradient.hpp:50-54; key "uncorrected"."""
+
+    def __init__(self, mesh, scheme="uncorrected"):
+        if scheme != "uncorrected":
+            raise KeyError(f"unknown faceNormalGradient scheme '{scheme}'")
+        self.mesh = mesh
+
+    def faceNormalGrad(self, phi: VolumeField, dst: SurfaceField | None = None):
+        dst = dst or SurfaceField(self.mesh, "snGrad", phi.ncomp, phi.internal.device)
+        ops.face_normal_grad(self.mesh, phi.internal, phi.boundary.value, dst.internal)
+        return dst
+
+
+class GaussGreenDiv:
+    """operators/gaussGreenDiv.hpp:75-81: div(divPhi, faceFlux, phi, operatorScaling)."""
+
+    def __init__(self, mesh, scheme="linear"):
+        self.mesh, self.interp = mesh, SurfaceInterpolation(mesh, scheme)
+
+    def div(self, divPhi: torch.Tensor, faceFlux: SurfaceField, phi: VolumeField, operatorScaling=Coeff(), mode=ops.ACC_SCALE):
+        """Default mode reproduces computeDiv: accumulate into divPhi, then scale all of it."""
+        return ops.div(self.mesh, faceFlux.internal, phi.internal, phi.boundary.value, divPhi, self.interp.scheme,
+                       operatorScaling.value, operatorScaling.view, mode)
+
+
+class GaussGreenGrad:
+    """operators/gaussGreenGrad.hpp: grad(phi, gradPhi); always linear."""
+
+    def __init__(self, mesh):
+        self.mesh = mesh
+
+    def grad(self, phi: VolumeField, gradPhi: torch.Tensor | None = None):
+        if gradPhi is None:
+            gradPhi = torch.empty((self.mesh.nCells, 3), dtype=torch.float64, device=phi.internal.device)
+            return ops.grad(self.mesh, phi.internal, phi.boundary.value, gradPhi, ops.SET)
+        return ops.grad(self.mesh, phi.internal, phi.boundary.value, gradPhi, ops.ACC_SCALE)
+
+
+class GaussGreenLaplacian:
+    """operators/gaussGreenLaplacian.hpp: laplacian(lapPhi, gamma, phi, operatorScaling); gamma is
+    ignored by the explicit reference kernel (gaussGreenLaplacian.cpp:14)."""
+
+    def __init__(self, mesh, scheme="uncorrected"):
+        self.mesh, self.fng = mesh, FaceNormalGradient(mesh, scheme)
+
+    def laplacian(self, lapPhi, gamma, phi: VolumeField, operatorScaling=Coeff(), mode=ops.ACC_SCALE):
+        return ops.laplacian(self.mesh, phi.internal, phi.boundary.value, lapPhi, operatorScaling.value,
+                             operatorScaling.view, mode)
+
+
+def computeCoNum(faceFlux: SurfaceField, dt: float) -> float:
+    """auxiliary/coNum.cpp:18-96; returns maxCoNum (device->host scalar, like the reference)."""
+    res = ops.conum(faceFlux.mesh, faceFlux.internal, dt)
+    return float(res[0].item())

@@ -93,6 +93,32 @@ class MeshDesc:
         self.patch_names = list(patch_names or [f"patch{i}" for i in range(c.nPatches)])
         return self
 
+    @classmethod
+    def uniform_1d(cls, nCells: int):
+        """NeoN::create1DUniformMesh (src/NeoN/src/mesh/unstructured/unstructuredMesh.cpp:112-220):
+        unit interval, nCells cells, internal faces i|i+1, then the left and the right boundary face
+        as two one-face patches."""
+        n = int(nCells)
+        h = (1.0 - 0.0) / float(n)
+        pts = np.zeros((n + 1, 3))
+        pts[: n - 1, 0] = 0.0 + (np.arange(n - 1) + 1.0) * h
+        pts[n - 1] = (0.0, 0.0, 0.0)
+        pts[n] = (1.0, 0.0, 0.0)
+        C_ = np.zeros((n, 3))
+        C_[:, 0] = 0.5 * h + h * np.arange(n, dtype=np.float64)
+        Sf = np.tile(np.array([1.0, 0.0, 0.0]), (n + 1, 1))
+        Sf[n - 1] = (-1.0, 0.0, 0.0)
+        owner = np.concatenate([np.arange(n - 1), [0, n - 1]]).astype(np.int32)
+        delta = np.array([[0.0 - C_[0, 0], 0, 0], [1.0 - C_[n - 1, 0], 0, 0]])
+        return cls.from_arrays(dict(
+            nCells=n, nInternalFaces=n - 1, nBoundaryFaces=2, nPatches=2, nPoints=n + 1, points=pts,
+            cellVolumes=np.full(n, h), cellCentres=C_, faceAreas=Sf, faceCentres=pts.copy(),
+            magFaceAreas=np.ones(n + 1), faceOwner=owner, faceNeighbour=np.arange(1, n, dtype=np.int32),
+            faceCells=np.array([0, n - 1], dtype=np.int32), bCf=pts[n - 1:].copy(), bCn=C_[[0, n - 1]].copy(),
+            bSf=Sf[n - 1:].copy(), bMagSf=np.ones(2), bNf=Sf[n - 1:].copy(), bDelta=delta,
+            bWeights=np.ones(2), bDeltaCoeffs=1.0 / np.abs(delta[:, 0]),
+            patchOffsets=np.array([0, 1, 2], dtype=np.int32)), patch_names=["left", "right"])
+
     def __del__(self):
         if self._owned_ptr is not None and _capi._lib is not None:
             _capi._lib.fvk_blockmesh_destroy(self._owned_ptr)

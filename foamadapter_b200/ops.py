@@ -1,0 +1,130 @@
+"""Typed Python wrappers over the C ABI (include/fvk.h). Tensors are torch CUDA tensors (fp64 /
+int32) used purely as device-memory handles; every call goes to libfvk.so on torch's current stream.
+There is no fallback: without the library or a GPU these raise."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from ._capi import check, lib, ptr
+from .mesh import UnstructuredMesh
+
+SET, ACC_SCALE, ADD = 0, 1, 2
+LINEAR, UPWIND = 0, 1
+SCHEMES = {"linear": LINEAR, "upwind": UPWIND}
+BC_CALCULATED, BC_FIXED_VALUE, BC_FIXED_GRADIENT, BC_EXTRAPOLATED, BC_EMPTY = range(5)
+
+gpu_launches = 0  # kernels launched through this module (bench.py reports it)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk(t, n, name, comps=None):
+    if t is None:
+        return
+    if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()):
+        raise ValueError(f"{name}: need a contiguous CUDA float64 tensor")
+    if t.shape[0] != n or (comps == 3 and (t.ndim != 2 or t.shape[1] != 3)) or (comps == 1 and t.ndim != 1):
+        raise ValueError(f"{name}: bad shape {tuple(t.shape)}, expected leading {n}, comps {comps}")
+
+
+def _count(k=1):
+    global gpu_launches
+    gpu_launches += k
+
+
+def div(mesh: UnstructuredMesh, faceFlux, phi, phiB, out, scheme=LINEAR, coeff=1.0, coeffView=None, mode=SET):
+    vec = phi.ndim == 2
+    _chk(faceFlux, mesh.nFaces, "faceFlux", 1); _chk(phi, mesh.nCells, "phi", 3 if vec else 1)
+    _chk(phiB, mesh.nBoundaryFaces, "phiB", 3 if vec else 1); _chk(out, mesh.nCells, "out", 3 if vec else 1)
+    _chk(coeffView, mesh.nCells, "coeffView", 1)
+    fn = lib().fvk_div_v if vec else lib().fvk_div_s
+    check(fn(mesh.handle, C.c_int(scheme), ptr(faceFlux), ptr(phi), ptr(phiB), C.c_double(coeff), ptr(coeffView),
+             ptr(out), C.c_int(mode), _stream()))
+    _count()
+    return out
+
+
+def grad(mesh, phi, phiB, out, mode=SET):
+    _chk(phi, mesh.nCells, "phi", 1); _chk(phiB, mesh.nBoundaryFaces, "phiB", 1); _chk(out, mesh.nCells, "out", 3)
+    check(lib().fvk_grad_s(mesh.handle, ptr(phi), ptr(phiB), ptr(out), C.c_int(mode), _stream()))
+    _count()
+    return out
+
+
+def laplacian(mesh, phi, phiB, out, coeff=1.0, coeffView=None, mode=SET):
+    vec = phi.ndim == 2
+    _chk(phi, mesh.nCells, "phi", 3 if vec else 1); _chk(phiB, mesh.nBoundaryFaces, "phiB", 3 if vec else 1)
+    _chk(out, mesh.nCells, "out", 3 if vec else 1); _chk(coeffView, mesh.nCells, "coeffView", 1)
+    fn = lib().fvk_laplacian_v if vec else lib().fvk_laplacian_s
+    check(fn(mesh.handle, ptr(phi), ptr(phiB), C.c_double(coeff), ptr(coeffView), ptr(out), C.c_int(mode), _stream()))
+    _count()
+    return out
+
+
+def surface_integrate(mesh, flux, out, coeff=1.0, coeffView=None, mode=SET):
+    vec = flux.ndim == 2
+    _chk(flux, mesh.nFaces, "flux", 3 if vec else 1); _chk(out, mesh.nCells, "out", 3 if vec else 1)
+    _chk(coeffView, mesh.nCells, "coeffView", 1)
+    fn = lib().fvk_surface_integrate_v if vec else lib().fvk_surface_integrate_s
+    check(fn(mesh.handle, ptr(flux), C.c_double(coeff), ptr(coeffView), ptr(out), C.c_int(mode), _stream()))
+    _count()
+    return out
+
+
+def interpolate(mesh, phi, phiB, outFace, scheme=LINEAR, faceFlux=None):
+    vec = phi.ndim == 2
+    _chk(phi, mesh.nCells, "phi", 3 if vec else 1); _chk(phiB, mesh.nBoundaryFaces, "phiB", 3 if vec else 1)
+    _chk(outFace, mesh.nFaces, "outFace", 3 if vec else 1); _chk(faceFlux, mesh.nFaces, "faceFlux", 1)
+    fn = lib().fvk_interpolate_v if vec else lib().fvk_interpolate_s
+    check(fn(mesh.handle, C.c_int(scheme), ptr(faceFlux), ptr(phi), ptr(phiB), ptr(outFace), _stream()))
+    _count()
+    return outFace
+
+
+def interpolation_weights(mesh, wFace, wBoundary=None, scheme=LINEAR, faceFlux=None):
+    _chk(wFace, mesh.nFaces, "wFace", 1); _chk(wBoundary, mesh.nBoundaryFaces, "wBoundary", 1)
+    _chk(faceFlux, mesh.nFaces, "faceFlux", 1)
+    check(lib().fvk_interpolation_weights(mesh.handle, C.c_int(scheme), ptr(faceFlux), ptr(wFace), ptr(wBoundary), _stream()))
+    _count()
+    return wFace
+
+
+def face_normal_grad(mesh, phi, phiB, outFace):
+    vec = phi.ndim == 2
+    _chk(phi, mesh.nCells, "phi", 3 if vec else 1); _chk(phiB, mesh.nBoundaryFaces, "phiB", 3 if vec else 1)
+    _chk(outFace, mesh.nFaces, "outFace", 3 if vec else 1)
+    fn = lib().fvk_face_normal_grad_v if vec else lib().fvk_face_normal_grad_s
+    check(fn(mesh.handle, ptr(phi), ptr(phiB), ptr(outFace), _stream()))
+    _count()
+    return outFace
+
+
+def conum(mesh, faceFlux, dt, result=None, scratch=None):
+    """Returns a device tensor [maxCoNum, meanCoNum]; no host sync."""
+    _chk(faceFlux, mesh.nFaces, "faceFlux", 1)
+    if result is None:
+        result = torch.empty(2, dtype=torch.float64, device=faceFlux.device)
+    if scratch is None:
+        scratch = torch.empty(lib().fvk_conum_scratch_bytes(mesh.handle) // 8, dtype=torch.float64, device=faceFlux.device)
+    check(lib().fvk_conum(mesh.handle, ptr(faceFlux), C.c_double(dt), ptr(result), ptr(scratch), _stream()))
+    _count(2)
+    return result
+
+
+def correct_boundary_conditions(mesh, kinds, consts, internal, value, refValue, valueFraction, refGrad):
+    ncomp = 3 if internal.ndim == 2 else 1
+    n = mesh.nPatches
+    if len(kinds) != n:
+        raise ValueError(f"need one boundary condition per patch ({n}), got {len(kinds)}")
+    k = (C.c_int32 * n)(*[int(x) for x in kinds])
+    flat = []
+    for c in consts:
+        flat += [float(x) for x in (c if ncomp == 3 else [c])]
+    v = (C.c_double * (n * ncomp))(*flat)
+    check(lib().fvk_correct_boundary_conditions(mesh.handle, C.c_int(ncomp), k, v, ptr(internal), ptr(value),
+                                                ptr(refValue), ptr(valueFraction), ptr(refGrad), _stream()))
+    _count()

@@ -1,0 +1,828 @@
+// TEST INFRASTRUCTURE -- the CPU oracle. NOT product code: only tests/, __graft_entry__.smoke()
+// and bench.py's cpu_baseline / --impl reference legs may load this library.
+//
+// CPU restatement of the NeoN / FoamAdapter kernels on the finite-volume hot path, written from the
+// reference's algorithms (file:line cited per function, all relative to /root/reference). The
+// reference itself cannot be built here (needs OpenFOAM, Kokkos, Ginkgo).
+//
+//   par == 0 : SerialExecutor semantics -- plain loops in index order
+//              (src/NeoN/include/NeoN/core/parallelAlgorithms.hpp:38-44). This is the parity oracle.
+//   par == 1 : CPUExecutor semantics -- `parallel for` + atomics, mirroring Kokkos::OpenMP +
+//              Kokkos::atomic_add; used as the multi-core CPU timing baseline.
+//
+// Pinned against the reference's own golden vectors in tests/test_oracle_golden.py
+// (test/setup_operator/0/{divT,gradT}_{Serial,OpenMP}, src/NeoN/test/linearAlgebra/*.cpp known
+// answers, stencil/sparsity known answers). The CG is a restatement of Ginkgo 1.10 solver::Cg
+// (third party, not in the tree) pinned by the 3x3 test of
+// src/NeoN/test/linearAlgebra/ginkgo.cpp:95-124; residual histories on real meshes: parity unpinned.
+//
+// Build: g++ -O3 -ffp-contract=off -fopenmp -shared -fPIC (oracle/Makefile).
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace
+{
+using label = int32_t;
+struct Vec3
+{
+    double c[3];
+};
+inline Vec3 operator+(Vec3 a, Vec3 b) { return {{a.c[0] + b.c[0], a.c[1] + b.c[1], a.c[2] + b.c[2]}}; }
+inline Vec3 operator-(Vec3 a, Vec3 b) { return {{a.c[0] - b.c[0], a.c[1] - b.c[1], a.c[2] - b.c[2]}}; }
+// vec3.hpp: Vec3*scalar and scalar*Vec3 both multiply component * scalar
+inline Vec3 operator*(Vec3 a, double s) { return {{a.c[0] * s, a.c[1] * s, a.c[2] * s}}; }
+inline Vec3 operator*(double s, Vec3 a) { return {{a.c[0] * s, a.c[1] * s, a.c[2] * s}}; }
+inline double dot(Vec3 a, Vec3 b) { return a.c[0] * b.c[0] + a.c[1] * b.c[1] + a.c[2] * b.c[2]; }
+inline double mag(Vec3 a) { return std::sqrt(a.c[0] * a.c[0] + a.c[1] * a.c[1] + a.c[2] * a.c[2]); }
+inline Vec3& operator+=(Vec3& a, Vec3 b) { a = a + b; return a; }
+inline Vec3& operator-=(Vec3& a, Vec3 b) { a = a - b; return a; }
+inline Vec3& operator*=(Vec3& a, double s) { a = a * s; return a; }
+
+template <class T> T zero();
+template <> double zero<double>() { return 0.0; }
+template <> Vec3 zero<Vec3>() { return {{0.0, 0.0, 0.0}}; }
+template <class T> T one();
+template <> double one<double>() { return 1.0; }
+template <> Vec3 one<Vec3>() { return {{1.0, 1.0, 1.0}}; }
+
+inline void atomic_add(double* p, double v)
+{
+#pragma omp atomic
+    *p += v;
+}
+inline void atomic_add(Vec3* p, Vec3 v)
+{
+    for (int d = 0; d < 3; ++d) atomic_add(&p->c[d], v.c[d]);
+}
+inline void atomic_sub(double* p, double v)
+{
+#pragma omp atomic
+    *p -= v;
+}
+inline void atomic_sub(Vec3* p, Vec3 v)
+{
+    for (int d = 0; d < 3; ++d) atomic_sub(&p->c[d], v.c[d]);
+}
+
+// dsl::Coeff::operator[] (src/NeoN/include/NeoN/dsl/coeff.hpp:35)
+struct Coeff
+{
+    double coeff;
+    const double* view;
+    double operator[](label i) const { return view ? view[i] * coeff : coeff; }
+};
+
+// parallelFor: Serial = plain loop; CPU = omp parallel for
+#define PFOR(par, i, b, e) _Pragma("omp parallel for schedule(static) if (par)") for (label i = (b); i < (e); ++i)
+
+// ---- interpolation/linear.cpp:12-46 -----------------------------------------------------------------
+template <class T>
+void linearInterpolate(int par, label nI, label nB, const label* own, const label* nei, const double* w,
+                       const T* src, const T* bvalue, T* dst)
+{
+    PFOR(par, f, 0, nI + nB)
+    {
+        if (f < nI)
+            dst[f] = w[f] * src[own[f]] + (1 - w[f]) * src[nei[f]];
+        else
+            dst[f] = w[f] * bvalue[f - nI];
+    }
+}
+// ---- interpolation/upwind.cpp:12-56 ------------------------------------------------------------------
+template <class T>
+void upwindInterpolate(int par, label nI, label nB, const label* own, const label* nei, const double* w,
+                       const double* flux, const T* src, const T* bvalue, T* dst)
+{
+    PFOR(par, f, 0, nI + nB)
+    {
+        if (f < nI)
+            dst[f] = (flux[f] >= 0) ? src[own[f]] : src[nei[f]];
+        else
+            dst[f] = w[f] * bvalue[f - nI];
+    }
+}
+// ---- faceNormalGradient/uncorrected.cpp:11-52 -----------------------------------------------------------
+template <class T>
+void faceNormalGrad(int par, label nI, label nB, const label* own, const label* nei, const label* faceCells,
+                    const double* nodc, const T* phi, const T* bvalue, T* phif)
+{
+    PFOR(par, f, 0, nI) { phif[f] = nodc[f] * (phi[nei[f]] - phi[own[f]]); }
+    PFOR(par, f, nI, nI + nB) { phif[f] = nodc[f] * (bvalue[f - nI] - phi[faceCells[f - nI]]); }
+}
+// ---- generic "sum face values to cells, then scale" used by computeDiv (gaussGreenDiv.cpp:29-101),
+//      computeGrad (gaussGreenGrad.cpp:46-70), computeLaplacianExp (gaussGreenLaplacian.cpp:34-60),
+//      surfaceIntegrate (surfaceIntegrate.cpp:26-47). faceVal(f) is the value added to the owner and
+//      subtracted from the neighbour. Serial: plain += in face order (explicit branch :46-67).
+template <class T, class F, class S>
+void scatterAndScale(int par, label nC, label nI, label nB, const label* own, const label* nei,
+                     const label* faceCells, F faceVal, S scale, T* res)
+{
+    if (!par)
+    {
+        for (label f = 0; f < nI; ++f)
+        {
+            T flux = faceVal(f);
+            res[own[f]] += flux;
+            res[nei[f]] -= flux;
+        }
+        for (label f = nI; f < nI + nB; ++f) { res[faceCells[f - nI]] += faceVal(f); }
+        for (label c = 0; c < nC; ++c) res[c] *= scale(c);
+    }
+    else
+    {
+        PFOR(1, f, 0, nI)
+        {
+            T flux = faceVal(f);
+            atomic_add(&res[own[f]], flux);
+            atomic_sub(&res[nei[f]], flux);
+        }
+        PFOR(1, f, nI, nI + nB) { atomic_add(&res[faceCells[f - nI]], faceVal(f)); }
+        PFOR(1, c, 0, nC) { res[c] *= scale(c); }
+    }
+}
+
+template <class T>
+void divExp(int par, int scheme, label nC, label nI, label nB, const label* own, const label* nei,
+            const label* faceCells, const double* V, const double* w, const double* faceFlux, const T* phi,
+            const T* bvalue, Coeff cf, T* res)
+{
+    // computeDivExp (gaussGreenDiv.cpp:103-140): phif temporary, interpolate, computeDiv
+    std::vector<T> phif(size_t(nI) + nB);
+    if (scheme == 0)
+        linearInterpolate(par, nI, nB, own, nei, w, phi, bvalue, phif.data());
+    else
+        upwindInterpolate(par, nI, nB, own, nei, w, faceFlux, phi, bvalue, phif.data());
+    scatterAndScale<T>(par, nC, nI, nB, own, nei, faceCells,
+                       [&](label f) { return faceFlux[f] * phif[f]; },
+                       [&](label c) { return cf[c] / V[c]; }, res);
+}
+
+template <class T>
+void laplacianExp(int par, label nC, label nI, label nB, const label* own, const label* nei,
+                  const label* faceCells, const double* V, const double* magSf, const double* nodc,
+                  const T* phi, const T* bvalue, Coeff cf, T* res)
+{
+    std::vector<T> fn(size_t(nI) + nB);
+    faceNormalGrad(par, nI, nB, own, nei, faceCells, nodc, phi, bvalue, fn.data());
+    scatterAndScale<T>(par, nC, nI, nB, own, nei, faceCells,
+                       [&](label f) { return magSf[f] * fn[f]; },
+                       [&](label c) { return cf[c] / V[c]; }, res);
+}
+
+// ---- implicit operators ------------------------------------------------------------------------------
+// gaussGreenDiv.cpp:155-262
+template <class T>
+void divImp(int par, label nI, label nB, const label* own, const label* nei, const label* faceCells,
+            const label* rowOffs, const uint8_t* diagOffs, const uint8_t* ownOffs, const uint8_t* neiOffs,
+            const double* faceFlux, const double* weights /*nF*/, const double* bweights /*nB*/,
+            const double* bDeltaCoeffs, const double* valueFraction, const T* refValue, const T* refGrad,
+            Coeff os, T* values, T* rhs, T* bcMatrix, T* bcRhs)
+{
+    PFOR(par, f, 0, nI)
+    {
+        double flux = faceFlux[f];
+        double weight = weights[f];
+        label o = own[f], n = nei[f];
+        label rowNeiStart = rowOffs[n], rowOwnStart = rowOffs[o];
+        double osN = os[n], osO = os[o];
+        T value = -weight * flux * one<T>();
+        values[rowNeiStart + neiOffs[f]] += value * osN;
+        if (par) atomic_sub(&values[rowOwnStart + diagOffs[o]], value * osO);
+        else values[rowOwnStart + diagOffs[o]] -= value * osO;
+        value = flux * (1 - weight) * one<T>();
+        values[rowOwnStart + ownOffs[f]] += value * osO;
+        if (par) atomic_sub(&values[rowNeiStart + diagOffs[n]], value * osN);
+        else values[rowNeiStart + diagOffs[n]] -= value * osN;
+    }
+    PFOR(par, f, nI, nI + nB)
+    {
+        label b = f - nI;
+        double flux = bweights[b] * faceFlux[f];
+        label o = faceCells[b];
+        label rowOwnStart = rowOffs[o];
+        double osO = os[o];
+        double vf1 = valueFraction[b];
+        double vf2 = 1.0 - vf1;
+        T valueMat = flux * osO * vf2 * one<T>();
+        if (par) atomic_add(&values[rowOwnStart + diagOffs[o]], valueMat);
+        else values[rowOwnStart + diagOffs[o]] += valueMat;
+        bcMatrix[b] = valueMat;
+        // (sic) the second term is not multiplied by the flux, gaussGreenDiv.cpp:253-254
+        T valueRhs = (flux * osO * (vf1 * refValue[b])) + vf2 * refGrad[b] * (1 / bDeltaCoeffs[b]);
+        if (par) atomic_sub(&rhs[o], valueRhs);
+        else rhs[o] -= valueRhs;
+        bcRhs[b] = valueRhs;
+    }
+}
+// gaussGreenLaplacian.cpp:76-177
+template <class T>
+void laplacianImp(int par, label nI, label nB, const label* own, const label* nei, const label* faceCells,
+                  const label* rowOffs, const uint8_t* diagOffs, const uint8_t* ownOffs, const uint8_t* neiOffs,
+                  const double* gamma, const double* deltaCoeffs /*nonOrth, nF*/, const double* magSf,
+                  const double* valueFraction, const T* refValue, const T* refGrad, Coeff os, T* values, T* rhs,
+                  T* bcMatrix, T* bcRhs)
+{
+    PFOR(par, f, 0, nI)
+    {
+        double flux = deltaCoeffs[f] * gamma[f] * magSf[f];
+        label o = own[f], n = nei[f];
+        label rowNeiStart = rowOffs[n], rowOwnStart = rowOffs[o];
+        double osN = os[n], osO = os[o];
+        values[rowNeiStart + neiOffs[f]] += flux * one<T>() * osN;
+        if (par) atomic_sub(&values[rowOwnStart + diagOffs[o]], flux * one<T>() * osO);
+        else values[rowOwnStart + diagOffs[o]] -= flux * one<T>() * osO;
+        values[rowOwnStart + ownOffs[f]] += flux * one<T>() * osO;
+        if (par) atomic_sub(&values[rowNeiStart + diagOffs[n]], flux * one<T>() * osN);
+        else values[rowNeiStart + diagOffs[n]] -= flux * one<T>() * osN;
+    }
+    PFOR(par, f, nI, nI + nB)
+    {
+        label b = f - nI;
+        double flux = gamma[f] * magSf[f];
+        label o = faceCells[b];
+        label rowOwnStart = rowOffs[o];
+        double osO = os[o];
+        T valueMat = flux * osO * valueFraction[b] * deltaCoeffs[f] * one<T>();
+        if (par) atomic_sub(&values[rowOwnStart + diagOffs[o]], valueMat);
+        else values[rowOwnStart + diagOffs[o]] -= valueMat;
+        bcMatrix[b] = valueMat;
+        T valueRhs = flux * osO * (valueFraction[b] * deltaCoeffs[f] * refValue[b] + (1.0 - valueFraction[b]) * refGrad[b]);
+        if (par) atomic_sub(&rhs[o], valueRhs);
+        else rhs[o] -= valueRhs;
+        bcRhs[b] = valueRhs;
+    }
+}
+// ddtOperator.cpp:38-60
+template <class T>
+void ddtImp(int par, label nC, const label* rowOffs, const uint8_t* diagOffs, const double* V, const T* oldField,
+            double dt, Coeff os, T* values, T* rhs)
+{
+    const double dtInver = 1.0 / dt;
+    PFOR(par, c, 0, nC)
+    {
+        const label idx = rowOffs[c] + diagOffs[c];
+        const double commonCoef = os[c] * V[c] * dtInver;
+        values[idx] += commonCoef * one<T>();
+        rhs[c] += commonCoef * oldField[c];
+    }
+}
+// ddtOperator.cpp:21-36
+template <class T>
+void ddtExp(int par, label nC, const double* V, const T* field, const T* oldField, double dt, T* source)
+{
+    const double dtInver = 1.0 / dt;
+    PFOR(par, c, 0, nC) { source[c] += dtInver * (field[c] - oldField[c]) * V[c]; }
+}
+// sourceTerm.cpp:22-55
+template <class T>
+void sourceImp(int par, label nC, const label* rowOffs, const uint8_t* diagOffs, const double* V, const double* coeff,
+               Coeff os, T* values)
+{
+    PFOR(par, c, 0, nC)
+    {
+        label idx = rowOffs[c] + diagOffs[c];
+        values[idx] += os[c] * coeff[c] * V[c] * one<T>();
+    }
+}
+template <class T>
+void sourceExp(int par, label nC, const double* coeff, const T* field, Coeff os, T* source)
+{
+    PFOR(par, c, 0, nC) { source[c] += os[c] * coeff[c] * field[c]; }
+}
+
+template <class T>
+void correctBCs(label nPatches, const label* offsets, const label* kind, const T* cst, const label* faceCells,
+                const double* bDeltaCoeffs, const T* internal, T* value, T* refValue, double* valueFraction, T* refGrad)
+{
+    for (label p = 0; p < nPatches; ++p)
+        for (label i = offsets[p]; i < offsets[p + 1]; ++i)
+        {
+            if (kind[p] == 1)
+            { // fixedValue.hpp:33-42
+                refValue[i] = cst[p]; value[i] = cst[p]; valueFraction[i] = 1.0; refGrad[i] = cst[p];
+            }
+            else if (kind[p] == 2)
+            { // fixedGradient.hpp:42-53
+                refGrad[i] = cst[p];
+                value[i] = internal[faceCells[i]] + cst[p] * (1 / bDeltaCoeffs[i]);
+                valueFraction[i] = 0.0; refValue[i] = zero<T>();
+            }
+            else if (kind[p] == 3)
+            { // extrapolated.hpp:40-52
+                T v = internal[faceCells[i]];
+                value[i] = v; valueFraction[i] = 1.0; refValue[i] = v; refGrad[i] = zero<T>();
+            }
+        }
+}
+} // namespace
+
+extern "C" {
+
+int fvo_max_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+void fvo_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
+// basicGeometryScheme.cpp:15-136
+void fvo_geometry_scheme(int32_t nI, int32_t nB, const int32_t* own, const int32_t* nei, const int32_t* faceCells,
+                         const double* C_, const double* Cf_, const double* Sf_, const double* magSf, double* w,
+                         double* dc, double* nodc)
+{
+    const Vec3* C = reinterpret_cast<const Vec3*>(C_);
+    const Vec3* Cf = reinterpret_cast<const Vec3*>(Cf_);
+    const Vec3* Sf = reinterpret_cast<const Vec3*>(Sf_);
+    constexpr double ROOTVSMALL = 1e-18;
+    for (label f = 0; f < nI; ++f)
+    {
+        double sfdOwn = std::abs(dot(Sf[f], Cf[f] - C[own[f]]));
+        double sfdNei = std::abs(dot(Sf[f], C[nei[f]] - Cf[f]));
+        w[f] = (std::abs(sfdOwn + sfdNei) > ROOTVSMALL) ? sfdNei / (sfdOwn + sfdNei) : 0.5;
+        Vec3 d = C[nei[f]] - C[own[f]];
+        dc[f] = 1.0 / mag(d);
+        Vec3 n = 1 / magSf[f] * Sf[f];
+        nodc[f] = 1.0 / std::max(dot(n, d), 0.05 * mag(d));
+    }
+    for (label f = nI; f < nI + nB; ++f)
+    {
+        w[f] = 1.0;
+        Vec3 d = Cf[f] - C[faceCells[f - nI]];
+        dc[f] = 1.0 / mag(d);
+        Vec3 n = 1 / magSf[f] * Sf[f];
+        nodc[f] = 1.0 / std::max(dot(n, d), 0.05 * mag(d));
+    }
+}
+
+// sparsityPattern.cpp:21-143 (three passes over the faces, serial on the host)
+void fvo_sparsity(int32_t nC, int32_t nI, const int32_t* own, const int32_t* nei, int32_t* rowOffs, int32_t* colIdxs,
+                  uint8_t* ownerOffset, uint8_t* neighbourOffset, uint8_t* diagOffset)
+{
+    std::vector<label> nPerCell(nC, 1);
+    for (label f = 0; f < nI; ++f) { ++nPerCell[own[f]]; ++nPerCell[nei[f]]; }
+    rowOffs[0] = 0; // segmentsFromIntervals (core/segmentedVector.hpp:26-50): exclusive scan
+    for (label c = 0; c < nC; ++c) rowOffs[c + 1] = rowOffs[c] + nPerCell[c];
+    std::fill(nPerCell.begin(), nPerCell.end(), 0);
+    for (label f = 0; f < nI; ++f)
+    {
+        label n = nei[f], o = own[f];
+        label seg = nPerCell[n]++;
+        neighbourOffset[f] = static_cast<uint8_t>(seg);
+        colIdxs[rowOffs[n] + seg] = o;
+    }
+    for (label c = 0; c < nC; ++c)
+    {
+        label nFaces = nPerCell[c];
+        diagOffset[c] = static_cast<uint8_t>(nFaces);
+        colIdxs[rowOffs[c] + nFaces] = c;
+        nPerCell[c] = nFaces + 1;
+    }
+    for (label f = 0; f < nI; ++f)
+    {
+        label n = nei[f], o = own[f];
+        uint8_t seg = static_cast<uint8_t>(nPerCell[o]++);
+        ownerOffset[f] = seg;
+        colIdxs[rowOffs[o] + seg] = n;
+    }
+}
+
+// cellToFaceStencil.cpp:14-96: count, fill (own, nei interleaved per face, then boundary), sort per cell
+void fvo_cell_to_face_stencil(int32_t nC, int32_t nI, int32_t nB, const int32_t* own, const int32_t* nei,
+                              const int32_t* faceCells, int32_t* segments, int32_t* values)
+{
+    std::vector<label> n(nC, 0);
+    for (label f = 0; f < nI; ++f) { ++n[own[f]]; ++n[nei[f]]; }
+    for (label b = 0; b < nB; ++b) ++n[faceCells[b]];
+    segments[0] = 0;
+    for (label c = 0; c < nC; ++c) segments[c + 1] = segments[c] + n[c];
+    std::fill(n.begin(), n.end(), 0);
+    for (label f = 0; f < nI; ++f)
+    {
+        label o = own[f], ne = nei[f];
+        label so = n[o]++;
+        label sn = n[ne]++;
+        values[segments[o] + so] = f;
+        values[segments[ne] + sn] = f;
+    }
+    for (label f = nI; f < nI + nB; ++f)
+    {
+        label o = faceCells[f - nI];
+        values[segments[o] + n[o]++] = f;
+    }
+    for (label c = 0; c < nC; ++c) std::sort(values + segments[c], values + segments[c + 1]);
+}
+
+void fvo_interpolate_s(int par, int scheme, int32_t nI, int32_t nB, const int32_t* own, const int32_t* nei,
+                       const double* w, const double* flux, const double* src, const double* bvalue, double* dst)
+{
+    if (scheme == 0) linearInterpolate(par, nI, nB, own, nei, w, src, bvalue, dst);
+    else upwindInterpolate(par, nI, nB, own, nei, w, flux, src, bvalue, dst);
+}
+void fvo_interpolate_v(int par, int scheme, int32_t nI, int32_t nB, const int32_t* own, const int32_t* nei,
+                       const double* w, const double* flux, const double* src, const double* bvalue, double* dst)
+{
+    auto s = reinterpret_cast<const Vec3*>(src);
+    auto b = reinterpret_cast<const Vec3*>(bvalue);
+    auto d = reinterpret_cast<Vec3*>(dst);
+    if (scheme == 0) linearInterpolate(par, nI, nB, own, nei, w, s, b, d);
+    else upwindInterpolate(par, nI, nB, own, nei, w, flux, s, b, d);
+}
+// upwind.cpp:59-93
+void fvo_upwind_weights(int32_t nI, int32_t nB, const double* flux, double* wFace, double* wB)
+{
+    for (label f = 0; f < nI + nB; ++f)
+    {
+        if (f < nI) wFace[f] = flux[f] >= 0 ? 1 : 0;
+        else { wB[f - nI] = 1.0; wFace[f] = 1.0; }
+    }
+}
+void fvo_face_normal_grad_s(int par, int32_t nI, int32_t nB, const int32_t* own, const int32_t* nei,
+                            const int32_t* faceCells, const double* nodc, const double* phi, const double* bvalue,
+                            double* phif)
+{
+    faceNormalGrad(par, nI, nB, own, nei, faceCells, nodc, phi, bvalue, phif);
+}
+void fvo_face_normal_grad_v(int par, int32_t nI, int32_t nB, const int32_t* own, const int32_t* nei,
+                            const int32_t* faceCells, const double* nodc, const double* phi, const double* bvalue,
+                            double* phif)
+{
+    faceNormalGrad(par, nI, nB, own, nei, faceCells, nodc, reinterpret_cast<const Vec3*>(phi),
+                   reinterpret_cast<const Vec3*>(bvalue), reinterpret_cast<Vec3*>(phif));
+}
+
+// res is accumulated into and then scaled as a whole (reference semantics); callers zero it.
+void fvo_div_s(int par, int scheme, int32_t nC, int32_t nI, int32_t nB, const int32_t* own, const int32_t* nei,
+               const int32_t* faceCells, const double* V, const double* w, const double* faceFlux, const double* phi,
+               const double* bvalue, double coeff, const double* coeffView, double* res)
+{
+    divExp<double>(par, scheme, nC, nI, nB, own, nei, faceCells, V, w, faceFlux, phi, bvalue, Coeff {coeff, coeffView}, res);
+}
+void fvo_div_v(int par, int scheme, int32_t nC, int32_t nI, int32_t nB, const int32_t* own, const int32_t* nei,
+               const int32_t* faceCells, const double* V, const double* w, const double* faceFlux, const double* phi,
+               const double* bvalue, double coeff, const double* coeffView, double* res)
+{
+    divExp<Vec3>(par, scheme, nC, nI, nB, own, nei, faceCells, V, w, faceFlux, reinterpret_cast<const Vec3*>(phi),
+                 reinterpret_cast<const Vec3*>(bvalue), Coeff {coeff, coeffView}, reinterpret_cast<Vec3*>(res));
+}
+// gaussGreenGrad.cpp:18-71 (always linear; faceAreas indexed over all nF faces; scale 1/V)
+void fvo_grad_s(int par, int32_t nC, int32_t nI, int32_t nB, const int32_t* own, const int32_t* nei,
+                const int32_t* faceCells, const double* V, const double* w, const double* Sf_, const double* phi,
+                const double* bvalue, double* res)
+{
+    const Vec3* Sf = reinterpret_cast<const Vec3*>(Sf_);
+    std::vector<double> phif(size_t(nI) + nB);
+    linearInterpolate(par, nI, nB, own, nei, w, phi, bvalue, phif.data());
+    scatterAndScale<Vec3>(par, nC, nI, nB, own, nei, faceCells, [&](label f) { return Sf[f] * phif[f]; },
+                          [&](label c) { return 1 / V[c]; }, reinterpret_cast<Vec3*>(res));
+}
+void fvo_laplacian_s(int par, int32_t nC, int32_t nI, int32_t nB, const int32_t* own, const int32_t* nei,
+                     const int32_t* faceCells, const double* V, const double* magSf, const double* nodc,
+                     const double* phi, const double* bvalue, double coeff, const double* coeffView, double* res)
+{
+    laplacianExp<double>(par, nC, nI, nB, own, nei, faceCells, V, magSf, nodc, phi, bvalue, Coeff {coeff, coeffView}, res);
+}
+void fvo_laplacian_v(int par, int32_t nC, int32_t nI, int32_t nB, const int32_t* own, const int32_t* nei,
+                     const int32_t* faceCells, const double* V, const double* magSf, const double* nodc,
+                     const double* phi, const double* bvalue, double coeff, const double* coeffView, double* res)
+{
+    laplacianExp<Vec3>(par, nC, nI, nB, own, nei, faceCells, V, magSf, nodc, reinterpret_cast<const Vec3*>(phi),
+                       reinterpret_cast<const Vec3*>(bvalue), Coeff {coeff, coeffView}, reinterpret_cast<Vec3*>(res));
+}
+void fvo_surface_integrate_s(int par, int32_t nC, int32_t nI, int32_t nB, const int32_t* own, const int32_t* nei,
+                             const int32_t* faceCells, const double* V, const double* flux, double coeff,
+                             const double* coeffView, double* res)
+{
+    Coeff cf {coeff, coeffView};
+    scatterAndScale<double>(par, nC, nI, nB, own, nei, faceCells, [&](label f) { return flux[f]; },
+                            [&](label c) { return cf[c] / V[c]; }, res);
+}
+void fvo_surface_integrate_v(int par, int32_t nC, int32_t nI, int32_t nB, const int32_t* own, const int32_t* nei,
+                             const int32_t* faceCells, const double* V, const double* flux_, double coeff,
+                             const double* coeffView, double* res)
+{
+    Coeff cf {coeff, coeffView};
+    const Vec3* flux = reinterpret_cast<const Vec3*>(flux_);
+    scatterAndScale<Vec3>(par, nC, nI, nB, own, nei, faceCells, [&](label f) { return flux[f]; },
+                          [&](label c) { return cf[c] / V[c]; }, reinterpret_cast<Vec3*>(res));
+}
+
+// coNum.cpp:18-96. out[0] = maxCoNum, out[1] = meanCoNum
+void fvo_conum(int par, int32_t nC, int32_t nI, int32_t nB, const int32_t* own, const int32_t* nei,
+               const int32_t* faceCells, const double* V, const double* faceFlux, double dt, double* out)
+{
+    std::vector<double> phi(nC, 0.0);
+    if (!par)
+    {
+        for (label f = 0; f < nI; ++f)
+        {
+            double flux = std::sqrt(faceFlux[f] * faceFlux[f]);
+            phi[own[f]] += flux;
+            phi[nei[f]] += flux;
+        }
+        for (label f = nI; f < nI + nB; ++f) phi[faceCells[f - nI]] += std::sqrt(faceFlux[f] * faceFlux[f]);
+    }
+    else
+    {
+        PFOR(1, f, 0, nI)
+        {
+            double flux = std::sqrt(faceFlux[f] * faceFlux[f]);
+            atomic_add(&phi[own[f]], flux);
+            atomic_add(&phi[nei[f]], flux);
+        }
+        PFOR(1, f, nI, nI + nB) { atomic_add(&phi[faceCells[f - nI]], std::sqrt(faceFlux[f] * faceFlux[f])); }
+    }
+    double maxValue = 0.0, totalPhi = 0.0, totalVol = 0.0;
+    // Kokkos::Max reducer starts from the identity (lowest); the local 0.0 initialiser is overwritten
+    maxValue = -1.7976931348623157e308;
+#pragma omp parallel for reduction(max : maxValue) if (par)
+    for (label c = 0; c < nC; ++c) { double v = phi[c] / V[c]; if (v > maxValue) maxValue = v; }
+#pragma omp parallel for reduction(+ : totalPhi) if (par)
+    for (label c = 0; c < nC; ++c) totalPhi += phi[c];
+#pragma omp parallel for reduction(+ : totalVol) if (par)
+    for (label c = 0; c < nC; ++c) totalVol += V[c];
+    out[0] = maxValue * 0.5 * dt;
+    out[1] = 0.5 * (totalPhi / totalVol) * dt;
+}
+
+// ---- implicit ----------------------------------------------------------------------------------------
+#define IMP_ARGS                                                                                   \
+    int32_t nI, int32_t nB, const int32_t *own, const int32_t *nei, const int32_t *faceCells,      \
+        const int32_t *rowOffs, const uint8_t *diagOffs, const uint8_t *ownOffs, const uint8_t *neiOffs
+
+void fvo_div_imp_s(int par, IMP_ARGS, const double* faceFlux, const double* weights, const double* bweights,
+                   const double* bDeltaCoeffs, const double* valueFraction, const double* refValue, const double* refGrad,
+                   double coeff, const double* coeffView, double* values, double* rhs, double* bcMatrix, double* bcRhs)
+{
+    divImp<double>(par, nI, nB, own, nei, faceCells, rowOffs, diagOffs, ownOffs, neiOffs, faceFlux, weights, bweights,
+                   bDeltaCoeffs, valueFraction, refValue, refGrad, Coeff {coeff, coeffView}, values, rhs, bcMatrix, bcRhs);
+}
+void fvo_div_imp_v(int par, IMP_ARGS, const double* faceFlux, const double* weights, const double* bweights,
+                   const double* bDeltaCoeffs, const double* valueFraction, const double* refValue, const double* refGrad,
+                   double coeff, const double* coeffView, double* values, double* rhs, double* bcMatrix, double* bcRhs)
+{
+    divImp<Vec3>(par, nI, nB, own, nei, faceCells, rowOffs, diagOffs, ownOffs, neiOffs, faceFlux, weights, bweights,
+                 bDeltaCoeffs, valueFraction, reinterpret_cast<const Vec3*>(refValue), reinterpret_cast<const Vec3*>(refGrad),
+                 Coeff {coeff, coeffView}, reinterpret_cast<Vec3*>(values), reinterpret_cast<Vec3*>(rhs),
+                 reinterpret_cast<Vec3*>(bcMatrix), reinterpret_cast<Vec3*>(bcRhs));
+}
+void fvo_laplacian_imp_s(int par, IMP_ARGS, const double* gamma, const double* nodc, const double* magSf,
+                         const double* valueFraction, const double* refValue, const double* refGrad, double coeff,
+                         const double* coeffView, double* values, double* rhs, double* bcMatrix, double* bcRhs)
+{
+    laplacianImp<double>(par, nI, nB, own, nei, faceCells, rowOffs, diagOffs, ownOffs, neiOffs, gamma, nodc, magSf,
+                         valueFraction, refValue, refGrad, Coeff {coeff, coeffView}, values, rhs, bcMatrix, bcRhs);
+}
+void fvo_laplacian_imp_v(int par, IMP_ARGS, const double* gamma, const double* nodc, const double* magSf,
+                         const double* valueFraction, const double* refValue, const double* refGrad, double coeff,
+                         const double* coeffView, double* values, double* rhs, double* bcMatrix, double* bcRhs)
+{
+    laplacianImp<Vec3>(par, nI, nB, own, nei, faceCells, rowOffs, diagOffs, ownOffs, neiOffs, gamma, nodc, magSf,
+                       valueFraction, reinterpret_cast<const Vec3*>(refValue), reinterpret_cast<const Vec3*>(refGrad),
+                       Coeff {coeff, coeffView}, reinterpret_cast<Vec3*>(values), reinterpret_cast<Vec3*>(rhs),
+                       reinterpret_cast<Vec3*>(bcMatrix), reinterpret_cast<Vec3*>(bcRhs));
+}
+void fvo_ddt_imp_s(int par, int32_t nC, const int32_t* rowOffs, const uint8_t* diagOffs, const double* V,
+                   const double* oldField, double dt, double coeff, const double* coeffView, double* values, double* rhs)
+{
+    ddtImp<double>(par, nC, rowOffs, diagOffs, V, oldField, dt, Coeff {coeff, coeffView}, values, rhs);
+}
+void fvo_ddt_imp_v(int par, int32_t nC, const int32_t* rowOffs, const uint8_t* diagOffs, const double* V,
+                   const double* oldField, double dt, double coeff, const double* coeffView, double* values, double* rhs)
+{
+    ddtImp<Vec3>(par, nC, rowOffs, diagOffs, V, reinterpret_cast<const Vec3*>(oldField), dt, Coeff {coeff, coeffView},
+                 reinterpret_cast<Vec3*>(values), reinterpret_cast<Vec3*>(rhs));
+}
+void fvo_ddt_exp_s(int par, int32_t nC, const double* V, const double* field, const double* oldField, double dt, double* source)
+{
+    ddtExp<double>(par, nC, V, field, oldField, dt, source);
+}
+void fvo_ddt_exp_v(int par, int32_t nC, const double* V, const double* field, const double* oldField, double dt, double* source)
+{
+    ddtExp<Vec3>(par, nC, V, reinterpret_cast<const Vec3*>(field), reinterpret_cast<const Vec3*>(oldField), dt,
+                 reinterpret_cast<Vec3*>(source));
+}
+void fvo_source_imp_s(int par, int32_t nC, const int32_t* rowOffs, const uint8_t* diagOffs, const double* V,
+                      const double* k, double coeff, const double* coeffView, double* values)
+{
+    sourceImp<double>(par, nC, rowOffs, diagOffs, V, k, Coeff {coeff, coeffView}, values);
+}
+void fvo_source_imp_v(int par, int32_t nC, const int32_t* rowOffs, const uint8_t* diagOffs, const double* V,
+                      const double* k, double coeff, const double* coeffView, double* values)
+{
+    sourceImp<Vec3>(par, nC, rowOffs, diagOffs, V, k, Coeff {coeff, coeffView}, reinterpret_cast<Vec3*>(values));
+}
+void fvo_source_exp_s(int par, int32_t nC, const double* k, const double* field, double coeff, const double* coeffView, double* source)
+{
+    sourceExp<double>(par, nC, k, field, Coeff {coeff, coeffView}, source);
+}
+void fvo_source_exp_v(int par, int32_t nC, const double* k, const double* field, double coeff, const double* coeffView, double* source)
+{
+    sourceExp<Vec3>(par, nC, k, reinterpret_cast<const Vec3*>(field), Coeff {coeff, coeffView}, reinterpret_cast<Vec3*>(source));
+}
+
+void fvo_correct_bcs_s(int32_t nPatches, const int32_t* offsets, const int32_t* kind, const double* cst,
+                       const int32_t* faceCells, const double* bDeltaCoeffs, const double* internal, double* value,
+                       double* refValue, double* valueFraction, double* refGrad)
+{
+    correctBCs<double>(nPatches, offsets, kind, cst, faceCells, bDeltaCoeffs, internal, value, refValue, valueFraction, refGrad);
+}
+void fvo_correct_bcs_v(int32_t nPatches, const int32_t* offsets, const int32_t* kind, const double* cst,
+                       const int32_t* faceCells, const double* bDeltaCoeffs, const double* internal, double* value,
+                       double* refValue, double* valueFraction, double* refGrad)
+{
+    correctBCs<Vec3>(nPatches, offsets, kind, reinterpret_cast<const Vec3*>(cst), faceCells, bDeltaCoeffs,
+                     reinterpret_cast<const Vec3*>(internal), reinterpret_cast<Vec3*>(value), reinterpret_cast<Vec3*>(refValue),
+                     valueFraction, reinterpret_cast<Vec3*>(refGrad));
+}
+
+// ---- linear algebra ------------------------------------------------------------------------------------
+// computeResidual (src/NeoN/src/linearAlgebra/utilities.cpp:11-35): res = A x - b
+void fvo_residual(int par, int32_t n, const int32_t* rowOffs, const int32_t* colIdxs, const double* values,
+                  const double* b, const double* x, double* res)
+{
+    PFOR(par, r, 0, n)
+    {
+        double sum = 0.0;
+        for (label k = rowOffs[r]; k < rowOffs[r + 1]; ++k) sum += values[k] * x[colIdxs[k]];
+        res[r] = sum - b[r];
+    }
+}
+void fvo_spmv(int par, int32_t n, const int32_t* rowOffs, const int32_t* colIdxs, const double* values,
+              const double* x, double* y)
+{
+    PFOR(par, r, 0, n)
+    {
+        double sum = 0.0;
+        for (label k = rowOffs[r]; k < rowOffs[r + 1]; ++k) sum += values[k] * x[colIdxs[k]];
+        y[r] = sum;
+    }
+}
+
+// Ginkgo 1.10 solver::Cg with optional scalar-Jacobi preconditioner, restated from the published
+// algorithm (third party; call site src/NeoN/include/NeoN/linearAlgebra/ginkgo.hpp:116-155):
+//   r = b - A x; z = p = q = 0; rho_prev = 1
+//   loop: z = M^-1 r; rho = r.z; stop if iter>=maxIter or ||r|| <= rel*||b|| or ||r|| <= abs;
+//         p = z + (rho/rho_prev) p; q = A p; beta = p.q; alpha = rho/beta; x += alpha p; r -= alpha q
+// stats[0] = numIter, stats[1] = initResNorm (= ||b||, the reference's quirk, ginkgo.hpp:143-144),
+// stats[2] = finalResNorm (= ||r|| at stop). history (may be NULL) receives ||r|| at each check
+// (history[0] = ||r0||), up to maxHist entries. Returns the number of history entries written.
+int fvo_cg(int par, int jacobi, int32_t n, const int32_t* rowOffs, const int32_t* colIdxs, const double* values,
+           const double* b, double* x, int maxIter, double relTol, double absTol, double* stats, double* history,
+           int maxHist)
+{
+    std::vector<double> r(n), z(n), p(n, 0.0), q(n, 0.0), dinv(n, 1.0);
+    auto dotp = [&](const double* a, const double* c) {
+        double s = 0.0;
+#pragma omp parallel for reduction(+ : s) if (par)
+        for (label i = 0; i < n; ++i) s += a[i] * c[i];
+        return s;
+    };
+    if (jacobi)
+        for (label i = 0; i < n; ++i)
+            for (label k = rowOffs[i]; k < rowOffs[i + 1]; ++k)
+                if (colIdxs[k] == i) dinv[i] = 1.0 / values[k];
+    fvo_spmv(par, n, rowOffs, colIdxs, values, x, r.data());
+    PFOR(par, i, 0, n) { r[i] = b[i] - r[i]; }
+    const double normB = std::sqrt(dotp(b, b));
+    double rhoPrev = 1.0;
+    int iter = 0, nh = 0;
+    double normR = 0.0;
+    while (true)
+    {
+        PFOR(par, i, 0, n) { z[i] = jacobi ? r[i] * dinv[i] : r[i]; }
+        const double rho = dotp(r.data(), z.data());
+        normR = std::sqrt(dotp(r.data(), r.data()));
+        if (history && nh < maxHist) history[nh++] = normR;
+        if (iter >= maxIter || normR <= relTol * normB || normR <= absTol) break;
+        const double bt = rho / rhoPrev;
+        PFOR(par, i, 0, n) { p[i] = z[i] + bt * p[i]; }
+        fvo_spmv(par, n, rowOffs, colIdxs, values, p.data(), q.data());
+        const double pq = dotp(p.data(), q.data());
+        const double alpha = rho / pq;
+        PFOR(par, i, 0, n) { x[i] += alpha * p[i]; r[i] -= alpha * q[i]; }
+        rhoPrev = rho;
+        ++iter;
+    }
+    stats[0] = iter; stats[1] = normB; stats[2] = normR;
+    return nh;
+}
+
+// ---- PISO glue (FoamAdapter src/algorithms/pressureVelocityCoupling.cpp) ---------------------------------
+// computeRAU :38-63 : rAU = V / diag[0] of the Vec3 momentum matrix
+void fvo_rAU(int32_t nC, const int32_t* rowOffs, const uint8_t* diagOffs, const double* V, const double* valuesV,
+             double* rAU)
+{
+    const Vec3* values = reinterpret_cast<const Vec3*>(valuesV);
+    for (label c = 0; c < nC; ++c) rAU[c] = V[c] / (values[rowOffs[c] + diagOffs[c]].c[0]);
+}
+// computeRAUandHByA :65-128 (internal part; BC correction by the caller)
+void fvo_HbyA(int par, int32_t nC, int32_t nI, const int32_t* own, const int32_t* nei, const int32_t* rowOffs,
+              const uint8_t* ownOffs, const uint8_t* neiOffs, const double* V, const double* valuesV, const double* rhsV,
+              const double* rAU, const double* U_, double* HbyA_)
+{
+    const Vec3* values = reinterpret_cast<const Vec3*>(valuesV);
+    const Vec3* rhs = reinterpret_cast<const Vec3*>(rhsV);
+    const Vec3* U = reinterpret_cast<const Vec3*>(U_);
+    Vec3* H = reinterpret_cast<Vec3*>(HbyA_);
+    for (label c = 0; c < nC; ++c) H[c] = zero<Vec3>();
+    if (!par)
+        for (label f = 0; f < nI; ++f)
+        {
+            label o = own[f], n = nei[f];
+            Vec3 lower = values[rowOffs[n] + neiOffs[f]];
+            Vec3 upper = values[rowOffs[o] + ownOffs[f]];
+            H[n] -= lower.c[0] * U[o];
+            H[o] -= upper.c[0] * U[n];
+        }
+    else
+        PFOR(1, f, 0, nI)
+        {
+            label o = own[f], n = nei[f];
+            Vec3 lower = values[rowOffs[n] + neiOffs[f]];
+            Vec3 upper = values[rowOffs[o] + ownOffs[f]];
+            atomic_sub(&H[n], lower.c[0] * U[o]);
+            atomic_sub(&H[o], upper.c[0] * U[n]);
+        }
+    PFOR(par, c, 0, nC)
+    {
+        H[c] += rhs[c];
+        H[c] *= rAU[c] / V[c];
+    }
+}
+// flux :215-267 : Sf & (w (U_P - U_N) + U_N); boundary bSf & U_b
+void fvo_flux(int par, int32_t nI, int32_t nB, const int32_t* own, const int32_t* nei, const double* w, const double* Sf_,
+              const double* bSf_, const double* U_, const double* Ub_, double* faceFlux, double* bvalue)
+{
+    const Vec3* Sf = reinterpret_cast<const Vec3*>(Sf_);
+    const Vec3* bSf = reinterpret_cast<const Vec3*>(bSf_);
+    const Vec3* U = reinterpret_cast<const Vec3*>(U_);
+    const Vec3* Ub = reinterpret_cast<const Vec3*>(Ub_);
+    PFOR(par, f, 0, nI) { faceFlux[f] = dot(Sf[f], w[f] * (U[own[f]] - U[nei[f]]) + U[nei[f]]); }
+    PFOR(par, f, nI, nI + nB)
+    {
+        faceFlux[f] = dot(bSf[f - nI], Ub[f - nI]);
+        bvalue[f - nI] = dot(bSf[f - nI], Ub[f - nI]);
+    }
+}
+// updateFaceVelocity :131-197
+void fvo_update_face_velocity(int par, int32_t nI, int32_t nB, const int32_t* own, const int32_t* nei,
+                              const int32_t* faceCells, const int32_t* rowOffs, const uint8_t* ownOffs,
+                              const uint8_t* neiOffs, const double* values, const double* bcMatrix, const double* bcRhs,
+                              const double* p, const double* predPhi, const double* predPhiB, double* phi, double* phiB)
+{
+    PFOR(par, f, 0, nI)
+    {
+        label o = own[f], n = nei[f];
+        double upper = values[rowOffs[n] + neiOffs[f]];
+        double lower = values[rowOffs[o] + ownOffs[f]];
+        phi[f] = predPhi[f] - (upper * p[n] - lower * p[o]);
+    }
+    PFOR(par, f, nI, nI + nB)
+    {
+        label b = f - nI;
+        double bflux = (bcRhs[b] - bcMatrix[b] * p[faceCells[b]]);
+        phi[f] = predPhi[f] - bflux;
+        phiB[b] = predPhiB[b] - bflux;
+    }
+}
+// updateVelocity :199-213 (gradP computed by the caller with fvo_grad_s)
+void fvo_update_velocity(int par, int32_t nC, const double* HbyA_, const double* rAU, const double* gradP_, double* U_)
+{
+    const Vec3* H = reinterpret_cast<const Vec3*>(HbyA_);
+    const Vec3* g = reinterpret_cast<const Vec3*>(gradP_);
+    Vec3* U = reinterpret_cast<Vec3*>(U_);
+    PFOR(par, c, 0, nC) { U[c] = H[c] - rAU[c] * g[c]; }
+}
+// PDESolver::SetReference (include/FoamAdapter/datastructures/expression.hpp:86-112)
+void fvo_set_reference(int32_t refCell, double refValue, const int32_t* rowOffs, const uint8_t* diagOffs, double* values,
+                       double* rhs)
+{
+    label idx = rowOffs[refCell] + diagOffs[refCell];
+    double d = values[idx];
+    rhs[refCell] += d * refValue;
+    values[idx] += d;
+}
+// dsl/solver.hpp:73-77 : rhs -= expSource * V
+void fvo_rhs_sub_source(int par, int32_t nC, const double* V, const double* src, double* rhs)
+{
+    PFOR(par, c, 0, nC) { rhs[c] -= src[c] * V[c]; }
+}
+
+} // extern "C"
