@@ -42,6 +42,10 @@ struct S3 // Vec3 field, AoS
 // internal(f, own, nei) is the value the reference adds to res[own] and subtracts from res[nei];
 // boundary(f, b, own) is the value added to res[own] for boundary face f = nI + b.
 
+// Split interface used by the batched kernel: cell(c) loads what the thread's own cell contributes,
+// load(f, other) issues the raw loads of one internal face (nothing else), flux(face, cell, side) is the
+// signed value to ADD to the cell's sum: side 0 = the cell owns the face (+flux with own = cell,
+// nei = other), side 1 = the cell is the neighbour (-flux with own = other, nei = cell).
 template <class VT, int SCHEME>
 struct DivOp // gaussGreenDiv.cpp:46-67 with linear.cpp:30-45 / upwind.cpp:32-55
 {
@@ -51,6 +55,27 @@ struct DivOp // gaussGreenDiv.cpp:46-67 with linear.cpp:30-45 / upwind.cpp:32-55
     const double* __restrict__ w;
     const double* __restrict__ phi;
     const double* __restrict__ phiB;
+    struct Face { double F, w; T pO; };
+    __device__ __forceinline__ T cell(int c) const { return VT::ld(phi, c); }
+    __device__ __forceinline__ Face load(int f, int other) const
+    {
+        Face r;
+        r.F = faceFlux[f];
+        r.w = (SCHEME == FVK_LINEAR) ? w[f] : 0.0;
+        r.pO = VT::ld(phi, other);
+        return r;
+    }
+    __device__ __forceinline__ T flux(const Face& fd, const T& pc, bool side) const
+    {
+        const T pOwn = side ? fd.pO : pc, pNei = side ? pc : fd.pO;
+        T phif;
+        if (SCHEME == FVK_LINEAR)
+            phif = VT::add(VT::mul(fd.w, pOwn), VT::mul(1 - fd.w, pNei));
+        else
+            phif = (fd.F >= 0) ? pOwn : pNei;
+        const T fl = VT::mul(fd.F, phif);
+        return side ? VT::sub(VT::zero(), fl) : fl;
+    }
     __device__ __forceinline__ T internal(int f, int own, int nei) const
     {
         const double F = faceFlux[f];
@@ -81,6 +106,16 @@ struct GradOp // gaussGreenGrad.cpp:46-64 with linear.cpp:30-45
     const double* __restrict__ w;
     const double* __restrict__ phi;
     const double* __restrict__ phiB;
+    struct Face { Vec3d s; double w, pO; };
+    __device__ __forceinline__ double cell(int c) const { return phi[c]; }
+    __device__ __forceinline__ Face load(int f, int other) const { return Face {ld3(Sf, f), w[f], phi[other]}; }
+    __device__ __forceinline__ T flux(const Face& fd, double pc, bool side) const
+    {
+        const double pOwn = side ? fd.pO : pc, pNei = side ? pc : fd.pO;
+        const double phif = fd.w * pOwn + (1 - fd.w) * pNei;
+        const Vec3d fl {fd.s.x * phif, fd.s.y * phif, fd.s.z * phif};
+        return side ? Vec3d {0.0 - fl.x, 0.0 - fl.y, 0.0 - fl.z} : fl;
+    }
     __device__ __forceinline__ T internal(int f, int own, int nei) const
     {
         const double wf = w[f];
@@ -105,6 +140,15 @@ struct LaplacianOp // gaussGreenLaplacian.cpp:34-52 with uncorrected.cpp:34-51
     const double* __restrict__ dc; // nonOrthDeltaCoeffs
     const double* __restrict__ phi;
     const double* __restrict__ phiB;
+    struct Face { double a, d; T pO; };
+    __device__ __forceinline__ T cell(int c) const { return VT::ld(phi, c); }
+    __device__ __forceinline__ Face load(int f, int other) const { return Face {magSf[f], dc[f], VT::ld(phi, other)}; }
+    __device__ __forceinline__ T flux(const Face& fd, const T& pc, bool side) const
+    {
+        const T pOwn = side ? fd.pO : pc, pNei = side ? pc : fd.pO;
+        const T fl = VT::mul(fd.a, VT::mul(fd.d, VT::sub(pNei, pOwn)));
+        return side ? VT::sub(VT::zero(), fl) : fl;
+    }
     __device__ __forceinline__ T internal(int f, int own, int nei) const
     {
         const T sn = VT::mul(dc[f], VT::sub(VT::ld(phi, nei), VT::ld(phi, own)));
@@ -122,9 +166,16 @@ struct SurfIntOp // surfaceIntegrate.cpp:26-41
 {
     using V = VT;
     using T = typename VT::T;
-    const double* __restrict__ flux;
-    __device__ __forceinline__ T internal(int f, int, int) const { return VT::ld(flux, f); }
-    __device__ __forceinline__ T boundary(int f, int, int) const { return VT::ld(flux, f); }
+    const double* __restrict__ flux_;
+    struct Face { T v; };
+    __device__ __forceinline__ int cell(int) const { return 0; }
+    __device__ __forceinline__ Face load(int f, int) const { return Face {VT::ld(flux_, f)}; }
+    __device__ __forceinline__ T flux(const Face& fd, int, bool side) const
+    {
+        return side ? VT::sub(VT::zero(), fd.v) : fd.v;
+    }
+    __device__ __forceinline__ T internal(int f, int, int) const { return VT::ld(flux_, f); }
+    __device__ __forceinline__ T boundary(int f, int, int) const { return VT::ld(flux_, f); }
 };
 
 // ---- scaling + store ---------------------------------------------------------------------------
@@ -152,7 +203,7 @@ __device__ __forceinline__ void finish(double* __restrict__ out, int c, typename
 }
 // NOTE: res[c] *= s in the reference is (res * s); mul(s, acc) is the same product (commutative).
 
-// ---- variant 0: unified sorted stencil ------------------------------------------------------------
+// ---- variant 0 (default): unified sorted stencil, one face in flight per thread ------------------------------------------------------------
 template <class Op>
 __global__ void __launch_bounds__(256)
 k_gather_stencil(Op op, Scaling sc, int nC, int nI, const int* __restrict__ seg,
@@ -183,104 +234,48 @@ k_gather_stencil(Op op, Scaling sc, int nC, int nI, const int* __restrict__ seg,
     finish<VT>(out, c, acc, sc.at(c), mode);
 }
 
-// ---- split plan for owner-sorted meshes (OpenFOAM upper-triangular order) --------------------------
-// lower faces (cell is the neighbour; their ids are below every owned face) ascending, then the
-// contiguous owned faces, then boundary faces -- together ascending face id.
-struct SplitPlan
-{
-    const int* __restrict__ lowSeg;
-    const int* __restrict__ lowFace;
-    const int* __restrict__ lowOwner;
-    const int* __restrict__ ownStart;
-    const int* __restrict__ neighbour;
-    const unsigned* __restrict__ hasBnd;
-    int nBndCells;
-    const int* __restrict__ bndCell;
-    const int* __restrict__ bndSeg;
-    const int* __restrict__ bndFace;
-};
-
-template <class Op>
-__device__ __forceinline__ typename Op::T boundary_sum(const Op& op, const SplitPlan& pl, int c, int nI, typename Op::T acc)
-{
-    using VT = typename Op::V;
-    if ((pl.hasBnd[c >> 5] >> (c & 31)) & 1u)
-    {
-        int lo = 0, hi = pl.nBndCells - 1;
-        while (lo < hi)
-        {
-            const int mid = (lo + hi) >> 1;
-            if (pl.bndCell[mid] < c) lo = mid + 1; else hi = mid;
-        }
-        const int b1 = pl.bndSeg[lo + 1];
-        for (int e = pl.bndSeg[lo]; e < b1; ++e)
-        {
-            const int f = pl.bndFace[e];
-            acc = VT::add(acc, op.boundary(f, f - nI, c));
-        }
-    }
-    return acc;
-}
-
-// variant 2: plain loops (one face in flight per thread)
-template <class Op>
-__global__ void __launch_bounds__(256)
-k_gather_split_simple(Op op, Scaling sc, int nC, int nI, SplitPlan pl, double* __restrict__ out, int mode)
-{
-    using VT = typename Op::V;
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= nC) return;
-    typename VT::T acc = (mode == FVK_ACC_SCALE) ? VT::ld(out, c) : VT::zero();
-    const int l0 = pl.lowSeg[c], l1 = pl.lowSeg[c + 1];
-    const int f0 = pl.ownStart[c], f1 = pl.ownStart[c + 1];
-    for (int e = l0; e < l1; ++e) acc = VT::sub(acc, op.internal(pl.lowFace[e], pl.lowOwner[e], c));
-    for (int f = f0; f < f1; ++f) acc = VT::add(acc, op.internal(f, c, pl.neighbour[f]));
-    acc = boundary_sum(op, pl, c, nI, acc);
-    finish<VT>(out, c, acc, sc.at(c), mode);
-}
-
-// variant 0 (default): the first CH lower and CH owned faces are fetched as one batch of independent,
-// predicated loads (memory-level parallelism: all index loads, then all data loads in flight
-// together), then folded in ascending face order; longer lists fall back to chunked loops.
-template <class Op, int CH>
-__global__ void __launch_bounds__(256)
-k_gather_split(Op op, Scaling sc, int nC, int nI, SplitPlan pl, double* __restrict__ out, int mode)
+// ---- variants 1-4: packed plan, U faces in flight per thread -----------------------------------
+// plan entry (8 B, one coalescable load): x = (faceId << 1) | side for internal faces (side 1: the cell is
+// the face's neighbour), x = -(b + 1) for boundary face b; y = the other cell. Each iteration fetches U
+// entries, then issues all their face/cell loads back to back (branch-free, padded lanes re-read the last
+// valid entry), then folds the signed fluxes in ascending face order. Compared with the plain loop this
+// removes one dependent load level (no owner[]/neighbour[] lookup) and multiplies the bytes in flight per
+// thread by U, which is what a latency-bound gather needs to approach the HBM roofline.
+template <class Op, int U>
+__global__ void __launch_bounds__(256, (U >= 6 ? 3 : 4))
+k_gather_plan(Op op, Scaling sc, int nC, int nI, const int* __restrict__ seg, const int2* __restrict__ plan,
+              double* __restrict__ out, int mode)
 {
     using VT = typename Op::V;
     using T = typename VT::T;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nC) return;
     T acc = (mode == FVK_ACC_SCALE) ? VT::ld(out, c) : VT::zero();
-    const int l0 = pl.lowSeg[c], l1 = pl.lowSeg[c + 1];
-    const int f0 = pl.ownStart[c], f1 = pl.ownStart[c + 1];
+    const int e0 = seg[c], e1 = seg[c + 1];
     const double s = sc.at(c);
-    // straight-line, branch-free batch: indices first, then data. Padding lanes read a clamped,
-    // valid (and cached) entry whose flux is computed but never summed.
-    const int last = nI - 1; // nI > 0 guaranteed by the launcher
-    T fl[CH], fo[CH];
-    int lf[CH], lo[CH], ff[CH], nn[CH];
-#pragma unroll
-    for (int k = 0; k < CH; ++k)
+    const auto cd = op.cell(c);
+    for (int e = e0; e < e1; e += U)
     {
-        const int e = min(l0 + k, last);
-        lf[k] = pl.lowFace[e];
-        lo[k] = pl.lowOwner[e];
-        ff[k] = min(f0 + k, last);
-        nn[k] = pl.neighbour[ff[k]];
+        int2 pe[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) pe[k] = plan[min(e + k, e1 - 1)];
+        typename Op::Face fd[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) fd[k] = op.load(pe[k].x < 0 ? 0 : (pe[k].x >> 1), pe[k].y);
+        T v[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) v[k] = op.flux(fd[k], cd, (pe[k].x & 1) != 0);
+#pragma unroll
+        for (int k = 0; k < U; ++k)
+        {
+            if (pe[k].x < 0)
+            {
+                const int b = -pe[k].x - 1;
+                v[k] = op.boundary(nI + b, b, c);
+            }
+            if (e + k < e1) acc = VT::add(acc, v[k]);
+        }
     }
-#pragma unroll
-    for (int k = 0; k < CH; ++k) fl[k] = op.internal(lf[k], lo[k], c);
-#pragma unroll
-    for (int k = 0; k < CH; ++k) fo[k] = op.internal(ff[k], c, nn[k]);
-#pragma unroll
-    for (int k = 0; k < CH; ++k)
-        if (l0 + k < l1) acc = VT::sub(acc, fl[k]);
-    for (int e = l0 + CH; e < l1; ++e) acc = VT::sub(acc, op.internal(pl.lowFace[e], pl.lowOwner[e], c));
-#pragma unroll
-    for (int k = 0; k < CH; ++k)
-        if (f0 + k < f1) acc = VT::add(acc, fo[k]);
-    for (int f = f0 + CH; f < f1; ++f) acc = VT::add(acc, op.internal(f, c, pl.neighbour[f]));
-    acc = boundary_sum(op, pl, c, nI, acc);
     finish<VT>(out, c, acc, s, mode);
 }
 
@@ -290,22 +285,21 @@ int launch_gather(const fvk_mesh* m, Op op, Scaling sc, double* out, int mode, f
     if (mode != FVK_SET && mode != FVK_ACC_SCALE && mode != FVK_ADD)
         return fvk_fail(FVK_EINVAL, "bad mode %d", mode);
     const int nC = m->nCells;
+    const int nI = m->nInternalFaces;
     const int grid = (nC + 255) / 256;
-    const int variant = fvk_variant();
-    const SplitPlan pl {m->lowSeg, m->lowFace, m->lowOwner, m->ownStart, m->neighbour, m->hasBnd,
-                        m->nBndCells, m->bndCell, m->bndSeg, m->bndFace};
-    if (m->ownerSorted && m->nInternalFaces > 0 && (variant == 0 || variant == 3))
+    const int variant = (nI == 0) ? 0 : fvk_variant(); // the plan kernels read face 0 on padded lanes
+    const int2* plan = reinterpret_cast<const int2*>(m->gatherPlan);
+    cudaStream_t st = fvk_cu(stream);
+    switch (variant)
     {
-        if (variant == 0)
-            k_gather_split<Op, 3><<<grid, 256, 0, fvk_cu(stream)>>>(op, sc, nC, m->nInternalFaces, pl, out, mode);
-        else
-            k_gather_split<Op, 4><<<grid, 256, 0, fvk_cu(stream)>>>(op, sc, nC, m->nInternalFaces, pl, out, mode);
+        case 1: k_gather_plan<Op, 3><<<grid, 256, 0, st>>>(op, sc, nC, nI, m->stencilSeg, plan, out, mode); break;
+        case 2: k_gather_plan<Op, 2><<<grid, 256, 0, st>>>(op, sc, nC, nI, m->stencilSeg, plan, out, mode); break;
+        case 3: k_gather_plan<Op, 6><<<grid, 256, 0, st>>>(op, sc, nC, nI, m->stencilSeg, plan, out, mode); break;
+        case 4: k_gather_plan<Op, 1><<<grid, 256, 0, st>>>(op, sc, nC, nI, m->stencilSeg, plan, out, mode); break;
+        default: // measured best at 256^3 (profiles/r1_roofline_*.jsonl): full occupancy, 32 registers
+            k_gather_stencil<Op><<<grid, 256, 0, st>>>(op, sc, nC, nI, m->stencilSeg, m->gatherEnt, m->owner, m->neighbour, out, mode);
+            break;
     }
-    else if (m->ownerSorted && (variant == 2 || (m->nInternalFaces == 0 && variant != 1)))
-        k_gather_split_simple<Op><<<grid, 256, 0, fvk_cu(stream)>>>(op, sc, nC, m->nInternalFaces, pl, out, mode);
-    else
-        k_gather_stencil<Op><<<grid, 256, 0, fvk_cu(stream)>>>(
-            op, sc, nC, m->nInternalFaces, m->stencilSeg, m->gatherEnt, m->owner, m->neighbour, out, mode);
     FVK_LAUNCH_CHECK();
     return FVK_OK;
 }

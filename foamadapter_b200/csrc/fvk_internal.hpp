@@ -28,6 +28,8 @@ struct fvk_mesh
     int32_t *stencilSeg = nullptr, *stencilVal = nullptr;
     // gather plan: entry = (faceId << 1) | (cell is the face's neighbour), same order as stencilVal
     int32_t* gatherEnt = nullptr;
+    // same order, 8 bytes per entry: {(faceId << 1) | side, other cell}; boundary face b: {-(b + 1), own cell}
+    int32_t* gatherPlan = nullptr;
     // SparsityPattern
     int32_t *rowOffs = nullptr, *colIdxs = nullptr;
     uint8_t *ownerOffset = nullptr, *neighbourOffset = nullptr, *diagOffset = nullptr;

@@ -198,7 +198,7 @@ extern "C" int fvk_mesh_destroy(fvk_mesh* m)
     void* ptrs[] = {m->V, m->C, m->Sf, m->Cf, m->magSf, m->owner, m->neighbour, m->faceCells, m->bCf,
                     m->bCn, m->bSf, m->bMagSf, m->bNf, m->bDelta, m->bWeights, m->bDeltaCoeffs,
                     m->weights, m->deltaCoeffs, m->nonOrthDeltaCoeffs, m->stencilSeg, m->stencilVal,
-                    m->gatherEnt, m->rowOffs, m->colIdxs, m->ownerOffset, m->neighbourOffset,
+                    m->gatherEnt, m->gatherPlan, m->rowOffs, m->colIdxs, m->ownerOffset, m->neighbourOffset,
                     m->diagOffset, m->ownStart, m->lowSeg, m->lowFace, m->lowOwner, m->bndCell,
                     m->bndSeg, m->bndFace, m->hasBnd};
     for (void* p : ptrs)
@@ -273,22 +273,26 @@ extern "C" int fvk_mesh_create(const fvk_mesh_desc* d, fvk_mesh** out)
         for (int32_t b = 0; b < nB; ++b) ++seg[size_t(d->faceCells[b]) + 1];
         for (int32_t c = 0; c < nC; ++c) seg[size_t(c) + 1] += seg[c];
         const size_t nEnt = size_t(seg[nC]);
-        std::vector<int32_t> val(nEnt), ent(nEnt), pos(seg.begin(), seg.end() - 1);
+        std::vector<int32_t> val(nEnt), ent(nEnt), plan(2 * nEnt), pos(seg.begin(), seg.end() - 1);
         for (int32_t f = 0; f < nI; ++f)
         {
             int32_t k = pos[own[f]]++;
             val[k] = f; ent[k] = f << 1;
+            plan[2 * size_t(k)] = f << 1; plan[2 * size_t(k) + 1] = nei[f];
             k = pos[nei[f]]++;
             val[k] = f; ent[k] = (f << 1) | 1;
+            plan[2 * size_t(k)] = (f << 1) | 1; plan[2 * size_t(k) + 1] = own[f];
         }
         for (int32_t b = 0; b < nB; ++b)
         {
             const int32_t k = pos[d->faceCells[b]]++;
             val[k] = nI + b; ent[k] = (nI + b) << 1;
+            plan[2 * size_t(k)] = -(b + 1); plan[2 * size_t(k) + 1] = d->faceCells[b];
         }
         UP(stencilSeg, seg.data(), seg.size());
         UP(stencilVal, val.data(), nEnt);
         UP(gatherEnt, ent.data(), nEnt);
+        UP(gatherPlan, plan.data(), 2 * nEnt);
     }
     // ---- sparsity pattern: row = [lower (face order) | diag | upper (face order)]
     {

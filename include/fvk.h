@@ -232,6 +232,67 @@ int fvk_correct_boundary_conditions(const fvk_mesh* mesh, int ncomp, const int32
                                     double* bRefValue, double* bValueFraction, double* bRefGrad,
                                     fvk_stream stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Implicit assembly into LinearSystem<scalar|Vec3, localIdx> (values T[nnz], rhs T[nCells]) over the
+ * mesh's SparsityPattern, plus the BoundaryCoefficients arrays (linearSystem.hpp:36-43).
+ *
+ * One fused kernel assembles an ordered list of terms; row c is written by one thread, each entry
+ * exactly once, with the accumulation order of applying the reference operators one after another
+ * (Expression::implicitOperation: spatial operators in insertion order, then temporal,
+ * src/NeoN/include/NeoN/dsl/expression.hpp:80-101; timeIntegration/backwardEuler.hpp:49-50).
+ *   FVK_TERM_DDT        DdtOperator::implicitOperation   (operators/ddtOperator.cpp:38-60)
+ *                       cellField = old-time field (T[nCells]), dt
+ *   FVK_TERM_DIV        computeDivImp                    (operators/gaussGreenDiv.cpp:155-262)
+ *                       faceField = faceFlux [nFaces], scheme = FVK_LINEAR | FVK_UPWIND
+ *   FVK_TERM_LAPLACIAN  computeLaplacianImpl             (operators/gaussGreenLaplacian.cpp:76-177)
+ *                       faceField = gamma [nFaces]
+ *   FVK_TERM_SOURCE     SourceTerm::implicitOperation    (operators/sourceTerm.cpp:37-55)
+ *                       cellField = coefficients (double[nCells])
+ * coeff/coeffView = the operator's dsl::Coeff (a subtracted operator carries coeff = -1,
+ * dsl/expression.hpp:207-224).
+ * accumulate = 0: write a fresh system (replaces createEmptyLinearSystem's zero-fill + the operators);
+ * accumulate = 1: add to the existing values/rhs (an operator applied to a non-empty system).
+ * bcMatrix/bcRhs [nBoundaryFaces] receive the boundary coefficients of the LAST div/laplacian term
+ * (each reference operator overwrites them, gaussGreenDiv.cpp:251,258).
+ * ---------------------------------------------------------------------------------------------- */
+enum { FVK_TERM_DDT = 0, FVK_TERM_DIV = 1, FVK_TERM_LAPLACIAN = 2, FVK_TERM_SOURCE = 3 };
+#define FVK_MAX_TERMS 6
+typedef struct fvk_term {
+    int32_t kind;
+    int32_t scheme;
+    double coeff;
+    const double* coeffView; /* [nCells] or NULL */
+    const double* faceField; /* div: faceFlux, laplacian: gamma; [nFaces] */
+    const double* cellField; /* ddt: old field T[nCells]; source: coefficients double[nCells] */
+    double dt;
+} fvk_term;
+/* BoundaryData of the unknown field (fields/boundaryData.hpp:32-215), device pointers */
+typedef struct fvk_bfield {
+    const double* value;         /* T[nB] */
+    const double* refValue;      /* T[nB] */
+    const double* valueFraction; /* double[nB] */
+    const double* refGrad;       /* T[nB] */
+} fvk_bfield;
+int fvk_assemble_s(const fvk_mesh* mesh, int nTerms, const fvk_term* terms_h, const fvk_bfield* bd,
+                   double* values, double* rhs, double* bcMatrix, double* bcRhs, int accumulate,
+                   fvk_stream stream);
+int fvk_assemble_v(const fvk_mesh* mesh, int nTerms, const fvk_term* terms_h, const fvk_bfield* bd,
+                   double* values, double* rhs, double* bcMatrix, double* bcRhs, int accumulate,
+                   fvk_stream stream);
+/* BoundaryCoefficients::matrixIdxs / rhsIdxs as createEmptyLinearSystem fills them
+ * (linearSystem.hpp:163-174; matrixIdxs = celli + diagOffset[celli], sic). */
+int fvk_bc_coeff_indices(const fvk_mesh* mesh, int32_t* matrixIdxs, int32_t* rhsIdxs,
+                         fvk_stream stream);
+/* DdtOperator::explicitOperation (ddtOperator.cpp:21-36): source += (field - old)/dt * V */
+int fvk_ddt_explicit(const fvk_mesh* mesh, int ncomp, const double* field, const double* oldField,
+                     double dt, double* source, fvk_stream stream);
+/* SourceTerm::explicitOperation (sourceTerm.cpp:22-35): source += coeff * k * field */
+int fvk_source_explicit(const fvk_mesh* mesh, int ncomp, const double* k, const double* field,
+                        double coeff, const double* coeffView, double* source, fvk_stream stream);
+/* dsl::solve (dsl/solver.hpp:73-77): rhs -= explicitSource * V */
+int fvk_rhs_sub_source(const fvk_mesh* mesh, int ncomp, const double* src, double* rhs,
+                       fvk_stream stream);
+
 /* experiment switch: selects the kernel variant used by the gather operators
  * (0 = default). Used by the roofline harness only. */
 int fvk_set_variant(int variant);
