@@ -1,0 +1,562 @@
+// Linear algebra of the pressure solve: CSR SpMV, BLAS-1, and the Jacobi-preconditioned CG that
+// NeoN::la::Solver delegates to Ginkgo (src/NeoN/include/NeoN/linearAlgebra/ginkgo.hpp:116-155,
+// src/NeoN/src/linearAlgebra/utilities.cpp:11-35, src/NeoN/src/core/vector/vectorFreeFunctions.cpp).
+//
+// SpMV: a persistent grid walks tiles of 256 rows. A tile's values/colIdxs range is contiguous in
+// CSR, so the block streams it with fully coalesced loads, multiplies by the gathered x and parks the
+// products in shared memory; then thread r adds up row r's products in ascending entry order -- the
+// summation order of the reference's row loop, so y is bit-identical to the Serial executor.
+// CG: two kernels per iteration, every scalar (rho, alpha, beta, norms, stop flag) lives in a device
+// struct, reductions are two-stage (warp shuffle -> block partial -> last block folds the partials in
+// a fixed order), so a solve is bit-reproducible run to run and needs no host round trip per iteration.
+#include "fvk_device.cuh"
+
+#include <cmath>
+#include <cstring>
+
+namespace
+{
+constexpr int TB = 256;          // threads per block
+constexpr int SPMV_ROWS = 256;   // rows per tile
+constexpr int SPMV_CAP = 2304;   // products staged per pass (18 KB)
+constexpr int MAX_GRID = 148 * 8;
+
+struct PcgState
+{
+    double rho, rhoPrev, alpha, beta, pq, rr, normB, normR;
+    double sums[4]; // local (pre-allreduce) partial results: [0] r.z  [1] r.r  [2] p.q  [3] b.b
+    double relTol, absTol;
+    int iter, done, nHist, maxHist, maxIter, pad;
+};
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum of NV values per thread; result valid in thread 0.
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* sh /* [NV*8] */)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+    {
+        v[k] = warp_sum(v[k]);
+        if (lane == 0) sh[k * 8 + wid] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+#pragma unroll
+        for (int k = 0; k < NV; ++k)
+        {
+            double s = sh[k * 8];
+            for (int w = 1; w < TB / 32; ++w) s += sh[k * 8 + w];
+            v[k] = s;
+        }
+    }
+}
+
+// Grid-wide deterministic sum: every block deposits its NV partials; the last block to arrive folds
+// all of them in index order (independent of arrival order) and returns true in ALL its threads with
+// the totals in out[] (thread 0 only).
+template <int NV>
+__device__ __forceinline__ bool grid_sum(double (&v)[NV], double* __restrict__ partial, unsigned* __restrict__ counter,
+                                         double (&out)[NV])
+{
+    __shared__ double sh[NV * 8];
+    __shared__ bool last;
+    block_sum<NV>(v, sh);
+    if (threadIdx.x == 0)
+    {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) partial[size_t(k) * MAX_GRID + blockIdx.x] = v[k];
+        __threadfence();
+        const unsigned t = atomicAdd(counter, 1u);
+        last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return false;
+    __threadfence();
+    double acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+    {
+        acc[k] = 0.0;
+        for (int i = threadIdx.x; i < int(gridDim.x); i += TB) acc[k] += __ldcg(&partial[size_t(k) * MAX_GRID + i]);
+    }
+    __syncthreads(); // sh reuse
+    block_sum<NV>(acc, sh);
+    if (threadIdx.x == 0)
+    {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) out[k] = acc[k];
+        *counter = 0u;
+    }
+    return true;
+}
+
+// ---- stopping rule + scalar updates (Ginkgo CG) ----------------------------------
+__device__ __forceinline__ void decide_after_update(PcgState* st, double* __restrict__ hist)
+{
+    // sums[0] = r.z, sums[1] = r.r (global)
+    st->rho = st->sums[0];
+    st->rr = st->sums[1];
+    const double normR = sqrt(st->sums[1]);
+    st->normR = normR;
+    if (hist && st->nHist < st->maxHist) hist[st->nHist++] = normR;
+    if (st->iter >= st->maxIter || normR <= st->relTol * st->normB || normR <= st->absTol)
+        st->done = 1;
+    else
+        st->beta = st->rho / st->rhoPrev;
+}
+__device__ __forceinline__ void decide_after_spmv(PcgState* st)
+{
+    st->pq = st->sums[2];
+    st->alpha = st->rho / st->sums[2];
+    st->rhoPrev = st->rho;
+    st->iter += 1;
+}
+__global__ void k_decide_after_update(PcgState* st, double* hist)
+{
+    if (st->done) return;
+    decide_after_update(st, hist);
+}
+__global__ void k_decide_after_spmv(PcgState* st)
+{
+    if (st->done) return;
+    decide_after_spmv(st);
+}
+__global__ void k_set_normB(PcgState* st) { st->normB = sqrt(st->sums[3]); }
+
+// ---- K1: x += alpha p; r -= alpha q; z = M^-1 r; r.z; r.r ------------------------------------------
+template <bool FIRST, bool JACOBI>
+__global__ void __launch_bounds__(TB)
+k_cg_update(int n, PcgState* __restrict__ st, double* __restrict__ x, const double* __restrict__ p,
+            const double* __restrict__ q, double* __restrict__ r, const double* __restrict__ dinv,
+            double* __restrict__ z, double* __restrict__ partial, unsigned* __restrict__ counter,
+            double* __restrict__ hist, int distributed)
+{
+    if (st->done) return;
+    const double alpha = FIRST ? 0.0 : st->alpha;
+    double acc[2] = {0.0, 0.0};
+    for (int i = blockIdx.x * TB + threadIdx.x; i < n; i += gridDim.x * TB)
+    {
+        double ri = r[i];
+        if (!FIRST)
+        {
+            x[i] = x[i] + alpha * p[i];
+            ri = ri - alpha * q[i];
+            r[i] = ri;
+        }
+        const double zi = JACOBI ? ri * dinv[i] : ri;
+        z[i] = zi;
+        acc[0] += ri * zi;
+        acc[1] += ri * ri;
+    }
+    double tot[2];
+    if (grid_sum<2>(acc, partial, counter, tot) && threadIdx.x == 0)
+    {
+        st->sums[0] = tot[0];
+        st->sums[1] = tot[1];
+        if (!distributed) decide_after_update(st, hist);
+    }
+}
+
+// p = z + beta p on the owned rows (distributed path: followed by a halo exchange of p)
+__global__ void __launch_bounds__(TB)
+k_cg_pupdate(int n, const PcgState* __restrict__ st, const double* __restrict__ z, double* __restrict__ p)
+{
+    if (st->done) return;
+    const double beta = st->beta;
+    for (int i = blockIdx.x * TB + threadIdx.x; i < n; i += gridDim.x * TB) p[i] = z[i] + beta * p[i];
+}
+
+// ---- tiled CSR SpMV ----------------------------------------------------------------------------
+// MODE 0: y = A x            (fvk_spmv)
+// MODE 1: y = A x - b        (computeResidual)
+// MODE 2: y = b - A x        (CG start-up r0)
+// MODE 3: CG: q = A p, dot p.q, scalar update; p read from `x`
+// MODE 4: CG fused: pNew = z + beta pOld evaluated on the fly for the gathered columns, q = A pNew
+template <int MODE>
+__global__ void __launch_bounds__(TB)
+k_spmv(int nRows, const int* __restrict__ rowOffs, const int* __restrict__ colIdxs, const double* __restrict__ values,
+       const double* __restrict__ x, const double* __restrict__ b, double* __restrict__ y, PcgState* __restrict__ st,
+       const double* __restrict__ z, double* __restrict__ pNew, double* __restrict__ partial,
+       unsigned* __restrict__ counter, int distributed)
+{
+    __shared__ double prod[SPMV_CAP];
+    __shared__ int ro[SPMV_ROWS + 1];
+    double beta = 0.0;
+    if (MODE >= 3)
+    {
+        if (st->done) return;
+        beta = st->beta;
+    }
+    double acc[1] = {0.0};
+    const int nTiles = (nRows + SPMV_ROWS - 1) / SPMV_ROWS;
+    for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x)
+    {
+        const int r0 = tile * SPMV_ROWS;
+        const int nr = min(SPMV_ROWS, nRows - r0);
+        __syncthreads(); // previous tile done with ro/prod
+        for (int i = threadIdx.x; i <= nr; i += TB) ro[i] = rowOffs[r0 + i];
+        __syncthreads();
+        const int base = ro[0], end = ro[nr];
+        const bool hasRow = threadIdx.x < nr;
+        int k = hasRow ? ro[threadIdx.x] : 0;
+        const int kend = hasRow ? ro[threadIdx.x + 1] : 0;
+        double sum = 0.0;
+        for (int cb = base; cb < end; cb += SPMV_CAP)
+        {
+            const int ce = min(end, cb + SPMV_CAP);
+            if (cb != base) __syncthreads();
+#pragma unroll 4
+            for (int e = cb + threadIdx.x; e < ce; e += TB)
+            {
+                const int j = colIdxs[e];
+                const double xv = (MODE == 4) ? (z[j] + beta * x[j]) : x[j];
+                prod[e - cb] = ld_stream(values + e) * xv;
+            }
+            __syncthreads();
+            const int ke = min(kend, ce);
+            for (; k < ke; ++k) sum += prod[k - cb];
+        }
+        if (hasRow)
+        {
+            const int r = r0 + threadIdx.x;
+            if (MODE == 0) y[r] = sum;
+            if (MODE == 1) y[r] = sum - b[r];
+            if (MODE == 2) y[r] = b[r] - sum;
+            if (MODE == 3)
+            {
+                y[r] = sum;
+                acc[0] += x[r] * sum;
+            }
+            if (MODE == 4)
+            {
+                const double pr = z[r] + beta * x[r];
+                pNew[r] = pr;
+                y[r] = sum;
+                acc[0] += pr * sum;
+            }
+        }
+    }
+    if (MODE >= 3)
+    {
+        double tot[1];
+        if (grid_sum<1>(acc, partial, counter, tot) && threadIdx.x == 0)
+        {
+            st->sums[2] = tot[0];
+            if (!distributed) decide_after_spmv(st);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TB)
+k_extract_dinv(int n, const int* __restrict__ rowOffs, const int* __restrict__ colIdxs, const double* __restrict__ values,
+               double* __restrict__ dinv)
+{
+    const int r = blockIdx.x * TB + threadIdx.x;
+    if (r >= n) return;
+    double d = 1.0;
+    for (int k = rowOffs[r]; k < rowOffs[r + 1]; ++k)
+        if (colIdxs[k] == r) d = 1.0 / values[k];
+    dinv[r] = d;
+}
+
+// ---- BLAS-1 --------------------------------------------------------------------------------------
+enum { OP_FILL, OP_SCALE, OP_ADD, OP_SUB, OP_MUL, OP_AXPBY };
+template <int OP>
+__global__ void __launch_bounds__(TB)
+k_vec(int64_t n, double a, double bb, double* __restrict__ x, const double* __restrict__ y)
+{
+    for (int64_t i = int64_t(blockIdx.x) * TB + threadIdx.x; i < n; i += int64_t(gridDim.x) * TB)
+    {
+        if (OP == OP_FILL) x[i] = a;
+        if (OP == OP_SCALE) x[i] = x[i] * a;
+        if (OP == OP_ADD) x[i] = x[i] + y[i];
+        if (OP == OP_SUB) x[i] = x[i] - y[i];
+        if (OP == OP_MUL) x[i] = x[i] * y[i];
+        if (OP == OP_AXPBY) x[i] = a * y[i] + bb * x[i]; // here x is the output `y` of fvk_vec_axpby
+    }
+}
+
+template <bool NORM>
+__global__ void __launch_bounds__(TB)
+k_dot(int64_t n, const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ result,
+      double* __restrict__ partial, unsigned* __restrict__ counter)
+{
+    double acc[1] = {0.0};
+    for (int64_t i = int64_t(blockIdx.x) * TB + threadIdx.x; i < n; i += int64_t(gridDim.x) * TB) acc[0] += x[i] * y[i];
+    double tot[1];
+    if (grid_sum<1>(acc, partial, counter, tot) && threadIdx.x == 0) result[0] = NORM ? sqrt(tot[0]) : tot[0];
+}
+
+int stream_grid(int64_t n, int perThread = 4)
+{
+    int64_t g = (n + int64_t(TB) * perThread - 1) / (int64_t(TB) * perThread);
+    const int cap = min(MAX_GRID, fvk_sm_count() * 8);
+    if (g > cap) g = cap;
+    return g < 1 ? 1 : int(g);
+}
+int spmv_grid(int nRows)
+{
+    const int tiles = (nRows + SPMV_ROWS - 1) / SPMV_ROWS;
+    const int cap = min(MAX_GRID, fvk_sm_count() * 8);
+    return tiles < 1 ? 1 : (tiles < cap ? tiles : cap);
+}
+
+// per-device scratch of the stand-alone reductions (fvk_dot / fvk_norm2)
+struct RedScratch
+{
+    double* partial = nullptr;
+    unsigned* counter = nullptr;
+};
+int get_scratch(RedScratch** out)
+{
+    static RedScratch tab[64];
+    int dev = 0;
+    FVK_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fvk_fail(FVK_EUNSUPPORTED, "device index %d", dev);
+    RedScratch& s = tab[dev];
+    if (!s.partial)
+    {
+        FVK_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.partial), sizeof(double) * 4 * MAX_GRID));
+        FVK_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.counter), sizeof(unsigned)));
+        FVK_CUDA(cudaMemset(s.counter, 0, sizeof(unsigned)));
+    }
+    *out = &s;
+    return FVK_OK;
+}
+} // namespace
+
+// comm hooks implemented in fvk_comm.cu
+int fvk_comm_allreduce_sum_impl(fvk_comm* comm, double* data_d, int count, cudaStream_t st);
+int fvk_comm_halo_exchange_impl(fvk_comm* comm, double* field_d, int ncomp, cudaStream_t st);
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" int fvk_spmv(int32_t nRows, const int32_t* rowOffs, const int32_t* colIdxs, const double* values,
+                        const double* x, double* y, fvk_stream s)
+{
+    if (nRows < 0 || !rowOffs || (nRows && (!colIdxs || !values || !x || !y))) return fvk_fail(FVK_EINVAL, "fvk_spmv: bad argument");
+    if (nRows == 0) return FVK_OK;
+    k_spmv<0><<<spmv_grid(nRows), TB, 0, fvk_cu(s)>>>(nRows, rowOffs, colIdxs, values, x, nullptr, y, nullptr, nullptr,
+                                                      nullptr, nullptr, nullptr, 0);
+    FVK_LAUNCH_CHECK();
+    return FVK_OK;
+}
+extern "C" int fvk_residual(int32_t nRows, const int32_t* rowOffs, const int32_t* colIdxs, const double* values,
+                            const double* b, const double* x, double* res, fvk_stream s)
+{
+    if (nRows < 0 || !rowOffs || (nRows && (!colIdxs || !values || !x || !b || !res)))
+        return fvk_fail(FVK_EINVAL, "fvk_residual: bad argument");
+    if (nRows == 0) return FVK_OK;
+    k_spmv<1><<<spmv_grid(nRows), TB, 0, fvk_cu(s)>>>(nRows, rowOffs, colIdxs, values, x, b, res, nullptr, nullptr,
+                                                      nullptr, nullptr, nullptr, 0);
+    FVK_LAUNCH_CHECK();
+    return FVK_OK;
+}
+
+#define VEC_OP(OP, a, b, x, y)                                                                     \
+    do                                                                                             \
+    {                                                                                              \
+        if (n < 0 || (n && !(x))) return fvk_fail(FVK_EINVAL, "%s: bad argument", __func__);       \
+        if (n == 0) return FVK_OK;                                                                 \
+        k_vec<OP><<<stream_grid(n), TB, 0, fvk_cu(s)>>>(n, a, b, x, y);                            \
+        FVK_LAUNCH_CHECK();                                                                        \
+        return FVK_OK;                                                                             \
+    } while (0)
+
+extern "C" int fvk_vec_fill(int64_t n, double v, double* x, fvk_stream s) { VEC_OP(OP_FILL, v, 0.0, x, nullptr); }
+extern "C" int fvk_vec_scale(int64_t n, double a, double* x, fvk_stream s) { VEC_OP(OP_SCALE, a, 0.0, x, nullptr); }
+extern "C" int fvk_vec_add(int64_t n, double* x, const double* y, fvk_stream s)
+{
+    if (n && !y) return fvk_fail(FVK_EINVAL, "fvk_vec_add: null");
+    VEC_OP(OP_ADD, 0.0, 0.0, x, y);
+}
+extern "C" int fvk_vec_sub(int64_t n, double* x, const double* y, fvk_stream s)
+{
+    if (n && !y) return fvk_fail(FVK_EINVAL, "fvk_vec_sub: null");
+    VEC_OP(OP_SUB, 0.0, 0.0, x, y);
+}
+extern "C" int fvk_vec_mul(int64_t n, double* x, const double* y, fvk_stream s)
+{
+    if (n && !y) return fvk_fail(FVK_EINVAL, "fvk_vec_mul: null");
+    VEC_OP(OP_MUL, 0.0, 0.0, x, y);
+}
+extern "C" int fvk_vec_axpby(int64_t n, double a, const double* x, double b, double* y, fvk_stream s)
+{
+    if (n && !x) return fvk_fail(FVK_EINVAL, "fvk_vec_axpby: null");
+    VEC_OP(OP_AXPBY, a, b, y, x);
+}
+
+extern "C" int fvk_dot(int64_t n, const double* x, const double* y, double* result_d, fvk_stream s)
+{
+    if (n < 0 || !result_d || (n && (!x || !y))) return fvk_fail(FVK_EINVAL, "fvk_dot: bad argument");
+    RedScratch* sc = nullptr;
+    if (int rc = get_scratch(&sc)) return rc;
+    k_dot<false><<<stream_grid(n), TB, 0, fvk_cu(s)>>>(n, x, y, result_d, sc->partial, sc->counter);
+    FVK_LAUNCH_CHECK();
+    return FVK_OK;
+}
+extern "C" int fvk_norm2(int64_t n, const double* x, double* result_d, fvk_stream s)
+{
+    if (n < 0 || !result_d || (n && !x)) return fvk_fail(FVK_EINVAL, "fvk_norm2: bad argument");
+    RedScratch* sc = nullptr;
+    if (int rc = get_scratch(&sc)) return rc;
+    k_dot<true><<<stream_grid(n), TB, 0, fvk_cu(s)>>>(n, x, x, result_d, sc->partial, sc->counter);
+    FVK_LAUNCH_CHECK();
+    return FVK_OK;
+}
+
+// ---- solver ---------------------------------------------------------------------------------------
+struct fvk_solver
+{
+    int32_t nRows = 0, nCols = 0;
+    fvk_solver_config cfg {};
+    fvk_comm* comm = nullptr;
+    double *r = nullptr, *z = nullptr, *p0 = nullptr, *p1 = nullptr, *q = nullptr, *dinv = nullptr;
+    double *partial = nullptr, *hist = nullptr;
+    unsigned* counter = nullptr;
+    PcgState* state = nullptr;
+    PcgState* state_h = nullptr; // pinned
+    int32_t histCap = 0;
+};
+
+extern "C" int fvk_solver_destroy(fvk_solver* sv)
+{
+    if (!sv) return FVK_OK;
+    for (void* ptr : {(void*) sv->r, (void*) sv->z, (void*) sv->p0, (void*) sv->p1, (void*) sv->q, (void*) sv->dinv,
+                      (void*) sv->partial, (void*) sv->hist, (void*) sv->counter, (void*) sv->state})
+        if (ptr) cudaFree(ptr);
+    if (sv->state_h) cudaFreeHost(sv->state_h);
+    delete sv;
+    return FVK_OK;
+}
+
+extern "C" int fvk_solver_create(int32_t nRows, int32_t nCols, const fvk_solver_config* cfg, fvk_comm* comm, fvk_solver** out)
+{
+    if (!cfg || !out || nRows <= 0 || nCols < nRows) return fvk_fail(FVK_EINVAL, "fvk_solver_create: bad argument");
+    if (cfg->maxIter < 0 || cfg->checkEvery < 1 || (cfg->preconditioner != FVK_PRECOND_NONE && cfg->preconditioner != FVK_PRECOND_JACOBI))
+        return fvk_fail(FVK_EINVAL, "fvk_solver_create: bad configuration");
+    *out = nullptr;
+    fvk_solver* sv = new fvk_solver;
+    sv->nRows = nRows; sv->nCols = nCols; sv->cfg = *cfg; sv->comm = comm;
+    sv->histCap = cfg->maxIter + 2;
+    cudaError_t e = cudaSuccess;
+    auto A = [&](double** ptr, size_t n) { if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(ptr), sizeof(double) * n); };
+    A(&sv->r, nRows); A(&sv->z, nCols); A(&sv->p0, nCols); A(&sv->p1, nCols); A(&sv->q, nRows); A(&sv->dinv, nRows);
+    A(&sv->partial, 4 * MAX_GRID); A(&sv->hist, sv->histCap);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&sv->counter), sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMemset(sv->counter, 0, sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&sv->state), sizeof(PcgState));
+    if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&sv->state_h), sizeof(PcgState));
+    if (e != cudaSuccess)
+    {
+        fvk_solver_destroy(sv);
+        return fvk_fail(e == cudaErrorNoDevice ? FVK_ENODEVICE : FVK_ECUDA, "fvk_solver_create: %s", cudaGetErrorString(e));
+    }
+    *out = sv;
+    return FVK_OK;
+}
+
+extern "C" int fvk_solver_solve(fvk_solver* sv, const int32_t* rowOffs, const int32_t* colIdxs, const double* values,
+                                const double* b, double* x, fvk_solver_stats* stats_h, double* history_h,
+                                int32_t maxHistory, fvk_stream s)
+{
+    if (!sv || !rowOffs || !colIdxs || !values || !b || !x || !stats_h) return fvk_fail(FVK_EINVAL, "fvk_solver_solve: null argument");
+    cudaStream_t st = fvk_cu(s);
+    const int n = sv->nRows;
+    const bool dist = sv->comm != nullptr;
+    const bool jacobi = sv->cfg.preconditioner == FVK_PRECOND_JACOBI;
+    const int gV = stream_grid(n), gS = spmv_grid(n);
+    const int wantHist = (history_h && maxHistory > 0) ? (maxHistory < sv->histCap ? maxHistory : sv->histCap) : 0;
+
+    PcgState init;
+    std::memset(&init, 0, sizeof(init));
+    init.rhoPrev = 1.0;
+    init.relTol = sv->cfg.relTol; init.absTol = sv->cfg.absTol;
+    init.maxIter = sv->cfg.maxIter; init.maxHist = wantHist;
+    *sv->state_h = init;
+    FVK_CUDA(cudaMemcpyAsync(sv->state, sv->state_h, sizeof(PcgState), cudaMemcpyHostToDevice, st));
+    FVK_CUDA(cudaMemsetAsync(sv->p0, 0, sizeof(double) * sv->nCols, st));
+    FVK_CUDA(cudaMemsetAsync(sv->p1, 0, sizeof(double) * sv->nCols, st));
+    FVK_CUDA(cudaMemsetAsync(sv->q, 0, sizeof(double) * n, st));
+    if (jacobi)
+    {
+        k_extract_dinv<<<(n + TB - 1) / TB, TB, 0, st>>>(n, rowOffs, colIdxs, values, sv->dinv);
+        FVK_LAUNCH_CHECK();
+    }
+    // ||b|| (the reference's "initial residual", ginkgo.hpp:143-144)
+    k_dot<false><<<gV, TB, 0, st>>>(n, b, b, &sv->state->sums[3], sv->partial, sv->counter);
+    FVK_LAUNCH_CHECK();
+    if (dist)
+    {
+        if (int rc = fvk_comm_allreduce_sum_impl(sv->comm, &sv->state->sums[3], 1, st)) return rc;
+        if (int rc = fvk_comm_halo_exchange_impl(sv->comm, x, 1, st)) return rc;
+    }
+    k_set_normB<<<1, 1, 0, st>>>(sv->state);
+    // r = b - A x
+    k_spmv<2><<<gS, TB, 0, st>>>(n, rowOffs, colIdxs, values, x, b, sv->r, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
+    FVK_LAUNCH_CHECK();
+
+    double* pCur = sv->p0;  // p of the previous iteration
+    double* pNext = sv->p1;
+    const int every = sv->cfg.checkEvery;
+    for (int it = 0; it <= sv->cfg.maxIter; ++it)
+    {
+        // K1
+        if (it == 0)
+        {
+            if (jacobi) k_cg_update<true, true><<<gV, TB, 0, st>>>(n, sv->state, x, pCur, sv->q, sv->r, sv->dinv, sv->z, sv->partial, sv->counter, sv->hist, dist);
+            else k_cg_update<true, false><<<gV, TB, 0, st>>>(n, sv->state, x, pCur, sv->q, sv->r, sv->dinv, sv->z, sv->partial, sv->counter, sv->hist, dist);
+        }
+        else
+        {
+            if (jacobi) k_cg_update<false, true><<<gV, TB, 0, st>>>(n, sv->state, x, pCur, sv->q, sv->r, sv->dinv, sv->z, sv->partial, sv->counter, sv->hist, dist);
+            else k_cg_update<false, false><<<gV, TB, 0, st>>>(n, sv->state, x, pCur, sv->q, sv->r, sv->dinv, sv->z, sv->partial, sv->counter, sv->hist, dist);
+        }
+        FVK_LAUNCH_CHECK();
+        if (dist)
+        {
+            if (int rc = fvk_comm_allreduce_sum_impl(sv->comm, &sv->state->sums[0], 2, st)) return rc;
+            k_decide_after_update<<<1, 1, 0, st>>>(sv->state, sv->hist);
+            k_cg_pupdate<<<gV, TB, 0, st>>>(n, sv->state, sv->z, pCur);
+            if (int rc = fvk_comm_halo_exchange_impl(sv->comm, pCur, 1, st)) return rc;
+            k_spmv<3><<<gS, TB, 0, st>>>(n, rowOffs, colIdxs, values, pCur, nullptr, sv->q, sv->state, nullptr, nullptr, sv->partial, sv->counter, 1);
+            FVK_LAUNCH_CHECK();
+            if (int rc = fvk_comm_allreduce_sum_impl(sv->comm, &sv->state->sums[2], 1, st)) return rc;
+            k_decide_after_spmv<<<1, 1, 0, st>>>(sv->state);
+        }
+        else
+        {
+            // K2 (fused): pNext = z + beta pCur, q = A pNext, p.q, alpha
+            k_spmv<4><<<gS, TB, 0, st>>>(n, rowOffs, colIdxs, values, pCur, nullptr, sv->q, sv->state, sv->z, pNext, sv->partial, sv->counter, 0);
+            FVK_LAUNCH_CHECK();
+            double* t = pCur; pCur = pNext; pNext = t;
+        }
+        if ((it + 1) % every == 0 || it == sv->cfg.maxIter)
+        {
+            FVK_CUDA(cudaMemcpyAsync(sv->state_h, sv->state, sizeof(PcgState), cudaMemcpyDeviceToHost, st));
+            FVK_CUDA(cudaStreamSynchronize(st));
+            if (sv->state_h->done) break;
+        }
+    }
+    if (!sv->state_h->done) return fvk_fail(FVK_ECUDA, "fvk_solver_solve: stop flag not raised after maxIter+1 checks");
+    stats_h->numIter = sv->state_h->iter;
+    stats_h->initResNorm = sv->state_h->normB;
+    stats_h->finalResNorm = sv->state_h->normR;
+    stats_h->nHistory = sv->state_h->nHist;
+    if (wantHist && sv->state_h->nHist > 0)
+    {
+        FVK_CUDA(cudaMemcpyAsync(history_h, sv->hist, sizeof(double) * sv->state_h->nHist, cudaMemcpyDeviceToHost, st));
+        FVK_CUDA(cudaStreamSynchronize(st));
+    }
+    return FVK_OK;
+}

@@ -1,0 +1,195 @@
+"""Python mirror of NeoN::la (src/NeoN/include/NeoN/linearAlgebra/{sparsityPattern,CSRMatrix,linearSystem,
+solver,utilities}.hpp): SparsityPattern, LinearSystem, Solver/SolverStats, computeResidual, spmv and the
+Vector free functions. Bodies call the C ABI (include/fvk.h); tensors are device-memory handles only."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import mesh as _m
+from . import ops
+from ._capi import check, lib, ptr
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class SparsityPattern:
+    """la::SparsityPattern (sparsityPattern.hpp:20-92); built once per mesh by fvk_mesh_create and cached there
+    like SparsityPattern::readOrCreate (sparsityPattern.cpp:11-19). Arrays are views of the handle's device memory."""
+
+    def __init__(self, mesh):
+        self.mesh = mesh
+        self.rowOffs_ptr, _ = mesh.device_array(_m.ROW_OFFS)
+        self.colIdxs_ptr, _ = mesh.device_array(_m.COL_IDXS)
+
+    @staticmethod
+    def readOrCreate(mesh):
+        if getattr(mesh, "_sparsity", None) is None:
+            mesh._sparsity = SparsityPattern(mesh)
+        return mesh._sparsity
+
+    def rowOffs(self): return self.mesh.to_host(_m.ROW_OFFS)
+    def colIdxs(self): return self.mesh.to_host(_m.COL_IDXS)
+    def ownerOffset(self): return self.mesh.to_host(_m.OWNER_OFFSET)
+    def neighbourOffset(self): return self.mesh.to_host(_m.NEIGHBOUR_OFFSET)
+    def diagOffset(self): return self.mesh.to_host(_m.DIAG_OFFSET)
+
+
+class LinearSystem:
+    """la::LinearSystem<scalar|Vec3, localIdx> + BoundaryCoefficients (linearSystem.hpp:36-186)."""
+
+    def __init__(self, mesh, ncomp=1, device="cuda", zero=True):
+        self.mesh, self.ncomp = mesh, ncomp
+        self.sp = SparsityPattern.readOrCreate(mesh)
+        mk = torch.zeros if zero else torch.empty
+        shp = (lambda n: (n, 3)) if ncomp == 3 else (lambda n: (n,))
+        self.values = mk(shp(mesh.nnz), dtype=torch.float64, device=device)
+        self.rhs = mk(shp(mesh.nCells), dtype=torch.float64, device=device)
+        self.bcMatrix = torch.zeros(shp(mesh.nBoundaryFaces), dtype=torch.float64, device=device)
+        self.bcRhs = torch.zeros(shp(mesh.nBoundaryFaces), dtype=torch.float64, device=device)
+
+    def reset(self):
+        self.values.zero_(); self.rhs.zero_()
+
+
+def createEmptyLinearSystem(mesh, ncomp=1):
+    """linearSystem.hpp:140-186."""
+    return LinearSystem(mesh, ncomp, zero=True)
+
+
+def spmv(sp: SparsityPattern, values, x, y=None, nRows=None):
+    n = nRows if nRows is not None else sp.mesh.nOwned
+    if y is None:
+        y = torch.empty(n, dtype=torch.float64, device=x.device)
+    check(lib().fvk_spmv(C.c_int32(n), C.c_void_p(sp.rowOffs_ptr), C.c_void_p(sp.colIdxs_ptr), ptr(values), ptr(x), ptr(y), _stream()))
+    ops._count()
+    return y
+
+
+def computeResidual(sp: SparsityPattern, values, b, x, res=None):
+    """la::computeResidual (utilities.cpp:11-35): res = A x - b."""
+    n = sp.mesh.nOwned
+    if res is None:
+        res = torch.empty(n, dtype=torch.float64, device=x.device)
+    check(lib().fvk_residual(C.c_int32(n), C.c_void_p(sp.rowOffs_ptr), C.c_void_p(sp.colIdxs_ptr), ptr(values), ptr(b), ptr(x), ptr(res), _stream()))
+    ops._count()
+    return res
+
+
+@dataclass
+class SolverStats:
+    """la::SolverStats (solver.hpp:14-27)."""
+    numIter: int
+    initResNorm: float
+    finalResNorm: float
+    history: np.ndarray | None = None
+
+    def print(self, name):
+        print(f"Solver: {name} , Initial residual = {self.initResNorm} , Final residual = {self.finalResNorm} , No Iterations = {self.numIter}")
+
+
+class _Cfg(C.Structure):
+    _fields_ = [("maxIter", C.c_int32), ("relTol", C.c_double), ("absTol", C.c_double), ("preconditioner", C.c_int32),
+                ("checkEvery", C.c_int32)]
+
+
+class _Stats(C.Structure):
+    _fields_ = [("numIter", C.c_int32), ("initResNorm", C.c_double), ("finalResNorm", C.c_double), ("nHistory", C.c_int32)]
+
+
+def mapFvSolution(d: dict) -> dict:
+    """src/compatibility/fvSolution.cpp:19-159: OpenFOAM solver entry -> Ginkgo-style config. Keys handled:
+    solver PCG|PBiCGStab(unsupported here), preconditioner DIC|DILU|none, tolerance, relTol, maxIter."""
+    if "type" in d:  # already a Ginkgo-style dict
+        return d
+    solver = d.get("solver", "PCG")
+    if solver not in ("PCG", "CG"):
+        raise KeyError(f"solver '{solver}' is not on the hot path (only PCG/CG -> solver::Cg)")
+    pre = d.get("preconditioner", "none")
+    out = {"solver": "Ginkgo", "type": "solver::Cg",
+           "criteria": {"iteration": int(d.get("maxIter", 1000)), "relative_residual_norm": float(d.get("relTol", 0.0)),
+                        "absolute_residual_norm": float(d.get("tolerance", 1e-6))}}
+    if pre in ("DIC", "DILU", "Jacobi", "diagonal"):
+        out["preconditioner"] = {"type": "preconditioner::Jacobi", "max_block_size": 1}
+    elif pre not in ("none", None):
+        raise KeyError(f"preconditioner '{pre}' not supported")
+    return out
+
+
+class Solver:
+    """la::Solver(exec, dict) (solver.hpp:63-91) for the configurations mapFvSolution emits: solver::Cg with an
+    optional scalar Jacobi preconditioner. solve(ls, x) -> SolverStats like GinkgoSolver::solve (ginkgo.hpp:116-155)."""
+
+    def __init__(self, config: dict, comm=None, check_every=8, history=False):
+        cfg = mapFvSolution(config)
+        if cfg.get("type") != "solver::Cg":
+            raise KeyError(f"solver type '{cfg.get('type')}' is not on the hot path")
+        crit = cfg.get("criteria", {})
+        pre = cfg.get("preconditioner")
+        self.cfg = _Cfg(int(crit.get("iteration", 1000)), float(crit.get("relative_residual_norm", 0.0)),
+                        float(crit.get("absolute_residual_norm", 0.0)),
+                        1 if (pre and pre.get("type") == "preconditioner::Jacobi") else 0, int(check_every))
+        self.comm, self.history = comm, history
+        self._h, self._shape = None, None
+
+    def _handle(self, nRows, nCols):
+        if self._shape != (nRows, nCols):
+            self.close()
+            h = C.c_void_p()
+            check(lib().fvk_solver_create(C.c_int32(nRows), C.c_int32(nCols), C.byref(self.cfg),
+                                          self.comm.handle if self.comm is not None else None, C.byref(h)))
+            self._h, self._shape = h, (nRows, nCols)
+        return self._h
+
+    def close(self):
+        if self._h is not None:
+            lib().fvk_solver_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def solve_csr(self, nRows, nCols, rowOffs_ptr, colIdxs_ptr, values, b, x) -> SolverStats:
+        h = self._handle(nRows, nCols)
+        st = _Stats()
+        nh = self.cfg.maxIter + 2 if self.history else 0
+        hist = np.zeros(max(nh, 1))
+        check(lib().fvk_solver_solve(h, C.c_void_p(rowOffs_ptr), C.c_void_p(colIdxs_ptr), ptr(values), ptr(b), ptr(x),
+                                     C.byref(st), hist.ctypes.data_as(C.c_void_p) if nh else None, C.c_int32(nh), _stream()))
+        # K1 + K2 per completed iteration, + the final K1, + dinv / ||b|| / normB / r0
+        ops._count(2 * st.numIter + 5)
+        return SolverStats(st.numIter, st.initResNorm, st.finalResNorm, hist[:st.nHistory] if nh else None)
+
+    def solve(self, ls: LinearSystem, x) -> SolverStats:
+        m = ls.mesh
+        return self.solve_csr(m.nOwned, m.nCells, ls.sp.rowOffs_ptr, ls.sp.colIdxs_ptr, ls.values, ls.rhs, x)
+
+
+# ---- Vector free functions (vectorFreeFunctions.cpp:18-106) ----------------------------------------
+def _n(x): return C.c_int64(x.numel())
+def fill(x, v): check(lib().fvk_vec_fill(_n(x), C.c_double(v), ptr(x), _stream())); ops._count(); return x
+def scalarMul(x, a): check(lib().fvk_vec_scale(_n(x), C.c_double(a), ptr(x), _stream())); ops._count(); return x
+def add(x, y): check(lib().fvk_vec_add(_n(x), ptr(x), ptr(y), _stream())); ops._count(); return x
+def sub(x, y): check(lib().fvk_vec_sub(_n(x), ptr(x), ptr(y), _stream())); ops._count(); return x
+def mul(x, y): check(lib().fvk_vec_mul(_n(x), ptr(x), ptr(y), _stream())); ops._count(); return x
+def axpby(a, x, b, y): check(lib().fvk_vec_axpby(_n(y), C.c_double(a), ptr(x), C.c_double(b), ptr(y), _stream())); ops._count(); return y
+
+
+def dot(x, y, out=None):
+    out = out if out is not None else torch.empty(1, dtype=torch.float64, device=x.device)
+    check(lib().fvk_dot(_n(x), ptr(x), ptr(y), ptr(out), _stream())); ops._count()
+    return out
+
+
+def norm2(x, out=None):
+    out = out if out is not None else torch.empty(1, dtype=torch.float64, device=x.device)
+    check(lib().fvk_norm2(_n(x), ptr(x), ptr(out), _stream())); ops._count()
+    return out

@@ -178,6 +178,7 @@ class UnstructuredMesh:
         self.nFaces = self.nInternalFaces + self.nBoundaryFaces
         self.nPatches = self.size(N_PATCHES)
         self.nnz = self.size(NNZ)
+        self.nOwned = self.nCells  # cells this rank owns (ghost cells of a decomposed mesh follow them)
         off = (C.c_int32 * (self.nPatches + 1))()
         check(lib().fvk_mesh_patch_offsets(self._h, off))
         self.patch_offsets = list(off)

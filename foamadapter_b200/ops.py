@@ -128,3 +128,61 @@ def correct_boundary_conditions(mesh, kinds, consts, internal, value, refValue, 
     check(lib().fvk_correct_boundary_conditions(mesh.handle, C.c_int(ncomp), k, v, ptr(internal), ptr(value),
                                                 ptr(refValue), ptr(valueFraction), ptr(refGrad), _stream()))
     _count()
+
+
+# ---- implicit assembly ---------------------------------------------------------------------------
+TERM_DDT, TERM_DIV, TERM_LAPLACIAN, TERM_SOURCE = range(4)
+
+
+class _Term(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("scheme", C.c_int32), ("coeff", C.c_double), ("coeffView", C.c_void_p),
+                ("faceField", C.c_void_p), ("cellField", C.c_void_p), ("dt", C.c_double)]
+
+
+class _BField(C.Structure):
+    _fields_ = [("value", C.c_void_p), ("refValue", C.c_void_p), ("valueFraction", C.c_void_p), ("refGrad", C.c_void_p)]
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def assemble(mesh, terms, boundary, values, rhs, bcMatrix=None, bcRhs=None, accumulate=False):
+    """terms: list of dicts {kind, scheme?, coeff?, coeffView?, faceField?, cellField?, dt?} applied in order
+    (Expression::implicitOperation). boundary: BoundaryData of the unknown field (or None)."""
+    vec = values.ndim == 2
+    arr = (_Term * len(terms))()
+    keep = []
+    for i, t in enumerate(terms):
+        keep += [t.get("coeffView"), t.get("faceField"), t.get("cellField")]
+        arr[i] = _Term(int(t["kind"]), int(t.get("scheme", 0)), float(t.get("coeff", 1.0)), _p(t.get("coeffView")),
+                       _p(t.get("faceField")), _p(t.get("cellField")), float(t.get("dt", 0.0)))
+    bf = None
+    if boundary is not None:
+        bf = C.byref(_BField(_p(boundary.value), _p(boundary.refValue), _p(boundary.valueFraction), _p(boundary.refGrad)))
+    fn = lib().fvk_assemble_v if vec else lib().fvk_assemble_s
+    check(fn(mesh.handle, C.c_int(len(terms)), arr, bf, ptr(values), ptr(rhs), ptr(bcMatrix), ptr(bcRhs),
+             C.c_int(1 if accumulate else 0), _stream()))
+    _count()
+
+
+def ddt_explicit(mesh, field, oldField, dt, source):
+    check(lib().fvk_ddt_explicit(mesh.handle, C.c_int(3 if field.ndim == 2 else 1), ptr(field), ptr(oldField), C.c_double(dt),
+                                 ptr(source), _stream()))
+    _count()
+
+
+def source_explicit(mesh, k, field, source, coeff=1.0, coeffView=None):
+    check(lib().fvk_source_explicit(mesh.handle, C.c_int(3 if field.ndim == 2 else 1), ptr(k), ptr(field), C.c_double(coeff),
+                                    ptr(coeffView), ptr(source), _stream()))
+    _count()
+
+
+def rhs_sub_source(mesh, src, rhs):
+    check(lib().fvk_rhs_sub_source(mesh.handle, C.c_int(3 if rhs.ndim == 2 else 1), ptr(src), ptr(rhs), _stream()))
+    _count()
+
+
+def bc_coeff_indices(mesh, matrixIdxs, rhsIdxs):
+    check(lib().fvk_bc_coeff_indices(mesh.handle, ptr(matrixIdxs), ptr(rhsIdxs), _stream()))
+    _count()

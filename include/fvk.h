@@ -293,6 +293,94 @@ int fvk_source_explicit(const fvk_mesh* mesh, int ncomp, const double* k, const 
 int fvk_rhs_sub_source(const fvk_mesh* mesh, int ncomp, const double* src, double* rhs,
                        fvk_stream stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Linear algebra.
+ * ---------------------------------------------------------------------------------------------- */
+/* CSR y = A x over LinearSystem<scalar,localIdx> arrays (CSRMatrix.hpp:19-74). Rows are summed in
+ * ascending entry order like the reference's row loop (linearAlgebra/utilities.cpp:21-34). x has
+ * nCols >= nRows entries (ghost columns of a decomposed mesh follow the owned rows). */
+int fvk_spmv(int32_t nRows, const int32_t* rowOffs, const int32_t* colIdxs, const double* values,
+             const double* x, double* y, fvk_stream stream);
+/* computeResidual (src/NeoN/src/linearAlgebra/utilities.cpp:11-35): res = A x - b */
+int fvk_residual(int32_t nRows, const int32_t* rowOffs, const int32_t* colIdxs, const double* values,
+                 const double* b, const double* x, double* res, fvk_stream stream);
+/* Vector free functions (src/NeoN/src/core/vector/vectorFreeFunctions.cpp:18-106,
+ * core/containerFreeFunctions.hpp:51-115): fill, setContainer (copy = fvk_memcpy_d2d), scalarMul,
+ * add / sub / mul (x op= y), and the axpby the time integrators spell as temporaries
+ * (forwardEuler.hpp:44-49: phi = old - source*dt). n counts doubles (3*n for a Vec3 vector). */
+int fvk_vec_fill(int64_t n, double value, double* x, fvk_stream stream);
+int fvk_vec_scale(int64_t n, double a, double* x, fvk_stream stream);
+int fvk_vec_add(int64_t n, double* x, const double* y, fvk_stream stream);
+int fvk_vec_sub(int64_t n, double* x, const double* y, fvk_stream stream);
+int fvk_vec_mul(int64_t n, double* x, const double* y, fvk_stream stream);
+/* y = a*x + b*y */
+int fvk_vec_axpby(int64_t n, double a, const double* x, double b, double* y, fvk_stream stream);
+/* result_d[0] = sum x[i]*y[i]  /  sqrt(sum x[i]^2): deterministic two-stage warp-shuffle reduction,
+ * result stays on the device (no host sync). */
+int fvk_dot(int64_t n, const double* x, const double* y, double* result_d, fvk_stream stream);
+int fvk_norm2(int64_t n, const double* x, double* result_d, fvk_stream stream);
+
+/* la::Solver (linearAlgebra/solver.hpp:14-91) with the Ginkgo configuration mapFvSolution produces
+ * for the PISO pressure equation (src/compatibility/fvSolution.cpp:19-159): solver::Cg, optional
+ * preconditioner::Jacobi (max_block_size 1), criteria iteration / relative_residual_norm /
+ * absolute_residual_norm OR-combined. Ginkgo itself is a third-party dependency of the reference
+ * (1.10.0, src/NeoN/cmake/CxxThirdParty.cmake:158-179); the iteration follows its published CG
+ *  and GinkgoSolver::solve's bookkeeping (linearAlgebra/ginkgo.hpp:116-155):
+ * initResNorm = ||b||_2 (sic), finalResNorm = ||r||_2 at stop, numIter = completed updates.
+ * Two kernels per iteration: {x += alpha p; r -= alpha q; z = r/d; r.z; r.r} and
+ * {p = z + beta p; q = A p; p.q}; scalars stay on the device; the host polls the stop flag every
+ * `checkEvery` iterations (kernels after the stop are no-ops, so results equal a per-iteration check). */
+typedef struct fvk_solver fvk_solver;
+typedef struct fvk_comm fvk_comm;
+enum { FVK_PRECOND_NONE = 0, FVK_PRECOND_JACOBI = 1 };
+typedef struct fvk_solver_config {
+    int32_t maxIter;        /* criteria.iteration (default 1000, fvSolution.cpp:117-138) */
+    double relTol;          /* criteria.relative_residual_norm */
+    double absTol;          /* criteria.absolute_residual_norm */
+    int32_t preconditioner; /* FVK_PRECOND_* */
+    int32_t checkEvery;     /* host polls the device stop flag every this many iterations (>=1) */
+} fvk_solver_config;
+typedef struct fvk_solver_stats {
+    int32_t numIter;
+    double initResNorm;
+    double finalResNorm;
+    int32_t nHistory; /* entries written to history_h */
+} fvk_solver_stats;
+/* nRows owned rows, nCols >= nRows entries in x (ghosts after the owned rows). comm may be NULL
+ * (single GPU); with a comm, dots are all-reduced and p is halo-exchanged before every A p. */
+int fvk_solver_create(int32_t nRows, int32_t nCols, const fvk_solver_config* cfg, fvk_comm* comm,
+                      fvk_solver** out);
+int fvk_solver_destroy(fvk_solver* solver);
+/* Solves A x = b in place (x = initial guess). history_h (HOST, may be NULL) receives ||r||_2 at
+ * every stopping check (history[0] = ||r0||), at most maxHistory entries. Synchronises `stream`. */
+int fvk_solver_solve(fvk_solver* solver, const int32_t* rowOffs, const int32_t* colIdxs,
+                     const double* values, const double* b, double* x, fvk_solver_stats* stats_h,
+                     double* history_h, int32_t maxHistory, fvk_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU: one process per GPU, NCCL over NVLink/NVSwitch. Replaces the reference's unhooked MPI
+ * halo layer (src/NeoN/include/NeoN/mesh/unstructured/communicator.hpp:89-143 startComm /
+ * finaliseComm; core/mpi/operators.hpp:132-160 allReduce), which packs and unpacks on the host.
+ * A decomposed sub-mesh keeps its ghost cells directly behind its nOwned cells in every cell field
+ * (see fvk_decompose), so received values land in place and every kernel indexes them like cells.
+ * ---------------------------------------------------------------------------------------------- */
+#define FVK_UNIQUE_ID_BYTES 128
+/* rank 0 creates the id; the host distributes it (torch.distributed / MPI broadcast) */
+int fvk_comm_unique_id(void* id128);
+/* collective over all ranks (ncclCommInitRank on the current device); nRanks == 1 needs no id */
+int fvk_comm_create(int rank, int nRanks, const void* id128, fvk_comm** out);
+int fvk_comm_destroy(fvk_comm* comm);
+int fvk_comm_rank(const fvk_comm* comm, int* rank, int* nRanks);
+/* halo plan (HOST arrays): for neighbour k, sendCells[sendOffsets[k]..sendOffsets[k+1]) are owned
+ * cells whose values rank neighbourRanks[k] needs, in the order of that rank's ghost slots; this
+ * rank's ghosts owned by neighbour k are field[nOwned + recvOffsets[k] .. nOwned + recvOffsets[k+1]). */
+int fvk_comm_set_halo(fvk_comm* comm, int32_t nOwned, int32_t nNeighbours, const int32_t* neighbourRanks_h,
+                      const int32_t* sendOffsets_h, const int32_t* sendCells_h, const int32_t* recvOffsets_h);
+/* pack + one NCCL send/recv group on `stream`; field has (nOwned + nGhost) * ncomp doubles */
+int fvk_comm_halo_exchange(fvk_comm* comm, double* field, int ncomp, fvk_stream stream);
+int fvk_comm_allreduce_sum(fvk_comm* comm, double* data_d, int count, fvk_stream stream);
+int fvk_comm_allreduce_max(fvk_comm* comm, double* data_d, int count, fvk_stream stream);
+
 /* experiment switch: selects the kernel variant used by the gather operators
  * (0 = default). Used by the roofline harness only. */
 int fvk_set_variant(int variant);
