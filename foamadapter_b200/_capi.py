@@ -21,6 +21,7 @@ class MeshDesc(C.Structure):
         ("bCf", c_double_p), ("bCn", c_double_p), ("bSf", c_double_p), ("bMagSf", c_double_p),
         ("bNf", c_double_p), ("bDelta", c_double_p), ("bWeights", c_double_p),
         ("bDeltaCoeffs", c_double_p), ("patchOffsets", c_int32_p),
+        ("nOwnedCells", C.c_int32), ("faceOrder", c_int32_p),
     ]
 
 

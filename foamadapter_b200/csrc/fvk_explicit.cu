@@ -284,7 +284,7 @@ int launch_gather(const fvk_mesh* m, Op op, Scaling sc, double* out, int mode, f
 {
     if (mode != FVK_SET && mode != FVK_ACC_SCALE && mode != FVK_ADD)
         return fvk_fail(FVK_EINVAL, "bad mode %d", mode);
-    const int nC = m->nCells;
+    const int nC = m->nOwned;
     const int nI = m->nInternalFaces;
     const int grid = (nC + 255) / 256;
     const int variant = (nI == 0) ? 0 : fvk_variant(); // the plan kernels read face 0 on padded lanes
@@ -605,7 +605,7 @@ extern "C" int fvk_face_normal_grad_v(const fvk_mesh* m, const double* phi, cons
 
 static int conum_grid(const fvk_mesh* m)
 {
-    const int want = (m->nCells + 255) / 256;
+    const int want = (m->nOwned + 255) / 256;
     const int cap = fvk_sm_count() * 8;
     return want < cap ? (want > 0 ? want : 1) : cap;
 }
@@ -619,7 +619,7 @@ extern "C" int fvk_conum(const fvk_mesh* m, const double* faceFlux, double dt, d
     if (!m || !faceFlux || !result_d || !scratch_d) return fvk_fail(FVK_EINVAL, "fvk_conum: null argument");
     const int grid = conum_grid(m);
     double* partial = static_cast<double*>(scratch_d);
-    k_conum_stage1<<<grid, 256, 0, fvk_cu(s)>>>(CoNumOp {faceFlux}, m->nCells, m->stencilSeg, m->gatherEnt, m->V, partial);
+    k_conum_stage1<<<grid, 256, 0, fvk_cu(s)>>>(CoNumOp {faceFlux}, m->nOwned, m->stencilSeg, m->gatherEnt, m->V, partial);
     FVK_LAUNCH_CHECK();
     k_conum_stage2<<<1, 256, 0, fvk_cu(s)>>>(grid, partial, dt, result_d);
     FVK_LAUNCH_CHECK();

@@ -270,9 +270,9 @@ int assemble_impl(const fvk_mesh* m, int nTerms, const fvk_term* terms_h, const 
         if (!m->bDeltaCoeffs) return fvk_fail(FVK_EINVAL, "fvk_assemble: mesh has no boundary deltaCoeffs");
         b = *bd;
     }
-    AsmMesh am {m->nCells, m->nInternalFaces, m->stencilSeg, m->gatherEnt, m->rowOffs, m->diagOffset, m->ownerOffset,
+    AsmMesh am {m->nOwned, m->nInternalFaces, m->stencilSeg, m->gatherEnt, m->rowOffs, m->diagOffset, m->ownerOffset,
                 m->neighbourOffset, m->V, m->weights, m->nonOrthDeltaCoeffs, m->magSf, m->bDeltaCoeffs};
-    const int grid = (m->nCells + 255) / 256;
+    const int grid = (m->nOwned + 255) / 256;
     k_assemble<VT><<<grid, 256, 0, fvk_cu(s)>>>(T, am, b, values, rhs, bcMatrix, bcRhs, accumulate ? 1 : 0);
     FVK_LAUNCH_CHECK();
     return FVK_OK;
@@ -300,14 +300,14 @@ extern "C" int fvk_bc_coeff_indices(const fvk_mesh* m, int32_t* matrixIdxs, int3
     return FVK_OK;
 }
 
-#define CELL_GRID(m) ((m)->nCells + 255) / 256, 256, 0, fvk_cu(s)
+#define CELL_GRID(m) ((m)->nOwned + 255) / 256, 256, 0, fvk_cu(s)
 extern "C" int fvk_ddt_explicit(const fvk_mesh* m, int ncomp, const double* field, const double* oldField, double dt,
                                 double* source, fvk_stream s)
 {
     if (!m || !field || !oldField || !source || (ncomp != 1 && ncomp != 3) || !(dt != 0.0))
         return fvk_fail(FVK_EINVAL, "fvk_ddt_explicit: bad argument");
-    if (ncomp == 1) k_ddt_exp<S1><<<CELL_GRID(m)>>>(m->nCells, m->V, field, oldField, dt, source);
-    else k_ddt_exp<S3><<<CELL_GRID(m)>>>(m->nCells, m->V, field, oldField, dt, source);
+    if (ncomp == 1) k_ddt_exp<S1><<<CELL_GRID(m)>>>(m->nOwned, m->V, field, oldField, dt, source);
+    else k_ddt_exp<S3><<<CELL_GRID(m)>>>(m->nOwned, m->V, field, oldField, dt, source);
     FVK_LAUNCH_CHECK();
     return FVK_OK;
 }
@@ -315,16 +315,16 @@ extern "C" int fvk_source_explicit(const fvk_mesh* m, int ncomp, const double* k
                                    const double* coeffView, double* source, fvk_stream s)
 {
     if (!m || !k || !field || !source || (ncomp != 1 && ncomp != 3)) return fvk_fail(FVK_EINVAL, "fvk_source_explicit: bad argument");
-    if (ncomp == 1) k_source_exp<S1><<<CELL_GRID(m)>>>(m->nCells, k, field, coeff, coeffView, source);
-    else k_source_exp<S3><<<CELL_GRID(m)>>>(m->nCells, k, field, coeff, coeffView, source);
+    if (ncomp == 1) k_source_exp<S1><<<CELL_GRID(m)>>>(m->nOwned, k, field, coeff, coeffView, source);
+    else k_source_exp<S3><<<CELL_GRID(m)>>>(m->nOwned, k, field, coeff, coeffView, source);
     FVK_LAUNCH_CHECK();
     return FVK_OK;
 }
 extern "C" int fvk_rhs_sub_source(const fvk_mesh* m, int ncomp, const double* src, double* rhs, fvk_stream s)
 {
     if (!m || !src || !rhs || (ncomp != 1 && ncomp != 3)) return fvk_fail(FVK_EINVAL, "fvk_rhs_sub_source: bad argument");
-    if (ncomp == 1) k_rhs_sub_source<S1><<<CELL_GRID(m)>>>(m->nCells, m->V, src, rhs);
-    else k_rhs_sub_source<S3><<<CELL_GRID(m)>>>(m->nCells, m->V, src, rhs);
+    if (ncomp == 1) k_rhs_sub_source<S1><<<CELL_GRID(m)>>>(m->nOwned, m->V, src, rhs);
+    else k_rhs_sub_source<S3><<<CELL_GRID(m)>>>(m->nOwned, m->V, src, rhs);
     FVK_LAUNCH_CHECK();
     return FVK_OK;
 }

@@ -12,6 +12,7 @@ int fvk_fail(int code, const char* fmt, ...);
 struct fvk_mesh
 {
     int32_t nCells = 0, nInternalFaces = 0, nBoundaryFaces = 0, nPatches = 0;
+    int32_t nOwned = 0; // cells [0, nOwned) are computed; [nOwned, nCells) are ghosts of a decomposed mesh
     int64_t nnz = 0;
     int device = 0;
     // UnstructuredMesh

@@ -10,7 +10,9 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
+#include <utility>
 #include <vector>
 
 // ------------------------------------------------------------------------------------------------
@@ -238,6 +240,7 @@ extern "C" int fvk_mesh_create(const fvk_mesh_desc* d, fvk_mesh** out)
     fvk_mesh* m = new fvk_mesh;
     m->nCells = nC; m->nInternalFaces = nI; m->nBoundaryFaces = nB; m->nPatches = d->nPatches;
     m->nnz = int64_t(nC) + 2 * int64_t(nI);
+    m->nOwned = (d->nOwnedCells > 0 && d->nOwnedCells <= nC) ? d->nOwnedCells : nC;
     cudaGetDevice(&m->device);
     for (int p = 0; p <= d->nPatches; ++p) m->patchOffsets[p] = nB ? d->patchOffsets[p] : 0;
 
@@ -288,6 +291,32 @@ extern "C" int fvk_mesh_create(const fvk_mesh_desc* d, fvk_mesh** out)
             const int32_t k = pos[d->faceCells[b]]++;
             val[k] = nI + b; ent[k] = (nI + b) << 1;
             plan[2 * size_t(k)] = -(b + 1); plan[2 * size_t(k) + 1] = d->faceCells[b];
+        }
+        if (d->faceOrder)
+        {
+            // per-cell gather order = ascending key over the internal faces (boundary faces stay last);
+            // stencilVal keeps the reference's ascending local id (cellToFaceStencil.cpp:82-93)
+            const int32_t* key = d->faceOrder;
+            std::vector<std::pair<int32_t, int32_t>> tmp;
+            for (int32_t c = 0; c < nC; ++c)
+            {
+                int32_t b0 = seg[c], b1 = seg[size_t(c) + 1];
+                while (b1 > b0 && (ent[b1 - 1] >> 1) >= nI) --b1;
+                tmp.clear();
+                for (int32_t k = b0; k < b1; ++k) tmp.emplace_back(key[ent[k] >> 1], k);
+                std::stable_sort(tmp.begin(), tmp.end());
+                std::vector<int32_t> e2(tmp.size()), p2(2 * tmp.size());
+                for (size_t i = 0; i < tmp.size(); ++i)
+                {
+                    e2[i] = ent[tmp[i].second];
+                    p2[2 * i] = plan[2 * size_t(tmp[i].second)]; p2[2 * i + 1] = plan[2 * size_t(tmp[i].second) + 1];
+                }
+                for (size_t i = 0; i < tmp.size(); ++i)
+                {
+                    ent[b0 + i] = e2[i];
+                    plan[2 * (size_t(b0) + i)] = p2[2 * i]; plan[2 * (size_t(b0) + i) + 1] = p2[2 * i + 1];
+                }
+            }
         }
         UP(stencilSeg, seg.data(), seg.size());
         UP(stencilVal, val.data(), nEnt);
@@ -415,6 +444,7 @@ extern "C" int fvk_mesh_size(const fvk_mesh* m, int field, int64_t* value)
         case FVK_N_BOUNDARY_FACES: *value = m->nBoundaryFaces; break;
         case FVK_N_PATCHES: *value = m->nPatches; break;
         case FVK_NNZ: *value = m->nnz; break;
+        case FVK_N_OWNED_CELLS: *value = m->nOwned; break;
         default: return fvk_fail(FVK_EINVAL, "fvk_mesh_size: unknown field %d", field);
     }
     return FVK_OK;

@@ -71,6 +71,13 @@ class VolumeField:
     def boundaryData(self):
         return self.boundary
 
+    def oldTime(self):
+        """fvcc::oldTime(field) (core/database/oldTimeCollection.hpp:146-152): a registered copy, created on first use."""
+        if getattr(self, "_old", None) is None:
+            self._old = VolumeField(self.mesh, self.name + "_0", self.ncomp, list(self.bcs), self.internal.device)
+            self._old.internal.copy_(self.internal)
+        return self._old
+
     def assignable(self, patch: int) -> bool:
         # fixedValue is the only non-assignable BC (fixedValue.hpp:56 vs fixedGradient/extrapolated)
         return _BC_KINDS[self.bcs[patch][0]] != ops.BC_FIXED_VALUE

@@ -186,3 +186,41 @@ def rhs_sub_source(mesh, src, rhs):
 def bc_coeff_indices(mesh, matrixIdxs, rhsIdxs):
     check(lib().fvk_bc_coeff_indices(mesh.handle, ptr(matrixIdxs), ptr(rhsIdxs), _stream()))
     _count()
+
+
+# ---- PISO glue -----------------------------------------------------------------------------------
+def rAU_HbyA(mesh, valuesV, rhsV, U, rAU, HbyA=None):
+    check(lib().fvk_rAU_HbyA(mesh.handle, ptr(valuesV), ptr(rhsV), ptr(U), ptr(rAU), ptr(HbyA), _stream()))
+    _count()
+
+
+def copy_patches(mesh, mask, srcB, dstB):
+    m = (C.c_int32 * mesh.nPatches)(*[int(bool(x)) for x in mask])
+    check(lib().fvk_copy_patches(mesh.handle, C.c_int(3 if srcB.ndim == 2 else 1), m, ptr(srcB), ptr(dstB), _stream()))
+    _count()
+
+
+def flux(mesh, U, Ub, outFace, outB=None):
+    check(lib().fvk_flux(mesh.handle, ptr(U), ptr(Ub), ptr(outFace), ptr(outB), _stream()))
+    _count()
+
+
+def update_face_velocity(mesh, values, bcMatrix, bcRhs, p, predPhi, predPhiB, phi, phiB):
+    check(lib().fvk_update_face_velocity(mesh.handle, ptr(values), ptr(bcMatrix), ptr(bcRhs), ptr(p), ptr(predPhi),
+                                         ptr(predPhiB), ptr(phi), ptr(phiB), _stream()))
+    _count()
+
+
+def update_velocity(mesh, HbyA, rAU, gradP, U):
+    check(lib().fvk_update_velocity(mesh.handle, ptr(HbyA), ptr(rAU), ptr(gradP), ptr(U), _stream()))
+    _count()
+
+
+def set_reference(mesh, refCell, refValue, values, rhs):
+    check(lib().fvk_set_reference(mesh.handle, C.c_int32(refCell), C.c_double(refValue), ptr(values), ptr(rhs), _stream()))
+    _count()
+
+
+def diag(mesh, values, out):
+    check(lib().fvk_diag(mesh.handle, C.c_int(3 if values.ndim == 2 else 1), ptr(values), ptr(out), _stream()))
+    _count()

@@ -1,0 +1,143 @@
+"""Python mirror of FoamAdapter's PISO helpers (src/algorithms/pressureVelocityCoupling.cpp) and of the
+neoIcoFoam time loop (examples/neoIcoFoam/neoIcoFoam.cpp:80-180) on a synthetic lid-driven cavity. Function names
+and argument meaning follow the reference; bodies call the CUDA kernels through the C ABI."""
+from __future__ import annotations
+
+import torch
+
+from . import dsl, fvcc, la, ops
+from .mesh import MeshDesc, PATCHES_CAVITY2D, PATCHES_CAVITY3D, UnstructuredMesh
+
+
+def _extrapolated(mesh):
+    return [("extrapolated", 0.0)] * mesh.nPatches
+
+
+def computeRAU(expr: dsl.PDESolver, rAU: fvcc.VolumeField | None = None):
+    """pressureVelocityCoupling.cpp:38-63"""
+    mesh = expr.psi.mesh
+    rAU = rAU or fvcc.VolumeField(mesh, "rAU", 1, _extrapolated(mesh))
+    ops.rAU_HbyA(mesh, expr.ls.values, None, None, rAU.internal, None)
+    return rAU
+
+
+def computeRAUandHByA(expr: dsl.PDESolver, rAU=None, HbyA=None):
+    """pressureVelocityCoupling.cpp:65-128 (one fused kernel + the two extrapolated BC launches)."""
+    mesh = expr.psi.mesh
+    rAU = rAU or fvcc.VolumeField(mesh, "rAU", 1, _extrapolated(mesh))
+    HbyA = HbyA or fvcc.VolumeField(mesh, "HbyA", 3, _extrapolated(mesh))
+    ops.rAU_HbyA(mesh, expr.ls.values, expr.ls.rhs, expr.psi.internal, rAU.internal, HbyA.internal)
+    HbyA.correctBoundaryConditions()
+    rAU.correctBoundaryConditions()
+    return rAU, HbyA
+
+
+def constrainHbyA(U: fvcc.VolumeField, p: fvcc.VolumeField, HbyA: fvcc.VolumeField):
+    """pressureVelocityCoupling.cpp:14-36"""
+    mask = [not U.assignable(i) for i in range(U.mesh.nPatches)]
+    if any(mask):
+        ops.copy_patches(U.mesh, mask, U.boundary.value, HbyA.boundary.value)
+
+
+def flux(volField: fvcc.VolumeField, out: fvcc.SurfaceField | None = None):
+    """pressureVelocityCoupling.cpp:215-267"""
+    out = out or fvcc.SurfaceField(volField.mesh, "out", 1)
+    ops.flux(volField.mesh, volField.internal, volField.boundary.value, out.internal, out.bvalue)
+    return out
+
+
+def updateFaceVelocity(predictedPhi: fvcc.SurfaceField, expr: dsl.PDESolver, phi: fvcc.SurfaceField):
+    """pressureVelocityCoupling.cpp:131-197"""
+    ls = expr.ls
+    ops.update_face_velocity(phi.mesh, ls.values, ls.bcMatrix, ls.bcRhs, expr.psi.internal, predictedPhi.internal,
+                             predictedPhi.bvalue, phi.internal, phi.bvalue)
+
+
+def updateVelocity(HbyA, rAU, p, U, gradP=None):
+    """pressureVelocityCoupling.cpp:199-213"""
+    mesh = U.mesh
+    if gradP is None:
+        gradP = torch.empty((mesh.nCells, 3), dtype=torch.float64, device=U.internal.device)
+    ops.grad(mesh, p.internal, p.boundary.value, gradP, ops.SET)
+    ops.update_velocity(mesh, HbyA.internal, rAU.internal, gradP, U.internal)
+
+
+# tutorials/cavity/system/{fvSchemes,fvSolution}
+CAVITY_FVSCHEMES = {"ddtSchemes": {"type": "backwardEuler"}, "divSchemes": {"div(phi,U)": "Gauss linear"},
+                    "laplacianSchemes": {"laplacian(nu,U)": "Gauss linear uncorrected", "laplacian(rAUf,p)": "Gauss linear uncorrected"}}
+CAVITY_FVSOLUTION = {"solvers": {"p": {"solver": "PCG", "preconditioner": "DIC", "tolerance": 1e-6, "relTol": 0.0}},
+                     "PISO": {"nCorrectors": 2, "nNonOrthogonalCorrectors": 0, "momentumPredictor": False, "pRefCell": 0, "pRefValue": 0.0}}
+
+
+def cavity_desc(n, three_d=False, L=0.1):
+    """tutorials/cavity/system/blockMeshDict: N x N x 1 (scale 0.1, front/back empty) or the 3-D N^3 variant of
+    BASELINE.json configs[4]."""
+    if three_d:
+        return MeshDesc.block(n, n, n, L, L, L, patches=PATCHES_CAVITY3D)
+    return MeshDesc.block(n, n, 1, L, L, 0.1 * L, patches=PATCHES_CAVITY2D)
+
+
+class IcoFoam:
+    """neoIcoFoam (examples/neoIcoFoam/neoIcoFoam.cpp) on a lid-driven cavity: U = (1 0 0) on movingWall, noSlip on
+    fixedWalls, p zeroGradient everywhere (tutorials/cavity/0.orig/{U,p}), nu uniform, momentumPredictor no."""
+
+    def __init__(self, mesh: UnstructuredMesh, nu=0.01, dt=1e-4, fvSolution=None, fvSchemes=None, comm=None,
+                 lid=(1.0, 0.0, 0.0), history=False, check_every=8):
+        self.mesh = mesh
+        fvSolution = fvSolution or CAVITY_FVSOLUTION
+        self.rt = dsl.RunTime(mesh, dt, 0.0, fvSchemes or CAVITY_FVSCHEMES, fvSolution, comm, check_every, history)
+        self.piso = fvSolution["PISO"]
+        nP = mesh.nPatches
+        self.U = fvcc.VolumeField(mesh, "U", 3, [("fixedValue", lid)] + [("noSlip", 0.0)] * (nP - 1))
+        self.p = fvcc.VolumeField(mesh, "p", 1, [("zeroGradient", 0.0)] * nP)
+        self.U.correctBoundaryConditions(); self.p.correctBoundaryConditions()
+        self.nu = fvcc.SurfaceField(mesh, "nu", 1); self.nu.internal.fill_(nu); self.nu.bvalue.fill_(nu)
+        self.phi = fvcc.SurfaceField(mesh, "phi", 1)
+        flux(self.U, self.phi)  # createFields.H / createPhi.H: phi = linearInterpolate(U) & Sf
+        # persistent work fields (the reference allocates these every corrector)
+        self.rAU = fvcc.VolumeField(mesh, "rAU", 1, _extrapolated(mesh))
+        self.HbyA = fvcc.VolumeField(mesh, "HbyA", 3, _extrapolated(mesh))
+        self.rAUf = fvcc.SurfaceField(mesh, "rAUf", 1)
+        self.phiHbyA = fvcc.SurfaceField(mesh, "phiHbyA", 1)
+        self.gradP = torch.empty((mesh.nCells, 3), dtype=torch.float64, device="cuda")
+        self.Uls = la.LinearSystem(mesh, 3, zero=False)
+        self.pls = la.LinearSystem(mesh, 1, zero=False)
+        self.linear = fvcc.SurfaceInterpolation(mesh, "linear")
+        self.solver = la.Solver(fvSolution["solvers"]["p"], comm=comm, check_every=check_every, history=history)
+        self.stats = []
+        self.coNum = None
+
+    def _halo(self, t):
+        if self.rt.comm is not None:
+            self.rt.comm.halo_exchange(t)
+
+    def step(self):
+        rt, mesh, U, p, phi = self.rt, self.mesh, self.U, self.p, self.phi
+        U.oldTime().internal.copy_(U.internal)                         # neoIcoFoam.cpp:84-85
+        self.coNum = ops.conum(mesh, phi.internal, rt.dt)              # :87 (device scalars; no host sync here)
+        self._halo(U.internal)
+        UEqn = dsl.PDESolver(dsl.imp.ddt(U) + dsl.imp.div(phi, U) - dsl.imp.laplacian(self.nu, U), U, rt, ls=self.Uls)
+        UEqn.assemble()                                                # momentumPredictor no (:100-109)
+        self.stats.append([])
+        for _ in range(self.piso["nCorrectors"]):
+            rAU, HbyA = computeRAUandHByA(UEqn, self.rAU, self.HbyA)   # :114
+            constrainHbyA(U, p, HbyA)                                  # :115
+            self._halo(rAU.internal); self._halo(HbyA.internal)
+            self.linear.interpolate(rAU, self.rAUf)                    # :117-124
+            phiHbyA = flux(HbyA, self.phiHbyA)                         # :126
+            nNon = self.piso["nNonOrthogonalCorrectors"]
+            for k in range(nNon + 1):
+                pEqn = dsl.PDESolver(dsl.imp.laplacian(self.rAUf, p) - dsl.exp.div(phiHbyA), p, rt, ls=self.pls)
+                if self.piso.get("pRefCell", -1) >= 0 and (rt.comm is None or rt.comm.rank == self.piso.get("pRefRank", 0)):
+                    pEqn.setReference(self.piso["pRefCell"], self.piso["pRefValue"])  # :150-153
+                st = pEqn.solve(self.solver)                           # :155
+                self.stats[-1].append(st)
+                self._halo(p.internal)
+                p.correctBoundaryConditions()                          # :156
+                if k == nNon:
+                    updateFaceVelocity(phiHbyA, pEqn, phi)             # :160
+            updateVelocity(HbyA, rAU, p, U, self.gradP)                # :166
+            U.correctBoundaryConditions()                              # :167
+            self._halo(U.internal)
+        rt.t += rt.dt
+        return self.stats[-1]

@@ -100,6 +100,14 @@ typedef struct fvk_mesh_desc {
     const double* bWeights;
     const double* bDeltaCoeffs;
     const int32_t* patchOffsets; /* [nPatches+1] */
+    /* decomposed sub-mesh (fvk_decompose): cells [0, nOwnedCells) are owned by this rank, cells
+     * [nOwnedCells, nCells) are ghost copies of neighbour ranks' cells; 0 means all cells are owned.
+     * Operators produce results for owned cells only. */
+    int32_t nOwnedCells;
+    /* optional sort key of the internal faces [nInternalFaces] (the global face id of a decomposed
+     * mesh): per-cell accumulation follows ascending key instead of ascending local face id, which
+     * makes a sub-domain sum in exactly the order of the undecomposed mesh. NULL = local face id. */
+    const int32_t* faceOrder;
 } fvk_mesh_desc;
 
 /* ------------------------------------------------------------------------------------------------
@@ -132,7 +140,7 @@ int fvk_mesh_destroy(fvk_mesh* mesh);
 
 enum fvk_mesh_field {
     /* sizes */
-    FVK_N_CELLS = 0, FVK_N_INTERNAL_FACES, FVK_N_BOUNDARY_FACES, FVK_N_PATCHES, FVK_NNZ,
+    FVK_N_CELLS = 0, FVK_N_INTERNAL_FACES, FVK_N_BOUNDARY_FACES, FVK_N_PATCHES, FVK_NNZ, FVK_N_OWNED_CELLS,
     /* device arrays, reference order */
     FVK_CELL_VOLUMES = 16, FVK_CELL_CENTRES, FVK_FACE_AREAS, FVK_FACE_CENTRES, FVK_MAG_FACE_AREAS,
     FVK_FACE_OWNER, FVK_FACE_NEIGHBOUR, FVK_FACE_CELLS,
@@ -356,6 +364,37 @@ int fvk_solver_destroy(fvk_solver* solver);
 int fvk_solver_solve(fvk_solver* solver, const int32_t* rowOffs, const int32_t* colIdxs,
                      const double* values, const double* b, double* x, fvk_solver_stats* stats_h,
                      double* history_h, int32_t maxHistory, fvk_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * PISO pressure-velocity coupling (FoamAdapter src/algorithms/pressureVelocityCoupling.cpp) and the
+ * PDESolver helpers (include/FoamAdapter/datastructures/expression.hpp). valuesV / rhsV are the Vec3
+ * momentum LinearSystem (identical components; component [0] is read, like the reference).
+ * ---------------------------------------------------------------------------------------------- */
+/* computeRAU (:38-63) and computeRAUandHByA (:65-128) in one cell-centric pass:
+ * rAU[c] = V[c] / diag[c][0];  HbyA[c] = (rhs[c] - sum_offdiag A[c][k][0] * U[k]) * (rAU[c] / V[c]),
+ * off-diagonals subtracted in ascending face order. HbyA == NULL computes rAU only.
+ * Boundary values follow from fvk_correct_boundary_conditions with FVK_BC_EXTRAPOLATED. */
+int fvk_rAU_HbyA(const fvk_mesh* mesh, const double* valuesV, const double* rhsV, const double* U,
+                 double* rAU, double* HbyA, fvk_stream stream);
+/* constrainHbyA (:14-36): dstB = srcB on the patches with patchMask_h[p] != 0 (the non-assignable
+ * patches of U). patchMask_h is HOST [nPatches]. */
+int fvk_copy_patches(const fvk_mesh* mesh, int ncomp, const int32_t* patchMask_h, const double* srcB,
+                     double* dstB, fvk_stream stream);
+/* flux (:215-267): outFace[f] = Sf . (w (U_P - U_N) + U_N); boundary bSf . Ub, also to outB (may be NULL) */
+int fvk_flux(const fvk_mesh* mesh, const double* U, const double* Ub, double* outFace, double* outB,
+             fvk_stream stream);
+/* updateFaceVelocity (:131-197) from the assembled scalar pressure system + its boundary coefficients */
+int fvk_update_face_velocity(const fvk_mesh* mesh, const double* values, const double* bcMatrix,
+                             const double* bcRhs, const double* p, const double* predPhi,
+                             const double* predPhiB, double* phi, double* phiB, fvk_stream stream);
+/* updateVelocity (:199-213): U = HbyA - rAU * gradP (gradP from fvk_grad_s) */
+int fvk_update_velocity(const fvk_mesh* mesh, const double* HbyA, const double* rAU, const double* gradP,
+                        double* U, fvk_stream stream);
+/* PDESolver::SetReference (expression.hpp:86-112): rhs[r] += diag*value; diag += diag */
+int fvk_set_reference(const fvk_mesh* mesh, int32_t refCell, double refValue, double* values, double* rhs,
+                      fvk_stream stream);
+/* diag(ls, sparsityPattern) (expression.hpp:181-199) */
+int fvk_diag(const fvk_mesh* mesh, int ncomp, const double* values, double* out, fvk_stream stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Multi-GPU: one process per GPU, NCCL over NVLink/NVSwitch. Replaces the reference's unhooked MPI

@@ -229,6 +229,41 @@ class Mesh:
         call("fvo_residual", par, self.nC, self.rowOffs, self.colIdxs, f64(values), f64(b), f64(x), r)
         return r
 
+    # ---- PISO glue (FoamAdapter src/algorithms/pressureVelocityCoupling.cpp) -------------------------
+    def rAU(self, valuesV):
+        out = np.zeros(self.nC)
+        call("fvo_rAU", self.nC, self.rowOffs, self.diagOffset, self.V, f64(valuesV), out)
+        return out
+
+    def HbyA(self, valuesV, rhsV, rAU, U, par=0):
+        out = np.zeros((self.nC, 3))
+        call("fvo_HbyA", par, self.nC, self.nI, self.owner, self.neighbour, self.rowOffs, self.ownerOffset,
+             self.neighbourOffset, self.V, f64(valuesV), f64(rhsV), f64(rAU), f64(U), out)
+        return out
+
+    def flux(self, U, Ub, par=0):
+        ff, bv = np.zeros(self.nF), np.zeros(self.nB)
+        call("fvo_flux", par, self.nI, self.nB, self.owner, self.neighbour, self.w, self.Sf, self.bSf, f64(U), f64(Ub), ff, bv)
+        return ff, bv
+
+    def update_face_velocity(self, ls, p, predPhi, predPhiB, par=0):
+        phi, phiB = np.zeros(self.nF), np.zeros(self.nB)
+        call("fvo_update_face_velocity", par, self.nI, self.nB, self.owner, self.neighbour, self.faceCells, self.rowOffs,
+             self.ownerOffset, self.neighbourOffset, ls["values"], ls["bcMatrix"], ls["bcRhs"], f64(p), f64(predPhi),
+             f64(predPhiB), phi, phiB)
+        return phi, phiB
+
+    def update_velocity(self, HbyA, rAU, gradP, par=0):
+        U = np.zeros((self.nC, 3))
+        call("fvo_update_velocity", par, self.nC, f64(HbyA), f64(rAU), f64(gradP), U)
+        return U
+
+    def set_reference(self, ls, refCell, refValue):
+        call("fvo_set_reference", int(refCell), float(refValue), self.rowOffs, self.diagOffset, ls["values"], ls["rhs"])
+
+    def rhs_sub_source(self, ls, src, par=0):
+        call("fvo_rhs_sub_source", par, self.nC, self.V, f64(src), ls["rhs"])
+
     def cg(self, values, b, x0, jacobi=True, max_iter=1000, rel_tol=0.0, abs_tol=1e-6, par=0, max_hist=0):
         return cg(self.rowOffs, self.colIdxs, values, b, x0, jacobi, max_iter, rel_tol, abs_tol, par, max_hist)
 
