@@ -12,6 +12,9 @@
 // -fmad=false, so results are bit-identical to the Serial executor built without FP contraction.
 #include "fvk_device.cuh"
 
+#include <cstdio>
+#include <cstdlib>
+
 namespace
 {
 
@@ -19,6 +22,7 @@ namespace
 struct S1 // scalar field
 {
     using T = double;
+    static constexpr int NC = 1;
     static __device__ __forceinline__ T zero() { return 0.0; }
     static __device__ __forceinline__ T ld(const double* __restrict__ p, int64_t i) { return p[i]; }
     static __device__ __forceinline__ void st(double* __restrict__ p, int64_t i, T v) { p[i] = v; }
@@ -29,6 +33,7 @@ struct S1 // scalar field
 struct S3 // Vec3 field, AoS
 {
     using T = Vec3d;
+    static constexpr int NC = 3;
     static __device__ __forceinline__ T zero() { return Vec3d {0.0, 0.0, 0.0}; }
     static __device__ __forceinline__ T ld(const double* __restrict__ p, int64_t i) { return ld3(p, i); }
     static __device__ __forceinline__ void st(double* __restrict__ p, int64_t i, T v) { st3(p, i, v); }
@@ -55,6 +60,26 @@ struct DivOp // gaussGreenDiv.cpp:46-67 with linear.cpp:30-45 / upwind.cpp:32-55
     const double* __restrict__ w;
     const double* __restrict__ phi;
     const double* __restrict__ phiB;
+    // staged-stream interface of the tile kernel: stream 0 = faceFlux, stream 1 = weights (linear only)
+    using CV = VT;
+    static constexpr int W0 = 1, W1 = (SCHEME == FVK_LINEAR) ? 1 : 0;
+    __device__ __forceinline__ bool ownsStreams() const { return false; } // stream 0 is the caller's faceFlux
+    __host__ __device__ __forceinline__ const double* s0() const { return faceFlux; }
+    __host__ __device__ __forceinline__ const double* s1() const { return w; }
+    __host__ __device__ __forceinline__ const double* cells() const { return phi; }
+    __device__ __forceinline__ T fluxv(const double* a, const double* b, const T& pOwn, const T& pNei) const
+    {
+        const double F = a[0];
+        T phif;
+        if (SCHEME == FVK_LINEAR)
+        {
+            const double wf = b[0];
+            phif = VT::add(VT::mul(wf, pOwn), VT::mul(1 - wf, pNei));
+        }
+        else
+            phif = (F >= 0) ? pOwn : pNei;
+        return VT::mul(F, phif);
+    }
     struct Face { double F, w; T pO; };
     __device__ __forceinline__ T cell(int c) const { return VT::ld(phi, c); }
     __device__ __forceinline__ Face load(int f, int other) const
@@ -106,6 +131,18 @@ struct GradOp // gaussGreenGrad.cpp:46-64 with linear.cpp:30-45
     const double* __restrict__ w;
     const double* __restrict__ phi;
     const double* __restrict__ phiB;
+    using CV = S1;
+    static constexpr int W0 = 3, W1 = 1; // stream 0 = Sf (Vec3), stream 1 = weights
+    __device__ __forceinline__ bool ownsStreams() const { return true; }
+    __host__ __device__ __forceinline__ const double* s0() const { return Sf; }
+    __host__ __device__ __forceinline__ const double* s1() const { return w; }
+    __host__ __device__ __forceinline__ const double* cells() const { return phi; }
+    __device__ __forceinline__ T fluxv(const double* a, const double* b, double pOwn, double pNei) const
+    {
+        const double wf = b[0];
+        const double phif = wf * pOwn + (1 - wf) * pNei;
+        return Vec3d {a[0] * phif, a[1] * phif, a[2] * phif};
+    }
     struct Face { Vec3d s; double w, pO; };
     __device__ __forceinline__ double cell(int c) const { return phi[c]; }
     __device__ __forceinline__ Face load(int f, int other) const { return Face {ld3(Sf, f), w[f], phi[other]}; }
@@ -140,6 +177,16 @@ struct LaplacianOp // gaussGreenLaplacian.cpp:34-52 with uncorrected.cpp:34-51
     const double* __restrict__ dc; // nonOrthDeltaCoeffs
     const double* __restrict__ phi;
     const double* __restrict__ phiB;
+    using CV = VT;
+    static constexpr int W0 = 1, W1 = 1; // stream 0 = magSf, stream 1 = nonOrthDeltaCoeffs
+    __device__ __forceinline__ bool ownsStreams() const { return true; }
+    __host__ __device__ __forceinline__ const double* s0() const { return magSf; }
+    __host__ __device__ __forceinline__ const double* s1() const { return dc; }
+    __host__ __device__ __forceinline__ const double* cells() const { return phi; }
+    __device__ __forceinline__ T fluxv(const double* a, const double* b, const T& pOwn, const T& pNei) const
+    {
+        return VT::mul(a[0], VT::mul(b[0], VT::sub(pNei, pOwn)));
+    }
     struct Face { double a, d; T pO; };
     __device__ __forceinline__ T cell(int c) const { return VT::ld(phi, c); }
     __device__ __forceinline__ Face load(int f, int other) const { return Face {magSf[f], dc[f], VT::ld(phi, other)}; }
@@ -167,6 +214,13 @@ struct SurfIntOp // surfaceIntegrate.cpp:26-41
     using V = VT;
     using T = typename VT::T;
     const double* __restrict__ flux_;
+    using CV = void; // no cell field
+    static constexpr int W0 = VT::NC, W1 = 0; // stream 0 = the face flux itself
+    __device__ __forceinline__ bool ownsStreams() const { return false; }
+    __host__ __device__ __forceinline__ const double* s0() const { return flux_; }
+    __host__ __device__ __forceinline__ const double* s1() const { return nullptr; }
+    __host__ __device__ __forceinline__ const double* cells() const { return nullptr; }
+    __device__ __forceinline__ T fluxv(const double* a, const double*, int, int) const { return VT::ld(a, 0); }
     struct Face { T v; };
     __device__ __forceinline__ int cell(int) const { return 0; }
     __device__ __forceinline__ Face load(int f, int) const { return Face {VT::ld(flux_, f)}; }
@@ -279,6 +333,286 @@ k_gather_plan(Op op, Scaling sc, int nC, int nI, const int* __restrict__ seg, co
     finish<VT>(out, c, acc, s, mode);
 }
 
+// ---- variant 6 (opt-in, owner-sorted meshes): TMA-staged tile kernel, optionally double-buffered -------------
+// A persistent grid (a few blocks per SM) walks the tiles of the mesh's FvkTilePlan. Everything a tile
+// streams -- the face streams of its own faces (e.g. faceFlux + weights), the cells' phi, and ONE blob with
+// all mesh-static data (volumes, neighbour labels, slot codes, segments, cross / boundary face lists) -- is
+// a contiguous range, so one elected thread stages it with 3-4 cp.async.bulk copies (TMA, completion on an
+// mbarrier) into one of two shared-memory stages while the block computes on the other: no registers, no
+// dependent index loads, every byte through L2 once, loads never wait for compute. Per tile:
+//   A1  thread per cell: flux of the cell's own faces from the staged streams (phi of an in-tile neighbour
+//       from shared memory, otherwise one global gather)                                  -> slot [0, nf)
+//   A2  thread per cross face (owner outside the tile): evaluated from global memory      -> slot [nf, nf+nx)
+//   A3  thread per boundary face                                                          -> slot [nf+nx, ..)
+//   B   thread per cell: adds the cell's slots in the reference's order (owner side +, neighbour side -),
+//       scales by coeff/V and writes the result once.
+// Bit-identical to the per-cell gather (same per-face arithmetic, same summation order).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+struct Stager
+{
+    uint32_t bar;   // mbarrier (shared address)
+    uint32_t bytes; // bytes in flight
+    template <class E>
+    static __device__ __forceinline__ int lead(int64_t start) { return int(start & (16 / int(sizeof(E)) - 1)); }
+    // Executed by ONE thread. Stage elements [start, start+count) of the 16-byte aligned global array `g` (which
+    // holds `len` readable elements) so that element start+i lands at sm[lead + i]: ONE cp.async.bulk over the
+    // enclosing 16-byte aligned range (over-fetching < 16 bytes on either side). Only a range that would run past
+    // `len` is cut at the last aligned boundary and finished with plain loads (at most one tile per array).
+    template <class E>
+    __device__ __forceinline__ void stage(E* sm, const E* g, int64_t start, int count, int64_t len)
+    {
+        constexpr int PER = 16 / int(sizeof(E));
+        if (count <= 0) return;
+        const int64_t a0 = start & ~int64_t(PER - 1);
+        int64_t a1 = (start + count + PER - 1) & ~int64_t(PER - 1);
+        if (a1 > len)
+        {
+            a1 = (start + count) & ~int64_t(PER - 1);
+            for (int64_t i = (a1 > a0 ? a1 : start); i < start + count; ++i) sm[i - a0] = g[i];
+        }
+        if (a1 > a0)
+        {
+            const uint32_t nbytes = uint32_t((a1 - a0) * sizeof(E));
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(smem_u32(sm)), "l"(g + a0), "r"(nbytes), "r"(bar) : "memory");
+            bytes += nbytes;
+        }
+    }
+};
+
+template <class CV>
+struct CellLd
+{
+    using T = typename CV::T;
+    static constexpr int NC = CV::NC;
+    static __device__ __forceinline__ T ld(const double* p, int64_t i) { return CV::ld(p, i); }
+};
+template <>
+struct CellLd<void>
+{
+    using T = int;
+    static constexpr int NC = 0;
+    static __device__ __forceinline__ int ld(const double*, int64_t) { return 0; }
+};
+
+__host__ __device__ inline size_t al16(size_t n) { return (n + 15) & ~size_t(15); }
+// shared-memory layout: [2 mbarriers | 2 tile headers | sflux | stage 0 | stage 1], stage = S0 | S1 | phi | blob
+template <class Op, int NSTAGE>
+struct TileSmem
+{
+    using VT = typename Op::V;
+    static constexpr int CN = CellLd<typename Op::CV>::NC;
+    size_t s0, s1, phi, blob, stage, flux, total;
+    __host__ __device__ explicit TileSmem(const FvkTilePlan& tp)
+    {
+        s0 = 0;
+        s1 = s0 + al16(sizeof(double) * (size_t(Op::W0) * tp.maxF + 4));
+        phi = s1 + al16(sizeof(double) * (size_t(Op::W1) * tp.maxF + 4));
+        blob = phi + al16(sizeof(double) * (size_t(CN) * tp.maxC + 4));
+        stage = blob + al16(size_t(tp.maxBlob));
+        flux = 16 + al16(2 * sizeof(FvkTileHdr));
+        total = flux + al16(sizeof(typename VT::T) * (size_t(tp.maxF) + tp.maxX + tp.maxB + 1)) + NSTAGE * stage;
+    }
+};
+
+template <class Op, int NSTAGE>
+__global__ void __launch_bounds__(256)
+k_gather_tile(Op op, Scaling sc, FvkTilePlan tp, int nI, double* __restrict__ out, int mode)
+{
+    using VT = typename Op::V;
+    using T = typename VT::T;
+    using CL = CellLd<typename Op::CV>;
+    using CT = typename CL::T;
+    constexpr int CN = CL::NC;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const TileSmem<Op, NSTAGE> lay(tp);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+    FvkTileHdr* sHdr = reinterpret_cast<FvkTileHdr*>(smem + 16);
+    T* sflux = reinterpret_cast<T*>(smem + lay.flux);
+    unsigned char* stage0 = smem + lay.total - NSTAGE * lay.stage;
+
+    const int G = gridDim.x;
+    int t = blockIdx.x;
+    if (t >= tp.nTiles) return;
+    const bool producer = threadIdx.x == 0;
+    const int64_t nF = int64_t(nI) + tp.nB, big = int64_t(1) << 60; // mesh/plan arrays carry 16 bytes of slack
+    const int64_t lenS0 = op.ownsStreams() ? big : int64_t(Op::W0) * nF, lenPhi = int64_t(CN) * tp.nCells;
+
+    auto issue = [&](int stg, const FvkTileHdr& h) {
+        unsigned char* base = stage0 + size_t(stg) * lay.stage;
+        Stager st {smem_u32(bars + stg), 0u};
+        st.stage(base + lay.blob, tp.blob, h.blobOff, h.blobBytes, big);
+        st.stage(reinterpret_cast<double*>(base + lay.s0), op.s0(), int64_t(Op::W0) * h.f0, Op::W0 * h.nf, lenS0);
+        if (Op::W1) st.stage(reinterpret_cast<double*>(base + lay.s1), op.s1(), int64_t(Op::W1) * h.f0, Op::W1 * h.nf, big);
+        if (CN) st.stage(reinterpret_cast<double*>(base + lay.phi), op.cells(), int64_t(CN) * h.c0, CN * h.nc, lenPhi);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(st.bar), "r"(st.bytes) : "memory");
+        sHdr[stg] = h;
+    };
+
+    FvkTileHdr hn; // producer only: header of the next tile to issue
+    if (producer)
+    {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(bars)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(bars + 1)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        hn = tp.hdr[t];
+        issue(0, hn);
+        if (t + G < tp.nTiles) hn = tp.hdr[t + G];
+    }
+    const double* cellsG = op.cells();
+    for (int k = 0; t < tp.nTiles; ++k, t += G)
+    {
+        const int cur = k & (NSTAGE - 1);
+        if (producer)
+        {
+            if (NSTAGE == 2 && t + G < tp.nTiles)
+            {
+                // stage cur^1 was released by the barrier that ended the previous iteration
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(cur ^ 1, hn);
+                if (t + 2 * G < tp.nTiles) hn = tp.hdr[t + 2 * G];
+            }
+            const uint32_t parity = (NSTAGE == 2 ? (k >> 1) : k) & 1;
+            uint32_t done = 0;
+            while (!done)
+                asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                             : "=r"(done) : "r"(smem_u32(bars + cur)), "r"(parity) : "memory");
+        }
+        __syncthreads(); // stage `cur` has landed (and sHdr[cur] is visible)
+        const FvkTileHdr h = sHdr[cur];
+        const unsigned char* base = stage0 + size_t(cur) * lay.stage;
+        const double* sS0 = reinterpret_cast<const double*>(base + lay.s0) + Stager::lead<double>(int64_t(Op::W0) * h.f0);
+        const double* sS1 = reinterpret_cast<const double*>(base + lay.s1) + Stager::lead<double>(int64_t(Op::W1) * h.f0);
+        const double* sPhi = reinterpret_cast<const double*>(base + lay.phi) + Stager::lead<double>(int64_t(CN) * h.c0);
+        const unsigned char* sBlob = base + lay.blob;
+        const FvkBlobLayout L = fvk_blob_layout(h.nc, h.nf, h.nx, h.nb, h.ne);
+        const double* sV = reinterpret_cast<const double*>(sBlob);
+        const int* sNei = reinterpret_cast<const int*>(sBlob + L.nei);
+        const int* sXF = reinterpret_cast<const int*>(sBlob + L.xFace);
+        const int* sXO = reinterpret_cast<const int*>(sBlob + L.xOwner);
+        const int* sBF = reinterpret_cast<const int*>(sBlob + L.bFace);
+        const uint16_t* sSeg = reinterpret_cast<const uint16_t*>(sBlob + L.seg);
+        const uint16_t* sOseg = reinterpret_cast<const uint16_t*>(sBlob + L.oseg);
+        const uint16_t* sCode = reinterpret_cast<const uint16_t*>(sBlob + L.code);
+        const uint16_t* sXC = reinterpret_cast<const uint16_t*>(sBlob + L.xCell);
+        const uint16_t* sBC = reinterpret_cast<const uint16_t*>(sBlob + L.bCell);
+
+        // ---- A2 operands of this thread's first cross face are requested before A1 so both gather rounds overlap
+        const bool hx = int(threadIdx.x) < h.nx;
+        double xa[Op::W0], xb[Op::W1 ? Op::W1 : 1];
+        CT xpo = CL::ld(sPhi, 0);
+        if (hx)
+        {
+            const int f = sXF[threadIdx.x];
+            xpo = CL::ld(cellsG, sXO[threadIdx.x]);
+#pragma unroll
+            for (int q = 0; q < Op::W0; ++q) xa[q] = op.s0()[int64_t(Op::W0) * f + q];
+            if (Op::W1) xb[0] = op.s1()[f];
+        }
+        // ---- A1: own faces, thread per cell
+        for (int i = threadIdx.x; i < h.nc; i += 256)
+        {
+            const CT pc = CL::ld(sPhi, i);
+            const int j1 = sOseg[i + 1];
+            for (int j = sOseg[i]; j < j1; ++j)
+            {
+                const int n = sNei[j];
+                const unsigned nl = unsigned(n - h.c0);
+                const CT pn = (nl < unsigned(h.nc)) ? CL::ld(sPhi, nl) : CL::ld(cellsG, n);
+                sflux[j] = op.fluxv(sS0 + Op::W0 * j, sS1 + Op::W1 * j, pc, pn);
+            }
+        }
+        // ---- A2: cross faces (this tile holds the neighbour cell), thread per face
+        if (hx) sflux[h.nf + threadIdx.x] = op.fluxv(xa, xb, xpo, CL::ld(sPhi, sXC[threadIdx.x]));
+        for (int i = threadIdx.x + 256; i < h.nx; i += 256)
+        {
+            const int f = sXF[i];
+            const CT po = CL::ld(cellsG, sXO[i]);
+            const CT pn = CL::ld(sPhi, sXC[i]);
+            double a[Op::W0], b[Op::W1 ? Op::W1 : 1];
+#pragma unroll
+            for (int q = 0; q < Op::W0; ++q) a[q] = op.s0()[int64_t(Op::W0) * f + q];
+            if (Op::W1) b[0] = op.s1()[f];
+            sflux[h.nf + i] = op.fluxv(a, b, po, pn);
+        }
+        // ---- A3: boundary faces
+        for (int i = threadIdx.x; i < h.nb; i += 256)
+        {
+            const int f = sBF[i];
+            sflux[h.nf + h.nx + i] = op.boundary(f, f - nI, h.c0 + sBC[i]);
+        }
+        __syncthreads();
+        // ---- B: per-cell accumulation in the reference's order
+        for (int i = threadIdx.x; i < h.nc; i += 256)
+        {
+            const int c = h.c0 + i;
+            T acc = (mode == FVK_ACC_SCALE) ? VT::ld(out, c) : VT::zero();
+            const int e1 = sSeg[i + 1];
+            for (int e = sSeg[i]; e < e1; ++e)
+            {
+                const unsigned code = sCode[e];
+                const T v = sflux[code >> 1];
+                acc = (code & 1u) ? VT::sub(acc, v) : VT::add(acc, v);
+            }
+            const double vol = sV[i];
+            double s;
+            if (sc.invVolOnly) s = 1 / vol;
+            else s = (sc.view ? sc.view[c] * sc.coeff : sc.coeff) / vol;
+            finish<VT>(out, c, acc, s, mode);
+        }
+        __syncthreads(); // stage `cur` and sflux are free again
+        if (NSTAGE == 1 && producer && t + G < tp.nTiles)
+        {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(0, hn);
+            if (t + 2 * G < tp.nTiles) hn = tp.hdr[t + 2 * G];
+        }
+    }
+}
+
+template <class Op, int NSTAGE>
+int launch_tile_n(const fvk_mesh* m, Op op, Scaling sc, double* out, int mode, cudaStream_t st)
+{
+    static int blocksPerSm[64] = {0};
+    static size_t cachedBytes[64] = {0};
+    static bool optedIn[64] = {false};
+    const TileSmem<Op, NSTAGE> lay(m->tp);
+    const size_t bytes = lay.total;
+    if (bytes > 220 * 1024) return -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return -1;
+    if (!optedIn[dev])
+    {
+        // opt in to large dynamic shared memory once per device and instantiation
+        FVK_CUDA(cudaFuncSetAttribute(k_gather_tile<Op, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        optedIn[dev] = true;
+    }
+    if (cachedBytes[dev] != bytes)
+    {
+        int nb = 0;
+        FVK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gather_tile<Op, NSTAGE>, 256, bytes));
+        blocksPerSm[dev] = nb > 0 ? nb : 1;
+        cachedBytes[dev] = bytes;
+    }
+    // NSTAGE 2: persistent grid, loads of tile k+1 overlap compute of tile k inside a block.
+    // NSTAGE 1: one tile per block; overlap comes from the 2x more blocks resident per SM.
+    int grid = (NSTAGE == 2) ? fvk_sm_count() * blocksPerSm[dev] : m->tp.nTiles;
+    if (grid > m->tp.nTiles) grid = m->tp.nTiles;
+    k_gather_tile<Op, NSTAGE><<<grid, 256, bytes, st>>>(op, sc, m->tp, m->nInternalFaces, out, mode);
+    FVK_LAUNCH_CHECK();
+    return FVK_OK;
+}
+template <class Op>
+int launch_tile(const fvk_mesh* m, Op op, Scaling sc, double* out, int mode, cudaStream_t st)
+{
+    static const int stages = [] { const char* e = std::getenv("FVK_TILE_STAGES"); return e ? std::atoi(e) : 1; }();
+    return stages == 2 ? launch_tile_n<Op, 2>(m, op, sc, out, mode, st) : launch_tile_n<Op, 1>(m, op, sc, out, mode, st);
+}
+
+__host__ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
 template <class Op>
 int launch_gather(const fvk_mesh* m, Op op, Scaling sc, double* out, int mode, fvk_stream stream)
 {
@@ -288,6 +622,14 @@ int launch_gather(const fvk_mesh* m, Op op, Scaling sc, double* out, int mode, f
     const int nI = m->nInternalFaces;
     const int grid = (nC + 255) / 256;
     const int variant = (nI == 0) ? 0 : fvk_variant(); // the plan kernels read face 0 on padded lanes
+    if (nC == 0) return FVK_OK;
+    // variant 6: TMA-staged tile kernel. Parity-green but (r1 measurements, profiles/r1_tile_kernel_sweep.md) not yet
+    // faster than the per-cell gather, so it is opt-in until the staging pipeline is tuned.
+    if (variant == 6 && m->tp.nTiles > 0 && aligned16(op.s0()) && aligned16(op.s1()) && aligned16(op.cells()))
+    {
+        const int rc = launch_tile(m, op, sc, out, mode, fvk_cu(stream));
+        if (rc >= 0) return rc; // -1: tile does not fit in shared memory -> per-cell gather below
+    }
     const int2* plan = reinterpret_cast<const int2*>(m->gatherPlan);
     cudaStream_t st = fvk_cu(stream);
     switch (variant)
@@ -296,7 +638,7 @@ int launch_gather(const fvk_mesh* m, Op op, Scaling sc, double* out, int mode, f
         case 2: k_gather_plan<Op, 2><<<grid, 256, 0, st>>>(op, sc, nC, nI, m->stencilSeg, plan, out, mode); break;
         case 3: k_gather_plan<Op, 6><<<grid, 256, 0, st>>>(op, sc, nC, nI, m->stencilSeg, plan, out, mode); break;
         case 4: k_gather_plan<Op, 1><<<grid, 256, 0, st>>>(op, sc, nC, nI, m->stencilSeg, plan, out, mode); break;
-        default: // measured best at 256^3 (profiles/r1_roofline_*.jsonl): full occupancy, 32 registers
+        default: // variant 0 (default): per-cell gather over the unified sorted stencil
             k_gather_stencil<Op><<<grid, 256, 0, st>>>(op, sc, nC, nI, m->stencilSeg, m->gatherEnt, m->owner, m->neighbour, out, mode);
             break;
     }

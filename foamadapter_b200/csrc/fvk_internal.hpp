@@ -5,8 +5,59 @@
 #include <cstddef>
 #include <cstdint>
 
+
 // record an error message (thread-local) and return `code`
 int fvk_fail(int code, const char* fmt, ...);
+
+// Tile plan of the explicit gather kernels (built once per mesh on the host, fvk_mesh.cu).
+// Tile t owns the consecutive cells [c0, c0+nc) and the faces those cells own [f0, f0+nf) -- contiguous because
+// OpenFOAM orders faces by owner. Every face value a tile needs gets a SLOT in shared memory:
+//   [0, nf)            the tile's own faces (flux evaluated once, used by owner AND in-tile neighbour)
+//   [nf, nf+nx)        "cross" faces: owned by another tile (or a ghost cell) with their neighbour in this tile
+//   [nf+nx, nf+nx+nb)  boundary faces of the tile's cells
+// Everything mesh-static a tile needs lives in ONE contiguous, 16-byte aligned blob (one TMA bulk copy):
+//   V[nc] f64 | neighbour[nf] i32 | xFace[nx] i32 | xOwner[nx] i32 | bFace[nb] i32 |
+//   seg[nc+1] u16 | oseg[nc+1] u16 | code[ne] u16 | xCell[nx] u16 | bCell[nb] u16     (each section 16-byte aligned)
+// code[e] = (slot << 1) | side lists, per cell, the slots in the reference's accumulation order (side 1 = the
+// cell is the face's neighbour -> subtract); seg / oseg are tile-local offsets into code / the own-face slots.
+struct FvkTileHdr
+{
+    int32_t c0, nc, f0, nf, nx, nb, ne, blobBytes;
+    int64_t blobOff;
+};
+struct FvkTilePlan
+{
+    int32_t nTiles = 0;
+    int32_t nCells = 0, nB = 0; // array lengths (owned + ghost cells, boundary faces) for the staging bounds
+    int32_t maxC = 0, maxF = 0, maxX = 0, maxB = 0, maxE = 0, maxBlob = 0;
+    FvkTileHdr* hdr = nullptr;
+    unsigned char* blob = nullptr;
+};
+// section offsets inside a tile blob
+struct FvkBlobLayout
+{
+    int32_t nei, xFace, xOwner, bFace, seg, oseg, code, xCell, bCell, total;
+};
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline FvkBlobLayout fvk_blob_layout(int32_t nc, int32_t nf, int32_t nx, int32_t nb, int32_t ne)
+{
+    auto al = [](int32_t n) { return (n + 15) & ~15; };
+    FvkBlobLayout L;
+    int32_t o = al(8 * nc);
+    L.nei = o; o += al(4 * nf);
+    L.xFace = o; o += al(4 * nx);
+    L.xOwner = o; o += al(4 * nx);
+    L.bFace = o; o += al(4 * nb);
+    L.seg = o; o += al(2 * (nc + 1));
+    L.oseg = o; o += al(2 * (nc + 1));
+    L.code = o; o += al(2 * ne);
+    L.xCell = o; o += al(2 * nx);
+    L.bCell = o; o += al(2 * nb);
+    L.total = o;
+    return L;
+}
 
 // Device-side mesh. All arrays are device pointers in reference order.
 struct fvk_mesh
@@ -44,4 +95,5 @@ struct fvk_mesh
     int32_t nBndCells = 0;
     int32_t *bndCell = nullptr, *bndSeg = nullptr, *bndFace = nullptr;
     uint32_t* hasBnd = nullptr; // bitmask [ceil(nCells/32)]
+    FvkTilePlan tp; // tile plan of the explicit gather kernels (nTiles == 0: faces not sorted by owner)
 };

@@ -10,6 +10,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <algorithm>
 #include <cstring>
 #include <utility>
@@ -182,7 +183,7 @@ int upload(T** dst, const T* src, size_t n)
 {
     *dst = nullptr;
     if (n == 0) return FVK_OK;
-    FVK_CUDA(cudaMalloc(reinterpret_cast<void**>(dst), n * sizeof(T)));
+    FVK_CUDA(cudaMalloc(reinterpret_cast<void**>(dst), n * sizeof(T) + 16)); // 16 bytes of slack: bulk copies over-fetch
     FVK_CUDA(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
     return FVK_OK;
 }
@@ -202,7 +203,7 @@ extern "C" int fvk_mesh_destroy(fvk_mesh* m)
                     m->weights, m->deltaCoeffs, m->nonOrthDeltaCoeffs, m->stencilSeg, m->stencilVal,
                     m->gatherEnt, m->gatherPlan, m->rowOffs, m->colIdxs, m->ownerOffset, m->neighbourOffset,
                     m->diagOffset, m->ownStart, m->lowSeg, m->lowFace, m->lowOwner, m->bndCell,
-                    m->bndSeg, m->bndFace, m->hasBnd};
+                    m->bndSeg, m->bndFace, m->hasBnd, m->tp.hdr, m->tp.blob};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete m;
@@ -318,6 +319,120 @@ extern "C" int fvk_mesh_create(const fvk_mesh_desc* d, fvk_mesh** out)
                 }
             }
         }
+        // ---- tile plan (see FvkTilePlan): consecutive owned cells, bounded slot / entry counts
+        {
+            bool sorted = nI > 0;
+            for (int32_t f = 1; f < nI && sorted; ++f) sorted = own[f - 1] <= own[f];
+            int tileCells = 256;
+            if (const char* e = std::getenv("FVK_TILE_CELLS")) tileCells = std::atoi(e);
+            if (tileCells < 32) tileCells = 32;
+            if (tileCells > 2048) tileCells = 2048;
+            const int32_t maxSlots = 12 * tileCells, maxEnt = 16 * tileCells; // uint16 codes: slot < 32768
+            if (sorted)
+            {
+                const int32_t nOwned = m->nOwned;
+                std::vector<int32_t> os(size_t(nC) + 1, 0);
+                for (int32_t f = 0; f < nI; ++f) ++os[size_t(own[f]) + 1];
+                for (int32_t c = 0; c < nC; ++c) os[size_t(c) + 1] += os[c];
+                // greedy tiling; a cell's slot demand is bounded by its entry count
+                std::vector<int32_t> tc(1, 0), cellTile(nC, -1);
+                int32_t cells = 0, ents = 0;
+                bool ok = true;
+                for (int32_t c = 0; c < nOwned; ++c)
+                {
+                    const int32_t k = seg[size_t(c) + 1] - seg[c];
+                    if (k > maxSlots) { ok = false; break; }
+                    if (cells == tileCells || ents + k > maxSlots)
+                    {
+                        tc.push_back(c);
+                        cells = 0; ents = 0;
+                    }
+                    cellTile[c] = int32_t(tc.size()) - 1;
+                    ++cells; ents += k;
+                }
+                if (ok && nOwned > 0)
+                {
+                    tc.push_back(nOwned);
+                    const int32_t nT = int32_t(tc.size()) - 1;
+                    std::vector<FvkTileHdr> hdr(nT);
+                    std::vector<unsigned char> blob;
+                    std::vector<uint16_t> tseg, oseg, code, xCell, bCell;
+                    std::vector<int32_t> xFace, xOwner, bFace;
+                    FvkTilePlan& tp = m->tp;
+                    for (int32_t t = 0; t < nT && ok; ++t)
+                    {
+                        FvkTileHdr& h = hdr[t];
+                        h.c0 = tc[t]; h.nc = tc[size_t(t) + 1] - tc[t];
+                        h.f0 = os[h.c0]; h.nf = os[h.c0 + h.nc] - h.f0;
+                        tseg.clear(); oseg.clear(); code.clear(); xCell.clear(); bCell.clear();
+                        xFace.clear(); xOwner.clear(); bFace.clear();
+                        int32_t nx = 0, nb = 0, ne = 0;
+                        // first pass: count cross and boundary faces so slots can be numbered
+                        for (int32_t c = h.c0; c < h.c0 + h.nc; ++c)
+                            for (int32_t k = seg[c]; k < seg[size_t(c) + 1]; ++k)
+                            {
+                                const int32_t f = ent[k] >> 1;
+                                if (f >= nI) ++nb;
+                                else if ((ent[k] & 1) && !(own[f] < nOwned && cellTile[own[f]] == t)) ++nx;
+                            }
+                        int32_t ix = 0, ib = 0;
+                        for (int32_t c = h.c0; c < h.c0 + h.nc; ++c)
+                        {
+                            tseg.push_back(uint16_t(ne));
+                            oseg.push_back(uint16_t(os[c] - h.f0));
+                            for (int32_t k = seg[c]; k < seg[size_t(c) + 1]; ++k, ++ne)
+                            {
+                                const int32_t f = ent[k] >> 1, side = ent[k] & 1;
+                                int32_t slot;
+                                if (f >= nI)
+                                {
+                                    slot = h.nf + nx + ib++;
+                                    bFace.push_back(f); bCell.push_back(uint16_t(c - h.c0));
+                                }
+                                else if (!side || (own[f] < nOwned && cellTile[own[f]] == t))
+                                    slot = f - h.f0; // own face, or lower face owned inside the tile
+                                else
+                                {
+                                    slot = h.nf + ix++;
+                                    xFace.push_back(f); xOwner.push_back(own[f]); xCell.push_back(uint16_t(c - h.c0));
+                                }
+                                code.push_back(uint16_t((slot << 1) | side));
+                            }
+                        }
+                        tseg.push_back(uint16_t(ne));
+                        oseg.push_back(uint16_t(h.nf));
+                        h.nx = nx; h.nb = nb; h.ne = ne;
+                        if (h.nf + nx + nb >= 32768 || ne >= 65536) { ok = false; break; }
+                        const FvkBlobLayout L = fvk_blob_layout(h.nc, h.nf, nx, nb, ne);
+                        h.blobOff = int64_t(blob.size()); h.blobBytes = L.total;
+                        blob.resize(blob.size() + size_t(L.total), 0);
+                        unsigned char* bp = blob.data() + h.blobOff;
+                        std::memcpy(bp, d->cellVolumes + h.c0, sizeof(double) * size_t(h.nc));
+                        if (h.nf) std::memcpy(bp + L.nei, nei + h.f0, sizeof(int32_t) * size_t(h.nf));
+                        if (nx) std::memcpy(bp + L.xFace, xFace.data(), sizeof(int32_t) * size_t(nx));
+                        if (nx) std::memcpy(bp + L.xOwner, xOwner.data(), sizeof(int32_t) * size_t(nx));
+                        if (nb) std::memcpy(bp + L.bFace, bFace.data(), sizeof(int32_t) * size_t(nb));
+                        std::memcpy(bp + L.seg, tseg.data(), sizeof(uint16_t) * tseg.size());
+                        std::memcpy(bp + L.oseg, oseg.data(), sizeof(uint16_t) * oseg.size());
+                        if (ne) std::memcpy(bp + L.code, code.data(), sizeof(uint16_t) * size_t(ne));
+                        if (nx) std::memcpy(bp + L.xCell, xCell.data(), sizeof(uint16_t) * size_t(nx));
+                        if (nb) std::memcpy(bp + L.bCell, bCell.data(), sizeof(uint16_t) * size_t(nb));
+                        tp.maxC = std::max(tp.maxC, h.nc); tp.maxF = std::max(tp.maxF, h.nf);
+                        tp.maxX = std::max(tp.maxX, nx); tp.maxB = std::max(tp.maxB, nb); tp.maxE = std::max(tp.maxE, ne);
+                        tp.maxBlob = std::max(tp.maxBlob, L.total);
+                    }
+                    (void) maxEnt;
+                    if (ok)
+                    {
+                        UP(tp.hdr, hdr.data(), hdr.size());
+                        UP(tp.blob, blob.data(), blob.size());
+                        tp.nTiles = nT; tp.nCells = nC; tp.nB = nB;
+                    }
+                    else
+                        tp = FvkTilePlan {};
+                }
+            }
+        }
         UP(stencilSeg, seg.data(), seg.size());
         UP(stencilVal, val.data(), nEnt);
         UP(gatherEnt, ent.data(), nEnt);
@@ -415,7 +530,7 @@ extern "C" int fvk_mesh_create(const fvk_mesh_desc* d, fvk_mesh** out)
     {
         cudaError_t e = cudaSuccess;
         for (double** p : {&m->weights, &m->deltaCoeffs, &m->nonOrthDeltaCoeffs})
-            if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(p), sizeof(double) * size_t(nF));
+            if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(p), sizeof(double) * size_t(nF) + 16);
         if (e == cudaSuccess)
         {
             const int grid = int((nF + 255) / 256 < 148 * 16 ? (nF + 255) / 256 : 148 * 16);

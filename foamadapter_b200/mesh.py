@@ -120,7 +120,7 @@ class MeshDesc:
             patchOffsets=np.array([0, 1, 2], dtype=np.int32)), patch_names=["left", "right"])
 
     def __del__(self):
-        if self._owned_ptr is not None and _capi._lib is not None:
+        if getattr(self, "_owned_ptr", None) is not None and _capi is not None and _capi._lib is not None:
             _capi._lib.fvk_blockmesh_destroy(self._owned_ptr)
             self._owned_ptr = None
 
@@ -184,7 +184,7 @@ class UnstructuredMesh:
         self.patch_offsets = list(off)
 
     def __del__(self):
-        if getattr(self, "_h", None) and _capi._lib is not None:
+        if getattr(self, "_h", None) and _capi is not None and _capi._lib is not None:
             _capi._lib.fvk_mesh_destroy(self._h)
             self._h = None
 

@@ -73,7 +73,7 @@ def test_mesh_handle_matches_oracle(case):
     assert np.array_equal(gm.to_host(M.NONORTH_DELTACOEFFS), om.nodc)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 6])
 @pytest.mark.parametrize("vec", [False, True])
 @pytest.mark.parametrize("scheme", [0, 1])
 def test_div(case, scheme, vec, variant):
@@ -100,7 +100,7 @@ def test_div(case, scheme, vec, variant):
         _capi.lib().fvk_set_variant(0)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 6])
 def test_grad(case, variant):
     name, d, gm, om = case
     phi, phib, _, _ = _fields(om, 2)
@@ -113,7 +113,7 @@ def test_grad(case, variant):
         _capi.lib().fvk_set_variant(0)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 6])
 @pytest.mark.parametrize("vec", [False, True])
 def test_laplacian(case, vec, variant):
     name, d, gm, om = case

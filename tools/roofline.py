@@ -36,7 +36,7 @@ def timeit(fn, reps, flush):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--mesh", type=int, nargs="+", default=[128, 256])
-    ap.add_argument("--variants", type=int, nargs="+", default=[0, 1, 2, 3])
+    ap.add_argument("--variants", type=int, nargs="+", default=[0, 6, 1])
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--out", default=str(ROOT / "gpurun_out" / "roofline.jsonl"))
     args = ap.parse_args()
