@@ -270,9 +270,10 @@ int assemble_impl(const fvk_mesh* m, int nTerms, const fvk_term* terms_h, const 
         if (!m->bDeltaCoeffs) return fvk_fail(FVK_EINVAL, "fvk_assemble: mesh has no boundary deltaCoeffs");
         b = *bd;
     }
-    AsmMesh am {m->nOwned, m->nInternalFaces, m->stencilSeg, m->gatherEnt, m->rowOffs, m->diagOffset, m->ownerOffset,
+    // all rows incl. ghost rows: a ghost row's off-diagonals over the cut faces are read by updateFaceVelocity
+    AsmMesh am {m->nCells, m->nInternalFaces, m->stencilSeg, m->gatherEnt, m->rowOffs, m->diagOffset, m->ownerOffset,
                 m->neighbourOffset, m->V, m->weights, m->nonOrthDeltaCoeffs, m->magSf, m->bDeltaCoeffs};
-    const int grid = (m->nOwned + 255) / 256;
+    const int grid = (m->nCells + 255) / 256;
     k_assemble<VT><<<grid, 256, 0, fvk_cu(s)>>>(T, am, b, values, rhs, bcMatrix, bcRhs, accumulate ? 1 : 0);
     FVK_LAUNCH_CHECK();
     return FVK_OK;

@@ -420,6 +420,32 @@ int fvk_comm_halo_exchange(fvk_comm* comm, double* field, int ncomp, fvk_stream 
 int fvk_comm_allreduce_sum(fvk_comm* comm, double* data_d, int count, fvk_stream stream);
 int fvk_comm_allreduce_max(fvk_comm* comm, double* data_d, int count, fvk_stream stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Domain decomposition (HOST). The reference carries OpenFOAM decomposeParDict files
+ * (tutorials/cavity/system/decomposeParDict:17-24, method hierarchical/simple, n (px py pz)) but no
+ * decomposed solver path, so the layout is defined here: a sub-mesh keeps GHOST CELLS
+ * behind its owned cells (grouped by owning rank, ascending global id), every global internal face that
+ * touches an owned cell stays an internal face (faceOrder = global face id, so sub-domain sums follow the
+ * undecomposed mesh's order), and boundary faces keep their patch. See fvk_decomp.cpp.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct fvk_decomp fvk_decomp;
+/* OpenFOAM `simple` restated: per axis, stable sort by cell-centre coordinate, p equal-count groups;
+ * rank = bx + px*(by + py*bz). cellRank [nCells] (host, out). */
+int fvk_decomp_simple_map(const fvk_mesh_desc* global_h, int px, int py, int pz, int32_t* cellRank);
+int fvk_decompose(const fvk_mesh_desc* global_h, const int32_t* cellRank, int nRanks, int rank,
+                  fvk_decomp** out);
+int fvk_decomp_destroy(fvk_decomp* d);
+/* the sub-mesh description (owned by the fvk_decomp); feed it to fvk_mesh_create */
+const fvk_mesh_desc* fvk_decomp_mesh(const fvk_decomp* d);
+int fvk_decomp_info(const fvk_decomp* d, int32_t* nOwned, int32_t* nGhost, int32_t* nNeighbours);
+/* local -> global maps: cellGlobal [nOwned+nGhost]; faceGlobal [local nI + nB] (global face id, boundary
+ * faces as nI_global + global boundary index) */
+int fvk_decomp_maps(const fvk_decomp* d, const int32_t** cellGlobal, const int32_t** faceGlobal);
+/* halo plan in the form fvk_comm_set_halo takes */
+int fvk_decomp_halo(const fvk_decomp* d, const int32_t** neighbourRanks, const int32_t** sendOffsets,
+                    const int32_t** sendCells, const int32_t** recvOffsets);
+int fvk_comm_set_halo_from_decomp(fvk_comm* comm, const fvk_decomp* d);
+
 /* experiment switch: selects the kernel variant used by the gather operators
  * (0 = default). Used by the roofline harness only. */
 int fvk_set_variant(int variant);
