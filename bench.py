@@ -17,7 +17,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 from pathlib import Path
 
@@ -57,34 +56,36 @@ def peaks():
     return 6650.0, "fallback"
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 100 ms DURING the timed region (B200_PROFILING.md)."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+        self.index, self.proc = index, None
 
-    def run(self):
-        while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self.stop_flag.wait(0.2)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index),
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
 
     def summary(self):
-        self.stop_flag.set()
-        self.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        rows = []
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                self.proc.kill()
+                out = ""
+            rows = [[x.strip() for x in ln.split(",")] for ln in out.splitlines() if ln.strip()]
+        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) >= 6 and r[2 + i].lower().startswith("active")})
+        reasons = sorted({names[i] for r in rows for i in range(4) if len(r) >= 6 and r[2 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
 
@@ -127,6 +128,8 @@ def run_reference(args, rank, world):
     n = args.mesh
     d, T, flux = host_workload(n)
     nC, nI, nB = d.nCells, d.nInternalFaces, d.nBoundaryFaces
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core it can get
+    ocpu.lib().fvo_set_threads(C.c_int(len(os.sched_getaffinity(0))))
     cores = ocpu.max_threads()
     from oracle.cpu import Mesh as OMesh
     om = OMesh.from_desc(d)
@@ -139,20 +142,23 @@ def run_reference(args, rank, world):
         om.grad(T, phib, par=1, res=r2)
         om.laplacian(T, phib, par=1, res=r3)
 
-    for _ in range(args.warmup):
+    for _ in range(min(args.warmup, 2)):
         step()
+    # bounded sample: at most args.steps full steps, and at most ~60 s of CPU work
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    done = 0
+    while done < args.steps and (done == 0 or time.perf_counter() - t0 < 60.0):
         step()
-    dt = (time.perf_counter() - t0) / args.steps
+        done += 1
+    dt = (time.perf_counter() - t0) / done
     value = 3.0 * (nI + nB) / dt
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
+        "steps_requested": args.steps, "warmup": min(args.warmup, 2), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"explicit div+grad+laplacian, {n}^3 block-hex mesh (BASELINE configs[1])"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"full {n}^3 step, OpenMP+atomics restatement of the NeoN CPU executor (oracle/fvo.cpp); "
+                         "sample": f"{done} full {n}^3 steps (bounded to ~60 s), OpenMP+atomics restatement of the NeoN CPU executor (oracle/fvo.cpp); "
                                    "the reference itself needs OpenFOAM/Kokkos/Ginkgo and cannot be built here"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -162,6 +168,75 @@ def run_reference(args, rank, world):
 # ----------------------------------------------------------------------------------------------------
 # native arm
 # ----------------------------------------------------------------------------------------------------
+def solver_path_extras(n, peak):
+    """Secondary measurements of the implicit / solver part of the hot path on the same N^3 mesh (reported under
+    "solver_path", not part of `value`): fused ddt+div+laplacian assembly, CSR SpMV, Jacobi-CG iteration, and one PISO
+    step of the 3-D lid-driven cavity at 64^3. CUDA events / wall clock around synchronised solves."""
+    import torch
+    from foamadapter_b200 import fvcc, la, ops, piso
+    from foamadapter_b200.mesh import MeshDesc, UnstructuredMesh
+    out = {}
+    gm = UnstructuredMesh(MeshDesc.block(n, n, n, 0.1, 0.1, 0.01))
+    nC, nI, nB = mesh_counts(n)
+    nnz = nC + 2 * nI
+    rng = np.random.Generator(np.random.MT19937(42))
+    T = fvcc.VolumeField(gm, "T", 1, [("fixedValue", 10.5), ("fixedValue", 1.5), ("zeroGradient", 0.0)])
+    T.internal.copy_(torch.from_numpy(rng.uniform(1, 2, nC)))
+    T.correctBoundaryConditions()
+    flux = torch.cat([torch.arange(nI, dtype=torch.float64), torch.zeros(nB, dtype=torch.float64)]).cuda()
+    gamma = torch.ones(nI + nB, dtype=torch.float64, device="cuda")
+    old = T.internal - 1.0
+    ls = la.LinearSystem(gm, 1, zero=False)
+    terms = [dict(kind=ops.TERM_DIV, scheme=0, coeff=1.0, faceField=flux), dict(kind=ops.TERM_LAPLACIAN, coeff=-1.0, faceField=gamma),
+             dict(kind=ops.TERM_DDT, coeff=1.0, cellField=old, dt=1.0)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def timed(fn, reps=10):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for _ in range(3):
+            fn()
+        for a_, b_ in ev:
+            flush.zero_()
+            a_.record(); fn(); b_.record()
+        torch.cuda.synchronize()
+        return float(np.median([a_.elapsed_time(b_) for a_, b_ in ev]))
+
+    ms = timed(lambda: ops.assemble(gm, terms, T.boundary, ls.values, ls.rhs, ls.bcMatrix, ls.bcRhs))
+    by = 50 * nI + 85 * nC + 52 * nB
+    out["assemble_ddt_div_lap"] = {"ms": ms, "algorithmic_bytes": by, "achieved_gbs": by / ms / 1e6, "frac": by / ms / 1e6 / peak}
+    sp = la.SparsityPattern.readOrCreate(gm)
+    x = torch.from_numpy(rng.uniform(-1, 1, nC)).cuda()
+    y = torch.empty_like(x)
+    ms = timed(lambda: la.spmv(sp, ls.values, x, y))
+    by = nnz * 12 + nC * 20
+    out["spmv"] = {"ms": ms, "algorithmic_bytes": by, "achieved_gbs": by / ms / 1e6, "frac": by / ms / 1e6 / peak}
+    ops.assemble(gm, [terms[1], terms[2]], T.boundary, ls.values, ls.rhs, ls.bcMatrix, ls.bcRhs)
+    iters = 50
+    solver = la.Solver({"solver": "Ginkgo", "type": "solver::Cg", "preconditioner": {"type": "preconditioner::Jacobi", "max_block_size": 1},
+                        "criteria": {"iteration": iters, "relative_residual_norm": 0.0, "absolute_residual_norm": 0.0}}, check_every=iters + 1)
+    xs = torch.zeros(nC, dtype=torch.float64, device="cuda")
+    solver.solve(ls, xs)
+    ts = []
+    for _ in range(3):
+        xs.zero_(); torch.cuda.synchronize()
+        t0 = time.perf_counter(); solver.solve(ls, xs); torch.cuda.synchronize()
+        ts.append((time.perf_counter() - t0) * 1e3 / iters)
+    ms = float(np.median(ts)); by = nnz * 12 + nC * 20 + 72 * nC
+    out["pcg_jacobi_iteration"] = {"ms": ms, "algorithmic_bytes": by, "achieved_gbs": by / ms / 1e6, "frac": by / ms / 1e6 / peak}
+    del gm, ls, T, solver
+    gmc = UnstructuredMesh(piso.cavity_desc(64, True))
+    app = piso.IcoFoam(gmc, nu=0.01, dt=1e-4 * 20 / 64, check_every=16)
+    for _ in range(2):
+        app.step()
+    torch.cuda.synchronize()
+    ts, its = [], []
+    for _ in range(5):
+        t0 = time.perf_counter(); st = app.step(); torch.cuda.synchronize()
+        ts.append((time.perf_counter() - t0) * 1e3); its.append(sum(s_.numIter for s_ in st))
+    out["piso_step_cavity3d_64"] = {"ms": float(np.median(ts)), "cg_iterations_per_step": its}
+    return out
+
+
 def run_native(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -173,20 +248,40 @@ def run_native(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from foamadapter_b200 import fvcc, ops
     from foamadapter_b200._capi import lib, ptr
-    from foamadapter_b200.mesh import UnstructuredMesh
+    from foamadapter_b200.decomp import Comm, Decomposition, default_split
+    from foamadapter_b200.mesh import MeshDesc, UnstructuredMesh
 
     n = args.mesh
-    d, T_h, flux_h = host_workload(n)
-    nC, nI, nB = d.nCells, d.nInternalFaces, d.nBoundaryFaces
-    nF = nI + nB
-    mesh = UnstructuredMesh(d)
     dev = torch.device("cuda", local_rank)
+    comm, dec = None, None
+    if world == 1:
+        d, T_h, flux_h = host_workload(n)
+        nF_global = d.nInternalFaces + d.nBoundaryFaces
+        phib_sel = None
+    else:
+        # weak scaling: every rank owns an n^3 block of the (n px, n py, n pz) mesh; same cell size as the 1-GPU case
+        px, py, pz = default_split(world)
+        G = MeshDesc.block(n * px, n * py, n * pz, 0.1 * px, 0.1 * py, 0.01 * pz)
+        nF_global = G.nInternalFaces + G.nBoundaryFaces
+        rng = np.random.Generator(np.random.MT19937(42))
+        Tg = rng.uniform(1.0, 2.0, G.nCells)
+        dec = Decomposition(G, world, rank, n=(px, py, pz))
+        d = dec.desc
+        T_h = np.ascontiguousarray(Tg[dec.cellGlobal])
+        fg = dec.faceGlobal.astype(np.float64)
+        flux_h = np.where(dec.faceGlobal < G.nInternalFaces, fg, 0.0)  # phi[f] = global face id, 0 on the boundary
+        del Tg, G
+        comm = Comm.from_torch()
+    nC, nI, nB = d.nCells, d.nInternalFaces, d.nBoundaryFaces
+    mesh = UnstructuredMesh(d)
+    if comm is not None:
+        comm.set_halo(dec)
     bcs = [("fixedValue", 10.5), ("fixedValue", 1.5), ("zeroGradient", 0.0)]
     # distinct phi per operator so no operator finds its input in L2 from the previous one
     fields = []
     for i in range(3):
         f = fvcc.VolumeField(mesh, f"T{i}", 1, bcs, device=dev)
-        f.internal.copy_(torch.from_numpy(T_h + 0.0 * i))
+        f.internal.copy_(torch.from_numpy(T_h))
         f.correctBoundaryConditions()
         fields.append(f)
     flux = torch.from_numpy(flux_h).to(dev)
@@ -201,16 +296,21 @@ def run_native(args, rank, world, local_rank):
              ptr(out_div), C.c_int(0), s)
     a_grad = (mesh.handle, ptr(fields[1].internal), ptr(fields[1].boundary.value), ptr(out_grad), C.c_int(0), s)
     a_lap = (mesh.handle, ptr(fields[2].internal), ptr(fields[2].boundary.value), one, None, ptr(out_lap), C.c_int(0), s)
+    halo = (lambda t: comm.halo_exchange(t)) if comm is not None else (lambda t: None)
 
     def step(ev=None):
+        # multi-GPU: the processor-boundary exchange of each operator's input field is part of the step
         if ev is not None:
             ev[0].record(stream)
+        halo(fields[0].internal)
         rc = L.fvk_div_s(*a_div)
         if ev is not None:
             ev[1].record(stream)
+        halo(fields[1].internal)
         rc |= L.fvk_grad_s(*a_grad)
         if ev is not None:
             ev[2].record(stream)
+        halo(fields[2].internal)
         rc |= L.fvk_laplacian_s(*a_lap)
         if ev is not None:
             ev[3].record(stream)
@@ -243,7 +343,7 @@ def run_native(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
-    value = 3.0 * nF * world / (ms_per_step * 1e-3)
+    value = 3.0 * nF_global / (ms_per_step * 1e-3)
     kern_ms = {name: float(np.mean([evs[k][i].elapsed_time(evs[k][i + 1]) for k in range(args.steps)]))
                for i, name in enumerate(("div", "grad", "laplacian"))}
 
@@ -258,6 +358,7 @@ def run_native(args, rank, world, local_rank):
     def e2e_step():
         f0.internal.copy_(T_pin, non_blocking=True)
         flux.copy_(flux_pin, non_blocking=True)
+        halo(f0.internal)
         f0.correctBoundaryConditions()
         rc = L.fvk_div_s(*a_div)
         rc |= L.fvk_grad_s(mesh.handle, ptr(f0.internal), ptr(f0.boundary.value), ptr(out_grad), C.c_int(0), s)
@@ -281,7 +382,7 @@ def run_native(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item()) / e2e_steps
-    e2e_value = 3.0 * nF * world / (e2e_ms * 1e-3)
+    e2e_value = 3.0 * nF_global / (e2e_ms * 1e-3)
 
     if rank == 0:
         peak, peak_kind = peaks()
@@ -296,33 +397,47 @@ def run_native(args, rank, world, local_rank):
                 traffic = json.loads(tp.read_text()).get(f"{dom}_{n}")
             except Exception:
                 traffic = None
+        halo_note = "" if world == 1 else (f"; {world} sub-domains ({'x'.join(map(str, default_split(world)))}) of one "
+                                           f"{'x'.join(str(n * q) for q in default_split(world))} mesh, NCCL halo exchange of each "
+                                           "operator's input inside the step (kernel ms include it)")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"explicit div+grad+laplacian, {n}^3 block-hex mesh (BASELINE configs[1])",
-                       "cells": nC, "internal_faces": nI, "boundary_faces": nB,
+            "config": {"workload": f"explicit div+grad+laplacian, {n}^3 block-hex mesh per GPU (BASELINE configs[1])" + halo_note,
+                       "cells_per_gpu": mesh.nOwned, "internal_faces_per_gpu": nI, "boundary_faces_per_gpu": nB, "faces_global": nF_global,
                        "l2": "inputs larger than L2: each operator streams 203/338/203 MB (>126 MB L2) and reads its own phi array",
-                       "parallelism": "1 GPU" if world == 1 else f"{world} independent sub-domain replicas (halo exchange not in this bench yet)"},
+                       "parallelism": "1 GPU" if world == 1 else f"domain decomposition, {world} ranks, ghost cells + NCCL send/recv"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                          "frac": kernels[dom]["frac"], "traffic": traffic, "peak_kind": peak_kind},
             "kernels": kernels,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
-            "gpu_launches": 3 * args.steps,
+            "gpu_launches": (3 + (3 if world > 1 else 0)) * args.steps,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:
             from oracle import cpu as ocpu
+            ocpu.lib().fvo_set_threads(C.c_int(len(os.sched_getaffinity(0))))
             cores = ocpu.max_threads()
             t_par = cpu_step_time(n, d, T_h, flux_h, par=1, reps=3)
             t_ser = cpu_step_time(n, d, T_h, flux_h, par=0, reps=1)
             line["cpu_baseline"] = {
-                "value": 3.0 * nF / t_par, "unit": UNIT, "cores": cores, "kind": "port",
+                "value": 3.0 * nF_global / t_par, "unit": UNIT, "cores": cores, "kind": "port",
                 "sample": f"full {n}^3 step (div+grad+laplacian), best of 3, OpenMP+atomics restatement of the NeoN CPU "
-                          f"executor on {cores} threads; Serial executor restatement on 1 core: {3.0 * nF / t_ser:.4g} {UNIT}",
-                "serial_value": 3.0 * nF / t_ser,
+                          f"executor on {cores} threads; Serial executor restatement on 1 core: {3.0 * nF_global / t_ser:.4g} {UNIT}",
+                "serial_value": 3.0 * nF_global / t_ser,
             }
+        if world == 1 and not args.no_extras:
+            del fields, flux, out_div, out_grad, out_lap, mesh
+            torch.cuda.empty_cache()
+            try:
+                line["solver_path"] = solver_path_extras(n, peak)
+            except Exception as e:  # secondary numbers must never cost the headline line
+                line["solver_path"] = {"error": repr(e)}
         print(json.dumps(line), flush=True)
+    if comm is not None:
+        barrier()
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -330,11 +445,12 @@ def run_native(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--mesh", type=int, default=128)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the solver_path secondary measurements")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
