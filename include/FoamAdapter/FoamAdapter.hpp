@@ -1,0 +1,177 @@
+// FoamAdapter glue for the B200 build: RunTime, mapFvSolution, PDESolver<T> and the PISO pressure-velocity coupling
+// helpers -- the names and call sequence of the reference (include/FoamAdapter/datastructures/{runTime,expression}.hpp,
+// src/compatibility/fvSolution.cpp, src/algorithms/pressureVelocityCoupling.cpp). OpenFOAM itself (mesh reading,
+// dictionaries, Time) is outside the hot path: the mesh comes from NeoN::UnstructuredMesh::createBlockMesh or any
+// fvk_mesh_desc, the dictionaries are NeoN::Dictionary objects.
+#pragma once
+
+#include "NeoN/NeoN.hpp"
+
+namespace FoamAdapter
+{
+namespace nnfvcc = NeoN::finiteVolume::cellCentred;
+namespace dsl = NeoN::dsl;
+namespace la = NeoN::la;
+using NeoN::scalar;
+using NeoN::Vec3;
+
+// datastructures/runTime.hpp
+struct RunTime
+{
+    NeoN::Executor exec;
+    NeoN::UnstructuredMesh nfMesh;
+    NeoN::scalar t = 0.0, dt = 1.0;
+    NeoN::Dictionary fvSchemesDict, fvSolutionDict;
+    fvk_comm* comm = nullptr; // multi-GPU runs: halo exchange + all-reduced dots (nullptr = single GPU)
+};
+
+// src/compatibility/fvSolution.cpp:19-159: OpenFOAM solver entry -> Ginkgo-style dictionary
+inline NeoN::Dictionary mapFvSolution(const NeoN::Dictionary& in)
+{
+    if (in.contains("type")) return in; // already mapped (configFile / Ginkgo-style entry)
+    NeoN::Dictionary out;
+    const auto solver = in.getOr<std::string>("solver", "PCG");
+    if (solver == "PCG" || solver == "CG") out.insert("type", std::string("solver::Cg"));
+    else if (solver == "PBiCGStab") out.insert("type", std::string("solver::Bicgstab"));
+    else NF_ERROR_EXIT("unsupported solver " + solver);
+    out.insert("solver", std::string("Ginkgo"));
+    const auto pre = in.getOr<std::string>("preconditioner", "none");
+    if (pre == "DIC" || pre == "DILU")
+    {
+        NeoN::Dictionary p;
+        p.insert("type", std::string("preconditioner::Jacobi"));
+        p.insert("max_block_size", 1);
+        out.insert("preconditioner", p);
+    }
+    else if (pre != "none") NF_ERROR_EXIT("unsupported preconditioner " + pre);
+    NeoN::Dictionary crit;
+    crit.insert("iteration", in.getOr<int>("maxIter", 1000));
+    crit.insert("relative_residual_norm", in.getOr<scalar>("relTol", 0.0));
+    crit.insert("absolute_residual_norm", in.getOr<scalar>("tolerance", 1e-6));
+    out.insert("criteria", crit);
+    return out;
+}
+
+// datastructures/expression.hpp:23-179
+template<typename ValueType, typename IndexType = NeoN::localIdx>
+class PDESolver
+{
+    using VolumeField = nnfvcc::VolumeField<ValueType>;
+
+public:
+    PDESolver(dsl::Expression<ValueType> expr, VolumeField& psi, const RunTime& runTime)
+        : psi_(psi), expr_(std::move(expr)), runTime_(runTime), sparsityPattern_(la::SparsityPattern::readOrCreate(psi.mesh())),
+          ls_(psi.mesh(), sparsityPattern_, false) // the fused assembly writes every entry: no zero-fill
+    {
+        expr_.read(runTime_.fvSchemesDict);
+    }
+    VolumeField& getField() { return psi_; }
+    const VolumeField& getField() const { return psi_; }
+    const la::SparsityPattern& sparsityPattern() const { return sparsityPattern_; }
+    la::LinearSystem<ValueType, IndexType>& linearSystem() { return ls_; }
+    const la::LinearSystem<ValueType, IndexType>& linearSystem() const { return ls_; }
+    const NeoN::Executor& exec() const { return ls_.exec(); }
+
+    la::LinearSystem<ValueType, IndexType>& assemble()
+    {
+        expr_.assemble(runTime_.t, runTime_.dt, sparsityPattern_, ls_, psi_);
+        return ls_;
+    }
+    void setReference(NeoN::localIdx pRefCell, scalar pRefValue) { needReference_ = true; pRefCell_ = pRefCell; pRefValue_ = pRefValue; }
+
+    la::SolverStats solve()
+    {
+        static_assert(std::is_same_v<ValueType, scalar>, "momentumPredictor (Vec3 solve) is outside the hot path");
+        const auto& solverDict = runTime_.fvSolutionDict.subDict("solvers").subDict(psi_.name);
+        if (!solver_) solver_ = std::make_shared<la::Solver>(exec(), solverDict, runTime_.comm);
+        auto post = [&](const la::SparsityPattern&, la::LinearSystem<ValueType, IndexType>& ls)
+        { // SetReference (expression.hpp:86-112)
+            if (needReference_) NeoN::check(fvk_set_reference(psi_.mesh().handle(), pRefCell_, pRefValue_, ls.values().data(), ls.rhs().data(), exec().stream()));
+        };
+        if (runTime_.comm) NeoN::check(fvk_comm_halo_exchange(runTime_.comm, psi_.internalVector().raw(), 1, exec().stream()));
+        auto stats = dsl::detail::iterativeSolveImpl(expr_, sparsityPattern_, ls_, psi_, runTime_.t, runTime_.dt, *solver_, post);
+        std::cout << "[NeoN] Solving for " << psi_.name << ":" << " Initial residual: " << stats.initResNorm
+                  << " Final residual: " << stats.finalResNorm << " No Iterations: " << stats.numIter << std::endl;
+        return stats;
+    }
+    void useSolver(std::shared_ptr<la::Solver> s) { solver_ = std::move(s); }
+
+private:
+    VolumeField& psi_;
+    dsl::Expression<ValueType> expr_;
+    const RunTime& runTime_;
+    la::SparsityPattern sparsityPattern_;
+    la::LinearSystem<ValueType, IndexType> ls_;
+    bool needReference_ = false;
+    NeoN::localIdx pRefCell_ = 0;
+    scalar pRefValue_ = 0.0;
+    std::shared_ptr<la::Solver> solver_;
+};
+
+// diag(ls, sparsityPattern) (expression.hpp:181-199)
+template<typename T>
+NeoN::Vector<T> diag(const la::LinearSystem<T>& ls, const la::SparsityPattern&)
+{
+    NeoN::Vector<T> d(ls.exec(), size_t(ls.mesh().nCells()), NeoN::zero<T>());
+    NeoN::check(fvk_diag(ls.mesh().handle(), NeoN::nComponents<T>(), ls.values().raw(), d.raw(), ls.exec().stream()));
+    return d;
+}
+
+// ---- src/algorithms/pressureVelocityCoupling.cpp ------------------------------------------------------------------
+inline void constrainHbyA(const nnfvcc::VolumeField<Vec3>& u, const nnfvcc::VolumeField<scalar>&, nnfvcc::VolumeField<Vec3>& hByA)
+{ // :14-36
+    std::vector<int32_t> mask;
+    bool any = false;
+    for (const auto& bc : u.boundaryConditions()) { mask.push_back(bc.assignable() ? 0 : 1); any = any || !bc.assignable(); }
+    if (any) NeoN::check(fvk_copy_patches(u.mesh().handle(), 3, mask.data(), u.boundaryData().value().raw(), hByA.boundaryData().value().raw(), u.exec().stream()));
+}
+
+inline nnfvcc::VolumeField<scalar> computeRAU(const PDESolver<Vec3>& expr)
+{ // :38-63
+    const auto& mesh = expr.getField().mesh();
+    nnfvcc::VolumeField<scalar> rAU(expr.exec(), "rAU", mesh, nnfvcc::createExtrapolatedBCs<scalar>(mesh));
+    NeoN::check(fvk_rAU_HbyA(mesh.handle(), expr.linearSystem().values().raw(), nullptr, nullptr, rAU.internalVector().data(), nullptr, expr.exec().stream()));
+    return rAU;
+}
+
+inline std::tuple<nnfvcc::VolumeField<scalar>, nnfvcc::VolumeField<Vec3>> computeRAUandHByA(const PDESolver<Vec3>& expr)
+{ // :65-128, one fused kernel
+    const auto& u = expr.getField();
+    const auto& mesh = u.mesh();
+    nnfvcc::VolumeField<scalar> rAU(expr.exec(), "rAU", mesh, nnfvcc::createExtrapolatedBCs<scalar>(mesh));
+    nnfvcc::VolumeField<Vec3> hByA(expr.exec(), "HbyA", mesh, nnfvcc::createExtrapolatedBCs<Vec3>(mesh));
+    const auto& ls = expr.linearSystem();
+    NeoN::check(fvk_rAU_HbyA(mesh.handle(), ls.values().raw(), ls.rhs().raw(), u.internalVector().raw(), rAU.internalVector().data(),
+                             hByA.internalVector().raw(), expr.exec().stream()));
+    hByA.correctBoundaryConditions();
+    rAU.correctBoundaryConditions();
+    return {std::move(rAU), std::move(hByA)};
+}
+
+inline nnfvcc::SurfaceField<scalar> flux(const nnfvcc::VolumeField<Vec3>& volField)
+{ // :215-267
+    nnfvcc::SurfaceField<scalar> faceFlux(volField.exec(), "out", volField.mesh());
+    NeoN::check(fvk_flux(volField.mesh().handle(), volField.internalVector().raw(), volField.boundaryData().value().raw(),
+                         faceFlux.internalVector().data(), faceFlux.boundaryData().value().data(), volField.exec().stream()));
+    return faceFlux;
+}
+
+inline void updateFaceVelocity(const nnfvcc::SurfaceField<scalar>& predictedPhi, const PDESolver<scalar>& expr, nnfvcc::SurfaceField<scalar>& phi)
+{ // :131-197
+    const auto& ls = expr.linearSystem();
+    const auto& bc = ls.boundaryCoefficients();
+    NeoN::check(fvk_update_face_velocity(phi.mesh().handle(), ls.values().data(), bc.matrixValues.data(), bc.rhsValues.data(),
+                                         expr.getField().internalVector().data(), predictedPhi.internalVector().data(),
+                                         predictedPhi.boundaryData().value().data(), phi.internalVector().data(),
+                                         phi.boundaryData().value().data(), phi.exec().stream()));
+}
+
+inline void updateVelocity(const nnfvcc::VolumeField<Vec3>& hByA, const nnfvcc::VolumeField<scalar>& rAU, const nnfvcc::VolumeField<scalar>& p,
+                           nnfvcc::VolumeField<Vec3>& u)
+{ // :199-213
+    auto gradP = nnfvcc::GaussGreenGrad(p.exec(), p.mesh()).grad(p);
+    NeoN::check(fvk_update_velocity(u.mesh().handle(), hByA.internalVector().raw(), rAU.internalVector().data(), gradP.internalVector().raw(),
+                                    u.internalVector().raw(), u.exec().stream()));
+}
+
+} // namespace FoamAdapter

@@ -1,0 +1,168 @@
+// NeoN::la for the B200 build: SparsityPattern, CSRMatrix views, LinearSystem, BoundaryCoefficients, computeResidual and
+// the Solver front end (src/NeoN/include/NeoN/linearAlgebra/{sparsityPattern,CSRMatrix,linearSystem,utilities,solver,
+// ginkgo}.hpp). The sparsity pattern is built once per mesh by fvk_mesh_create (bit-exact with
+// src/NeoN/src/linearAlgebra/sparsityPattern.cpp:21-143); the solver is libfvk's device-resident Jacobi-CG instead of Ginkgo.
+#pragma once
+
+#include "NeoN/core.hpp"
+#include "NeoN/mesh.hpp"
+
+namespace NeoN::la
+{
+class SparsityPattern
+{
+public:
+    explicit SparsityPattern(const UnstructuredMesh& mesh) : mesh_(mesh) {}
+    // cached in the mesh handle like SparsityPattern::readOrCreate (sparsityPattern.cpp:11-19)
+    static SparsityPattern readOrCreate(const UnstructuredMesh& mesh) { return SparsityPattern(mesh); }
+    const UnstructuredMesh& mesh() const { return mesh_; }
+    View<const localIdx> rowOffs() const { return mesh_.arr<localIdx>(FVK_ROW_OFFS); }
+    View<const localIdx> colIdxs() const { return mesh_.arr<localIdx>(FVK_COL_IDXS); }
+    View<const uint8_t> ownerOffset() const { return mesh_.arr<uint8_t>(FVK_OWNER_OFFSET); }
+    View<const uint8_t> neighbourOffset() const { return mesh_.arr<uint8_t>(FVK_NEIGHBOUR_OFFSET); }
+    View<const uint8_t> diagOffset() const { return mesh_.arr<uint8_t>(FVK_DIAG_OFFSET); }
+    localIdx rows() const { return mesh_.nCells(); }
+    int64_t nnz() const { return mesh_.nnz(); }
+private:
+    UnstructuredMesh mesh_;
+};
+
+// linearSystem.hpp:36-43
+template<typename T>
+struct BoundaryCoefficients
+{
+    BoundaryCoefficients(const Executor& exec, size_t nB) : matrixValues(exec, nB, zero<T>()), rhsValues(exec, nB, zero<T>()), matrixIdxs(exec, nB), rhsIdxs(exec, nB) {}
+    Vector<T> matrixValues, rhsValues;
+    Vector<localIdx> matrixIdxs, rhsIdxs;
+};
+
+template<typename T>
+struct CSRMatrixView
+{
+    T* values;
+    const localIdx* colIdxs;
+    const localIdx* rowOffs;
+};
+
+// LinearSystem<ValueType, localIdx> (linearSystem.hpp:53-121): values T[nnz], rhs T[nCells] over the mesh's pattern
+template<typename T, typename IndexType = localIdx>
+class LinearSystem
+{
+public:
+    LinearSystem(const UnstructuredMesh& mesh, const SparsityPattern& sp, bool zeroFill = true)
+        : mesh_(mesh), sp_(sp), values_(mesh.exec(), size_t(sp.nnz())), rhs_(mesh.exec(), size_t(mesh.nCells())),
+          bc_(mesh.exec(), size_t(mesh.nBoundaryFaces()))
+    {
+        if (zeroFill) reset();
+        check(fvk_bc_coeff_indices(mesh.handle(), bc_.matrixIdxs.data(), bc_.rhsIdxs.data(), mesh.exec().stream()));
+    }
+    const Executor& exec() const { return mesh_.exec(); }
+    const UnstructuredMesh& mesh() const { return mesh_; }
+    const SparsityPattern& sparsityPattern() const { return sp_; }
+    Vector<T>& values() { return values_; }
+    const Vector<T>& values() const { return values_; }
+    Vector<T>& rhs() { return rhs_; }
+    const Vector<T>& rhs() const { return rhs_; }
+    BoundaryCoefficients<T>& boundaryCoefficients() { return bc_; }
+    const BoundaryCoefficients<T>& boundaryCoefficients() const { return bc_; }
+    CSRMatrixView<T> view() { return {values_.data(), sp_.colIdxs().ptr, sp_.rowOffs().ptr}; }
+    void reset() { values_.fillWith(zero<T>()); rhs_.fillWith(zero<T>()); }
+private:
+    UnstructuredMesh mesh_;
+    SparsityPattern sp_;
+    Vector<T> values_, rhs_;
+    BoundaryCoefficients<T> bc_;
+};
+
+// createEmptyLinearSystem (linearSystem.hpp:140-186)
+template<typename T, typename IndexType = localIdx>
+LinearSystem<T, IndexType> createEmptyLinearSystem(const UnstructuredMesh& mesh, const SparsityPattern& sp)
+{
+    return LinearSystem<T, IndexType>(mesh, sp, true);
+}
+
+// computeResidual (src/NeoN/src/linearAlgebra/utilities.cpp:11-35): res = A x - b
+inline void computeResidual(const LinearSystem<scalar>& ls, const Vector<scalar>& x, Vector<scalar>& res)
+{
+    const auto& sp = ls.sparsityPattern();
+    check(fvk_residual(ls.mesh().nOwnedCells(), sp.rowOffs().ptr, sp.colIdxs().ptr, ls.values().data(), ls.rhs().data(), x.data(),
+                       res.data(), ls.exec().stream()));
+}
+inline void spmv(const LinearSystem<scalar>& ls, const Vector<scalar>& x, Vector<scalar>& y)
+{
+    const auto& sp = ls.sparsityPattern();
+    check(fvk_spmv(ls.mesh().nOwnedCells(), sp.rowOffs().ptr, sp.colIdxs().ptr, ls.values().data(), x.data(), y.data(), ls.exec().stream()));
+}
+
+// solver.hpp:14-27
+struct SolverStats
+{
+    int numIter;
+    scalar initResNorm;
+    scalar finalResNorm;
+    std::vector<scalar> residualHistory; // ||r|| at every stopping check (extension: the reference logs only the final value)
+    void print(std::string solverName) const
+    {
+        std::cout << "Solver: " << solverName << " , Initial residual = " << initResNorm << " , Final residual = " << finalResNorm
+                  << " , No Iterations = " << numIter << std::endl;
+    }
+};
+
+// la::Solver(exec, dict) (solver.hpp:63-91) for the dictionaries mapFvSolution emits (FoamAdapter
+// src/compatibility/fvSolution.cpp:19-159): {solver Ginkgo; type solver::Cg; preconditioner{type preconditioner::Jacobi;
+// max_block_size 1}; criteria{iteration; relative_residual_norm; absolute_residual_norm}}.
+class Solver
+{
+public:
+    Solver(const Executor& exec, const Dictionary& dict, fvk_comm* comm = nullptr, int checkEvery = 8, bool history = false)
+        : exec_(exec), comm_(comm), history_(history)
+    {
+        const auto type = dict.getOr<std::string>("type", "solver::Cg");
+        if (type != "solver::Cg") NF_ERROR_EXIT("solver type " + type + " is not on the hot path (solver::Cg only)");
+        cfg_.maxIter = 1000; cfg_.relTol = 0.0; cfg_.absTol = 0.0; cfg_.preconditioner = FVK_PRECOND_NONE; cfg_.checkEvery = checkEvery;
+        if (dict.contains("criteria"))
+        {
+            const auto& c = dict.subDict("criteria");
+            cfg_.maxIter = c.getOr<int>("iteration", 1000);
+            cfg_.relTol = c.getOr<scalar>("relative_residual_norm", 0.0);
+            cfg_.absTol = c.getOr<scalar>("absolute_residual_norm", 0.0);
+        }
+        if (dict.contains("preconditioner"))
+        {
+            const auto ptype = dict.subDict("preconditioner").getOr<std::string>("type", "");
+            if (ptype == "preconditioner::Jacobi") cfg_.preconditioner = FVK_PRECOND_JACOBI;
+            else NF_ERROR_EXIT("preconditioner " + ptype + " not supported");
+        }
+    }
+    Solver(const Solver&) = delete;
+    Solver& operator=(const Solver&) = delete;
+    ~Solver() { if (h_) fvk_solver_destroy(h_); }
+
+    SolverStats solve(const LinearSystem<scalar, localIdx>& ls, Vector<scalar>& x) const
+    {
+        const auto& m = ls.mesh();
+        if (!h_ || rows_ != m.nOwnedCells() || cols_ != m.nCells())
+        {
+            if (h_) fvk_solver_destroy(h_);
+            h_ = nullptr;
+            check(fvk_solver_create(m.nOwnedCells(), m.nCells(), &cfg_, comm_, &h_));
+            rows_ = m.nOwnedCells(); cols_ = m.nCells();
+        }
+        const auto& sp = ls.sparsityPattern();
+        fvk_solver_stats st {};
+        std::vector<scalar> hist(history_ ? size_t(cfg_.maxIter) + 2 : 0);
+        check(fvk_solver_solve(h_, sp.rowOffs().ptr, sp.colIdxs().ptr, ls.values().data(), ls.rhs().data(), x.data(), &st,
+                               history_ ? hist.data() : nullptr, int32_t(hist.size()), exec_.stream()));
+        hist.resize(history_ ? size_t(st.nHistory) : 0);
+        return {st.numIter, st.initResNorm, st.finalResNorm, hist};
+    }
+private:
+    Executor exec_;
+    fvk_comm* comm_;
+    bool history_;
+    fvk_solver_config cfg_ {};
+    mutable fvk_solver* h_ = nullptr;
+    mutable localIdx rows_ = 0, cols_ = 0;
+};
+
+} // namespace NeoN::la
