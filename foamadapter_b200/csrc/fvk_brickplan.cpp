@@ -1,0 +1,453 @@
+// Host-side plans of the explicit gather kernels: the cell->face stencil in the reference's accumulation order and
+// the brick plan of k_gather_brick (fvk_explicit.cu). Nothing here is reference code: the reference scatters face
+// fluxes with atomics (src/NeoN/src/finiteVolume/cellCentred/operators/gaussGreenDiv.cpp:69-101); the plan exists so
+// that a cell-centric gather can reproduce the SerialExecutor's summation order (gaussGreenDiv.cpp:46-67) while
+// streaming every face array once.
+#include "fvk_brickplan.hpp"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <utility>
+
+void fvk_build_stencil(const fvk_mesh_desc* d, FvkStencilHost& st)
+{
+    const int32_t nC = d->nCells, nI = d->nInternalFaces, nB = d->nBoundaryFaces;
+    const int32_t* own = d->faceOwner;
+    const int32_t* nei = d->faceNeighbour;
+    std::vector<int32_t>& seg = st.seg;
+    seg.assign(size_t(nC) + 1, 0);
+    for (int32_t f = 0; f < nI; ++f) { ++seg[size_t(own[f]) + 1]; ++seg[size_t(nei[f]) + 1]; }
+    for (int32_t b = 0; b < nB; ++b) ++seg[size_t(d->faceCells[b]) + 1];
+    for (int32_t c = 0; c < nC; ++c) seg[size_t(c) + 1] += seg[c];
+    const size_t nEnt = size_t(seg[nC]);
+    std::vector<int32_t>&val = st.val, &ent = st.ent, &plan = st.plan;
+    val.resize(nEnt); ent.resize(nEnt); plan.resize(2 * nEnt);
+    std::vector<int32_t> pos(seg.begin(), seg.end() - 1);
+    // visiting faces in ascending id appends ascending ids (cellToFaceStencil.cpp:82-93 sorts; same result)
+    for (int32_t f = 0; f < nI; ++f)
+    {
+        int32_t k = pos[own[f]]++;
+        val[k] = f; ent[k] = f << 1;
+        plan[2 * size_t(k)] = f << 1; plan[2 * size_t(k) + 1] = nei[f];
+        k = pos[nei[f]]++;
+        val[k] = f; ent[k] = (f << 1) | 1;
+        plan[2 * size_t(k)] = (f << 1) | 1; plan[2 * size_t(k) + 1] = own[f];
+    }
+    for (int32_t b = 0; b < nB; ++b)
+    {
+        const int32_t k = pos[d->faceCells[b]]++;
+        val[k] = nI + b; ent[k] = (nI + b) << 1;
+        plan[2 * size_t(k)] = -(b + 1); plan[2 * size_t(k) + 1] = d->faceCells[b];
+    }
+    if (d->faceOrder)
+    {
+        // per-cell gather order = ascending key over the internal faces (boundary faces stay last);
+        // stencil values keep the ascending local id
+        const int32_t* key = d->faceOrder;
+#pragma omp parallel
+        {
+            std::vector<std::pair<int32_t, int32_t>> tmp;
+            std::vector<int32_t> e2, p2;
+#pragma omp for schedule(static)
+            for (int32_t c = 0; c < nC; ++c)
+            {
+                int32_t b0 = seg[c], b1 = seg[size_t(c) + 1];
+                while (b1 > b0 && (ent[b1 - 1] >> 1) >= nI) --b1;
+                tmp.clear();
+                for (int32_t k = b0; k < b1; ++k) tmp.emplace_back(key[ent[k] >> 1], k);
+                if (std::is_sorted(tmp.begin(), tmp.end())) continue;
+                std::stable_sort(tmp.begin(), tmp.end());
+                e2.resize(tmp.size()); p2.resize(2 * tmp.size());
+                for (size_t i = 0; i < tmp.size(); ++i)
+                {
+                    e2[i] = ent[tmp[i].second];
+                    p2[2 * i] = plan[2 * size_t(tmp[i].second)]; p2[2 * i + 1] = plan[2 * size_t(tmp[i].second) + 1];
+                }
+                for (size_t i = 0; i < tmp.size(); ++i)
+                {
+                    ent[b0 + i] = e2[i];
+                    plan[2 * (size_t(b0) + i)] = p2[2 * i]; plan[2 * (size_t(b0) + i) + 1] = p2[2 * i + 1];
+                }
+            }
+        }
+    }
+}
+
+namespace
+{
+constexpr int32_t kTileCells = 512; // k_gather_brick: 256 threads x 2 cells
+
+struct TileShape
+{
+    int32_t c0, runLen, by, nRuns, sy, sz;
+};
+
+int32_t log2_exact(int32_t v)
+{
+    if (v <= 0 || (v & (v - 1))) return -1;
+    int32_t s = 0;
+    while ((1 << s) < v) ++s;
+    return s;
+}
+
+// Block-structured numbering c = i + nx*(j + ny*k) of the computed cells, read off the owner->neighbour id strides.
+// Purely a tiling hint: any partition of the cells gives a correct plan.
+bool detect_dims(int32_t nOwned, int32_t nI, const int32_t* own, const int32_t* nei, int32_t dims[3])
+{
+    std::map<int32_t, int64_t> diffs;
+    int32_t last = 0;
+    for (int32_t f = 0; f < nI; ++f)
+    {
+        if (own[f] >= nOwned || nei[f] >= nOwned) continue;
+        const int32_t dlt = nei[f] - own[f];
+        if (dlt == last) continue;
+        if (dlt <= 0) return false;
+        last = dlt;
+        if (diffs.find(dlt) == diffs.end())
+        {
+            if (diffs.size() == 3) return false;
+            diffs[dlt] = 1;
+        }
+    }
+    if (diffs.empty()) { dims[0] = nOwned; dims[1] = dims[2] = 1; return true; }
+    std::vector<int32_t> s;
+    for (auto& kv : diffs) s.push_back(kv.first);
+    if (s[0] != 1) return false;
+    if (s.size() == 1) { dims[0] = nOwned; dims[1] = dims[2] = 1; return true; }
+    if (nOwned % s[1]) return false;
+    if (s.size() == 2) { dims[0] = s[1]; dims[1] = nOwned / s[1]; dims[2] = 1; return true; }
+    if (s[2] % s[1] || nOwned % s[2]) return false;
+    dims[0] = s[1]; dims[1] = s[2] / s[1]; dims[2] = nOwned / s[2];
+    return true;
+}
+
+void make_tiles(int32_t nOwned, const int32_t dims[3], bool structured, int32_t brick[3], std::vector<TileShape>& tiles)
+{
+    tiles.clear();
+    if (!structured)
+    {
+        brick[0] = kTileCells; brick[1] = brick[2] = 1;
+        for (int32_t c = 0; c < nOwned; c += kTileCells)
+            tiles.push_back(TileShape {c, std::min(kTileCells, nOwned - c), 1, 1, 0, 0});
+        return;
+    }
+    int32_t L = 32, BY = 4, BZ = 4;
+    bool fixed = false; // FVK_BRICK="lx,by,bz": use exactly this shape (clipped to the mesh and to 512 cells)
+    if (const char* e = std::getenv("FVK_BRICK"))
+    {
+        int a = 0, b = 0, c = 0;
+        if (std::sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && a > 0 && b > 0 && c > 0) { L = a; BY = b; BZ = c; fixed = true; }
+    }
+    const int32_t nx = dims[0], ny = dims[1], nz = dims[2];
+    int32_t lx = std::min(std::min(L, nx), kTileCells), bz = std::min(BZ, nz);
+    if (lx * bz > kTileCells) bz = std::max(1, kTileCells / lx);
+    int32_t by = std::min(ny, BY);
+    if (!fixed) by = std::min(ny, std::max(BY, kTileCells / (lx * bz))); // flat meshes: more rows per tile
+    while (by > 1 && lx * by * bz > kTileCells) --by;
+    if (!fixed)
+    {
+        if (lx * by * bz < kTileCells && bz < nz) bz = std::min(nz, kTileCells / (lx * by)); // thin in y: stack more planes
+        if (lx * by * bz < kTileCells && lx < nx) lx = std::min(nx, kTileCells / (by * bz));  // 1-D / thin meshes: longer runs
+    }
+    brick[0] = lx; brick[1] = by; brick[2] = bz;
+    for (int32_t z0 = 0; z0 < nz; z0 += bz)
+        for (int32_t y0 = 0; y0 < ny; y0 += by)
+            for (int32_t x0 = 0; x0 < nx; x0 += lx)
+            {
+                const int32_t rl = std::min(lx, nx - x0), ry = std::min(by, ny - y0), rz = std::min(bz, nz - z0);
+                tiles.push_back(TileShape {x0 + nx * (y0 + ny * z0), rl, ry, ry * rz, nx, nx * ny});
+            }
+}
+
+template <class F>
+inline void for_tile_cells(const TileShape& t, F&& fn)
+{
+    int32_t lc = 0;
+    for (int32_t r = 0; r < t.nRuns; ++r)
+    {
+        const int32_t a = r % t.by, b = r / t.by;
+        const int32_t base = t.c0 + a * t.sy + b * t.sz;
+        for (int32_t o = 0; o < t.runLen; ++o, ++lc) fn(base + o, lc);
+    }
+}
+
+struct CellInfo
+{
+    int32_t fs = 0, nOwn = 0, nLow = 0, nBnd = 0;
+    bool ok = true;
+};
+// the per-cell order the kernel assumes: [lower faces | owned faces, consecutive ascending ids | boundary faces]
+inline CellInfo analyse(int32_t c, int32_t nI, const int32_t* seg, const int32_t* ent)
+{
+    CellInfo ci;
+    int phase = 0;
+    for (int32_t e = seg[c]; e < seg[size_t(c) + 1]; ++e)
+    {
+        const int32_t f = ent[e] >> 1, side = ent[e] & 1;
+        if (f >= nI)
+        {
+            if (side) { ci.ok = false; return ci; }
+            phase = 2; ++ci.nBnd;
+        }
+        else if (side)
+        {
+            if (phase != 0) { ci.ok = false; return ci; }
+            ++ci.nLow;
+        }
+        else
+        {
+            if (phase == 2) { ci.ok = false; return ci; }
+            if (phase == 0) { phase = 1; ci.fs = f; }
+            if (f != ci.fs + ci.nOwn) { ci.ok = false; return ci; }
+            ++ci.nOwn;
+        }
+    }
+    return ci;
+}
+} // namespace
+
+bool fvk_build_brick_plan(const fvk_mesh_desc* d, const FvkStencilHost& st, FvkBrickPlanHost& out, const char** reason)
+{
+    const char* dummy;
+    if (!reason) reason = &dummy;
+    *reason = "";
+    const int32_t nC = d->nCells, nI = d->nInternalFaces;
+    const int32_t nOwned = (d->nOwnedCells > 0 && d->nOwnedCells <= nC) ? d->nOwnedCells : nC;
+    const int32_t* own = d->faceOwner;
+    const int32_t* nei = d->faceNeighbour;
+    const int32_t* seg = st.seg.data();
+    const int32_t* ent = st.ent.data();
+    out = FvkBrickPlanHost {};
+    if (nOwned <= 0) { *reason = "no cells"; return false; }
+
+    const bool structured = detect_dims(nOwned, nI, own, nei, out.dims)
+                            && int64_t(out.dims[0]) * out.dims[1] * out.dims[2] == nOwned;
+    if (!structured) out.dims[0] = out.dims[1] = out.dims[2] = 0;
+    std::vector<TileShape> tiles;
+    make_tiles(nOwned, out.dims, structured, out.brick, tiles);
+    const int32_t nT = int32_t(tiles.size());
+
+    std::vector<int32_t> cellTile(size_t(nC), -1), cellFaceStart(size_t(nC), 0), cellSlotBase(size_t(nC), 0);
+    std::vector<int32_t> tSlots(nT, 0), tCodes(nT, 0), tX(nT, 0), tB(nT, 0), tC(nT, 0);
+    int bad = 0;
+    // pass 1: per-cell order check, own-slot numbering
+#pragma omp parallel for schedule(static) reduction(| : bad)
+    for (int32_t t = 0; t < nT; ++t)
+    {
+        int32_t slots = 0, codes = 0, nb = 0, nc = 0;
+        for_tile_cells(tiles[t], [&](int32_t c, int32_t) {
+            if (c < 0 || c >= nOwned) { bad |= 1; return; }
+            const CellInfo ci = analyse(c, nI, seg, ent);
+            if (!ci.ok) { bad |= 2; return; }
+            cellTile[c] = t; cellFaceStart[c] = ci.fs; cellSlotBase[c] = slots;
+            slots += ci.nOwn; codes += ci.nLow + ci.nBnd; nb += ci.nBnd; ++nc;
+        });
+        tSlots[t] = slots; tCodes[t] = codes; tB[t] = nb; tC[t] = nc;
+    }
+    if (bad & 1) { *reason = "tiling left the cell range"; return false; }
+    if (bad & 2) { *reason = "per-cell face order is not [lower | owned consecutive | boundary]"; return false; }
+    for (int32_t c = 0; c < nOwned; ++c)
+        if (cellTile[c] < 0) { *reason = "tiling does not cover every cell"; return false; }
+    // pass 1b: cross faces (lower faces whose owner is not a cell of the same tile)
+#pragma omp parallel for schedule(static)
+    for (int32_t t = 0; t < nT; ++t)
+    {
+        int32_t nx = 0;
+        for_tile_cells(tiles[t], [&](int32_t c, int32_t) {
+            for (int32_t e = seg[c]; e < seg[size_t(c) + 1]; ++e)
+            {
+                const int32_t f = ent[e] >> 1;
+                if (f < nI && (ent[e] & 1))
+                {
+                    const int32_t o = own[f];
+                    if (!(o < nOwned && cellTile[o] == t)) ++nx;
+                }
+            }
+        });
+        tX[t] = nx;
+    }
+    out.hdr.resize(nT);
+    int64_t recBase = 0, codeBase = 0, xBase = 0, bBase = 0;
+    for (int32_t t = 0; t < nT; ++t)
+    {
+        const TileShape& s = tiles[t];
+        if (tSlots[t] + tX[t] + tB[t] >= 32768 || tCodes[t] >= 65535 || tC[t] > kTileCells)
+        {
+            *reason = "tile exceeds the 16-bit slot range";
+            return false;
+        }
+        if (recBase + tC[t] + 1 >= (int64_t(1) << 31) || codeBase + tCodes[t] >= (int64_t(1) << 31))
+        {
+            *reason = "plan exceeds 2^31 entries";
+            return false;
+        }
+        FvkBrickHdr& h = out.hdr[t];
+        h.c0 = s.c0; h.runLen = s.runLen; h.by = s.by; h.nRuns = s.nRuns; h.sy = s.sy; h.sz = s.sz;
+        h.shiftL = log2_exact(s.runLen); h.shiftBy = log2_exact(s.by);
+        h.recBase = int32_t(recBase); h.codeBase = int32_t(codeBase);
+        h.xBase = int32_t(xBase); h.nx = tX[t]; h.bBase = int32_t(bBase); h.nb = tB[t];
+        h.nOwnSlots = tSlots[t]; h.nc = tC[t];
+        recBase += tC[t] + 1; codeBase += tCodes[t]; xBase += tX[t]; bBase += tB[t];
+        out.maxSlots = std::max(out.maxSlots, tSlots[t] + tX[t] + tB[t]);
+        out.maxCells = std::max(out.maxCells, tC[t]);
+    }
+    out.rec.resize(size_t(recBase));
+    out.codes.resize(size_t(codeBase) + 8, 0); // slack: the kernel prefetches 4 codes per cell unconditionally
+    out.xFace.resize(size_t(xBase)); out.xOwner.resize(size_t(xBase)); out.xNei.resize(size_t(xBase));
+    out.bFace.resize(size_t(bBase)); out.bCell.resize(size_t(bBase));
+    // pass 2: fill
+#pragma omp parallel for schedule(static)
+    for (int32_t t = 0; t < nT; ++t)
+    {
+        const FvkBrickHdr& h = out.hdr[t];
+        int32_t list = 0, ix = 0, ib = 0, lastLc = -1;
+        for_tile_cells(tiles[t], [&](int32_t c, int32_t lc) {
+            FvkBrickRec& r = out.rec[size_t(h.recBase) + lc];
+            r.faceStart = cellFaceStart[c];
+            r.bases = uint32_t(cellSlotBase[c]) | (uint32_t(list) << 16);
+            for (int32_t e = seg[c]; e < seg[size_t(c) + 1]; ++e)
+            {
+                const int32_t f = ent[e] >> 1, side = ent[e] & 1;
+                if (f >= nI)
+                {
+                    const int32_t slot = h.nOwnSlots + h.nx + ib;
+                    out.bFace[size_t(h.bBase) + ib] = f; out.bCell[size_t(h.bBase) + ib] = c;
+                    ++ib;
+                    out.codes[size_t(h.codeBase) + list++] = uint16_t(slot << 1);
+                }
+                else if (side)
+                {
+                    const int32_t o = own[f];
+                    int32_t slot;
+                    if (o < nOwned && cellTile[o] == t)
+                        slot = cellSlotBase[o] + (f - cellFaceStart[o]);
+                    else
+                    {
+                        slot = h.nOwnSlots + ix;
+                        out.xFace[size_t(h.xBase) + ix] = f; out.xOwner[size_t(h.xBase) + ix] = o; out.xNei[size_t(h.xBase) + ix] = c;
+                        ++ix;
+                    }
+                    out.codes[size_t(h.codeBase) + list++] = uint16_t((slot << 1) | 1);
+                }
+            }
+            lastLc = lc;
+        });
+        FvkBrickRec& r = out.rec[size_t(h.recBase) + lastLc + 1]; // closing record
+        r.faceStart = 0;
+        r.bases = uint32_t(h.nOwnSlots) | (uint32_t(list) << 16);
+    }
+    return true;
+}
+
+int64_t fvk_verify_brick_plan(const fvk_mesh_desc* d, const FvkStencilHost& st, const FvkBrickPlanHost& bp)
+{
+    const int32_t nC = d->nCells, nI = d->nInternalFaces;
+    const int32_t nOwned = (d->nOwnedCells > 0 && d->nOwnedCells <= nC) ? d->nOwnedCells : nC;
+    const int32_t* own = d->faceOwner;
+    const int32_t* nei = d->faceNeighbour;
+    std::vector<uint8_t> seen(size_t(nOwned), 0);
+    int64_t badCells = 0;
+    for (size_t t = 0; t < bp.hdr.size(); ++t)
+    {
+        const FvkBrickHdr& h = bp.hdr[t];
+        const int32_t nSlots = h.nOwnSlots + h.nx + h.nb;
+        std::vector<int64_t> slotFace(size_t(nSlots), -1);
+        std::vector<int32_t> cellOf(size_t(h.nc), -1);
+        bool tileOk = nSlots <= bp.maxSlots && h.nc <= bp.maxCells && h.nc == h.runLen * h.nRuns;
+        if (h.shiftL >= 0 && (1 << h.shiftL) != h.runLen) tileOk = false;
+        if (h.shiftBy >= 0 && (1 << h.shiftBy) != h.by) tileOk = false;
+        // phase A1 as the kernel does it
+        for (int32_t lc = 0; lc < h.nc; ++lc)
+        {
+            const int32_t r = lc / h.runLen, off = lc - r * h.runLen, b = r / h.by, a = r - b * h.by;
+            const int32_t c = h.c0 + a * h.sy + b * h.sz + off;
+            cellOf[lc] = c;
+            if (c < 0 || c >= nOwned || seen[c]) { tileOk = false; continue; }
+            seen[c] = 1;
+            const FvkBrickRec r0 = bp.rec[size_t(h.recBase) + lc], r1 = bp.rec[size_t(h.recBase) + lc + 1];
+            const int32_t slotBase = int32_t(r0.bases & 0xffffu), nOwn = int32_t(r1.bases & 0xffffu) - slotBase;
+            if (nOwn < 0 || slotBase + nOwn > h.nOwnSlots) { tileOk = false; continue; }
+            for (int32_t k = 0; k < nOwn; ++k)
+            {
+                const int32_t f = r0.faceStart + k;
+                if (f < 0 || f >= nI || own[f] != c) { tileOk = false; continue; }
+                slotFace[size_t(slotBase) + k] = f;
+            }
+        }
+        for (int32_t i = 0; i < h.nx; ++i)
+        {
+            const int32_t f = bp.xFace[size_t(h.xBase) + i];
+            if (f < 0 || f >= nI || own[f] != bp.xOwner[size_t(h.xBase) + i] || nei[f] != bp.xNei[size_t(h.xBase) + i]) { tileOk = false; continue; }
+            slotFace[size_t(h.nOwnSlots) + i] = f;
+        }
+        for (int32_t i = 0; i < h.nb; ++i)
+        {
+            const int32_t f = bp.bFace[size_t(h.bBase) + i];
+            if (f < nI || f >= nI + d->nBoundaryFaces || d->faceCells[f - nI] != bp.bCell[size_t(h.bBase) + i]) { tileOk = false; continue; }
+            slotFace[size_t(h.nOwnSlots) + h.nx + i] = f;
+        }
+        // phase B
+        for (int32_t lc = 0; lc < h.nc; ++lc)
+        {
+            const int32_t c = cellOf[lc];
+            if (c < 0 || c >= nOwned) { ++badCells; continue; }
+            const FvkBrickRec r0 = bp.rec[size_t(h.recBase) + lc], r1 = bp.rec[size_t(h.recBase) + lc + 1];
+            const int32_t slotBase = int32_t(r0.bases & 0xffffu), nOwn = int32_t(r1.bases & 0xffffu) - slotBase;
+            const int32_t listBase = int32_t(r0.bases >> 16), nList = int32_t(r1.bases >> 16) - listBase;
+            std::vector<int32_t> seq;
+            bool ok = tileOk && nList >= 0;
+            int32_t i = 0;
+            auto pull = [&](uint16_t code, int32_t wantSide) {
+                const int32_t slot = code >> 1;
+                if (slot >= nSlots || slotFace[slot] < 0) { ok = false; return; }
+                const int64_t f = slotFace[slot];
+                if (wantSide) { if (f >= nI || nei[f] != c) ok = false; }
+                else if (f < nI || d->faceCells[f - nI] != c) ok = false;
+                seq.push_back(int32_t((f << 1) | wantSide));
+            };
+            for (; ok && i < nList && (bp.codes[size_t(h.codeBase) + listBase + i] & 1); ++i)
+                pull(bp.codes[size_t(h.codeBase) + listBase + i], 1);
+            for (int32_t k = 0; ok && k < nOwn; ++k) seq.push_back((r0.faceStart + k) << 1);
+            for (; ok && i < nList; ++i)
+            {
+                const uint16_t code = bp.codes[size_t(h.codeBase) + listBase + i];
+                if (code & 1) { ok = false; break; }
+                pull(code, 0);
+            }
+            const int32_t e0 = st.seg[c], e1 = st.seg[size_t(c) + 1];
+            if (ok && int32_t(seq.size()) == e1 - e0)
+            {
+                for (int32_t e = e0; e < e1; ++e)
+                    if (seq[size_t(e - e0)] != st.ent[e]) ok = false;
+            }
+            else
+                ok = false;
+            if (!ok) ++badCells;
+        }
+    }
+    for (int32_t c = 0; c < nOwned; ++c)
+        if (!seen[c]) ++badCells;
+    return badCells;
+}
+
+// diagnostics entry (host only, no device needed): build stencil + brick plan for a mesh description and replay it
+extern "C" int fvk_brick_plan_selftest(const fvk_mesh_desc* d, int32_t* info /* [8] */, int64_t* badCells)
+{
+    if (!d || !info || !badCells) return fvk_fail(FVK_EINVAL, "fvk_brick_plan_selftest: null");
+    FvkStencilHost st;
+    fvk_build_stencil(d, st);
+    FvkBrickPlanHost bp;
+    const char* why = "";
+    std::memset(info, 0, sizeof(int32_t) * 8);
+    *badCells = -1;
+    if (!fvk_build_brick_plan(d, st, bp, &why)) return fvk_fail(FVK_EUNSUPPORTED, "brick plan: %s", why);
+    info[0] = int32_t(bp.hdr.size());
+    info[1] = bp.dims[0]; info[2] = bp.dims[1]; info[3] = bp.dims[2];
+    info[4] = bp.brick[0]; info[5] = bp.brick[1]; info[6] = bp.brick[2];
+    info[7] = bp.maxSlots;
+    *badCells = fvk_verify_brick_plan(d, st, bp);
+    return FVK_OK;
+}

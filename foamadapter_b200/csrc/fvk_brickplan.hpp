@@ -1,0 +1,34 @@
+// Host-side builder of the brick plan (FvkBrickPlan, fvk_internal.hpp) and of the per-cell face stencil.
+#pragma once
+#include "fvk_internal.hpp"
+
+#include <vector>
+
+// cell -> faces in the reference's accumulation order (ascending face id, or ascending faceOrder key over the
+// internal faces of a decomposed mesh; boundary faces last): CellToFaceStencil,
+// src/NeoN/src/finiteVolume/cellCentred/stencil/cellToFaceStencil.cpp:14-96.
+struct FvkStencilHost
+{
+    std::vector<int32_t> seg;  // [nC+1]
+    std::vector<int32_t> val;  // ascending local face id per cell (the reference's stencil values)
+    std::vector<int32_t> ent;  // (face << 1) | (cell is the face's neighbour), accumulation order
+    std::vector<int32_t> plan; // 2 per entry: {ent, other cell}; boundary face b: {-(b + 1), own cell}
+};
+void fvk_build_stencil(const fvk_mesh_desc* d, FvkStencilHost& st);
+
+struct FvkBrickPlanHost
+{
+    std::vector<FvkBrickHdr> hdr;
+    std::vector<FvkBrickRec> rec;
+    std::vector<uint16_t> codes;
+    std::vector<int32_t> xFace, xOwner, xNei, bFace, bCell;
+    int32_t maxSlots = 0, maxCells = 0;
+    int32_t dims[3] = {0, 0, 0};  // detected block-structured numbering (0,0,0: none -> runs of consecutive cells)
+    int32_t brick[3] = {0, 0, 0}; // brick shape used
+};
+// false: the mesh does not have the [lower | owned (consecutive ids) | boundary] per-cell order, or a tile exceeds the
+// 16-bit slot range -> the caller keeps the per-cell gather kernel. `reason` (may be NULL) gets a short text.
+bool fvk_build_brick_plan(const fvk_mesh_desc* d, const FvkStencilHost& st, FvkBrickPlanHost& out, const char** reason);
+// replay the plan on the host exactly as k_gather_brick reads it and compare, cell by cell, the (face, sign) sequence
+// with the stencil; returns the number of mismatching cells (0 = the plan reproduces the reference order)
+int64_t fvk_verify_brick_plan(const fvk_mesh_desc* d, const FvkStencilHost& st, const FvkBrickPlanHost& bp);

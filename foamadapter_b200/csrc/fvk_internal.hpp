@@ -59,6 +59,44 @@ inline FvkBlobLayout fvk_blob_layout(int32_t nc, int32_t nf, int32_t nx, int32_t
     return L;
 }
 
+// Brick plan of the explicit gather kernels (k_gather_brick, built once per mesh on the host, fvk_brickplan.cpp).
+// A tile is a small strided set of cell RUNS {c0 + a*sy + b*sz + [0, runLen) : a < by, b < nRuns/by}: an (x,y,z)
+// brick of a block-structured numbering, or one run of consecutive cells for any other numbering. Faces are in
+// OpenFOAM order (sorted by owner), so the faces a cell owns are the consecutive ids [faceStart, faceStart+nOwn).
+// Every face value a tile needs has a SLOT in shared memory:
+//   [0, nOwnSlots)                 faces owned by the tile's cells, cell after cell (evaluated once, used by the owner
+//                                  and by an in-tile neighbour)
+//   [nOwnSlots, +nx)               "cross" faces: a tile cell is the neighbour, the owner lies outside the tile
+//   [nOwnSlots+nx, +nb)            boundary faces of the tile's cells
+// rec[recBase + lc] = {faceStart, slotBase | listBase << 16} for local cell lc (one extra record closes the tile);
+// codes[codeBase + listBase ...] lists, in the reference's accumulation order, the slots the cell does not own:
+// (slot << 1) | 1 = lower face (subtract), (slot << 1) | 0 = boundary face (add). The reference order per cell is
+// [lower faces | owned faces | boundary faces] (checked at build time; meshes that violate it get no brick plan).
+struct FvkBrickHdr // 64 bytes
+{
+    int32_t c0, runLen, by, nRuns;
+    int32_t sy, sz;
+    int32_t shiftL, shiftBy; // log2 of runLen / by when they are powers of two, else -1
+    int32_t recBase, codeBase;
+    int32_t xBase, nx;
+    int32_t bBase, nb;
+    int32_t nOwnSlots, nc;
+};
+struct FvkBrickRec
+{
+    int32_t faceStart;
+    uint32_t bases; // slotBase | listBase << 16
+};
+struct FvkBrickPlan
+{
+    int32_t nTiles = 0, maxSlots = 0, maxCells = 0;
+    FvkBrickHdr* hdr = nullptr;
+    FvkBrickRec* rec = nullptr;
+    uint16_t* codes = nullptr;
+    int32_t *xFace = nullptr, *xOwner = nullptr, *xNei = nullptr;
+    int32_t *bFace = nullptr, *bCell = nullptr;
+};
+
 // Device-side mesh. All arrays are device pointers in reference order.
 struct fvk_mesh
 {
@@ -96,4 +134,5 @@ struct fvk_mesh
     int32_t *bndCell = nullptr, *bndSeg = nullptr, *bndFace = nullptr;
     uint32_t* hasBnd = nullptr; // bitmask [ceil(nCells/32)]
     FvkTilePlan tp; // tile plan of the explicit gather kernels (nTiles == 0: faces not sorted by owner)
+    FvkBrickPlan bp; // brick plan (nTiles == 0: not available for this mesh)
 };

@@ -7,6 +7,7 @@
 // (src/NeoN/src/linearAlgebra/sparsityPattern.cpp:21-143; like the reference the pattern is
 // assembled once per mesh on the host and uploaded).
 #include "fvk_device.cuh"
+#include "fvk_brickplan.hpp"
 
 #include <cstdarg>
 #include <cstdio>
@@ -203,7 +204,8 @@ extern "C" int fvk_mesh_destroy(fvk_mesh* m)
                     m->weights, m->deltaCoeffs, m->nonOrthDeltaCoeffs, m->stencilSeg, m->stencilVal,
                     m->gatherEnt, m->gatherPlan, m->rowOffs, m->colIdxs, m->ownerOffset, m->neighbourOffset,
                     m->diagOffset, m->ownStart, m->lowSeg, m->lowFace, m->lowOwner, m->bndCell,
-                    m->bndSeg, m->bndFace, m->hasBnd, m->tp.hdr, m->tp.blob};
+                    m->bndSeg, m->bndFace, m->hasBnd, m->tp.hdr, m->tp.blob, m->bp.hdr, m->bp.rec, m->bp.codes,
+                    m->bp.xFace, m->bp.xOwner, m->bp.xNei, m->bp.bFace, m->bp.bCell};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete m;
@@ -272,51 +274,27 @@ extern "C" int fvk_mesh_create(const fvk_mesh_desc* d, fvk_mesh** out)
     const int32_t* own = d->faceOwner;
     const int32_t* nei = d->faceNeighbour;
     {
-        std::vector<int32_t> seg(size_t(nC) + 1, 0);
-        for (int32_t f = 0; f < nI; ++f) { ++seg[size_t(own[f]) + 1]; ++seg[size_t(nei[f]) + 1]; }
-        for (int32_t b = 0; b < nB; ++b) ++seg[size_t(d->faceCells[b]) + 1];
-        for (int32_t c = 0; c < nC; ++c) seg[size_t(c) + 1] += seg[c];
-        const size_t nEnt = size_t(seg[nC]);
-        std::vector<int32_t> val(nEnt), ent(nEnt), plan(2 * nEnt), pos(seg.begin(), seg.end() - 1);
-        for (int32_t f = 0; f < nI; ++f)
+        FvkStencilHost sth;
+        fvk_build_stencil(d, sth);
+        std::vector<int32_t>&seg = sth.seg, &val = sth.val, &ent = sth.ent, &plan = sth.plan;
+        const size_t nEnt = ent.size();
+        // ---- brick plan of k_gather_brick (default explicit-operator kernel when available)
         {
-            int32_t k = pos[own[f]]++;
-            val[k] = f; ent[k] = f << 1;
-            plan[2 * size_t(k)] = f << 1; plan[2 * size_t(k) + 1] = nei[f];
-            k = pos[nei[f]]++;
-            val[k] = f; ent[k] = (f << 1) | 1;
-            plan[2 * size_t(k)] = (f << 1) | 1; plan[2 * size_t(k) + 1] = own[f];
-        }
-        for (int32_t b = 0; b < nB; ++b)
-        {
-            const int32_t k = pos[d->faceCells[b]]++;
-            val[k] = nI + b; ent[k] = (nI + b) << 1;
-            plan[2 * size_t(k)] = -(b + 1); plan[2 * size_t(k) + 1] = d->faceCells[b];
-        }
-        if (d->faceOrder)
-        {
-            // per-cell gather order = ascending key over the internal faces (boundary faces stay last);
-            // stencilVal keeps the reference's ascending local id (cellToFaceStencil.cpp:82-93)
-            const int32_t* key = d->faceOrder;
-            std::vector<std::pair<int32_t, int32_t>> tmp;
-            for (int32_t c = 0; c < nC; ++c)
+            FvkBrickPlanHost bph;
+            const char* why = "";
+            static const bool off = [] { const char* e = std::getenv("FVK_NO_BRICK"); return e && *e == '1'; }();
+            if (!off && fvk_build_brick_plan(d, sth, bph, &why))
             {
-                int32_t b0 = seg[c], b1 = seg[size_t(c) + 1];
-                while (b1 > b0 && (ent[b1 - 1] >> 1) >= nI) --b1;
-                tmp.clear();
-                for (int32_t k = b0; k < b1; ++k) tmp.emplace_back(key[ent[k] >> 1], k);
-                std::stable_sort(tmp.begin(), tmp.end());
-                std::vector<int32_t> e2(tmp.size()), p2(2 * tmp.size());
-                for (size_t i = 0; i < tmp.size(); ++i)
-                {
-                    e2[i] = ent[tmp[i].second];
-                    p2[2 * i] = plan[2 * size_t(tmp[i].second)]; p2[2 * i + 1] = plan[2 * size_t(tmp[i].second) + 1];
-                }
-                for (size_t i = 0; i < tmp.size(); ++i)
-                {
-                    ent[b0 + i] = e2[i];
-                    plan[2 * (size_t(b0) + i)] = p2[2 * i]; plan[2 * (size_t(b0) + i) + 1] = p2[2 * i + 1];
-                }
+                FvkBrickPlan& bp = m->bp;
+                UP(bp.hdr, bph.hdr.data(), bph.hdr.size());
+                UP(bp.rec, bph.rec.data(), bph.rec.size());
+                UP(bp.codes, bph.codes.data(), bph.codes.size());
+                UP(bp.xFace, bph.xFace.data(), bph.xFace.size());
+                UP(bp.xOwner, bph.xOwner.data(), bph.xOwner.size());
+                UP(bp.xNei, bph.xNei.data(), bph.xNei.size());
+                UP(bp.bFace, bph.bFace.data(), bph.bFace.size());
+                UP(bp.bCell, bph.bCell.data(), bph.bCell.size());
+                bp.nTiles = int32_t(bph.hdr.size()); bp.maxSlots = bph.maxSlots; bp.maxCells = bph.maxCells;
             }
         }
         // ---- tile plan (see FvkTilePlan): consecutive owned cells, bounded slot / entry counts

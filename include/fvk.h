@@ -446,9 +446,19 @@ int fvk_decomp_halo(const fvk_decomp* d, const int32_t** neighbourRanks, const i
                     const int32_t** sendCells, const int32_t** recvOffsets);
 int fvk_comm_set_halo_from_decomp(fvk_comm* comm, const fvk_decomp* d);
 
-/* experiment switch: selects the kernel variant used by the gather operators
- * (0 = default). Used by the roofline harness only. */
+/* experiment switch: selects the kernel variant used by the gather operators. 0 = default (the brick
+ * kernel when the mesh has a brick plan, else the per-cell gather), 5 = per-cell gather, 1-4 = packed-plan
+ * gathers, 6 = TMA tile kernel, 7 = brick kernel. Used by the roofline harness and the parity tests only. */
 int fvk_set_variant(int variant);
+
+/* Diagnostics, HOST only (no device needed): build the cell->face stencil and the brick plan of the explicit
+ * gather kernel for a mesh description and replay the plan exactly as the kernel reads it. info_h[8] =
+ * {nTiles, detected block dims nx ny nz (0 0 0: none -> runs of consecutive cells), brick shape lx by bz,
+ * max shared-memory slots per tile}; *badCells_h = number of cells whose replayed (face, sign) sequence differs
+ * from the reference's accumulation order (0 = exact). Returns FVK_EUNSUPPORTED when the mesh gets no brick plan
+ * (its per-cell face order is not [lower | owned, consecutive ids | boundary]); operators then use the per-cell
+ * gather. Environment: FVK_BRICK="lx,by,bz" overrides the default 32,4,4 brick. */
+int fvk_brick_plan_selftest(const fvk_mesh_desc* desc_h, int32_t* info_h, int64_t* badCells_h);
 
 #ifdef __cplusplus
 }

@@ -64,3 +64,32 @@ def rel_err(a, b):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     scale = max(np.abs(b).max(), 1e-300)
     return float(np.abs(a - b).max() / scale)
+
+
+def renumbered_block(nx, ny, nz, seed, box=(1.0, 1.0, 1.0)):
+    """A block mesh whose cells were renumbered at random, faces re-sorted into OpenFOAM's upper-triangular order
+    (owner < neighbour, by owner then neighbour; a flipped face gets -Sf). Same geometry, no block structure in the
+    numbering: exercises the unstructured path of every kernel."""
+    from foamadapter_b200.mesh import MeshDesc
+    g = MeshDesc.block(nx, ny, nz, *box)
+    nC, nI, nB = g.nCells, g.nInternalFaces, g.nBoundaryFaces
+    rng = np.random.default_rng(seed)
+    perm = rng.permutation(nC).astype(np.int32)  # old cell -> new cell
+    inv = np.argsort(perm)
+    o, n = perm[g.array("faceOwner")[:nI]], perm[g.array("faceNeighbour")]
+    flip = o > n
+    lo, hi = np.minimum(o, n), np.maximum(o, n)
+    order = np.lexsort((hi, lo))
+    fsel = np.concatenate([order, nI + np.arange(nB)])
+    Sf = g.array("faceAreas").reshape(-1, 3).copy()
+    Sf[:nI][flip] *= -1.0
+    fc = perm[g.array("faceCells")]
+    a = dict(nCells=nC, nInternalFaces=nI, nBoundaryFaces=nB, nPatches=g.nPatches,
+             cellVolumes=g.array("cellVolumes")[inv], cellCentres=g.array("cellCentres").reshape(-1, 3)[inv],
+             faceAreas=Sf[fsel], faceCentres=g.array("faceCentres").reshape(-1, 3)[fsel],
+             magFaceAreas=g.array("magFaceAreas")[fsel],
+             faceOwner=np.concatenate([lo[order], fc]).astype(np.int32), faceNeighbour=hi[order].astype(np.int32),
+             faceCells=fc.astype(np.int32), patchOffsets=g.array("patchOffsets"))
+    for k in ("bCf", "bCn", "bSf", "bMagSf", "bNf", "bDelta", "bWeights", "bDeltaCoeffs"):
+        a[k] = g.array(k)
+    return MeshDesc.from_arrays(a, g.patch_names)

@@ -1,0 +1,77 @@
+"""CPU tests of the brick plan (host code of libfvk, no GPU): the plan of the default explicit-operator kernel is
+replayed on the host exactly as k_gather_brick reads it and must reproduce, cell by cell, the (face, sign) sequence of
+the reference's Serial accumulation order (gaussGreenDiv.cpp:46-67) -- on block meshes of awkward sizes, on every
+sub-mesh of a decomposition (ghost cells, faceOrder key) and on a randomly renumbered mesh (no block structure)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from foamadapter_b200._capi import FvkError, check, lib
+from foamadapter_b200.decomp import Decomposition
+from foamadapter_b200.mesh import PATCHES_CAVITY2D, MeshDesc
+from tests.helpers import renumbered_block
+
+
+def selftest(desc):
+    info = (C.c_int32 * 8)()
+    bad = C.c_int64(-1)
+    check(lib().fvk_brick_plan_selftest(C.byref(desc.c), info, C.byref(bad)))
+    return list(info), bad.value
+
+
+@pytest.mark.parametrize("dims", [(5, 5, 1), (3, 3, 3), (20, 20, 1), (33, 7, 5), (100, 3, 2), (1, 1, 1), (7, 1, 1),
+                                  (1, 9, 4), (64, 48, 40), (40, 12, 9)])
+def test_block_meshes(dims):
+    d = MeshDesc.block(*dims)
+    info, bad = selftest(d)
+    assert bad == 0
+    nT, nx, ny, nz, lx, by, bz, slots = info
+    assert nx * ny * nz == d.nCells  # numbering detected (degenerate axes may be merged)
+    assert lx * by * bz <= 512 and nT >= -(-d.nCells // 512)
+    assert slots < 32768
+
+
+def test_cavity_patches_with_empty_faces():
+    info, bad = selftest(MeshDesc.block(20, 20, 1, patches=PATCHES_CAVITY2D))
+    assert bad == 0
+
+
+def test_brick_override(monkeypatch):
+    monkeypatch.setenv("FVK_BRICK", "16,8,4")
+    info, bad = selftest(MeshDesc.block(64, 32, 16))
+    assert bad == 0 and info[4:7] == [16, 8, 4] and info[0] == 4 * 4 * 4
+    monkeypatch.setenv("FVK_BRICK", "8,3,5")  # non power-of-two run/row counts: the kernel's division path
+    info, bad = selftest(MeshDesc.block(20, 10, 11))
+    assert bad == 0 and info[4:7] == [8, 3, 5]
+
+
+@pytest.mark.parametrize("P", [2, 4, 8])
+def test_decomposed_sub_meshes(P):
+    g = MeshDesc.block(16, 12, 10)
+    for r in range(P):
+        dec = Decomposition(g, P, r)
+        info, bad = selftest(dec.desc)
+        assert bad == 0
+        assert info[1] * info[2] * info[3] == dec.nOwned  # the owned block is still recognised
+
+
+def test_unstructured_numbering_uses_runs_of_consecutive_cells():
+    d = renumbered_block(12, 11, 10, 3)
+    info, bad = selftest(d)
+    assert bad == 0
+    assert info[1:4] == [0, 0, 0] and info[0] == -(-d.nCells // 512)
+
+
+def test_unsorted_faces_get_no_plan():
+    g = MeshDesc.block(6, 5, 4)
+    a = {k: g.array(k) for k in ("cellVolumes", "cellCentres", "faceAreas", "faceCentres", "magFaceAreas", "faceOwner",
+                                 "faceNeighbour", "faceCells", "patchOffsets")}
+    a.update(nCells=g.nCells, nInternalFaces=g.nInternalFaces, nBoundaryFaces=g.nBoundaryFaces, nPatches=g.nPatches)
+    nI = g.nInternalFaces
+    o, n = a["faceOwner"].copy(), a["faceNeighbour"].copy()
+    o[:nI], n[:] = o[:nI][::-1].copy(), n[::-1].copy()  # faces in descending owner order
+    a["faceOwner"], a["faceNeighbour"] = o, n
+    with pytest.raises(FvkError) as e:
+        selftest(MeshDesc.from_arrays(a))
+    assert e.value.code == 5  # FVK_EUNSUPPORTED: operators keep the per-cell gather

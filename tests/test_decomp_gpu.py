@@ -25,7 +25,7 @@ def emulate_halo(decs, fields):
 
 
 @pytest.mark.parametrize("P", [2, 8])
-@pytest.mark.parametrize("variant", [0, 6])
+@pytest.mark.parametrize("variant", [0, 5, 6])
 def test_subdomain_operators_bit_exact(P, variant):
     from foamadapter_b200 import _capi
     g = M.MeshDesc.block(12, 10, 8, 1.2, 1.0, 0.8)

@@ -13,7 +13,7 @@ import torch
 
 from foamadapter_b200 import _capi, fvcc, mesh as M, ops
 from oracle.cpu import Mesh as OMesh
-from tests.helpers import FIXTURE_BLOCKS, load_golden, neon_view, oracle_mesh_from_view
+from tests.helpers import FIXTURE_BLOCKS, load_golden, neon_view, oracle_mesh_from_view, renumbered_block
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-12
@@ -36,13 +36,27 @@ MESHES = {
     "33x17x9": lambda: M.MeshDesc.block(33, 17, 9, 1.0, 0.5, 0.2),
     "1x1x1": lambda: M.MeshDesc.block(1, 1, 1),
     "cavity20": lambda: M.MeshDesc.block(20, 20, 1, 0.1, 0.1, 0.01, patches=M.PATCHES_CAVITY2D),
+    # several 32x4x4 bricks per axis incl. ragged edge bricks (variant 0 = brick kernel)
+    "70x11x9": lambda: M.MeshDesc.block(70, 11, 9, 1.0, 0.5, 0.2),
+    # randomly renumbered cells: no block structure, the brick plan falls back to runs of consecutive cells
+    "renum12x11x10": lambda: renumbered_block(12, 11, 10, 3),
+    # non power-of-two brick (FVK_BRICK at mesh creation): the kernel's integer-division index path
+    "20x10x11@brick8,3,5": lambda: M.MeshDesc.block(20, 10, 11, 1.0, 0.5, 0.55),
 }
 
 
 @pytest.fixture(scope="module", params=sorted(MESHES))
 def case(request):
+    import os
     d = MESHES[request.param]()
-    return request.param, d, M.UnstructuredMesh(d), OMesh.from_desc(d)
+    brick = request.param.partition("@brick")[2]
+    if brick:
+        os.environ["FVK_BRICK"] = brick
+    try:
+        gm = M.UnstructuredMesh(d)
+    finally:
+        os.environ.pop("FVK_BRICK", None)
+    return request.param, d, gm, OMesh.from_desc(d)
 
 
 def _fields(om, seed, vec=False):
@@ -73,7 +87,7 @@ def test_mesh_handle_matches_oracle(case):
     assert np.array_equal(gm.to_host(M.NONORTH_DELTACOEFFS), om.nodc)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 6])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6])
 @pytest.mark.parametrize("vec", [False, True])
 @pytest.mark.parametrize("scheme", [0, 1])
 def test_div(case, scheme, vec, variant):
@@ -100,7 +114,7 @@ def test_div(case, scheme, vec, variant):
         _capi.lib().fvk_set_variant(0)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 6])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6])
 def test_grad(case, variant):
     name, d, gm, om = case
     phi, phib, _, _ = _fields(om, 2)
@@ -113,7 +127,7 @@ def test_grad(case, variant):
         _capi.lib().fvk_set_variant(0)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 6])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6])
 @pytest.mark.parametrize("vec", [False, True])
 def test_laplacian(case, vec, variant):
     name, d, gm, om = case
@@ -240,7 +254,7 @@ def test_128_parity_and_properties(big):
     phib = host(T.boundary.value)
     dphi, dflux, dphib = T.internal, dev(flux), T.boundary.value
     out = torch.zeros(om.nC, dtype=torch.float64, device="cuda")
-    for variant in (0, 1, 2, 3):
+    for variant in (0, 1, 2, 3, 5):
         _capi.lib().fvk_set_variant(variant)
         ops.div(gm, dflux, dphi, dphib, out, ops.LINEAR)
         assert np.array_equal(host(out), om.div(flux, phi, phib, 0))

@@ -5,6 +5,7 @@ Usage: python tools/roofline.py [--mesh 128 256] [--variants 0 1 2 3] [--reps 20
 """
 import argparse
 import json
+import os
 import sys
 from pathlib import Path
 
@@ -36,7 +37,7 @@ def timeit(fn, reps, flush):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--mesh", type=int, nargs="+", default=[128, 256])
-    ap.add_argument("--variants", type=int, nargs="+", default=[0, 6, 1])
+    ap.add_argument("--variants", type=int, nargs="+", default=[0, 5])
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--out", default=str(ROOT / "gpurun_out" / "roofline.jsonl"))
     args = ap.parse_args()
@@ -80,6 +81,9 @@ def main():
                 row = {"mesh": n, "variant": v, "kernel": name, "ms": med, "best_ms": best, "alg_bytes": ab[name],
                        "gbs": ab[name] / med / 1e6, "frac_of_" + kind: ab[name] / med / 1e6 / peak,
                        "face_ops_per_s": (nI + nB) / (med * 1e-3)}
+                for k in ("FVK_BRICK", "FVK_BRICK_MINB"):
+                    if os.environ.get(k):
+                        row[k] = os.environ[k]
                 rows.append(row)
                 print(json.dumps(row), flush=True)
         _capi.lib().fvk_set_variant(0)
