@@ -78,7 +78,15 @@ void fvk_build_stencil(const fvk_mesh_desc* d, FvkStencilHost& st)
 
 namespace
 {
-constexpr int32_t kTileCells = 512; // k_gather_brick: 256 threads x 2 cells
+constexpr int32_t kMaxTileCells = 512; // k_gather_brick: up to 2 cells per thread x 256 threads, or 512 threads
+constexpr uint16_t kPad = 0xffffu;     // pads a cell's code list to a multiple of 4 (one aligned 8-byte load)
+// cells per tile: FVK_BRICK_CELLS (64..512) overrides; default 256 = one cell per thread (kernel occupancy, see k_gather_brick)
+int32_t tile_cells()
+{
+    int32_t v = 256;
+    if (const char* e = std::getenv("FVK_BRICK_CELLS")) v = std::atoi(e);
+    return std::max(64, std::min(kMaxTileCells, v));
+}
 
 struct TileShape
 {
@@ -126,6 +134,7 @@ bool detect_dims(int32_t nOwned, int32_t nI, const int32_t* own, const int32_t* 
 
 void make_tiles(int32_t nOwned, const int32_t dims[3], bool structured, int32_t brick[3], std::vector<TileShape>& tiles)
 {
+    int32_t kTileCells = tile_cells();
     tiles.clear();
     if (!structured)
     {
@@ -134,12 +143,12 @@ void make_tiles(int32_t nOwned, const int32_t dims[3], bool structured, int32_t 
             tiles.push_back(TileShape {c, std::min(kTileCells, nOwned - c), 1, 1, 0, 0});
         return;
     }
-    int32_t L = 32, BY = 4, BZ = 4;
+    int32_t L = 32, BY = 4, BZ = kTileCells >= 512 ? 4 : 2;
     bool fixed = false; // FVK_BRICK="lx,by,bz": use exactly this shape (clipped to the mesh and to 512 cells)
     if (const char* e = std::getenv("FVK_BRICK"))
     {
         int a = 0, b = 0, c = 0;
-        if (std::sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && a > 0 && b > 0 && c > 0) { L = a; BY = b; BZ = c; fixed = true; }
+        if (std::sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && a > 0 && b > 0 && c > 0) { L = a; BY = b; BZ = c; fixed = true; kTileCells = kMaxTileCells; }
     }
     const int32_t nx = dims[0], ny = dims[1], nz = dims[2];
     int32_t lx = std::min(std::min(L, nx), kTileCells), bz = std::min(BZ, nz);
@@ -243,7 +252,7 @@ bool fvk_build_brick_plan(const fvk_mesh_desc* d, const FvkStencilHost& st, FvkB
             const CellInfo ci = analyse(c, nI, seg, ent);
             if (!ci.ok) { bad |= 2; return; }
             cellTile[c] = t; cellFaceStart[c] = ci.fs; cellSlotBase[c] = slots;
-            slots += ci.nOwn; codes += ci.nLow + ci.nBnd; nb += ci.nBnd; ++nc;
+            slots += ci.nOwn; codes += (ci.nLow + ci.nBnd + 3) & ~3; nb += ci.nBnd; ++nc;
         });
         tSlots[t] = slots; tCodes[t] = codes; tB[t] = nb; tC[t] = nc;
     }
@@ -274,7 +283,7 @@ bool fvk_build_brick_plan(const fvk_mesh_desc* d, const FvkStencilHost& st, FvkB
     for (int32_t t = 0; t < nT; ++t)
     {
         const TileShape& s = tiles[t];
-        if (tSlots[t] + tX[t] + tB[t] >= 32768 || tCodes[t] >= 65535 || tC[t] > kTileCells)
+        if (tSlots[t] + tX[t] + tB[t] >= 32767 || tCodes[t] >= 65535 || tC[t] > kMaxTileCells)
         {
             *reason = "tile exceeds the 16-bit slot range";
             return false;
@@ -295,7 +304,7 @@ bool fvk_build_brick_plan(const fvk_mesh_desc* d, const FvkStencilHost& st, FvkB
         out.maxCells = std::max(out.maxCells, tC[t]);
     }
     out.rec.resize(size_t(recBase));
-    out.codes.resize(size_t(codeBase) + 8, 0); // slack: the kernel prefetches 4 codes per cell unconditionally
+    out.codes.assign(size_t(codeBase) + 8, kPad); // every list is a multiple of 4 codes (codeBase too), padded with kPad
     out.xFace.resize(size_t(xBase)); out.xOwner.resize(size_t(xBase)); out.xNei.resize(size_t(xBase));
     out.bFace.resize(size_t(bBase)); out.bCell.resize(size_t(bBase));
     // pass 2: fill
@@ -333,6 +342,7 @@ bool fvk_build_brick_plan(const fvk_mesh_desc* d, const FvkStencilHost& st, FvkB
                     out.codes[size_t(h.codeBase) + list++] = uint16_t((slot << 1) | 1);
                 }
             }
+            while (list & 3) out.codes[size_t(h.codeBase) + list++] = kPad;
             lastLc = lc;
         });
         FvkBrickRec& r = out.rec[size_t(h.recBase) + lastLc + 1]; // closing record
@@ -408,15 +418,19 @@ int64_t fvk_verify_brick_plan(const fvk_mesh_desc* d, const FvkStencilHost& st, 
                 else if (f < nI || d->faceCells[f - nI] != c) ok = false;
                 seq.push_back(int32_t((f << 1) | wantSide));
             };
-            for (; ok && i < nList && (bp.codes[size_t(h.codeBase) + listBase + i] & 1); ++i)
-                pull(bp.codes[size_t(h.codeBase) + listBase + i], 1);
+            if ((listBase & 3) || (nList & 3) || (h.codeBase & 3)) ok = false; // aligned 8-byte code loads
+            auto codeAt = [&](int32_t k) { return bp.codes[size_t(h.codeBase) + listBase + k]; };
+            for (; ok && i < nList && codeAt(i) != kPad && (codeAt(i) & 1); ++i) pull(codeAt(i), 1);
             for (int32_t k = 0; ok && k < nOwn; ++k) seq.push_back((r0.faceStart + k) << 1);
             for (; ok && i < nList; ++i)
             {
-                const uint16_t code = bp.codes[size_t(h.codeBase) + listBase + i];
+                const uint16_t code = codeAt(i);
+                if (code == kPad) break; // padding only at the end of a list
                 if (code & 1) { ok = false; break; }
                 pull(code, 0);
             }
+            for (; ok && i < nList; ++i)
+                if (codeAt(i) != kPad) ok = false;
             const int32_t e0 = st.seg[c], e1 = st.seg[size_t(c) + 1];
             if (ok && int32_t(seq.size()) == e1 - e0)
             {

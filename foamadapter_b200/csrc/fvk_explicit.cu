@@ -612,217 +612,205 @@ int launch_tile(const fvk_mesh* m, Op op, Scaling sc, double* out, int mode, cud
 }
 
 // ---- brick kernel (default when the mesh has a brick plan) ---------------------------------------------------------
-// One block per tile of the FvkBrickPlan (<= 512 cells: an x-run x y x z brick of a block-structured numbering, or a
-// run of consecutive cells otherwise), 256 threads, 2 cells per thread. OpenFOAM orders faces by owner, so the faces a
+// One block per tile of the FvkBrickPlan (<= K*TB cells: an x-run x y x z brick of a block-structured numbering, or a
+// run of consecutive cells otherwise), TB threads, K cells per thread. OpenFOAM orders faces by owner, so the faces a
 // cell owns are consecutive: the thread reads them straight from the face streams (no index array), evaluates each
 // flux ONCE and parks it in a shared-memory slot; the few lower faces whose owner lies outside the tile ("cross"
-// faces, ~0.5 per cell for a 32x4x4 brick instead of 2-3 for a run of consecutive cells) and the boundary faces are
+// faces, ~0.5 per cell for a brick instead of 2-3 for a run of consecutive cells) and the boundary faces are
 // evaluated by a thread each. After one barrier every cell adds its slots in the reference's order
 // [lower | owned | boundary] (gaussGreenDiv.cpp:46-67: ascending face id), scales by coeff/V and writes once.
-// All loads of a phase are issued before the first use (2 cells x 3 faces x 3-5 operands in flight per thread), the
-// only mesh-static data read besides neighbour[] are 8 B/cell of records and 2 B per lower face of slot codes:
-// DRAM traffic ~1.05x the algorithmic bytes (the owner[] array is never read).
-template <class Op, int MINB>
-__global__ void __launch_bounds__(256, MINB)
+// All loads of a phase are issued before the first use (K cells x 3 faces x 3-5 operands in flight per thread), the
+// only mesh-static data read besides neighbour[] are 8 B/cell of records and 8 B/cell of slot codes (4 uint16, one
+// aligned load): DRAM traffic ~1.09x the algorithmic bytes (ncu, profiles/), the owner[] array is never read.
+// The load chain hdr -> record -> face operands -> neighbour phi is 4 deep, so the kernel lives on resident blocks:
+// K = 1 keeps it under 48 registers (5-6 blocks of 256 threads per SM).
+// 16-byte load of one quarter of the tile header that the compiler may not keep alive across phases (volatile):
+// the later phases re-read the header from L1 instead of holding eight more registers through phase A1.
+__device__ __forceinline__ int4 ld_hdr_q(const FvkBrickHdr* h, int q)
+{
+    int4 v;
+    asm volatile("ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(reinterpret_cast<const int4*>(h) + q));
+    return v;
+}
+
+template <class Op, int TB, int MINB>
+__global__ void __launch_bounds__(TB, MINB)
 k_gather_brick(Op op, Scaling sc, FvkBrickPlan bp, int nI, const int* __restrict__ neighbour, double* __restrict__ out, int mode)
 {
     using VT = typename Op::V;
     using T = typename VT::T;
     using CL = CellLd<typename Op::CV>;
     using CT = typename CL::T;
-    constexpr int K = 2, MO = 3; // cells per thread, owned faces handled in the unrolled path
+    constexpr int MO = 3; // owned faces handled in the unrolled path
     constexpr int W0 = Op::W0, W1 = Op::W1 ? Op::W1 : 1;
     extern __shared__ __align__(16) unsigned char smem[];
     T* sflux = reinterpret_cast<T*>(smem);
-
-    const int4* hp = reinterpret_cast<const int4*>(bp.hdr + blockIdx.x);
-    const int4 h0 = hp[0], h1 = hp[1], h2 = hp[2], h3 = hp[3];
-    const int c0 = h0.x, runLen = h0.y, by = h0.z, nRuns = h0.w, sy = h1.x, sz = h1.y, shiftL = h1.z, shiftBy = h1.w;
-    const int recBase = h2.x, codeBase = h2.y, xBase = h2.z, nx = h2.w, bBase = h3.x, nb = h3.y, nOwnSlots = h3.z, nc = h3.w;
+    const FvkBrickHdr* hdr = bp.hdr + blockIdx.x;
     const double* __restrict__ S0 = op.s0();
     const double* __restrict__ S1 = op.s1();
     const double* __restrict__ cellsG = op.cells();
     const int tid = threadIdx.x;
 
-    // ---- indices of this thread's first cross face (phase A2) are requested first: they start a second load chain
-    const bool hx = tid < nx;
-    int xf = 0, xo = 0, xn = 0;
-    if (hx) { xf = bp.xFace[xBase + tid]; xo = bp.xOwner[xBase + tid]; xn = bp.xNei[xBase + tid]; }
-
-    // ---- phase A1: records -> owned faces of K cells
-    int cell[K], fs[K], slotBase[K], nOwn[K], listBase[K], nList[K];
-    bool valid[K];
-    unsigned short cd[K][4];
-#pragma unroll
-    for (int q = 0; q < K; ++q)
+    // ---- phase A1: record -> the faces this thread's cell owns
+    int cell, fs, slotBase, nOwn, listInfo; // listInfo = listBase | nList << 16
+    bool valid;
+    uint2 cw; // 4 uint16 slot codes (lists start on 8-byte boundaries; 0xffff pads)
     {
-        const int lc = tid + 256 * q;
-        valid[q] = lc < nc;
+        const int4 h0 = ld_hdr_q(hdr, 0), h1 = ld_hdr_q(hdr, 1), h2 = ld_hdr_q(hdr, 2), h3 = ld_hdr_q(hdr, 3);
+        const int c0 = h0.x, runLen = h0.y, by = h0.z, nRuns = h0.w, sy = h1.x, sz = h1.y, shiftL = h1.z, shiftBy = h1.w;
+        valid = tid < h3.w;
         int r = 0;
-        if (nRuns > 1) r = (shiftL >= 0) ? (lc >> shiftL) : (lc / runLen);
-        const int off = lc - r * runLen;
+        if (nRuns > 1) r = (shiftL >= 0) ? (tid >> shiftL) : (tid / runLen);
+        const int off = tid - r * runLen;
         const int b = (shiftBy >= 0) ? (r >> shiftBy) : (r / by);
         const int a = r - b * by;
-        cell[q] = valid[q] ? c0 + a * sy + b * sz + off : c0;
+        cell = valid ? c0 + a * sy + b * sz + off : c0;
         uint2 r0 = make_uint2(0u, 0u), r1 = make_uint2(0u, 0u);
-        if (valid[q])
+        if (valid)
         {
-            const uint2* rp = reinterpret_cast<const uint2*>(bp.rec) + recBase + lc;
+            const uint2* rp = reinterpret_cast<const uint2*>(bp.rec) + h2.x + tid;
             r0 = rp[0]; r1 = rp[1];
         }
-        fs[q] = int(r0.x);
-        slotBase[q] = int(r0.y & 0xffffu); listBase[q] = int(r0.y >> 16);
-        nOwn[q] = int(r1.y & 0xffffu) - slotBase[q]; nList[q] = int(r1.y >> 16) - listBase[q];
+        fs = int(r0.x);
+        slotBase = int(r0.y & 0xffffu);
+        nOwn = int(r1.y & 0xffffu) - slotBase;
+        const int listBase = int(r0.y >> 16), nList = int(r1.y >> 16) - listBase;
+        listInfo = listBase | (nList << 16);
+        cw = (valid && nList > 0) ? *reinterpret_cast<const uint2*>(bp.codes + h2.y + listBase) : make_uint2(0xffffffffu, 0xffffffffu);
     }
-    int nbr[K][MO];
+    const double vol = sc.V[cell];
+    {
+        int nbr[MO];
 #pragma unroll
-    for (int q = 0; q < K; ++q)
-#pragma unroll
-        for (int k = 0; k < MO; ++k) nbr[q][k] = (k < nOwn[q]) ? neighbour[fs[q] + k] : cell[q];
-    double fa[K][MO][W0], fb[K][MO][W1];
-#pragma unroll
-    for (int q = 0; q < K; ++q)
+        for (int k = 0; k < MO; ++k) nbr[k] = (k < nOwn) ? neighbour[fs + k] : cell;
+        double fa[MO][W0], fb[MO][W1];
 #pragma unroll
         for (int k = 0; k < MO; ++k)
         {
-            const bool p = k < nOwn[q];
-            const int64_t f = fs[q] + k;
+            const bool p = k < nOwn;
+            const int64_t f = fs + k;
 #pragma unroll
-            for (int i = 0; i < W0; ++i) fa[q][k][i] = p ? S0[int64_t(W0) * f + i] : 0.0;
-            fb[q][k][0] = (Op::W1 && p) ? S1[f] : 0.0;
+            for (int i = 0; i < W0; ++i) fa[k][i] = p ? S0[int64_t(W0) * f + i] : 0.0;
+            fb[k][0] = (Op::W1 && p) ? S1[f] : 0.0;
         }
-    CT pc[K];
-    double vol[K], vw[K];
+        const CT pc = CL::ld(cellsG, cell);
+        CT pn[MO];
 #pragma unroll
-    for (int q = 0; q < K; ++q)
-    {
-        pc[q] = CL::ld(cellsG, cell[q]);
-        vol[q] = sc.V[cell[q]];
-        vw[q] = sc.view ? sc.view[cell[q]] : 1.0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) cd[q][j] = valid[q] ? bp.codes[codeBase + listBase[q] + j] : (unsigned short) 0;
-    }
-    // cross-face operands
-    double xa[W0], xb[W1];
-    CT xpo = CL::ld(cellsG, c0), xpn = xpo;
-    if (hx)
-    {
-#pragma unroll
-        for (int i = 0; i < W0; ++i) xa[i] = S0[int64_t(W0) * xf + i];
-        if (Op::W1) xb[0] = S1[xf];
-        xpo = CL::ld(cellsG, xo);
-        xpn = CL::ld(cellsG, xn);
-    }
-    CT pn[K][MO];
-#pragma unroll
-    for (int q = 0; q < K; ++q)
-#pragma unroll
-        for (int k = 0; k < MO; ++k) pn[q][k] = CL::ld(cellsG, nbr[q][k]);
-#pragma unroll
-    for (int q = 0; q < K; ++q)
-    {
+        for (int k = 0; k < MO; ++k) pn[k] = CL::ld(cellsG, nbr[k]);
 #pragma unroll
         for (int k = 0; k < MO; ++k)
-            if (k < nOwn[q]) sflux[slotBase[q] + k] = op.fluxv(fa[q][k], fb[q][k], pc[q], pn[q][k]);
-        for (int k = MO; k < nOwn[q]; ++k) // polyhedral cells owning more than MO faces
+            if (k < nOwn) sflux[slotBase + k] = op.fluxv(fa[k], fb[k], pc, pn[k]);
+        for (int k = MO; k < nOwn; ++k) // polyhedral cells owning more than MO faces
         {
-            const int64_t f = fs[q] + k;
+            const int64_t f = fs + k;
             double a[W0], b[W1];
 #pragma unroll
             for (int i = 0; i < W0; ++i) a[i] = S0[int64_t(W0) * f + i];
             if (Op::W1) b[0] = S1[f];
-            sflux[slotBase[q] + k] = op.fluxv(a, b, pc[q], CL::ld(cellsG, neighbour[f]));
+            sflux[slotBase + k] = op.fluxv(a, b, pc, CL::ld(cellsG, neighbour[f]));
         }
     }
-    // ---- phase A2: cross faces, thread per face
-    if (hx) sflux[nOwnSlots + tid] = op.fluxv(xa, xb, xpo, xpn);
-    for (int i = tid + 256; i < nx; i += 256)
+    // ---- phase A2 / A3: cross faces and boundary faces, thread per face
     {
-        const int f = bp.xFace[xBase + i];
-        const CT po = CL::ld(cellsG, bp.xOwner[xBase + i]);
-        const CT pnn = CL::ld(cellsG, bp.xNei[xBase + i]);
-        double a[W0], b[W1];
+        const int4 h2 = ld_hdr_q(hdr, 2), h3 = ld_hdr_q(hdr, 3);
+        const int xBase = h2.z, nx = h2.w, bBase = h3.x, nb = h3.y, nOwnSlots = h3.z;
+        for (int i = tid; i < nx; i += TB)
+        {
+            const int f = bp.xFace[xBase + i];
+            const CT po = CL::ld(cellsG, bp.xOwner[xBase + i]);
+            const CT pnn = CL::ld(cellsG, bp.xNei[xBase + i]);
+            double a[W0], b[W1];
 #pragma unroll
-        for (int q = 0; q < W0; ++q) a[q] = S0[int64_t(W0) * f + q];
-        if (Op::W1) b[0] = S1[f];
-        sflux[nOwnSlots + i] = op.fluxv(a, b, po, pnn);
-    }
-    // ---- phase A3: boundary faces, thread per face
-    for (int i = tid; i < nb; i += 256)
-    {
-        const int f = bp.bFace[bBase + i];
-        sflux[nOwnSlots + nx + i] = op.boundary(f, f - nI, bp.bCell[bBase + i]);
+            for (int q = 0; q < W0; ++q) a[q] = S0[int64_t(W0) * f + q];
+            if (Op::W1) b[0] = S1[f];
+            sflux[nOwnSlots + i] = op.fluxv(a, b, po, pnn);
+        }
+        for (int i = tid; i < nb; i += TB)
+        {
+            const int f = bp.bFace[bBase + i];
+            sflux[nOwnSlots + nx + i] = op.boundary(f, f - nI, bp.bCell[bBase + i]);
+        }
     }
     __syncthreads();
     // ---- phase B: per-cell accumulation in the reference's order
+    if (!valid) return;
+    T acc = (mode == FVK_ACC_SCALE) ? VT::ld(out, cell) : VT::zero();
+    const unsigned cd[4] = {cw.x & 0xffffu, cw.x >> 16, cw.y & 0xffffu, cw.y >> 16};
+    const int nList = listInfo >> 16;
+    int nLow = 0;
+    bool more = true;
 #pragma unroll
-    for (int q = 0; q < K; ++q)
+    for (int j = 0; j < 4; ++j)
     {
-        if (!valid[q]) continue;
-        const int c = cell[q];
-        T acc = (mode == FVK_ACC_SCALE) ? VT::ld(out, c) : VT::zero();
-        const unsigned short* gcodes = bp.codes + codeBase + listBase[q];
-        int nLow = 0;
-        bool more = true;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-        {
-            const bool low = more && j < nList[q] && (cd[q][j] & 1);
-            if (low) { acc = VT::sub(acc, sflux[cd[q][j] >> 1]); ++nLow; }
-            more = low;
-        }
-        if (more)
-            for (; nLow < nList[q]; ++nLow)
-            {
-                const unsigned code = gcodes[nLow];
-                if (!(code & 1u)) break;
-                acc = VT::sub(acc, sflux[code >> 1]);
-            }
-        for (int k = 0; k < nOwn[q]; ++k) acc = VT::add(acc, sflux[slotBase[q] + k]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (j >= nLow && j < nList[q]) acc = VT::add(acc, sflux[cd[q][j] >> 1]);
-        for (int j = (nLow > 4 ? nLow : 4); j < nList[q]; ++j) acc = VT::add(acc, sflux[gcodes[j] >> 1]);
-        double s;
-        if (sc.invVolOnly) s = 1 / vol[q];
-        else s = (sc.view ? vw[q] * sc.coeff : sc.coeff) / vol[q];
-        finish<VT>(out, c, acc, s, mode);
+        const bool low = more && cd[j] != 0xffffu && (cd[j] & 1u);
+        if (low) { acc = VT::sub(acc, sflux[cd[j] >> 1]); ++nLow; }
+        more = low;
     }
+    if (more && nList > 4) // more than 4 lower faces: the rest of the list comes from global memory
+    {
+        const unsigned short* gcodes = bp.codes + ld_hdr_q(hdr, 2).y + (listInfo & 0xffff);
+        for (; nLow < nList; ++nLow)
+        {
+            const unsigned code = gcodes[nLow];
+            if (code == 0xffffu || !(code & 1u)) break;
+            acc = VT::sub(acc, sflux[code >> 1]);
+        }
+    }
+    for (int k = 0; k < nOwn; ++k) acc = VT::add(acc, sflux[slotBase + k]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (j >= nLow && cd[j] != 0xffffu) acc = VT::add(acc, sflux[cd[j] >> 1]);
+    if (nList > 4)
+    {
+        const unsigned short* gcodes = bp.codes + ld_hdr_q(hdr, 2).y + (listInfo & 0xffff);
+        for (int j = (nLow > 4 ? nLow : 4); j < nList; ++j)
+        {
+            const unsigned code = gcodes[j];
+            if (code == 0xffffu) break;
+            acc = VT::add(acc, sflux[code >> 1]);
+        }
+    }
+    double s;
+    if (sc.invVolOnly) s = 1 / vol;
+    else s = (sc.view ? sc.view[cell] * sc.coeff : sc.coeff) / vol;
+    finish<VT>(out, cell, acc, s, mode);
 }
 
-template <class Op, int MINB>
+template <class Op, int TB, int MINB>
 int launch_brick_n(const fvk_mesh* m, Op op, Scaling sc, double* out, int mode, cudaStream_t st)
 {
     using T = typename Op::V::T;
     static bool optedIn[64] = {false};
     const size_t bytes = size_t(m->bp.maxSlots) * sizeof(T);
-    if (bytes > 200 * 1024) return -1;
+    if (bytes > 200 * 1024 || m->bp.maxCells > TB) return -1;
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) return -1;
     if (!optedIn[dev])
     {
-        FVK_CUDA(cudaFuncSetAttribute(k_gather_brick<Op, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        FVK_CUDA(cudaFuncSetAttribute(k_gather_brick<Op, TB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         optedIn[dev] = true;
     }
-    k_gather_brick<Op, MINB><<<m->bp.nTiles, 256, bytes, st>>>(op, sc, m->bp, m->nInternalFaces, m->neighbour, out, mode);
+    k_gather_brick<Op, TB, MINB><<<m->bp.nTiles, TB, bytes, st>>>(op, sc, m->bp, m->nInternalFaces, m->neighbour, out, mode);
     FVK_LAUNCH_CHECK();
     return FVK_OK;
 }
+// kernel configuration: threads per block TB (= max cells per tile), resident blocks the register allocation aims at.
+// fvk_set_brick_config / FVK_BRICK_CFG="1,TB,MINB" override for sweeps (instantiated combinations only).
 template <class Op>
 int launch_brick(const fvk_mesh* m, Op op, Scaling sc, double* out, int mode, cudaStream_t st)
 {
-    // resident blocks per SM the register allocation aims at: scalar operators keep 2 cells x 3 faces of operands in
-    // <= 85 registers (3 blocks), Vec3 operands need <= 128 (2 blocks). FVK_BRICK_MINB overrides for sweeps.
-    static const int env = [] { const char* e = std::getenv("FVK_BRICK_MINB"); return e ? std::atoi(e) : 0; }();
     constexpr bool wide = sizeof(typename Op::V::T) > 8 || Op::W0 > 1;
-    const int minb = env ? env : (wide ? 2 : 3);
-    switch (minb)
-    {
-        case 2: return launch_brick_n<Op, 2>(m, op, sc, out, mode, st);
-        case 4: return launch_brick_n<Op, 4>(m, op, sc, out, mode, st);
-        default: return launch_brick_n<Op, 3>(m, op, sc, out, mode, st);
-    }
+    int TB = m->bp.maxCells > 256 ? 512 : (m->bp.maxCells > 128 ? 256 : 128);
+    int MINB = (wide ? 4 : 6) * 256 / TB;
+    int cfg[3];
+    if (fvk_brick_config(cfg)) { TB = cfg[1]; MINB = cfg[2]; }
+#define FVK_BRICK_CASE(tb, mb) if (TB == tb && MINB == mb) return launch_brick_n<Op, tb, mb>(m, op, sc, out, mode, st)
+    FVK_BRICK_CASE(256, 3); FVK_BRICK_CASE(256, 4); FVK_BRICK_CASE(256, 5); FVK_BRICK_CASE(256, 6); FVK_BRICK_CASE(256, 8);
+    FVK_BRICK_CASE(512, 2); FVK_BRICK_CASE(512, 3); FVK_BRICK_CASE(512, 4);
+    FVK_BRICK_CASE(128, 8); FVK_BRICK_CASE(128, 12); FVK_BRICK_CASE(128, 16);
+#undef FVK_BRICK_CASE
+    return -1;
 }
 
 __host__ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

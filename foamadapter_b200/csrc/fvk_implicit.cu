@@ -12,6 +12,8 @@
 // inside a term, faces in ascending id, then boundary faces), so the result is bit-identical.
 #include "fvk_device.cuh"
 
+#include <cstdlib>
+
 namespace
 {
 struct S1
@@ -183,6 +185,191 @@ k_assemble(Terms terms, AsmMesh m, fvk_bfield bd, double* __restrict__ values, d
     VT::st(rhs, c, r);
 }
 
+// ---- fast path: fresh system, rows laid out like the stencil, at most two face terms -----------------------------
+// Same arithmetic and accumulation order as k_assemble, organised for the memory system:
+//  * the first E internal entries of the cell->face stencil are fetched up front and the face loop is fully unrolled
+//    with the kinds of the (<= 2) face terms as template parameters, so all face operands of a row are in flight
+//    together instead of one dependent load chain per face and term;
+//  * the coefficient each face contributes to the diagonal is kept in registers: the term-major diagonal pass reads
+//    no memory for the first E faces;
+//  * rows of a mesh in OpenFOAM face order are [lower | diag | upper] in stencil order, so an entry's slot is its
+//    position: ownerOffset/neighbourOffset are not read;
+//  * a warp's 32 rows are contiguous in CSR: entries are parked in shared memory and written with coalesced stores
+//    (the per-thread 56-byte row stride costs 4x the L2 write transactions).
+constexpr int ASM_E = 6;      // stencil entries handled in registers
+constexpr int ASM_CAPW = 288; // staged entries per warp (32 rows x 9)
+
+template <int KIND>
+__device__ __forceinline__ void face_coeffs_k(const fvk_term& t, const AsmMesh& m, int f, double& lowerAndOwnDiag,
+                                              double& upperAndNeiDiag)
+{
+    if (KIND == FVK_TERM_DIV)
+    {
+        const double F = t.faceField[f];
+        const double wf = (t.scheme == FVK_LINEAR) ? m.w[f] : (F >= 0 ? 1.0 : 0.0);
+        lowerAndOwnDiag = -wf * F;
+        upperAndNeiDiag = F * (1 - wf);
+    }
+    else
+    {
+        const double flux = m.nodc[f] * t.faceField[f] * m.magSf[f];
+        lowerAndOwnDiag = flux;
+        upperAndNeiDiag = flux;
+    }
+}
+
+template <class VT, int K0, int K1>
+__global__ void __launch_bounds__(256)
+k_assemble_fast(Terms terms, AsmMesh m, fvk_bfield bd, int ft0, int ft1, double* __restrict__ values,
+                double* __restrict__ rhs, double* __restrict__ bcMatrix, double* __restrict__ bcRhs)
+{
+    using T = typename VT::T;
+    constexpr int NC = VT::NC;
+    constexpr bool HAS1 = K1 != 0;
+    extern __shared__ double stageAll[];
+    const int lane = threadIdx.x & 31;
+    double* stage = stageAll + size_t(threadIdx.x >> 5) * ASM_CAPW * NC;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = c < m.nC;
+    const int r0 = active ? m.rowOffs[c] : 0, r1 = active ? m.rowOffs[c + 1] : 0;
+    const int s0 = active ? m.seg[c] : 0, s1 = active ? m.seg[c + 1] : 0;
+    const int nInt = r1 - r0 - 1; // internal faces of the cell (-1 on inactive lanes)
+    const int wbase = __shfl_sync(0xffffffffu, r0, 0);
+    const int wend = __reduce_max_sync(0xffffffffu, r1);
+    const bool staged = (wend - wbase) <= ASM_CAPW;
+    int code[ASM_E];
+#pragma unroll
+    for (int k = 0; k < ASM_E; ++k) code[k] = (k < nInt) ? m.ent[s0 + k] : 0;
+    const int nLower = active ? int(m.diagOffs[c]) : 0;
+    const fvk_term& t0 = terms.t[ft0];
+    const fvk_term& t1 = terms.t[HAS1 ? ft1 : ft0];
+    const double os0 = active ? term_scaling(t0, c) : 0.0;
+    const double os1 = (HAS1 && active) ? term_scaling(t1, c) : 0.0;
+
+    auto put = [&](int pos, const T& v) {
+        if (staged)
+        {
+            double* q = stage + size_t(r0 - wbase + pos) * NC;
+            if (NC == 1) q[0] = reinterpret_cast<const double&>(v);
+            else { const double* pv = reinterpret_cast<const double*>(&v); q[0] = pv[0]; q[1] = pv[1]; q[2] = pv[2]; }
+        }
+        else
+            VT::st(values, r0 + pos, v);
+    };
+
+    // ---- internal faces: coefficients once, off-diagonal entries out, diagonal contributions kept
+    double lo0[ASM_E], up0[ASM_E], lo1[ASM_E], up1[ASM_E];
+#pragma unroll
+    for (int k = 0; k < ASM_E; ++k)
+    {
+        const int f = code[k] >> 1; // face 0 on padded lanes: valid address, value unused
+        face_coeffs_k<K0>(t0, m, f, lo0[k], up0[k]);
+        if (HAS1) face_coeffs_k<K1>(t1, m, f, lo1[k], up1[k]);
+    }
+    double dc0[ASM_E], dc1[ASM_E];
+#pragma unroll
+    for (int k = 0; k < ASM_E; ++k)
+    {
+        const bool side = code[k] & 1;
+        T v = VT::zero();
+        v = VT::add(v, VT::mul(os0, VT::splat(side ? lo0[k] : up0[k])));
+        if (HAS1) v = VT::add(v, VT::mul(os1, VT::splat(side ? lo1[k] : up1[k])));
+        dc0[k] = side ? up0[k] : lo0[k];
+        dc1[k] = HAS1 ? (side ? up1[k] : lo1[k]) : 0.0;
+        if (k < nInt) put(side ? k : k + 1, v);
+    }
+    for (int k = ASM_E; k < nInt; ++k) // polyhedral cells with more than ASM_E internal faces
+    {
+        const int cd = m.ent[s0 + k], f = cd >> 1;
+        const bool side = cd & 1;
+        double lo, up;
+        T v = VT::zero();
+        face_coeffs_k<K0>(t0, m, f, lo, up);
+        v = VT::add(v, VT::mul(os0, VT::splat(side ? lo : up)));
+        if (HAS1)
+        {
+            face_coeffs_k<K1>(t1, m, f, lo, up);
+            v = VT::add(v, VT::mul(os1, VT::splat(side ? lo : up)));
+        }
+        put(side ? k : k + 1, v);
+    }
+    // ---- diagonal and rhs: term-major, faces ascending inside a term (identical order to k_assemble)
+    T d = VT::zero(), r = VT::zero();
+    if (active)
+        for (int kt = 0; kt < terms.n; ++kt)
+        {
+            const fvk_term& t = terms.t[kt];
+            if (t.kind == FVK_TERM_DIV || t.kind == FVK_TERM_LAPLACIAN)
+            {
+                const bool second = HAS1 && kt == ft1;
+                const double os = second ? os1 : os0;
+#pragma unroll
+                for (int k = 0; k < ASM_E; ++k)
+                    if (k < nInt) d = VT::sub(d, VT::mul(os, VT::splat(second ? dc1[k] : dc0[k])));
+                for (int k = ASM_E; k < nInt; ++k)
+                {
+                    const int cd = m.ent[s0 + k];
+                    double lo, up;
+                    face_coeffs(t, m, cd >> 1, lo, up);
+                    d = VT::sub(d, VT::mul(os, VT::splat((cd & 1) ? up : lo)));
+                }
+                for (int e = s0 + nInt; e < s1; ++e)
+                {
+                    const int f = m.ent[e] >> 1;
+                    const int b = f - m.nI;
+                    const double vf1 = bd.valueFraction[b];
+                    T valueMat, valueRhs;
+                    if (t.kind == FVK_TERM_DIV)
+                    { // gaussGreenDiv.cpp:237-260 (boundary weight of both schemes is 1)
+                        const double flux = 1.0 * t.faceField[f];
+                        const double vf2 = 1.0 - vf1;
+                        valueMat = VT::splat(flux * os * vf2);
+                        d = VT::add(d, valueMat);
+                        valueRhs = VT::add(VT::mul(flux * os, VT::mul(vf1, VT::ld(bd.refValue, b))),
+                                           VT::mul(1 / m.bDeltaCoeffs[b], VT::mul(vf2, VT::ld(bd.refGrad, b))));
+                    }
+                    else
+                    { // gaussGreenLaplacian.cpp:156-175
+                        const double flux = t.faceField[f] * m.magSf[f];
+                        const double dcf = m.nodc[f];
+                        valueMat = VT::splat(flux * os * vf1 * dcf);
+                        d = VT::sub(d, valueMat);
+                        valueRhs = VT::mul(flux * os, VT::add(VT::mul(vf1 * dcf, VT::ld(bd.refValue, b)),
+                                                              VT::mul(1.0 - vf1, VT::ld(bd.refGrad, b))));
+                    }
+                    r = VT::sub(r, valueRhs);
+                    VT::st(bcMatrix, b, valueMat);
+                    VT::st(bcRhs, b, valueRhs);
+                }
+            }
+            else if (t.kind == FVK_TERM_DDT)
+            { // ddtOperator.cpp:50-59
+                const double os = term_scaling(t, c);
+                const double dtInver = 1.0 / t.dt;
+                const double commonCoef = os * m.V[c] * dtInver;
+                d = VT::add(d, VT::splat(commonCoef));
+                r = VT::add(r, VT::mul(commonCoef, VT::ld(t.cellField, c)));
+            }
+            else if (t.kind == FVK_TERM_SOURCE)
+            { // sourceTerm.cpp:46-54
+                const double os = term_scaling(t, c);
+                d = VT::add(d, VT::splat(os * t.cellField[c] * m.V[c]));
+            }
+        }
+    if (active)
+    {
+        put(nLower, d);
+        VT::st(rhs, c, r);
+    }
+    if (staged)
+    {
+        __syncwarp();
+        const int n = (wend - wbase) * NC;
+        double* __restrict__ dst = values + size_t(wbase) * NC;
+        for (int i = lane; i < n; i += 32) dst[i] = stage[i];
+    }
+}
+
 // createEmptyLinearSystem's BoundaryCoefficients index arrays (linearSystem.hpp:163-174):
 // matrixIdxs[b] = celli + diagOffset[celli] (sic), rhsIdxs[b] = celli
 __global__ void __launch_bounds__(256)
@@ -274,6 +461,33 @@ int assemble_impl(const fvk_mesh* m, int nTerms, const fvk_term* terms_h, const 
     AsmMesh am {m->nCells, m->nInternalFaces, m->stencilSeg, m->gatherEnt, m->rowOffs, m->diagOffset, m->ownerOffset,
                 m->neighbourOffset, m->V, m->weights, m->nonOrthDeltaCoeffs, m->magSf, m->bDeltaCoeffs};
     const int grid = (m->nCells + 255) / 256;
+    // fast path (k_assemble_fast): fresh system, rows in stencil order, one or two face terms
+    int ft[2] = {-1, -1}, nFace = 0;
+    for (int k = 0; k < nTerms; ++k)
+        if (terms_h[k].kind == FVK_TERM_DIV || terms_h[k].kind == FVK_TERM_LAPLACIAN)
+        {
+            if (nFace < 2) ft[nFace] = k;
+            ++nFace;
+        }
+    static const bool noFast = [] { const char* e = std::getenv("FVK_ASM_GENERIC"); return e && *e == '1'; }();
+    if (!noFast && !accumulate && m->rowsInStencilOrder && nFace >= 1 && nFace <= 2)
+    {
+        const size_t shm = sizeof(double) * 8 * ASM_CAPW * VT::NC;
+        const int k0 = terms_h[ft[0]].kind, k1 = nFace == 2 ? terms_h[ft[1]].kind : 0;
+#define FVK_ASM_CASE(a, bb)                                                                                             \
+    if (k0 == a && k1 == bb)                                                                                            \
+    {                                                                                                                   \
+        if (shm > 48 * 1024)                                                                                            \
+            FVK_CUDA(cudaFuncSetAttribute(k_assemble_fast<VT, a, bb>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(shm))); \
+        k_assemble_fast<VT, a, bb><<<grid, 256, shm, fvk_cu(s)>>>(T, am, b, ft[0], ft[1], values, rhs, bcMatrix, bcRhs); \
+        FVK_LAUNCH_CHECK();                                                                                             \
+        return FVK_OK;                                                                                                  \
+    }
+        FVK_ASM_CASE(FVK_TERM_DIV, 0) FVK_ASM_CASE(FVK_TERM_LAPLACIAN, 0)
+        FVK_ASM_CASE(FVK_TERM_DIV, FVK_TERM_LAPLACIAN) FVK_ASM_CASE(FVK_TERM_LAPLACIAN, FVK_TERM_DIV)
+        FVK_ASM_CASE(FVK_TERM_DIV, FVK_TERM_DIV) FVK_ASM_CASE(FVK_TERM_LAPLACIAN, FVK_TERM_LAPLACIAN)
+#undef FVK_ASM_CASE
+    }
     k_assemble<VT><<<grid, 256, 0, fvk_cu(s)>>>(T, am, b, values, rhs, bcMatrix, bcRhs, accumulate ? 1 : 0);
     FVK_LAUNCH_CHECK();
     return FVK_OK;

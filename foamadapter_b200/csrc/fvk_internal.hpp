@@ -123,6 +123,9 @@ struct fvk_mesh
     // SparsityPattern
     int32_t *rowOffs = nullptr, *colIdxs = nullptr;
     uint8_t *ownerOffset = nullptr, *neighbourOffset = nullptr, *diagOffset = nullptr;
+    // every row is [lower | diag | upper] in the order of the cell's stencil entries (true for OpenFOAM face order
+    // without a faceOrder key): an internal entry's slot is its stencil position (+1 behind the diagonal)
+    bool rowsInStencilOrder = false;
     // faces sorted by owner (OpenFOAM upper-triangular order)? then the faces owned by cell c are
     // [ownStart[c], ownStart[c+1])
     bool ownerSorted = false;

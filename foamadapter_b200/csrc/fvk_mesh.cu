@@ -41,6 +41,28 @@ extern "C" int fvk_set_variant(int v)
 }
 int fvk_variant() { return g_variant; }
 
+// brick kernel configuration override {cells per thread, threads per block, resident blocks aimed at}; {0,0,0}: defaults
+static int g_brickCfg[3] = {0, 0, 0};
+static bool g_brickCfgEnv = false;
+extern "C" int fvk_set_brick_config(int cellsPerThread, int threads, int minBlocks)
+{
+    g_brickCfg[0] = cellsPerThread; g_brickCfg[1] = threads; g_brickCfg[2] = minBlocks;
+    g_brickCfgEnv = true; // an explicit call wins over the environment
+    return FVK_OK;
+}
+bool fvk_brick_config(int cfg[3])
+{
+    if (!g_brickCfgEnv)
+    {
+        g_brickCfgEnv = true;
+        if (const char* e = std::getenv("FVK_BRICK_CFG"))
+            if (std::sscanf(e, "%d,%d,%d", &g_brickCfg[0], &g_brickCfg[1], &g_brickCfg[2]) != 3)
+                g_brickCfg[0] = g_brickCfg[1] = g_brickCfg[2] = 0;
+    }
+    cfg[0] = g_brickCfg[0]; cfg[1] = g_brickCfg[1]; cfg[2] = g_brickCfg[2];
+    return cfg[0] > 0;
+}
+
 int fvk_sm_count()
 {
     static int sms[64] = {0};
@@ -273,9 +295,9 @@ extern "C" int fvk_mesh_create(const fvk_mesh_desc* d, fvk_mesh** out)
     // ---- cell->face stencil + gather plan: visiting faces in ascending id appends ascending ids
     const int32_t* own = d->faceOwner;
     const int32_t* nei = d->faceNeighbour;
+    FvkStencilHost sth;
+    fvk_build_stencil(d, sth);
     {
-        FvkStencilHost sth;
-        fvk_build_stencil(d, sth);
         std::vector<int32_t>&seg = sth.seg, &val = sth.val, &ent = sth.ent, &plan = sth.plan;
         const size_t nEnt = ent.size();
         // ---- brick plan of k_gather_brick (default explicit-operator kernel when available)
@@ -451,6 +473,23 @@ extern "C" int fvk_mesh_create(const fvk_mesh_desc* d, fvk_mesh** out)
             const int32_t k = cnt[r]++;
             ownOff[f] = uint8_t(k);
             col[size_t(rowOffs[r]) + k] = nei[f];
+        }
+        {
+            // rows in stencil order? (k_assemble_fast derives slots from stencil positions)
+            int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+            for (int32_t c = 0; c < nC; ++c)
+            {
+                int32_t k = 0;
+                for (int32_t e = sth.seg[c]; e < sth.seg[size_t(c) + 1]; ++e, ++k)
+                {
+                    const int32_t f = sth.ent[e] >> 1;
+                    if (f >= nI) break;
+                    const bool side = sth.ent[e] & 1;
+                    if (side ? (neiOff[f] != k || k >= diagOff[c]) : (ownOff[f] != k + 1 || k < diagOff[c])) bad |= 1;
+                }
+            }
+            m->rowsInStencilOrder = !bad;
         }
         UP(rowOffs, rowOffs.data(), rowOffs.size());
         UP(colIdxs, col.data(), col.size());

@@ -81,12 +81,12 @@ class MeshDesc:
         c.nPoints = int(a.get("nPoints", 0))
         for k in _F64:
             if a.get(k) is not None:
-                arr = np.ascontiguousarray(a[k], dtype=np.float64)
+                arr = np.array(a[k], dtype=np.float64, order="C", copy=True)  # own the storage: views of another desc dangle
                 self._keep[k] = arr
                 setattr(c, k, arr.ctypes.data_as(_capi.c_double_p))
         for k in _I32:
             if a.get(k) is not None:
-                arr = np.ascontiguousarray(a[k], dtype=np.int32)
+                arr = np.array(a[k], dtype=np.int32, order="C", copy=True)
                 self._keep[k] = arr
                 setattr(c, k, arr.ctypes.data_as(_capi.c_int32_p))
         self._c = c

@@ -450,6 +450,10 @@ int fvk_comm_set_halo_from_decomp(fvk_comm* comm, const fvk_decomp* d);
  * kernel when the mesh has a brick plan, else the per-cell gather), 5 = per-cell gather, 1-4 = packed-plan
  * gathers, 6 = TMA tile kernel, 7 = brick kernel. Used by the roofline harness and the parity tests only. */
 int fvk_set_variant(int variant);
+/* tuning switch of the brick kernel (roofline sweeps only): cells per thread, threads per block, resident blocks per SM
+ * the register allocation aims at; only combinations instantiated in fvk_explicit.cu are honoured (others fall back to
+ * the per-cell gather). (0,0,0) restores the defaults. Environment FVK_BRICK_CFG="K,TB,MINB" does the same. */
+int fvk_set_brick_config(int cellsPerThread, int threads, int minBlocks);
 
 /* Diagnostics, HOST only (no device needed): build the cell->face stencil and the brick plan of the explicit
  * gather kernel for a mesh description and replay the plan exactly as the kernel reads it. info_h[8] =

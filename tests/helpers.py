@@ -89,7 +89,7 @@ def renumbered_block(nx, ny, nz, seed, box=(1.0, 1.0, 1.0)):
              faceAreas=Sf[fsel], faceCentres=g.array("faceCentres").reshape(-1, 3)[fsel],
              magFaceAreas=g.array("magFaceAreas")[fsel],
              faceOwner=np.concatenate([lo[order], fc]).astype(np.int32), faceNeighbour=hi[order].astype(np.int32),
-             faceCells=fc.astype(np.int32), patchOffsets=g.array("patchOffsets"))
+             faceCells=fc.astype(np.int32), patchOffsets=g.array("patchOffsets").copy())
     for k in ("bCf", "bCn", "bSf", "bMagSf", "bNf", "bDelta", "bWeights", "bDeltaCoeffs"):
-        a[k] = g.array(k)
+        a[k] = g.array(k).copy()  # g owns the storage behind array(); it dies with this frame
     return MeshDesc.from_arrays(a, g.patch_names)
