@@ -80,10 +80,11 @@ namespace
 {
 constexpr int32_t kMaxTileCells = 512; // k_gather_brick: up to 2 cells per thread x 256 threads, or 512 threads
 constexpr uint16_t kPad = 0xffffu;     // pads a cell's code list to a multiple of 4 (one aligned 8-byte load)
-// cells per tile: FVK_BRICK_CELLS (64..512) overrides; default 256 = one cell per thread (kernel occupancy, see k_gather_brick)
+// cells per tile = threads per block (one cell per thread): FVK_BRICK_CELLS (64..512) overrides. Default 128 cells as a
+// 16x4x2 brick: best of the r2 sweeps on B200 (profiles/r2_brick_sweep.md) -- small blocks retire and refill fastest.
 int32_t tile_cells()
 {
-    int32_t v = 256;
+    int32_t v = 128;
     if (const char* e = std::getenv("FVK_BRICK_CELLS")) v = std::atoi(e);
     return std::max(64, std::min(kMaxTileCells, v));
 }
@@ -138,12 +139,13 @@ void make_tiles(int32_t nOwned, const int32_t dims[3], bool structured, int32_t 
     tiles.clear();
     if (!structured)
     {
+        kTileCells = kTileCells <= 128 ? 128 : (kTileCells <= 256 ? 256 : 512); // = FvkBrickGeom::cap
         brick[0] = kTileCells; brick[1] = brick[2] = 1;
         for (int32_t c = 0; c < nOwned; c += kTileCells)
             tiles.push_back(TileShape {c, std::min(kTileCells, nOwned - c), 1, 1, 0, 0});
         return;
     }
-    int32_t L = 32, BY = 4, BZ = kTileCells >= 512 ? 4 : 2;
+    int32_t L = kTileCells >= 256 ? 32 : 16, BY = 4, BZ = kTileCells >= 512 ? 4 : 2;
     bool fixed = false; // FVK_BRICK="lx,by,bz": use exactly this shape (clipped to the mesh and to 512 cells)
     if (const char* e = std::getenv("FVK_BRICK"))
     {
@@ -349,6 +351,48 @@ bool fvk_build_brick_plan(const fvk_mesh_desc* d, const FvkStencilHost& st, FvkB
         r.faceStart = 0;
         r.bases = uint32_t(h.nOwnSlots) | (uint32_t(list) << 16);
     }
+    // ---- direct-indexed copies: the kernel's first load level needs no header
+    FvkBrickGeom& g = out.geom;
+    g.structured = structured ? 1 : 0;
+    g.nOwned = nOwned;
+    g.cap = out.maxCells <= 128 ? 128 : (out.maxCells <= 256 ? 256 : 512);
+    for (int k = 0; k < 3; ++k) { g.dims[k] = out.dims[k]; g.brick[k] = out.brick[k]; }
+    if (structured)
+    {
+        g.tdim[0] = (g.dims[0] + g.brick[0] - 1) / g.brick[0];
+        g.tdim[1] = (g.dims[1] + g.brick[1] - 1) / g.brick[1];
+        g.shiftL = log2_exact(g.brick[0]); g.shiftBy = log2_exact(g.brick[1]);
+    }
+    else
+        g.brick[0] = g.cap; // tiles of `cap` consecutive cells (make_tiles used the same size)
+    out.recF.assign(size_t(nT) * (g.cap + 1), FvkBrickRec {0, 0});
+    out.codes4.assign(size_t(nT) * g.cap, make_uint2(0xffffffffu, 0xffffffffu));
+    out.tileInfo.resize(nT);
+    int geomBad = 0;
+#pragma omp parallel for schedule(static) reduction(| : geomBad)
+    for (int32_t t = 0; t < nT; ++t)
+    {
+        const FvkBrickHdr& h = out.hdr[t];
+        bool ghost = false;
+        for (int32_t lc = 0; lc <= h.nc; ++lc) out.recF[size_t(t) * (g.cap + 1) + lc] = out.rec[size_t(h.recBase) + lc];
+        for_tile_cells(tiles[t], [&](int32_t c, int32_t lc) {
+            int32_t nc = 0;
+            if (fvk_brick_cell(g, t, lc, nc) != c || nc != h.nc) geomBad |= 1;
+            const FvkBrickRec r0 = out.rec[size_t(h.recBase) + lc], r1 = out.rec[size_t(h.recBase) + lc + 1];
+            const int32_t listBase = int32_t(r0.bases >> 16), nList = int32_t(r1.bases >> 16) - listBase;
+            uint16_t cd[4] = {kPad, kPad, kPad, kPad};
+            for (int32_t j = 0; j < 4 && j < nList; ++j) cd[j] = out.codes[size_t(h.codeBase) + listBase + j];
+            out.codes4[size_t(t) * g.cap + lc] = make_uint2(uint32_t(cd[0]) | (uint32_t(cd[1]) << 16), uint32_t(cd[2]) | (uint32_t(cd[3]) << 16));
+            const int32_t nOwn = int32_t(r1.bases & 0xffffu) - int32_t(r0.bases & 0xffffu);
+            for (int32_t k = 0; k < nOwn; ++k)
+                if (nei[r0.faceStart + k] >= nOwned) ghost = true;
+        });
+        for (int32_t i = 0; i < h.nx; ++i) // a lower face whose owner is a ghost cell (the ghost side keeps the global orientation)
+            if (out.xOwner[size_t(h.xBase) + i] >= nOwned) ghost = true;
+        out.tileInfo[t] = make_int4(h.xBase, h.nx | (h.nb << 16), h.bBase, h.nOwnSlots | (ghost ? (1 << 30) : 0));
+        if (h.nx >= 65536 || h.nb >= 32768) geomBad |= 2;
+    }
+    if (geomBad) { *reason = "tile geometry does not reproduce the tiling"; return false; }
     return true;
 }
 

@@ -23,6 +23,11 @@ struct FvkBrickPlanHost
     std::vector<uint16_t> codes;
     std::vector<int32_t> xFace, xOwner, xNei, bFace, bCell;
     int32_t maxSlots = 0, maxCells = 0;
+    // direct-indexed copies + tiling geometry (see FvkBrickPlan)
+    FvkBrickGeom geom;
+    std::vector<FvkBrickRec> recF;
+    std::vector<uint2> codes4;
+    std::vector<int4> tileInfo;
     int32_t dims[3] = {0, 0, 0};  // detected block-structured numbering (0,0,0: none -> runs of consecutive cells)
     int32_t brick[3] = {0, 0, 0}; // brick shape used
 };

@@ -63,6 +63,7 @@ struct DivOp // gaussGreenDiv.cpp:46-67 with linear.cpp:30-45 / upwind.cpp:32-55
     // staged-stream interface of the tile kernel: stream 0 = faceFlux, stream 1 = weights (linear only)
     using CV = VT;
     static constexpr int W0 = 1, W1 = (SCHEME == FVK_LINEAR) ? 1 : 0;
+    static constexpr bool NEEDS_BLEND = true; // w*own + (1-w)*nei: more live registers than a difference
     __device__ __forceinline__ bool ownsStreams() const { return false; } // stream 0 is the caller's faceFlux
     __host__ __device__ __forceinline__ const double* s0() const { return faceFlux; }
     __host__ __device__ __forceinline__ const double* s1() const { return w; }
@@ -133,6 +134,7 @@ struct GradOp // gaussGreenGrad.cpp:46-64 with linear.cpp:30-45
     const double* __restrict__ phiB;
     using CV = S1;
     static constexpr int W0 = 3, W1 = 1; // stream 0 = Sf (Vec3), stream 1 = weights
+    static constexpr bool NEEDS_BLEND = true;
     __device__ __forceinline__ bool ownsStreams() const { return true; }
     __host__ __device__ __forceinline__ const double* s0() const { return Sf; }
     __host__ __device__ __forceinline__ const double* s1() const { return w; }
@@ -179,6 +181,7 @@ struct LaplacianOp // gaussGreenLaplacian.cpp:34-52 with uncorrected.cpp:34-51
     const double* __restrict__ phiB;
     using CV = VT;
     static constexpr int W0 = 1, W1 = 1; // stream 0 = magSf, stream 1 = nonOrthDeltaCoeffs
+    static constexpr bool NEEDS_BLEND = false;
     __device__ __forceinline__ bool ownsStreams() const { return true; }
     __host__ __device__ __forceinline__ const double* s0() const { return magSf; }
     __host__ __device__ __forceinline__ const double* s1() const { return dc; }
@@ -216,6 +219,7 @@ struct SurfIntOp // surfaceIntegrate.cpp:26-41
     const double* __restrict__ flux_;
     using CV = void; // no cell field
     static constexpr int W0 = VT::NC, W1 = 0; // stream 0 = the face flux itself
+    static constexpr bool NEEDS_BLEND = false;
     __device__ __forceinline__ bool ownsStreams() const { return false; }
     __host__ __device__ __forceinline__ const double* s0() const { return flux_; }
     __host__ __device__ __forceinline__ const double* s1() const { return nullptr; }
@@ -624,18 +628,14 @@ int launch_tile(const fvk_mesh* m, Op op, Scaling sc, double* out, int mode, cud
 // aligned load): DRAM traffic ~1.09x the algorithmic bytes (ncu, profiles/), the owner[] array is never read.
 // The load chain hdr -> record -> face operands -> neighbour phi is 4 deep, so the kernel lives on resident blocks:
 // K = 1 keeps it under 48 registers (5-6 blocks of 256 threads per SM).
-// 16-byte load of one quarter of the tile header that the compiler may not keep alive across phases (volatile):
-// the later phases re-read the header from L1 instead of holding eight more registers through phase A1.
-__device__ __forceinline__ int4 ld_hdr_q(const FvkBrickHdr* h, int q)
-{
-    int4 v;
-    asm volatile("ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(reinterpret_cast<const int4*>(h) + q));
-    return v;
-}
-
-template <class Op, int TB, int MINB>
+// Load levels (each waits for the previous one): (1) record, slot codes, V, phi of the own cell, the tile's cross /
+// boundary list bases -- all addressed arithmetically from blockIdx/threadIdx (FvkBrickGeom), no header; (2) the
+// owned faces' neighbour labels and face operands, the cross face's labels; (3) phi of the neighbours, the cross
+// face's operands. PHASE: 0 = all tiles, 1 = tiles that read no ghost cell, 2 = tiles that do (halo overlap).
+template <class Op, int TB, int MINB, bool XDEFER>
 __global__ void __launch_bounds__(TB, MINB)
-k_gather_brick(Op op, Scaling sc, FvkBrickPlan bp, int nI, const int* __restrict__ neighbour, double* __restrict__ out, int mode)
+k_gather_brick(Op op, Scaling sc, FvkBrickPlan bp, int nI, const int* __restrict__ neighbour, double* __restrict__ out, int mode,
+               int phase)
 {
     using VT = typename Op::V;
     using T = typename VT::T;
@@ -645,98 +645,105 @@ k_gather_brick(Op op, Scaling sc, FvkBrickPlan bp, int nI, const int* __restrict
     constexpr int W0 = Op::W0, W1 = Op::W1 ? Op::W1 : 1;
     extern __shared__ __align__(16) unsigned char smem[];
     T* sflux = reinterpret_cast<T*>(smem);
-    const FvkBrickHdr* hdr = bp.hdr + blockIdx.x;
     const double* __restrict__ S0 = op.s0();
     const double* __restrict__ S1 = op.s1();
     const double* __restrict__ cellsG = op.cells();
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, t = blockIdx.x;
 
-    // ---- phase A1: record -> the faces this thread's cell owns
-    int cell, fs, slotBase, nOwn, listInfo; // listInfo = listBase | nList << 16
-    bool valid;
-    uint2 cw; // 4 uint16 slot codes (lists start on 8-byte boundaries; 0xffff pads)
+    // ---- level 1
+    const int4 ti = bp.tileInfo[t]; // xBase, nx | nb << 16, bBase, nOwnSlots | touchesGhost << 30
+    if (phase && ((ti.w >> 30) & 1) != phase - 1) return;
+    int nc;
+    int cell = fvk_brick_cell(bp.geom, t, tid, nc);
+    const bool valid = tid < nc;
+    if (!valid) cell = fvk_brick_cell(bp.geom, t, 0, nc);
+    uint2 r0 = make_uint2(0u, 0u), r1 = make_uint2(0u, 0u), cw = make_uint2(0xffffffffu, 0xffffffffu);
+    if (valid)
     {
-        const int4 h0 = ld_hdr_q(hdr, 0), h1 = ld_hdr_q(hdr, 1), h2 = ld_hdr_q(hdr, 2), h3 = ld_hdr_q(hdr, 3);
-        const int c0 = h0.x, runLen = h0.y, by = h0.z, nRuns = h0.w, sy = h1.x, sz = h1.y, shiftL = h1.z, shiftBy = h1.w;
-        valid = tid < h3.w;
-        int r = 0;
-        if (nRuns > 1) r = (shiftL >= 0) ? (tid >> shiftL) : (tid / runLen);
-        const int off = tid - r * runLen;
-        const int b = (shiftBy >= 0) ? (r >> shiftBy) : (r / by);
-        const int a = r - b * by;
-        cell = valid ? c0 + a * sy + b * sz + off : c0;
-        uint2 r0 = make_uint2(0u, 0u), r1 = make_uint2(0u, 0u);
-        if (valid)
-        {
-            const uint2* rp = reinterpret_cast<const uint2*>(bp.rec) + h2.x + tid;
-            r0 = rp[0]; r1 = rp[1];
-        }
-        fs = int(r0.x);
-        slotBase = int(r0.y & 0xffffu);
-        nOwn = int(r1.y & 0xffffu) - slotBase;
-        const int listBase = int(r0.y >> 16), nList = int(r1.y >> 16) - listBase;
-        listInfo = listBase | (nList << 16);
-        cw = (valid && nList > 0) ? *reinterpret_cast<const uint2*>(bp.codes + h2.y + listBase) : make_uint2(0xffffffffu, 0xffffffffu);
+        const uint2* rp = reinterpret_cast<const uint2*>(bp.recF) + size_t(t) * (TB + 1) + tid;
+        r0 = rp[0]; r1 = rp[1];
+        cw = bp.codes4[size_t(t) * TB + tid];
     }
     const double vol = sc.V[cell];
+    const CT pc = CL::ld(cellsG, cell);
+    const int xBase = ti.x, nx = ti.y & 0xffff, nb = ti.y >> 16, bBase = ti.z, nOwnSlots = ti.w & 0xffff;
+    const bool hx = tid < nx;
+    int xf = 0, xo = 0, xn = 0;
+    if (hx) { xf = bp.xFace[xBase + tid]; xo = bp.xOwner[xBase + tid]; xn = bp.xNei[xBase + tid]; }
+    // ---- level 2
+    const int fs = int(r0.x), slotBase = int(r0.y & 0xffffu), nOwn = int(r1.y & 0xffffu) - slotBase;
+    int nbr[MO];
+#pragma unroll
+    for (int k = 0; k < MO; ++k) nbr[k] = (k < nOwn) ? neighbour[fs + k] : cell;
+    double fa[MO][W0], fb[MO][W1];
+#pragma unroll
+    for (int k = 0; k < MO; ++k)
     {
-        int nbr[MO];
+        const bool p = k < nOwn;
+        const int64_t f = fs + k;
 #pragma unroll
-        for (int k = 0; k < MO; ++k) nbr[k] = (k < nOwn) ? neighbour[fs + k] : cell;
-        double fa[MO][W0], fb[MO][W1];
-#pragma unroll
-        for (int k = 0; k < MO; ++k)
-        {
-            const bool p = k < nOwn;
-            const int64_t f = fs + k;
-#pragma unroll
-            for (int i = 0; i < W0; ++i) fa[k][i] = p ? S0[int64_t(W0) * f + i] : 0.0;
-            fb[k][0] = (Op::W1 && p) ? S1[f] : 0.0;
-        }
-        const CT pc = CL::ld(cellsG, cell);
-        CT pn[MO];
-#pragma unroll
-        for (int k = 0; k < MO; ++k) pn[k] = CL::ld(cellsG, nbr[k]);
-#pragma unroll
-        for (int k = 0; k < MO; ++k)
-            if (k < nOwn) sflux[slotBase + k] = op.fluxv(fa[k], fb[k], pc, pn[k]);
-        for (int k = MO; k < nOwn; ++k) // polyhedral cells owning more than MO faces
-        {
-            const int64_t f = fs + k;
-            double a[W0], b[W1];
-#pragma unroll
-            for (int i = 0; i < W0; ++i) a[i] = S0[int64_t(W0) * f + i];
-            if (Op::W1) b[0] = S1[f];
-            sflux[slotBase + k] = op.fluxv(a, b, pc, CL::ld(cellsG, neighbour[f]));
-        }
+        for (int i = 0; i < W0; ++i) fa[k][i] = p ? S0[int64_t(W0) * f + i] : 0.0;
+        fb[k][0] = (Op::W1 && p) ? S1[f] : 0.0;
     }
-    // ---- phase A2 / A3: cross faces and boundary faces, thread per face
+    // ---- level 3 (XDEFER: the cross face's operands are fetched after the owned faces are done -- one more exposed
+    // round trip for the first nx threads, eight fewer live registers at the peak)
+    double xa[W0], xb[W1];
+    CT xpo = pc, xpn = pc;
+    if (!XDEFER && hx)
     {
-        const int4 h2 = ld_hdr_q(hdr, 2), h3 = ld_hdr_q(hdr, 3);
-        const int xBase = h2.z, nx = h2.w, bBase = h3.x, nb = h3.y, nOwnSlots = h3.z;
-        for (int i = tid; i < nx; i += TB)
-        {
-            const int f = bp.xFace[xBase + i];
-            const CT po = CL::ld(cellsG, bp.xOwner[xBase + i]);
-            const CT pnn = CL::ld(cellsG, bp.xNei[xBase + i]);
-            double a[W0], b[W1];
 #pragma unroll
-            for (int q = 0; q < W0; ++q) a[q] = S0[int64_t(W0) * f + q];
-            if (Op::W1) b[0] = S1[f];
-            sflux[nOwnSlots + i] = op.fluxv(a, b, po, pnn);
-        }
-        for (int i = tid; i < nb; i += TB)
-        {
-            const int f = bp.bFace[bBase + i];
-            sflux[nOwnSlots + nx + i] = op.boundary(f, f - nI, bp.bCell[bBase + i]);
-        }
+        for (int i = 0; i < W0; ++i) xa[i] = S0[int64_t(W0) * xf + i];
+        if (Op::W1) xb[0] = S1[xf];
+        xpo = CL::ld(cellsG, xo);
+        xpn = CL::ld(cellsG, xn);
+    }
+    CT pn[MO];
+#pragma unroll
+    for (int k = 0; k < MO; ++k) pn[k] = CL::ld(cellsG, nbr[k]);
+#pragma unroll
+    for (int k = 0; k < MO; ++k)
+        if (k < nOwn) sflux[slotBase + k] = op.fluxv(fa[k], fb[k], pc, pn[k]);
+    for (int k = MO; k < nOwn; ++k) // polyhedral cells owning more than MO faces
+    {
+        const int64_t f = fs + k;
+        double a[W0], b[W1];
+#pragma unroll
+        for (int i = 0; i < W0; ++i) a[i] = S0[int64_t(W0) * f + i];
+        if (Op::W1) b[0] = S1[f];
+        sflux[slotBase + k] = op.fluxv(a, b, pc, CL::ld(cellsG, neighbour[f]));
+    }
+    // ---- cross faces beyond the first TB, boundary faces: thread per face
+    if (XDEFER && hx)
+    {
+#pragma unroll
+        for (int i = 0; i < W0; ++i) xa[i] = S0[int64_t(W0) * xf + i];
+        if (Op::W1) xb[0] = S1[xf];
+        xpo = CL::ld(cellsG, xo);
+        xpn = CL::ld(cellsG, xn);
+    }
+    if (hx) sflux[nOwnSlots + tid] = op.fluxv(xa, xb, xpo, xpn);
+    for (int i = tid + TB; i < nx; i += TB)
+    {
+        const int f = bp.xFace[xBase + i];
+        const CT po = CL::ld(cellsG, bp.xOwner[xBase + i]);
+        const CT pnn = CL::ld(cellsG, bp.xNei[xBase + i]);
+        double a[W0], b[W1];
+#pragma unroll
+        for (int q = 0; q < W0; ++q) a[q] = S0[int64_t(W0) * f + q];
+        if (Op::W1) b[0] = S1[f];
+        sflux[nOwnSlots + i] = op.fluxv(a, b, po, pnn);
+    }
+    for (int i = tid; i < nb; i += TB)
+    {
+        const int f = bp.bFace[bBase + i];
+        sflux[nOwnSlots + nx + i] = op.boundary(f, f - nI, bp.bCell[bBase + i]);
     }
     __syncthreads();
-    // ---- phase B: per-cell accumulation in the reference's order
+    // ---- per-cell accumulation in the reference's order
     if (!valid) return;
     T acc = (mode == FVK_ACC_SCALE) ? VT::ld(out, cell) : VT::zero();
     const unsigned cd[4] = {cw.x & 0xffffu, cw.x >> 16, cw.y & 0xffffu, cw.y >> 16};
-    const int nList = listInfo >> 16;
+    const int listBase = int(r0.y >> 16), nList = int(r1.y >> 16) - listBase;
     int nLow = 0;
     bool more = true;
 #pragma unroll
@@ -746,9 +753,9 @@ k_gather_brick(Op op, Scaling sc, FvkBrickPlan bp, int nI, const int* __restrict
         if (low) { acc = VT::sub(acc, sflux[cd[j] >> 1]); ++nLow; }
         more = low;
     }
-    if (more && nList > 4) // more than 4 lower faces: the rest of the list comes from global memory
+    if (more && nList > 4) // more than 4 lower faces: the rest of the list comes from the tile's code array
     {
-        const unsigned short* gcodes = bp.codes + ld_hdr_q(hdr, 2).y + (listInfo & 0xffff);
+        const unsigned short* gcodes = bp.codes + bp.hdr[t].codeBase + listBase;
         for (; nLow < nList; ++nLow)
         {
             const unsigned code = gcodes[nLow];
@@ -762,7 +769,7 @@ k_gather_brick(Op op, Scaling sc, FvkBrickPlan bp, int nI, const int* __restrict
         if (j >= nLow && cd[j] != 0xffffu) acc = VT::add(acc, sflux[cd[j] >> 1]);
     if (nList > 4)
     {
-        const unsigned short* gcodes = bp.codes + ld_hdr_q(hdr, 2).y + (listInfo & 0xffff);
+        const unsigned short* gcodes = bp.codes + bp.hdr[t].codeBase + listBase;
         for (int j = (nLow > 4 ? nLow : 4); j < nList; ++j)
         {
             const unsigned code = gcodes[j];
@@ -776,22 +783,22 @@ k_gather_brick(Op op, Scaling sc, FvkBrickPlan bp, int nI, const int* __restrict
     finish<VT>(out, cell, acc, s, mode);
 }
 
-template <class Op, int TB, int MINB>
+template <class Op, int TB, int MINB, bool XDEFER>
 int launch_brick_n(const fvk_mesh* m, Op op, Scaling sc, double* out, int mode, cudaStream_t st)
 {
     using T = typename Op::V::T;
     static bool optedIn[64] = {false};
     const size_t bytes = size_t(m->bp.maxSlots) * sizeof(T);
-    if (bytes > 200 * 1024 || m->bp.maxCells > TB) return -1;
+    if (bytes > 200 * 1024 || m->bp.geom.cap != TB) return -1;
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) return -1;
     if (!optedIn[dev])
     {
-        FVK_CUDA(cudaFuncSetAttribute(k_gather_brick<Op, TB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        FVK_CUDA(cudaFuncSetAttribute(k_gather_brick<Op, TB, MINB, XDEFER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         optedIn[dev] = true;
     }
-    k_gather_brick<Op, TB, MINB><<<m->bp.nTiles, TB, bytes, st>>>(op, sc, m->bp, m->nInternalFaces, m->neighbour, out, mode);
+    k_gather_brick<Op, TB, MINB, XDEFER><<<m->bp.nTiles, TB, bytes, st>>>(op, sc, m->bp, m->nInternalFaces, m->neighbour, out, mode, m->tilePhase);
     FVK_LAUNCH_CHECK();
     return FVK_OK;
 }
@@ -800,14 +807,19 @@ int launch_brick_n(const fvk_mesh* m, Op op, Scaling sc, double* out, int mode, 
 template <class Op>
 int launch_brick(const fvk_mesh* m, Op op, Scaling sc, double* out, int mode, cudaStream_t st)
 {
-    constexpr bool wide = sizeof(typename Op::V::T) > 8 || Op::W0 > 1;
-    int TB = m->bp.maxCells > 256 ? 512 : (m->bp.maxCells > 128 ? 256 : 128);
-    int MINB = (wide ? 4 : 6) * 256 / TB;
+    // resident blocks aimed at = the highest occupancy ptxas reaches WITHOUT spilling (spills cost more than the extra
+    // warps bring, r2 sweeps): 40 registers only fit the two-operand scalar laplacian and surfaceIntegrate
+    constexpr bool light = sizeof(typename Op::V::T) == 8 && Op::W0 == 1 && !Op::NEEDS_BLEND;
+    const int TB = m->bp.geom.cap; // threads per block = the stride of the plan's per-cell arrays
+    int MINB = (light ? 6 : 4) * 256 / TB;
     int cfg[3];
-    if (fvk_brick_config(cfg)) { TB = cfg[1]; MINB = cfg[2]; }
-#define FVK_BRICK_CASE(tb, mb) if (TB == tb && MINB == mb) return launch_brick_n<Op, tb, mb>(m, op, sc, out, mode, st)
-    FVK_BRICK_CASE(256, 3); FVK_BRICK_CASE(256, 4); FVK_BRICK_CASE(256, 5); FVK_BRICK_CASE(256, 6); FVK_BRICK_CASE(256, 8);
-    FVK_BRICK_CASE(512, 2); FVK_BRICK_CASE(512, 3); FVK_BRICK_CASE(512, 4);
+    if (fvk_brick_config(cfg) && cfg[1] == TB) MINB = cfg[2];
+    const bool xdefer = fvk_brick_config(cfg) ? cfg[0] == 2 : false; // config[0]: 1 = cross operands early, 2 = deferred
+#define FVK_BRICK_CASE(tb, mb)                                                                                          \
+    if (TB == tb && MINB == mb)                                                                                         \
+        return xdefer ? launch_brick_n<Op, tb, mb, true>(m, op, sc, out, mode, st) : launch_brick_n<Op, tb, mb, false>(m, op, sc, out, mode, st)
+    FVK_BRICK_CASE(256, 4); FVK_BRICK_CASE(256, 5); FVK_BRICK_CASE(256, 6); FVK_BRICK_CASE(256, 8);
+    FVK_BRICK_CASE(512, 2); FVK_BRICK_CASE(512, 3);
     FVK_BRICK_CASE(128, 8); FVK_BRICK_CASE(128, 12); FVK_BRICK_CASE(128, 16);
 #undef FVK_BRICK_CASE
     return -1;
@@ -831,6 +843,8 @@ int launch_gather(const fvk_mesh* m, Op op, Scaling sc, double* out, int mode, f
         const int rc = launch_brick(m, op, sc, out, mode, fvk_cu(stream));
         if (rc >= 0) return rc; // -1: slots do not fit in shared memory -> per-cell gather below
     }
+    // the other kernels have no interior / halo split: the interior phase does nothing, the halo phase everything
+    if (m->tilePhase == 1) return FVK_OK;
     // variant 6: TMA-staged tile kernel. Parity-green but (r1 measurements, profiles/r1_tile_kernel_sweep.md) not yet
     // faster than the per-cell gather, so it is opt-in until the staging pipeline is tuned.
     if (variant == 6 && m->tp.nTiles > 0 && aligned16(op.s0()) && aligned16(op.s1()) && aligned16(op.cells()))

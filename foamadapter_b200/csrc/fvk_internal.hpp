@@ -87,6 +87,51 @@ struct FvkBrickRec
     int32_t faceStart;
     uint32_t bases; // slotBase | listBase << 16
 };
+// Geometry of the tiling, enough to compute a tile's cells WITHOUT loading anything (the kernel's first load level
+// then already fetches per-cell data): structured = bricks of a block-structured numbering c = i + nx*(j + ny*k),
+// tile t = (tx, ty, tz) in x-fastest order; otherwise tile t = cells [t*cap, t*cap + cap).
+struct FvkBrickGeom
+{
+    int32_t structured = 0;
+    int32_t dims[3] = {0, 0, 0};  // nx, ny, nz of the owned block
+    int32_t brick[3] = {0, 0, 0}; // lx, by, bz
+    int32_t tdim[2] = {0, 0};     // tiles along x, y
+    int32_t shiftL = -1, shiftBy = -1; // log2(lx), log2(by) when powers of two (full tiles use shifts)
+    int32_t cap = 0;              // cells per tile the per-cell arrays are strided with (= threads per block)
+    int32_t nOwned = 0;
+};
+#ifdef __CUDACC__
+#define FVK_HD __host__ __device__ __forceinline__
+#else
+#define FVK_HD inline
+#endif
+// local cell lc of tile t -> global cell id; nc = number of cells of the tile. Same enumeration as the host plan.
+FVK_HD int32_t fvk_brick_cell(const FvkBrickGeom& g, int32_t t, int32_t lc, int32_t& nc)
+{
+    if (!g.structured)
+    {
+        const int32_t c0 = t * g.cap;
+        nc = g.nOwned - c0 < g.cap ? g.nOwned - c0 : g.cap;
+        return c0 + lc;
+    }
+    const int32_t ix = t % g.tdim[0], q = t / g.tdim[0], iy = q % g.tdim[1], iz = q / g.tdim[1];
+    const int32_t x0 = ix * g.brick[0], y0 = iy * g.brick[1], z0 = iz * g.brick[2];
+    const int32_t rl = g.dims[0] - x0 < g.brick[0] ? g.dims[0] - x0 : g.brick[0];
+    const int32_t ry = g.dims[1] - y0 < g.brick[1] ? g.dims[1] - y0 : g.brick[1];
+    const int32_t rz = g.dims[2] - z0 < g.brick[2] ? g.dims[2] - z0 : g.brick[2];
+    nc = rl * ry * rz;
+    int32_t r, off, a, b;
+    if (rl == g.brick[0] && ry == g.brick[1] && g.shiftL >= 0 && g.shiftBy >= 0)
+    {
+        r = lc >> g.shiftL; off = lc & (rl - 1); b = r >> g.shiftBy; a = r & (ry - 1);
+    }
+    else
+    {
+        r = lc / rl; off = lc - r * rl; b = r / ry; a = r - b * ry;
+    }
+    return (x0 + off) + g.dims[0] * ((y0 + a) + g.dims[1] * (z0 + b));
+}
+
 struct FvkBrickPlan
 {
     int32_t nTiles = 0, maxSlots = 0, maxCells = 0;
@@ -95,6 +140,12 @@ struct FvkBrickPlan
     uint16_t* codes = nullptr;
     int32_t *xFace = nullptr, *xOwner = nullptr, *xNei = nullptr;
     int32_t *bFace = nullptr, *bCell = nullptr;
+    // direct-indexed copies (no header needed): recF[t*(cap+1) + lc], codes4[t*cap + lc] = first 4 codes of the cell's
+    // list, tileInfo[t] = {xBase, nx | nb << 16, bBase, nOwnSlots | touchesGhost << 30}
+    FvkBrickGeom geom;
+    FvkBrickRec* recF = nullptr;
+    uint2* codes4 = nullptr;
+    int4* tileInfo = nullptr;
 };
 
 // Device-side mesh. All arrays are device pointers in reference order.
@@ -138,4 +189,7 @@ struct fvk_mesh
     uint32_t* hasBnd = nullptr; // bitmask [ceil(nCells/32)]
     FvkTilePlan tp; // tile plan of the explicit gather kernels (nTiles == 0: faces not sorted by owner)
     FvkBrickPlan bp; // brick plan (nTiles == 0: not available for this mesh)
+    // halo overlap (fvk_mesh_set_tile_phase): 0 = operators compute every cell, 1 = only tiles that read no ghost
+    // cell, 2 = only tiles that do
+    int tilePhase = 0;
 };

@@ -138,8 +138,9 @@ __global__ void __launch_bounds__(TB)
 k_cg_update(int n, PcgState* __restrict__ st, double* __restrict__ x, const double* __restrict__ p,
             const double* __restrict__ q, double* __restrict__ r, const double* __restrict__ dinv,
             double* __restrict__ z, double* __restrict__ partial, unsigned* __restrict__ counter,
-            double* __restrict__ hist, int distributed)
+            double* __restrict__ hist, int distributed, const FvkP2PCtx* __restrict__ p2p)
 {
+    __shared__ double shv[4];
     if (st->done) return;
     const double alpha = FIRST ? 0.0 : st->alpha;
     double acc[2] = {0.0, 0.0};
@@ -158,11 +159,27 @@ k_cg_update(int n, PcgState* __restrict__ st, double* __restrict__ x, const doub
         acc[1] += ri * ri;
     }
     double tot[2];
-    if (grid_sum<2>(acc, partial, counter, tot) && threadIdx.x == 0)
+    if (grid_sum<2>(acc, partial, counter, tot)) // true in every thread of the last block
     {
-        st->sums[0] = tot[0];
-        st->sums[1] = tot[1];
-        if (!distributed) decide_after_update(st, hist);
+        if (distributed == 2)
+        { // peer-memory all-reduce of (r.z, r.r) by this block, then the scalar update: no NCCL kernel, no extra launch
+            if (threadIdx.x == 0) { shv[0] = tot[0]; shv[1] = tot[1]; }
+            __syncthreads();
+            fvk_p2p_allreduce_sum(*p2p, shv, 2);
+            __syncthreads();
+            if (threadIdx.x == 0)
+            {
+                st->sums[0] = shv[0];
+                st->sums[1] = shv[1];
+                decide_after_update(st, hist);
+            }
+        }
+        else if (threadIdx.x == 0)
+        {
+            st->sums[0] = tot[0];
+            st->sums[1] = tot[1];
+            if (!distributed) decide_after_update(st, hist);
+        }
     }
 }
 
@@ -186,7 +203,7 @@ __global__ void __launch_bounds__(TB)
 k_spmv(int nRows, const int* __restrict__ rowOffs, const int* __restrict__ colIdxs, const double* __restrict__ values,
        const double* __restrict__ x, const double* __restrict__ b, double* __restrict__ y, PcgState* __restrict__ st,
        const double* __restrict__ z, double* __restrict__ pNew, double* __restrict__ partial,
-       unsigned* __restrict__ counter, int distributed)
+       unsigned* __restrict__ counter, int distributed, const FvkP2PCtx* __restrict__ p2p = nullptr)
 {
     __shared__ double prod[SPMV_CAP];
     __shared__ int ro[SPMV_ROWS + 1];
@@ -248,10 +265,26 @@ k_spmv(int nRows, const int* __restrict__ rowOffs, const int* __restrict__ colId
     if (MODE >= 3)
     {
         double tot[1];
-        if (grid_sum<1>(acc, partial, counter, tot) && threadIdx.x == 0)
+        if (grid_sum<1>(acc, partial, counter, tot))
         {
-            st->sums[2] = tot[0];
-            if (!distributed) decide_after_spmv(st);
+            if (distributed == 2)
+            { // peer-memory all-reduce of p.q inside the SpMV's last block
+                __syncthreads();
+                if (threadIdx.x == 0) prod[0] = tot[0];
+                __syncthreads();
+                fvk_p2p_allreduce_sum(*p2p, prod, 1);
+                __syncthreads();
+                if (threadIdx.x == 0)
+                {
+                    st->sums[2] = prod[0];
+                    decide_after_spmv(st);
+                }
+            }
+            else if (threadIdx.x == 0)
+            {
+                st->sums[2] = tot[0];
+                if (!distributed) decide_after_spmv(st);
+            }
         }
     }
 }
@@ -310,6 +343,25 @@ int spmv_grid(int nRows)
     return tiles < 1 ? 1 : (tiles < cap ? tiles : cap);
 }
 
+// ---- bandwidth probe (diagnostics): out[i] = sum_k in_k[i] over NS concurrent read streams + one write stream ------
+// Same launch shape as the operator kernels (one 8-byte element per thread and stream, 256-thread blocks): measures
+// what HBM delivers for NS interleaved streams, the practical ceiling of kernels that read 6-8 arrays at once.
+struct ProbePtrs { const double* p[8]; };
+template <int NS>
+__global__ void __launch_bounds__(256)
+k_probe_streams(ProbePtrs in, int64_t n, double* __restrict__ out)
+{
+    const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
+    if (i >= n) return;
+    double v[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) v[k] = in.p[k][i];
+    double s = v[0];
+#pragma unroll
+    for (int k = 1; k < NS; ++k) s += v[k];
+    out[i] = s;
+}
+
 // per-device scratch of the stand-alone reductions (fvk_dot / fvk_norm2)
 struct RedScratch
 {
@@ -359,6 +411,28 @@ extern "C" int fvk_residual(int32_t nRows, const int32_t* rowOffs, const int32_t
     if (nRows == 0) return FVK_OK;
     k_spmv<1><<<spmv_grid(nRows), TB, 0, fvk_cu(s)>>>(nRows, rowOffs, colIdxs, values, x, b, res, nullptr, nullptr,
                                                       nullptr, nullptr, nullptr, 0);
+    FVK_LAUNCH_CHECK();
+    return FVK_OK;
+}
+
+extern "C" int fvk_probe_streams(int nStreams, const double* const* in_h, int64_t n, double* out, fvk_stream s)
+{
+    if (nStreams < 1 || nStreams > 8 || !in_h || !out || n < 0) return fvk_fail(FVK_EINVAL, "fvk_probe_streams: bad argument");
+    if (n == 0) return FVK_OK;
+    ProbePtrs pp;
+    for (int k = 0; k < 8; ++k) pp.p[k] = in_h[k < nStreams ? k : 0];
+    const unsigned grid = unsigned((n + 255) / 256);
+    switch (nStreams)
+    {
+        case 1: k_probe_streams<1><<<grid, 256, 0, fvk_cu(s)>>>(pp, n, out); break;
+        case 2: k_probe_streams<2><<<grid, 256, 0, fvk_cu(s)>>>(pp, n, out); break;
+        case 3: k_probe_streams<3><<<grid, 256, 0, fvk_cu(s)>>>(pp, n, out); break;
+        case 4: k_probe_streams<4><<<grid, 256, 0, fvk_cu(s)>>>(pp, n, out); break;
+        case 5: k_probe_streams<5><<<grid, 256, 0, fvk_cu(s)>>>(pp, n, out); break;
+        case 6: k_probe_streams<6><<<grid, 256, 0, fvk_cu(s)>>>(pp, n, out); break;
+        case 7: k_probe_streams<7><<<grid, 256, 0, fvk_cu(s)>>>(pp, n, out); break;
+        default: k_probe_streams<8><<<grid, 256, 0, fvk_cu(s)>>>(pp, n, out); break;
+    }
     FVK_LAUNCH_CHECK();
     return FVK_OK;
 }
@@ -474,6 +548,8 @@ extern "C" int fvk_solver_solve(fvk_solver* sv, const int32_t* rowOffs, const in
     cudaStream_t st = fvk_cu(s);
     const int n = sv->nRows;
     const bool dist = sv->comm != nullptr;
+    const FvkP2PCtx* p2p = fvk_comm_p2p_ctx(sv->comm);
+    const int dmode = !dist ? 0 : (p2p ? 2 : 1); // 2: all-reduces fused into the kernels over peer memory
     const bool jacobi = sv->cfg.preconditioner == FVK_PRECOND_JACOBI;
     const int gV = stream_grid(n), gS = spmv_grid(n);
     const int wantHist = (history_h && maxHistory > 0) ? (maxHistory < sv->histCap ? maxHistory : sv->histCap) : 0;
@@ -514,25 +590,31 @@ extern "C" int fvk_solver_solve(fvk_solver* sv, const int32_t* rowOffs, const in
         // K1
         if (it == 0)
         {
-            if (jacobi) k_cg_update<true, true><<<gV, TB, 0, st>>>(n, sv->state, x, pCur, sv->q, sv->r, sv->dinv, sv->z, sv->partial, sv->counter, sv->hist, dist);
-            else k_cg_update<true, false><<<gV, TB, 0, st>>>(n, sv->state, x, pCur, sv->q, sv->r, sv->dinv, sv->z, sv->partial, sv->counter, sv->hist, dist);
+            if (jacobi) k_cg_update<true, true><<<gV, TB, 0, st>>>(n, sv->state, x, pCur, sv->q, sv->r, sv->dinv, sv->z, sv->partial, sv->counter, sv->hist, dmode, p2p);
+            else k_cg_update<true, false><<<gV, TB, 0, st>>>(n, sv->state, x, pCur, sv->q, sv->r, sv->dinv, sv->z, sv->partial, sv->counter, sv->hist, dmode, p2p);
         }
         else
         {
-            if (jacobi) k_cg_update<false, true><<<gV, TB, 0, st>>>(n, sv->state, x, pCur, sv->q, sv->r, sv->dinv, sv->z, sv->partial, sv->counter, sv->hist, dist);
-            else k_cg_update<false, false><<<gV, TB, 0, st>>>(n, sv->state, x, pCur, sv->q, sv->r, sv->dinv, sv->z, sv->partial, sv->counter, sv->hist, dist);
+            if (jacobi) k_cg_update<false, true><<<gV, TB, 0, st>>>(n, sv->state, x, pCur, sv->q, sv->r, sv->dinv, sv->z, sv->partial, sv->counter, sv->hist, dmode, p2p);
+            else k_cg_update<false, false><<<gV, TB, 0, st>>>(n, sv->state, x, pCur, sv->q, sv->r, sv->dinv, sv->z, sv->partial, sv->counter, sv->hist, dmode, p2p);
         }
         FVK_LAUNCH_CHECK();
         if (dist)
         {
-            if (int rc = fvk_comm_allreduce_sum_impl(sv->comm, &sv->state->sums[0], 2, st)) return rc;
-            k_decide_after_update<<<1, 1, 0, st>>>(sv->state, sv->hist);
+            if (dmode == 1)
+            {
+                if (int rc = fvk_comm_allreduce_sum_impl(sv->comm, &sv->state->sums[0], 2, st)) return rc;
+                k_decide_after_update<<<1, 1, 0, st>>>(sv->state, sv->hist);
+            }
             k_cg_pupdate<<<gV, TB, 0, st>>>(n, sv->state, sv->z, pCur);
             if (int rc = fvk_comm_halo_exchange_impl(sv->comm, pCur, 1, st)) return rc;
-            k_spmv<3><<<gS, TB, 0, st>>>(n, rowOffs, colIdxs, values, pCur, nullptr, sv->q, sv->state, nullptr, nullptr, sv->partial, sv->counter, 1);
+            k_spmv<3><<<gS, TB, 0, st>>>(n, rowOffs, colIdxs, values, pCur, nullptr, sv->q, sv->state, nullptr, nullptr, sv->partial, sv->counter, dmode, p2p);
             FVK_LAUNCH_CHECK();
-            if (int rc = fvk_comm_allreduce_sum_impl(sv->comm, &sv->state->sums[2], 1, st)) return rc;
-            k_decide_after_spmv<<<1, 1, 0, st>>>(sv->state);
+            if (dmode == 1)
+            {
+                if (int rc = fvk_comm_allreduce_sum_impl(sv->comm, &sv->state->sums[2], 1, st)) return rc;
+                k_decide_after_spmv<<<1, 1, 0, st>>>(sv->state);
+            }
         }
         else
         {

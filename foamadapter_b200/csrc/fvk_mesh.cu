@@ -44,6 +44,12 @@ int fvk_variant() { return g_variant; }
 // brick kernel configuration override {cells per thread, threads per block, resident blocks aimed at}; {0,0,0}: defaults
 static int g_brickCfg[3] = {0, 0, 0};
 static bool g_brickCfgEnv = false;
+extern "C" int fvk_mesh_set_tile_phase(fvk_mesh* m, int phase)
+{
+    if (!m || phase < 0 || phase > 2) return fvk_fail(FVK_EINVAL, "fvk_mesh_set_tile_phase: bad argument");
+    m->tilePhase = phase;
+    return FVK_OK;
+}
 extern "C" int fvk_set_brick_config(int cellsPerThread, int threads, int minBlocks)
 {
     g_brickCfg[0] = cellsPerThread; g_brickCfg[1] = threads; g_brickCfg[2] = minBlocks;
@@ -227,7 +233,7 @@ extern "C" int fvk_mesh_destroy(fvk_mesh* m)
                     m->gatherEnt, m->gatherPlan, m->rowOffs, m->colIdxs, m->ownerOffset, m->neighbourOffset,
                     m->diagOffset, m->ownStart, m->lowSeg, m->lowFace, m->lowOwner, m->bndCell,
                     m->bndSeg, m->bndFace, m->hasBnd, m->tp.hdr, m->tp.blob, m->bp.hdr, m->bp.rec, m->bp.codes,
-                    m->bp.xFace, m->bp.xOwner, m->bp.xNei, m->bp.bFace, m->bp.bCell};
+                    m->bp.xFace, m->bp.xOwner, m->bp.xNei, m->bp.bFace, m->bp.bCell, m->bp.recF, m->bp.codes4, m->bp.tileInfo};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete m;
@@ -316,6 +322,10 @@ extern "C" int fvk_mesh_create(const fvk_mesh_desc* d, fvk_mesh** out)
                 UP(bp.xNei, bph.xNei.data(), bph.xNei.size());
                 UP(bp.bFace, bph.bFace.data(), bph.bFace.size());
                 UP(bp.bCell, bph.bCell.data(), bph.bCell.size());
+                UP(bp.recF, bph.recF.data(), bph.recF.size());
+                UP(bp.codes4, bph.codes4.data(), bph.codes4.size());
+                UP(bp.tileInfo, bph.tileInfo.data(), bph.tileInfo.size());
+                bp.geom = bph.geom;
                 bp.nTiles = int32_t(bph.hdr.size()); bp.maxSlots = bph.maxSlots; bp.maxCells = bph.maxCells;
             }
         }

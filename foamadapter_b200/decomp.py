@@ -104,8 +104,35 @@ class Comm:
     def handle(self):
         return self._h
 
-    def set_halo(self, dec: Decomposition):
+    def set_halo(self, dec: Decomposition, p2p: bool | None = None):
+        """Attach the halo plan of `dec`. p2p=True connects the peer-memory windows for it (collective over all ranks;
+        None keeps the transport chosen by the last call)."""
         check(lib().fvk_comm_set_halo_from_decomp(self._h, dec._h))
+        if p2p is not None:
+            self._want_p2p = bool(p2p)
+        if getattr(self, "_want_p2p", False) and self.nRanks > 1:
+            self.enable_p2p()
+
+    P2P_BLOB = 512
+
+    def enable_p2p(self):
+        """fvk_comm_p2p_export -> all-gather of the blobs over torch.distributed -> fvk_comm_p2p_connect. Collective.
+        Raises FvkError (and leaves NCCL as the transport) when CUDA IPC is not available between the ranks."""
+        import torch
+        import torch.distributed as dist
+        blob = (C.c_char * self.P2P_BLOB)()
+        check(lib().fvk_comm_p2p_export(self._h, blob))
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        mine = torch.frombuffer(bytearray(blob.raw), dtype=torch.uint8).clone().to(dev)
+        allb = torch.empty(self.nRanks * self.P2P_BLOB, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allb, mine)
+        raw = bytes(allb.cpu().numpy().tobytes())
+        check(lib().fvk_comm_p2p_connect(self._h, (C.c_char * len(raw)).from_buffer_copy(raw)))
+        dist.barrier()  # nobody pushes into a window before every rank has mapped and zeroed its own
+
+    @property
+    def p2p(self) -> bool:
+        return bool(lib().fvk_comm_p2p_enabled(self._h))
 
     def halo_exchange(self, field):
         import torch

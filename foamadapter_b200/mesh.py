@@ -192,6 +192,10 @@ class UnstructuredMesh:
     def handle(self):
         return self._h
 
+    def set_tile_phase(self, phase: int):
+        """fvk_mesh_set_tile_phase: 0 all cells, 1 only tiles that read no ghost cell, 2 only tiles that do."""
+        check(lib().fvk_mesh_set_tile_phase(self._h, C.c_int(phase)))
+
     def size(self, field) -> int:
         v = C.c_int64()
         check(lib().fvk_mesh_size(self._h, C.c_int(field), C.byref(v)))

@@ -419,6 +419,17 @@ int fvk_comm_set_halo(fvk_comm* comm, int32_t nOwned, int32_t nNeighbours, const
 int fvk_comm_halo_exchange(fvk_comm* comm, double* field, int ncomp, fvk_stream stream);
 int fvk_comm_allreduce_sum(fvk_comm* comm, double* data_d, int count, fvk_stream stream);
 int fvk_comm_allreduce_max(fvk_comm* comm, double* data_d, int count, fvk_stream stream);
+/* Peer-memory transport (NVLink/NVSwitch P2P through CUDA IPC), optional, after fvk_comm_set_halo: every rank exports
+ * a window blob (FVK_P2P_BLOB_BYTES), the host all-gathers the blobs (torch.distributed / MPI_Allgather), every rank
+ * connects. From then on fvk_comm_halo_exchange stores the send cells straight into the neighbours' windows and raises
+ * a flag (no NCCL kernel), fvk_comm_allreduce_sum (count <= 4) is a mailbox exchange, and the distributed CG fuses its
+ * all-reduces into the kernels that produce the partial sums. Sums are formed in rank order on every rank
+ * (bit-identical everywhere, run to run). fvk_comm_p2p_connect fails (NCCL stays the transport) when CUDA IPC is
+ * unavailable. All ranks must issue the same sequence of exchanges / reductions. */
+#define FVK_P2P_BLOB_BYTES 512
+int fvk_comm_p2p_export(fvk_comm* comm, void* blob_h);
+int fvk_comm_p2p_connect(fvk_comm* comm, const void* allBlobs_h /* nRanks x FVK_P2P_BLOB_BYTES, rank order */);
+int fvk_comm_p2p_enabled(const fvk_comm* comm);
 
 /* ------------------------------------------------------------------------------------------------
  * Domain decomposition (HOST). The reference carries OpenFOAM decomposeParDict files
@@ -450,7 +461,19 @@ int fvk_comm_set_halo_from_decomp(fvk_comm* comm, const fvk_decomp* d);
  * kernel when the mesh has a brick plan, else the per-cell gather), 5 = per-cell gather, 1-4 = packed-plan
  * gathers, 6 = TMA tile kernel, 7 = brick kernel. Used by the roofline harness and the parity tests only. */
 int fvk_set_variant(int variant);
-/* tuning switch of the brick kernel (roofline sweeps only): cells per thread, threads per block, resident blocks per SM
+/* Halo overlap for the cell-centric explicit operators (div / grad / laplacian / surface_integrate) on a decomposed
+ * mesh: phase FVK_TILES_INTERIOR makes them compute only the cells of tiles that read no ghost cell (safe to run
+ * while the halo exchange of the operand is in flight), FVK_TILES_HALO only the remaining tiles (after the exchange);
+ * FVK_TILES_ALL (default) computes everything. The two phases together write every owned cell exactly once, with
+ * bit-identical results. New here: the reference has no distributed operator path (communicator.hpp:89-143 is the
+ * host-side start/finish protocol this mirrors). */
+enum { FVK_TILES_ALL = 0, FVK_TILES_INTERIOR = 1, FVK_TILES_HALO = 2 };
+int fvk_mesh_set_tile_phase(fvk_mesh* mesh, int phase);
+/* Diagnostics: out[i] = sum_k in[k][i] (k < nStreams <= 8, in_h = HOST array of device pointers), one element per
+ * thread like the operator kernels. tools/stream_probe.py uses it to measure what HBM delivers for N concurrent read
+ * streams -- the practical ceiling the 6-8-array operator kernels are compared with next to the 2-stream copy peak. */
+int fvk_probe_streams(int nStreams, const double* const* in_h, int64_t n, double* out, fvk_stream stream);
+/* tuning switch of the brick kernel (roofline sweeps only): cross-face operand timing (1 = early, 2 = deferred), threads per block, resident blocks per SM
  * the register allocation aims at; only combinations instantiated in fvk_explicit.cu are honoured (others fall back to
  * the per-cell gather). (0,0,0) restores the defaults. Environment FVK_BRICK_CFG="K,TB,MINB" does the same. */
 int fvk_set_brick_config(int cellsPerThread, int threads, int minBlocks);

@@ -28,7 +28,7 @@ def test_block_meshes(dims):
     assert bad == 0
     nT, nx, ny, nz, lx, by, bz, slots = info
     assert nx * ny * nz == d.nCells  # numbering detected (degenerate axes may be merged)
-    assert lx * by * bz <= 256 and nT >= -(-d.nCells // 256)  # default: one cell per thread of a 256-thread block
+    assert lx * by * bz <= 128 and nT >= -(-d.nCells // 128)  # default: one cell per thread of a 128-thread block
     assert slots < 32768
 
 
@@ -60,7 +60,7 @@ def test_unstructured_numbering_uses_runs_of_consecutive_cells():
     d = renumbered_block(12, 11, 10, 3)
     info, bad = selftest(d)
     assert bad == 0
-    assert info[1:4] == [0, 0, 0] and info[0] == -(-d.nCells // 256)
+    assert info[1:4] == [0, 0, 0] and info[0] == -(-d.nCells // 128)
 
 
 def test_unsorted_faces_get_no_plan():

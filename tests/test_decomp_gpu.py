@@ -71,6 +71,48 @@ def test_subdomain_operators_bit_exact(P, variant):
         _capi.lib().fvk_set_variant(0)
 
 
+@pytest.mark.parametrize("dims,P", [((160, 8, 6), 2), ((24, 20, 18), 8), ((12, 10, 8), 4)])
+def test_tile_phases_split_the_operator(dims, P):
+    """fvk_mesh_set_tile_phase: INTERIOR leaves the tiles that read ghost cells untouched (so it may run while the halo
+    exchange is in flight), HALO computes exactly those; together they equal the one-pass result bit for bit."""
+    from foamadapter_b200._capi import check, lib
+    g = M.MeshDesc.block(*dims, 1.2, 1.0, 0.8)
+    om = OMesh.from_desc(g)
+    rng = np.random.default_rng(4)
+    phi, phib, flux = rng.uniform(1, 2, om.nC), rng.uniform(1, 2, om.nB), rng.uniform(-1, 1, om.nF)
+    for r in range(P):
+        d = Decomposition(g, P, r)
+        lm = M.UnstructuredMesh(d.desc)
+        f = dev(phi[d.cellGlobal])
+        lflux, lphib = dev(d.scatter_faces(flux)), dev(d.scatter_boundary(phib, om.nI))
+        full = torch.full((lm.nCells,), float("nan"), dtype=torch.float64, device="cuda")
+        ops.div(lm, lflux, f, lphib, full)
+        full3 = torch.zeros((lm.nCells, 3), dtype=torch.float64, device="cuda")
+        ops.grad(lm, f, lphib, full3)
+        try:
+            # interior phase with POISONED ghost values: nothing it computes may depend on them
+            fp = f.clone()
+            fp[d.nOwned:] = float("nan")
+            split = torch.full((lm.nCells,), 7.0, dtype=torch.float64, device="cuda")
+            split3 = torch.full((lm.nCells, 3), 7.0, dtype=torch.float64, device="cuda")
+            check(lib().fvk_mesh_set_tile_phase(lm.handle, 1))
+            ops.div(lm, lflux, fp, lphib, split)
+            ops.grad(lm, fp, lphib, split3)
+            inter = host(split).copy()
+            assert not np.isnan(inter[: d.nOwned]).any()
+            done = inter[: d.nOwned] != 7.0
+            assert np.array_equal(inter[: d.nOwned][done], host(full)[: d.nOwned][done])
+            check(lib().fvk_mesh_set_tile_phase(lm.handle, 2))
+            ops.div(lm, lflux, f, lphib, split)
+            ops.grad(lm, f, lphib, split3)
+        finally:
+            check(lib().fvk_mesh_set_tile_phase(lm.handle, 0))
+        assert np.array_equal(host(split)[: d.nOwned], host(full)[: d.nOwned])
+        assert np.array_equal(host(split3)[: d.nOwned], host(full3)[: d.nOwned])
+        if d.nGhost and lm.nOwned >= 2048:
+            assert done.any() and not done.all()  # a real split: some tiles on each side
+
+
 def test_subdomain_assembly_and_spmv_rows():
     g = M.MeshDesc.block(9, 7, 5, 0.9, 0.7, 0.5)
     gm, om = M.UnstructuredMesh(g), OMesh.from_desc(g)

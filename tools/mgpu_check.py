@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Multi-GPU parity check over NCCL (run under torchrun, one rank per GPU):
+"""Multi-GPU parity check over both transports, NCCL and peer-memory windows (run under torchrun, one rank per GPU):
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/mgpu_check.py
 Checks, against the single-domain CPU oracle on the same global mesh: halo exchange through fvk_comm, explicit
 operators (bit-exact on owned cells), distributed Jacobi-CG (iteration count +-1, solution), and two neoIcoFoam steps."""
@@ -24,13 +24,78 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    for p2p in (False, True):
+        check(rank, world, p2p)
+    if "--perf" in sys.argv:
+        perf(rank, world)
+    dist.destroy_process_group()
+
+
+def perf(rank, world):
+    """Latency of one halo exchange and time of one distributed Jacobi-CG iteration, NCCL vs peer-memory windows."""
+    import json
+    from foamadapter_b200.decomp import default_split
+    n = 128
+    px, py, pz = default_split(world)
+    G = MeshDesc.block(n * px, n * py, n * pz, 0.1 * px, 0.1 * py, 0.1 * pz)
+    d = Decomposition(G, world, rank, n=(px, py, pz))
+    lm = UnstructuredMesh(d.desc)
+    out = {"ranks": world, "cells_per_rank": d.nOwned, "ghosts": d.nGhost}
+    for p2p in (False, True):
+        comm = Comm.from_torch()
+        comm.set_halo(d, p2p=p2p)
+        f = torch.rand(lm.nCells, dtype=torch.float64, device="cuda")
+        for _ in range(20):
+            comm.halo_exchange(f)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier(); torch.cuda.synchronize()
+        e0.record()
+        for _ in range(200):
+            comm.halo_exchange(f)
+        e1.record(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / 200 * 1e3], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        key = "p2p" if p2p else "nccl"
+        out[f"halo_us_{key}"] = float(t.item())
+        ls = la.LinearSystem(lm, 1, zero=False)
+        nB = lm.nBoundaryFaces
+
+        class BD:
+            value = torch.zeros(nB, dtype=torch.float64, device="cuda"); refValue = value; refGrad = value
+            valueFraction = torch.ones(nB, dtype=torch.float64, device="cuda")
+        ops.assemble(lm, [dict(kind=ops.TERM_LAPLACIAN, coeff=-1.0, faceField=torch.ones(lm.nFaces, dtype=torch.float64, device="cuda"))],
+                     BD, ls.values, ls.rhs, ls.bcMatrix, ls.bcRhs)
+        ls.rhs[: d.nOwned] = torch.rand(d.nOwned, dtype=torch.float64, device="cuda") - 0.5
+        iters = 100
+        cfg = {"solver": "Ginkgo", "type": "solver::Cg", "preconditioner": {"type": "preconditioner::Jacobi", "max_block_size": 1},
+               "criteria": {"iteration": iters, "relative_residual_norm": 0.0, "absolute_residual_norm": 0.0}}
+        solver = la.Solver(cfg, comm=comm, check_every=iters + 1)
+        x = torch.zeros(lm.nCells, dtype=torch.float64, device="cuda")
+        solver.solve(ls, x)
+        ts = []
+        for _ in range(3):
+            x.zero_(); dist.barrier(); torch.cuda.synchronize()
+            e0.record(); st = solver.solve(ls, x); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) / iters * 1e3)
+        t = torch.tensor([float(np.median(ts))], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out[f"cg_iter_us_{key}"] = float(t.item())
+        out[f"cg_final_res_{key}"] = st.finalResNorm
+        del solver
+        comm.close()
+    if rank == 0:
+        print("MGPU PERF " + json.dumps(out), flush=True)
+
+
+def check(rank, world, p2p):
     comm = Comm.from_torch()
     dev = lambda a: torch.as_tensor(np.ascontiguousarray(a), device="cuda")
     g = MeshDesc.block(24, 20, 16, 1.2, 1.0, 0.8)
     om = OMesh.from_desc(g)
     d = Decomposition(g, world, rank)
     lm = UnstructuredMesh(d.desc)
-    comm.set_halo(d)
+    comm.set_halo(d, p2p=p2p)
+    assert comm.p2p == p2p
     rng = np.random.default_rng(7)
     phi, phib, flux = rng.uniform(1, 2, om.nC), rng.uniform(1, 2, om.nB), rng.uniform(-1, 1, om.nF)
     # 1. halo exchange
@@ -98,9 +163,8 @@ def main():
     ok = torch.ones(1, device="cuda")
     dist.all_reduce(ok)
     if rank == 0:
-        print(f"MGPU CHECK OK on {world} ranks: halo, explicit ops bit-exact, CG iters {st.numIter} (oracle {so['numIter']}), PISO 2 steps", flush=True)
+        print(f"MGPU CHECK OK on {world} ranks ({'peer-memory windows' if p2p else 'NCCL'}): halo, explicit ops bit-exact, CG iters {st.numIter} (oracle {so['numIter']}), PISO 2 steps", flush=True)
     comm.close()
-    dist.destroy_process_group()
 
 
 if __name__ == "__main__":

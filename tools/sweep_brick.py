@@ -19,14 +19,11 @@ from foamadapter_b200.mesh import MeshDesc, UnstructuredMesh  # noqa: E402
 from tools.roofline import timeit  # noqa: E402
 
 PLANS = [
-    (256, "16,4,4", [(1, 256, 4), (1, 256, 5), (1, 256, 6), (1, 256, 8)]),
-    (256, "32,4,2", [(1, 256, 4), (1, 256, 5), (1, 256, 6)]),
+    (256, "16,4,4", [(1, 256, 4), (1, 256, 5), (1, 256, 6), (1, 256, 8), (2, 256, 5), (2, 256, 6), (2, 256, 8)]),
+    (256, "32,4,2", [(1, 256, 5), (1, 256, 6), (2, 256, 6)]),
     (256, "16,8,2", [(1, 256, 5), (1, 256, 6)]),
-    (256, "8,8,4", [(1, 256, 5), (1, 256, 6)]),
-    (512, "16,8,4", [(1, 512, 2), (1, 512, 3)]),
-    (128, "16,4,2", [(1, 128, 8), (1, 128, 12), (1, 128, 16)]),
-    (128, "8,4,4", [(1, 128, 8), (1, 128, 12)]),
-    (128, "32,2,2", [(1, 128, 12)]),
+    (128, "16,4,2", [(1, 128, 8), (1, 128, 12), (2, 128, 12), (2, 128, 16)]),
+    (512, "16,8,4", [(1, 512, 2), (1, 512, 3), (2, 512, 3)]),
 ]
 
 
