@@ -354,6 +354,7 @@ struct P2PBlob // what a rank publishes (FVK_P2P_BLOB_BYTES)
 {
     cudaIpcMemHandle_t handle; // 64 bytes
     int32_t nGhost;
+    int32_t nOwned;
     int32_t nNbr;
     int32_t nbrRank[FVK_P2P_MAX_NBR];
     int32_t recvOff[FVK_P2P_MAX_NBR]; // offset (cells) of neighbour k's data in this rank's ghost range
@@ -372,7 +373,7 @@ extern "C" int fvk_comm_p2p_export(fvk_comm* c, void* blob)
     c->peerWin.clear();
     if (c->window) { cudaFree(c->window); c->window = nullptr; }
     const size_t nGhost = size_t(c->recvOff.empty() ? 0 : c->recvOff.back());
-    c->windowBytes = FVK_P2P_HALO_OFF + sizeof(double) * 2 * 3 * (nGhost + 1);
+    c->windowBytes = FVK_P2P_Z_OFF(nGhost) + sizeof(double) * 2 * (size_t(c->nOwned) + nGhost);
     FVK_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->window), c->windowBytes));
     FVK_CUDA(cudaMemset(c->window, 0, c->windowBytes));
     FVK_CUDA(cudaDeviceSynchronize());
@@ -380,6 +381,7 @@ extern "C" int fvk_comm_p2p_export(fvk_comm* c, void* blob)
     std::memset(&b, 0, sizeof(b));
     FVK_CUDA(cudaIpcGetMemHandle(&b.handle, c->window));
     b.nGhost = int32_t(nGhost);
+    b.nOwned = c->nOwned;
     b.nNbr = int32_t(c->nbrRank.size());
     for (int k = 0; k < b.nNbr; ++k) { b.nbrRank[k] = c->nbrRank[k]; b.recvOff[k] = c->recvOff[k]; }
     std::memset(blob, 0, FVK_P2P_BLOB_BYTES);
@@ -425,7 +427,7 @@ extern "C" int fvk_comm_p2p_connect(fvk_comm* c, const void* blobs)
         for (int j = 0; j < b.nNbr; ++j)
             if (b.nbrRank[j] == c->rank) kk = j;
         if (kk < 0) return fvk_fail(FVK_EINVAL, "fvk_comm_p2p_connect: rank %d does not list rank %d as a neighbour", r, c->rank);
-        ctx.nbrRank[k] = r; ctx.peerRecvOff[k] = b.recvOff[kk]; ctx.peerGhost[k] = b.nGhost;
+        ctx.nbrRank[k] = r; ctx.peerRecvOff[k] = b.recvOff[kk]; ctx.peerGhost[k] = b.nGhost; ctx.peerOwned[k] = b.nOwned;
         ctx.sendOff[k] = c->sendOff[k];
     }
     ctx.sendOff[ctx.nNbr] = c->sendOff.empty() ? 0 : c->sendOff.back();
@@ -435,6 +437,8 @@ extern "C" int fvk_comm_p2p_connect(fvk_comm* c, const void* blobs)
         FVK_CUDA(cudaMemset(c->state_d, 0, sizeof(FvkP2PState)));
     }
     ctx.state = c->state_d;
+    ctx.sendCells = c->sendCells;
+    ctx.zwin = reinterpret_cast<double*>(c->window + FVK_P2P_Z_OFF(ctx.nGhost));
     if (!c->ctx_d) FVK_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->ctx_d), sizeof(FvkP2PCtx)));
     FVK_CUDA(cudaMemcpy(c->ctx_d, &ctx, sizeof(ctx), cudaMemcpyHostToDevice));
     FVK_CUDA(cudaDeviceSynchronize());
@@ -443,3 +447,14 @@ extern "C" int fvk_comm_p2p_connect(fvk_comm* c, const void* blobs)
 }
 
 extern "C" int fvk_comm_p2p_enabled(const fvk_comm* c) { return (c && c->p2p) ? 1 : 0; }
+
+/* accumulated nanoseconds of the in-kernel communication phases (diagnostics): [0] flag raise + system fence, [1] all-reduce
+ * (r.z, r.r), [2] wait for the halo flags, [3] count; [4] all-reduce p.q, [5] count */
+extern "C" int fvk_comm_p2p_debug(const fvk_comm* c, uint64_t* out8)
+{
+    if (!c || !out8 || !c->state_d) return fvk_fail(FVK_EINVAL, "fvk_comm_p2p_debug: not connected");
+    FvkP2PState s;
+    FVK_CUDA(cudaMemcpy(&s, c->state_d, sizeof(s), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 8; ++k) out8[k] = s.dbg[k];
+    return FVK_OK;
+}

@@ -57,18 +57,29 @@ __device__ __forceinline__ int ld_stream(const int* p)
 
 // ---- peer-memory windows (fvk_comm.cu; used by the CG kernels of fvk_la.cu) ----------------------------------------
 // Window layout (bytes): [0, 512) halo flags (u64 per sender rank) | [1024, ...) all-reduce flags u64[2][64] |
-// [4096, ...) all-reduce values double[2][64][4] | [FVK_P2P_HALO_OFF, ...) halo data double[2][3 * nGhost]
+// [4096, 12288) all-reduce words u64[2][64][8] ({32 data bits | 32-bit sequence} pairs) | [FVK_P2P_HALO_OFF, ...) halo data double[2][3 * nGhost]
 #define FVK_P2P_MAX_RANKS 64
 #define FVK_P2P_MAX_NBR 32
 #define FVK_P2P_HALOFLAG_OFF 0
 #define FVK_P2P_ARFLAG_OFF 1024
 #define FVK_P2P_ARVAL_OFF 4096
 #define FVK_P2P_HALO_OFF 16384
+// byte offset of the CG work area z[2][nOwned + nGhost] of a rank with nGhost ghost cells: behind its halo area
+#define FVK_P2P_Z_OFF(nGhost) (FVK_P2P_HALO_OFF + ((sizeof(double) * 2 * 3 * (size_t(nGhost) + 1) + 255) & ~size_t(255)))
 struct FvkP2PState // device memory of the owning rank only
 {
     unsigned long long haloSeq, arSeq;
     unsigned pushCounter, pad;
+    unsigned long long dbg[8]; // accumulated ns of the last-block phases of k_cg_update / k_spmv (fvk_comm_p2p_debug)
 };
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long fvk_gtime()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
 struct FvkP2PCtx
 {
     int rank, nRanks, nNbr, nOwned, nGhost;
@@ -76,6 +87,9 @@ struct FvkP2PCtx
     int nbrRank[FVK_P2P_MAX_NBR], sendOff[FVK_P2P_MAX_NBR + 1];
     int peerRecvOff[FVK_P2P_MAX_NBR];      // where my cells start in neighbour k's ghost range
     int peerGhost[FVK_P2P_MAX_NBR];        // neighbour k's ghost count (parity stride of its halo area)
+    int peerOwned[FVK_P2P_MAX_NBR];        // neighbour k's owned-cell count
+    double* zwin;                          // this rank's CG work area in its window: z[2][nOwned + nGhost]
+    const int* sendCells;                  // [sendOff[nNbr]] owned cells whose values the neighbours need
     FvkP2PState* state;
 };
 struct fvk_comm;
@@ -83,45 +97,107 @@ const FvkP2PCtx* fvk_comm_p2p_ctx(const fvk_comm* c); // nullptr: windows not co
 
 #ifdef __CUDACC__
 // Sum of n <= 4 doubles over all ranks, executed by (at least) the first warp of ONE block per rank; vals (shared or
-// global memory visible to the block) is replaced by the total. Every rank adds the contributions in rank order, so
-// the result is bit-identical everywhere. Mailboxes are double-buffered by the parity of the sequence number: a rank
-// can only be one all-reduce ahead of the slowest one.
+// global memory visible to the block) is replaced by the total. Low-latency mailbox protocol: every double travels as
+// two 8-byte stores {32 data bits | 32-bit sequence number}, so data and "flag" arrive together -- no fence, no
+// separate flag store; the receiver polls each word until it carries the current sequence number (one NVLink
+// traversal on the critical path). Every rank adds the contributions in rank order: bit-identical everywhere.
+// Mailboxes are double-buffered by the parity of the sequence number: a rank can only be one all-reduce ahead.
 __device__ __forceinline__ void fvk_p2p_allreduce_sum(const FvkP2PCtx& ctx, double* vals, int n)
 {
+    __shared__ double ar_sh[FVK_P2P_MAX_RANKS][4];
     if (threadIdx.x >= 32) return;
     const unsigned long long seq = ctx.state->arSeq + 1;
+    const unsigned long long tag = (seq & 0xffffffffull) << 32;
     const int par = int(seq & 1);
-    double mine[4];
-    for (int q = 0; q < n; ++q) mine[q] = vals[q];
+    unsigned long long bits[4];
+    for (int q = 0; q < n; ++q) bits[q] = (unsigned long long) __double_as_longlong(vals[q]);
     for (int r = threadIdx.x; r < ctx.nRanks; r += 32)
     {
-        double* dv = reinterpret_cast<double*>(ctx.win[r] + FVK_P2P_ARVAL_OFF) + (size_t(par) * FVK_P2P_MAX_RANKS + ctx.rank) * 4;
-        for (int q = 0; q < n; ++q) dv[q] = mine[q];
-        __threadfence_system();
-        unsigned long long* df = reinterpret_cast<unsigned long long*>(ctx.win[r] + FVK_P2P_ARFLAG_OFF) + size_t(par) * FVK_P2P_MAX_RANKS + ctx.rank;
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(df), "l"(seq) : "memory");
+        unsigned long long* slot = reinterpret_cast<unsigned long long*>(ctx.win[r] + FVK_P2P_ARVAL_OFF) + (size_t(par) * FVK_P2P_MAX_RANKS + ctx.rank) * 8;
+        for (int q = 0; q < n; ++q)
+        {
+            asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(slot + 2 * q), "l"((bits[q] & 0xffffffffull) | tag) : "memory");
+            asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(slot + 2 * q + 1), "l"((bits[q] >> 32) | tag) : "memory");
+        }
     }
     for (int r = threadIdx.x; r < ctx.nRanks; r += 32)
     {
-        const unsigned long long* f = reinterpret_cast<const unsigned long long*>(ctx.win[ctx.rank] + FVK_P2P_ARFLAG_OFF) + size_t(par) * FVK_P2P_MAX_RANKS + r;
+        const unsigned long long* slot = reinterpret_cast<const unsigned long long*>(ctx.win[ctx.rank] + FVK_P2P_ARVAL_OFF) + (size_t(par) * FVK_P2P_MAX_RANKS + r) * 8;
+        for (int q = 0; q < n; ++q)
+        {
+            unsigned long long lo, hi;
+            do
+            {
+                asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(lo) : "l"(slot + 2 * q) : "memory");
+                asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(hi) : "l"(slot + 2 * q + 1) : "memory");
+            } while ((lo & 0xffffffff00000000ull) != tag || (hi & 0xffffffff00000000ull) != tag);
+            ar_sh[r][q] = __longlong_as_double((long long) ((lo & 0xffffffffull) | (hi << 32)));
+        }
+    }
+    __syncwarp();
+    if (threadIdx.x == 0)
+    {
+        for (int q = 0; q < n; ++q)
+        {
+            double s = 0.0;
+            for (int r = 0; r < ctx.nRanks; ++r) s += ar_sh[r][q];
+            vals[q] = s;
+        }
+        ctx.state->arSeq = seq;
+    }
+    __syncwarp();
+}
+#endif
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// Halo exchange of a scalar cell field executed by ONE block (the last block of the kernel that produced the field):
+// store my send cells into the neighbours' windows, raise the flags; then (second call) wait for the neighbours'
+// flags and copy my window into the ghost range. Returns / takes the sequence number of the exchange.
+__device__ __forceinline__ unsigned long long fvk_p2p_halo_push_block(const FvkP2PCtx& ctx, const double* field)
+{
+    const unsigned long long seq = ctx.state->haloSeq + 1;
+    const int nSend = ctx.sendOff[ctx.nNbr];
+    for (int i = threadIdx.x; i < nSend; i += blockDim.x)
+    {
+        int k = 0;
+        while (i >= ctx.sendOff[k + 1]) ++k;
+        double* dst = reinterpret_cast<double*>(ctx.win[ctx.nbrRank[k]] + FVK_P2P_HALO_OFF) + (seq & 1) * size_t(3) * ctx.peerGhost[k]
+                      + (ctx.peerRecvOff[k] + (i - ctx.sendOff[k]));
+        *dst = __ldcg(field + ctx.sendCells[i]); // written by other blocks of this kernel: read through L2
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < ctx.nNbr)
+    {
+        unsigned long long* f = reinterpret_cast<unsigned long long*>(ctx.win[ctx.nbrRank[threadIdx.x]] + FVK_P2P_HALOFLAG_OFF) + ctx.rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(seq) : "memory");
+    }
+    return seq;
+}
+__device__ __forceinline__ void fvk_p2p_halo_wait_unpack_block(const FvkP2PCtx& ctx, double* field, unsigned long long seq)
+{
+    if (threadIdx.x < ctx.nNbr)
+    {
+        const unsigned long long* f = reinterpret_cast<const unsigned long long*>(ctx.win[ctx.rank] + FVK_P2P_HALOFLAG_OFF) + ctx.nbrRank[threadIdx.x];
         unsigned long long v;
         do
         {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
         } while (v < seq);
     }
-    __syncwarp();
-    if (threadIdx.x == 0)
-    {
-        const double* mv = reinterpret_cast<const double*>(ctx.win[ctx.rank] + FVK_P2P_ARVAL_OFF) + size_t(par) * FVK_P2P_MAX_RANKS * 4;
-        for (int q = 0; q < n; ++q)
-        {
-            double s = 0.0;
-            for (int r = 0; r < ctx.nRanks; ++r) s += __ldcg(mv + r * 4 + q);
-            vals[q] = s;
-        }
-        ctx.state->arSeq = seq;
-    }
-    __syncwarp();
+    __syncthreads();
+    const double* src = reinterpret_cast<const double*>(ctx.win[ctx.rank] + FVK_P2P_HALO_OFF) + (seq & 1) * size_t(3) * ctx.nGhost;
+    for (int i = threadIdx.x; i < ctx.nGhost; i += blockDim.x) field[ctx.nOwned + i] = __ldcg(src + i);
+    if (threadIdx.x == 0) ctx.state->haloSeq = seq;
 }
 #endif

@@ -12,6 +12,8 @@
 #include "fvk_device.cuh"
 
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace
@@ -65,7 +67,7 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* sh /* [NV*8] 
 // the totals in out[] (thread 0 only).
 template <int NV>
 __device__ __forceinline__ bool grid_sum(double (&v)[NV], double* __restrict__ partial, unsigned* __restrict__ counter,
-                                         double (&out)[NV])
+                                         double (&out)[NV], bool sysFence = false)
 {
     __shared__ double sh[NV * 8];
     __shared__ bool last;
@@ -74,7 +76,8 @@ __device__ __forceinline__ bool grid_sum(double (&v)[NV], double* __restrict__ p
     {
 #pragma unroll
         for (int k = 0; k < NV; ++k) partial[size_t(k) * MAX_GRID + blockIdx.x] = v[k];
-        __threadfence();
+        if (sysFence) __threadfence_system(); // the block's stores into peer windows are performed before it checks in
+        else __threadfence();
         const unsigned t = atomicAdd(counter, 1u);
         last = (t == gridDim.x - 1);
     }
@@ -136,22 +139,47 @@ __global__ void k_set_normB(PcgState* st) { st->normB = sqrt(st->sums[3]); }
 template <bool FIRST, bool JACOBI>
 __global__ void __launch_bounds__(TB)
 k_cg_update(int n, PcgState* __restrict__ st, double* __restrict__ x, const double* __restrict__ p,
-            const double* __restrict__ q, double* __restrict__ r, const double* __restrict__ dinv,
-            double* __restrict__ z, double* __restrict__ partial, unsigned* __restrict__ counter,
+            const double* __restrict__ q, const double* rIn, double* rOut, const double* __restrict__ dinv,
+            double* z, double* __restrict__ partial, unsigned* __restrict__ counter,
             double* __restrict__ hist, int distributed, const FvkP2PCtx* __restrict__ p2p)
 {
     __shared__ double shv[4];
     if (st->done) return;
     const double alpha = FIRST ? 0.0 : st->alpha;
+    unsigned long long hseq = 0;
+    if (distributed == 2)
+    {
+        // z of this iteration lives in the window half selected by the exchange's parity (zero-copy halo)
+        z = p2p->zwin + ((p2p->state->haloSeq + 1) & 1) * size_t(p2p->nOwned + p2p->nGhost);
+        // peer-memory halo of z, spread over the whole grid: z of my send cells is formed from the kernel's INPUTS (rIn is
+        // not written here: r is double-buffered in this mode) with the same expression as below and stored straight
+        // into the neighbours' windows over NVLink while the main loop streams
+        const FvkP2PCtx& ctx = *p2p;
+        hseq = ctx.state->haloSeq + 1; // advanced by the last block only, after every block has read it
+        const int nSend = ctx.sendOff[ctx.nNbr];
+        for (int i = blockIdx.x * TB + threadIdx.x; i < nSend; i += gridDim.x * TB)
+        {
+            int k = 0;
+            while (i >= ctx.sendOff[k + 1]) ++k;
+            const int c = ctx.sendCells[i];
+            double ri = rIn[c];
+            if (!FIRST) ri = ri - alpha * q[c];
+            const double zi = JACOBI ? ri * dinv[c] : ri;
+            // the neighbour's ghost entry of ITS z (same parity): it reads it like any other column
+            double* dst = reinterpret_cast<double*>(ctx.win[ctx.nbrRank[k]] + FVK_P2P_Z_OFF(ctx.peerGhost[k]))
+                          + (hseq & 1) * size_t(ctx.peerOwned[k] + ctx.peerGhost[k]) + ctx.peerOwned[k] + ctx.peerRecvOff[k] + (i - ctx.sendOff[k]);
+            *dst = zi;
+        }
+    }
     double acc[2] = {0.0, 0.0};
     for (int i = blockIdx.x * TB + threadIdx.x; i < n; i += gridDim.x * TB)
     {
-        double ri = r[i];
+        double ri = rIn[i];
         if (!FIRST)
         {
             x[i] = x[i] + alpha * p[i];
             ri = ri - alpha * q[i];
-            r[i] = ri;
+            rOut[i] = ri;
         }
         const double zi = JACOBI ? ri * dinv[i] : ri;
         z[i] = zi;
@@ -159,27 +187,44 @@ k_cg_update(int n, PcgState* __restrict__ st, double* __restrict__ x, const doub
         acc[1] += ri * ri;
     }
     double tot[2];
-    if (grid_sum<2>(acc, partial, counter, tot)) // true in every thread of the last block
+    if (distributed == 2)
     {
-        if (distributed == 2)
-        { // peer-memory all-reduce of (r.z, r.r) by this block, then the scalar update: no NCCL kernel, no extra launch
-            if (threadIdx.x == 0) { shv[0] = tot[0]; shv[1] = tot[1]; }
-            __syncthreads();
-            fvk_p2p_allreduce_sum(*p2p, shv, 2);
-            __syncthreads();
-            if (threadIdx.x == 0)
-            {
-                st->sums[0] = shv[0];
-                st->sums[1] = shv[1];
-                decide_after_update(st, hist);
-            }
-        }
-        else if (threadIdx.x == 0)
+        // only the blocks that stored into a peer window pay for a system-scope fence
+        if (!grid_sum<2>(acc, partial, counter, tot, blockIdx.x * TB < p2p->sendOff[p2p->nNbr])) return;
+        // last block: every block's window stores are done. Raise the halo flags, all-reduce (r.z, r.r) through the
+        // mailboxes, wait for the neighbours' flags (the next kernel reads the ghost z from the window), scalar update.
+        const FvkP2PCtx& ctx = *p2p;
+        const unsigned long long t0 = fvk_gtime();
+        __threadfence(); // every block fenced its window stores at system scope before checking in (grid_sum, sysFence)
+        if (threadIdx.x < ctx.nNbr)
+            st_release_sys_u64(reinterpret_cast<unsigned long long*>(ctx.win[ctx.nbrRank[threadIdx.x]] + FVK_P2P_HALOFLAG_OFF) + ctx.rank, hseq);
+        if (threadIdx.x == 0) { shv[0] = tot[0]; shv[1] = tot[1]; }
+        __syncthreads();
+        const unsigned long long t1 = fvk_gtime();
+        fvk_p2p_allreduce_sum(ctx, shv, 2);
+        const unsigned long long t2 = fvk_gtime();
+        if (threadIdx.x < ctx.nNbr)
         {
-            st->sums[0] = tot[0];
-            st->sums[1] = tot[1];
-            if (!distributed) decide_after_update(st, hist);
+            const unsigned long long* f = reinterpret_cast<const unsigned long long*>(ctx.win[ctx.rank] + FVK_P2P_HALOFLAG_OFF) + ctx.nbrRank[threadIdx.x];
+            while (ld_acquire_sys_u64(f) < hseq) {}
         }
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            const unsigned long long t3 = fvk_gtime();
+            ctx.state->dbg[0] += t1 - t0; ctx.state->dbg[1] += t2 - t1; ctx.state->dbg[2] += t3 - t2; ctx.state->dbg[3] += 1;
+            ctx.state->haloSeq = hseq;
+            st->sums[0] = shv[0];
+            st->sums[1] = shv[1];
+            decide_after_update(st, hist);
+        }
+        return;
+    }
+    if (grid_sum<2>(acc, partial, counter, tot) && threadIdx.x == 0)
+    {
+        st->sums[0] = tot[0];
+        st->sums[1] = tot[1];
+        if (!distributed) decide_after_update(st, hist);
     }
 }
 
@@ -203,7 +248,7 @@ __global__ void __launch_bounds__(TB)
 k_spmv(int nRows, const int* __restrict__ rowOffs, const int* __restrict__ colIdxs, const double* __restrict__ values,
        const double* __restrict__ x, const double* __restrict__ b, double* __restrict__ y, PcgState* __restrict__ st,
        const double* __restrict__ z, double* __restrict__ pNew, double* __restrict__ partial,
-       unsigned* __restrict__ counter, int distributed, const FvkP2PCtx* __restrict__ p2p = nullptr)
+       unsigned* __restrict__ counter, int distributed, const FvkP2PCtx* __restrict__ p2p = nullptr, int nCols = 0)
 {
     __shared__ double prod[SPMV_CAP];
     __shared__ int ro[SPMV_ROWS + 1];
@@ -214,6 +259,14 @@ k_spmv(int nRows, const int* __restrict__ rowOffs, const int* __restrict__ colId
         beta = st->beta;
     }
     double acc[1] = {0.0};
+    // peer-memory CG: z (owned + ghost entries, the latter stored by the neighbours' update kernels, flags already
+    // awaited) lies in the window half of the last exchange's parity; p of the ghost columns follows p = z + beta p
+    const double* zz = z; // read with __ldg below: the non-coherent path the __restrict__ parameter would get
+    if (MODE == 4 && distributed == 2)
+    {
+        zz = p2p->zwin + (p2p->state->haloSeq & 1) * size_t(nCols);
+        for (int g = nRows + blockIdx.x * TB + threadIdx.x; g < nCols; g += gridDim.x * TB) pNew[g] = __ldg(zz + g) + beta * x[g];
+    }
     const int nTiles = (nRows + SPMV_ROWS - 1) / SPMV_ROWS;
     for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x)
     {
@@ -235,7 +288,7 @@ k_spmv(int nRows, const int* __restrict__ rowOffs, const int* __restrict__ colId
             for (int e = cb + threadIdx.x; e < ce; e += TB)
             {
                 const int j = colIdxs[e];
-                const double xv = (MODE == 4) ? (z[j] + beta * x[j]) : x[j];
+                const double xv = (MODE == 4) ? (__ldg(zz + j) + beta * x[j]) : x[j];
                 prod[e - cb] = ld_stream(values + e) * xv;
             }
             __syncthreads();
@@ -255,7 +308,7 @@ k_spmv(int nRows, const int* __restrict__ rowOffs, const int* __restrict__ colId
             }
             if (MODE == 4)
             {
-                const double pr = z[r] + beta * x[r];
+                const double pr = __ldg(zz + r) + beta * x[r];
                 pNew[r] = pr;
                 y[r] = sum;
                 acc[0] += pr * sum;
@@ -272,10 +325,12 @@ k_spmv(int nRows, const int* __restrict__ rowOffs, const int* __restrict__ colId
                 __syncthreads();
                 if (threadIdx.x == 0) prod[0] = tot[0];
                 __syncthreads();
+                const unsigned long long t0 = fvk_gtime();
                 fvk_p2p_allreduce_sum(*p2p, prod, 1);
                 __syncthreads();
                 if (threadIdx.x == 0)
                 {
+                    p2p->state->dbg[4] += fvk_gtime() - t0; p2p->state->dbg[5] += 1;
                     st->sums[2] = prod[0];
                     decide_after_spmv(st);
                 }
@@ -495,6 +550,7 @@ struct fvk_solver
     int32_t nRows = 0, nCols = 0;
     fvk_solver_config cfg {};
     fvk_comm* comm = nullptr;
+    double *r2 = nullptr; // second residual buffer of the peer-memory mode
     double *r = nullptr, *z = nullptr, *p0 = nullptr, *p1 = nullptr, *q = nullptr, *dinv = nullptr;
     double *partial = nullptr, *hist = nullptr;
     unsigned* counter = nullptr;
@@ -506,7 +562,7 @@ struct fvk_solver
 extern "C" int fvk_solver_destroy(fvk_solver* sv)
 {
     if (!sv) return FVK_OK;
-    for (void* ptr : {(void*) sv->r, (void*) sv->z, (void*) sv->p0, (void*) sv->p1, (void*) sv->q, (void*) sv->dinv,
+    for (void* ptr : {(void*) sv->r, (void*) sv->r2, (void*) sv->z, (void*) sv->p0, (void*) sv->p1, (void*) sv->q, (void*) sv->dinv,
                       (void*) sv->partial, (void*) sv->hist, (void*) sv->counter, (void*) sv->state})
         if (ptr) cudaFree(ptr);
     if (sv->state_h) cudaFreeHost(sv->state_h);
@@ -525,7 +581,7 @@ extern "C" int fvk_solver_create(int32_t nRows, int32_t nCols, const fvk_solver_
     sv->histCap = cfg->maxIter + 2;
     cudaError_t e = cudaSuccess;
     auto A = [&](double** ptr, size_t n) { if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(ptr), sizeof(double) * n); };
-    A(&sv->r, nRows); A(&sv->z, nCols); A(&sv->p0, nCols); A(&sv->p1, nCols); A(&sv->q, nRows); A(&sv->dinv, nRows);
+    A(&sv->r, nRows); if (comm) A(&sv->r2, nRows); A(&sv->z, nCols); A(&sv->p0, nCols); A(&sv->p1, nCols); A(&sv->q, nRows); A(&sv->dinv, nRows);
     A(&sv->partial, 4 * MAX_GRID); A(&sv->hist, sv->histCap);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&sv->counter), sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMemset(sv->counter, 0, sizeof(unsigned));
@@ -584,22 +640,43 @@ extern "C" int fvk_solver_solve(fvk_solver* sv, const int32_t* rowOffs, const in
 
     double* pCur = sv->p0;  // p of the previous iteration
     double* pNext = sv->p1;
+    double* rIn = sv->r;    // peer-memory mode double-buffers r (k_cg_update re-reads its input for the halo cells)
+    double* rOut = dmode == 2 ? sv->r2 : sv->r;
     const int every = sv->cfg.checkEvery;
+    // FVK_CG_TIMING=1: CUDA events around the two kernels of the first 64 iterations, averages to stderr
+    static const bool timing = [] { const char* e = std::getenv("FVK_CG_TIMING"); return e && *e == '1'; }();
+    constexpr int NT = 64;
+    cudaEvent_t tev[NT][3];
+    if (timing)
+        for (auto& e3 : tev)
+            for (auto& e : e3) cudaEventCreate(&e);
+    int timed = 0;
     for (int it = 0; it <= sv->cfg.maxIter; ++it)
     {
+        if (timing && it >= 1 && it <= NT) cudaEventRecord(tev[it - 1][0], st);
         // K1
         if (it == 0)
         {
-            if (jacobi) k_cg_update<true, true><<<gV, TB, 0, st>>>(n, sv->state, x, pCur, sv->q, sv->r, sv->dinv, sv->z, sv->partial, sv->counter, sv->hist, dmode, p2p);
-            else k_cg_update<true, false><<<gV, TB, 0, st>>>(n, sv->state, x, pCur, sv->q, sv->r, sv->dinv, sv->z, sv->partial, sv->counter, sv->hist, dmode, p2p);
+            if (jacobi) k_cg_update<true, true><<<gV, TB, 0, st>>>(n, sv->state, x, pCur, sv->q, rIn, rIn, sv->dinv, sv->z, sv->partial, sv->counter, sv->hist, dmode, p2p);
+            else k_cg_update<true, false><<<gV, TB, 0, st>>>(n, sv->state, x, pCur, sv->q, rIn, rIn, sv->dinv, sv->z, sv->partial, sv->counter, sv->hist, dmode, p2p);
         }
         else
         {
-            if (jacobi) k_cg_update<false, true><<<gV, TB, 0, st>>>(n, sv->state, x, pCur, sv->q, sv->r, sv->dinv, sv->z, sv->partial, sv->counter, sv->hist, dmode, p2p);
-            else k_cg_update<false, false><<<gV, TB, 0, st>>>(n, sv->state, x, pCur, sv->q, sv->r, sv->dinv, sv->z, sv->partial, sv->counter, sv->hist, dmode, p2p);
+            if (jacobi) k_cg_update<false, true><<<gV, TB, 0, st>>>(n, sv->state, x, pCur, sv->q, rIn, rOut, sv->dinv, sv->z, sv->partial, sv->counter, sv->hist, dmode, p2p);
+            else k_cg_update<false, false><<<gV, TB, 0, st>>>(n, sv->state, x, pCur, sv->q, rIn, rOut, sv->dinv, sv->z, sv->partial, sv->counter, sv->hist, dmode, p2p);
         }
         FVK_LAUNCH_CHECK();
-        if (dist)
+        if (timing && it >= 1 && it <= NT) cudaEventRecord(tev[it - 1][1], st);
+        if (it > 0 && dmode == 2) { double* t = rIn; rIn = rOut; rOut = t; }
+        if (dmode == 2)
+        {
+            // peer-memory CG: the same two kernels as on one GPU. K1's last block exchanged the halo of z and all-reduced
+            // (r.z, r.r); K2 forms p = z + beta p on the fly for owned AND ghost columns and all-reduces p.q.
+            k_spmv<4><<<gS, TB, 0, st>>>(n, rowOffs, colIdxs, values, pCur, nullptr, sv->q, sv->state, sv->z, pNext, sv->partial, sv->counter, 2, p2p, sv->nCols);
+            FVK_LAUNCH_CHECK();
+            double* t = pCur; pCur = pNext; pNext = t;
+        }
+        else if (dist)
         {
             if (dmode == 1)
             {
@@ -623,12 +700,28 @@ extern "C" int fvk_solver_solve(fvk_solver* sv, const int32_t* rowOffs, const in
             FVK_LAUNCH_CHECK();
             double* t = pCur; pCur = pNext; pNext = t;
         }
+        if (timing && it >= 1 && it <= NT) { cudaEventRecord(tev[it - 1][2], st); timed = it; }
         if ((it + 1) % every == 0 || it == sv->cfg.maxIter)
         {
             FVK_CUDA(cudaMemcpyAsync(sv->state_h, sv->state, sizeof(PcgState), cudaMemcpyDeviceToHost, st));
             FVK_CUDA(cudaStreamSynchronize(st));
             if (sv->state_h->done) break;
         }
+    }
+    if (timing)
+    {
+        cudaStreamSynchronize(st);
+        double a = 0, b = 0;
+        for (int i = 0; i < timed; ++i)
+        {
+            float x1 = 0, x2 = 0;
+            cudaEventElapsedTime(&x1, tev[i][0], tev[i][1]);
+            cudaEventElapsedTime(&x2, tev[i][1], tev[i][2]);
+            a += x1; b += x2;
+        }
+        if (timed) std::fprintf(stderr, "[fvk cg timing] mode %d: update phase %.1f us, spmv phase %.1f us (avg of %d iterations)\n", dmode, a / timed * 1e3, b / timed * 1e3, timed);
+        for (auto& e3 : tev)
+            for (auto& e : e3) cudaEventDestroy(e);
     }
     if (!sv->state_h->done) return fvk_fail(FVK_ECUDA, "fvk_solver_solve: stop flag not raised after maxIter+1 checks");
     stats_h->numIter = sv->state_h->iter;

@@ -81,6 +81,14 @@ def perf(rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         out[f"cg_iter_us_{key}"] = float(t.item())
         out[f"cg_final_res_{key}"] = st.finalResNorm
+        if p2p:
+            import ctypes as C
+            from foamadapter_b200._capi import lib
+            dbg = (C.c_uint64 * 8)()
+            lib().fvk_comm_p2p_debug(comm.handle, dbg)
+            d_ = list(dbg)
+            out["p2p_phase_us"] = {"flag_raise": d_[0] / max(d_[3], 1) / 1e3, "allreduce_rz_rr": d_[1] / max(d_[3], 1) / 1e3,
+                                   "halo_wait": d_[2] / max(d_[3], 1) / 1e3, "allreduce_pq": d_[4] / max(d_[5], 1) / 1e3}
         del solver
         comm.close()
     if rank == 0:
