@@ -393,6 +393,45 @@ bool fvk_build_brick_plan(const fvk_mesh_desc* d, const FvkStencilHost& st, FvkB
         if (h.nx >= 65536 || h.nb >= 32768) geomBad |= 2;
     }
     if (geomBad) { *reason = "tile geometry does not reproduce the tiling"; return false; }
+    // ---- affine interior box: prove, cell by cell, the closed-form topology k_gather_affine assumes
+    static const bool noAffine = [] { const char* e = std::getenv("FVK_NO_AFFINE"); return e && *e == '1'; }();
+    g.tdimZ = structured ? (g.dims[2] + g.brick[2] - 1) / g.brick[2] : 0;
+    if (!noAffine && structured && nOwned == nC && !d->faceOrder && g.shiftL >= 0 && g.shiftBy >= 0 && g.tdim[0] > 2 && g.tdim[1] > 2
+        && g.tdimZ > 2 && g.brick[0] * g.brick[1] * g.brick[2] == g.cap)
+    {
+        const int64_t nx = g.dims[0], ny = g.dims[1], nxy = nx * ny;
+        int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+        for (int32_t t = 0; t < nT; ++t)
+        {
+            const int32_t ix = t % g.tdim[0], q = t / g.tdim[0], iy = q % g.tdim[1], iz = q / g.tdim[1];
+            if (ix < 1 || ix > g.tdim[0] - 2 || iy < 1 || iy > g.tdim[1] - 2 || iz < 1 || iz > g.tdimZ - 2) continue;
+            const FvkBrickHdr& h = out.hdr[t];
+            if (h.nb != 0 || h.nc != g.cap) { bad |= 1; continue; }
+            for_tile_cells(tiles[t], [&](int32_t c, int32_t) {
+                const int64_t j = (c / nx) % ny, k = c / nxy;
+                const int64_t fs = 3 * int64_t(c) - j - k * (nx + ny);
+                const int64_t want[6] = {((fs - 3 * nxy + nx + ny + 2) << 1) | 1, ((fs - 3 * nx + 2) << 1) | 1, ((fs - 3) << 1) | 1,
+                                         fs << 1, (fs + 1) << 1, (fs + 2) << 1};
+                if (seg[size_t(c) + 1] - seg[c] != 6) { bad |= 1; return; }
+                for (int e = 0; e < 6; ++e)
+                    if (ent[seg[c] + e] != want[e]) { bad |= 1; return; }
+                if (nei[fs] != c + 1 || nei[fs + 1] != c + nx || nei[fs + 2] != c + nxy || own[fs] != c || own[fs + 1] != c || own[fs + 2] != c
+                    || own[fs - 3] != c - 1 || own[fs - 3 * nx + 2] != c - nx || own[fs - 3 * nxy + nx + ny + 2] != c - nxy)
+                    bad |= 1;
+            });
+        }
+        if (!bad)
+        {
+            g.affineBox = 1;
+            g.box[0] = g.tdim[0] - 2; g.box[1] = g.tdim[1] - 2; g.box[2] = g.tdimZ - 2;
+            for (int32_t t = 0; t < nT; ++t)
+            {
+                const int32_t ix = t % g.tdim[0], q = t / g.tdim[0], iy = q % g.tdim[1], iz = q / g.tdim[1];
+                if (ix < 1 || ix > g.tdim[0] - 2 || iy < 1 || iy > g.tdim[1] - 2 || iz < 1 || iz > g.tdimZ - 2) out.shellTiles.push_back(t);
+            }
+        }
+    }
     return true;
 }
 
@@ -507,5 +546,19 @@ extern "C" int fvk_brick_plan_selftest(const fvk_mesh_desc* d, int32_t* info /* 
     info[4] = bp.brick[0]; info[5] = bp.brick[1]; info[6] = bp.brick[2];
     info[7] = bp.maxSlots;
     *badCells = fvk_verify_brick_plan(d, st, bp);
+    return FVK_OK;
+}
+
+// diagnostics (host only): did the plan prove an affine interior box? info[4] = {affineBox, box tiles x, y, z}, nShell
+extern "C" int fvk_brick_plan_affine_info(const fvk_mesh_desc* d, int32_t* info /* [5] */)
+{
+    if (!d || !info) return fvk_fail(FVK_EINVAL, "fvk_brick_plan_affine_info: null");
+    FvkStencilHost st;
+    fvk_build_stencil(d, st);
+    FvkBrickPlanHost bp;
+    const char* why = "";
+    if (!fvk_build_brick_plan(d, st, bp, &why)) return fvk_fail(FVK_EUNSUPPORTED, "brick plan: %s", why);
+    info[0] = bp.geom.affineBox; info[1] = bp.geom.box[0]; info[2] = bp.geom.box[1]; info[3] = bp.geom.box[2];
+    info[4] = int32_t(bp.shellTiles.size());
     return FVK_OK;
 }

@@ -28,6 +28,7 @@ struct FvkBrickPlanHost
     std::vector<FvkBrickRec> recF;
     std::vector<uint2> codes4;
     std::vector<int4> tileInfo;
+    std::vector<int32_t> shellTiles;
     int32_t dims[3] = {0, 0, 0};  // detected block-structured numbering (0,0,0: none -> runs of consecutive cells)
     int32_t brick[3] = {0, 0, 0}; // brick shape used
 };

@@ -23,6 +23,7 @@ static inline cudaStream_t fvk_cu(fvk_stream s) { return reinterpret_cast<cudaSt
 int fvk_sm_count();
 // current experiment variant (fvk_set_variant)
 int fvk_variant();
+bool fvk_no_affine(); // true: the affine interior kernel is switched off (A/B measurements)
 bool fvk_brick_config(int cfg[3]); // true: {cells per thread, threads per block, resident blocks} override is set
 
 struct Vec3d

@@ -635,7 +635,7 @@ int launch_tile(const fvk_mesh* m, Op op, Scaling sc, double* out, int mode, cud
 template <class Op, int TB, int MINB, bool XDEFER>
 __global__ void __launch_bounds__(TB, MINB)
 k_gather_brick(Op op, Scaling sc, FvkBrickPlan bp, int nI, const int* __restrict__ neighbour, double* __restrict__ out, int mode,
-               int phase)
+               int phase, const int* __restrict__ tileList)
 {
     using VT = typename Op::V;
     using T = typename VT::T;
@@ -648,7 +648,7 @@ k_gather_brick(Op op, Scaling sc, FvkBrickPlan bp, int nI, const int* __restrict
     const double* __restrict__ S0 = op.s0();
     const double* __restrict__ S1 = op.s1();
     const double* __restrict__ cellsG = op.cells();
-    const int tid = threadIdx.x, t = blockIdx.x;
+    const int tid = threadIdx.x, t = tileList ? tileList[blockIdx.x] : int(blockIdx.x); // list: the tiles outside the affine box
 
     // ---- level 1
     const int4 ti = bp.tileInfo[t]; // xBase, nx | nb << 16, bBase, nOwnSlots | touchesGhost << 30
@@ -783,13 +783,94 @@ k_gather_brick(Op op, Scaling sc, FvkBrickPlan bp, int nI, const int* __restrict
     finish<VT>(out, cell, acc, s, mode);
 }
 
+// ---- affine kernel: the interior box of a block-structured mesh --------------------------------------------------
+// For the tiles whose topology the plan proved to follow the closed form of FvkBrickGeom (fvk_brickplan.cpp checks every
+// cell), NO index array is read: cell ids, face ids, neighbours and slots are arithmetic, so every load of the kernel is
+// issued in the first instruction window (one memory round trip per block instead of three dependent ones) and the
+// owner / neighbour labels (24 B per face of the algorithmic traffic) stay in DRAM. Arithmetic, summation order
+// [zL, yL, xL | x, y, z] and results are those of the generic kernel, bit for bit. One block per tile, one cell per
+// thread; the faces on the tile's three lower sides ("cross" faces) are evaluated by a thread each.
+template <class Op, int TB, int MINB>
+__global__ void __launch_bounds__(TB, MINB)
+k_gather_affine(Op op, Scaling sc, FvkBrickGeom g, double* __restrict__ out, int mode)
+{
+    using VT = typename Op::V;
+    using T = typename VT::T;
+    using CL = CellLd<typename Op::CV>;
+    using CT = typename CL::T;
+    constexpr int W0 = Op::W0, W1 = Op::W1 ? Op::W1 : 1;
+    extern __shared__ __align__(16) unsigned char smem[];
+    T* sflux = reinterpret_cast<T*>(smem);
+    const double* __restrict__ S0 = op.s0();
+    const double* __restrict__ S1 = op.s1();
+    const double* __restrict__ cellsG = op.cells();
+    const int tid = threadIdx.x;
+    const int lx = g.brick[0], by = g.brick[1], bz = g.brick[2], nx = g.dims[0], ny = g.dims[1];
+    const int64_t nxy = int64_t(nx) * ny;
+    // tile of the interior box -> first cell
+    const int bxi = blockIdx.x % g.box[0], q = blockIdx.x / g.box[0], byi = q % g.box[1], bzi = q / g.box[1];
+    const int x0 = (bxi + 1) * lx, y0 = (byi + 1) * by, z0 = (bzi + 1) * bz;
+    const int off = tid & (lx - 1), r = tid >> g.shiftL, a = r & (by - 1), b = r >> g.shiftBy;
+    const int i = x0 + off, j = y0 + a, k = z0 + b;
+    const int64_t cell = i + int64_t(nx) * j + nxy * k;
+    const int64_t fs = 3 * cell - j - int64_t(k) * (nx + ny);
+    // ---- every load of the owned faces
+    double fa[3][W0], fb[3][W1];
+#pragma unroll
+    for (int f = 0; f < 3; ++f)
+    {
+#pragma unroll
+        for (int c = 0; c < W0; ++c) fa[f][c] = S0[int64_t(W0) * (fs + f) + c];
+        fb[f][0] = Op::W1 ? S1[fs + f] : 0.0;
+    }
+    const CT pc = CL::ld(cellsG, cell);
+    const CT pn0 = CL::ld(cellsG, cell + 1), pn1 = CL::ld(cellsG, cell + nx), pn2 = CL::ld(cellsG, cell + nxy);
+    const double vol = sc.V[cell];
+    // ---- cross faces: e < lx*by: z side (b = 0) | < lx*by + lx*bz: y side (a = 0) | x side (off = 0)
+    const int nZ = lx * by, nY = lx * bz, nX = by * bz, nCross = nZ + nY + nX;
+    const int XB = 3 * TB;
+    for (int e = tid; e < nCross; e += TB)
+    {
+        int co, ca, cb;
+        int64_t dOwner, dFace;
+        if (e < nZ) { co = e & (lx - 1); ca = e >> g.shiftL; cb = 0; dOwner = nxy; dFace = -3 * nxy + nx + ny + 2; }
+        else if (e < nZ + nY) { const int e1 = e - nZ; co = e1 & (lx - 1); cb = e1 >> g.shiftL; ca = 0; dOwner = nx; dFace = -3 * int64_t(nx) + 2; }
+        else { const int e2 = e - nZ - nY; ca = e2 & (by - 1); cb = e2 >> g.shiftBy; co = 0; dOwner = 1; dFace = -3; }
+        const int cj = y0 + ca, ck = z0 + cb;
+        const int64_t cc = (x0 + co) + int64_t(nx) * cj + nxy * ck;
+        const int64_t xf = 3 * cc - cj - int64_t(ck) * (nx + ny) + dFace;
+        double xa[W0], xb[W1];
+#pragma unroll
+        for (int c = 0; c < W0; ++c) xa[c] = S0[int64_t(W0) * xf + c];
+        xb[0] = Op::W1 ? S1[xf] : 0.0;
+        const CT po = CL::ld(cellsG, cc - dOwner), pnn = CL::ld(cellsG, cc);
+        sflux[XB + e] = op.fluxv(xa, xb, po, pnn);
+    }
+    sflux[3 * tid + 0] = op.fluxv(fa[0], fb[0], pc, pn0);
+    sflux[3 * tid + 1] = op.fluxv(fa[1], fb[1], pc, pn1);
+    sflux[3 * tid + 2] = op.fluxv(fa[2], fb[2], pc, pn2);
+    __syncthreads();
+    T acc = (mode == FVK_ACC_SCALE) ? VT::ld(out, cell) : VT::zero();
+    acc = VT::sub(acc, b > 0 ? sflux[3 * (tid - lx * by) + 2] : sflux[XB + off + lx * a]);
+    acc = VT::sub(acc, a > 0 ? sflux[3 * (tid - lx) + 1] : sflux[XB + nZ + off + lx * b]);
+    acc = VT::sub(acc, off > 0 ? sflux[3 * (tid - 1)] : sflux[XB + nZ + nY + a + by * b]);
+    acc = VT::add(acc, sflux[3 * tid + 0]);
+    acc = VT::add(acc, sflux[3 * tid + 1]);
+    acc = VT::add(acc, sflux[3 * tid + 2]);
+    double s;
+    if (sc.invVolOnly) s = 1 / vol;
+    else s = (sc.view ? sc.view[cell] * sc.coeff : sc.coeff) / vol;
+    finish<VT>(out, cell, acc, s, mode);
+}
+
 template <class Op, int TB, int MINB, bool XDEFER>
 int launch_brick_n(const fvk_mesh* m, Op op, Scaling sc, double* out, int mode, cudaStream_t st)
 {
     using T = typename Op::V::T;
     static bool optedIn[64] = {false};
+    const FvkBrickGeom& g = m->bp.geom;
     const size_t bytes = size_t(m->bp.maxSlots) * sizeof(T);
-    if (bytes > 200 * 1024 || m->bp.geom.cap != TB) return -1;
+    if (bytes > 200 * 1024 || g.cap != TB) return -1;
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) return -1;
@@ -798,7 +879,17 @@ int launch_brick_n(const fvk_mesh* m, Op op, Scaling sc, double* out, int mode, 
         FVK_CUDA(cudaFuncSetAttribute(k_gather_brick<Op, TB, MINB, XDEFER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         optedIn[dev] = true;
     }
-    k_gather_brick<Op, TB, MINB, XDEFER><<<m->bp.nTiles, TB, bytes, st>>>(op, sc, m->bp, m->nInternalFaces, m->neighbour, out, mode, m->tilePhase);
+    // interior box of a block-structured mesh: the affine kernel (no index arrays); the generic kernel does the shell
+    const bool affine = g.affineBox && m->tilePhase == 0 && !fvk_no_affine();
+    if (affine)
+    {
+        const size_t ab = (size_t(3) * TB + size_t(g.brick[0]) * g.brick[1] + size_t(g.brick[0]) * g.brick[2] + size_t(g.brick[1]) * g.brick[2]) * sizeof(T);
+        k_gather_affine<Op, TB, MINB><<<g.box[0] * g.box[1] * g.box[2], TB, ab, st>>>(op, sc, g, out, mode);
+        if (m->bp.nShell > 0)
+            k_gather_brick<Op, TB, MINB, XDEFER><<<m->bp.nShell, TB, bytes, st>>>(op, sc, m->bp, m->nInternalFaces, m->neighbour, out, mode, 0, m->bp.shellTiles);
+    }
+    else
+        k_gather_brick<Op, TB, MINB, XDEFER><<<m->bp.nTiles, TB, bytes, st>>>(op, sc, m->bp, m->nInternalFaces, m->neighbour, out, mode, m->tilePhase, nullptr);
     FVK_LAUNCH_CHECK();
     return FVK_OK;
 }

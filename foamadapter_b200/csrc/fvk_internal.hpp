@@ -99,6 +99,13 @@ struct FvkBrickGeom
     int32_t shiftL = -1, shiftBy = -1; // log2(lx), log2(by) when powers of two (full tiles use shifts)
     int32_t cap = 0;              // cells per tile the per-cell arrays are strided with (= threads per block)
     int32_t nOwned = 0;
+    // Interior box of tiles (tile coordinates [1, tdim-2] per axis) whose topology the plan PROVED affine: every cell c
+    // has the lower faces {zL, yL, xL}, owns the faces {fs, fs+1, fs+2} with neighbours {c+1, c+nx, c+nx*ny}, no boundary
+    // face, and fs = 3c - j - k(nx+ny), xL = fs-3, yL = fs-3nx+2, zL = fs-3nx*ny+nx+ny+2 (OpenFOAM face order of a
+    // block mesh). k_gather_affine computes those tiles without reading any index array; shellTiles lists the others.
+    int32_t affineBox = 0;
+    int32_t box[3] = {0, 0, 0};   // interior tiles along x, y, z (tdim - 2)
+    int32_t tdimZ = 0;
 };
 #ifdef __CUDACC__
 #define FVK_HD __host__ __device__ __forceinline__
@@ -146,6 +153,8 @@ struct FvkBrickPlan
     FvkBrickRec* recF = nullptr;
     uint2* codes4 = nullptr;
     int4* tileInfo = nullptr;
+    int32_t* shellTiles = nullptr; // tiles outside the affine box (only when geom.affineBox)
+    int32_t nShell = 0;
 };
 
 // Device-side mesh. All arrays are device pointers in reference order.

@@ -50,6 +50,22 @@ extern "C" int fvk_mesh_set_tile_phase(fvk_mesh* m, int phase)
     m->tilePhase = phase;
     return FVK_OK;
 }
+// run-time switch for A/B measurements: 1 = keep the generic brick kernel for the whole mesh
+static int g_noAffine = -1;
+extern "C" int fvk_set_affine(int enabled)
+{
+    g_noAffine = enabled ? 0 : 1;
+    return FVK_OK;
+}
+bool fvk_no_affine()
+{
+    if (g_noAffine < 0)
+    {
+        const char* e = std::getenv("FVK_NO_AFFINE");
+        g_noAffine = (e && *e == '1') ? 1 : 0;
+    }
+    return g_noAffine == 1;
+}
 extern "C" int fvk_set_brick_config(int cellsPerThread, int threads, int minBlocks)
 {
     g_brickCfg[0] = cellsPerThread; g_brickCfg[1] = threads; g_brickCfg[2] = minBlocks;
@@ -233,7 +249,7 @@ extern "C" int fvk_mesh_destroy(fvk_mesh* m)
                     m->gatherEnt, m->gatherPlan, m->rowOffs, m->colIdxs, m->ownerOffset, m->neighbourOffset,
                     m->diagOffset, m->ownStart, m->lowSeg, m->lowFace, m->lowOwner, m->bndCell,
                     m->bndSeg, m->bndFace, m->hasBnd, m->tp.hdr, m->tp.blob, m->bp.hdr, m->bp.rec, m->bp.codes,
-                    m->bp.xFace, m->bp.xOwner, m->bp.xNei, m->bp.bFace, m->bp.bCell, m->bp.recF, m->bp.codes4, m->bp.tileInfo};
+                    m->bp.xFace, m->bp.xOwner, m->bp.xNei, m->bp.bFace, m->bp.bCell, m->bp.recF, m->bp.codes4, m->bp.tileInfo, m->bp.shellTiles};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete m;
@@ -326,6 +342,8 @@ extern "C" int fvk_mesh_create(const fvk_mesh_desc* d, fvk_mesh** out)
                 UP(bp.codes4, bph.codes4.data(), bph.codes4.size());
                 UP(bp.tileInfo, bph.tileInfo.data(), bph.tileInfo.size());
                 bp.geom = bph.geom;
+                if (!bph.shellTiles.empty()) UP(bp.shellTiles, bph.shellTiles.data(), bph.shellTiles.size());
+                bp.nShell = int32_t(bph.shellTiles.size());
                 bp.nTiles = int32_t(bph.hdr.size()); bp.maxSlots = bph.maxSlots; bp.maxCells = bph.maxCells;
             }
         }

@@ -480,6 +480,9 @@ int fvk_probe_streams(int nStreams, const double* const* in_h, int64_t n, double
  * the register allocation aims at; only combinations instantiated in fvk_explicit.cu are honoured (others fall back to
  * the per-cell gather). (0,0,0) restores the defaults. Environment FVK_BRICK_CFG="K,TB,MINB" does the same. */
 int fvk_set_brick_config(int cellsPerThread, int threads, int minBlocks);
+/* A/B switch (roofline harness, parity tests): 0 = the generic brick kernel computes every tile, 1 (default) = tiles of a
+ * block-structured mesh whose topology the plan proved affine are computed by the index-free kernel. */
+int fvk_set_affine(int enabled);
 
 /* Diagnostics, HOST only (no device needed): build the cell->face stencil and the brick plan of the explicit
  * gather kernel for a mesh description and replay the plan exactly as the kernel reads it. info_h[8] =
@@ -489,6 +492,8 @@ int fvk_set_brick_config(int cellsPerThread, int threads, int minBlocks);
  * (its per-cell face order is not [lower | owned, consecutive ids | boundary]); operators then use the per-cell
  * gather. Environment: FVK_BRICK="lx,by,bz" overrides the default 32,4,4 brick. */
 int fvk_brick_plan_selftest(const fvk_mesh_desc* desc_h, int32_t* info_h, int64_t* badCells_h);
+/* HOST only: {affine box proven (0/1), interior tiles along x, y, z, number of shell tiles} of the plan (info_h[5]). */
+int fvk_brick_plan_affine_info(const fvk_mesh_desc* desc_h, int32_t* info_h);
 
 #ifdef __cplusplus
 }

@@ -75,3 +75,20 @@ def test_unsorted_faces_get_no_plan():
     with pytest.raises(FvkError) as e:
         selftest(MeshDesc.from_arrays(a))
     assert e.value.code == 5  # FVK_EUNSUPPORTED: operators keep the per-cell gather
+
+
+def affine_info(desc):
+    info = (C.c_int32 * 5)()
+    check(lib().fvk_brick_plan_affine_info(C.byref(desc.c), info))
+    return list(info)
+
+
+def test_affine_interior_box_is_proven_only_where_it_holds():
+    """k_gather_affine reads no index array: the plan must prove the closed-form topology cell by cell."""
+    a = affine_info(MeshDesc.block(64, 48, 40))      # 16x4x2 bricks: 4 x 12 x 20 tiles -> interior box 2 x 10 x 18
+    assert a[0] == 1 and a[1:4] == [2, 10, 18] and a[4] == 4 * 12 * 20 - 2 * 10 * 18
+    assert affine_info(MeshDesc.block(32, 48, 40))[0] == 0          # only two tiles along x: no interior
+    assert affine_info(MeshDesc.block(20, 20, 1, patches=PATCHES_CAVITY2D))[0] == 0
+    assert affine_info(renumbered_block(12, 11, 10, 3))[0] == 0     # no block structure
+    dec = Decomposition(MeshDesc.block(64, 48, 40), 2, 0)
+    assert affine_info(dec.desc)[0] == 0                             # ghost cells / faceOrder: generic kernel

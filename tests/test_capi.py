@@ -25,3 +25,21 @@ def test_no_cpu_fallback_without_gpu():
     rc = _capi.lib().fvk_mesh_create(C.byref(d.c), C.byref(h))
     assert rc == 2  # FVK_ENODEVICE
     assert b"no CUDA device" in _capi.lib().fvk_last_error() or b"cuda" in _capi.lib().fvk_last_error().lower()
+
+
+def test_new_entry_points_validate_arguments():
+    """Argument checks of the r1e additions run before any device work, so they hold on a CPU-only box."""
+    lib = _capi.lib()
+    assert lib.fvk_mesh_set_tile_phase(None, C.c_int(1)) == 1          # FVK_EINVAL
+    assert lib.fvk_comm_p2p_export(None, None) == 1
+    assert lib.fvk_comm_p2p_connect(None, None) == 1
+    assert lib.fvk_comm_p2p_enabled(None) == 0
+    assert lib.fvk_probe_streams(C.c_int(0), None, C.c_int64(0), None, None) == 1
+    assert lib.fvk_set_brick_config(C.c_int(0), C.c_int(0), C.c_int(0)) == 0
+    h = C.c_void_p()
+    assert lib.fvk_comm_create(C.c_int(0), C.c_int(1), None, C.byref(h)) == 0  # a 1-rank comm needs neither NCCL nor a device
+    blob = (C.c_char * 512)()
+    if not torch.cuda.is_available():
+        assert lib.fvk_comm_p2p_export(h, blob) in (2, 3)  # FVK_ENODEVICE / FVK_ECUDA: no CPU stand-in for the window
+    assert lib.fvk_comm_p2p_enabled(h) == 0
+    lib.fvk_comm_destroy(h)

@@ -145,6 +145,47 @@ def test_laplacian(case, vec, variant):
 
 
 @pytest.mark.parametrize("vec", [False, True])
+def test_affine_interior_kernel_equals_generic_kernel(vec):
+    """A/B of the index-free kernel (interior box of a block mesh) against the generic brick kernel: every operator and
+    accumulation mode, bit for bit; and the plan really has an affine box for this mesh."""
+    import ctypes as C
+    d = M.MeshDesc.block(64, 24, 12, 1.0, 0.5, 0.2)
+    info = (C.c_int32 * 5)()
+    _capi.check(_capi.lib().fvk_brick_plan_affine_info(C.byref(d.c), info))
+    assert info[0] == 1 and info[1] * info[2] * info[3] > 0
+    gm, om = M.UnstructuredMesh(d), OMesh.from_desc(d)
+    phi, phib, flux, view = _fields(om, 11, vec)
+    res = {}
+    try:
+        for affine in (1, 0):
+            _capi.lib().fvk_set_affine(affine)
+            r = []
+            for scheme in (0, 1):
+                for mode, coeff, vw in ((ops.SET, 1.0, None), (ops.ACC_SCALE, -0.5, dev(view)), (ops.ADD, 2.0, None)):
+                    out = dev(np.random.default_rng(5).uniform(-1, 1, phi.shape))
+                    ops.div(gm, dev(flux), dev(phi), dev(phib), out, scheme, coeff, vw, mode)
+                    r.append(host(out).copy())
+            out = dev(np.random.default_rng(6).uniform(-1, 1, phi.shape))
+            ops.laplacian(gm, dev(phi), dev(phib), out, 0.7, dev(view), ops.ACC_SCALE)
+            r.append(host(out).copy())
+            if not vec:
+                o3 = torch.empty((om.nC, 3), dtype=torch.float64, device="cuda")
+                ops.grad(gm, dev(phi), dev(phib), o3, ops.SET)
+                r.append(host(o3).copy())
+            fl = np.random.default_rng(7).uniform(-1, 1, (om.nF, 3) if vec else om.nF)
+            out = torch.zeros_like(dev(phi))
+            ops.surface_integrate(gm, dev(fl), out)
+            r.append(host(out).copy())
+            res[affine] = r
+    finally:
+        _capi.lib().fvk_set_affine(1)
+    assert len(res[0]) == len(res[1])
+    for x, y in zip(res[0], res[1]):
+        assert np.array_equal(x, y)
+    assert np.array_equal(res[1][0], om.div(flux, phi, phib, 0))
+
+
+@pytest.mark.parametrize("vec", [False, True])
 def test_surface_integrate(case, vec):
     name, d, gm, om = case
     rng = np.random.default_rng(4)
