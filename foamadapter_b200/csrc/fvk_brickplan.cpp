@@ -393,44 +393,63 @@ bool fvk_build_brick_plan(const fvk_mesh_desc* d, const FvkStencilHost& st, FvkB
         if (h.nx >= 65536 || h.nb >= 32768) geomBad |= 2;
     }
     if (geomBad) { *reason = "tile geometry does not reproduce the tiling"; return false; }
-    // ---- affine interior box: prove, cell by cell, the closed-form topology k_gather_affine assumes
+    // ---- affine topology: prove, cell by cell, the closed form k_gather_affine assumes (see FvkBrickGeom)
     static const bool noAffine = [] { const char* e = std::getenv("FVK_NO_AFFINE"); return e && *e == '1'; }();
     g.tdimZ = structured ? (g.dims[2] + g.brick[2] - 1) / g.brick[2] : 0;
-    if (!noAffine && structured && nOwned == nC && !d->faceOrder && g.shiftL >= 0 && g.shiftBy >= 0 && g.tdim[0] > 2 && g.tdim[1] > 2
-        && g.tdimZ > 2 && g.brick[0] * g.brick[1] * g.brick[2] == g.cap)
+    g.maxCross = g.brick[0] * g.brick[1] + g.brick[0] * g.brick[2] + g.brick[1] * g.brick[2];
+    if (!noAffine && structured && g.dims[0] >= 3 && g.dims[1] >= 3 && g.dims[2] >= 3 && int64_t(3) * nOwned + 8 < (int64_t(1) << 31))
     {
-        const int64_t nx = g.dims[0], ny = g.dims[1], nxy = nx * ny;
-        int bad = 0;
+        const int64_t nx = g.dims[0], ny = g.dims[1], nz = g.dims[2], nxy = nx * ny;
+        for (int combo = 0; combo < 8 && !g.affine; ++combo)
+        {
+            const int64_t tx = combo & 1, ty = (combo >> 1) & 1, tz = (combo >> 2) & 1;
+            auto fsOf = [&](int64_t c) {
+                const int64_t i = c % nx, j = (c / nx) % ny, k = c / nxy;
+                return 3 * c - tx * (j + ny * k) - ty * (k * nx + (j == ny - 1 ? i : 0)) - tz * (k == nz - 1 ? i + nx * j : 0);
+            };
+            int bad = 0;
 #pragma omp parallel for schedule(static) reduction(| : bad)
-        for (int32_t t = 0; t < nT; ++t)
-        {
-            const int32_t ix = t % g.tdim[0], q = t / g.tdim[0], iy = q % g.tdim[1], iz = q / g.tdim[1];
-            if (ix < 1 || ix > g.tdim[0] - 2 || iy < 1 || iy > g.tdim[1] - 2 || iz < 1 || iz > g.tdimZ - 2) continue;
-            const FvkBrickHdr& h = out.hdr[t];
-            if (h.nb != 0 || h.nc != g.cap) { bad |= 1; continue; }
-            for_tile_cells(tiles[t], [&](int32_t c, int32_t) {
-                const int64_t j = (c / nx) % ny, k = c / nxy;
-                const int64_t fs = 3 * int64_t(c) - j - k * (nx + ny);
-                const int64_t want[6] = {((fs - 3 * nxy + nx + ny + 2) << 1) | 1, ((fs - 3 * nx + 2) << 1) | 1, ((fs - 3) << 1) | 1,
-                                         fs << 1, (fs + 1) << 1, (fs + 2) << 1};
-                if (seg[size_t(c) + 1] - seg[c] != 6) { bad |= 1; return; }
-                for (int e = 0; e < 6; ++e)
-                    if (ent[seg[c] + e] != want[e]) { bad |= 1; return; }
-                if (nei[fs] != c + 1 || nei[fs + 1] != c + nx || nei[fs + 2] != c + nxy || own[fs] != c || own[fs + 1] != c || own[fs + 2] != c
-                    || own[fs - 3] != c - 1 || own[fs - 3 * nx + 2] != c - nx || own[fs - 3 * nxy + nx + ny + 2] != c - nxy)
-                    bad |= 1;
-            });
-        }
-        if (!bad)
-        {
-            g.affineBox = 1;
-            g.box[0] = g.tdim[0] - 2; g.box[1] = g.tdim[1] - 2; g.box[2] = g.tdimZ - 2;
-            for (int32_t t = 0; t < nT; ++t)
+            for (int32_t c = 0; c < nOwned; ++c)
             {
-                const int32_t ix = t % g.tdim[0], q = t / g.tdim[0], iy = q % g.tdim[1], iz = q / g.tdim[1];
-                if (ix < 1 || ix > g.tdim[0] - 2 || iy < 1 || iy > g.tdim[1] - 2 || iz < 1 || iz > g.tdimZ - 2) out.shellTiles.push_back(t);
+                if (bad) continue;
+                const int64_t i = c % nx, j = (c / nx) % ny, k = c / nxy;
+                const bool hasX = !(tx && i == nx - 1), hasY = !(ty && j == ny - 1), hasZ = !(tz && k == nz - 1);
+                const int64_t fs = fsOf(c), nOwn = int64_t(hasX) + hasY + hasZ;
+                if (fs < 0 || fs + nOwn > nI) { bad |= 1; continue; }
+                for (int64_t q = 0; q < nOwn; ++q)
+                    if (own[fs + q] != c) bad |= 1;
+                if ((fs + nOwn < nI && own[fs + nOwn] == c) || (fs > 0 && own[fs - 1] == c)) bad |= 1;
+                int64_t q = 0;
+                if (hasX) { const int32_t n = nei[fs + q++]; if (i < nx - 1 ? n != c + 1 : n < nOwned) bad |= 1; }
+                if (hasY) { const int32_t n = nei[fs + q++]; if (j < ny - 1 ? n != c + nx : n < nOwned) bad |= 1; }
+                if (hasZ) { const int32_t n = nei[fs + q++]; if (k < nz - 1 ? n != c + nxy : n < nOwned) bad |= 1; }
+                if (bad) continue;
+                if (i > 0 && i < nx - 1 && j > 0 && j < ny - 1 && k > 0 && k < nz - 1)
+                {
+                    const int64_t want[6] = {((fsOf(c - nxy) + 2) << 1) | 1, ((fsOf(c - nx) + 1) << 1) | 1, (fsOf(c - 1) << 1) | 1,
+                                             fs << 1, (fs + 1) << 1, (fs + 2) << 1};
+                    if (seg[size_t(c) + 1] - seg[c] != 6) { bad |= 1; continue; }
+                    for (int e = 0; e < 6; ++e)
+                        if (ent[seg[c] + e] != want[e]) bad |= 1;
+                    // the simplified forms the kernel uses
+                    const int64_t f0 = 3 * int64_t(c) - tx * (j + ny * k) - ty * k * nx;
+                    if (f0 != fs || fsOf(c - 1) != f0 - 3 || fsOf(c - nx) + 1 != f0 - 3 * nx + tx + 1
+                        || fsOf(c - nxy) + 2 != f0 - 3 * nxy + tx * ny + ty * nx + 2)
+                        bad |= 1;
+                }
+            }
+            if (!bad)
+            {
+                g.affine = 1;
+                g.tUp[0] = int32_t(tx); g.tUp[1] = int32_t(ty); g.tUp[2] = int32_t(tz);
             }
         }
+        if (g.affine)
+            for (int32_t c = 0; c < nOwned; ++c)
+            {
+                const int64_t i = c % nx, j = (c / nx) % ny, k = c / nxy;
+                if (!(i > 0 && i < nx - 1 && j > 0 && j < ny - 1 && k > 0 && k < nz - 1)) out.irrCells.push_back(c);
+            }
     }
     return true;
 }
@@ -549,7 +568,7 @@ extern "C" int fvk_brick_plan_selftest(const fvk_mesh_desc* d, int32_t* info /* 
     return FVK_OK;
 }
 
-// diagnostics (host only): did the plan prove an affine interior box? info[4] = {affineBox, box tiles x, y, z}, nShell
+// diagnostics (host only): did the plan prove the affine topology? info[5] = {affine, tUp x, y, z, irregular cells}
 extern "C" int fvk_brick_plan_affine_info(const fvk_mesh_desc* d, int32_t* info /* [5] */)
 {
     if (!d || !info) return fvk_fail(FVK_EINVAL, "fvk_brick_plan_affine_info: null");
@@ -558,7 +577,7 @@ extern "C" int fvk_brick_plan_affine_info(const fvk_mesh_desc* d, int32_t* info 
     FvkBrickPlanHost bp;
     const char* why = "";
     if (!fvk_build_brick_plan(d, st, bp, &why)) return fvk_fail(FVK_EUNSUPPORTED, "brick plan: %s", why);
-    info[0] = bp.geom.affineBox; info[1] = bp.geom.box[0]; info[2] = bp.geom.box[1]; info[3] = bp.geom.box[2];
-    info[4] = int32_t(bp.shellTiles.size());
+    info[0] = bp.geom.affine; info[1] = bp.geom.tUp[0]; info[2] = bp.geom.tUp[1]; info[3] = bp.geom.tUp[2];
+    info[4] = int32_t(bp.irrCells.size());
     return FVK_OK;
 }

@@ -28,7 +28,7 @@ struct FvkBrickPlanHost
     std::vector<FvkBrickRec> recF;
     std::vector<uint2> codes4;
     std::vector<int4> tileInfo;
-    std::vector<int32_t> shellTiles;
+    std::vector<int32_t> irrCells;
     int32_t dims[3] = {0, 0, 0};  // detected block-structured numbering (0,0,0: none -> runs of consecutive cells)
     int32_t brick[3] = {0, 0, 0}; // brick shape used
 };

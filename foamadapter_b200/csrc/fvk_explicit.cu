@@ -262,15 +262,13 @@ __device__ __forceinline__ void finish(double* __restrict__ out, int c, typename
 // NOTE: res[c] *= s in the reference is (res * s); mul(s, acc) is the same product (commutative).
 
 // ---- variant 0 (default): unified sorted stencil, one face in flight per thread ------------------------------------------------------------
+// one cell: walk its stencil in ascending face id (the Serial executor's accumulation order)
 template <class Op>
-__global__ void __launch_bounds__(256)
-k_gather_stencil(Op op, Scaling sc, int nC, int nI, const int* __restrict__ seg,
-                 const int* __restrict__ ent, const int* __restrict__ owner,
-                 const int* __restrict__ neighbour, double* __restrict__ out, int mode)
+__device__ __forceinline__ void gather_cell(const Op& op, const Scaling& sc, int c, int nI, const int* __restrict__ seg,
+                                            const int* __restrict__ ent, const int* __restrict__ owner,
+                                            const int* __restrict__ neighbour, double* __restrict__ out, int mode)
 {
     using VT = typename Op::V;
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= nC) return;
     typename VT::T acc = (mode == FVK_ACC_SCALE) ? VT::ld(out, c) : VT::zero();
     const int e1 = seg[c + 1];
     for (int e = seg[c]; e < e1; ++e)
@@ -290,6 +288,18 @@ k_gather_stencil(Op op, Scaling sc, int nC, int nI, const int* __restrict__ seg,
         }
     }
     finish<VT>(out, c, acc, sc.at(c), mode);
+}
+
+template <class Op>
+__global__ void __launch_bounds__(256)
+k_gather_stencil(Op op, Scaling sc, int nC, int nI, const int* __restrict__ seg,
+                 const int* __restrict__ ent, const int* __restrict__ owner,
+                 const int* __restrict__ neighbour, double* __restrict__ out, int mode, const int* __restrict__ cellList = nullptr)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nC) return;
+    const int c = cellList ? cellList[idx] : idx; // list: the irregular cells next to k_gather_affine (nC = list length)
+    gather_cell(op, sc, c, nI, seg, ent, owner, neighbour, out, mode);
 }
 
 // ---- variants 1-4: packed plan, U faces in flight per thread -----------------------------------
@@ -783,17 +793,33 @@ k_gather_brick(Op op, Scaling sc, FvkBrickPlan bp, int nI, const int* __restrict
     finish<VT>(out, cell, acc, s, mode);
 }
 
-// ---- affine kernel: the interior box of a block-structured mesh --------------------------------------------------
-// For the tiles whose topology the plan proved to follow the closed form of FvkBrickGeom (fvk_brickplan.cpp checks every
-// cell), NO index array is read: cell ids, face ids, neighbours and slots are arithmetic, so every load of the kernel is
-// issued in the first instruction window (one memory round trip per block instead of three dependent ones) and the
-// owner / neighbour labels (24 B per face of the algorithmic traffic) stay in DRAM. Arithmetic, summation order
-// [zL, yL, xL | x, y, z] and results are those of the generic kernel, bit for bit. One block per tile, one cell per
-// thread; the faces on the tile's three lower sides ("cross" faces) are evaluated by a thread each.
+// ---- affine kernel: block-structured meshes whose topology the plan proved (FvkBrickGeom) ----------------------------
+// NO index array is read: cell ids, face ids, neighbours and slots are arithmetic, so every load of the kernel is issued
+// in the first instruction window (one memory round trip per block instead of three dependent ones) and the owner /
+// neighbour labels (24 B per face of the algorithmic traffic) stay in DRAM. One block per tile, one cell per thread.
+// Every cell that owns all three upper faces evaluates them once into shared-memory slots; the faces on the tile's three
+// lower sides ("cross" faces) are evaluated by a thread each; REGULAR cells (not in the outermost layer of the block) then
+// add their six slots in the reference's order [zL, yL, xL | x, y, z] -- arithmetic and results are those of the generic
+// kernels, bit for bit. The irregular cells (boundary / processor-cut layers, a few per cent) are written by
+// k_gather_stencil over the plan's cell list. The regular cells never read a ghost cell: this kernel IS the interior
+// phase of the halo overlap.
+struct AffineTail
+{
+    int nBlocks, nIrr, nI; // nBlocks = 0: tiles only
+    const int *irrCells, *seg, *ent, *owner, *neighbour;
+};
 template <class Op, int TB, int MINB>
 __global__ void __launch_bounds__(TB, MINB)
-k_gather_affine(Op op, Scaling sc, FvkBrickGeom g, double* __restrict__ out, int mode)
+k_gather_affine(Op op, Scaling sc, FvkBrickGeom g, double* __restrict__ out, int mode, AffineTail tail)
 {
+    if (int(blockIdx.x) < tail.nBlocks)
+    { // the first blocks of the grid: the irregular cells, per-cell gather (same launch; latency-bound, so they start
+      // first and run beside the streaming tiles)
+        const int idx = blockIdx.x * TB + threadIdx.x;
+        if (idx < tail.nIrr) gather_cell(op, sc, tail.irrCells[idx], tail.nI, tail.seg, tail.ent, tail.owner, tail.neighbour, out, mode);
+        return;
+    }
+    const int tileId = blockIdx.x - tail.nBlocks;
     using VT = typename Op::V;
     using T = typename VT::T;
     using CL = CellLd<typename Op::CV>;
@@ -805,40 +831,59 @@ k_gather_affine(Op op, Scaling sc, FvkBrickGeom g, double* __restrict__ out, int
     const double* __restrict__ S1 = op.s1();
     const double* __restrict__ cellsG = op.cells();
     const int tid = threadIdx.x;
-    const int lx = g.brick[0], by = g.brick[1], bz = g.brick[2], nx = g.dims[0], ny = g.dims[1];
+    const int nx = g.dims[0], ny = g.dims[1], nz = g.dims[2];
     const int64_t nxy = int64_t(nx) * ny;
-    // tile of the interior box -> first cell
-    const int bxi = blockIdx.x % g.box[0], q = blockIdx.x / g.box[0], byi = q % g.box[1], bzi = q / g.box[1];
-    const int x0 = (bxi + 1) * lx, y0 = (byi + 1) * by, z0 = (bzi + 1) * bz;
-    const int off = tid & (lx - 1), r = tid >> g.shiftL, a = r & (by - 1), b = r >> g.shiftBy;
+    const int tx = g.tUp[0], ty = g.tUp[1];
+    // tile -> origin and extent (edge tiles may be ragged)
+    const int ix = tileId % g.tdim[0], q = tileId / g.tdim[0], iy = q % g.tdim[1], iz = q / g.tdim[1];
+    const int x0 = ix * g.brick[0], y0 = iy * g.brick[1], z0 = iz * g.brick[2];
+    const int rl = min(g.brick[0], nx - x0), ry = min(g.brick[1], ny - y0), rz = min(g.brick[2], nz - z0);
+    const bool full = rl == g.brick[0] && ry == g.brick[1] && g.shiftL >= 0 && g.shiftBy >= 0;
+    const int nc = rl * ry * rz;
+    int off, a, b;
+    if (full) { off = tid & (rl - 1); const int r = tid >> g.shiftL; a = r & (ry - 1); b = r >> g.shiftBy; }
+    else { off = tid % rl; const int r = tid / rl; a = r % ry; b = r / ry; }
+    const bool valid = tid < nc;
     const int i = x0 + off, j = y0 + a, k = z0 + b;
+    // owns three faces with owned neighbours / is a regular cell
+    const bool upper = valid && i < nx - 1 && j < ny - 1 && k < nz - 1;
+    const bool regular = upper && i > 0 && j > 0 && k > 0;
     const int64_t cell = i + int64_t(nx) * j + nxy * k;
-    const int64_t fs = 3 * cell - j - int64_t(k) * (nx + ny);
+    const int64_t fs = 3 * cell - int64_t(tx) * (j + int64_t(ny) * k) - int64_t(ty) * k * nx;
     // ---- every load of the owned faces
     double fa[3][W0], fb[3][W1];
-#pragma unroll
-    for (int f = 0; f < 3; ++f)
+    CT pc = CL::ld(cellsG, 0), pn0 = pc, pn1 = pc, pn2 = pc;
+    double vol = 1.0;
+    if (upper)
     {
 #pragma unroll
-        for (int c = 0; c < W0; ++c) fa[f][c] = S0[int64_t(W0) * (fs + f) + c];
-        fb[f][0] = Op::W1 ? S1[fs + f] : 0.0;
+        for (int f = 0; f < 3; ++f)
+        {
+#pragma unroll
+            for (int c = 0; c < W0; ++c) fa[f][c] = S0[int64_t(W0) * (fs + f) + c];
+            fb[f][0] = Op::W1 ? S1[fs + f] : 0.0;
+        }
+        pc = CL::ld(cellsG, cell);
+        pn0 = CL::ld(cellsG, cell + 1); pn1 = CL::ld(cellsG, cell + nx); pn2 = CL::ld(cellsG, cell + nxy);
+        vol = sc.V[cell];
     }
-    const CT pc = CL::ld(cellsG, cell);
-    const CT pn0 = CL::ld(cellsG, cell + 1), pn1 = CL::ld(cellsG, cell + nx), pn2 = CL::ld(cellsG, cell + nxy);
-    const double vol = sc.V[cell];
-    // ---- cross faces: e < lx*by: z side (b = 0) | < lx*by + lx*bz: y side (a = 0) | x side (off = 0)
-    const int nZ = lx * by, nY = lx * bz, nX = by * bz, nCross = nZ + nY + nX;
+    // ---- cross faces: e < nZ: z side (b = 0) | < nZ + nY: y side (a = 0) | x side (off = 0); only for regular consumers
+    const int nZ = rl * ry, nY = rl * rz, nX = ry * rz, nCross = nZ + nY + nX;
     const int XB = 3 * TB;
     for (int e = tid; e < nCross; e += TB)
     {
-        int co, ca, cb;
+        int co, ca, cb, e1;
         int64_t dOwner, dFace;
-        if (e < nZ) { co = e & (lx - 1); ca = e >> g.shiftL; cb = 0; dOwner = nxy; dFace = -3 * nxy + nx + ny + 2; }
-        else if (e < nZ + nY) { const int e1 = e - nZ; co = e1 & (lx - 1); cb = e1 >> g.shiftL; ca = 0; dOwner = nx; dFace = -3 * int64_t(nx) + 2; }
-        else { const int e2 = e - nZ - nY; ca = e2 & (by - 1); cb = e2 >> g.shiftBy; co = 0; dOwner = 1; dFace = -3; }
-        const int cj = y0 + ca, ck = z0 + cb;
-        const int64_t cc = (x0 + co) + int64_t(nx) * cj + nxy * ck;
-        const int64_t xf = 3 * cc - cj - int64_t(ck) * (nx + ny) + dFace;
+        if (e < nZ) { e1 = e; cb = 0; dOwner = nxy; dFace = -3 * nxy + int64_t(tx) * ny + int64_t(ty) * nx + 2; }
+        else if (e < nZ + nY) { e1 = e - nZ; ca = 0; dOwner = nx; dFace = -3 * int64_t(nx) + tx + 1; }
+        else { e1 = e - nZ - nY; co = 0; dOwner = 1; dFace = -3; }
+        if (e < nZ) { if (full) { co = e1 & (rl - 1); ca = e1 >> g.shiftL; } else { co = e1 % rl; ca = e1 / rl; } }
+        else if (e < nZ + nY) { if (full) { co = e1 & (rl - 1); cb = e1 >> g.shiftL; } else { co = e1 % rl; cb = e1 / rl; } }
+        else { if (full) { ca = e1 & (ry - 1); cb = e1 >> g.shiftBy; } else { ca = e1 % ry; cb = e1 / ry; } }
+        const int ci = x0 + co, cj = y0 + ca, ck = z0 + cb;
+        if (!(ci > 0 && ci < nx - 1 && cj > 0 && cj < ny - 1 && ck > 0 && ck < nz - 1)) continue; // consumer not regular
+        const int64_t cc = ci + int64_t(nx) * cj + nxy * ck;
+        const int64_t xf = 3 * cc - int64_t(tx) * (cj + int64_t(ny) * ck) - int64_t(ty) * ck * nx + dFace;
         double xa[W0], xb[W1];
 #pragma unroll
         for (int c = 0; c < W0; ++c) xa[c] = S0[int64_t(W0) * xf + c];
@@ -846,14 +891,18 @@ k_gather_affine(Op op, Scaling sc, FvkBrickGeom g, double* __restrict__ out, int
         const CT po = CL::ld(cellsG, cc - dOwner), pnn = CL::ld(cellsG, cc);
         sflux[XB + e] = op.fluxv(xa, xb, po, pnn);
     }
-    sflux[3 * tid + 0] = op.fluxv(fa[0], fb[0], pc, pn0);
-    sflux[3 * tid + 1] = op.fluxv(fa[1], fb[1], pc, pn1);
-    sflux[3 * tid + 2] = op.fluxv(fa[2], fb[2], pc, pn2);
+    if (upper)
+    {
+        sflux[3 * tid + 0] = op.fluxv(fa[0], fb[0], pc, pn0);
+        sflux[3 * tid + 1] = op.fluxv(fa[1], fb[1], pc, pn1);
+        sflux[3 * tid + 2] = op.fluxv(fa[2], fb[2], pc, pn2);
+    }
     __syncthreads();
+    if (!regular) return;
     T acc = (mode == FVK_ACC_SCALE) ? VT::ld(out, cell) : VT::zero();
-    acc = VT::sub(acc, b > 0 ? sflux[3 * (tid - lx * by) + 2] : sflux[XB + off + lx * a]);
-    acc = VT::sub(acc, a > 0 ? sflux[3 * (tid - lx) + 1] : sflux[XB + nZ + off + lx * b]);
-    acc = VT::sub(acc, off > 0 ? sflux[3 * (tid - 1)] : sflux[XB + nZ + nY + a + by * b]);
+    acc = VT::sub(acc, b > 0 ? sflux[3 * (tid - rl * ry) + 2] : sflux[XB + off + rl * a]);
+    acc = VT::sub(acc, a > 0 ? sflux[3 * (tid - rl) + 1] : sflux[XB + nZ + off + rl * b]);
+    acc = VT::sub(acc, off > 0 ? sflux[3 * (tid - 1)] : sflux[XB + nZ + nY + a + ry * b]);
     acc = VT::add(acc, sflux[3 * tid + 0]);
     acc = VT::add(acc, sflux[3 * tid + 1]);
     acc = VT::add(acc, sflux[3 * tid + 2]);
@@ -879,20 +928,30 @@ int launch_brick_n(const fvk_mesh* m, Op op, Scaling sc, double* out, int mode, 
         FVK_CUDA(cudaFuncSetAttribute(k_gather_brick<Op, TB, MINB, XDEFER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         optedIn[dev] = true;
     }
-    // interior box of a block-structured mesh: the affine kernel (no index arrays); the generic kernel does the shell
-    const bool affine = g.affineBox && m->tilePhase == 0 && !fvk_no_affine();
-    if (affine)
-    {
-        const size_t ab = (size_t(3) * TB + size_t(g.brick[0]) * g.brick[1] + size_t(g.brick[0]) * g.brick[2] + size_t(g.brick[1]) * g.brick[2]) * sizeof(T);
-        k_gather_affine<Op, TB, MINB><<<g.box[0] * g.box[1] * g.box[2], TB, ab, st>>>(op, sc, g, out, mode);
-        if (m->bp.nShell > 0)
-            k_gather_brick<Op, TB, MINB, XDEFER><<<m->bp.nShell, TB, bytes, st>>>(op, sc, m->bp, m->nInternalFaces, m->neighbour, out, mode, 0, m->bp.shellTiles);
-    }
-    else
-        k_gather_brick<Op, TB, MINB, XDEFER><<<m->bp.nTiles, TB, bytes, st>>>(op, sc, m->bp, m->nInternalFaces, m->neighbour, out, mode, m->tilePhase, nullptr);
+    k_gather_brick<Op, TB, MINB, XDEFER><<<m->bp.nTiles, TB, bytes, st>>>(op, sc, m->bp, m->nInternalFaces, m->neighbour, out, mode, m->tilePhase, nullptr);
     FVK_LAUNCH_CHECK();
     return FVK_OK;
 }
+// block-structured mesh with proven topology: the affine kernel writes the regular cells (= the interior phase of the halo
+// overlap), the per-cell gather over the plan's list the irregular boundary / cut layers (= the halo phase)
+template <class Op, int TB, int MINB>
+int launch_affine_n(const fvk_mesh* m, Op op, Scaling sc, double* out, int mode, cudaStream_t st)
+{
+    using T = typename Op::V::T;
+    const FvkBrickGeom& g = m->bp.geom;
+    const size_t ab = (size_t(3) * TB + size_t(g.maxCross)) * sizeof(T);
+    if (ab > 48 * 1024) return -1;
+    const int listBlocks = m->tilePhase == 0 ? (m->bp.nIrr + TB - 1) / TB : 0;
+    AffineTail tail {listBlocks, m->bp.nIrr, m->nInternalFaces, m->bp.irrCells, m->stencilSeg, m->gatherEnt, m->owner, m->neighbour};
+    if (m->tilePhase != 2) // phase 0: one launch, list blocks + tiles
+        k_gather_affine<Op, TB, MINB><<<listBlocks + m->bp.nTiles, TB, ab, st>>>(op, sc, g, out, mode, tail);
+    else if (m->bp.nIrr > 0)
+        k_gather_stencil<Op><<<(m->bp.nIrr + 255) / 256, 256, 0, st>>>(op, sc, m->bp.nIrr, m->nInternalFaces, m->stencilSeg, m->gatherEnt, m->owner,
+                                                                        m->neighbour, out, mode, m->bp.irrCells);
+    FVK_LAUNCH_CHECK();
+    return FVK_OK;
+}
+
 // kernel configuration: threads per block TB (= max cells per tile), resident blocks the register allocation aims at.
 // fvk_set_brick_config / FVK_BRICK_CFG="1,TB,MINB" override for sweeps (instantiated combinations only).
 template <class Op>
@@ -901,11 +960,25 @@ int launch_brick(const fvk_mesh* m, Op op, Scaling sc, double* out, int mode, cu
     // resident blocks aimed at = the highest occupancy ptxas reaches WITHOUT spilling (spills cost more than the extra
     // warps bring, r2 sweeps): 40 registers only fit the two-operand scalar laplacian and surfaceIntegrate
     constexpr bool light = sizeof(typename Op::V::T) == 8 && Op::W0 == 1 && !Op::NEEDS_BLEND;
+    constexpr bool wide = sizeof(typename Op::V::T) > 8 || Op::W0 > 1;
     const int TB = m->bp.geom.cap; // threads per block = the stride of the plan's per-cell arrays
     int MINB = (light ? 6 : 4) * 256 / TB;
     int cfg[3];
     if (fvk_brick_config(cfg) && cfg[1] == TB) MINB = cfg[2];
     const bool xdefer = fvk_brick_config(cfg) ? cfg[0] == 2 : false; // config[0]: 1 = cross operands early, 2 = deferred
+    if (m->bp.geom.affine && !fvk_no_affine())
+    {
+        // the affine kernel keeps all operands of a cell in flight: spill-free register budgets (ptxas -v): 40 for the
+        // scalar surfaceIntegrate, 64 for the scalar operators, 80 for Vec3 operands
+        constexpr bool tiny = sizeof(typename Op::V::T) == 8 && Op::W0 == 1 && Op::W1 == 0 && !Op::NEEDS_BLEND;
+        int MA = (tiny ? 6 : (wide ? 3 : 4)) * 256 / TB;
+        if (fvk_brick_config(cfg) && cfg[1] == TB && cfg[0] == 3) MA = cfg[2]; // config[0] == 3: override for the affine kernel
+#define FVK_AFFINE_CASE(tb, mb) if (TB == tb && MA == mb) { const int rc = launch_affine_n<Op, tb, mb>(m, op, sc, out, mode, st); if (rc >= 0) return rc; }
+        FVK_AFFINE_CASE(128, 6) FVK_AFFINE_CASE(128, 8) FVK_AFFINE_CASE(128, 12)
+        FVK_AFFINE_CASE(256, 3) FVK_AFFINE_CASE(256, 4) FVK_AFFINE_CASE(256, 6)
+        FVK_AFFINE_CASE(512, 2) FVK_AFFINE_CASE(512, 3)
+#undef FVK_AFFINE_CASE
+    }
 #define FVK_BRICK_CASE(tb, mb)                                                                                          \
     if (TB == tb && MINB == mb)                                                                                         \
         return xdefer ? launch_brick_n<Op, tb, mb, true>(m, op, sc, out, mode, st) : launch_brick_n<Op, tb, mb, false>(m, op, sc, out, mode, st)

@@ -99,13 +99,16 @@ struct FvkBrickGeom
     int32_t shiftL = -1, shiftBy = -1; // log2(lx), log2(by) when powers of two (full tiles use shifts)
     int32_t cap = 0;              // cells per tile the per-cell arrays are strided with (= threads per block)
     int32_t nOwned = 0;
-    // Interior box of tiles (tile coordinates [1, tdim-2] per axis) whose topology the plan PROVED affine: every cell c
-    // has the lower faces {zL, yL, xL}, owns the faces {fs, fs+1, fs+2} with neighbours {c+1, c+nx, c+nx*ny}, no boundary
-    // face, and fs = 3c - j - k(nx+ny), xL = fs-3, yL = fs-3nx+2, zL = fs-3nx*ny+nx+ny+2 (OpenFOAM face order of a
-    // block mesh). k_gather_affine computes those tiles without reading any index array; shellTiles lists the others.
-    int32_t affineBox = 0;
-    int32_t box[3] = {0, 0, 0};   // interior tiles along x, y, z (tdim - 2)
+    // Block-structured topology PROVEN by the plan (fvk_brickplan.cpp checks every cell): cell c = i + nx(j + ny k) owns
+    // the consecutive faces fs(c).. towards +x, +y, +z (those that exist), fs(c) = 3c - tx(j + ny k) - ty k nx for every
+    // cell with j < ny-1 and k < nz-1 (t* = 1 where the block's upper side is a true boundary, 0 where it is a processor
+    // cut), neighbours c+1, c+nx, c+nx*ny, and a REGULAR cell (0 < i < nx-1, ...) has exactly the stencil
+    // [zL, yL, xL | x, y, z] with xL = fs(c-1), yL = fs(c-nx)+1, zL = fs(c-nx*ny)+2. k_gather_affine computes the regular
+    // cells without reading any index array; the irregular ones (boundary / cut layers, irrCells) use the per-cell gather.
+    int32_t affine = 0;
+    int32_t tUp[3] = {1, 1, 1};
     int32_t tdimZ = 0;
+    int32_t maxCross = 0; // cross faces of a full tile: lx*by + lx*bz + by*bz
 };
 #ifdef __CUDACC__
 #define FVK_HD __host__ __device__ __forceinline__
@@ -153,8 +156,8 @@ struct FvkBrickPlan
     FvkBrickRec* recF = nullptr;
     uint2* codes4 = nullptr;
     int4* tileInfo = nullptr;
-    int32_t* shellTiles = nullptr; // tiles outside the affine box (only when geom.affineBox)
-    int32_t nShell = 0;
+    int32_t* irrCells = nullptr; // owned cells that are not regular (only when geom.affine), ascending
+    int32_t nIrr = 0;
 };
 
 // Device-side mesh. All arrays are device pointers in reference order.

@@ -249,7 +249,7 @@ extern "C" int fvk_mesh_destroy(fvk_mesh* m)
                     m->gatherEnt, m->gatherPlan, m->rowOffs, m->colIdxs, m->ownerOffset, m->neighbourOffset,
                     m->diagOffset, m->ownStart, m->lowSeg, m->lowFace, m->lowOwner, m->bndCell,
                     m->bndSeg, m->bndFace, m->hasBnd, m->tp.hdr, m->tp.blob, m->bp.hdr, m->bp.rec, m->bp.codes,
-                    m->bp.xFace, m->bp.xOwner, m->bp.xNei, m->bp.bFace, m->bp.bCell, m->bp.recF, m->bp.codes4, m->bp.tileInfo, m->bp.shellTiles};
+                    m->bp.xFace, m->bp.xOwner, m->bp.xNei, m->bp.bFace, m->bp.bCell, m->bp.recF, m->bp.codes4, m->bp.tileInfo, m->bp.irrCells};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete m;
@@ -342,8 +342,8 @@ extern "C" int fvk_mesh_create(const fvk_mesh_desc* d, fvk_mesh** out)
                 UP(bp.codes4, bph.codes4.data(), bph.codes4.size());
                 UP(bp.tileInfo, bph.tileInfo.data(), bph.tileInfo.size());
                 bp.geom = bph.geom;
-                if (!bph.shellTiles.empty()) UP(bp.shellTiles, bph.shellTiles.data(), bph.shellTiles.size());
-                bp.nShell = int32_t(bph.shellTiles.size());
+                if (!bph.irrCells.empty()) UP(bp.irrCells, bph.irrCells.data(), bph.irrCells.size());
+                bp.nIrr = int32_t(bph.irrCells.size());
                 bp.nTiles = int32_t(bph.hdr.size()); bp.maxSlots = bph.maxSlots; bp.maxCells = bph.maxCells;
             }
         }

@@ -492,7 +492,8 @@ int fvk_set_affine(int enabled);
  * (its per-cell face order is not [lower | owned, consecutive ids | boundary]); operators then use the per-cell
  * gather. Environment: FVK_BRICK="lx,by,bz" overrides the default 32,4,4 brick. */
 int fvk_brick_plan_selftest(const fvk_mesh_desc* desc_h, int32_t* info_h, int64_t* badCells_h);
-/* HOST only: {affine box proven (0/1), interior tiles along x, y, z, number of shell tiles} of the plan (info_h[5]). */
+/* HOST only: {affine topology proven (0/1), upper side x / y / z is a true boundary (1) or a processor cut (0), number of
+ * irregular (boundary / cut layer) cells} of the plan (info_h[5]). */
 int fvk_brick_plan_affine_info(const fvk_mesh_desc* desc_h, int32_t* info_h);
 
 #ifdef __cplusplus

@@ -83,12 +83,17 @@ def affine_info(desc):
     return list(info)
 
 
-def test_affine_interior_box_is_proven_only_where_it_holds():
+def test_affine_topology_is_proven_only_where_it_holds():
     """k_gather_affine reads no index array: the plan must prove the closed-form topology cell by cell."""
-    a = affine_info(MeshDesc.block(64, 48, 40))      # 16x4x2 bricks: 4 x 12 x 20 tiles -> interior box 2 x 10 x 18
-    assert a[0] == 1 and a[1:4] == [2, 10, 18] and a[4] == 4 * 12 * 20 - 2 * 10 * 18
-    assert affine_info(MeshDesc.block(32, 48, 40))[0] == 0          # only two tiles along x: no interior
-    assert affine_info(MeshDesc.block(20, 20, 1, patches=PATCHES_CAVITY2D))[0] == 0
-    assert affine_info(renumbered_block(12, 11, 10, 3))[0] == 0     # no block structure
-    dec = Decomposition(MeshDesc.block(64, 48, 40), 2, 0)
-    assert affine_info(dec.desc)[0] == 0                             # ghost cells / faceOrder: generic kernel
+    a = affine_info(MeshDesc.block(64, 48, 40))
+    assert a[:4] == [1, 1, 1, 1] and a[4] == 64 * 48 * 40 - 62 * 46 * 38      # irregular = the outermost cell layer
+    assert affine_info(MeshDesc.block(33, 7, 5))[0] == 1                      # ragged edge tiles are fine
+    assert affine_info(MeshDesc.block(20, 20, 1, patches=PATCHES_CAVITY2D))[0] == 0   # 2-D: per-cell order differs
+    assert affine_info(renumbered_block(12, 11, 10, 3))[0] == 0                # no block structure
+    g = MeshDesc.block(64, 48, 40)
+    lo, hi = affine_info(Decomposition(g, 2, 0).desc), affine_info(Decomposition(g, 2, 1).desc)
+    assert lo[:4] == [1, 0, 1, 1]    # rank 0: its +x side is a processor cut (cells there own a face to a ghost)
+    assert hi[:4] == [1, 1, 1, 1]    # rank 1: ghosts only on the lower side
+    for P in (4, 8):
+        for r in range(P):
+            assert affine_info(Decomposition(MeshDesc.block(16, 12, 10), P, r).desc)[0] == 1
