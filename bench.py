@@ -478,10 +478,31 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-    else:
-        run_native(args, rank, world, local_rank)
+    # stdout carries exactly ONE JSON line: everything native libraries print while we run (e.g. NCCL's version banner)
+    # goes to stderr; the real stdout is restored just for the final print
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    import io
+    buf = io.StringIO()
+    py_stdout, sys.stdout = sys.stdout, buf
+    try:
+        if args.impl == "reference":
+            run_reference(args, rank, world)
+        else:
+            run_native(args, rank, world, local_rank)
+    finally:
+        sys.stdout = py_stdout
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+        lines = [ln for ln in buf.getvalue().splitlines() if ln.strip()]
+        json_lines = [ln for ln in lines if ln.lstrip().startswith("{")]
+        for ln in lines:
+            if ln not in json_lines:
+                print(ln, file=sys.stderr)
+        if json_lines:
+            print(json_lines[-1], flush=True)
 
 
 if __name__ == "__main__":

@@ -555,7 +555,8 @@ struct fvk_solver
     double *partial = nullptr, *hist = nullptr;
     unsigned* counter = nullptr;
     PcgState* state = nullptr;
-    PcgState* state_h = nullptr; // pinned
+    PcgState* state_h = nullptr; // pinned, [2]: double-buffered stop checks
+    cudaEvent_t checkEv[2] = {nullptr, nullptr};
     int32_t histCap = 0;
 };
 
@@ -566,6 +567,8 @@ extern "C" int fvk_solver_destroy(fvk_solver* sv)
                       (void*) sv->partial, (void*) sv->hist, (void*) sv->counter, (void*) sv->state})
         if (ptr) cudaFree(ptr);
     if (sv->state_h) cudaFreeHost(sv->state_h);
+    for (auto& e : sv->checkEv)
+        if (e) cudaEventDestroy(e);
     delete sv;
     return FVK_OK;
 }
@@ -586,7 +589,9 @@ extern "C" int fvk_solver_create(int32_t nRows, int32_t nCols, const fvk_solver_
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&sv->counter), sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMemset(sv->counter, 0, sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&sv->state), sizeof(PcgState));
-    if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&sv->state_h), sizeof(PcgState));
+    if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&sv->state_h), 2 * sizeof(PcgState));
+    for (auto& ev : sv->checkEv)
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     if (e != cudaSuccess)
     {
         fvk_solver_destroy(sv);
@@ -643,6 +648,7 @@ extern "C" int fvk_solver_solve(fvk_solver* sv, const int32_t* rowOffs, const in
     double* rIn = sv->r;    // peer-memory mode double-buffers r (k_cg_update re-reads its input for the halo cells)
     double* rOut = dmode == 2 ? sv->r2 : sv->r;
     const int every = sv->cfg.checkEvery;
+    int nextCheck = 1, pending = -1, finalBuf = 0;
     // FVK_CG_TIMING=1: CUDA events around the two kernels of the first 64 iterations, averages to stderr
     static const bool timing = [] { const char* e = std::getenv("FVK_CG_TIMING"); return e && *e == '1'; }();
     constexpr int NT = 64;
@@ -701,11 +707,27 @@ extern "C" int fvk_solver_solve(fvk_solver* sv, const int32_t* rowOffs, const in
             double* t = pCur; pCur = pNext; pNext = t;
         }
         if (timing && it >= 1 && it <= NT) { cudaEventRecord(tev[it - 1][2], st); timed = it; }
-        if ((it + 1) % every == 0 || it == sv->cfg.maxIter)
+        // stop check after 1, 2, 4, ... iterations up to `every`, then every `every`: a solve that converges at once (the
+        // second PISO corrector often needs 0-3 iterations) does not queue `every` pairs of no-op kernels first
+        // The check is pipelined: the state copy of batch k is awaited only after batch k+1 has been queued, so the GPU
+        // never waits for the host; at most one batch of (no-op) kernels is queued beyond the stop.
+        if (it + 1 == nextCheck || it == sv->cfg.maxIter)
         {
-            FVK_CUDA(cudaMemcpyAsync(sv->state_h, sv->state, sizeof(PcgState), cudaMemcpyDeviceToHost, st));
-            FVK_CUDA(cudaStreamSynchronize(st));
-            if (sv->state_h->done) break;
+            if (pending >= 0)
+            {
+                FVK_CUDA(cudaEventSynchronize(sv->checkEv[pending]));
+                if (sv->state_h[pending].done) { finalBuf = pending; break; }
+            }
+            pending = pending < 0 ? 0 : 1 - pending;
+            FVK_CUDA(cudaMemcpyAsync(&sv->state_h[pending], sv->state, sizeof(PcgState), cudaMemcpyDeviceToHost, st));
+            FVK_CUDA(cudaEventRecord(sv->checkEv[pending], st));
+            if (it == sv->cfg.maxIter)
+            {
+                FVK_CUDA(cudaEventSynchronize(sv->checkEv[pending]));
+                finalBuf = pending;
+                break;
+            }
+            nextCheck = nextCheck < every ? (2 * nextCheck < every ? 2 * nextCheck : every) : nextCheck + every;
         }
     }
     if (timing)
@@ -723,14 +745,15 @@ extern "C" int fvk_solver_solve(fvk_solver* sv, const int32_t* rowOffs, const in
         for (auto& e3 : tev)
             for (auto& e : e3) cudaEventDestroy(e);
     }
-    if (!sv->state_h->done) return fvk_fail(FVK_ECUDA, "fvk_solver_solve: stop flag not raised after maxIter+1 checks");
-    stats_h->numIter = sv->state_h->iter;
-    stats_h->initResNorm = sv->state_h->normB;
-    stats_h->finalResNorm = sv->state_h->normR;
-    stats_h->nHistory = sv->state_h->nHist;
-    if (wantHist && sv->state_h->nHist > 0)
+    const PcgState& fin = sv->state_h[finalBuf];
+    if (!fin.done) return fvk_fail(FVK_ECUDA, "fvk_solver_solve: stop flag not raised after maxIter+1 checks");
+    stats_h->numIter = fin.iter;
+    stats_h->initResNorm = fin.normB;
+    stats_h->finalResNorm = fin.normR;
+    stats_h->nHistory = fin.nHist;
+    if (wantHist && fin.nHist > 0)
     {
-        FVK_CUDA(cudaMemcpyAsync(history_h, sv->hist, sizeof(double) * sv->state_h->nHist, cudaMemcpyDeviceToHost, st));
+        FVK_CUDA(cudaMemcpyAsync(history_h, sv->hist, sizeof(double) * fin.nHist, cudaMemcpyDeviceToHost, st));
         FVK_CUDA(cudaStreamSynchronize(st));
     }
     return FVK_OK;

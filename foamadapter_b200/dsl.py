@@ -185,9 +185,9 @@ class PDESolver:
     def setReference(self, pRefCell, pRefValue):
         self.needReference, self.pRefCell, self.pRefValue = True, int(pRefCell), float(pRefValue)
 
-    def solve(self, solver: la.Solver | None = None) -> la.SolverStats:
-        """iterativeSolveImpl as inferred from dsl::solve (dsl/solver.hpp:60-80): implicit assembly, rhs -= explicit*V,
-        post-assembly functors (SetReference), la::Solver.solve."""
+    def prepare(self):
+        """Everything of `solve` before the linear solver runs: implicit assembly, rhs -= explicit*V, post-assembly
+        functors (SetReference), halo of the initial guess. Kernel launches only (CUDA-graph capturable)."""
         if self.psi.ncomp != 1:
             raise NotImplementedError("only the scalar (pressure) solve is on the hot path; momentumPredictor is 'no'")
         mesh = self.psi.mesh
@@ -197,11 +197,16 @@ class PDESolver:
             ops.rhs_sub_source(mesh, src, self.ls.rhs)
         if self.needReference:
             ops.set_reference(mesh, self.pRefCell, self.pRefValue, self.ls.values, self.ls.rhs)
+        if self.rt.comm is not None:
+            self.rt.comm.halo_exchange(self.psi.internal)
+
+    def solve(self, solver: la.Solver | None = None) -> la.SolverStats:
+        """iterativeSolveImpl as inferred from dsl::solve (dsl/solver.hpp:60-80): implicit assembly, rhs -= explicit*V,
+        post-assembly functors (SetReference), la::Solver.solve."""
+        self.prepare()
         if solver is None:
             cfg = self.rt.fvSolution.get("solvers", {}).get(self.psi.name)
             if cfg is None:
                 raise KeyError(f"fvSolution.solvers has no entry for '{self.psi.name}'")
             solver = la.Solver(cfg, comm=self.rt.comm, check_every=self.rt.check_every, history=self.rt.history)
-        if self.rt.comm is not None:
-            self.rt.comm.halo_exchange(self.psi.internal)
         return solver.solve(self.ls, self.psi.internal)

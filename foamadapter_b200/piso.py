@@ -82,7 +82,7 @@ class IcoFoam:
     fixedWalls, p zeroGradient everywhere (tutorials/cavity/0.orig/{U,p}), nu uniform, momentumPredictor no."""
 
     def __init__(self, mesh: UnstructuredMesh, nu=0.01, dt=1e-4, fvSolution=None, fvSchemes=None, comm=None,
-                 lid=(1.0, 0.0, 0.0), history=False, check_every=8):
+                 lid=(1.0, 0.0, 0.0), history=False, check_every=8, graphs=True):
         self.mesh = mesh
         fvSolution = fvSolution or CAVITY_FVSOLUTION
         self.rt = dsl.RunTime(mesh, dt, 0.0, fvSchemes or CAVITY_FVSCHEMES, fvSolution, comm, check_every, history)
@@ -106,38 +106,95 @@ class IcoFoam:
         self.solver = la.Solver(fvSolution["solvers"]["p"], comm=comm, check_every=check_every, history=history)
         self.stats = []
         self.coNum = None
+        self.graphs, self._captured, self._nsteps = bool(graphs), None, 0
 
     def _halo(self, t):
         if self.rt.comm is not None:
             self.rt.comm.halo_exchange(t)
 
-    def step(self):
+    # ---- the step in three kinds of segments; everything except the linear solver is plain kernel launches ----------
+    def _pre(self, first: bool):
+        """neoIcoFoam.cpp:84-153 up to (not including) pEqn.solve's linear solver."""
         rt, mesh, U, p, phi = self.rt, self.mesh, self.U, self.p, self.phi
-        U.oldTime().internal.copy_(U.internal)                         # neoIcoFoam.cpp:84-85
-        self.coNum = ops.conum(mesh, phi.internal, rt.dt)              # :87 (device scalars; no host sync here)
-        self._halo(U.internal)
-        UEqn = dsl.PDESolver(dsl.imp.ddt(U) + dsl.imp.div(phi, U) - dsl.imp.laplacian(self.nu, U), U, rt, ls=self.Uls)
-        UEqn.assemble()                                                # momentumPredictor no (:100-109)
-        self.stats.append([])
-        for _ in range(self.piso["nCorrectors"]):
-            rAU, HbyA = computeRAUandHByA(UEqn, self.rAU, self.HbyA)   # :114
-            constrainHbyA(U, p, HbyA)                                  # :115
-            self._halo(rAU.internal); self._halo(HbyA.internal)
-            self.linear.interpolate(rAU, self.rAUf)                    # :117-124
-            phiHbyA = flux(HbyA, self.phiHbyA)                         # :126
-            nNon = self.piso["nNonOrthogonalCorrectors"]
-            for k in range(nNon + 1):
-                pEqn = dsl.PDESolver(dsl.imp.laplacian(self.rAUf, p) - dsl.exp.div(phiHbyA), p, rt, ls=self.pls)
-                if self.piso.get("pRefCell", -1) >= 0 and (rt.comm is None or rt.comm.rank == self.piso.get("pRefRank", 0)):
-                    pEqn.setReference(self.piso["pRefCell"], self.piso["pRefValue"])  # :150-153
-                st = pEqn.solve(self.solver)                           # :155
-                self.stats[-1].append(st)
-                self._halo(p.internal)
-                p.correctBoundaryConditions()                          # :156
-                if k == nNon:
-                    updateFaceVelocity(phiHbyA, pEqn, phi)             # :160
-            updateVelocity(HbyA, rAU, p, U, self.gradP)                # :166
-            U.correctBoundaryConditions()                              # :167
+        if first:
+            U.oldTime().internal.copy_(U.internal)                         # neoIcoFoam.cpp:84-85
+            self.coNum = ops.conum(mesh, phi.internal, rt.dt)              # :87 (device scalars; no host sync here)
             self._halo(U.internal)
+            self._UEqn = dsl.PDESolver(dsl.imp.ddt(U) + dsl.imp.div(phi, U) - dsl.imp.laplacian(self.nu, U), U, rt, ls=self.Uls)
+            self._UEqn.assemble()                                          # momentumPredictor no (:100-109)
+        rAU, HbyA = computeRAUandHByA(self._UEqn, self.rAU, self.HbyA)     # :114
+        constrainHbyA(U, p, HbyA)                                          # :115
+        self._halo(rAU.internal); self._halo(HbyA.internal)
+        self.linear.interpolate(rAU, self.rAUf)                            # :117-124
+        flux(HbyA, self.phiHbyA)                                           # :126
+        self._p_prepare()
+
+    def _p_prepare(self):
+        """pEqn of one (non-orthogonal) corrector up to the linear solver (:140-153)."""
+        rt, p = self.rt, self.p
+        self._pEqn = dsl.PDESolver(dsl.imp.laplacian(self.rAUf, p) - dsl.exp.div(self.phiHbyA), p, rt, ls=self.pls)
+        if self.piso.get("pRefCell", -1) >= 0 and (rt.comm is None or rt.comm.rank == self.piso.get("pRefRank", 0)):
+            self._pEqn.setReference(self.piso["pRefCell"], self.piso["pRefValue"])  # :150-153
+        self._pEqn.prepare()
+
+    def _post(self, last_nonorth: bool = True):
+        """neoIcoFoam.cpp:156-167 after the linear solver."""
+        U, p = self.U, self.p
+        self._halo(p.internal)
+        p.correctBoundaryConditions()                                      # :156
+        if last_nonorth:
+            updateFaceVelocity(self.phiHbyA, self._pEqn, self.phi)         # :160
+            updateVelocity(self.HbyA, self.rAU, p, U, self.gradP)          # :166
+            U.correctBoundaryConditions()                                  # :167
+            self._halo(U.internal)
+
+    def _segments(self):
+        """The kernel-only parts of a step between the linear solves, merged: [pre] solve [post + pre] solve ... [post].
+        Each bracket is one CUDA graph once captured."""
+        nC, nN = self.piso["nCorrectors"], self.piso["nNonOrthogonalCorrectors"]
+        segs, cur = [], []
+        for c in range(nC):
+            for k in range(nN + 1):
+                cur.append((lambda c=c: self._pre(c == 0)) if k == 0 else self._p_prepare)
+                segs.append(cur)
+                cur = [lambda k=k: self._post(k == nN)]
+        segs.append(cur)
+        return [(lambda fs=fs: [f() for f in fs]) for fs in segs]
+
+    def _graphs_allowed(self):
+        comm = self.rt.comm
+        return (self.graphs and self.piso["nCorrectors"] >= 1
+                and (comm is None or comm.nRanks == 1 or comm.p2p))  # NCCL calls are kept out of captures
+
+    def step(self):
+        """One time step. The first two steps run eagerly (warm-up: lazy allocations, kernel attributes); from the third
+        on the segments between the linear solves are replayed as CUDA graphs (all fields are persistent, dt is fixed,
+        the peer-memory halo kernels keep their sequence numbers on the device), which removes ~60 host-driven launches
+        per step. `graphs=False` or the NCCL transport keep the eager path."""
+        rt = self.rt
+        segs = self._segments()
+        use_graphs = self._graphs_allowed() and self._nsteps >= 2
+        if use_graphs and self._captured is None:
+            try:
+                torch.cuda.synchronize()
+                captured = []
+                for seg in segs:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        seg()
+                    captured.append(g)
+                self._captured = captured
+            except Exception as e:  # not capturable on this setup: stay eager, loudly
+                import sys
+                print(f"[piso] CUDA-graph capture failed ({e!r}); continuing without graphs", file=sys.stderr)
+                self.graphs, self._captured, use_graphs = False, None, False
+                torch.cuda.synchronize()
+        run = (lambda k: self._captured[k].replay()) if (use_graphs and self._captured) else (lambda k: segs[k]())
+        self.stats.append([])
+        for k in range(len(segs) - 1):
+            run(k)
+            self.stats[-1].append(self.solver.solve(self.pls, self.p.internal))   # :155
+        run(len(segs) - 1)
         rt.t += rt.dt
+        self._nsteps += 1
         return self.stats[-1]

@@ -84,7 +84,7 @@ def test_icofoam_steps_track_oracle(which):
     g = piso.IcoFoam(gm, nu=0.01, dt=dt, history=True, check_every=4)
     o = IcoFoamOracle(om, nu=0.01, dt=dt)
     assert np.array_equal(host(g.phi.internal), o.phi)
-    for step in range(3):
+    for step in range(4):  # steps 0-1 eager, 2 captured + replayed, 3 replayed (CUDA-graph segments)
         gs = g.step()
         os_ = o.step()
         for (st, (so, ho)) in zip(gs, os_):
@@ -104,6 +104,20 @@ def test_icofoam_steps_track_oracle(which):
     assert float((div * dev(om.V)).abs().max()) < 1e-5
     co = host(g.coNum)
     assert np.isfinite(co).all() and co[0] > 0
+
+
+def test_cuda_graph_segments_equal_eager_steps():
+    """From the third step on IcoFoam replays the kernel-only segments between the linear solves as CUDA graphs: the
+    fields must be bit-identical to the eager time loop, step after step."""
+    d = piso.cavity_desc(12, True)
+    a = piso.IcoFoam(M.UnstructuredMesh(d), nu=0.01, dt=5e-4, check_every=4, graphs=True)
+    b = piso.IcoFoam(M.UnstructuredMesh(d), nu=0.01, dt=5e-4, check_every=4, graphs=False)
+    for step in range(6):
+        sa, sb = a.step(), b.step()
+        assert [s.numIter for s in sa] == [s.numIter for s in sb]
+        for x, y in ((a.U.internal, b.U.internal), (a.p.internal, b.p.internal), (a.phi.internal, b.phi.internal)):
+            assert torch.equal(x, y), step
+    assert a._captured is not None and len(a._captured) == 3 and b._captured is None
 
 
 def test_pdesolver_matches_dsl_solve_sequence(case):

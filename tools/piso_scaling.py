@@ -24,9 +24,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--steps", type=int, default=4)
-    ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"])
     ap.add_argument("--check-every", type=int, default=16)
+    ap.add_argument("--graphs", type=int, default=1)
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -44,7 +45,7 @@ def main():
     else:
         mesh = UnstructuredMesh(g)
     setup_s = time.perf_counter() - t0
-    app = piso.IcoFoam(mesh, nu=0.01, dt=1e-4 * 20 / args.size, comm=comm, check_every=args.check_every)
+    app = piso.IcoFoam(mesh, nu=0.01, dt=1e-4 * 20 / args.size, comm=comm, check_every=args.check_every, graphs=bool(args.graphs))
     for _ in range(args.warmup):
         app.step()
     torch.cuda.synchronize()
@@ -66,7 +67,7 @@ def main():
     if rank == 0:
         tot_it = [int(sum(i)) for i in its]
         print("PISO " + json.dumps({"n": args.size, "cells": args.size ** 3, "n_gpus": world, "transport": ("peer-memory windows" if (comm and comm.p2p) else ("NCCL" if comm else "none")),
-                                    "ms_per_step": [round(float(x), 3) for x in ms], "median_ms": float(np.median(ms)), "cg_iterations": its,
+                                    "ms_per_step": [round(float(x), 3) for x in ms], "median_ms": float(np.median(ms)), "cg_iterations": its, "cuda_graphs": bool(app._captured),
                                     "ms_per_cg_iteration_upper_bound": float(np.median(ms / np.maximum(tot_it, 1))), "setup_s": round(setup_s, 1)}), flush=True)
     if comm is not None:
         comm.close()
