@@ -210,6 +210,8 @@ def solver_path_extras(n, peak):
     ms = timed(lambda: la.spmv(sp, ls.values, x, y))
     by = nnz * 12 + nC * 20
     out["spmv"] = {"ms": ms, "algorithmic_bytes": by, "achieved_gbs": by / ms / 1e6, "frac": by / ms / 1e6 / peak}
+    ms = timed(lambda: la.spmv_structured(gm, ls.values, x, y))
+    out["spmv_structured"] = {"ms": ms, "algorithmic_bytes": by, "achieved_gbs": by / ms / 1e6, "frac": by / ms / 1e6 / peak}
     ops.assemble(gm, [terms[1], terms[2]], T.boundary, ls.values, ls.rhs, ls.bcMatrix, ls.bcRhs)
     iters = 50
     solver = la.Solver({"solver": "Ginkgo", "type": "solver::Cg", "preconditioner": {"type": "preconditioner::Jacobi", "max_block_size": 1},

@@ -243,12 +243,20 @@ k_cg_pupdate(int n, const PcgState* __restrict__ st, const double* __restrict__ 
 // MODE 2: y = b - A x        (CG start-up r0)
 // MODE 3: CG: q = A p, dot p.q, scalar update; p read from `x`
 // MODE 4: CG fused: pNew = z + beta pOld evaluated on the fly for the gathered columns, q = A pNew
+// Block-structured sparsity (the mesh plan proved the topology, FvkBrickGeom::affine): the row of a REGULAR cell c is
+// [c-nx*ny, c-nx, c-1 | c | c+1, c+nx, c+nx*ny]; its column indices are not read (28 of the 104 bytes a row moves).
+struct SpmvAffine
+{
+    int on, nx, ny, nz;
+};
+
 template <int MODE>
 __global__ void __launch_bounds__(TB)
 k_spmv(int nRows, const int* __restrict__ rowOffs, const int* __restrict__ colIdxs, const double* __restrict__ values,
        const double* __restrict__ x, const double* __restrict__ b, double* __restrict__ y, PcgState* __restrict__ st,
        const double* __restrict__ z, double* __restrict__ pNew, double* __restrict__ partial,
-       unsigned* __restrict__ counter, int distributed, const FvkP2PCtx* __restrict__ p2p = nullptr, int nCols = 0)
+       unsigned* __restrict__ counter, int distributed, const FvkP2PCtx* __restrict__ p2p = nullptr, int nCols = 0,
+       SpmvAffine aff = SpmvAffine {0, 0, 0, 0})
 {
     __shared__ double prod[SPMV_CAP];
     __shared__ int ro[SPMV_ROWS + 1];
@@ -280,6 +288,37 @@ k_spmv(int nRows, const int* __restrict__ rowOffs, const int* __restrict__ colId
         int k = hasRow ? ro[threadIdx.x] : 0;
         const int kend = hasRow ? ro[threadIdx.x + 1] : 0;
         double sum = 0.0;
+        if (aff.on && end - base <= SPMV_CAP)
+        {
+            // structured tile: stream the VALUES only (coalesced), then every row multiplies its own entries in entry
+            // order -- the same products in the same order as below, columns from arithmetic for regular rows
+            for (int e = base + threadIdx.x; e < end; e += TB) prod[e - base] = ld_stream(values + e);
+            __syncthreads();
+            if (hasRow)
+            {
+                const int c = r0 + threadIdx.x;
+                const int i = c % aff.nx, q = c / aff.nx, j = q % aff.ny, kz = q / aff.ny;
+                const bool reg = i > 0 && i < aff.nx - 1 && j > 0 && j < aff.ny - 1 && kz > 0 && kz < aff.nz - 1 && kend - k == 7;
+                if (reg)
+                {
+                    const int nxy = aff.nx * aff.ny;
+                    const int col[7] = {c - nxy, c - aff.nx, c - 1, c, c + 1, c + aff.nx, c + nxy};
+                    double xv[7];
+#pragma unroll
+                    for (int t = 0; t < 7; ++t) xv[t] = (MODE == 4) ? (__ldg(zz + col[t]) + beta * x[col[t]]) : x[col[t]];
+#pragma unroll
+                    for (int t = 0; t < 7; ++t) sum += prod[k - base + t] * xv[t];
+                }
+                else
+                    for (; k < kend; ++k)
+                    {
+                        const int jc = colIdxs[k];
+                        const double xv = (MODE == 4) ? (__ldg(zz + jc) + beta * x[jc]) : x[jc];
+                        sum += prod[k - base] * xv;
+                    }
+            }
+        }
+        else
         for (int cb = base; cb < end; cb += SPMV_CAP)
         {
             const int ce = min(end, cb + SPMV_CAP);
@@ -458,6 +497,24 @@ extern "C" int fvk_spmv(int32_t nRows, const int32_t* rowOffs, const int32_t* co
     FVK_LAUNCH_CHECK();
     return FVK_OK;
 }
+static SpmvAffine mesh_affine(const fvk_mesh* m)
+{
+    static const bool off = [] { const char* e = std::getenv("FVK_SPMV_NO_AFFINE"); return e && *e == '1'; }();
+    const FvkBrickGeom& g = m->bp.geom;
+    // rows [lower faces ascending | diag | upper faces ascending] + the plan's proof give the regular rows' columns
+    if (off || !g.affine || m->bp.nTiles == 0 || int64_t(g.dims[0]) * g.dims[1] * g.dims[2] != m->nOwned) return SpmvAffine {0, 0, 0, 0};
+    return SpmvAffine {1, g.dims[0], g.dims[1], g.dims[2]};
+}
+extern "C" int fvk_spmv_structured(const fvk_mesh* m, const double* values, const double* x, double* y, fvk_stream s)
+{
+    if (!m || !values || !x || !y) return fvk_fail(FVK_EINVAL, "fvk_spmv_structured: null argument");
+    const int nRows = m->nOwned;
+    if (nRows == 0) return FVK_OK;
+    k_spmv<0><<<spmv_grid(nRows), TB, 0, fvk_cu(s)>>>(nRows, m->rowOffs, m->colIdxs, values, x, nullptr, y, nullptr, nullptr, nullptr, nullptr,
+                                                      nullptr, 0, nullptr, 0, mesh_affine(m));
+    FVK_LAUNCH_CHECK();
+    return FVK_OK;
+}
 extern "C" int fvk_residual(int32_t nRows, const int32_t* rowOffs, const int32_t* colIdxs, const double* values,
                             const double* b, const double* x, double* res, fvk_stream s)
 {
@@ -550,6 +607,7 @@ struct fvk_solver
     int32_t nRows = 0, nCols = 0;
     fvk_solver_config cfg {};
     fvk_comm* comm = nullptr;
+    SpmvAffine aff {0, 0, 0, 0}; // set by fvk_solver_attach_mesh
     double *r2 = nullptr; // second residual buffer of the peer-memory mode
     double *r = nullptr, *z = nullptr, *p0 = nullptr, *p1 = nullptr, *q = nullptr, *dinv = nullptr;
     double *partial = nullptr, *hist = nullptr;
@@ -601,6 +659,13 @@ extern "C" int fvk_solver_create(int32_t nRows, int32_t nCols, const fvk_solver_
     return FVK_OK;
 }
 
+extern "C" int fvk_solver_attach_mesh(fvk_solver* sv, const fvk_mesh* m)
+{
+    if (!sv) return fvk_fail(FVK_EINVAL, "fvk_solver_attach_mesh: null solver");
+    sv->aff = (m && m->nOwned == sv->nRows && m->nCells == sv->nCols) ? mesh_affine(m) : SpmvAffine {0, 0, 0, 0};
+    return FVK_OK;
+}
+
 extern "C" int fvk_solver_solve(fvk_solver* sv, const int32_t* rowOffs, const int32_t* colIdxs, const double* values,
                                 const double* b, double* x, fvk_solver_stats* stats_h, double* history_h,
                                 int32_t maxHistory, fvk_stream s)
@@ -640,7 +705,7 @@ extern "C" int fvk_solver_solve(fvk_solver* sv, const int32_t* rowOffs, const in
     }
     k_set_normB<<<1, 1, 0, st>>>(sv->state);
     // r = b - A x
-    k_spmv<2><<<gS, TB, 0, st>>>(n, rowOffs, colIdxs, values, x, b, sv->r, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
+    k_spmv<2><<<gS, TB, 0, st>>>(n, rowOffs, colIdxs, values, x, b, sv->r, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0, sv->aff);
     FVK_LAUNCH_CHECK();
 
     double* pCur = sv->p0;  // p of the previous iteration
@@ -678,7 +743,7 @@ extern "C" int fvk_solver_solve(fvk_solver* sv, const int32_t* rowOffs, const in
         {
             // peer-memory CG: the same two kernels as on one GPU. K1's last block exchanged the halo of z and all-reduced
             // (r.z, r.r); K2 forms p = z + beta p on the fly for owned AND ghost columns and all-reduces p.q.
-            k_spmv<4><<<gS, TB, 0, st>>>(n, rowOffs, colIdxs, values, pCur, nullptr, sv->q, sv->state, sv->z, pNext, sv->partial, sv->counter, 2, p2p, sv->nCols);
+            k_spmv<4><<<gS, TB, 0, st>>>(n, rowOffs, colIdxs, values, pCur, nullptr, sv->q, sv->state, sv->z, pNext, sv->partial, sv->counter, 2, p2p, sv->nCols, sv->aff);
             FVK_LAUNCH_CHECK();
             double* t = pCur; pCur = pNext; pNext = t;
         }
@@ -691,7 +756,7 @@ extern "C" int fvk_solver_solve(fvk_solver* sv, const int32_t* rowOffs, const in
             }
             k_cg_pupdate<<<gV, TB, 0, st>>>(n, sv->state, sv->z, pCur);
             if (int rc = fvk_comm_halo_exchange_impl(sv->comm, pCur, 1, st)) return rc;
-            k_spmv<3><<<gS, TB, 0, st>>>(n, rowOffs, colIdxs, values, pCur, nullptr, sv->q, sv->state, nullptr, nullptr, sv->partial, sv->counter, dmode, p2p);
+            k_spmv<3><<<gS, TB, 0, st>>>(n, rowOffs, colIdxs, values, pCur, nullptr, sv->q, sv->state, nullptr, nullptr, sv->partial, sv->counter, dmode, p2p, 0, sv->aff);
             FVK_LAUNCH_CHECK();
             if (dmode == 1)
             {
@@ -702,7 +767,7 @@ extern "C" int fvk_solver_solve(fvk_solver* sv, const int32_t* rowOffs, const in
         else
         {
             // K2 (fused): pNext = z + beta pCur, q = A pNext, p.q, alpha
-            k_spmv<4><<<gS, TB, 0, st>>>(n, rowOffs, colIdxs, values, pCur, nullptr, sv->q, sv->state, sv->z, pNext, sv->partial, sv->counter, 0);
+            k_spmv<4><<<gS, TB, 0, st>>>(n, rowOffs, colIdxs, values, pCur, nullptr, sv->q, sv->state, sv->z, pNext, sv->partial, sv->counter, 0, nullptr, 0, sv->aff);
             FVK_LAUNCH_CHECK();
             double* t = pCur; pCur = pNext; pNext = t;
         }

@@ -62,6 +62,15 @@ def createEmptyLinearSystem(mesh, ncomp=1):
     return LinearSystem(mesh, ncomp, zero=True)
 
 
+def spmv_structured(mesh, values, x, y=None):
+    """y = A x over the mesh's own sparsity pattern with the structured fast path (fvk_spmv_structured)."""
+    if y is None:
+        y = torch.empty(mesh.nOwned, dtype=torch.float64, device=x.device)
+    check(lib().fvk_spmv_structured(mesh.handle, ptr(values), ptr(x), ptr(y), _stream()))
+    ops._count()
+    return y
+
+
 def spmv(sp: SparsityPattern, values, x, y=None, nRows=None):
     n = nRows if nRows is not None else sp.mesh.nOwned
     if y is None:
@@ -143,7 +152,7 @@ class Solver:
             h = C.c_void_p()
             check(lib().fvk_solver_create(C.c_int32(nRows), C.c_int32(nCols), C.byref(self.cfg),
                                           self.comm.handle if self.comm is not None else None, C.byref(h)))
-            self._h, self._shape = h, (nRows, nCols)
+            self._h, self._shape, self._attached = h, (nRows, nCols), None
         return self._h
 
     def close(self):
@@ -170,6 +179,10 @@ class Solver:
 
     def solve(self, ls: LinearSystem, x) -> SolverStats:
         m = ls.mesh
+        h = self._handle(m.nOwned, m.nCells)
+        if getattr(self, "_attached", None) is not m:  # structured SpMV fast path when the mesh plan allows it
+            check(lib().fvk_solver_attach_mesh(h, m.handle))
+            self._attached = m
         return self.solve_csr(m.nOwned, m.nCells, ls.sp.rowOffs_ptr, ls.sp.colIdxs_ptr, ls.values, ls.rhs, x)
 
 

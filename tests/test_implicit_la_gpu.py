@@ -113,6 +113,30 @@ def test_spmv_and_residual_bit_exact(case):
     assert np.array_equal(host(la.computeResidual(sp, dev(vals), dev(b), dev(x))), om.residual(vals, b, x))
 
 
+def test_structured_spmv_bit_exact(case):
+    """fvk_spmv_structured: columns of the regular rows from arithmetic when the plan proved the block topology, the
+    generic rows / meshes otherwise -- always the reference's row sums, bit for bit."""
+    name, d, gm, om = case
+    rng = np.random.default_rng(12)
+    vals, x = rng.uniform(-1, 1, om.nnz), rng.uniform(-1, 1, om.nC)
+    assert np.array_equal(host(la.spmv_structured(gm, dev(vals), dev(x))), om.spmv(vals, x))
+
+
+def test_structured_spmv_on_a_large_block_and_its_sub_domains():
+    from foamadapter_b200.decomp import Decomposition
+    g = M.MeshDesc.block(40, 24, 18, 1.0, 0.6, 0.45)
+    gm, om = M.UnstructuredMesh(g), OMesh.from_desc(g)
+    rng = np.random.default_rng(13)
+    vals, x = rng.uniform(-1, 1, om.nnz), rng.uniform(-1, 1, om.nC)
+    assert np.array_equal(host(la.spmv_structured(gm, dev(vals), dev(x))), om.spmv(vals, x))
+    for r in range(2):
+        dec = Decomposition(g, 2, r)
+        lm = M.UnstructuredMesh(dec.desc)
+        sp = la.SparsityPattern.readOrCreate(lm)
+        lv, lx = rng.uniform(-1, 1, lm.nnz), rng.uniform(-1, 1, lm.nCells)
+        assert torch.equal(la.spmv_structured(lm, dev(lv), dev(lx)), la.spmv(sp, dev(lv), dev(lx)))
+
+
 def test_residual_known_answer():
     # src/NeoN/test/linearAlgebra/utilities.cpp:22-44
     ro = torch.tensor([0, 3, 6, 9], dtype=torch.int32, device="cuda")

@@ -58,6 +58,9 @@ def main():
         med, best = timeit(lambda: la.spmv(sp, ls.values, x, y), args.reps, flush)
         emit({"mesh": n, "kernel": "spmv", "ms": med, "best_ms": best, "alg_bytes": bytes_spmv, "gbs": bytes_spmv / med / 1e6,
               "frac_of_" + kind: bytes_spmv / med / 1e6 / peak})
+        med, best = timeit(lambda: la.spmv_structured(gm, ls.values, x, y), args.reps, flush)
+        emit({"mesh": n, "kernel": "spmv_structured", "ms": med, "best_ms": best, "alg_bytes": bytes_spmv, "gbs": bytes_spmv / med / 1e6,
+              "frac_of_" + kind: bytes_spmv / med / 1e6 / peak})
         # CG iterations on the SPD system -laplacian + ddt (fixed iteration count, no early stop)
         ops.assemble(gm, [dict(kind=ops.TERM_LAPLACIAN, coeff=-1.0, faceField=gamma), dict(kind=ops.TERM_DDT, coeff=1.0, cellField=old, dt=1.0)],
                      T.boundary, ls.values, ls.rhs, ls.bcMatrix, ls.bcRhs)
