@@ -147,6 +147,12 @@ public:
             h_ = nullptr;
             check(fvk_solver_create(m.nOwnedCells(), m.nCells(), &cfg_, comm_, &h_));
             rows_ = m.nOwnedCells(); cols_ = m.nCells();
+            attached_ = nullptr;
+        }
+        if (attached_ != m.handle()) // structured SpMV inside CG when the mesh plan proved a block topology
+        {
+            check(fvk_solver_attach_mesh(h_, m.handle()));
+            attached_ = m.handle();
         }
         const auto& sp = ls.sparsityPattern();
         fvk_solver_stats st {};
@@ -163,6 +169,7 @@ private:
     fvk_solver_config cfg_ {};
     mutable fvk_solver* h_ = nullptr;
     mutable localIdx rows_ = 0, cols_ = 0;
+    mutable const fvk_mesh* attached_ = nullptr;
 };
 
 } // namespace NeoN::la

@@ -1,6 +1,6 @@
 #!/bin/bash
 # final multi-GPU numbers: PISO strong scaling 256^3 (CUDA graphs + peer-memory windows), bench weak scaling
-OUT=gpurun_out/r2s
+OUT=gpurun_out/${1:-mgpu}
 mkdir -p $OUT
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
 timeout 240 $TR --nproc-per-node 8 --master-port 29532 tools/piso_scaling.py --size 256 > $OUT/piso_n8_256.log 2>&1; grep -E "PISO|piso\]" $OUT/piso_n8_256.log | cut -c1-600
