@@ -965,7 +965,6 @@ int launch_brick(const fvk_mesh* m, Op op, Scaling sc, double* out, int mode, cu
     int MINB = (light ? 6 : 4) * 256 / TB;
     int cfg[3];
     if (fvk_brick_config(cfg) && cfg[1] == TB) MINB = cfg[2];
-    const bool xdefer = fvk_brick_config(cfg) ? cfg[0] == 2 : false; // config[0]: 1 = cross operands early, 2 = deferred
     if (m->bp.geom.affine && !fvk_no_affine())
     {
         // the affine kernel keeps all operands of a cell in flight: spill-free register budgets (ptxas -v): 40 for the
@@ -979,12 +978,9 @@ int launch_brick(const fvk_mesh* m, Op op, Scaling sc, double* out, int mode, cu
         FVK_AFFINE_CASE(512, 2) FVK_AFFINE_CASE(512, 3)
 #undef FVK_AFFINE_CASE
     }
-#define FVK_BRICK_CASE(tb, mb)                                                                                          \
-    if (TB == tb && MINB == mb)                                                                                         \
-        return xdefer ? launch_brick_n<Op, tb, mb, true>(m, op, sc, out, mode, st) : launch_brick_n<Op, tb, mb, false>(m, op, sc, out, mode, st)
-    FVK_BRICK_CASE(256, 4); FVK_BRICK_CASE(256, 5); FVK_BRICK_CASE(256, 6); FVK_BRICK_CASE(256, 8);
+#define FVK_BRICK_CASE(tb, mb) if (TB == tb && MINB == mb) return launch_brick_n<Op, tb, mb, false>(m, op, sc, out, mode, st)
+    FVK_BRICK_CASE(128, 8); FVK_BRICK_CASE(128, 12); FVK_BRICK_CASE(256, 4); FVK_BRICK_CASE(256, 6);
     FVK_BRICK_CASE(512, 2); FVK_BRICK_CASE(512, 3);
-    FVK_BRICK_CASE(128, 8); FVK_BRICK_CASE(128, 12); FVK_BRICK_CASE(128, 16);
 #undef FVK_BRICK_CASE
     return -1;
 }

@@ -41,7 +41,7 @@ extern "C" int fvk_set_variant(int v)
 }
 int fvk_variant() { return g_variant; }
 
-// brick kernel configuration override {cells per thread, threads per block, resident blocks aimed at}; {0,0,0}: defaults
+// kernel configuration override {kernel (1 brick, 3 affine), threads per block, resident blocks aimed at}; {0,0,0}: defaults
 static int g_brickCfg[3] = {0, 0, 0};
 static bool g_brickCfgEnv = false;
 extern "C" int fvk_mesh_set_tile_phase(fvk_mesh* m, int phase)
@@ -66,9 +66,9 @@ bool fvk_no_affine()
     }
     return g_noAffine == 1;
 }
-extern "C" int fvk_set_brick_config(int cellsPerThread, int threads, int minBlocks)
+extern "C" int fvk_set_brick_config(int kernel, int threads, int minBlocks)
 {
-    g_brickCfg[0] = cellsPerThread; g_brickCfg[1] = threads; g_brickCfg[2] = minBlocks;
+    g_brickCfg[0] = kernel; g_brickCfg[1] = threads; g_brickCfg[2] = minBlocks;
     g_brickCfgEnv = true; // an explicit call wins over the environment
     return FVK_OK;
 }

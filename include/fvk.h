@@ -483,10 +483,10 @@ int fvk_mesh_set_tile_phase(fvk_mesh* mesh, int phase);
  * thread like the operator kernels. tools/stream_probe.py uses it to measure what HBM delivers for N concurrent read
  * streams -- the practical ceiling the 6-8-array operator kernels are compared with next to the 2-stream copy peak. */
 int fvk_probe_streams(int nStreams, const double* const* in_h, int64_t n, double* out, fvk_stream stream);
-/* tuning switch of the brick kernel (roofline sweeps only): cross-face operand timing (1 = early, 2 = deferred), threads per block, resident blocks per SM
+/* tuning switch of the brick kernel (roofline sweeps only): which kernel the override applies to (1 = brick kernel, 3 = affine kernel), threads per block, resident blocks per SM
  * the register allocation aims at; only combinations instantiated in fvk_explicit.cu are honoured (others fall back to
  * the per-cell gather). (0,0,0) restores the defaults. Environment FVK_BRICK_CFG="K,TB,MINB" does the same. */
-int fvk_set_brick_config(int cellsPerThread, int threads, int minBlocks);
+int fvk_set_brick_config(int kernel, int threads, int minBlocks);
 /* A/B switch (roofline harness, parity tests): 0 = the generic brick kernel computes every tile, 1 (default) = tiles of a
  * block-structured mesh whose topology the plan proved affine are computed by the index-free kernel. */
 int fvk_set_affine(int enabled);

@@ -18,12 +18,10 @@ from foamadapter_b200 import _capi, fvcc, ops  # noqa: E402
 from foamadapter_b200.mesh import MeshDesc, UnstructuredMesh  # noqa: E402
 from tools.roofline import timeit  # noqa: E402
 
-PLANS = [
-    (256, "16,4,4", [(1, 256, 4), (1, 256, 5), (1, 256, 6), (1, 256, 8), (2, 256, 5), (2, 256, 6), (2, 256, 8)]),
-    (256, "32,4,2", [(1, 256, 5), (1, 256, 6), (2, 256, 6)]),
-    (256, "16,8,2", [(1, 256, 5), (1, 256, 6)]),
-    (128, "16,4,2", [(1, 128, 8), (1, 128, 12), (2, 128, 12), (2, 128, 16)]),
-    (512, "16,8,4", [(1, 512, 2), (1, 512, 3), (2, 512, 3)]),
+PLANS = [  # (tile cells, brick shape, [(kernel: 1 = brick / 3 = affine, threads, resident blocks aimed at)]) -- instantiated combinations only
+    (128, "16,4,2", [(1, 128, 8), (1, 128, 12), (3, 128, 6), (3, 128, 8), (3, 128, 12)]),
+    (256, "16,4,4", [(1, 256, 4), (1, 256, 6), (3, 256, 3), (3, 256, 4), (3, 256, 6)]),
+    (512, "16,8,4", [(1, 512, 2), (1, 512, 3), (3, 512, 2), (3, 512, 3)]),
 ]
 
 
@@ -66,6 +64,7 @@ def main():
         for kind_, cfg in todo:
             L.fvk_set_variant(0 if kind_ == "brick" else 5)
             L.fvk_set_brick_config(*cfg)
+            L.fvk_set_affine(1 if cfg[0] == 3 else 0)
             row = {"mesh": n, "kernel_kind": kind_, "cells": cells, "brick": shape, "cfg": list(cfg)}
             for name, fn in kernels.items():
                 med, best = timeit(fn, args.reps, flush)
@@ -74,6 +73,7 @@ def main():
             print(json.dumps(row), flush=True)
         L.fvk_set_variant(0)
         L.fvk_set_brick_config(0, 0, 0)
+        L.fvk_set_affine(1)
         del gm, T, phi, pb
         torch.cuda.empty_cache()
     Path(args.out).parent.mkdir(exist_ok=True, parents=True)
