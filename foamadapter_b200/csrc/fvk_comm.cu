@@ -447,6 +447,13 @@ extern "C" int fvk_comm_p2p_connect(fvk_comm* c, const void* blobs)
 }
 
 extern "C" int fvk_comm_p2p_enabled(const fvk_comm* c) { return (c && c->p2p) ? 1 : 0; }
+/* back to the NCCL transport (e.g. when another rank could not map the windows: the choice must be collective) */
+extern "C" int fvk_comm_p2p_disable(fvk_comm* c)
+{
+    if (!c) return fvk_fail(FVK_EINVAL, "fvk_comm_p2p_disable: null");
+    c->p2p = false;
+    return FVK_OK;
+}
 
 /* accumulated nanoseconds of the in-kernel communication phases (diagnostics): [0] flag raise + system fence, [1] all-reduce
  * (r.z, r.r), [2] wait for the halo flags, [3] count; [4] all-reduce p.q, [5] count */

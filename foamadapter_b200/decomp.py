@@ -117,7 +117,7 @@ class Comm:
 
     def enable_p2p(self):
         """fvk_comm_p2p_export -> all-gather of the blobs over torch.distributed -> fvk_comm_p2p_connect. Collective.
-        Raises FvkError (and leaves NCCL as the transport) when CUDA IPC is not available between the ranks."""
+        Returns False (and leaves NCCL as the transport on EVERY rank) when CUDA IPC is not available somewhere."""
         import torch
         import torch.distributed as dist
         blob = (C.c_char * self.P2P_BLOB)()
@@ -127,8 +127,18 @@ class Comm:
         allb = torch.empty(self.nRanks * self.P2P_BLOB, dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(allb, mine)
         raw = bytes(allb.cpu().numpy().tobytes())
-        check(lib().fvk_comm_p2p_connect(self._h, (C.c_char * len(raw)).from_buffer_copy(raw)))
+        rc = lib().fvk_comm_p2p_connect(self._h, (C.c_char * len(raw)).from_buffer_copy(raw))
+        # the transport must be the same everywhere: if any rank could not map a window, all go back to NCCL
+        ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            import sys
+            if rc != 0:
+                print(f"[fvk] rank {self.rank}: peer-memory windows unavailable ({lib().fvk_last_error().decode()}); using NCCL", file=sys.stderr)
+            check(lib().fvk_comm_p2p_disable(self._h))
+            return False
         dist.barrier()  # nobody pushes into a window before every rank has mapped and zeroed its own
+        return True
 
     @property
     def p2p(self) -> bool:

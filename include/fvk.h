@@ -437,6 +437,8 @@ int fvk_comm_allreduce_max(fvk_comm* comm, double* data_d, int count, fvk_stream
 int fvk_comm_p2p_export(fvk_comm* comm, void* blob_h);
 int fvk_comm_p2p_connect(fvk_comm* comm, const void* allBlobs_h /* nRanks x FVK_P2P_BLOB_BYTES, rank order */);
 int fvk_comm_p2p_enabled(const fvk_comm* comm);
+/* back to NCCL; the transport must be the same on every rank, so call it everywhere when any rank failed to connect */
+int fvk_comm_p2p_disable(fvk_comm* comm);
 /* diagnostics: accumulated ns spent by the CG kernels' last blocks in [0] flag raise, [1] all-reduce (r.z, r.r), [2] halo
  * flag wait, [3] count, [4] all-reduce p.q, [5] count */
 int fvk_comm_p2p_debug(const fvk_comm* comm, uint64_t* out8_h);
