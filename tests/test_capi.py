@@ -43,3 +43,22 @@ def test_new_entry_points_validate_arguments():
         assert lib.fvk_comm_p2p_export(h, blob) in (2, 3)  # FVK_ENODEVICE / FVK_ECUDA: no CPU stand-in for the window
     assert lib.fvk_comm_p2p_enabled(h) == 0
     lib.fvk_comm_destroy(h)
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py contract: stdout carries ONE JSON line (anything a native library prints goes to stderr); the reference
+    arm runs without a GPU. Tiny mesh so the CPU suite stays fast."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    r = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--mesh", "12", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "fp64_face_ops_per_s" and d["unit"] == "face-ops/s"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["higher_is_better"] is True
