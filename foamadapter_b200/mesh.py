@@ -72,6 +72,55 @@ class MeshDesc:
         return self
 
     @classmethod
+    def from_polymesh(cls, poly_mesh_dir):
+        """Read an OpenFOAM ASCII `constant/polyMesh` directory (fvk_polymesh_read): the stand-in for
+        FoamAdapter::readOpenFOAMMesh (src/datastructures/meshAdapter.cpp:59-136) without OpenFOAM."""
+        self = cls()
+        out = C.POINTER(_CDesc)()
+        check(lib().fvk_polymesh_read(str(poly_mesh_dir).encode(), C.byref(out)))
+        self._owned_ptr, self._owned_kind = out, "polymesh"
+        self._c = out.contents
+        name, typ = C.create_string_buffer(256), C.create_string_buffer(256)
+        self.patch_names, self.patch_types = [], []
+        for p in range(self._c.nPatches):
+            check(lib().fvk_polymesh_patch(out, C.c_int32(p), name, C.c_int32(256), typ, C.c_int32(256)))
+            self.patch_names.append(name.value.decode()); self.patch_types.append(typ.value.decode())
+        return self
+
+    def write_polymesh(self, poly_mesh_dir, patches=PATCHES_3DCUBE, types=None):
+        """Write a block mesh created `with_points=True` as an OpenFOAM ASCII polyMesh directory (fvk_polymesh_write).
+        `patches` is the layout the mesh was generated with; `types[name]` overrides the patch type
+        (default: `empty` for empty patches, else `wall`)."""
+        import os
+        os.makedirs(poly_mesh_dir, exist_ok=True)
+        fp, po = self.poly()
+        nPoly, nI = fp.shape[0], self.nInternalFaces
+        pts = np.ascontiguousarray(self.array("points"), dtype=np.float64)
+        # side sizes follow from the faces' owner cells: recover them from the patch layout and the face count
+        nei = np.ascontiguousarray(self.array("faceNeighbour"), dtype=np.int32)
+        kept = self.array("patchOffsets")
+        sizes, k = [], 0
+        empty_total = (nPoly - nI) - int(kept[-1])
+        n_empty = sum(1 for p in patches if p[2])
+        for name_, sides, is_empty in patches:
+            if is_empty:
+                if n_empty != 1:
+                    raise ValueError("write_polymesh: at most one empty patch")
+                sizes.append(empty_total)
+            else:
+                sizes.append(int(kept[k + 1] - kept[k])); k += 1
+        offs = np.arange(0, 4 * nPoly + 1, 4, dtype=np.int32)
+        names = [p[0].encode() for p in patches]
+        tys = [((types or {}).get(p[0]) or ("empty" if p[2] else "wall")).encode() for p in patches]
+        arr = lambda lst: (C.c_char_p * len(lst))(*lst)
+        fpc, poc = np.ascontiguousarray(fp, dtype=np.int32), np.ascontiguousarray(po, dtype=np.int32)
+        check(lib().fvk_polymesh_write(str(poly_mesh_dir).encode(), C.c_int32(pts.shape[0]), pts.ctypes.data_as(C.c_void_p),
+                                       C.c_int32(nPoly), offs.ctypes.data_as(C.c_void_p), fpc.ctypes.data_as(C.c_void_p),
+                                       poc.ctypes.data_as(C.c_void_p), C.c_int32(nI), nei.ctypes.data_as(C.c_void_p),
+                                       C.c_int32(len(patches)), arr(names), arr(tys), (C.c_int32 * len(sizes))(*sizes)))
+        return poly_mesh_dir
+
+    @classmethod
     def from_arrays(cls, a: dict, patch_names=None):
         """Build from numpy arrays keyed like the C struct (e.g. from a polyMesh fixture)."""
         self = cls()
@@ -121,7 +170,10 @@ class MeshDesc:
 
     def __del__(self):
         if getattr(self, "_owned_ptr", None) is not None and _capi is not None and _capi._lib is not None:
-            _capi._lib.fvk_blockmesh_destroy(self._owned_ptr)
+            if getattr(self, "_owned_kind", "block") == "polymesh":
+                _capi._lib.fvk_polymesh_destroy(self._owned_ptr)
+            else:
+                _capi._lib.fvk_blockmesh_destroy(self._owned_ptr)
             self._owned_ptr = None
 
     # -- access -----------------------------------------------------------------------------------

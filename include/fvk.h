@@ -128,6 +128,25 @@ int fvk_blockmesh_poly(const fvk_mesh_desc* desc, int32_t* nPolyFaces, const int
                        const int32_t** polyOwner);
 
 /* ------------------------------------------------------------------------------------------------
+ * OpenFOAM ASCII polyMesh directories (constant/polyMesh: points, faces, owner, neighbour, boundary) without OpenFOAM:
+ * the stand-in for Foam::polyMesh + FoamAdapter::readOpenFOAMMesh (src/datastructures/meshAdapter.cpp:12-45,59-136).
+ * Arbitrary polygons / polyhedra; geometry = OpenFOAM primitiveMesh (same arithmetic as the block generator, which
+ * reproduces the reference's committed fixtures bit for bit); boundary flattened like the reference's converter (patches
+ * in file order, `empty` patches contribute no faces). Host only; arrays owned by the returned object; the description
+ * feeds fvk_mesh_create / fvk_decompose like a generated one. Binary-format files are rejected.
+ * ---------------------------------------------------------------------------------------------- */
+int fvk_polymesh_read(const char* polyMeshDir, fvk_mesh_desc** out);
+int fvk_polymesh_destroy(fvk_mesh_desc* desc);
+/* name / type of kept (non-empty) patch `patch` of a mesh from fvk_polymesh_read, NUL-terminated into the buffers */
+int fvk_polymesh_patch(const fvk_mesh_desc* desc, int32_t patch, char* name, int32_t nameCap, char* type, int32_t typeCap);
+/* write the five files into an existing directory. Faces: faceOffsets [nFaces+1] into facePoints; faces [0, nInternalFaces)
+ * are internal, then the patches in order with patchSizes[p] faces each (all patches, `empty` ones included). */
+int fvk_polymesh_write(const char* polyMeshDir, int32_t nPoints, const double* points, int32_t nFaces,
+                       const int32_t* faceOffsets, const int32_t* facePoints, const int32_t* owner,
+                       int32_t nInternalFaces, const int32_t* neighbour, int32_t nPatches,
+                       const char* const* patchNames, const char* const* patchTypes, const int32_t* patchSizes);
+
+/* ------------------------------------------------------------------------------------------------
  * Device mesh handle. Uploads the description and builds, once per mesh:
  *   - BasicGeometryScheme weights / deltaCoeffs / nonOrthDeltaCoeffs
  *     (src/NeoN/src/finiteVolume/cellCentred/stencil/basicGeometryScheme.cpp:15-136),

@@ -1,0 +1,171 @@
+"""CPU tests of the product-side OpenFOAM polyMesh reader / writer (fvk_polymesh_read / _write, host code of libfvk):
+round trips of generated block meshes are bit-exact in every array of the mesh description (topology, ordering,
+primitiveMesh geometry, boundary flattening with `empty` patches), the reader agrees with the golden fixtures extracted
+from the reference's committed polyMesh directories and with the oracle's numpy restatement of primitiveMesh on a
+polyhedral (prism) mesh, and malformed input fails loudly."""
+import numpy as np
+import pytest
+
+from foamadapter_b200._capi import FvkError
+from foamadapter_b200.mesh import PATCHES_3DCUBE, PATCHES_CAVITY2D, PATCHES_CAVITY3D, MeshDesc
+from oracle import polymesh as opoly
+
+ARRAYS = ["cellVolumes", "cellCentres", "faceAreas", "faceCentres", "magFaceAreas", "faceOwner", "faceNeighbour", "faceCells",
+          "bCf", "bCn", "bSf", "bMagSf", "bNf", "bDelta", "bWeights", "bDeltaCoeffs", "patchOffsets", "points"]
+
+
+@pytest.mark.parametrize("dims,box,patches", [((5, 5, 1), (0.1, 0.1, 0.01), PATCHES_CAVITY2D), ((4, 3, 2), (1.0, 0.5, 0.25), PATCHES_3DCUBE),
+                                              ((7, 5, 4), (0.7, 0.3, 0.9), PATCHES_CAVITY3D), ((1, 1, 1), (1.0, 1.0, 1.0), PATCHES_3DCUBE)])
+def test_block_mesh_round_trip_is_bit_exact(tmp_path, dims, box, patches):
+    g = MeshDesc.block(*dims, *box, patches=patches, with_points=True)
+    d = g.write_polymesh(tmp_path / "polyMesh", patches)
+    r = MeshDesc.from_polymesh(d)
+    assert (r.nCells, r.nInternalFaces, r.nBoundaryFaces, r.nPatches) == (g.nCells, g.nInternalFaces, g.nBoundaryFaces, g.nPatches)
+    assert r.patch_names == g.patch_names
+    assert r.patch_types == ["wall"] * g.nPatches      # `empty` patches are dropped like fvPatch::size() == 0
+    for name in ARRAYS:
+        assert np.array_equal(r.array(name), g.array(name)), name
+
+
+def _write_raw(d, pts, faces, owner, nei, names, types, sizes):
+    import ctypes as C
+    from foamadapter_b200._capi import check, lib
+    d.mkdir(parents=True, exist_ok=True)
+    pts = np.ascontiguousarray(pts, dtype=np.float64)
+    off = np.cumsum([0] + [len(f) for f in faces]).astype(np.int32)
+    fp = np.array([p for f in faces for p in f], dtype=np.int32)
+    ow, ne = np.ascontiguousarray(owner, dtype=np.int32), np.ascontiguousarray(nei, dtype=np.int32)
+    cn = (C.c_char_p * len(names))(*[str(n).encode() for n in names])
+    ct = (C.c_char_p * len(types))(*[str(t).encode() for t in types])
+    check(lib().fvk_polymesh_write(str(d).encode(), C.c_int32(len(pts)), pts.ctypes.data_as(C.c_void_p), C.c_int32(len(faces)),
+                                   off.ctypes.data_as(C.c_void_p), fp.ctypes.data_as(C.c_void_p), ow.ctypes.data_as(C.c_void_p),
+                                   C.c_int32(len(ne)), ne.ctypes.data_as(C.c_void_p), C.c_int32(len(names)), cn, ct,
+                                   (C.c_int32 * len(sizes))(*[int(x) for x in sizes])))
+    return d
+
+
+@pytest.mark.parametrize("fixture", ["setup_operator", "setup_stencil3D", "setup_unstructuredMesh", "setup_advection",
+                                     "setup_pressureVelocityCoupling", "setup_compatibility"])
+def test_reader_on_the_reference_fixture_meshes(tmp_path, fixture):
+    """tests/golden/*.npz hold the raw content of the polyMesh directories the reference commits
+    (test/setup_*/constant/polyMesh, extracted by tests/golden/make_golden.py). Written back as ASCII files and read by the
+    product reader, they must give the reference's topology, the oracle's primitiveMesh geometry and the flattened
+    boundary of readOpenFOAMMesh (empty patches dropped)."""
+    from pathlib import Path
+    z = np.load(Path(__file__).parent / "golden" / f"{fixture}.npz")
+    if "faces" not in z.files:
+        pytest.skip("fixture without a mesh")
+    faces = [list(f) for f in z["faces"]]
+    d = _write_raw(tmp_path / "polyMesh", z["points"], faces, z["owner"], z["neighbour"], z["patch_names"], z["patch_types"], z["patch_size"])
+    r = MeshDesc.from_polymesh(d)
+    nI = len(z["neighbour"])
+    keep = [i for i, t in enumerate(z["patch_types"]) if str(t) != "empty"]
+    bsel = np.concatenate([np.arange(z["patch_start"][i], z["patch_start"][i] + z["patch_size"][i]) for i in keep]) if keep else np.zeros(0, int)
+    sel = np.concatenate([np.arange(nI), bsel]).astype(int)
+    assert r.nInternalFaces == nI and r.nBoundaryFaces == len(bsel) and r.nCells == int(max(z["owner"].max(), z["neighbour"].max())) + 1
+    assert r.patch_names == [str(z["patch_names"][i]) for i in keep]
+    assert np.array_equal(r.array("faceOwner"), z["owner"][sel]) and np.array_equal(r.array("faceNeighbour"), z["neighbour"])
+    assert np.array_equal(r.array("patchOffsets"), np.concatenate([[0], np.cumsum([z["patch_size"][i] for i in keep])]))
+    Cf, Sf = opoly.face_geometry(z["points"], [np.array(f) for f in faces])
+    Cc, V = opoly.cell_geometry(Cf, Sf, z["owner"], z["neighbour"], r.nCells)
+    assert np.allclose(r.array("faceCentres"), Cf[sel], rtol=1e-14, atol=1e-18) and np.allclose(r.array("faceAreas"), Sf[sel], rtol=1e-14, atol=1e-18)
+    assert np.allclose(r.array("cellVolumes"), V, rtol=1e-14) and np.allclose(r.array("cellCentres"), Cc, rtol=1e-14, atol=1e-18)
+    # the block generator reproduces the same mesh (what tests/test_blockmesh.py pins): same topology, geometry to the
+    # ~3e-16 absolute noise the fixture's points carry
+    from tests.helpers import FIXTURE_BLOCKS
+    if fixture in FIXTURE_BLOCKS:
+        g = MeshDesc.block(*FIXTURE_BLOCKS[fixture][0], *FIXTURE_BLOCKS[fixture][1], patches=FIXTURE_BLOCKS[fixture][2])
+        for name in ("faceOwner", "faceNeighbour", "faceCells", "patchOffsets"):
+            assert np.array_equal(r.array(name), g.array(name)), name
+        for name in ("cellVolumes", "cellCentres", "faceAreas", "faceCentres", "magFaceAreas", "bCf", "bCn", "bSf", "bMagSf", "bNf",
+                     "bDelta", "bWeights", "bDeltaCoeffs"):
+            x, y = r.array(name), g.array(name)
+            assert np.abs(x - y).max() <= 1e-12 * np.abs(y).max(), name
+
+
+def _write_prisms(tmp_path):
+    """Unit cube cut along the x = y diagonal into two triangular prisms: triangles, quads, one internal face."""
+    pts = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], dtype=np.float64)
+    faces = [[0, 4, 6, 2],                      # internal: the diagonal plane, owner 0 (normal towards cell 1)
+             [0, 2, 1], [4, 5, 6], [0, 1, 5, 4], [1, 2, 6, 5],      # cell 0: bottom, top, y = 0, x = 1 (outward normals)
+             [0, 3, 2], [4, 6, 7], [2, 3, 7, 6], [3, 0, 4, 7]]      # cell 1: bottom, top, y = 1, x = 0
+    owner = [0, 0, 0, 0, 0, 1, 1, 1, 1]
+    nei = [1]
+    import ctypes as C
+    from foamadapter_b200._capi import check, lib
+    d = tmp_path / "polyMesh"
+    d.mkdir()
+    off = np.cumsum([0] + [len(f) for f in faces]).astype(np.int32)
+    fp = np.array([p for f in faces for p in f], dtype=np.int32)
+    ow, ne = np.array(owner, dtype=np.int32), np.array(nei, dtype=np.int32)
+    names = (C.c_char_p * 2)(b"walls0", b"walls1")
+    types = (C.c_char_p * 2)(b"wall", b"patch")
+    check(lib().fvk_polymesh_write(str(d).encode(), C.c_int32(8), pts.ctypes.data_as(C.c_void_p), C.c_int32(9), off.ctypes.data_as(C.c_void_p),
+                                   fp.ctypes.data_as(C.c_void_p), ow.ctypes.data_as(C.c_void_p), C.c_int32(1), ne.ctypes.data_as(C.c_void_p),
+                                   C.c_int32(2), names, types, (C.c_int32 * 2)(4, 4)))
+    return d, pts, faces, ow, ne
+
+
+def test_polyhedral_mesh_matches_the_oracle_geometry(tmp_path):
+    d, pts, faces, ow, ne = _write_prisms(tmp_path)
+    r = MeshDesc.from_polymesh(d)
+    assert (r.nCells, r.nInternalFaces, r.nBoundaryFaces, r.nPatches) == (2, 1, 8, 2)
+    assert r.patch_names == ["walls0", "walls1"] and r.patch_types == ["wall", "patch"]
+    Cf, Sf = opoly.face_geometry(pts, [np.array(f) for f in faces])
+    Cc, V = opoly.cell_geometry(Cf, Sf, ow, ne, 2)
+    assert np.allclose(r.array("faceCentres"), Cf, rtol=1e-15, atol=1e-16) and np.allclose(r.array("faceAreas"), Sf, rtol=1e-15, atol=1e-16)
+    assert np.allclose(r.array("cellVolumes"), V, rtol=1e-15) and np.allclose(r.array("cellCentres"), Cc, rtol=1e-15)
+    assert np.allclose(r.array("cellVolumes"), [0.5, 0.5], rtol=1e-15)
+    # closed cells: the outward face area vectors of a cell sum to zero
+    s = np.zeros((2, 3))
+    own, Sfr = r.array("faceOwner"), r.array("faceAreas")
+    for f in range(r.nFaces):
+        s[own[f]] += Sfr[f]
+    s[r.array("faceNeighbour")[0]] -= Sfr[0]
+    assert np.abs(s).max() < 1e-15
+    # and the oracle's own file reader sees the same mesh in the files we wrote
+    assert np.array_equal(opoly.read_label_list(d / "owner"), ow) and np.allclose(opoly.read_points(d / "points"), pts)
+
+
+def test_malformed_input_fails_loudly(tmp_path):
+    with pytest.raises(FvkError):
+        MeshDesc.from_polymesh(tmp_path / "nowhere")
+    d, *_ = _write_prisms(tmp_path)
+    (d / "neighbour").write_text((d / "neighbour").read_text().replace("format      ascii", "format      binary"))
+    with pytest.raises(FvkError) as e:
+        MeshDesc.from_polymesh(d)
+    assert "binary" in str(e.value)
+    d2 = tmp_path / "b"
+    d2.mkdir()
+    for f in ("points", "faces", "owner", "neighbour"):
+        (d2 / f).write_text((d / f).read_text().replace("binary", "ascii"))
+    (d2 / "boundary").write_text((d / "boundary").read_text().replace("startFace       5", "startFace       6"))
+    with pytest.raises(FvkError) as e:
+        MeshDesc.from_polymesh(d2)
+    assert "does not start" in str(e.value)
+
+
+@pytest.mark.gpu
+def test_polyhedral_mesh_through_the_kernels(tmp_path):
+    """A mesh read from polyMesh files (triangular and quadrilateral faces, cells with 5 faces, 4 boundary faces per cell:
+    the overflow path of the brick plan's code lists) through the explicit operators, the assembly and SpMV: bit-identical
+    to the Serial oracle on the same description."""
+    import torch
+    from foamadapter_b200 import la, ops
+    from foamadapter_b200.mesh import UnstructuredMesh
+    from oracle.cpu import Mesh as OMesh
+    d, *_ = _write_prisms(tmp_path)
+    desc = MeshDesc.from_polymesh(d)
+    gm, om = UnstructuredMesh(desc), OMesh.from_desc(desc)
+    dev = lambda a: torch.as_tensor(np.ascontiguousarray(a), device="cuda")
+    rng = np.random.default_rng(3)
+    phi, phib, flux = rng.uniform(1, 2, om.nC), rng.uniform(1, 2, om.nB), rng.uniform(-1, 1, om.nF)
+    out = torch.zeros(om.nC, dtype=torch.float64, device="cuda")
+    assert np.array_equal(ops.div(gm, dev(flux), dev(phi), dev(phib), out).cpu().numpy(), om.div(flux, phi, phib, 0))
+    assert np.array_equal(ops.laplacian(gm, dev(phi), dev(phib), out).cpu().numpy(), om.laplacian(phi, phib))
+    o3 = torch.zeros((om.nC, 3), dtype=torch.float64, device="cuda")
+    assert np.array_equal(ops.grad(gm, dev(phi), dev(phib), o3).cpu().numpy(), om.grad(phi, phib))
+    vals, x = rng.uniform(-1, 1, om.nnz), rng.uniform(-1, 1, om.nC)
+    sp = la.SparsityPattern.readOrCreate(gm)
+    assert np.array_equal(la.spmv(sp, dev(vals), dev(x)).cpu().numpy(), om.spmv(vals, x))
+    assert np.array_equal(la.spmv_structured(gm, dev(vals), dev(x)).cpu().numpy(), om.spmv(vals, x))
