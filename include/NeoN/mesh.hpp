@@ -22,10 +22,12 @@ class UnstructuredMesh
     {
         fvk_mesh* h = nullptr;
         fvk_mesh_desc* blockDesc = nullptr; // owned when created by the block generator
+        fvk_mesh_desc* polyDesc = nullptr;  // owned when read from a polyMesh directory
         ~Impl()
         {
             if (h) fvk_mesh_destroy(h);
             if (blockDesc) fvk_blockmesh_destroy(blockDesc);
+            if (polyDesc) fvk_polymesh_destroy(polyDesc);
         }
     };
 
@@ -54,6 +56,24 @@ public:
         check(fvk_blockmesh_create(nx, ny, nz, lx, ly, lz, int32_t(patches.size()), nSides.data(), sides.data(), empty.data(), 0, &d));
         UnstructuredMesh m(exec, *d, names);
         m.impl_->blockDesc = d;
+        return m;
+    }
+
+    // FoamAdapter::readOpenFOAMMesh (src/datastructures/meshAdapter.cpp:59-136) without OpenFOAM: an ASCII
+    // constant/polyMesh directory (points, faces, owner, neighbour, boundary); `empty` patches are dropped
+    static UnstructuredMesh readPolyMesh(const Executor& exec, const std::string& polyMeshDir)
+    {
+        fvk_mesh_desc* d = nullptr;
+        check(fvk_polymesh_read(polyMeshDir.c_str(), &d));
+        std::vector<std::string> names;
+        char name[256], type[256];
+        for (int32_t p = 0; p < d->nPatches; ++p)
+        {
+            check(fvk_polymesh_patch(d, p, name, sizeof name, type, sizeof type));
+            names.emplace_back(name);
+        }
+        UnstructuredMesh m(exec, *d, names);
+        m.impl_->polyDesc = d;
         return m;
     }
 
