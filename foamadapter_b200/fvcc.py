@@ -180,3 +180,44 @@ def computeCoNum(faceFlux: SurfaceField, dt: float) -> float:
     """auxiliary/coNum.cpp:18-96; returns maxCoNum (device->host scalar, like the reference)."""
     res = ops.conum(faceFlux.mesh, faceFlux.internal, dt)
     return float(res[0].item())
+
+
+def read_field_file(path, nCells: int):
+    """internalField of an OpenFOAM ASCII field file -> numpy array [nCells] or [nCells, 3] (fvk_fieldfile_read_internal)."""
+    import ctypes as C
+    import numpy as np
+    from ._capi import check, lib
+    nc = C.c_int32(0)
+    out = np.zeros(3 * max(nCells, 1))
+    check(lib().fvk_fieldfile_read_internal(str(path).encode(), C.c_int32(nCells), C.byref(nc), out.ctypes.data_as(C.c_void_p), C.c_int64(out.size)))
+    return out[:nCells].copy() if nc.value == 1 else out[: 3 * nCells].reshape(nCells, 3).copy()
+
+
+def read_patch_conditions(path, patch_names):
+    """[(type, uniform value or None)] per patch from the boundaryField of an OpenFOAM ASCII field file: the (type,
+    constant) list VolumeField takes (readers.hpp:43-95 of the reference maps the same dictionaries)."""
+    import ctypes as C
+    import numpy as np
+    from ._capi import check, lib
+    bcs = []
+    for name in patch_names:
+        typ, has, nc = C.create_string_buffer(128), C.c_int32(0), C.c_int32(0)
+        val = np.zeros(3)
+        check(lib().fvk_fieldfile_read_patch(str(path).encode(), name.encode(), typ, C.c_int32(128), C.c_int32(1), C.byref(has), C.byref(nc),
+                                             val.ctypes.data_as(C.c_void_p), C.c_int64(3)))
+        v = None if not has.value else (float(val[0]) if nc.value == 1 else tuple(float(x) for x in val))
+        bcs.append((typ.value.decode(), v))
+    return bcs
+
+
+def read_volume_field(mesh, path, name=None, device="cuda"):
+    """VolumeField from an OpenFOAM ASCII field file on a mesh whose patches carry names (e.g. MeshDesc.from_polymesh)."""
+    import os
+    internal = read_field_file(path, mesh.nOwned)
+    ncomp = 3 if internal.ndim == 2 else 1
+    zero = (0.0, 0.0, 0.0) if ncomp == 3 else 0.0
+    bcs = [(t, v if v is not None else zero) for t, v in read_patch_conditions(path, mesh.patch_names)]
+    f = VolumeField(mesh, name or os.path.basename(str(path)), ncomp, bcs, device)
+    f.internal[: mesh.nOwned].copy_(torch.from_numpy(internal))
+    f.correctBoundaryConditions()
+    return f

@@ -146,6 +146,15 @@ int fvk_polymesh_write(const char* polyMeshDir, int32_t nPoints, const double* p
                        int32_t nInternalFaces, const int32_t* neighbour, int32_t nPatches,
                        const char* const* patchNames, const char* const* patchTypes, const int32_t* patchSizes);
 
+/* OpenFOAM ASCII field files (0/T, 0/U, 0/phi ...) without OpenFOAM, formats as in the reference's fixtures
+ * (test/setup_operator/0/): `internalField uniform v | nonuniform List<scalar|vector> n (...)` and the per-patch
+ * dictionaries of `boundaryField`. Host only. out (may be NULL to query ncomp) receives nCells * ncomp doubles. */
+int fvk_fieldfile_read_internal(const char* path, int32_t nCells, int32_t* ncomp, double* out, int64_t outCapacity);
+/* type of patch `patchName` and, when the dictionary has a `value` entry (hasValue = 1), its nPatchFaces * ncomp values
+ * (a uniform value is expanded); nPatchFaces < 0 skips the length check of a nonuniform list */
+int fvk_fieldfile_read_patch(const char* path, const char* patchName, char* type, int32_t typeCap, int32_t nPatchFaces,
+                             int32_t* hasValue, int32_t* ncomp, double* out, int64_t outCapacity);
+
 /* ------------------------------------------------------------------------------------------------
  * Device mesh handle. Uploads the description and builds, once per mesh:
  *   - BasicGeometryScheme weights / deltaCoeffs / nonOrthDeltaCoeffs

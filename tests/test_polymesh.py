@@ -169,3 +169,71 @@ def test_polyhedral_mesh_through_the_kernels(tmp_path):
     sp = la.SparsityPattern.readOrCreate(gm)
     assert np.array_equal(la.spmv(sp, dev(vals), dev(x)).cpu().numpy(), om.spmv(vals, x))
     assert np.array_equal(la.spmv_structured(gm, dev(vals), dev(x)).cpu().numpy(), om.spmv(vals, x))
+
+
+def _field_file(path, cls, internal, patches):
+    txt = ["FoamFile\n{\n    version 2.0;\n    format ascii;\n    class " + cls + ";\n    object " + path.name + ";\n}\n",
+           "// a comment\ndimensions      [0 0 0 1 0 0 0];\n", "internalField   " + internal + ";\n", "boundaryField\n{\n"]
+    for name, body in patches:
+        txt.append(f"    {name}\n    {{\n{body}    }}\n")
+    txt.append("}\n")
+    path.write_text("\n".join(txt))
+    return path
+
+
+def test_field_file_reader(tmp_path):
+    """fvk_fieldfile_read_*: the formats of the reference's test/setup_operator/0/ files."""
+    from foamadapter_b200 import fvcc
+    rng = np.random.default_rng(5)
+    T = rng.uniform(1, 2, 25)
+    p = _field_file(tmp_path / "T", "volScalarField", "nonuniform List<scalar> 25\n(\n" + "\n".join(repr(float(v)) for v in T) + "\n)",
+                    [("movingWall", "        type            fixedValue;\n        value           uniform 10.5;\n"),
+                     ("fixedWalls", "        type            zeroGradient;\n"), ("frontAndBack", "        type            empty;\n")])
+    assert np.array_equal(fvcc.read_field_file(p, 25), T)            # repr round-trips doubles exactly
+    assert fvcc.read_patch_conditions(p, ["movingWall", "fixedWalls", "frontAndBack"]) == [("fixedValue", 10.5), ("zeroGradient", None), ("empty", None)]
+    U = rng.uniform(-1, 1, (25, 3))
+    u = _field_file(tmp_path / "U", "volVectorField", "nonuniform List<vector> 25\n(\n" + "\n".join("(%r %r %r)" % tuple(map(float, v)) for v in U) + "\n)",
+                    [("movingWall", "        type            fixedValue;\n        value           uniform (1 0 0);\n"),
+                     ("fixedWalls", "        type            noSlip;\n")])
+    assert np.array_equal(fvcc.read_field_file(u, 25), U)
+    assert fvcc.read_patch_conditions(u, ["movingWall", "fixedWalls"]) == [("fixedValue", (1.0, 0.0, 0.0)), ("noSlip", None)]
+    q = _field_file(tmp_path / "p", "volScalarField", "uniform 0", [("movingWall", "        type            zeroGradient;\n")])
+    assert np.array_equal(fvcc.read_field_file(q, 25), np.zeros(25))
+    v = _field_file(tmp_path / "U0", "volVectorField", "uniform (0 0.5 -2)", [])
+    assert np.array_equal(fvcc.read_field_file(v, 4), np.tile([0.0, 0.5, -2.0], (4, 1)))
+    with pytest.raises(FvkError):
+        fvcc.read_field_file(p, 24)                                   # wrong cell count
+    with pytest.raises(FvkError):
+        fvcc.read_patch_conditions(p, ["noSuchPatch"])
+    with pytest.raises(FvkError):
+        fvcc.read_field_file(tmp_path / "missing", 25)
+
+
+@pytest.mark.gpu
+def test_reference_case_from_files_through_the_gpu(tmp_path):
+    """The reference's test/setup_operator case rebuilt as FILES (polyMesh + 0/T written from the golden vectors), loaded
+    by the product readers, through the GPU operators: the reference's own 16-digit divT / gradT come out."""
+    import torch
+    from pathlib import Path
+    from foamadapter_b200 import fvcc
+    from foamadapter_b200.mesh import UnstructuredMesh
+    z = np.load(Path(__file__).parent / "golden" / "setup_operator.npz")
+    d = _write_raw(tmp_path / "constant" / "polyMesh", z["points"], [list(f) for f in z["faces"]], z["owner"], z["neighbour"],
+                   z["patch_names"], z["patch_types"], z["patch_size"])
+    desc = MeshDesc.from_polymesh(d)
+    gm = UnstructuredMesh(desc)
+    assert gm.patch_names == desc.patch_names and (gm.nCells, gm.nInternalFaces, gm.nBoundaryFaces) == (25, 40, 20)
+    (tmp_path / "0").mkdir()
+    bodies = [(str(n), "        type            empty;\n" if str(t) == "empty" else "        type            zeroGradient;\n")
+              for n, t in zip(z["patch_names"], z["patch_types"])]
+    tf = _field_file(tmp_path / "0" / "T", "volScalarField",
+                     "nonuniform List<scalar> 25\n(\n" + "\n".join(repr(float(v)) for v in z["field_T"]) + "\n)", bodies)
+    T = fvcc.read_volume_field(gm, tf)
+    assert T.ncomp == 1 and [k for k, _ in T.bcs] == ["zeroGradient"] * gm.nPatches
+    phi = fvcc.SurfaceField(gm, "phi")
+    phi.internal[: gm.nInternalFaces] = torch.as_tensor(z["field_phi"], device="cuda")
+    div = torch.zeros(gm.nCells, dtype=torch.float64, device="cuda")
+    fvcc.GaussGreenDiv(gm, "linear").div(div, phi, T, fvcc.Coeff(1.0))
+    np.testing.assert_allclose(div.cpu().numpy(), z["field_divT_Serial"], rtol=5e-15, atol=0)
+    grad = fvcc.GaussGreenGrad(gm).grad(T).cpu().numpy()
+    np.testing.assert_allclose(grad[:, :2], z["field_gradT_Serial"][:, :2], rtol=0, atol=1e-12)
