@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Multi-GPU parity check over both transports, NCCL and peer-memory windows (run under torchrun, one rank per GPU):
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/mgpu_check.py
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_check.py
 Checks, against the single-domain CPU oracle on the same global mesh: halo exchange through fvk_comm, explicit
 operators (bit-exact on owned cells), distributed Jacobi-CG (iteration count +-1, solution), and two neoIcoFoam steps."""
 import os
@@ -11,7 +11,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-ROOT = Path(__file__).resolve().parents[1]
+ROOT = Path(__file__).resolve().parents[1]  # this script lives in tests/: it is the multi-GPU parity test (oracle = checker)
 sys.path.insert(0, str(ROOT))
 from foamadapter_b200 import la, ops, piso  # noqa: E402
 from foamadapter_b200.decomp import Comm, Decomposition  # noqa: E402

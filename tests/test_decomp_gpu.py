@@ -1,5 +1,5 @@
 """GPU tests of the decomposed path on ONE device: every rank's sub-mesh lives on the same GPU and the halo exchange is
-emulated with device copies that follow the fvk_comm plan (the NCCL transport itself is exercised by tools/mgpu_check.py
+emulated with device copies that follow the fvk_comm plan (the NCCL transport itself is exercised by tests/mgpu_check.py
 under torchrun). Explicit operators on a sub-domain are asserted BIT-EXACT against the single-domain GPU result: ghost
 cells + faceOrder keep the per-cell accumulation order of the undecomposed mesh."""
 import numpy as np
