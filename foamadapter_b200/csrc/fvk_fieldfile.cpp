@@ -188,3 +188,38 @@ extern "C" int fvk_fieldfile_read_patch(const char* path, const char* patchName,
     if (hasValue) *hasValue = 1;
     return parseValue(s, vk, path, nPatchFaces, ncomp, out, outCapacity, nullptr, nullptr);
 }
+
+// Writer: a vol<Scalar|Vector>Field file with a nonuniform internal field and one dictionary per patch
+// (`type`, and `value uniform v` where patchHasValue[p] != 0). 17 significant digits: values round-trip exactly.
+extern "C" int fvk_fieldfile_write(const char* path, const char* objectName, int32_t ncomp, int32_t nCells, const double* internal,
+                                   int32_t nPatches, const char* const* patchNames, const char* const* patchTypes,
+                                   const int32_t* patchHasValue, const double* patchValues /* [nPatches*ncomp] */)
+{
+    if (!path || !objectName || (ncomp != 1 && ncomp != 3) || nCells < 0 || (nCells && !internal) || nPatches < 0
+        || (nPatches && (!patchNames || !patchTypes)))
+        return fvk_fail(FVK_EINVAL, "fvk_fieldfile_write: bad argument");
+    FILE* fp = std::fopen(path, "w");
+    if (!fp) return fvk_fail(FVK_EINVAL, "fvk_fieldfile_write: cannot open %s", path);
+    std::fprintf(fp, "FoamFile\n{\n    version     2.0;\n    format      ascii;\n    class       %s;\n    object      %s;\n}\n\n",
+                 ncomp == 1 ? "volScalarField" : "volVectorField", objectName);
+    std::fprintf(fp, "dimensions      [0 0 0 0 0 0 0];\n\ninternalField   nonuniform List<%s> %d\n(\n", ncomp == 1 ? "scalar" : "vector", nCells);
+    for (int32_t c = 0; c < nCells; ++c)
+    {
+        if (ncomp == 1) std::fprintf(fp, "%.17g\n", internal[c]);
+        else std::fprintf(fp, "(%.17g %.17g %.17g)\n", internal[3 * c], internal[3 * c + 1], internal[3 * c + 2]);
+    }
+    std::fprintf(fp, ")\n;\n\nboundaryField\n{\n");
+    for (int32_t p = 0; p < nPatches; ++p)
+    {
+        std::fprintf(fp, "    %s\n    {\n        type            %s;\n", patchNames[p], patchTypes[p]);
+        if (patchHasValue && patchHasValue[p] && patchValues)
+        {
+            if (ncomp == 1) std::fprintf(fp, "        value           uniform %.17g;\n", patchValues[p]);
+            else std::fprintf(fp, "        value           uniform (%.17g %.17g %.17g);\n", patchValues[3 * p], patchValues[3 * p + 1], patchValues[3 * p + 2]);
+        }
+        std::fprintf(fp, "    }\n");
+    }
+    std::fprintf(fp, "}\n");
+    std::fclose(fp);
+    return FVK_OK;
+}

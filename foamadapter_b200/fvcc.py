@@ -221,3 +221,24 @@ def read_volume_field(mesh, path, name=None, device="cuda"):
     f.internal[: mesh.nOwned].copy_(torch.from_numpy(internal))
     f.correctBoundaryConditions()
     return f
+
+
+def write_field_file(path, internal, patch_names, bcs, name=None):
+    """Write an OpenFOAM ASCII vol<Scalar|Vector>Field file (fvk_fieldfile_write). bcs: [(type, value or None)] per patch."""
+    import ctypes as C
+    import os
+    import numpy as np
+    from ._capi import check, lib
+    a = np.ascontiguousarray(internal, dtype=np.float64)
+    ncomp = 3 if a.ndim == 2 else 1
+    n = a.shape[0]
+    names = (C.c_char_p * len(patch_names))(*[p.encode() for p in patch_names])
+    types = (C.c_char_p * len(bcs))(*[t.encode() for t, _ in bcs])
+    has = (C.c_int32 * len(bcs))(*[0 if v is None else 1 for _, v in bcs])
+    vals = np.zeros(max(len(bcs), 1) * ncomp)
+    for i, (_, v) in enumerate(bcs):
+        if v is not None:
+            vals[i * ncomp:(i + 1) * ncomp] = v
+    check(lib().fvk_fieldfile_write(str(path).encode(), (name or os.path.basename(str(path))).encode(), C.c_int32(ncomp), C.c_int32(n),
+                                    a.ctypes.data_as(C.c_void_p), C.c_int32(len(bcs)), names, types, has, vals.ctypes.data_as(C.c_void_p)))
+    return path

@@ -154,6 +154,11 @@ int fvk_fieldfile_read_internal(const char* path, int32_t nCells, int32_t* ncomp
  * (a uniform value is expanded); nPatchFaces < 0 skips the length check of a nonuniform list */
 int fvk_fieldfile_read_patch(const char* path, const char* patchName, char* type, int32_t typeCap, int32_t nPatchFaces,
                              int32_t* hasValue, int32_t* ncomp, double* out, int64_t outCapacity);
+/* write a vol<Scalar|Vector>Field file (nonuniform internal field, per patch `type` and, where patchHasValue[p] != 0,
+ * `value uniform patchValues[p*ncomp..]`); 17 significant digits, so a written field reads back bit for bit */
+int fvk_fieldfile_write(const char* path, const char* objectName, int32_t ncomp, int32_t nCells, const double* internal,
+                        int32_t nPatches, const char* const* patchNames, const char* const* patchTypes,
+                        const int32_t* patchHasValue, const double* patchValues);
 
 /* ------------------------------------------------------------------------------------------------
  * Device mesh handle. Uploads the description and builds, once per mesh:

@@ -237,3 +237,16 @@ def test_reference_case_from_files_through_the_gpu(tmp_path):
     np.testing.assert_allclose(div.cpu().numpy(), z["field_divT_Serial"], rtol=5e-15, atol=0)
     grad = fvcc.GaussGreenGrad(gm).grad(T).cpu().numpy()
     np.testing.assert_allclose(grad[:, :2], z["field_gradT_Serial"][:, :2], rtol=0, atol=1e-12)
+
+
+def test_field_file_round_trip(tmp_path):
+    from foamadapter_b200 import fvcc
+    rng = np.random.default_rng(8)
+    T, U = rng.uniform(-1e3, 1e3, 37), rng.uniform(-1, 1, (37, 3)) * 10.0 ** rng.integers(-12, 12, (37, 3))
+    names = ["inlet", "walls"]
+    fvcc.write_field_file(tmp_path / "T", T, names, [("fixedValue", 0.1), ("zeroGradient", None)])
+    fvcc.write_field_file(tmp_path / "U", U, names, [("fixedValue", (1.0, -2.5, 1e-9)), ("noSlip", None)])
+    assert np.array_equal(fvcc.read_field_file(tmp_path / "T", 37), T) and np.array_equal(fvcc.read_field_file(tmp_path / "U", 37), U)
+    assert fvcc.read_patch_conditions(tmp_path / "T", names) == [("fixedValue", 0.1), ("zeroGradient", None)]
+    assert fvcc.read_patch_conditions(tmp_path / "U", names) == [("fixedValue", (1.0, -2.5, 1e-9)), ("noSlip", None)]
+    assert np.array_equal(opoly.read_internal_field(tmp_path / "U"), U)   # the oracle's reader sees the same file
