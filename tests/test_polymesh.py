@@ -250,3 +250,32 @@ def test_field_file_round_trip(tmp_path):
     assert fvcc.read_patch_conditions(tmp_path / "T", names) == [("fixedValue", 0.1), ("zeroGradient", None)]
     assert fvcc.read_patch_conditions(tmp_path / "U", names) == [("fixedValue", (1.0, -2.5, 1e-9)), ("noSlip", None)]
     assert np.array_equal(opoly.read_internal_field(tmp_path / "U"), U)   # the oracle's reader sees the same file
+
+
+def test_reader_tolerates_formatting_variants(tmp_path):
+    """Same mesh, three spellings: as written by fvk_polymesh_write, everything on one line with block comments, and with the
+    `inGroups List<word> 1(wall);` / extra-key boundary dictionaries real OpenFOAM cases carry."""
+    d, pts, faces, ow, ne = _write_prisms(tmp_path)
+    ref = MeshDesc.from_polymesh(d)
+    d2 = tmp_path / "compact"
+    d2.mkdir()
+    hdr = "FoamFile { version 2.0; format ascii; class x; object y; } /* block\ncomment */ "
+    (d2 / "points").write_text(hdr + f"{len(pts)}(" + " ".join("(%r %r %r)" % tuple(map(float, p)) for p in pts) + ")")
+    (d2 / "faces").write_text(hdr + f"{len(faces)} ( " + "  ".join(f"{len(f)}(" + " ".join(map(str, f)) + ")" for f in faces) + " )  // tail")
+    (d2 / "owner").write_text(hdr + f"{len(ow)}(" + " ".join(map(str, ow)) + ")")
+    (d2 / "neighbour").write_text(hdr + "1\n(\n1 // the only internal face\n)\n")
+    (d2 / "boundary").write_text(hdr + """2
+(
+    walls0 { type wall; inGroups List<word> 1(wall); physicalType wall; nFaces 4; startFace 1; }
+    walls1
+    {
+        type            patch;
+        startFace       5;   // keys in any order
+        nFaces          4;
+    }
+)
+""")
+    r = MeshDesc.from_polymesh(d2)
+    assert r.patch_names == ref.patch_names and r.patch_types == ref.patch_types
+    for name in ARRAYS:
+        assert np.array_equal(r.array(name), ref.array(name)), name
