@@ -394,18 +394,93 @@ def run_native(args, rank, world, local_rank):
         r_grad.copy_(out_grad, non_blocking=True)
         r_lap.copy_(out_lap, non_blocking=True)
 
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    e_start.record(stream)
-    for _ in range(e2e_steps):
-        e2e_step()
-    e_end.record(stream)
-    barrier()
-    t = torch.tensor([e_start.elapsed_time(e_end)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    # Double-buffered variant of the same step: H2D of step k+1 and D2H of step k-1 run beside the operators of step k on
+    # three streams (PCIe is full duplex). Every step still copies ITS inputs from pinned host memory and ITS results back
+    # inside the timed region; the result on the host is checked against the sequential path before the number is used.
+    def make_pipeline():
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        bufs = []
+        for b in range(2):
+            f = fields[b]
+            fl = flux if b == 0 else torch.empty_like(flux)
+            od, og, ol = (out_div, out_grad, out_lap) if b == 0 else (torch.empty_like(out_div), torch.empty_like(out_grad), torch.empty_like(out_lap))
+            bufs.append(dict(
+                f=f, flux=fl, outs=(od, og, ol),
+                a_div=(mesh.handle, C.c_int(0), ptr(fl), ptr(f.internal), ptr(f.boundary.value), one, None, ptr(od), C.c_int(0), s),
+                a_grad=(mesh.handle, ptr(f.internal), ptr(f.boundary.value), ptr(og), C.c_int(0), s),
+                a_lap=(mesh.handle, ptr(f.internal), ptr(f.boundary.value), one, None, ptr(ol), C.c_int(0), s),
+                in_ready=torch.cuda.Event(), comp_done=torch.cuda.Event(), out_copied=torch.cuda.Event()))
+
+        def run(n):
+            for k in range(n):
+                B = bufs[k % 2]
+                with torch.cuda.stream(s_in):
+                    if k >= 2:
+                        s_in.wait_event(B["comp_done"])   # the operators of step k-2 have consumed this buffer's inputs
+                    else:
+                        s_in.wait_stream(stream)
+                    B["f"].internal.copy_(T_pin, non_blocking=True)
+                    B["flux"].copy_(flux_pin, non_blocking=True)
+                    B["in_ready"].record(s_in)
+                stream.wait_event(B["in_ready"])
+                if k >= 2:
+                    stream.wait_event(B["out_copied"])    # the results of step k-2 are on the host
+                halo(B["f"].internal)
+                B["f"].correctBoundaryConditions()
+                rc = L.fvk_div_s(*B["a_div"]) | L.fvk_grad_s(*B["a_grad"]) | L.fvk_laplacian_s(*B["a_lap"])
+                if rc:
+                    raise RuntimeError(L.fvk_last_error().decode())
+                B["comp_done"].record(stream)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(B["comp_done"])
+                    r_div.copy_(B["outs"][0], non_blocking=True)
+                    r_grad.copy_(B["outs"][1], non_blocking=True)
+                    r_lap.copy_(B["outs"][2], non_blocking=True)
+                    B["out_copied"].record(s_out)
+            for b in range(min(n, 2)):
+                stream.wait_event(bufs[b]["out_copied"])  # the timed region ends when the last results are on the host
+        return run, bufs
+
+    e2e_steps = max(4, min(args.steps, 10))
+
+    def measure(run):
+        run(2)
+        barrier()
+        e_start.record(stream)
+        run(e2e_steps)
+        e_end.record(stream)
+        barrier()
+        tt = torch.tensor([e_start.elapsed_time(e_end)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return tt
+
+    def sequential(n):
+        for _ in range(n):
+            e2e_step()
+
+    t = measure(sequential)
+    e2e_mode = "sequential copies and operators on one stream"
+    ref_host = (r_div.clone(), r_grad.clone(), r_lap.clone())
+    try:
+        if world > 1:
+            raise RuntimeError("multi-GPU arm keeps the sequential e2e step")
+        run_p, bufs = make_pipeline()
+        t_p = measure(run_p)
+        torch.cuda.synchronize()
+        same = all(torch.equal(a, b) for a, b in zip(ref_host, (r_div, r_grad, r_lap))) and all(
+            torch.equal(x, y) for x, y in zip(bufs[0]["outs"], bufs[1]["outs"]))
+        flag = torch.tensor([1 if same else 0], dtype=torch.int32, device=dev)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 1 and float(t_p.item()) < float(t.item()):
+            t, e2e_mode = t_p, "double-buffered: H2D / operators / D2H of consecutive steps overlap on three streams (results verified on the host)"
+        elif int(flag.item()) != 1:
+            print("bench.py: pipelined e2e results differ from the sequential path; reporting the sequential number", file=sys.stderr)
+        del bufs
+    except Exception as exc:  # the sequential measurement stands
+        if world == 1:
+            print(f"bench.py: pipelined e2e not available ({exc!r}); reporting the sequential number", file=sys.stderr)
     e2e_ms = float(t.item()) / e2e_steps
     e2e_value = 3.0 * nF_global / (e2e_ms * 1e-3)
 
@@ -436,7 +511,7 @@ def run_native(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                          "frac": kernels[dom]["frac"], "traffic": traffic, "peak_kind": peak_kind},
             "kernels": kernels,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "mode": e2e_mode},
             "gpu_launches": (3 if world == 1 else 12) * args.steps,
             "clocks": clocks,
         }
