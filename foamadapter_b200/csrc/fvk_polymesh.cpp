@@ -549,3 +549,17 @@ extern "C" int fvk_polymesh_write(const char* polyMeshDir, int32_t nPoints, cons
     std::fclose(fp);
     return FVK_OK;
 }
+
+// labelList files, e.g. constant/cellDecomposition written by `decomposePar -cellDist` (any decomposition method:
+// scotch, hierarchical, ...): the cell -> rank map fvk_decompose takes.
+extern "C" int fvk_labellist_read(const char* path, int32_t nExpected, int32_t* out)
+{
+    if (!path || nExpected < 0 || (nExpected && !out)) return fvk_fail(FVK_EINVAL, "fvk_labellist_read: bad argument");
+    std::vector<int32_t> v;
+    std::string err;
+    if (!readLabels(path, v, err)) return fvk_fail(FVK_EINVAL, "fvk_labellist_read: %s", err.c_str());
+    if (int64_t(v.size()) != nExpected)
+        return fvk_fail(FVK_EINVAL, "fvk_labellist_read: %s has %zu entries, expected %d", path, v.size(), nExpected);
+    if (nExpected) std::memcpy(out, v.data(), sizeof(int32_t) * v.size());
+    return FVK_OK;
+}

@@ -20,6 +20,14 @@ def simple_map(gdesc: MeshDesc, n) -> np.ndarray:
     return out
 
 
+def read_cell_decomposition(path, nCells: int) -> np.ndarray:
+    """cell -> rank map from an OpenFOAM labelList file (`decomposePar -cellDist` writes constant/cellDecomposition);
+    pass it as `cellRank=` to Decomposition (any decomposition method)."""
+    out = np.zeros(nCells, dtype=np.int32)
+    check(lib().fvk_labellist_read(str(path).encode(), C.c_int32(nCells), out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
 def default_split(nRanks: int):
     """n (px py pz) for 1/2/4/8 ranks: 8 -> 2x2x2, 4 -> 2x2x1, 2 -> 2x1x1."""
     return {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(nRanks) or (nRanks, 1, 1)

@@ -146,6 +146,10 @@ int fvk_polymesh_write(const char* polyMeshDir, int32_t nPoints, const double* p
                        int32_t nInternalFaces, const int32_t* neighbour, int32_t nPatches,
                        const char* const* patchNames, const char* const* patchTypes, const int32_t* patchSizes);
 
+/* ASCII labelList file with exactly nExpected entries, e.g. constant/cellDecomposition of `decomposePar -cellDist`
+ * (scotch, hierarchical, ... -- the reference's cases name several methods in system/decomposeParDict): the cellRank map
+ * of fvk_decompose. */
+int fvk_labellist_read(const char* path, int32_t nExpected, int32_t* out);
 /* OpenFOAM ASCII field files (0/T, 0/U, 0/phi ...) without OpenFOAM, formats as in the reference's fixtures
  * (test/setup_operator/0/): `internalField uniform v | nonuniform List<scalar|vector> n (...)` and the per-patch
  * dictionaries of `boundaryField`. Host only. out (may be NULL to query ncomp) receives nCells * ncomp doubles. */

@@ -138,3 +138,30 @@ def test_gloo_world_size_2_halo_protocol():
     ret = mgr.dict()
     mp.spawn(_gloo_worker, args=(2, port, ret), nprocs=2, join=True)
     assert ret.get(0) and ret.get(1)
+
+
+def test_external_cell_decomposition_file(tmp_path):
+    """A cellDecomposition file as `decomposePar -cellDist` writes it (any method; here a deliberately irregular map)
+    drives the same ghost-cell decomposition: every cell owned exactly once, halo plans consistent between ranks."""
+    from foamadapter_b200.decomp import read_cell_decomposition
+    g = MeshDesc.block(6, 5, 4)
+    rng = np.random.default_rng(9)
+    rank_of = (np.arange(g.nCells) * 3 // g.nCells).astype(np.int32)
+    rank_of[rng.choice(g.nCells, 15, replace=False)] = rng.integers(0, 3, 15)      # ragged sub-domains
+    f = tmp_path / "cellDecomposition"
+    f.write_text("FoamFile\n{\n    version 2.0;\n    format ascii;\n    class labelList;\n    object cellDecomposition;\n}\n\n"
+                 + f"{g.nCells}\n(\n" + "\n".join(map(str, rank_of)) + "\n)\n")
+    m = read_cell_decomposition(f, g.nCells)
+    assert np.array_equal(m, rank_of)
+    decs = [Decomposition(g, 3, r, cellRank=m) for r in range(3)]
+    owned = np.concatenate([d.cellGlobal[: d.nOwned] for d in decs])
+    assert np.array_equal(np.sort(owned), np.arange(g.nCells))
+    for d in decs:
+        for k, nb in enumerate(d.nbrRanks):
+            o = decs[nb]
+            kk = list(o.nbrRanks).index(d.rank)
+            sent = o.cellGlobal[o.sendCells[o.sendOff[kk]: o.sendOff[kk + 1]]]
+            assert np.array_equal(sent, d.cellGlobal[d.nOwned + d.recvOff[k]: d.nOwned + d.recvOff[k + 1]])
+    from foamadapter_b200._capi import FvkError
+    with pytest.raises(FvkError):
+        read_cell_decomposition(f, g.nCells + 1)
