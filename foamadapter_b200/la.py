@@ -166,8 +166,11 @@ class Solver:
         except Exception:
             pass
 
-    def solve_csr(self, nRows, nCols, rowOffs_ptr, colIdxs_ptr, values, b, x) -> SolverStats:
+    def solve_csr(self, nRows, nCols, rowOffs_ptr, colIdxs_ptr, values, b, x, _mesh=None) -> SolverStats:
         h = self._handle(nRows, nCols)
+        if _mesh is None and getattr(self, "_attached", None) is not None:
+            check(lib().fvk_solver_attach_mesh(h, None))  # a foreign CSR: no structured shortcut
+            self._attached = None
         st = _Stats()
         nh = self.cfg.maxIter + 2 if self.history else 0
         hist = np.zeros(max(nh, 1))
@@ -183,7 +186,7 @@ class Solver:
         if getattr(self, "_attached", None) is not m:  # structured SpMV fast path when the mesh plan allows it
             check(lib().fvk_solver_attach_mesh(h, m.handle))
             self._attached = m
-        return self.solve_csr(m.nOwned, m.nCells, ls.sp.rowOffs_ptr, ls.sp.colIdxs_ptr, ls.values, ls.rhs, x)
+        return self.solve_csr(m.nOwned, m.nCells, ls.sp.rowOffs_ptr, ls.sp.colIdxs_ptr, ls.values, ls.rhs, x, _mesh=m)
 
 
 # ---- Vector free functions (vectorFreeFunctions.cpp:18-106) ----------------------------------------
