@@ -97,3 +97,25 @@ def test_affine_topology_is_proven_only_where_it_holds():
     for P in (4, 8):
         for r in range(P):
             assert affine_info(Decomposition(MeshDesc.block(16, 12, 10), P, r).desc)[0] == 1
+
+
+def test_random_blocks_and_their_sub_domains():
+    """Randomised sweep (fixed seed): the plan replays the reference order on every block mesh and every sub-domain of a
+    2/4/8-way decomposition; the affine topology is proven exactly when every extent is >= 3, and its irregular-cell list
+    is the outermost layer."""
+    rng = np.random.default_rng(0)
+    for _ in range(12):
+        dims = tuple(int(x) for x in rng.integers(1, 28, 3))
+        g = MeshDesc.block(*dims)
+        info, bad = selftest(g)
+        assert bad == 0, dims
+        a = affine_info(g)
+        assert a[0] == (1 if min(dims) >= 3 else 0), (dims, a)
+        if a[0]:
+            assert a[4] == g.nCells - (dims[0] - 2) * (dims[1] - 2) * (dims[2] - 2)
+        P = int(rng.choice([2, 4, 8]))
+        if g.nCells >= 2 * P:
+            for r in range(P):
+                d = Decomposition(g, P, r)
+                if d.nOwned:
+                    assert selftest(d.desc)[1] == 0, (dims, P, r)
