@@ -581,3 +581,47 @@ extern "C" int fvk_brick_plan_affine_info(const fvk_mesh_desc* d, int32_t* info 
     info[4] = int32_t(bp.irrCells.size());
     return FVK_OK;
 }
+
+// diagnostics (host only): the assumption behind the structured SpMV (fvk_spmv_structured / fvk_solver_attach_mesh). With
+// the SparsityPattern built as in fvk_mesh_create (row = [lower faces ascending | diag | upper faces ascending]) and a
+// proven affine topology, every REGULAR row must be exactly [c-nx*ny, c-nx, c-1, c, c+1, c+nx, c+nx*ny]. result[0] = 1 when
+// the topology is affine and all regular rows check, 0 when not affine, -1 when a row violates it; result[1] = rows checked.
+extern "C" int fvk_brick_plan_structured_rows(const fvk_mesh_desc* d, int64_t* result /* [2] */)
+{
+    if (!d || !result) return fvk_fail(FVK_EINVAL, "fvk_brick_plan_structured_rows: null");
+    FvkStencilHost st;
+    fvk_build_stencil(d, st);
+    FvkBrickPlanHost bp;
+    const char* why = "";
+    result[0] = 0; result[1] = 0;
+    if (!fvk_build_brick_plan(d, st, bp, &why) || !bp.geom.affine) return FVK_OK;
+    const int32_t nC = d->nCells, nI = d->nInternalFaces;
+    const int32_t* own = d->faceOwner;
+    const int32_t* nei = d->faceNeighbour;
+    std::vector<int64_t> rowOffs(size_t(nC) + 1, 0);
+    for (int32_t c = 0; c < nC; ++c) rowOffs[size_t(c) + 1] = 1;
+    for (int32_t f = 0; f < nI; ++f) { ++rowOffs[size_t(own[f]) + 1]; ++rowOffs[size_t(nei[f]) + 1]; }
+    for (int32_t c = 0; c < nC; ++c) rowOffs[size_t(c) + 1] += rowOffs[c];
+    std::vector<int32_t> col, cnt;
+    col.resize(size_t(rowOffs[nC]));
+    cnt.assign(size_t(nC), 0);
+    for (int32_t f = 0; f < nI; ++f) col[size_t(rowOffs[nei[f]]) + cnt[nei[f]]++] = own[f];
+    for (int32_t c = 0; c < nC; ++c) col[size_t(rowOffs[c]) + cnt[c]++] = c;
+    for (int32_t f = 0; f < nI; ++f) col[size_t(rowOffs[own[f]]) + cnt[own[f]]++] = nei[f];
+    const int64_t nx = bp.geom.dims[0], ny = bp.geom.dims[1], nz = bp.geom.dims[2], nxy = nx * ny;
+    int64_t checked = 0;
+    bool ok = true;
+    for (int64_t c = 0; c < bp.geom.nOwned && ok; ++c)
+    {
+        const int64_t i = c % nx, j = (c / nx) % ny, k = c / nxy;
+        if (!(i > 0 && i < nx - 1 && j > 0 && j < ny - 1 && k > 0 && k < nz - 1)) continue;
+        const int64_t want[7] = {c - nxy, c - nx, c - 1, c, c + 1, c + nx, c + nxy};
+        if (rowOffs[c + 1] - rowOffs[c] != 7) { ok = false; break; }
+        for (int t = 0; t < 7; ++t)
+            if (col[size_t(rowOffs[c]) + t] != want[t]) ok = false;
+        ++checked;
+    }
+    result[0] = ok ? 1 : -1;
+    result[1] = checked;
+    return FVK_OK;
+}

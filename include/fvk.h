@@ -541,6 +541,10 @@ int fvk_brick_plan_selftest(const fvk_mesh_desc* desc_h, int32_t* info_h, int64_
 /* HOST only: {affine topology proven (0/1), upper side x / y / z is a true boundary (1) or a processor cut (0), number of
  * irregular (boundary / cut layer) cells} of the plan (info_h[5]). */
 int fvk_brick_plan_affine_info(const fvk_mesh_desc* desc_h, int32_t* info_h);
+/* HOST only: the assumption behind the structured SpMV, checked row by row: result_h[0] = 1 when the topology is affine
+ * and every regular row of the SparsityPattern is [c-nx*ny, c-nx, c-1, c, c+1, c+nx, c+nx*ny], 0 when the topology is not
+ * affine (generic SpMV is used), -1 on a violation; result_h[1] = rows checked. */
+int fvk_brick_plan_structured_rows(const fvk_mesh_desc* desc_h, int64_t* result_h);
 
 #ifdef __cplusplus
 }

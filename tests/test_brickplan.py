@@ -119,3 +119,20 @@ def test_random_blocks_and_their_sub_domains():
                 d = Decomposition(g, P, r)
                 if d.nOwned:
                     assert selftest(d.desc)[1] == 0, (dims, P, r)
+
+
+def test_structured_spmv_assumption_holds_row_by_row():
+    """The structured SpMV computes the columns of a regular row instead of reading them; this replays the
+    SparsityPattern on the host and checks every regular row of block meshes and of decomposition sub-domains."""
+    def rows(desc):
+        r = (C.c_int64 * 2)()
+        check(lib().fvk_brick_plan_structured_rows(C.byref(desc.c), r))
+        return list(r)
+    g = MeshDesc.block(13, 9, 7)
+    assert rows(g) == [1, 11 * 7 * 5]
+    assert rows(MeshDesc.block(20, 20, 1, patches=PATCHES_CAVITY2D))[0] == 0      # not affine: generic SpMV
+    assert rows(renumbered_block(12, 11, 10, 3))[0] == 0
+    for P in (2, 4, 8):
+        for r in range(P):
+            ok, n = rows(Decomposition(MeshDesc.block(16, 12, 10), P, r).desc)
+            assert ok == 1 and n > 0
