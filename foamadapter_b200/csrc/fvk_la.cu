@@ -28,7 +28,9 @@ struct PcgState
     double rho, rhoPrev, alpha, beta, pq, rr, normB, normR;
     double sums[4]; // local (pre-allreduce) partial results: [0] r.z  [1] r.r  [2] p.q  [3] b.b
     double relTol, absTol;
-    int iter, done, nHist, maxHist, maxIter, pad;
+    int iter, done, nHist, maxHist, maxIter, half; // half (BiCGStab): stopped at the half step, finalize pending
+    double gamma, omega, tmp; // BiCGStab scalars; tmp = (rho/rhoPrev)(alpha/omega) of step 1
+    int useP, pad2;           // BiCGStab step 1: 1 = p = r + tmp (p - omega v), 0 = p = r
 };
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -237,12 +239,174 @@ k_cg_pupdate(int n, const PcgState* __restrict__ st, const double* __restrict__ 
     for (int i = blockIdx.x * TB + threadIdx.x; i < n; i += gridDim.x * TB) p[i] = z[i] + beta * p[i];
 }
 
+
+// ---- BiCGStab (Ginkgo 1.10 solver::Bicgstab, restated in oracle/fvo.cpp fvo_bicgstab) -------------------------------
+// Five kernels per iteration: {p, y} | {v = A y, rr.v} | {s, z, s.s} | {t = A z, s.t, t.t} | {x, r, rr.r, r.r}; the scalar
+// updates and both stopping checks run in the last block of the kernel that finishes the reduction they depend on.
+__device__ __forceinline__ void bicg_decide_alpha(PcgState* st)
+{
+    st->beta = st->sums[2];
+    st->alpha = st->sums[2] != 0.0 ? st->rho / st->sums[2] : 0.0;
+}
+__device__ __forceinline__ void bicg_decide_half(PcgState* st, double* __restrict__ hist)
+{
+    const double normS = sqrt(st->sums[1]);
+    st->normR = normS;
+    if (hist && st->nHist < st->maxHist) hist[st->nHist++] = normS;
+    if (st->iter >= st->maxIter || normS <= st->relTol * st->normB || normS <= st->absTol) st->half = 1;
+}
+__device__ __forceinline__ void bicg_decide_omega(PcgState* st)
+{
+    st->gamma = st->sums[2];
+    st->omega = st->sums[3] != 0.0 ? st->sums[2] / st->sums[3] : 0.0;
+}
+// after step 3 (or the start-up): sums[0] = rr.r, sums[1] = r.r
+template <bool FIRST>
+__device__ __forceinline__ void bicg_decide_full(PcgState* st, double* __restrict__ hist)
+{
+    if (st->half)
+    { // the half-step check stopped the solve; x was finalised by this kernel
+        st->done = 1;
+        return;
+    }
+    if (!FIRST)
+    {
+        st->rhoPrev = st->rho; // swap(prev_rho, rho) followed by the next iteration's rho = rr.r
+        st->iter += 1;
+    }
+    st->rho = st->sums[0];
+    const double normR = sqrt(st->sums[1]);
+    st->normR = normR;
+    if (hist && st->nHist < st->maxHist) hist[st->nHist++] = normR;
+    if (st->iter >= st->maxIter || normR <= st->relTol * st->normB || normR <= st->absTol)
+    {
+        st->done = 1;
+        return;
+    }
+    if (st->rhoPrev * st->omega != 0.0)
+    {
+        st->tmp = (st->rho / st->rhoPrev) * (st->alpha / st->omega);
+        st->useP = 1;
+    }
+    else
+        st->useP = 0;
+}
+template <int STAGE>
+__global__ void k_bicg_decide(PcgState* st, double* hist)
+{
+    if (st->done) return;
+    if (STAGE == 0) bicg_decide_full<true>(st, hist);
+    if (STAGE == 1) bicg_decide_alpha(st);
+    if (STAGE == 2) bicg_decide_half(st, hist);
+    if (STAGE == 3 && !st->half) bicg_decide_omega(st);
+    if (STAGE == 4) bicg_decide_full<false>(st, hist);
+}
+
+// step 1 + preconditioner: p = r + tmp (p - omega v); y = M^-1 p
+template <bool JACOBI>
+__global__ void __launch_bounds__(TB)
+k_bicg_step1(int n, const PcgState* __restrict__ st, const double* __restrict__ r, double* __restrict__ p,
+             const double* __restrict__ v, const double* __restrict__ dinv, double* __restrict__ y)
+{
+    if (st->done) return;
+    const double tmp = st->tmp, omega = st->omega;
+    const bool useP = st->useP != 0;
+    for (int i = blockIdx.x * TB + threadIdx.x; i < n; i += gridDim.x * TB)
+    {
+        const double pi = useP ? r[i] + tmp * (p[i] - omega * v[i]) : r[i];
+        p[i] = pi;
+        y[i] = JACOBI ? pi * dinv[i] : pi;
+    }
+}
+// step 2 + preconditioner + ||s||^2: s = r - alpha v; z = M^-1 s
+template <bool JACOBI>
+__global__ void __launch_bounds__(TB)
+k_bicg_step2(int n, PcgState* __restrict__ st, const double* __restrict__ r, const double* __restrict__ v,
+             const double* __restrict__ dinv, double* __restrict__ sv, double* __restrict__ z, double* __restrict__ partial,
+             unsigned* __restrict__ counter, double* __restrict__ hist, int distributed)
+{
+    if (st->done) return;
+    const double alpha = st->alpha;
+    const bool plain = st->beta == 0.0; // step_2 of the reference kernel: beta == 0 -> alpha = 0, s = r
+    double acc[1] = {0.0};
+    for (int i = blockIdx.x * TB + threadIdx.x; i < n; i += gridDim.x * TB)
+    {
+        const double si = plain ? r[i] : r[i] - alpha * v[i];
+        sv[i] = si;
+        z[i] = JACOBI ? si * dinv[i] : si;
+        acc[0] += si * si;
+    }
+    double tot[1];
+    if (grid_sum<1>(acc, partial, counter, tot) && threadIdx.x == 0)
+    {
+        st->sums[1] = tot[0];
+        if (!distributed) bicg_decide_half(st, hist);
+    }
+}
+// step 3 (+ finalize after a half-step stop) + rho = rr.r + ||r||^2; FIRST: start-up (rr = r, the first check)
+template <bool FIRST>
+__global__ void __launch_bounds__(TB)
+k_bicg_step3(int n, PcgState* __restrict__ st, double* __restrict__ x, const double* __restrict__ y,
+             const double* __restrict__ z, const double* __restrict__ sv, const double* __restrict__ t,
+             double* __restrict__ r, double* __restrict__ rr, double* __restrict__ partial, unsigned* __restrict__ counter,
+             double* __restrict__ hist, int distributed)
+{
+    if (st->done) return;
+    double acc[2] = {0.0, 0.0};
+    if (FIRST)
+    {
+        for (int i = blockIdx.x * TB + threadIdx.x; i < n; i += gridDim.x * TB)
+        {
+            const double ri = r[i];
+            rr[i] = ri;
+            acc[0] += ri * ri;
+        }
+        acc[1] = acc[0];
+    }
+    else if (st->half)
+    {
+        const double alpha = st->alpha;
+        for (int i = blockIdx.x * TB + threadIdx.x; i < n; i += gridDim.x * TB) x[i] = x[i] + alpha * y[i];
+    }
+    else
+    {
+        const double alpha = st->alpha, omega = st->omega;
+        for (int i = blockIdx.x * TB + threadIdx.x; i < n; i += gridDim.x * TB)
+        {
+            x[i] = x[i] + (alpha * y[i] + omega * z[i]);
+            const double ri = sv[i] - omega * t[i];
+            r[i] = ri;
+            acc[0] += rr[i] * ri;
+            acc[1] += ri * ri;
+        }
+    }
+    double tot[2];
+    if (grid_sum<2>(acc, partial, counter, tot) && threadIdx.x == 0)
+    {
+        st->sums[0] = tot[0];
+        st->sums[1] = tot[1];
+        if (!distributed) bicg_decide_full<FIRST>(st, hist);
+    }
+}
+
+// Vec3 systems (identical components, A.3): component matrix / right-hand side / solution (un)packing
+__global__ void __launch_bounds__(TB) k_take_component(int64_t n, int comp, const double* __restrict__ v3, double* __restrict__ out)
+{
+    for (int64_t i = int64_t(blockIdx.x) * TB + threadIdx.x; i < n; i += int64_t(gridDim.x) * TB) out[i] = v3[3 * i + comp];
+}
+__global__ void __launch_bounds__(TB) k_put_component(int64_t n, int comp, const double* __restrict__ in, double* __restrict__ v3)
+{
+    for (int64_t i = int64_t(blockIdx.x) * TB + threadIdx.x; i < n; i += int64_t(gridDim.x) * TB) v3[3 * i + comp] = in[i];
+}
+
 // ---- tiled CSR SpMV ----------------------------------------------------------------------------
 // MODE 0: y = A x            (fvk_spmv)
 // MODE 1: y = A x - b        (computeResidual)
 // MODE 2: y = b - A x        (CG start-up r0)
 // MODE 3: CG: q = A p, dot p.q, scalar update; p read from `x`
 // MODE 4: CG fused: pNew = z + beta pOld evaluated on the fly for the gathered columns, q = A pNew
+// MODE 5: BiCGStab: v = A y, dot rr.v (rr passed as `b`), alpha update
+// MODE 6: BiCGStab: t = A z, dots s.t and t.t (s passed as `b`), omega update
 // Block-structured sparsity (the mesh plan proved the topology, FvkBrickGeom::affine): the row of a REGULAR cell c is
 // [c-nx*ny, c-nx, c-1 | c | c+1, c+nx, c+nx*ny]; its column indices are not read (28 of the 104 bytes a row moves).
 struct SpmvAffine
@@ -264,9 +428,11 @@ k_spmv(int nRows, const int* __restrict__ rowOffs, const int* __restrict__ colId
     if (MODE >= 3)
     {
         if (st->done) return;
+        if (MODE == 6 && st->half) return;
         beta = st->beta;
     }
-    double acc[1] = {0.0};
+    constexpr int NV = MODE == 6 ? 2 : 1;
+    double acc[NV] = {0.0};
     // peer-memory CG: z (owned + ghost entries, the latter stored by the neighbours' update kernels, flags already
     // awaited) lies in the window half of the last exchange's parity; p of the ghost columns follows p = z + beta p
     const double* zz = z; // read with __ldg below: the non-coherent path the __restrict__ parameter would get
@@ -352,12 +518,38 @@ k_spmv(int nRows, const int* __restrict__ rowOffs, const int* __restrict__ colId
                 y[r] = sum;
                 acc[0] += pr * sum;
             }
+            if (MODE == 5)
+            {
+                y[r] = sum;
+                acc[0] += b[r] * sum;
+            }
+            if (MODE == 6)
+            {
+                y[r] = sum;
+                acc[0] += b[r] * sum;
+                acc[NV - 1] += sum * sum;
+            }
         }
     }
-    if (MODE >= 3)
+    if (MODE == 5 || MODE == 6)
     {
-        double tot[1];
-        if (grid_sum<1>(acc, partial, counter, tot))
+        double tot[NV];
+        if (grid_sum<NV>(acc, partial, counter, tot) && threadIdx.x == 0)
+        {
+            st->sums[2] = tot[0];
+            if (MODE == 6) st->sums[3] = tot[NV - 1];
+            if (!distributed)
+            {
+                if (MODE == 5) bicg_decide_alpha(st);
+                else bicg_decide_omega(st);
+            }
+        }
+        return;
+    }
+    if (MODE == 3 || MODE == 4)
+    {
+        double tot[NV];
+        if (grid_sum<NV>(acc, partial, counter, tot))
         {
             if (distributed == 2)
             { // peer-memory all-reduce of p.q inside the SpMV's last block
@@ -396,7 +588,7 @@ k_extract_dinv(int n, const int* __restrict__ rowOffs, const int* __restrict__ c
 }
 
 // ---- BLAS-1 --------------------------------------------------------------------------------------
-enum { OP_FILL, OP_SCALE, OP_ADD, OP_SUB, OP_MUL, OP_AXPBY };
+enum { OP_FILL, OP_SCALE, OP_ADD, OP_SUB, OP_MUL, OP_AXPBY, OP_SCALED_COPY };
 template <int OP>
 __global__ void __launch_bounds__(TB)
 k_vec(int64_t n, double a, double bb, double* __restrict__ x, const double* __restrict__ y)
@@ -409,6 +601,7 @@ k_vec(int64_t n, double a, double bb, double* __restrict__ x, const double* __re
         if (OP == OP_SUB) x[i] = x[i] - y[i];
         if (OP == OP_MUL) x[i] = x[i] * y[i];
         if (OP == OP_AXPBY) x[i] = a * y[i] + bb * x[i]; // here x is the output `y` of fvk_vec_axpby
+        if (OP == OP_SCALED_COPY) x[i] = y[i] * a;
     }
 }
 
@@ -582,6 +775,12 @@ extern "C" int fvk_vec_axpby(int64_t n, double a, const double* x, double b, dou
     VEC_OP(OP_AXPBY, a, b, y, x);
 }
 
+extern "C" int fvk_vec_scaled_copy(int64_t n, double a, const double* x, double* out, fvk_stream s)
+{
+    if (n && !x) return fvk_fail(FVK_EINVAL, "fvk_vec_scaled_copy: null");
+    VEC_OP(OP_SCALED_COPY, a, 0.0, out, x);
+}
+
 extern "C" int fvk_dot(int64_t n, const double* x, const double* y, double* result_d, fvk_stream s)
 {
     if (n < 0 || !result_d || (n && (!x || !y))) return fvk_fail(FVK_EINVAL, "fvk_dot: bad argument");
@@ -608,7 +807,11 @@ struct fvk_solver
     fvk_solver_config cfg {};
     fvk_comm* comm = nullptr;
     SpmvAffine aff {0, 0, 0, 0}; // set by fvk_solver_attach_mesh
+    const int32_t *affRowOffs = nullptr, *affColIdxs = nullptr; // the attached mesh's pattern: aff applies to these arrays only
     double *r2 = nullptr; // second residual buffer of the peer-memory mode
+    double *rr = nullptr, *sB = nullptr, *tB = nullptr; // BiCGStab: shadow residual, s, t
+    double *vals0 = nullptr, *bC = nullptr, *xC = nullptr; // Vec3 solves: component matrix / rhs / solution (lazy)
+    int64_t vals0Cap = 0;
     double *r = nullptr, *z = nullptr, *p0 = nullptr, *p1 = nullptr, *q = nullptr, *dinv = nullptr;
     double *partial = nullptr, *hist = nullptr;
     unsigned* counter = nullptr;
@@ -621,6 +824,8 @@ struct fvk_solver
 extern "C" int fvk_solver_destroy(fvk_solver* sv)
 {
     if (!sv) return FVK_OK;
+    for (void* ptr : {(void*) sv->rr, (void*) sv->sB, (void*) sv->tB, (void*) sv->vals0, (void*) sv->bC, (void*) sv->xC})
+        if (ptr) cudaFree(ptr);
     for (void* ptr : {(void*) sv->r, (void*) sv->r2, (void*) sv->z, (void*) sv->p0, (void*) sv->p1, (void*) sv->q, (void*) sv->dinv,
                       (void*) sv->partial, (void*) sv->hist, (void*) sv->counter, (void*) sv->state})
         if (ptr) cudaFree(ptr);
@@ -634,15 +839,17 @@ extern "C" int fvk_solver_destroy(fvk_solver* sv)
 extern "C" int fvk_solver_create(int32_t nRows, int32_t nCols, const fvk_solver_config* cfg, fvk_comm* comm, fvk_solver** out)
 {
     if (!cfg || !out || nRows <= 0 || nCols < nRows) return fvk_fail(FVK_EINVAL, "fvk_solver_create: bad argument");
-    if (cfg->maxIter < 0 || cfg->checkEvery < 1 || (cfg->preconditioner != FVK_PRECOND_NONE && cfg->preconditioner != FVK_PRECOND_JACOBI))
+    if (cfg->maxIter < 0 || cfg->checkEvery < 1 || (cfg->preconditioner != FVK_PRECOND_NONE && cfg->preconditioner != FVK_PRECOND_JACOBI)
+        || (cfg->solverType != FVK_SOLVER_CG && cfg->solverType != FVK_SOLVER_BICGSTAB))
         return fvk_fail(FVK_EINVAL, "fvk_solver_create: bad configuration");
     *out = nullptr;
     fvk_solver* sv = new fvk_solver;
     sv->nRows = nRows; sv->nCols = nCols; sv->cfg = *cfg; sv->comm = comm;
-    sv->histCap = cfg->maxIter + 2;
+    sv->histCap = (cfg->solverType == FVK_SOLVER_BICGSTAB ? 2 : 1) * cfg->maxIter + 2;
     cudaError_t e = cudaSuccess;
     auto A = [&](double** ptr, size_t n) { if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(ptr), sizeof(double) * n); };
     A(&sv->r, nRows); if (comm) A(&sv->r2, nRows); A(&sv->z, nCols); A(&sv->p0, nCols); A(&sv->p1, nCols); A(&sv->q, nRows); A(&sv->dinv, nRows);
+    if (cfg->solverType == FVK_SOLVER_BICGSTAB) { A(&sv->rr, nRows); A(&sv->sB, nRows); A(&sv->tB, nRows); }
     A(&sv->partial, 4 * MAX_GRID); A(&sv->hist, sv->histCap);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&sv->counter), sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMemset(sv->counter, 0, sizeof(unsigned));
@@ -663,6 +870,140 @@ extern "C" int fvk_solver_attach_mesh(fvk_solver* sv, const fvk_mesh* m)
 {
     if (!sv) return fvk_fail(FVK_EINVAL, "fvk_solver_attach_mesh: null solver");
     sv->aff = (m && m->nOwned == sv->nRows && m->nCells == sv->nCols) ? mesh_affine(m) : SpmvAffine {0, 0, 0, 0};
+    sv->affRowOffs = m ? m->rowOffs : nullptr;
+    sv->affColIdxs = m ? m->colIdxs : nullptr;
+    return FVK_OK;
+}
+
+
+// Pipelined stop polling shared by the solvers: check after 1, 2, 4, ... rounds up to `every`, then every `every`; the
+// state copy of check k is awaited only after the rounds up to check k+1 have been queued.
+struct StopPoll
+{
+    fvk_solver* sv;
+    cudaStream_t st;
+    int every, nextCheck = 1, pending = -1, finalBuf = 0;
+    // returns 1 when the solve has stopped, 0 to continue, <0 on error (-(code))
+    int after_round(int it, int lastRound)
+    {
+        if (it + 1 != nextCheck && it != lastRound) return 0;
+        if (pending >= 0)
+        {
+            if (cudaEventSynchronize(sv->checkEv[pending]) != cudaSuccess) return -FVK_ECUDA;
+            if (sv->state_h[pending].done) { finalBuf = pending; return 1; }
+        }
+        pending = pending < 0 ? 0 : 1 - pending;
+        if (cudaMemcpyAsync(&sv->state_h[pending], sv->state, sizeof(PcgState), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -FVK_ECUDA;
+        if (cudaEventRecord(sv->checkEv[pending], st) != cudaSuccess) return -FVK_ECUDA;
+        if (it == lastRound)
+        {
+            if (cudaEventSynchronize(sv->checkEv[pending]) != cudaSuccess) return -FVK_ECUDA;
+            finalBuf = pending;
+            return 1;
+        }
+        nextCheck = nextCheck < every ? (2 * nextCheck < every ? 2 * nextCheck : every) : nextCheck + every;
+        return 0;
+    }
+};
+
+static int bicgstab_solve(fvk_solver* sv, const int32_t* rowOffs, const int32_t* colIdxs, const double* values, const double* b,
+                          double* x, fvk_solver_stats* stats_h, double* history_h, int32_t maxHistory, fvk_stream s)
+{
+    cudaStream_t st = fvk_cu(s);
+    const int n = sv->nRows;
+    const bool dist = sv->comm != nullptr;
+    const int dm = dist ? 1 : 0;
+    const bool jacobi = sv->cfg.preconditioner == FVK_PRECOND_JACOBI;
+    const int gV = stream_grid(n), gS = spmv_grid(n);
+    const int wantHist = (history_h && maxHistory > 0) ? (maxHistory < sv->histCap ? maxHistory : sv->histCap) : 0;
+    double *r = sv->r, *rr = sv->rr, *p = sv->p1, *v = sv->q, *sB = sv->sB, *tB = sv->tB, *y = sv->p0, *z = sv->z;
+
+    PcgState init;
+    std::memset(&init, 0, sizeof(init));
+    init.rho = init.rhoPrev = init.alpha = init.beta = init.gamma = init.omega = 1.0;
+    init.relTol = sv->cfg.relTol; init.absTol = sv->cfg.absTol;
+    init.maxIter = sv->cfg.maxIter; init.maxHist = wantHist;
+    *sv->state_h = init;
+    FVK_CUDA(cudaMemcpyAsync(sv->state, sv->state_h, sizeof(PcgState), cudaMemcpyHostToDevice, st));
+    FVK_CUDA(cudaMemsetAsync(p, 0, sizeof(double) * sv->nCols, st));
+    FVK_CUDA(cudaMemsetAsync(v, 0, sizeof(double) * n, st));
+    if (jacobi)
+    {
+        k_extract_dinv<<<(n + TB - 1) / TB, TB, 0, st>>>(n, rowOffs, colIdxs, values, sv->dinv);
+        FVK_LAUNCH_CHECK();
+    }
+    k_dot<false><<<gV, TB, 0, st>>>(n, b, b, &sv->state->sums[3], sv->partial, sv->counter);
+    FVK_LAUNCH_CHECK();
+    if (dist)
+    {
+        if (int rc = fvk_comm_allreduce_sum_impl(sv->comm, &sv->state->sums[3], 1, st)) return rc;
+        if (int rc = fvk_comm_halo_exchange_impl(sv->comm, x, 1, st)) return rc;
+    }
+    k_set_normB<<<1, 1, 0, st>>>(sv->state);
+    k_spmv<2><<<gS, TB, 0, st>>>(n, rowOffs, colIdxs, values, x, b, r, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0, sv->aff);
+    FVK_LAUNCH_CHECK();
+    auto reduce = [&](int first, int count) -> int { return dist ? fvk_comm_allreduce_sum_impl(sv->comm, &sv->state->sums[first], count, st) : FVK_OK; };
+    k_bicg_step3<true><<<gV, TB, 0, st>>>(n, sv->state, x, y, z, sB, tB, r, rr, sv->partial, sv->counter, sv->hist, dm);
+    FVK_LAUNCH_CHECK();
+    if (dist)
+    {
+        if (int rc = reduce(0, 2)) return rc;
+        k_bicg_decide<0><<<1, 1, 0, st>>>(sv->state, sv->hist);
+    }
+    StopPoll poll {sv, st, sv->cfg.checkEvery};
+    // round k runs the body of iteration k and the first stopping check of iteration k + 1
+    const int lastRound = sv->cfg.maxIter > 0 ? sv->cfg.maxIter - 1 : 0;
+    for (int it = 0; it <= lastRound; ++it)
+    {
+        if (jacobi) k_bicg_step1<true><<<gV, TB, 0, st>>>(n, sv->state, r, p, v, sv->dinv, y);
+        else k_bicg_step1<false><<<gV, TB, 0, st>>>(n, sv->state, r, p, v, sv->dinv, y);
+        FVK_LAUNCH_CHECK();
+        if (dist) if (int rc = fvk_comm_halo_exchange_impl(sv->comm, y, 1, st)) return rc;
+        k_spmv<5><<<gS, TB, 0, st>>>(n, rowOffs, colIdxs, values, y, rr, v, sv->state, nullptr, nullptr, sv->partial, sv->counter, dm, nullptr, 0, sv->aff);
+        FVK_LAUNCH_CHECK();
+        if (dist)
+        {
+            if (int rc = reduce(2, 1)) return rc;
+            k_bicg_decide<1><<<1, 1, 0, st>>>(sv->state, sv->hist);
+        }
+        if (jacobi) k_bicg_step2<true><<<gV, TB, 0, st>>>(n, sv->state, r, v, sv->dinv, sB, z, sv->partial, sv->counter, sv->hist, dm);
+        else k_bicg_step2<false><<<gV, TB, 0, st>>>(n, sv->state, r, v, sv->dinv, sB, z, sv->partial, sv->counter, sv->hist, dm);
+        FVK_LAUNCH_CHECK();
+        if (dist)
+        {
+            if (int rc = reduce(1, 1)) return rc;
+            k_bicg_decide<2><<<1, 1, 0, st>>>(sv->state, sv->hist);
+            if (int rc = fvk_comm_halo_exchange_impl(sv->comm, z, 1, st)) return rc;
+        }
+        k_spmv<6><<<gS, TB, 0, st>>>(n, rowOffs, colIdxs, values, z, sB, tB, sv->state, nullptr, nullptr, sv->partial, sv->counter, dm, nullptr, 0, sv->aff);
+        FVK_LAUNCH_CHECK();
+        if (dist)
+        {
+            if (int rc = reduce(2, 2)) return rc;
+            k_bicg_decide<3><<<1, 1, 0, st>>>(sv->state, sv->hist);
+        }
+        k_bicg_step3<false><<<gV, TB, 0, st>>>(n, sv->state, x, y, z, sB, tB, r, rr, sv->partial, sv->counter, sv->hist, dm);
+        FVK_LAUNCH_CHECK();
+        if (dist)
+        {
+            if (int rc = reduce(0, 2)) return rc;
+            k_bicg_decide<4><<<1, 1, 0, st>>>(sv->state, sv->hist);
+        }
+        const int pr = poll.after_round(it, lastRound);
+        if (pr < 0) return fvk_fail(FVK_ECUDA, "fvk_solver_solve: stop polling failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (pr == 1) break;
+    }
+    const PcgState& fin = sv->state_h[poll.finalBuf];
+    if (!fin.done) return fvk_fail(FVK_ECUDA, "fvk_solver_solve: stop flag not raised after maxIter rounds");
+    stats_h->numIter = fin.iter;
+    stats_h->initResNorm = fin.normB;
+    stats_h->finalResNorm = fin.normR;
+    stats_h->nHistory = fin.nHist;
+    if (wantHist && fin.nHist > 0)
+    {
+        FVK_CUDA(cudaMemcpyAsync(history_h, sv->hist, sizeof(double) * fin.nHist, cudaMemcpyDeviceToHost, st));
+        FVK_CUDA(cudaStreamSynchronize(st));
+    }
     return FVK_OK;
 }
 
@@ -671,6 +1012,10 @@ extern "C" int fvk_solver_solve(fvk_solver* sv, const int32_t* rowOffs, const in
                                 int32_t maxHistory, fvk_stream s)
 {
     if (!sv || !rowOffs || !colIdxs || !values || !b || !x || !stats_h) return fvk_fail(FVK_EINVAL, "fvk_solver_solve: null argument");
+    // the structured SpMV computes columns from the attached mesh's dimensions: only valid for that mesh's own pattern
+    struct AffGuard { fvk_solver* s; SpmvAffine saved; ~AffGuard() { s->aff = saved; } } guard {sv, sv->aff};
+    if (rowOffs != sv->affRowOffs || colIdxs != sv->affColIdxs) sv->aff = SpmvAffine {0, 0, 0, 0};
+    if (sv->cfg.solverType == FVK_SOLVER_BICGSTAB) return bicgstab_solve(sv, rowOffs, colIdxs, values, b, x, stats_h, history_h, maxHistory, s);
     cudaStream_t st = fvk_cu(s);
     const int n = sv->nRows;
     const bool dist = sv->comm != nullptr;
@@ -820,6 +1165,37 @@ extern "C" int fvk_solver_solve(fvk_solver* sv, const int32_t* rowOffs, const in
     {
         FVK_CUDA(cudaMemcpyAsync(history_h, sv->hist, sizeof(double) * fin.nHist, cudaMemcpyDeviceToHost, st));
         FVK_CUDA(cudaStreamSynchronize(st));
+    }
+    return FVK_OK;
+}
+
+// Vec3 LinearSystem (values Vec3[nnz] with identical components, rhs / x Vec3): three scalar solves over the component
+// matrix, like OpenFOAM's segregated vector solve. NeoN's la::Solver has no Vec3 overload (solver.hpp:52 is commented out);
+// this is the solve `momentumPredictor yes` (neoIcoFoam.cpp:100-103) needs.
+extern "C" int fvk_solver_solve_vec3(fvk_solver* sv, int64_t nnz, const int32_t* rowOffs, const int32_t* colIdxs, const double* valuesV,
+                                     const double* bV, double* xV, fvk_solver_stats* stats3_h, fvk_stream s)
+{
+    if (!sv || nnz <= 0 || !rowOffs || !colIdxs || !valuesV || !bV || !xV || !stats3_h) return fvk_fail(FVK_EINVAL, "fvk_solver_solve_vec3: bad argument");
+    cudaStream_t st = fvk_cu(s);
+    if (sv->vals0Cap < nnz)
+    {
+        if (sv->vals0) cudaFree(sv->vals0);
+        sv->vals0 = nullptr; sv->vals0Cap = 0;
+        FVK_CUDA(cudaMalloc(reinterpret_cast<void**>(&sv->vals0), sizeof(double) * nnz));
+        sv->vals0Cap = nnz;
+    }
+    if (!sv->bC) FVK_CUDA(cudaMalloc(reinterpret_cast<void**>(&sv->bC), sizeof(double) * sv->nRows));
+    if (!sv->xC) FVK_CUDA(cudaMalloc(reinterpret_cast<void**>(&sv->xC), sizeof(double) * sv->nCols));
+    k_take_component<<<stream_grid(nnz), TB, 0, st>>>(nnz, 0, valuesV, sv->vals0);
+    FVK_LAUNCH_CHECK();
+    for (int c = 0; c < 3; ++c)
+    {
+        k_take_component<<<stream_grid(sv->nRows), TB, 0, st>>>(sv->nRows, c, bV, sv->bC);
+        k_take_component<<<stream_grid(sv->nCols), TB, 0, st>>>(sv->nCols, c, xV, sv->xC);
+        FVK_LAUNCH_CHECK();
+        if (int rc = fvk_solver_solve(sv, rowOffs, colIdxs, sv->vals0, sv->bC, sv->xC, &stats3_h[c], nullptr, 0, s)) return rc;
+        k_put_component<<<stream_grid(sv->nRows), TB, 0, st>>>(sv->nRows, c, sv->xC, xV);
+        FVK_LAUNCH_CHECK();
     }
     return FVK_OK;
 }

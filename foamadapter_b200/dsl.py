@@ -123,6 +123,23 @@ class Expression:
                 raise NotImplementedError("explicit ddt needs dt; use ops.ddt_explicit")
         return src
 
+    def explicitOperationInto(self, mesh, src):
+        """Expression::explicitOperation(source) (dsl/expression.hpp:55-65): the explicit SPATIAL operators added to an
+        existing source vector (each operator: tmp = 0; op(tmp); source += tmp -- fused into one ADD-mode launch)."""
+        for o in self.spatial:
+            if o.type != "explicit":
+                continue
+            c = o.coeff
+            if o.kind == "surfaceIntegrate":
+                ops.surface_integrate(mesh, o.faceField.internal, src, c.value, c.view, ops.ADD)
+            elif o.kind == "div":
+                ops.div(mesh, o.faceField.internal, o.field.internal, o.field.boundary.value, src, o.scheme or 0, c.value, c.view, ops.ADD)
+            elif o.kind == "laplacian":
+                ops.laplacian(mesh, o.field.internal, o.field.boundary.value, src, c.value, c.view, ops.ADD)
+            elif o.kind == "source":
+                ops.source_explicit(mesh, o.cellField, o.field.internal, src, c.value, c.view)
+        return src
+
 
 class imp:
     """dsl::imp (dsl/implicit.hpp)."""
@@ -210,3 +227,117 @@ class PDESolver:
                 raise KeyError(f"fvSolution.solvers has no entry for '{self.psi.name}'")
             solver = la.Solver(cfg, comm=self.rt.comm, check_every=self.rt.check_every, history=self.rt.history)
         return solver.solve(self.ls, self.psi.internal)
+
+
+# ---- time integration (src/NeoN/include/NeoN/timeIntegration/*.hpp) and dsl::solve (dsl/solver.hpp:35-82) -------------
+class TimeIntegratorBase:
+    """timeIntegration::TimeIntegratorBase<SolutionVectorType> (timeIntegration.hpp:19-52): strategies registered by name
+    (RuntimeSelectionFactory, core/runtimeSelectionFactory.hpp:193-413), selected by ddtSchemes.type. A subclass registers
+    itself by defining `name` -- the Python spelling of `Register<Derived>`."""
+    table: dict = {}
+    name = None
+
+    def __init_subclass__(cls, **kw):
+        super().__init_subclass__(**kw)
+        if cls.name:
+            TimeIntegratorBase.table[cls.name] = cls
+
+    def __init__(self, schemeDict: dict, solutionDict: dict, comm=None, check_every=8):
+        self.schemeDict, self.solutionDict, self.comm, self.check_every = schemeDict, solutionDict, comm, check_every
+
+    @classmethod
+    def create(cls, key, schemeDict, solutionDict, **kw):
+        if key not in cls.table:
+            raise KeyError(f"unknown time integrator '{key}' (registered: {sorted(cls.table)})")  # keyExistsOrError
+        return cls.table[key](schemeDict, solutionDict, **kw)
+
+    def _source(self, eqn, sol):
+        """zero source + the explicit spatial operators (Expression::explicitOperation(nCells), expression.hpp:48-65);
+        the work vector is kept with the field instead of being allocated every step"""
+        src = getattr(sol, "_tiSource", None)
+        if src is None:
+            src = sol._tiSource = torch.empty_like(sol.internal)
+        src.zero_()
+        return eqn.explicitOperationInto(sol.mesh, src)
+
+
+class ForwardEuler(TimeIntegratorBase):
+    """forwardEuler.hpp:38-56: solution = old - source*dt; correctBoundaryConditions."""
+    name = "forwardEuler"
+
+    def solve(self, eqn, sol, t, dt):
+        src = self._source(eqn, sol)
+        old = sol.oldTime()
+        if old.internal.data_ptr() != sol.internal.data_ptr():
+            sol.internal.copy_(old.internal)
+        la.axpby(-dt, src, 1.0, sol.internal)   # old - source*dt, bit for bit
+        sol.correctBoundaryConditions()
+
+
+class RungeKutta(TimeIntegratorBase):
+    """rungeKutta.cpp:34-57 with SUNDIALS ERKStep, fixed step, table ddtSchemes.`Runge-Kutta-Method`. Only the 1-stage
+    Forward-Euler table is usable in the reference (sundials.hpp:59-78: Heun / Midpoint exit with "Currently unsupported");
+    one ERK step with it is y + dt*f(t, y), f = -explicitOperation (sundials.hpp:196-215), i.e. forwardEuler without the
+    boundary correction, followed by old = new (rungeKutta.cpp:55-56)."""
+    name = "Runge-Kutta"
+
+    def __init__(self, schemeDict, solutionDict, **kw):
+        super().__init__(schemeDict, solutionDict, **kw)
+        method = schemeDict.get("Runge-Kutta-Method")
+        if method in ("Heun", "Midpoint"):
+            raise RuntimeError("Currently unsupported until field time step-stage indexing resolved.")
+        if method != "Forward-Euler":
+            raise RuntimeError(f"Unsupported Runge-Kutta time integration method selectied: {method}.\n"
+                               "Supported methods are: Forward-Euler, Heun, Midpoint.")
+
+    def solve(self, eqn, sol, t, dt):
+        old = sol.oldTime()
+        src = self._source(eqn, sol)
+        sol.internal.copy_(old.internal)
+        la.axpby(-dt, src, 1.0, sol.internal)
+        old.internal.copy_(sol.internal)
+
+
+class BackwardEuler(TimeIntegratorBase):
+    """backwardEuler.hpp:41-60: the explicit source is evaluated and DROPPED (sic, :45), a fresh system takes the implicit
+    spatial then temporal operators (:49-50; one fused assembly launch here), la::Solver(solutionDict).solve."""
+    name = "backwardEuler"
+
+    def solve(self, eqn, sol, t, dt):
+        mesh = sol.mesh
+        if eqn.has_explicit():
+            self._source(eqn, sol)  # computed and dropped like the reference
+        ls = getattr(sol, "_tiSystem", None)
+        if ls is None:
+            ls = sol._tiSystem = la.LinearSystem(mesh, sol.ncomp, zero=False)
+        eqn.assemble(t, dt, ls.sp, ls, sol)
+        solver = getattr(sol, "_tiSolver", None)
+        if solver is None or solver._config is not self.solutionDict:
+            solver = sol._tiSolver = la.Solver(self.solutionDict, comm=self.comm, check_every=self.check_every)
+            solver._config = self.solutionDict
+        self.stats = solver.solve(ls, sol.internal)  # (the distributed solver exchanges the ghosts of its initial guess)
+        return self.stats
+
+
+def solve(exp: Expression, solution, t, dt, fvSchemes: dict, fvSolution: dict, comm=None, check_every=8):
+    """dsl::solve (dsl/solver.hpp:35-82). fvSolution is the solver dictionary of the field (Ginkgo-style, or OpenFOAM-style
+    and then mapped like FoamAdapter::mapFvSolution). Multi-GPU (new here): `comm` exchanges the ghost values of the
+    solution field before the operators read them and is handed to the linear solver."""
+    if not exp.temporal and not exp.spatial:
+        raise RuntimeError("No temporal or implicit terms to solve.")
+    exp.read(fvSchemes)
+    if comm is not None:
+        comm.halo_exchange(solution.internal)
+    if exp.temporal:
+        ddt = fvSchemes.get("ddtSchemes", {})
+        if "type" not in ddt:
+            raise KeyError("Key type not found in dictionary")
+        ti = TimeIntegratorBase.create(ddt["type"], ddt, fvSolution, comm=comm, check_every=check_every)
+        return ti.solve(exp, solution, t, dt)
+    mesh = solution.mesh
+    ls = la.LinearSystem(mesh, solution.ncomp, zero=False)
+    exp.assemble(t, dt, ls.sp, ls, solution)
+    src = torch.zeros_like(solution.internal)
+    exp.explicitOperationInto(mesh, src)
+    ops.rhs_sub_source(mesh, src, ls.rhs)
+    return la.Solver(fvSolution, comm=comm, check_every=check_every).solve(ls, solution.internal)

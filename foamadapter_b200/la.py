@@ -104,45 +104,81 @@ class SolverStats:
 
 class _Cfg(C.Structure):
     _fields_ = [("maxIter", C.c_int32), ("relTol", C.c_double), ("absTol", C.c_double), ("preconditioner", C.c_int32),
-                ("checkEvery", C.c_int32)]
+                ("checkEvery", C.c_int32), ("solverType", C.c_int32)]
 
 
 class _Stats(C.Structure):
     _fields_ = [("numIter", C.c_int32), ("initResNorm", C.c_double), ("finalResNorm", C.c_double), ("nHistory", C.c_int32)]
 
 
+# src/compatibility/fvSolution.cpp:22-28 (updateSolver) and :51-62 (updatePreconditioner)
+SOLVER_MAP = {"PCG": "solver::Cg", "PBiCG": "solver::Bicg", "PBiCGStab": "solver::Bicgstab", "smoothSolver": "solver::Bicgstab",
+              "GAMG": "solver::Multigrid"}
+PRECONDITIONER_MAP = {
+    "DIC": {"type": "preconditioner::Jacobi", "max_block_size": 1},
+    "DILU": {"type": "preconditioner::Ilu", "reverse_apply": False, "factorization": {"type": "factorization::ParIlu"}},
+}
+
+
 def mapFvSolution(d: dict) -> dict:
-    """src/compatibility/fvSolution.cpp:19-159: OpenFOAM solver entry -> Ginkgo-style config. Keys handled:
-    solver PCG|PBiCGStab(unsupported here), preconditioner DIC|DILU|none, tolerance, relTol, maxIter."""
-    if "type" in d:  # already a Ginkgo-style dict
+    """FoamAdapter::mapFvSolution (src/compatibility/fvSolution.cpp:142-157): OpenFOAM solver entry -> Ginkgo-style
+    dictionary, step for step: updateSolver (:19-46), updatePreconditioner (:48-105: a MISSING preconditioner becomes
+    DIC -> Jacobi, `smoother` is dropped, DILU -> Ilu/ParIlu), updateCriteria (:107-139: iteration 1000 unless maxIter,
+    relative/absolute norms only when relTol / tolerance are present). A dictionary with `configFile` is returned as is."""
+    if "configFile" in d:
         return d
-    solver = d.get("solver", "PCG")
-    if solver not in ("PCG", "CG"):
-        raise KeyError(f"solver '{solver}' is not on the hot path (only PCG/CG -> solver::Cg)")
-    pre = d.get("preconditioner", "none")
-    out = {"solver": "Ginkgo", "type": "solver::Cg",
-           "criteria": {"iteration": int(d.get("maxIter", 1000)), "relative_residual_norm": float(d.get("relTol", 0.0)),
-                        "absolute_residual_norm": float(d.get("tolerance", 1e-6))}}
-    if pre in ("DIC", "DILU", "Jacobi", "diagonal"):
-        out["preconditioner"] = {"type": "preconditioner::Jacobi", "max_block_size": 1}
-    elif pre not in ("none", None):
-        raise KeyError(f"preconditioner '{pre}' not supported")
+    out = {k: (dict(v) if isinstance(v, dict) else v) for k, v in d.items()}
+    name = out.get("solver")
+    if name in SOLVER_MAP:
+        out["solver"], out["type"] = "Ginkgo", SOLVER_MAP[name]
+    if "preconditioner" not in out:
+        out["preconditioner"] = dict(PRECONDITIONER_MAP["DIC"])
+    out.pop("smoother", None)
+    pre = out["preconditioner"]
+    if isinstance(pre, dict):
+        if isinstance(pre.get("type"), dict):
+            raise RuntimeError("GAMG is not supported in FoamAdapter, please use a different preconditioner.")
+    elif pre in PRECONDITIONER_MAP:
+        out["preconditioner"] = {k: (dict(v) if isinstance(v, dict) else v) for k, v in PRECONDITIONER_MAP[pre].items()}
+    crit = out.setdefault("criteria", {})
+    crit["iteration"] = 1000
+    if "relTol" in out:
+        crit["relative_residual_norm"] = float(out.pop("relTol"))
+    if "maxIter" in out:
+        crit["iteration"] = int(out.pop("maxIter"))
+    if "tolerance" in out:
+        crit["absolute_residual_norm"] = float(out.pop("tolerance"))
     return out
 
 
+SOLVER_TYPES = {"solver::Cg": 0, "solver::Bicgstab": 1}
+
+
 class Solver:
-    """la::Solver(exec, dict) (solver.hpp:63-91) for the configurations mapFvSolution emits: solver::Cg with an
-    optional scalar Jacobi preconditioner. solve(ls, x) -> SolverStats like GinkgoSolver::solve (ginkgo.hpp:116-155)."""
+    """la::Solver(exec, dict) (solver.hpp:63-91) with a Ginkgo-style dictionary (ginkgo.hpp:95-108), i.e. what
+    mapFvSolution emits or what the reference's tests pass directly (test/test_advection.cpp:125-131): solver::Cg or
+    solver::Bicgstab, optional scalar Jacobi preconditioner, criteria iteration / relative_residual_norm /
+    absolute_residual_norm. An OpenFOAM-style entry (no `type`) is mapped first. Everything else raises: there is no
+    silent downgrade (preconditioner::Ilu, solver::Bicg, solver::Multigrid are not on the hot path).
+    solve(ls, x) -> SolverStats like GinkgoSolver::solve (ginkgo.hpp:116-155)."""
 
     def __init__(self, config: dict, comm=None, check_every=8, history=False):
-        cfg = mapFvSolution(config)
-        if cfg.get("type") != "solver::Cg":
-            raise KeyError(f"solver type '{cfg.get('type')}' is not on the hot path")
+        cfg = config if "type" in config else mapFvSolution(config)
+        if cfg.get("solver", "Ginkgo") != "Ginkgo":
+            raise KeyError(f"la::SolverFactory has no solver '{cfg.get('solver')}'")  # RuntimeSelectionFactory::keyExistsOrError
+        if cfg.get("type") not in SOLVER_TYPES:
+            raise KeyError(f"solver type '{cfg.get('type')}' is not on the hot path (solver::Cg, solver::Bicgstab)")
         crit = cfg.get("criteria", {})
         pre = cfg.get("preconditioner")
+        if pre in (None, "none"):
+            precond = 0
+        elif isinstance(pre, dict) and pre.get("type") == "preconditioner::Jacobi" and int(pre.get("max_block_size", 1)) == 1:
+            precond = 1
+        else:
+            raise KeyError(f"preconditioner {pre!r} is not supported (scalar preconditioner::Jacobi only)")
         self.cfg = _Cfg(int(crit.get("iteration", 1000)), float(crit.get("relative_residual_norm", 0.0)),
-                        float(crit.get("absolute_residual_norm", 0.0)),
-                        1 if (pre and pre.get("type") == "preconditioner::Jacobi") else 0, int(check_every))
+                        float(crit.get("absolute_residual_norm", 0.0)), precond, int(check_every), SOLVER_TYPES[cfg["type"]])
+        self.type = cfg["type"]
         self.comm, self.history = comm, history
         self._h, self._shape = None, None
 
@@ -166,26 +202,40 @@ class Solver:
         except Exception:
             pass
 
+    def _launches(self, numIter):
+        # CG: K1 + K2 per completed iteration, + the final K1, + dinv / ||b|| / normB / r0; BiCGStab: 5 per iteration
+        return (2 * numIter + 5) if self.cfg.solverType == 0 else (5 * numIter + 10)
+
     def solve_csr(self, nRows, nCols, rowOffs_ptr, colIdxs_ptr, values, b, x, _mesh=None) -> SolverStats:
         h = self._handle(nRows, nCols)
         if _mesh is None and getattr(self, "_attached", None) is not None:
             check(lib().fvk_solver_attach_mesh(h, None))  # a foreign CSR: no structured shortcut
             self._attached = None
         st = _Stats()
-        nh = self.cfg.maxIter + 2 if self.history else 0
+        nh = (2 if self.cfg.solverType == 1 else 1) * self.cfg.maxIter + 2 if self.history else 0
         hist = np.zeros(max(nh, 1))
         check(lib().fvk_solver_solve(h, C.c_void_p(rowOffs_ptr), C.c_void_p(colIdxs_ptr), ptr(values), ptr(b), ptr(x),
                                      C.byref(st), hist.ctypes.data_as(C.c_void_p) if nh else None, C.c_int32(nh), _stream()))
-        # K1 + K2 per completed iteration, + the final K1, + dinv / ||b|| / normB / r0
-        ops._count(2 * st.numIter + 5)
+        ops._count(self._launches(st.numIter))
         return SolverStats(st.numIter, st.initResNorm, st.finalResNorm, hist[:st.nHistory] if nh else None)
 
-    def solve(self, ls: LinearSystem, x) -> SolverStats:
-        m = ls.mesh
+    def _attach(self, m):
         h = self._handle(m.nOwned, m.nCells)
         if getattr(self, "_attached", None) is not m:  # structured SpMV fast path when the mesh plan allows it
             check(lib().fvk_solver_attach_mesh(h, m.handle))
             self._attached = m
+        return h
+
+    def solve(self, ls: LinearSystem, x):
+        """Scalar system -> SolverStats; Vec3 system (identical components) -> one SolverStats per component."""
+        m = ls.mesh
+        h = self._attach(m)
+        if ls.ncomp == 3:
+            st3 = (_Stats * 3)()
+            check(lib().fvk_solver_solve_vec3(h, C.c_int64(m.nnz), C.c_void_p(ls.sp.rowOffs_ptr), C.c_void_p(ls.sp.colIdxs_ptr),
+                                              ptr(ls.values), ptr(ls.rhs), ptr(x), st3, _stream()))
+            ops._count(sum(self._launches(s.numIter) + 3 for s in st3) + 1)
+            return [SolverStats(s.numIter, s.initResNorm, s.finalResNorm) for s in st3]
         return self.solve_csr(m.nOwned, m.nCells, ls.sp.rowOffs_ptr, ls.sp.colIdxs_ptr, ls.values, ls.rhs, x, _mesh=m)
 
 
@@ -197,6 +247,11 @@ def add(x, y): check(lib().fvk_vec_add(_n(x), ptr(x), ptr(y), _stream())); ops._
 def sub(x, y): check(lib().fvk_vec_sub(_n(x), ptr(x), ptr(y), _stream())); ops._count(); return x
 def mul(x, y): check(lib().fvk_vec_mul(_n(x), ptr(x), ptr(y), _stream())); ops._count(); return x
 def axpby(a, x, b, y): check(lib().fvk_vec_axpby(_n(y), C.c_double(a), ptr(x), C.c_double(b), ptr(y), _stream())); ops._count(); return y
+
+
+def scaledCopy(a, x, out):
+    """out = x * a"""
+    check(lib().fvk_vec_scaled_copy(_n(x), C.c_double(a), ptr(x), ptr(out), _stream())); ops._count(); return out
 
 
 def dot(x, y, out=None):

@@ -25,30 +25,61 @@ struct RunTime
     fvk_comm* comm = nullptr; // multi-GPU runs: halo exchange + all-reduced dots (nullptr = single GPU)
 };
 
-// src/compatibility/fvSolution.cpp:19-159: OpenFOAM solver entry -> Ginkgo-style dictionary
+// FoamAdapter::mapFvSolution (src/compatibility/fvSolution.cpp:142-157), step for step: updateSolver (:19-46),
+// updatePreconditioner (:48-105; a MISSING preconditioner becomes DIC -> scalar Jacobi, `smoother` is dropped, DILU -> Ilu /
+// ParIlu, which la::Solver then rejects), updateCriteria (:107-139; iteration 1000 unless maxIter, the norms only when relTol /
+// tolerance are present). A dictionary with `configFile` is returned unchanged.
 inline NeoN::Dictionary mapFvSolution(const NeoN::Dictionary& in)
 {
-    if (in.contains("type")) return in; // already mapped (configFile / Ginkgo-style entry)
-    NeoN::Dictionary out;
-    const auto solver = in.getOr<std::string>("solver", "PCG");
-    if (solver == "PCG" || solver == "CG") out.insert("type", std::string("solver::Cg"));
-    else if (solver == "PBiCGStab") out.insert("type", std::string("solver::Bicgstab"));
-    else NF_ERROR_EXIT("unsupported solver " + solver);
-    out.insert("solver", std::string("Ginkgo"));
-    const auto pre = in.getOr<std::string>("preconditioner", "none");
-    if (pre == "DIC" || pre == "DILU")
+    if (in.contains("configFile")) return in;
+    NeoN::Dictionary out = in;
+    static const std::map<std::string, std::string> solverMap = {{"PCG", "solver::Cg"}, {"PBiCG", "solver::Bicg"}, {"PBiCGStab", "solver::Bicgstab"},
+                                                                 {"smoothSolver", "solver::Bicgstab"}, {"GAMG", "solver::Multigrid"}};
+    if (out.contains("solver"))
     {
+        auto it = solverMap.find(out.get<std::string>("solver"));
+        if (it != solverMap.end())
+        {
+            out.insert("solver", std::string("Ginkgo"));
+            out.insert("type", it->second);
+        }
+    }
+    auto jacobi = [] {
         NeoN::Dictionary p;
         p.insert("type", std::string("preconditioner::Jacobi"));
         p.insert("max_block_size", 1);
-        out.insert("preconditioner", p);
+        return p;
+    };
+    if (!out.contains("preconditioner")) out.insert("preconditioner", jacobi());
+    if (out.contains("smoother")) out.remove("smoother");
+    if (out.isDict("preconditioner"))
+    {
+        if (out.subDict("preconditioner").isDict("type"))
+            NF_ERROR_EXIT("GAMG is not supported in FoamAdapter, please use a different preconditioner.");
     }
-    else if (pre != "none") NF_ERROR_EXIT("unsupported preconditioner " + pre);
-    NeoN::Dictionary crit;
-    crit.insert("iteration", in.getOr<int>("maxIter", 1000));
-    crit.insert("relative_residual_norm", in.getOr<scalar>("relTol", 0.0));
-    crit.insert("absolute_residual_norm", in.getOr<scalar>("tolerance", 1e-6));
-    out.insert("criteria", crit);
+    else
+    {
+        const auto pre = out.get<std::string>("preconditioner");
+        if (pre == "DIC") out.insert("preconditioner", jacobi());
+        else if (pre == "DILU")
+        {
+            NeoN::Dictionary p, f;
+            f.insert("type", std::string("factorization::ParIlu"));
+            p.insert("type", std::string("preconditioner::Ilu"));
+            p.insert("reverse_apply", false);
+            p.insert("factorization", f);
+            out.insert("preconditioner", p);
+        }
+    }
+    if (!out.contains("criteria")) out.insert("criteria", NeoN::Dictionary());
+    auto& crit = out.subDict("criteria");
+    crit.insert("iteration", 1000);
+    auto num = [&](const std::string& key) { // scalar entries may have been written as integers (relTol 0)
+        try { return out.get<NeoN::scalar>(key); } catch (...) { return NeoN::scalar(out.get<int>(key)); }
+    };
+    if (out.contains("relTol")) { crit.insert("relative_residual_norm", num("relTol")); out.remove("relTol"); }
+    if (out.contains("maxIter")) { crit.insert("iteration", out.get<int>("maxIter")); out.remove("maxIter"); }
+    if (out.contains("tolerance")) { crit.insert("absolute_residual_norm", num("tolerance")); out.remove("tolerance"); }
     return out;
 }
 

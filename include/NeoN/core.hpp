@@ -207,6 +207,12 @@ public:
     Dictionary(std::initializer_list<std::pair<const std::string, std::any>> init) : data_(init) {}
     void insert(const std::string& key, const std::any& value) { data_[key] = value; }
     bool contains(const std::string& key) const { return data_.count(key) > 0; }
+    void remove(const std::string& key) { data_.erase(key); }
+    bool isDict(const std::string& key) const
+    {
+        auto it = data_.find(key);
+        return it != data_.end() && it->second.type() == typeid(Dictionary);
+    }
     template<typename T> T& get(const std::string& key)
     {
         auto it = data_.find(key);

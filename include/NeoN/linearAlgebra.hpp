@@ -108,17 +108,22 @@ struct SolverStats
     }
 };
 
-// la::Solver(exec, dict) (solver.hpp:63-91) for the dictionaries mapFvSolution emits (FoamAdapter
-// src/compatibility/fvSolution.cpp:19-159): {solver Ginkgo; type solver::Cg; preconditioner{type preconditioner::Jacobi;
-// max_block_size 1}; criteria{iteration; relative_residual_norm; absolute_residual_norm}}.
+// la::Solver(exec, dict) (solver.hpp:63-91) for Ginkgo-style dictionaries (ginkgo.hpp:95-108) as mapFvSolution emits them
+// (FoamAdapter src/compatibility/fvSolution.cpp:19-159) or as the reference's tests pass them (test/test_advection.cpp:125-131):
+// {solver Ginkgo; type solver::Cg | solver::Bicgstab; preconditioner{type preconditioner::Jacobi; max_block_size 1};
+// criteria{iteration; relative_residual_norm; absolute_residual_norm}}. Anything else is an error (no silent downgrade).
 class Solver
 {
 public:
     Solver(const Executor& exec, const Dictionary& dict, fvk_comm* comm = nullptr, int checkEvery = 8, bool history = false)
         : exec_(exec), comm_(comm), history_(history)
     {
+        const auto name = dict.getOr<std::string>("solver", "Ginkgo");
+        if (name != "Ginkgo") NF_ERROR_EXIT("la::SolverFactory has no solver " + name);
         const auto type = dict.getOr<std::string>("type", "solver::Cg");
-        if (type != "solver::Cg") NF_ERROR_EXIT("solver type " + type + " is not on the hot path (solver::Cg only)");
+        if (type == "solver::Cg") cfg_.solverType = FVK_SOLVER_CG;
+        else if (type == "solver::Bicgstab") cfg_.solverType = FVK_SOLVER_BICGSTAB;
+        else NF_ERROR_EXIT("solver type " + type + " is not on the hot path (solver::Cg, solver::Bicgstab)");
         cfg_.maxIter = 1000; cfg_.relTol = 0.0; cfg_.absTol = 0.0; cfg_.preconditioner = FVK_PRECOND_NONE; cfg_.checkEvery = checkEvery;
         if (dict.contains("criteria"))
         {
@@ -129,9 +134,11 @@ public:
         }
         if (dict.contains("preconditioner"))
         {
-            const auto ptype = dict.subDict("preconditioner").getOr<std::string>("type", "");
-            if (ptype == "preconditioner::Jacobi") cfg_.preconditioner = FVK_PRECOND_JACOBI;
-            else NF_ERROR_EXIT("preconditioner " + ptype + " not supported");
+            if (!dict.isDict("preconditioner")) NF_ERROR_EXIT("preconditioner " + dict.get<std::string>("preconditioner") + " not supported");
+            const auto& pd = dict.subDict("preconditioner");
+            const auto ptype = pd.getOr<std::string>("type", "");
+            if (ptype == "preconditioner::Jacobi" && pd.getOr<int>("max_block_size", 1) == 1) cfg_.preconditioner = FVK_PRECOND_JACOBI;
+            else NF_ERROR_EXIT("preconditioner " + ptype + " not supported (scalar preconditioner::Jacobi only)");
         }
     }
     Solver(const Solver&) = delete;
@@ -147,20 +154,36 @@ public:
             h_ = nullptr;
             check(fvk_solver_create(m.nOwnedCells(), m.nCells(), &cfg_, comm_, &h_));
             rows_ = m.nOwnedCells(); cols_ = m.nCells();
-            attached_ = nullptr;
         }
-        if (attached_ != m.handle()) // structured SpMV inside CG when the mesh plan proved a block topology
-        {
-            check(fvk_solver_attach_mesh(h_, m.handle()));
-            attached_ = m.handle();
-        }
+        // structured SpMV inside the solver when the mesh plan proved a block topology; re-attached on every solve (host-only,
+        // cheap): a mesh destroyed and re-created at the same address must not leave stale dimensions behind
+        check(fvk_solver_attach_mesh(h_, m.handle()));
         const auto& sp = ls.sparsityPattern();
         fvk_solver_stats st {};
-        std::vector<scalar> hist(history_ ? size_t(cfg_.maxIter) + 2 : 0);
+        std::vector<scalar> hist(history_ ? size_t(cfg_.solverType == FVK_SOLVER_BICGSTAB ? 2 : 1) * size_t(cfg_.maxIter) + 2 : 0);
         check(fvk_solver_solve(h_, sp.rowOffs().ptr, sp.colIdxs().ptr, ls.values().data(), ls.rhs().data(), x.data(), &st,
                                history_ ? hist.data() : nullptr, int32_t(hist.size()), exec_.stream()));
         hist.resize(history_ ? size_t(st.nHistory) : 0);
         return {st.numIter, st.initResNorm, st.finalResNorm, hist};
+    }
+    // Vec3 system with identical components (momentum equation): one scalar solve per component over the component matrix
+    std::array<SolverStats, 3> solve(const LinearSystem<Vec3, localIdx>& ls, Vector<Vec3>& x) const
+    {
+        const auto& m = ls.mesh();
+        if (!h_ || rows_ != m.nOwnedCells() || cols_ != m.nCells())
+        {
+            if (h_) fvk_solver_destroy(h_);
+            h_ = nullptr;
+            check(fvk_solver_create(m.nOwnedCells(), m.nCells(), &cfg_, comm_, &h_));
+            rows_ = m.nOwnedCells(); cols_ = m.nCells();
+        }
+        check(fvk_solver_attach_mesh(h_, m.handle()));
+        const auto& sp = ls.sparsityPattern();
+        fvk_solver_stats st[3] {};
+        check(fvk_solver_solve_vec3(h_, int64_t(ls.values().size()), sp.rowOffs().ptr, sp.colIdxs().ptr, ls.values().raw(), ls.rhs().raw(), x.raw(), st,
+                                    exec_.stream()));
+        return {SolverStats {st[0].numIter, st[0].initResNorm, st[0].finalResNorm, {}}, SolverStats {st[1].numIter, st[1].initResNorm, st[1].finalResNorm, {}},
+                SolverStats {st[2].numIter, st[2].initResNorm, st[2].finalResNorm, {}}};
     }
 private:
     Executor exec_;
@@ -169,7 +192,6 @@ private:
     fvk_solver_config cfg_ {};
     mutable fvk_solver* h_ = nullptr;
     mutable localIdx rows_ = 0, cols_ = 0;
-    mutable const fvk_mesh* attached_ = nullptr;
 };
 
 } // namespace NeoN::la

@@ -363,6 +363,9 @@ int fvk_vec_sub(int64_t n, double* x, const double* y, fvk_stream stream);
 int fvk_vec_mul(int64_t n, double* x, const double* y, fvk_stream stream);
 /* y = a*x + b*y */
 int fvk_vec_axpby(int64_t n, double a, const double* x, double b, double* y, fvk_stream stream);
+/* out = x * a: the temporary `Vector operator*(Vector, scalar)` creates (vector.hpp; scalarAdvection.cpp:66-67
+ * nfPhi = nfPhi0 * cos(...)), written straight to its destination */
+int fvk_vec_scaled_copy(int64_t n, double a, const double* x, double* out, fvk_stream stream);
 /* result_d[0] = sum x[i]*y[i]  /  sqrt(sum x[i]^2): deterministic two-stage warp-shuffle reduction,
  * result stays on the device (no host sync). */
 int fvk_dot(int64_t n, const double* x, const double* y, double* result_d, fvk_stream stream);
@@ -381,12 +384,17 @@ int fvk_norm2(int64_t n, const double* x, double* result_d, fvk_stream stream);
 typedef struct fvk_solver fvk_solver;
 typedef struct fvk_comm fvk_comm;
 enum { FVK_PRECOND_NONE = 0, FVK_PRECOND_JACOBI = 1 };
+/* solver::Cg (PCG) | solver::Bicgstab (PBiCGStab, smoothSolver: src/compatibility/fvSolution.cpp:22-28). BiCGStab follows
+ * Ginkgo 1.10's published loop (two stopping checks per iteration, on ||r|| and on the half-step residual ||s||; a stop at
+ * the half step adds alpha*y to x and does not count as an iteration); five kernels per iteration, scalars on the device. */
+enum { FVK_SOLVER_CG = 0, FVK_SOLVER_BICGSTAB = 1 };
 typedef struct fvk_solver_config {
     int32_t maxIter;        /* criteria.iteration (default 1000, fvSolution.cpp:117-138) */
     double relTol;          /* criteria.relative_residual_norm */
     double absTol;          /* criteria.absolute_residual_norm */
     int32_t preconditioner; /* FVK_PRECOND_* */
     int32_t checkEvery;     /* host polls the device stop flag every this many iterations (>=1) */
+    int32_t solverType;     /* FVK_SOLVER_* */
 } fvk_solver_config;
 typedef struct fvk_solver_stats {
     int32_t numIter;
@@ -408,6 +416,12 @@ int fvk_solver_attach_mesh(fvk_solver* solver, const fvk_mesh* mesh);
 int fvk_solver_solve(fvk_solver* solver, const int32_t* rowOffs, const int32_t* colIdxs,
                      const double* values, const double* b, double* x, fvk_solver_stats* stats_h,
                      double* history_h, int32_t maxHistory, fvk_stream stream);
+
+/* Vec3 LinearSystem (values Vec3[nnz] with identical components; rhs / x Vec3[nRows] / [nCols]): three scalar
+ * solves over the component matrix (NeoN's la::Solver has no Vec3 overload, solver.hpp:52; this is what `momentumPredictor yes`
+ * of neoIcoFoam.cpp:100-103 needs). stats3_h receives one fvk_solver_stats per component. */
+int fvk_solver_solve_vec3(fvk_solver* solver, int64_t nnz, const int32_t* rowOffs, const int32_t* colIdxs, const double* valuesV,
+                          const double* bV, double* xV, fvk_solver_stats* stats3_h, fvk_stream stream);
 
 /* ------------------------------------------------------------------------------------------------
  * PISO pressure-velocity coupling (FoamAdapter src/algorithms/pressureVelocityCoupling.cpp) and the

@@ -29,6 +29,7 @@ def lib() -> C.CDLL:
         _LIB = C.CDLL(str(build()))
         _LIB.fvo_max_threads.restype = C.c_int
         _LIB.fvo_cg.restype = C.c_int
+        _LIB.fvo_bicgstab.restype = C.c_int
     return _LIB
 
 
@@ -267,13 +268,21 @@ class Mesh:
     def cg(self, values, b, x0, jacobi=True, max_iter=1000, rel_tol=0.0, abs_tol=1e-6, par=0, max_hist=0):
         return cg(self.rowOffs, self.colIdxs, values, b, x0, jacobi, max_iter, rel_tol, abs_tol, par, max_hist)
 
+    def bicgstab(self, values, b, x0, jacobi=True, max_iter=1000, rel_tol=0.0, abs_tol=0.0, par=0, max_hist=0):
+        return bicgstab(self.rowOffs, self.colIdxs, values, b, x0, jacobi, max_iter, rel_tol, abs_tol, par, max_hist)
 
-def cg(rowOffs, colIdxs, values, b, x0, jacobi=True, max_iter=1000, rel_tol=0.0, abs_tol=1e-6, par=0, max_hist=0):
+
+def cg(rowOffs, colIdxs, values, b, x0, jacobi=True, max_iter=1000, rel_tol=0.0, abs_tol=1e-6, par=0, max_hist=0, fn="fvo_cg"):
     """Returns (x, dict(numIter, initResNorm, finalResNorm), history)."""
     x = f64(x0).copy()
     stats = np.zeros(3)
     hist = np.zeros(max(max_hist, 1))
-    nh = lib().fvo_cg(C.c_int(par), C.c_int(int(jacobi)), C.c_int32(len(x)), _arg(i32(rowOffs)), _arg(i32(colIdxs)),
+    nh = getattr(lib(), fn)(C.c_int(par), C.c_int(int(jacobi)), C.c_int32(len(x)), _arg(i32(rowOffs)), _arg(i32(colIdxs)),
                       _arg(f64(values)), _arg(f64(b)), _arg(x), C.c_int(max_iter), C.c_double(rel_tol),
                       C.c_double(abs_tol), _arg(stats), _arg(hist) if max_hist else C.c_void_p(0), C.c_int(max_hist))
     return x, dict(numIter=int(stats[0]), initResNorm=stats[1], finalResNorm=stats[2]), hist[:nh]
+
+
+def bicgstab(rowOffs, colIdxs, values, b, x0, jacobi=True, max_iter=1000, rel_tol=0.0, abs_tol=0.0, par=0, max_hist=0):
+    """Ginkgo solver::Bicgstab restated (fvo_bicgstab); history holds every checked norm (||r|| and ||s|| alternate)."""
+    return cg(rowOffs, colIdxs, values, b, x0, jacobi, max_iter, rel_tol, abs_tol, par, max_hist, fn="fvo_bicgstab")

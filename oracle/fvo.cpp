@@ -724,6 +724,88 @@ int fvo_cg(int par, int jacobi, int32_t n, const int32_t* rowOffs, const int32_t
     return nh;
 }
 
+// Ginkgo 1.10 solver::Bicgstab with optional scalar-Jacobi preconditioner, restated from the published algorithm
+// (third party, not in the tree; selected by mapFvSolution for PBiCGStab / smoothSolver, src/compatibility/fvSolution.cpp:25-26,
+// and by test/test_advection.cpp:125-131,176-183; call site ginkgo.hpp:116-155). Parity unpinned beyond the properties
+// tests/test_oracle_golden.py checks (exact solve of small systems, residual identities):
+//   r = b - A x; rr = r; rho = rho_prev = alpha = beta = gamma = omega = 1; p = v = s = t = y = z = 0
+//   loop (iter = 0, 1, ...):
+//     rho = rr.r; stop on ||r|| (iter >= maxIter or ||r|| <= rel ||b|| or ||r|| <= abs)
+//     p = r + (rho/rho_prev)(alpha/omega)(p - omega v)   [p = r when rho_prev*omega == 0]
+//     y = M^-1 p; v = A y; beta = rr.v; alpha = rho/beta (0 when beta == 0); s = r - alpha v
+//     stop on ||s|| (same criteria, same iter): x += alpha y (finalize) and leave
+//     z = M^-1 s; t = A z; gamma = s.t; beta = t.t; omega = gamma/beta (0 when beta == 0)
+//     x += alpha y + omega z; r = s - omega t; swap(rho_prev, rho)
+// stats / history as fvo_cg: numIter = iter at the stop (a half step does not count), finalResNorm = the norm the
+// stopping check saw (||r|| or ||s||); history gets every checked norm (two per full iteration).
+int fvo_bicgstab(int par, int jacobi, int32_t n, const int32_t* rowOffs, const int32_t* colIdxs, const double* values,
+                 const double* b, double* x, int maxIter, double relTol, double absTol, double* stats, double* history,
+                 int maxHist)
+{
+    std::vector<double> r(n), rr(n), p(n, 0.0), v(n, 0.0), s(n, 0.0), t(n, 0.0), y(n, 0.0), z(n, 0.0), dinv(n, 1.0);
+    auto dotp = [&](const double* a, const double* c) {
+        double sum = 0.0;
+#pragma omp parallel for reduction(+ : sum) if (par)
+        for (label i = 0; i < n; ++i) sum += a[i] * c[i];
+        return sum;
+    };
+    if (jacobi)
+        for (label i = 0; i < n; ++i)
+            for (label k = rowOffs[i]; k < rowOffs[i + 1]; ++k)
+                if (colIdxs[k] == i) dinv[i] = 1.0 / values[k];
+    fvo_spmv(par, n, rowOffs, colIdxs, values, x, r.data());
+    PFOR(par, i, 0, n) { r[i] = b[i] - r[i]; rr[i] = r[i]; }
+    const double normB = std::sqrt(dotp(b, b));
+    double rho = 1.0, rhoPrev = 1.0, alpha = 1.0, beta = 1.0, gamma = 1.0, omega = 1.0;
+    int iter = -1, nh = 0;
+    double normChk = 0.0;
+    auto stop = [&](const double* res) {
+        normChk = std::sqrt(dotp(res, res));
+        if (history && nh < maxHist) history[nh++] = normChk;
+        return iter >= maxIter || normChk <= relTol * normB || normChk <= absTol;
+    };
+    while (true)
+    {
+        ++iter;
+        rho = dotp(rr.data(), r.data());
+        if (stop(r.data())) break;
+        if (rhoPrev * omega != 0.0)
+        {
+            const double tmp = (rho / rhoPrev) * (alpha / omega);
+            PFOR(par, i, 0, n) { p[i] = r[i] + tmp * (p[i] - omega * v[i]); }
+        }
+        else
+            PFOR(par, i, 0, n) { p[i] = r[i]; }
+        PFOR(par, i, 0, n) { y[i] = jacobi ? p[i] * dinv[i] : p[i]; }
+        fvo_spmv(par, n, rowOffs, colIdxs, values, y.data(), v.data());
+        beta = dotp(rr.data(), v.data());
+        if (beta != 0.0)
+        {
+            alpha = rho / beta;
+            PFOR(par, i, 0, n) { s[i] = r[i] - alpha * v[i]; }
+        }
+        else
+        {
+            alpha = 0.0;
+            PFOR(par, i, 0, n) { s[i] = r[i]; }
+        }
+        if (stop(s.data()))
+        {
+            PFOR(par, i, 0, n) { x[i] += alpha * y[i]; }
+            break;
+        }
+        PFOR(par, i, 0, n) { z[i] = jacobi ? s[i] * dinv[i] : s[i]; }
+        fvo_spmv(par, n, rowOffs, colIdxs, values, z.data(), t.data());
+        gamma = dotp(s.data(), t.data());
+        beta = dotp(t.data(), t.data());
+        omega = beta != 0.0 ? gamma / beta : 0.0;
+        PFOR(par, i, 0, n) { x[i] += alpha * y[i] + omega * z[i]; r[i] = s[i] - omega * t[i]; }
+        std::swap(rhoPrev, rho);
+    }
+    stats[0] = iter; stats[1] = normB; stats[2] = normChk;
+    return nh;
+}
+
 // ---- PISO glue (FoamAdapter src/algorithms/pressureVelocityCoupling.cpp) ---------------------------------
 // computeRAU :38-63 : rAU = V / diag[0] of the Vec3 momentum matrix
 void fvo_rAU(int32_t nC, const int32_t* rowOffs, const uint8_t* diagOffs, const double* V, const double* valuesV,

@@ -232,4 +232,6 @@ def test_solver_rejects_unknown_configuration():
     with pytest.raises(KeyError):
         la.Solver({"solver": "GAMG"})
     with pytest.raises(KeyError):
-        la.Solver({"solver": "Ginkgo", "type": "solver::Bicgstab"})
+        la.Solver({"solver": "Ginkgo", "type": "solver::Bicg"})
+    with pytest.raises(KeyError):  # DILU -> preconditioner::Ilu (fvSolution.cpp:56-62) is not on the hot path: no silent downgrade
+        la.Solver({"solver": "PBiCGStab", "preconditioner": "DILU", "tolerance": 1e-6})
