@@ -12,6 +12,7 @@
 // inside a term, faces in ascending id, then boundary faces), so the result is bit-identical.
 #include "fvk_device.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace
@@ -221,7 +222,8 @@ __device__ __forceinline__ void face_coeffs_k(const fvk_term& t, const AsmMesh& 
 template <class VT, int K0, int K1>
 __global__ void __launch_bounds__(256)
 k_assemble_fast(Terms terms, AsmMesh m, fvk_bfield bd, int ft0, int ft1, double* __restrict__ values,
-                double* __restrict__ rhs, double* __restrict__ bcMatrix, double* __restrict__ bcRhs)
+                double* __restrict__ rhs, double* __restrict__ bcMatrix, double* __restrict__ bcRhs,
+                const int* __restrict__ cellList = nullptr, int nList = 0, int tailFirst = 0, int nTail = 0)
 {
     using T = typename VT::T;
     constexpr int NC = VT::NC;
@@ -229,14 +231,17 @@ k_assemble_fast(Terms terms, AsmMesh m, fvk_bfield bd, int ft0, int ft1, double*
     extern __shared__ double stageAll[];
     const int lane = threadIdx.x & 31;
     double* stage = stageAll + size_t(threadIdx.x >> 5) * ASM_CAPW * NC;
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = c < m.nC;
+    // cellList mode (the rows k_assemble_affine leaves out): entry idx < nList is cellList[idx], the following nTail
+    // entries are the rows tailFirst.. (ghost rows of a decomposed mesh); rows are not contiguous -> direct stores
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = cellList ? idx < nList + nTail : idx < m.nC;
+    const int c = !cellList ? idx : (idx < nList ? cellList[active ? idx : 0] : tailFirst + (idx - nList));
     const int r0 = active ? m.rowOffs[c] : 0, r1 = active ? m.rowOffs[c + 1] : 0;
     const int s0 = active ? m.seg[c] : 0, s1 = active ? m.seg[c + 1] : 0;
     const int nInt = r1 - r0 - 1; // internal faces of the cell (-1 on inactive lanes)
     const int wbase = __shfl_sync(0xffffffffu, r0, 0);
     const int wend = __reduce_max_sync(0xffffffffu, r1);
-    const bool staged = (wend - wbase) <= ASM_CAPW;
+    const bool staged = !cellList && (wend - wbase) <= ASM_CAPW;
     int code[ASM_E];
 #pragma unroll
     for (int k = 0; k < ASM_E; ++k) code[k] = (k < nInt) ? m.ent[s0 + k] : 0;
@@ -370,6 +375,167 @@ k_assemble_fast(Terms terms, AsmMesh m, fvk_bfield bd, int ft0, int ft1, double*
     }
 }
 
+
+// ---- block-structured meshes: index-free assembly of the regular rows ---------------------------------------------------
+// When the mesh plan proved the block topology (FvkBrickGeom::affine, fvk_brickplan.cpp), a REGULAR cell c = i + nx (j + ny k)
+// (not in the outermost layer) has the stencil [zL, yL, xL | x, y, z] with arithmetic face ids (fs(c) .. fs(c)+2 owned,
+// fs(c-1), fs(c-nx)+1, fs(c-nx ny)+2 lower) and its CSR row is [3 lower | diag | 3 upper]: no stencil, offset or diagOffset
+// array is read. A block owns a 32 x BY x BZ brick (one warp = one x-run of 32 cells): every cell evaluates the
+// coefficients of the three faces it owns ONCE into shared memory (the faces on the brick's three lower sides by spare
+// threads), so every face operand is read from DRAM once and all loads of a thread are independent; after one barrier a
+// regular cell folds its six faces in the reference's order (same arithmetic as k_assemble / k_assemble_fast: bit-identical)
+// and the warp writes its 32 rows (contiguous in CSR) with coalesced stores. Vec3 systems have identical components
+// (SURVEY A.3): the row is computed once and written replicated. Irregular cells (boundary / cut layers) and ghost rows go
+// through k_assemble_fast's cell-list mode.
+struct AsmAffine
+{
+    int nx, ny, nz, tx, ty;
+    int tdx, tdy; // tiles along x, y
+};
+constexpr int AFF_LX = 32;
+
+template <class VT, int K0, int K1, int BY, int BZ>
+__global__ void __launch_bounds__(AFF_LX * BY * BZ, 4)
+k_assemble_affine(Terms terms, AsmMesh m, AsmAffine g, int ft0, int ft1, double* __restrict__ values, double* __restrict__ rhs)
+{
+    using T = typename VT::T;
+    constexpr int NC = VT::NC;
+    constexpr bool HAS1 = K1 != 0;
+    constexpr int NCO = HAS1 ? 4 : 2; // doubles per face slot: {lo0, up0[, lo1, up1]}
+    constexpr int TB = AFF_LX * BY * BZ;
+    constexpr int XB = 3 * TB;
+    extern __shared__ __align__(16) double smemA[];
+    double* coef = smemA;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int nx = g.nx, ny = g.ny, nz = g.nz;
+    const int64_t nxy = int64_t(nx) * ny;
+    const int ix = blockIdx.x % g.tdx, q = blockIdx.x / g.tdx, iy = q % g.tdy, iz = q / g.tdy;
+    const int x0 = ix * AFF_LX, y0 = iy * BY, z0 = iz * BZ;
+    const int rl = min(AFF_LX, nx - x0), ry = min(BY, ny - y0), rz = min(BZ, nz - z0);
+    const int off = lane, r = tid >> 5;
+    const int a = (ry == BY) ? (r % BY) : (r % ry), b = (ry == BY) ? (r / BY) : (r / ry);
+    const bool valid = off < rl && b < rz;
+    const int i = x0 + off, j = y0 + a, k = z0 + b;
+    const bool upper = valid && i < nx - 1 && j < ny - 1 && k < nz - 1;
+    const bool regular = upper && i > 0 && j > 0 && k > 0;
+    const int64_t cell = i + int64_t(nx) * j + nxy * k;
+    const int64_t fs = 3 * cell - int64_t(g.tx) * (j + int64_t(ny) * k) - int64_t(g.ty) * k * nx;
+    const fvk_term& t0 = terms.t[ft0];
+    const fvk_term& t1 = terms.t[HAS1 ? ft1 : ft0];
+    // ---- the three faces this cell owns: all loads independent, coefficients into shared memory
+    if (upper)
+    {
+        double lo0[3], up0[3], lo1[3], up1[3];
+#pragma unroll
+        for (int f = 0; f < 3; ++f)
+        {
+            face_coeffs_k<K0>(t0, m, int(fs) + f, lo0[f], up0[f]);
+            if (HAS1) face_coeffs_k<K1>(t1, m, int(fs) + f, lo1[f], up1[f]);
+        }
+#pragma unroll
+        for (int f = 0; f < 3; ++f)
+        {
+            double* s = coef + size_t(3 * tid + f) * NCO;
+            s[0] = lo0[f]; s[1] = up0[f];
+            if (HAS1) { s[2] = lo1[f]; s[3] = up1[f]; }
+        }
+    }
+    // ---- per-cell operands of a regular row, issued before the barrier
+    int r0 = 0;
+    double os0 = 0.0, os1 = 0.0;
+    if (regular)
+    {
+        r0 = m.rowOffs[cell];
+        os0 = term_scaling(t0, int(cell));
+        if (HAS1) os1 = term_scaling(t1, int(cell));
+    }
+    // ---- cross faces: e < nZ: z side (b = 0) | < nZ + nY: y side (a = 0) | x side (off = 0); only for regular consumers
+    const int nZ = rl * ry, nY = rl * rz, nX = ry * rz, nCross = nZ + nY + nX;
+    for (int e = tid; e < nCross; e += TB)
+    {
+        int co, ca, cb;
+        int64_t dFace;
+        if (e < nZ) { co = e % rl; ca = e / rl; cb = 0; dFace = -3 * nxy + int64_t(g.tx) * ny + int64_t(g.ty) * nx + 2; }
+        else if (e < nZ + nY) { const int e1 = e - nZ; co = e1 % rl; cb = e1 / rl; ca = 0; dFace = -3 * int64_t(nx) + g.tx + 1; }
+        else { const int e1 = e - nZ - nY; ca = e1 % ry; cb = e1 / ry; co = 0; dFace = -3; }
+        const int ci = x0 + co, cj = y0 + ca, ck = z0 + cb;
+        if (!(ci > 0 && ci < nx - 1 && cj > 0 && cj < ny - 1 && ck > 0 && ck < nz - 1)) continue; // consumer not regular
+        const int64_t cc = ci + int64_t(nx) * cj + nxy * ck;
+        const int64_t xf = 3 * cc - int64_t(g.tx) * (cj + int64_t(ny) * ck) - int64_t(g.ty) * ck * nx + dFace;
+        double* s = coef + size_t(XB + e) * NCO;
+        face_coeffs_k<K0>(t0, m, int(xf), s[0], s[1]);
+        if (HAS1) face_coeffs_k<K1>(t1, m, int(xf), s[2], s[3]);
+    }
+    __syncthreads();
+    // ---- regular rows: [zL, yL, xL | diag | x, y, z]
+    double row[7];
+    T rr = VT::zero();
+    if (regular)
+    {
+        const int slot[6] = {b > 0 ? 3 * (tid - 32 * ry) + 2 : XB + off + rl * a,
+                             a > 0 ? 3 * (tid - 32) + 1 : XB + nZ + off + rl * b,
+                             off > 0 ? 3 * (tid - 1) : XB + nZ + nY + a + ry * b,
+                             3 * tid, 3 * tid + 1, 3 * tid + 2};
+        double dc0[6], dc1[6];
+#pragma unroll
+        for (int e = 0; e < 6; ++e)
+        {
+            const double* s = coef + size_t(slot[e]) * NCO;
+            const bool side = e < 3; // the cell is the face's neighbour
+            double v = 0.0 + os0 * (1.0 * (side ? s[0] : s[1]));
+            if (HAS1) v = v + os1 * (1.0 * (side ? s[2] : s[3]));
+            dc0[e] = side ? s[1] : s[0];
+            dc1[e] = HAS1 ? (side ? s[3] : s[2]) : 0.0;
+            row[side ? e : e + 1] = v;
+        }
+        // diagonal and rhs: term-major, faces ascending inside a term (identical order to k_assemble)
+        double d = 0.0;
+        for (int kt = 0; kt < terms.n; ++kt)
+        {
+            const fvk_term& t = terms.t[kt];
+            if (t.kind == FVK_TERM_DIV || t.kind == FVK_TERM_LAPLACIAN)
+            {
+                const bool second = HAS1 && kt == ft1;
+                const double os = second ? os1 : os0;
+#pragma unroll
+                for (int e = 0; e < 6; ++e) d = d - os * (1.0 * (second ? dc1[e] : dc0[e]));
+            }
+            else if (t.kind == FVK_TERM_DDT)
+            { // ddtOperator.cpp:50-59
+                const double os = term_scaling(t, int(cell));
+                const double dtInver = 1.0 / t.dt;
+                const double commonCoef = os * m.V[cell] * dtInver;
+                d = d + 1.0 * commonCoef;
+                rr = VT::add(rr, VT::mul(commonCoef, VT::ld(t.cellField, cell)));
+            }
+            else if (t.kind == FVK_TERM_SOURCE)
+            { // sourceTerm.cpp:46-54
+                const double os = term_scaling(t, int(cell));
+                d = d + 1.0 * (os * t.cellField[cell] * m.V[cell]);
+            }
+        }
+        row[3] = d;
+        VT::st(rhs, cell, rr);
+    }
+    // ---- coalesced row store: the regular lanes of a warp are consecutive cells = consecutive CSR rows of 7 entries
+    __syncthreads(); // every thread is done with the coefficient slots: the staging area reuses them
+    double* stage = smemA + size_t(r) * (32 * 7);
+    const unsigned regMask = __ballot_sync(0xffffffffu, regular);
+    if (regMask == 0) return;
+    const int first = __ffs(regMask) - 1;
+    const int nReg = __popc(regMask);
+    const int base = __shfl_sync(0xffffffffu, r0, first);
+    if (regular)
+    {
+#pragma unroll
+        for (int e = 0; e < 7; ++e) stage[(lane - first) * 7 + e] = row[e];
+    }
+    __syncwarp();
+    const int n = nReg * 7 * NC;
+    double* __restrict__ dst = values + size_t(base) * NC;
+    for (int e = lane; e < n; e += 32) dst[e] = stage[NC == 1 ? e : e / 3];
+}
+
 // createEmptyLinearSystem's BoundaryCoefficients index arrays (linearSystem.hpp:163-174):
 // matrixIdxs[b] = celli + diagOffset[celli] (sic), rhsIdxs[b] = celli
 __global__ void __launch_bounds__(256)
@@ -474,6 +640,34 @@ int assemble_impl(const fvk_mesh* m, int nTerms, const fvk_term* terms_h, const 
     {
         const size_t shm = sizeof(double) * 8 * ASM_CAPW * VT::NC;
         const int k0 = terms_h[ft[0]].kind, k1 = nFace == 2 ? terms_h[ft[1]].kind : 0;
+        // block-structured mesh with proven topology: index-free kernel for the regular rows + cell-list pass for the rest
+        static const bool noAffine = [] { const char* e = std::getenv("FVK_ASM_NO_AFFINE"); return e && *e == '1'; }();
+        const FvkBrickGeom& bg = m->bp.geom;
+        if (!noAffine && !fvk_no_affine() && bg.affine && m->bp.nTiles > 0 && int64_t(bg.dims[0]) * bg.dims[1] * bg.dims[2] == m->nOwned && bg.dims[0] >= 3
+            && bg.dims[1] >= 3 && bg.dims[2] >= 3)
+        {
+            constexpr int BY = 4, BZ = 2, TB = AFF_LX * BY * BZ;
+            AsmAffine ag {bg.dims[0], bg.dims[1], bg.dims[2], bg.tUp[0], bg.tUp[1], (bg.dims[0] + AFF_LX - 1) / AFF_LX, (bg.dims[1] + BY - 1) / BY};
+            const int nTilesA = ag.tdx * ag.tdy * ((bg.dims[2] + BZ - 1) / BZ);
+            const int nCo = (nFace == 2 ? 4 : 2);
+            const size_t shmA = sizeof(double) * std::max(size_t(3 * TB + AFF_LX * BY + AFF_LX * BZ + BY * BZ) * nCo, size_t(TB) * 7);
+            const int nTail = m->nCells - m->nOwned, nListed = m->bp.nIrr + nTail;
+#define FVK_ASMA_CASE(a, bb)                                                                                            \
+    if (k0 == a && k1 == bb)                                                                                            \
+    {                                                                                                                   \
+        k_assemble_affine<VT, a, bb, BY, BZ><<<nTilesA, TB, shmA, fvk_cu(s)>>>(T, am, ag, ft[0], ft[1], values, rhs);   \
+        FVK_LAUNCH_CHECK();                                                                                             \
+        if (nListed > 0)                                                                                                \
+            k_assemble_fast<VT, a, bb><<<(nListed + 255) / 256, 256, 0, fvk_cu(s)>>>(T, am, b, ft[0], ft[1], values, rhs, bcMatrix, bcRhs, \
+                                                                                     m->bp.irrCells, m->bp.nIrr, m->nOwned, nTail); \
+        FVK_LAUNCH_CHECK();                                                                                             \
+        return FVK_OK;                                                                                                  \
+    }
+            FVK_ASMA_CASE(FVK_TERM_DIV, 0) FVK_ASMA_CASE(FVK_TERM_LAPLACIAN, 0)
+            FVK_ASMA_CASE(FVK_TERM_DIV, FVK_TERM_LAPLACIAN) FVK_ASMA_CASE(FVK_TERM_LAPLACIAN, FVK_TERM_DIV)
+            FVK_ASMA_CASE(FVK_TERM_DIV, FVK_TERM_DIV) FVK_ASMA_CASE(FVK_TERM_LAPLACIAN, FVK_TERM_LAPLACIAN)
+#undef FVK_ASMA_CASE
+        }
 #define FVK_ASM_CASE(a, bb)                                                                                             \
     if (k0 == a && k1 == bb)                                                                                            \
     {                                                                                                                   \

@@ -9,6 +9,7 @@
 #include "fvk_device.cuh"
 #include "fvk_brickplan.hpp"
 
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -256,10 +257,34 @@ extern "C" int fvk_mesh_destroy(fvk_mesh* m)
     return FVK_OK;
 }
 
+namespace
+{
+// FVK_SETUP_TIMING=1: wall-clock of the phases of fvk_mesh_create to stderr
+struct SetupTimer
+{
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    SetupTimer() : on([] { const char* e = std::getenv("FVK_SETUP_TIMING"); return e && *e == '1'; }()), t0(std::chrono::steady_clock::now()) {}
+    void lap(const char* what)
+    {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[fvk setup] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+bool experiment_plans()
+{
+    static const bool on = [] { const char* e = std::getenv("FVK_EXPERIMENT_PLANS"); return e && *e == '1'; }();
+    return on;
+}
+} // namespace
+
 extern "C" int fvk_mesh_create(const fvk_mesh_desc* d, fvk_mesh** out)
 {
     if (!d || !out) return fvk_fail(FVK_EINVAL, "fvk_mesh_create: null argument");
     *out = nullptr;
+    SetupTimer tm;
     const int32_t nC = d->nCells, nI = d->nInternalFaces, nB = d->nBoundaryFaces;
     if (nC <= 0 || nI < 0 || nB < 0 || d->nPatches < 0 || d->nPatches > FVK_MAX_PATCHES)
         return fvk_fail(FVK_EINVAL, "fvk_mesh_create: bad sizes (nCells=%d nI=%d nB=%d nPatches=%d)",
@@ -274,15 +299,21 @@ extern "C" int fvk_mesh_create(const fvk_mesh_desc* d, fvk_mesh** out)
         int rc = fvk_device_count(&n);
         if (rc || n == 0) return fvk_fail(FVK_ENODEVICE, "fvk_mesh_create: no CUDA device (no CPU fallback)");
     }
-    for (int32_t f = 0; f < nI; ++f)
     {
-        const int32_t o = d->faceOwner[f], n = d->faceNeighbour[f];
-        if (o < 0 || o >= nC || n < 0 || n >= nC || o == n)
-            return fvk_fail(FVK_EINVAL, "fvk_mesh_create: face %d has bad owner/neighbour", f);
+        int32_t badFace = -1, badB = -1;
+#pragma omp parallel for schedule(static) reduction(max : badFace)
+        for (int32_t f = 0; f < nI; ++f)
+        {
+            const int32_t o = d->faceOwner[f], n = d->faceNeighbour[f];
+            if (o < 0 || o >= nC || n < 0 || n >= nC || o == n) badFace = std::max(badFace, f);
+        }
+        if (badFace >= 0) return fvk_fail(FVK_EINVAL, "fvk_mesh_create: face %d has bad owner/neighbour", badFace);
+#pragma omp parallel for schedule(static) reduction(max : badB)
+        for (int32_t b = 0; b < nB; ++b)
+            if (d->faceCells[b] < 0 || d->faceCells[b] >= nC) badB = std::max(badB, b);
+        if (badB >= 0) return fvk_fail(FVK_EINVAL, "fvk_mesh_create: boundary face %d has bad faceCell", badB);
     }
-    for (int32_t b = 0; b < nB; ++b)
-        if (d->faceCells[b] < 0 || d->faceCells[b] >= nC)
-            return fvk_fail(FVK_EINVAL, "fvk_mesh_create: boundary face %d has bad faceCell", b);
+    tm.lap("validate");
 
     fvk_mesh* m = new fvk_mesh;
     m->nCells = nC; m->nInternalFaces = nI; m->nBoundaryFaces = nB; m->nPatches = d->nPatches;
@@ -313,12 +344,14 @@ extern "C" int fvk_mesh_create(const fvk_mesh_desc* d, fvk_mesh** out)
     if (d->bDelta) UP(bDelta, d->bDelta, 3 * size_t(nB));
     if (d->bWeights) UP(bWeights, d->bWeights, nB);
     if (d->bDeltaCoeffs) UP(bDeltaCoeffs, d->bDeltaCoeffs, nB);
+    tm.lap("upload mesh arrays");
 
     // ---- cell->face stencil + gather plan: visiting faces in ascending id appends ascending ids
     const int32_t* own = d->faceOwner;
     const int32_t* nei = d->faceNeighbour;
     FvkStencilHost sth;
     fvk_build_stencil(d, sth);
+    tm.lap("cell->face stencil");
     {
         std::vector<int32_t>&seg = sth.seg, &val = sth.val, &ent = sth.ent, &plan = sth.plan;
         const size_t nEnt = ent.size();
@@ -347,7 +380,10 @@ extern "C" int fvk_mesh_create(const fvk_mesh_desc* d, fvk_mesh** out)
                 bp.nTiles = int32_t(bph.hdr.size()); bp.maxSlots = bph.maxSlots; bp.maxCells = bph.maxCells;
             }
         }
-        // ---- tile plan (see FvkTilePlan): consecutive owned cells, bounded slot / entry counts
+        tm.lap("brick plan + upload");
+        // ---- tile plan (see FvkTilePlan): consecutive owned cells, bounded slot / entry counts. Only the opt-in experiment
+        // kernel (fvk_set_variant 6) reads it: built on request (FVK_EXPERIMENT_PLANS=1; the parity tests set it)
+        if (experiment_plans())
         {
             bool sorted = nI > 0;
             for (int32_t f = 1; f < nI && sorted; ++f) sorted = own[f - 1] <= own[f];
@@ -461,46 +497,59 @@ extern "C" int fvk_mesh_create(const fvk_mesh_desc* d, fvk_mesh** out)
                 }
             }
         }
+        tm.lap("tile plan (experiments)");
         UP(stencilSeg, seg.data(), seg.size());
         UP(stencilVal, val.data(), nEnt);
         UP(gatherEnt, ent.data(), nEnt);
-        UP(gatherPlan, plan.data(), 2 * nEnt);
+        if (experiment_plans()) UP(gatherPlan, plan.data(), 2 * nEnt); // packed-plan gathers (fvk_set_variant 1-4)
+        tm.lap("upload stencil");
     }
-    // ---- sparsity pattern: row = [lower (face order) | diag | upper (face order)]
+    // ---- sparsity pattern: row = [lower (face order) | diag | upper (face order)] (sparsityPattern.cpp:21-143). The
+    // reference's three serial passes over the faces place, in row r, the lower entries in ascending face id, the diagonal,
+    // then the upper entries in ascending face id; built here row by row in parallel from the cell's stencil (sorted by
+    // LOCAL face id, which is what the passes visit -- a decomposed mesh's stencil is ordered by the global key instead).
     {
-        std::vector<int32_t> rowOffs(size_t(nC) + 1, 0), cnt(nC, 0);
-        for (int32_t c = 0; c < nC; ++c) rowOffs[size_t(c) + 1] = 1;
-        for (int32_t f = 0; f < nI; ++f) { ++rowOffs[size_t(own[f]) + 1]; ++rowOffs[size_t(nei[f]) + 1]; }
+        std::vector<int32_t> rowOffs(size_t(nC) + 1, 0);
+        int tooLong = -1;
+#pragma omp parallel for schedule(static) reduction(max : tooLong)
         for (int32_t c = 0; c < nC; ++c)
         {
-            if (rowOffs[size_t(c) + 1] > 255)
-            {
-                fvk_mesh_destroy(m);
-                return fvk_fail(FVK_EUNSUPPORTED, "fvk_mesh_create: cell %d has > 255 row entries (uint8 offsets)", c);
-            }
-            rowOffs[size_t(c) + 1] += rowOffs[c];
+            int32_t n = 1;
+            for (int32_t e = sth.seg[c]; e < sth.seg[size_t(c) + 1]; ++e) n += (sth.ent[e] >> 1) < nI;
+            if (n > 255) tooLong = std::max(tooLong, c);
+            rowOffs[size_t(c) + 1] = n;
         }
+        if (tooLong >= 0)
+        {
+            fvk_mesh_destroy(m);
+            return fvk_fail(FVK_EUNSUPPORTED, "fvk_mesh_create: cell %d has > 255 row entries (uint8 offsets)", tooLong);
+        }
+        for (int32_t c = 0; c < nC; ++c) rowOffs[size_t(c) + 1] += rowOffs[c];
         std::vector<int32_t> col(size_t(m->nnz));
         std::vector<uint8_t> ownOff(nI), neiOff(nI), diagOff(nC);
-        for (int32_t f = 0; f < nI; ++f)
+#pragma omp parallel
         {
-            const int32_t r = nei[f];
-            const int32_t k = cnt[r]++;
-            neiOff[f] = uint8_t(k);
-            col[size_t(rowOffs[r]) + k] = own[f];
-        }
-        for (int32_t c = 0; c < nC; ++c)
-        {
-            const int32_t k = cnt[c]++;
-            diagOff[c] = uint8_t(k);
-            col[size_t(rowOffs[c]) + k] = c;
-        }
-        for (int32_t f = 0; f < nI; ++f)
-        {
-            const int32_t r = own[f];
-            const int32_t k = cnt[r]++;
-            ownOff[f] = uint8_t(k);
-            col[size_t(rowOffs[r]) + k] = nei[f];
+            std::vector<int32_t> lower, upper;
+#pragma omp for schedule(static)
+            for (int32_t c = 0; c < nC; ++c)
+            {
+                lower.clear(); upper.clear();
+                for (int32_t e = sth.seg[c]; e < sth.seg[size_t(c) + 1]; ++e)
+                {
+                    const int32_t f = sth.ent[e] >> 1;
+                    if (f >= nI) continue;
+                    ((sth.ent[e] & 1) ? lower : upper).push_back(f);
+                }
+                std::sort(lower.begin(), lower.end());
+                std::sort(upper.begin(), upper.end());
+                const size_t r0 = size_t(rowOffs[c]);
+                int32_t k = 0;
+                for (int32_t f : lower) { neiOff[f] = uint8_t(k); col[r0 + k] = own[f]; ++k; }
+                diagOff[c] = uint8_t(k);
+                col[r0 + k] = c;
+                ++k;
+                for (int32_t f : upper) { ownOff[f] = uint8_t(k); col[r0 + k] = nei[f]; ++k; }
+            }
         }
         {
             // rows in stencil order? (k_assemble_fast derives slots from stencil positions)
@@ -524,52 +573,13 @@ extern "C" int fvk_mesh_create(const fvk_mesh_desc* d, fvk_mesh** out)
         UP(ownerOffset, ownOff.data(), nI);
         UP(neighbourOffset, neiOff.data(), nI);
         UP(diagOffset, diagOff.data(), nC);
+        tm.lap("sparsity pattern + upload");
     }
-    // ---- split plan for owner-sorted meshes (OpenFOAM upper-triangular face order)
     {
         bool sorted = true;
         for (int32_t f = 1; f < nI && sorted; ++f) sorted = own[f - 1] <= own[f];
         for (int32_t f = 0; f < nI && sorted; ++f) sorted = own[f] < nei[f];
-        m->ownerSorted = sorted;
-        std::vector<int32_t> seg(size_t(nC) + 1, 0);
-        if (sorted)
-        {
-            for (int32_t f = 0; f < nI; ++f) ++seg[size_t(own[f]) + 1];
-            for (int32_t c = 0; c < nC; ++c) seg[size_t(c) + 1] += seg[c];
-            UP(ownStart, seg.data(), seg.size());
-        }
-        std::fill(seg.begin(), seg.end(), 0);
-        for (int32_t f = 0; f < nI; ++f) ++seg[size_t(nei[f]) + 1];
-        for (int32_t c = 0; c < nC; ++c) seg[size_t(c) + 1] += seg[c];
-        std::vector<int32_t> lf(nI), lo(nI), pos(seg.begin(), seg.end() - 1);
-        for (int32_t f = 0; f < nI; ++f)
-        {
-            const int32_t k = pos[nei[f]]++;
-            lf[k] = f; lo[k] = own[f];
-        }
-        UP(lowSeg, seg.data(), seg.size());
-        UP(lowFace, lf.data(), nI);
-        UP(lowOwner, lo.data(), nI);
-        // boundary cells
-        std::vector<int32_t> bcnt(nC, 0);
-        for (int32_t b = 0; b < nB; ++b) ++bcnt[d->faceCells[b]];
-        std::vector<int32_t> bcell, bseg(1, 0);
-        std::vector<uint32_t> mask((size_t(nC) + 31) / 32, 0u);
-        for (int32_t c = 0; c < nC; ++c)
-            if (bcnt[c])
-            {
-                bcell.push_back(c);
-                bseg.push_back(bseg.back() + bcnt[c]);
-                mask[size_t(c) >> 5] |= 1u << (c & 31);
-            }
-        std::vector<int32_t> bface(nB), slot(nC, -1);
-        for (size_t i = 0; i < bcell.size(); ++i) slot[bcell[i]] = bseg[i];
-        for (int32_t b = 0; b < nB; ++b) bface[slot[d->faceCells[b]]++] = nI + b;
-        m->nBndCells = int32_t(bcell.size());
-        UP(bndCell, bcell.data(), bcell.size());
-        UP(bndSeg, bseg.data(), bseg.size());
-        UP(bndFace, bface.data(), nB);
-        UP(hasBnd, mask.data(), mask.size());
+        m->ownerSorted = sorted; // OpenFOAM upper-triangular face order
     }
     // ---- geometry scheme on device
     {
@@ -590,6 +600,7 @@ extern "C" int fvk_mesh_create(const fvk_mesh_desc* d, fvk_mesh** out)
             return fvk_fail(FVK_ECUDA, "fvk_mesh_create: geometry scheme: %s", cudaGetErrorString(e));
         }
     }
+    tm.lap("geometry scheme");
     *out = m;
     return FVK_OK;
 }
