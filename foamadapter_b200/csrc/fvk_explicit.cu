@@ -1013,6 +1013,8 @@ int launch_gather(const fvk_mesh* m, Op op, Scaling sc, double* out, int mode, f
         if (rc >= 0) return rc; // -1: tile does not fit in shared memory -> per-cell gather below
     }
     const int2* plan = reinterpret_cast<const int2*>(m->gatherPlan);
+    if (variant >= 1 && variant <= 4 && !plan)
+        return fvk_fail(FVK_EUNSUPPORTED, "the packed-plan experiment kernels need a mesh created with FVK_EXPERIMENT_PLANS=1");
     cudaStream_t st = fvk_cu(stream);
     switch (variant)
     {

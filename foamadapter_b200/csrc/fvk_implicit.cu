@@ -13,6 +13,7 @@
 #include "fvk_device.cuh"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 namespace
@@ -394,8 +395,8 @@ struct AsmAffine
 };
 constexpr int AFF_LX = 32;
 
-template <class VT, int K0, int K1, int BY, int BZ>
-__global__ void __launch_bounds__(AFF_LX * BY * BZ, 4)
+template <class VT, int K0, int K1, int BY, int BZ, int MINB>
+__global__ void __launch_bounds__(AFF_LX * BY * BZ, MINB)
 k_assemble_affine(Terms terms, AsmMesh m, AsmAffine g, int ft0, int ft1, double* __restrict__ values, double* __restrict__ rhs)
 {
     using T = typename VT::T;
@@ -646,16 +647,27 @@ int assemble_impl(const fvk_mesh* m, int nTerms, const fvk_term* terms_h, const 
         if (!noAffine && !fvk_no_affine() && bg.affine && m->bp.nTiles > 0 && int64_t(bg.dims[0]) * bg.dims[1] * bg.dims[2] == m->nOwned && bg.dims[0] >= 3
             && bg.dims[1] >= 3 && bg.dims[2] >= 3)
         {
-            constexpr int BY = 4, BZ = 2, TB = AFF_LX * BY * BZ;
-            AsmAffine ag {bg.dims[0], bg.dims[1], bg.dims[2], bg.tUp[0], bg.tUp[1], (bg.dims[0] + AFF_LX - 1) / AFF_LX, (bg.dims[1] + BY - 1) / BY};
-            const int nTilesA = ag.tdx * ag.tdy * ((bg.dims[2] + BZ - 1) / BZ);
-            const int nCo = (nFace == 2 ? 4 : 2);
-            const size_t shmA = sizeof(double) * std::max(size_t(3 * TB + AFF_LX * BY + AFF_LX * BZ + BY * BZ) * nCo, size_t(TB) * 7);
+            // brick 32 x BY x BZ and the resident blocks the register allocation aims at; FVK_ASM_TILE="by,bz,minb" selects
+            // another instantiated combination (roofline sweeps)
+            // B200 sweep at 256^3 (profiles/r2c_sweep_asm_256.jsonl): 32x2x2 bricks; the two-face-term scalar kernel wants its
+            // spill-free 6 resident blocks, the lighter ones 8
+            int cfg[3] = {2, 2, (VT::NC == 1 && nFace == 2) ? 6 : 8};
+            if (const char* e = std::getenv("FVK_ASM_TILE")) // read per call: sweeps change it in-process
+            {
+                int a_ = 0, b_ = 0, c_ = 0;
+                if (std::sscanf(e, "%d,%d,%d", &a_, &b_, &c_) == 3) { cfg[0] = a_; cfg[1] = b_; cfg[2] = c_; }
+            }
             const int nTail = m->nCells - m->nOwned, nListed = m->bp.nIrr + nTail;
-#define FVK_ASMA_CASE(a, bb)                                                                                            \
-    if (k0 == a && k1 == bb)                                                                                            \
+#define FVK_ASMA_LAUNCH(a, bb, BY, BZ, MINB)                                                                            \
+    if (cfg[0] == BY && cfg[1] == BZ && cfg[2] == MINB)                                                                 \
     {                                                                                                                   \
-        k_assemble_affine<VT, a, bb, BY, BZ><<<nTilesA, TB, shmA, fvk_cu(s)>>>(T, am, ag, ft[0], ft[1], values, rhs);   \
+        constexpr int TB = AFF_LX * BY * BZ;                                                                            \
+        AsmAffine ag {bg.dims[0], bg.dims[1], bg.dims[2], bg.tUp[0], bg.tUp[1], (bg.dims[0] + AFF_LX - 1) / AFF_LX, (bg.dims[1] + BY - 1) / BY}; \
+        const int nTilesA = ag.tdx * ag.tdy * ((bg.dims[2] + BZ - 1) / BZ);                                             \
+        const size_t shmA = sizeof(double) * std::max(size_t(3 * TB + AFF_LX * BY + AFF_LX * BZ + BY * BZ) * (nFace == 2 ? 4 : 2), size_t(TB) * 7); \
+        if (shmA > 48 * 1024)                                                                                           \
+            FVK_CUDA(cudaFuncSetAttribute(k_assemble_affine<VT, a, bb, BY, BZ, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(shmA))); \
+        k_assemble_affine<VT, a, bb, BY, BZ, MINB><<<nTilesA, TB, shmA, fvk_cu(s)>>>(T, am, ag, ft[0], ft[1], values, rhs); \
         FVK_LAUNCH_CHECK();                                                                                             \
         if (nListed > 0)                                                                                                \
             k_assemble_fast<VT, a, bb><<<(nListed + 255) / 256, 256, 0, fvk_cu(s)>>>(T, am, b, ft[0], ft[1], values, rhs, bcMatrix, bcRhs, \
@@ -663,9 +675,16 @@ int assemble_impl(const fvk_mesh* m, int nTerms, const fvk_term* terms_h, const 
         FVK_LAUNCH_CHECK();                                                                                             \
         return FVK_OK;                                                                                                  \
     }
+#define FVK_ASMA_CASE(a, bb)                                                                                            \
+    if (k0 == a && k1 == bb)                                                                                            \
+    {                                                                                                                   \
+        FVK_ASMA_LAUNCH(a, bb, 4, 2, 4) FVK_ASMA_LAUNCH(a, bb, 4, 2, 3) FVK_ASMA_LAUNCH(a, bb, 2, 2, 8) FVK_ASMA_LAUNCH(a, bb, 2, 2, 6) \
+        FVK_ASMA_LAUNCH(a, bb, 4, 4, 2) FVK_ASMA_LAUNCH(a, bb, 8, 2, 2) FVK_ASMA_LAUNCH(a, bb, 4, 1, 8)                  \
+    }
             FVK_ASMA_CASE(FVK_TERM_DIV, 0) FVK_ASMA_CASE(FVK_TERM_LAPLACIAN, 0)
             FVK_ASMA_CASE(FVK_TERM_DIV, FVK_TERM_LAPLACIAN) FVK_ASMA_CASE(FVK_TERM_LAPLACIAN, FVK_TERM_DIV)
             FVK_ASMA_CASE(FVK_TERM_DIV, FVK_TERM_DIV) FVK_ASMA_CASE(FVK_TERM_LAPLACIAN, FVK_TERM_LAPLACIAN)
+#undef FVK_ASMA_LAUNCH
 #undef FVK_ASMA_CASE
         }
 #define FVK_ASM_CASE(a, bb)                                                                                             \
