@@ -3,11 +3,21 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--mesh 128]
 
-Workload (BASELINE.json configs[1], reference benchmarks/bench_explicitOperators.cpp): one step =
-Gauss-Green div (linear) + grad + laplacian (uncorrected), fp64, on a synthetic N^3 block-hex mesh
-(N=128 by default) with T ~ U(1,2) (seed 42), phi[f] = f on internal faces / 0 on the boundary,
-fixedValue top/bottom + zeroGradient sides. metric = fp64 face-ops/s = 3*(nI+nB) per step.
-Prints ONE JSON line on rank 0.
+Headline workload (BASELINE.json configs[1], reference benchmarks/bench_explicitOperators.cpp): one step = Gauss-Green div
+(linear) + grad + laplacian (uncorrected), fp64, on a synthetic N^3 block-hex mesh per GPU (N = 128) with T ~ U(1,2)
+(seed 42), phi[f] = f on internal faces / 0 on the boundary, fixedValue top/bottom + zeroGradient sides.
+metric = fp64 face-ops/s = 3 (nI + nB) per step. Prints ONE JSON line on rank 0.
+
+The same line carries, at EVERY N, the measurements the other BASELINE configs and the north-star targets are stated on
+(each bounded to a few seconds of GPU time; --no-extras skips them):
+  kernels_256   div / upwind div / grad / laplacian, fused assembly (scalar, Vec3), SpMV (generic, structured) and one
+                Jacobi-CG iteration on the 256^3 mesh (N > 1: on each rank's sub-domain of the decomposed 256^3 mesh), L2
+                flushed between launches, against the measured HBM peak (configs[2], north-star >= 0.70)
+  piso_256      neoIcoFoam PISO step of the 256^3 lid-driven cavity, strong scaling over the N ranks (configs[4])
+  advection_256 scalarAdvection, upwind + forward Euler, 256^3 decomposed over the N ranks (configs[3])
+  parity        outside every timed region: the headline step's outputs bit-compared with the Serial CPU oracle (N = 1,
+                in the cpu_baseline leg) or with a single-domain GPU run of the same global mesh (N > 1); PISO / advection
+                fields of the decomposed run compared with a single-domain run
 """
 from __future__ import annotations
 
@@ -29,6 +39,11 @@ METRIC = "fp64_face_ops_per_s"
 UNIT = "face-ops/s"
 
 
+def workload_name(n):
+    """config.workload: ONE string for both arms and every N (the per-N layout goes to config.parallelism)."""
+    return f"explicit div+grad+laplacian, fp64, {n}^3 block-hex mesh per GPU (BASELINE configs[1])"
+
+
 def mesh_counts(n):
     nC = n ** 3
     nI = 3 * n * n * (n - 1)
@@ -46,6 +61,20 @@ def algorithmic_bytes(n):
     }
 
 
+def alg_bytes_counts(nC, nI, nB):
+    """Algorithmic bytes of every measured kernel for a mesh (or sub-domain) with these counts."""
+    nnz = nC + 2 * nI
+    return {
+        "div": 24 * nI + 24 * nC + 28 * nB, "div_upwind": 16 * nI + 24 * nC + 28 * nB, "grad": 40 * nI + 40 * nC + 44 * nB,
+        "laplacian": 24 * nI + 24 * nC + 28 * nB,
+        "assemble_ddt_div_lap": 50 * nI + 85 * nC + 52 * nB,
+        "assemble_ddt_div_lap_vec3": 50 * nI + (4 + 1 + 8 + 24 + 24 + 7 * 24) * nC + 52 * nB,
+        "spmv": 12 * nnz + 20 * nC, "spmv_structured": 12 * nnz + 20 * nC, "pcg_jacobi_iteration": 12 * nnz + 20 * nC + 72 * nC,
+        # forward-Euler advection step: upwind div + old = T (16) + phi = phi0 * c (16 / face) + CoNum (8 / face + V) + T update
+        "advection_step": (16 + 16 + 8) * nI + (24 + 16 + 8 + 8 + 24) * nC + (28 + 16 + 8) * nB,
+    }
+
+
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -57,7 +86,7 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled every 100 ms DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the step runs (B200_PROFILING.md)."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -68,7 +97,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index),
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
 
@@ -91,34 +120,27 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------
-# CPU arms (the oracle): cpu_baseline leg of the native arm, and --impl reference
+# CPU arms (the oracle): cpu_baseline leg of the native arm, and --impl reference. The mesh comes from the
+# oracle's own generator (oracle/blockmesh.cpp): these legs never load the product library.
 # ----------------------------------------------------------------------------------------------------
-def host_workload(n):
-    from foamadapter_b200.mesh import MeshDesc
-    d = MeshDesc.block(n, n, n, 0.1, 0.1, 0.01)
-    nC, nI, nB = d.nCells, d.nInternalFaces, d.nBoundaryFaces
-    rng = np.random.Generator(np.random.MT19937(42))
-    T = rng.uniform(1.0, 2.0, nC)
-    flux = np.concatenate([np.arange(nI, dtype=np.float64), np.zeros(nB)])
-    return d, T, flux
-
-
-def cpu_step_time(n, d, T, flux, par, reps):
-    """Seconds per step (div+grad+laplacian) of the CPU restatement; best of `reps`."""
+def oracle_workload(n):
     from oracle.cpu import Mesh as OMesh
-    om = OMesh.from_desc(d)
-    off = om.patchOffsets
-    bd = om.correct_bcs([1, 1, 2], [10.5, 1.5, 0.0], T)
-    phib = bd["value"]
-    best = float("inf")
-    for _ in range(reps):
-        r1, r2, r3 = np.zeros(om.nC), np.zeros((om.nC, 3)), np.zeros(om.nC)
-        t0 = time.perf_counter()
-        om.div(flux, T, phib, 0, par=par, res=r1)
-        om.grad(T, phib, par=par, res=r2)
-        om.laplacian(T, phib, par=par, res=r3)
-        best = min(best, time.perf_counter() - t0)
-    return best
+    om = OMesh.block(n, n, n, 0.1, 0.1, 0.01)
+    rng = np.random.Generator(np.random.MT19937(42))
+    T = rng.uniform(1.0, 2.0, om.nC)
+    flux = np.concatenate([np.arange(om.nI, dtype=np.float64), np.zeros(om.nB)])
+    phib = om.correct_bcs([1, 1, 2], [10.5, 1.5, 0.0], T)["value"]
+    return om, T, flux, phib
+
+
+def cpu_step(om, T, flux, phib, par, out=None):
+    r1, r2, r3 = out if out is not None else (np.zeros(om.nC), np.zeros((om.nC, 3)), np.zeros(om.nC))
+    r1[:] = 0; r2[:] = 0; r3[:] = 0
+    t0 = time.perf_counter()
+    om.div(flux, T, phib, 0, par=par, res=r1)
+    om.grad(T, phib, par=par, res=r2)
+    om.laplacian(T, phib, par=par, res=r3)
+    return time.perf_counter() - t0, (r1, r2, r3)
 
 
 def run_reference(args, rank, world):
@@ -126,119 +148,311 @@ def run_reference(args, rank, world):
         return
     from oracle import cpu as ocpu
     n = args.mesh
-    d, T, flux = host_workload(n)
-    nC, nI, nB = d.nCells, d.nInternalFaces, d.nBoundaryFaces
     # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core it can get
     ocpu.lib().fvo_set_threads(C.c_int(len(os.sched_getaffinity(0))))
     cores = ocpu.max_threads()
-    from oracle.cpu import Mesh as OMesh
-    om = OMesh.from_desc(d)
-    phib = om.correct_bcs([1, 1, 2], [10.5, 1.5, 0.0], T)["value"]
-    r1, r2, r3 = np.zeros(nC), np.zeros((nC, 3)), np.zeros(nC)
-
-    def step():
-        r1[:] = 0; r2[:] = 0; r3[:] = 0
-        om.div(flux, T, phib, 0, par=1, res=r1)
-        om.grad(T, phib, par=1, res=r2)
-        om.laplacian(T, phib, par=1, res=r3)
-
-    for _ in range(min(args.warmup, 2)):
-        step()
-    # bounded sample: at most args.steps full steps, and at most ~60 s of CPU work
+    om, T, flux, phib = oracle_workload(n)
+    out = (np.zeros(om.nC), np.zeros((om.nC, 3)), np.zeros(om.nC))
+    for _ in range(args.warmup):
+        cpu_step(om, T, flux, phib, 1, out)
+    # every step is one full n^3 sub-domain's worth of the workload; bounded to ~150 s of CPU work in total
     t0 = time.perf_counter()
     done = 0
-    while done < args.steps and (done == 0 or time.perf_counter() - t0 < 60.0):
-        step()
+    while done < args.steps and (done == 0 or time.perf_counter() - t0 < 150.0):
+        cpu_step(om, T, flux, phib, 1, out)
         done += 1
     dt = (time.perf_counter() - t0) / done
-    value = 3.0 * (nI + nB) / dt
+    value = 3.0 * (om.nI + om.nB) / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
-        "steps_requested": args.steps, "warmup": min(args.warmup, 2), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"explicit div+grad+laplacian, {n}^3 block-hex mesh (BASELINE configs[1])"},
+        "config": {"workload": workload_name(n)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{done} full {n}^3 steps (bounded to ~60 s), OpenMP+atomics restatement of the NeoN CPU executor (oracle/fvo.cpp); "
-                                   "the reference itself needs OpenFOAM/Kokkos/Ginkgo and cannot be built here"},
+                         "sample": f"{done} steps, each one full {n}^3 sub-domain (one GPU's share of the workload) on all {cores} host threads: "
+                                   "OpenMP+atomics restatement of the NeoN CPU executor (oracle/fvo.cpp) on the oracle's own block mesh "
+                                   "(oracle/blockmesh.cpp); the reference itself needs OpenFOAM/Kokkos/Ginkgo and cannot be built here"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if done != args.steps:
+        line["steps_requested"] = args.steps
     print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+# native arm: helpers
+# ----------------------------------------------------------------------------------------------------
+class Ctx:
+    """rank / world / device + the collectives the measurements need (no-ops on one GPU)."""
+
+    def __init__(self, rank, world, local_rank):
+        import torch
+        self.rank, self.world, self.local = rank, world, local_rank
+        self.dev = torch.device("cuda", local_rank)
+
+    def barrier(self):
+        import torch
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max(self, x):
+        import torch
+        t = torch.tensor(np.atleast_1d(np.asarray(x, dtype=np.float64)), device=self.dev)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.cpu().numpy()
+
+    def sum(self, x):
+        import torch
+        t = torch.tensor(np.atleast_1d(np.asarray(x, dtype=np.float64)), device=self.dev)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.cpu().numpy()
+
+    def min_flag(self, ok):
+        return bool(-self.max([0.0 if ok else 1.0])[0] == 0.0)
+
+    def gather_to_root(self, t):
+        """list of every rank's tensor on rank 0 (variable lengths), None elsewhere"""
+        import torch
+        if self.world == 1:
+            return [t]
+        import torch.distributed as dist
+        n = torch.tensor([t.shape[0]], dtype=torch.int64, device=self.dev)
+        ns = [torch.zeros_like(n) for _ in range(self.world)]
+        dist.all_gather(ns, n)
+        m = int(max(int(x.item()) for x in ns))
+        pad = torch.zeros((m,) + tuple(t.shape[1:]), dtype=t.dtype, device=self.dev)
+        pad[: t.shape[0]] = t
+        outs = [torch.empty_like(pad) for _ in range(self.world)] if self.rank == 0 else None
+        dist.gather(pad, outs, dst=0)
+        return [o[: int(k.item())] for o, k in zip(outs, ns)] if self.rank == 0 else None
+
+
+def timed_kernel(fn, reps, flush):
+    """median ms of `fn` over `reps` launches, L2 flushed (write of a buffer > L2) before each, CUDA events on the current stream"""
+    import torch
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for _ in range(2):
+        fn()
+    for a_, b_ in ev:
+        flush.zero_()
+        a_.record(); fn(); b_.record()
+    torch.cuda.synchronize()
+    return float(np.median([a_.elapsed_time(b_) for a_, b_ in ev]))
+
+
+def decomposed(ctx, gdesc, comm_needed=True):
+    """(mesh, dec, comm) of this rank's share of `gdesc` (dec/comm None on one GPU)"""
+    from foamadapter_b200.decomp import Comm, Decomposition, default_split
+    from foamadapter_b200.mesh import UnstructuredMesh
+    if ctx.world == 1:
+        return UnstructuredMesh(gdesc), None, None
+    dec = Decomposition(gdesc, ctx.world, ctx.rank, n=default_split(ctx.world))
+    mesh = UnstructuredMesh(dec.desc)
+    comm = None
+    if comm_needed:
+        comm = Comm.from_torch()
+        comm.set_halo(dec, p2p=os.environ.get("FVK_BENCH_TRANSPORT", "p2p") != "nccl")
+    return mesh, dec, comm
+
+
+def kernels_on(ctx, mesh, comm, peak, reps=5):
+    """Per-kernel roofline on `mesh` (a whole 256^3 mesh, or this rank's sub-domain of one): ms = max over ranks, algorithmic
+    bytes = sum over ranks of the local counts, frac against world x the measured peak."""
+    import torch
+    from foamadapter_b200 import fvcc, la, ops
+    nC, nI, nB = mesh.nOwned, mesh.nInternalFaces, mesh.nBoundaryFaces
+    ab = alg_bytes_counts(nC, nI, nB)
+    rng = np.random.Generator(np.random.MT19937(42 + ctx.rank))
+    bcs = [("fixedValue", 10.5)] + [("zeroGradient", 0.0)] * (mesh.nPatches - 1)
+    T = fvcc.VolumeField(mesh, "T", 1, bcs)
+    T.internal.copy_(torch.from_numpy(rng.uniform(1, 2, mesh.nCells)))
+    T.correctBoundaryConditions()
+    U = fvcc.VolumeField(mesh, "U", 3, [("fixedValue", (1.0, 0.0, 0.0))] + [("noSlip", 0.0)] * (mesh.nPatches - 1))
+    U.internal.copy_(torch.from_numpy(rng.uniform(-1, 1, (mesh.nCells, 3))))
+    U.correctBoundaryConditions()
+    flux = torch.cat([torch.arange(nI, dtype=torch.float64), torch.zeros(nB, dtype=torch.float64)]).to(ctx.dev)
+    gamma = torch.ones(nI + nB, dtype=torch.float64, device=ctx.dev)
+    out = torch.zeros(mesh.nCells, dtype=torch.float64, device=ctx.dev)
+    out3 = torch.zeros((mesh.nCells, 3), dtype=torch.float64, device=ctx.dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=ctx.dev)
+    res = {}
+
+    def rec(name, fn, n=reps):
+        ms = float(ctx.max(timed_kernel(fn, n, flush))[0])
+        by = float(ctx.sum(ab[name])[0])
+        res[name] = {"ms": ms, "algorithmic_bytes": by, "achieved_gbs": by / ms / 1e6, "frac": by / ms / 1e6 / (peak * ctx.world)}
+
+    rec("div", lambda: ops.div(mesh, flux, T.internal, T.boundary.value, out))
+    rec("div_upwind", lambda: ops.div(mesh, flux, T.internal, T.boundary.value, out, scheme=ops.UPWIND))
+    rec("grad", lambda: ops.grad(mesh, T.internal, T.boundary.value, out3))
+    rec("laplacian", lambda: ops.laplacian(mesh, T.internal, T.boundary.value, out))
+    del out3
+    ls = la.LinearSystem(mesh, 1, zero=False)
+    oldS = T.internal - 1.0
+    terms = lambda old: [dict(kind=ops.TERM_DIV, scheme=0, coeff=1.0, faceField=flux), dict(kind=ops.TERM_LAPLACIAN, coeff=-1.0, faceField=gamma),
+                         dict(kind=ops.TERM_DDT, coeff=1.0, cellField=old, dt=1.0)]
+    tS = terms(oldS)
+    rec("assemble_ddt_div_lap", lambda: ops.assemble(mesh, tS, T.boundary, ls.values, ls.rhs, ls.bcMatrix, ls.bcRhs))
+    lsV = la.LinearSystem(mesh, 3, zero=False)
+    tV = terms(U.internal - 1.0)
+    rec("assemble_ddt_div_lap_vec3", lambda: ops.assemble(mesh, tV, U.boundary, lsV.values, lsV.rhs, lsV.bcMatrix, lsV.bcRhs))
+    del lsV, tV
+    sp = la.SparsityPattern.readOrCreate(mesh)
+    x = torch.from_numpy(rng.uniform(-1, 1, mesh.nCells)).to(ctx.dev)
+    y = torch.empty(nC, dtype=torch.float64, device=ctx.dev)
+    rec("spmv", lambda: la.spmv(sp, ls.values, x, y))
+    rec("spmv_structured", lambda: la.spmv_structured(mesh, ls.values, x, y))
+    # one Jacobi-CG iteration: a fixed-length solve of the SPD part (-laplacian + ddt), events around the whole solve
+    ops.assemble(mesh, tS[1:], T.boundary, ls.values, ls.rhs, ls.bcMatrix, ls.bcRhs)
+    iters = 40
+    solver = la.Solver({"solver": "Ginkgo", "type": "solver::Cg", "preconditioner": {"type": "preconditioner::Jacobi", "max_block_size": 1},
+                        "criteria": {"iteration": iters, "relative_residual_norm": 0.0, "absolute_residual_norm": 0.0}}, comm=comm, check_every=iters + 1)
+    xs = torch.zeros(mesh.nCells, dtype=torch.float64, device=ctx.dev)
+    solver.solve(ls, xs)
+    ts = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        xs.zero_(); ctx.barrier()
+        e0.record(); solver.solve(ls, xs); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) / iters)
+    ms = float(ctx.max(float(np.median(ts)))[0])
+    by = float(ctx.sum(ab["pcg_jacobi_iteration"])[0])
+    res["pcg_jacobi_iteration"] = {"ms": ms, "algorithmic_bytes": by, "achieved_gbs": by / ms / 1e6, "frac": by / ms / 1e6 / (peak * ctx.world),
+                                   "note": f"a {iters}-iteration solve / {iters} (start-up kernels included" + ("; halo + all-reduces inside the kernels)" if comm else ")")}
+    solver.close()
+    return res
+
+
+def piso_256(ctx, n, steps, peak):
+    """neoIcoFoam PISO step of the n^3 lid-driven cavity, strong scaling (BASELINE configs[4]); then kernels_256 on the same
+    (sub-)mesh. Parity (N > 1): U and p after the same steps against a single-domain run on rank 0."""
+    import torch
+    from foamadapter_b200 import piso
+    from foamadapter_b200.mesh import UnstructuredMesh
+    t0 = time.perf_counter()
+    g = piso.cavity_desc(n, True)
+    mesh, dec, comm = decomposed(ctx, g)
+    setup_s = time.perf_counter() - t0
+    dt = 1e-4 * 20 / n
+    warm = 3
+    app = piso.IcoFoam(mesh, nu=0.01, dt=dt, comm=comm, check_every=16)
+    for _ in range(warm):
+        app.step()
+    ctx.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms, its = [], []
+    for _ in range(steps):
+        e0.record(); st = app.step(); e1.record(); torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1)); its.append([s.numIter for s in st])
+    ms = ctx.max(ms)
+    out = {"mesh": f"{n}^3 lid-driven cavity, {ctx.world} sub-domain(s)", "steps_timed": steps, "warmup_steps": warm, "ms_per_step": [round(float(x), 4) for x in ms],
+           "median_ms": float(np.median(ms)), "min_ms": float(np.min(ms)), "cg_iterations_per_solve": its, "cuda_graphs": bool(app._captured),
+           "transport": ("peer-memory windows" if (comm and comm.p2p) else ("NCCL" if comm else "none")), "setup_s": round(setup_s, 1),
+           "cells_per_gpu": mesh.nOwned}
+    parity = None
+    if ctx.world > 1:
+        nO = dec.nOwned
+        Us = ctx.gather_to_root(app.U.internal[:nO].contiguous())
+        ps = ctx.gather_to_root(app.p.internal[:nO].contiguous())
+        gids = ctx.gather_to_root(torch.from_numpy(dec.cellGlobal[:nO].astype(np.int64)).to(ctx.dev))
+        if ctx.rank == 0:
+            ref = piso.IcoFoam(UnstructuredMesh(g), nu=0.01, dt=dt, check_every=16)
+            rits = []
+            for _ in range(warm + steps):
+                rits.append([s.numIter for s in ref.step()])
+            Ug, pg = torch.empty_like(ref.U.internal), torch.empty_like(ref.p.internal)
+            for u_, p_, gi in zip(Us, ps, gids):
+                Ug[gi] = u_; pg[gi] = p_
+            eU = float((Ug - ref.U.internal).abs().max() / ref.U.internal.abs().max())
+            ep = float((pg - ref.p.internal).abs().max() / ref.p.internal.abs().max())
+            dit = max(abs(a - b) for x, y in zip(its, rits[warm:]) for a, b in zip(x, y))
+            parity = {"vs": "single-domain GPU run of the same cavity on rank 0", "steps": warm + steps, "U_rel_max": eU, "p_rel_max": ep,
+                      "cg_iteration_count_max_diff": int(dit), "ok": bool(eU <= 1e-7 and ep <= 1e-6 and dit <= 2)}
+            del ref, Ug, pg
+        del Us, ps, gids
+    del app
+    torch.cuda.empty_cache()
+    kern = kernels_on(ctx, mesh, comm, peak)
+    if comm is not None:
+        ctx.barrier()
+        comm.close()
+    return out, kern, parity
+
+
+def advection_256(ctx, n, steps, peak):
+    """scalarAdvection (BASELINE configs[3]): upwind + forward Euler on the n^3 unit cube decomposed over the ranks."""
+    import torch
+    from foamadapter_b200 import advection as adv
+    from foamadapter_b200 import mesh as M
+    from foamadapter_b200.mesh import UnstructuredMesh
+    t0 = time.perf_counter()
+    g = adv.advection_desc(n, True)
+    mesh, dec, comm = decomposed(ctx, g)
+    C_l = mesh.to_host(M.CELL_CENTRES).reshape(-1, 3)
+    # the fields depend on (x, y) only: evaluate the distinct columns once (host libm, like the reference's createFields.H)
+    key = np.round(C_l[:, :2] * (4.0 * n)).astype(np.int64)
+    uniq, inv = np.unique(key[:, 0] * (8 * n) + key[:, 1], return_inverse=True)
+    first = np.zeros(len(uniq), dtype=np.int64)
+    first[inv[::-1]] = np.arange(len(inv))[::-1]
+    U0, T0 = adv.init_fields(C_l[first])
+    U_l, T_l = U0[inv], T0[inv]
+    setup_s = time.perf_counter() - t0
+    dtv, endTime = 0.1 / n, 3.0   # CFL ~ 0.1 like the tutorial's maxCo
+    app = adv.ScalarAdvection(mesh, dtv, endTime, comm=comm, U=U_l, T=T_l)
+    warm = 3
+    for _ in range(warm):
+        app.step()
+    ctx.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        app.step()
+    e1.record(); ctx.barrier()
+    ms = float(ctx.max(e0.elapsed_time(e1) / steps)[0])
+    by = float(ctx.sum(alg_bytes_counts(mesh.nOwned, mesh.nInternalFaces, mesh.nBoundaryFaces)["advection_step"])[0])
+    co = app.coNum.clone()
+    if comm is not None:
+        comm.allreduce_max(co[:1])
+    out = {"mesh": f"{n}^3 unit cube, {ctx.world} sub-domain(s)", "scheme": "Gauss upwind, forwardEuler", "steps_timed": steps, "warmup_steps": warm, "ms_per_step": ms,
+           "face_updates_per_s": float(ctx.sum(mesh.nFaces)[0]) / (ms * 1e-3), "algorithmic_bytes": by, "achieved_gbs": by / ms / 1e6,
+           "frac": by / ms / 1e6 / (peak * ctx.world), "max_courant": float(co[0].item()), "setup_s": round(setup_s, 1), "cells_per_gpu": mesh.nOwned,
+           "transport": ("peer-memory windows" if (comm and comm.p2p) else ("NCCL" if comm else "none"))}
+    parity = None
+    if ctx.world > 1:
+        nO = dec.nOwned
+        Ts = ctx.gather_to_root(app.T.internal[:nO].contiguous())
+        gids = ctx.gather_to_root(torch.from_numpy(dec.cellGlobal[:nO].astype(np.int64)).to(ctx.dev))
+        Ug = ctx.gather_to_root(torch.from_numpy(np.ascontiguousarray(U_l[:nO])).to(ctx.dev))
+        Tg0 = ctx.gather_to_root(torch.from_numpy(np.ascontiguousarray(T_l[:nO])).to(ctx.dev))
+        if ctx.rank == 0:
+            gm = UnstructuredMesh(g)
+            Uall = torch.empty((gm.nCells, 3), dtype=torch.float64, device=ctx.dev)
+            Tall0, Tall = torch.empty(gm.nCells, dtype=torch.float64, device=ctx.dev), torch.empty(gm.nCells, dtype=torch.float64, device=ctx.dev)
+            for u_, t0_, t_, gi in zip(Ug, Tg0, Ts, gids):
+                Uall[gi] = u_; Tall0[gi] = t0_; Tall[gi] = t_
+            ref = adv.ScalarAdvection(gm, dtv, endTime, U=Uall.cpu().numpy(), T=Tall0.cpu().numpy())
+            for _ in range(warm + steps):
+                ref.step()
+            same = bool(torch.equal(Tall, ref.T.internal))
+            parity = {"vs": "single-domain GPU run of the same case on rank 0", "steps": warm + steps, "T_bit_identical": same,
+                      "T_rel_max": float((Tall - ref.T.internal).abs().max() / ref.T.internal.abs().max()), "ok": same}
+            del ref, gm, Uall, Tall, Tall0
+        del Ts, gids, Ug, Tg0
+    if comm is not None:
+        ctx.barrier()
+        comm.close()
+    return out, parity
 
 
 # ----------------------------------------------------------------------------------------------------
 # native arm
 # ----------------------------------------------------------------------------------------------------
-def solver_path_extras(n, peak):
-    """Secondary measurements of the implicit / solver part of the hot path on the same N^3 mesh (reported under
-    "solver_path", not part of `value`): fused ddt+div+laplacian assembly, CSR SpMV, Jacobi-CG iteration, and one PISO
-    step of the 3-D lid-driven cavity at 64^3. CUDA events / wall clock around synchronised solves."""
-    import torch
-    from foamadapter_b200 import fvcc, la, ops, piso
-    from foamadapter_b200.mesh import MeshDesc, UnstructuredMesh
-    out = {}
-    gm = UnstructuredMesh(MeshDesc.block(n, n, n, 0.1, 0.1, 0.01))
-    nC, nI, nB = mesh_counts(n)
-    nnz = nC + 2 * nI
-    rng = np.random.Generator(np.random.MT19937(42))
-    T = fvcc.VolumeField(gm, "T", 1, [("fixedValue", 10.5), ("fixedValue", 1.5), ("zeroGradient", 0.0)])
-    T.internal.copy_(torch.from_numpy(rng.uniform(1, 2, nC)))
-    T.correctBoundaryConditions()
-    flux = torch.cat([torch.arange(nI, dtype=torch.float64), torch.zeros(nB, dtype=torch.float64)]).cuda()
-    gamma = torch.ones(nI + nB, dtype=torch.float64, device="cuda")
-    old = T.internal - 1.0
-    ls = la.LinearSystem(gm, 1, zero=False)
-    terms = [dict(kind=ops.TERM_DIV, scheme=0, coeff=1.0, faceField=flux), dict(kind=ops.TERM_LAPLACIAN, coeff=-1.0, faceField=gamma),
-             dict(kind=ops.TERM_DDT, coeff=1.0, cellField=old, dt=1.0)]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-
-    def timed(fn, reps=10):
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
-        for _ in range(3):
-            fn()
-        for a_, b_ in ev:
-            flush.zero_()
-            a_.record(); fn(); b_.record()
-        torch.cuda.synchronize()
-        return float(np.median([a_.elapsed_time(b_) for a_, b_ in ev]))
-
-    ms = timed(lambda: ops.assemble(gm, terms, T.boundary, ls.values, ls.rhs, ls.bcMatrix, ls.bcRhs))
-    by = 50 * nI + 85 * nC + 52 * nB
-    out["assemble_ddt_div_lap"] = {"ms": ms, "algorithmic_bytes": by, "achieved_gbs": by / ms / 1e6, "frac": by / ms / 1e6 / peak}
-    sp = la.SparsityPattern.readOrCreate(gm)
-    x = torch.from_numpy(rng.uniform(-1, 1, nC)).cuda()
-    y = torch.empty_like(x)
-    ms = timed(lambda: la.spmv(sp, ls.values, x, y))
-    by = nnz * 12 + nC * 20
-    out["spmv"] = {"ms": ms, "algorithmic_bytes": by, "achieved_gbs": by / ms / 1e6, "frac": by / ms / 1e6 / peak}
-    ms = timed(lambda: la.spmv_structured(gm, ls.values, x, y))
-    out["spmv_structured"] = {"ms": ms, "algorithmic_bytes": by, "achieved_gbs": by / ms / 1e6, "frac": by / ms / 1e6 / peak}
-    ops.assemble(gm, [terms[1], terms[2]], T.boundary, ls.values, ls.rhs, ls.bcMatrix, ls.bcRhs)
-    iters = 50
-    solver = la.Solver({"solver": "Ginkgo", "type": "solver::Cg", "preconditioner": {"type": "preconditioner::Jacobi", "max_block_size": 1},
-                        "criteria": {"iteration": iters, "relative_residual_norm": 0.0, "absolute_residual_norm": 0.0}}, check_every=iters + 1)
-    xs = torch.zeros(nC, dtype=torch.float64, device="cuda")
-    solver.solve(ls, xs)
-    ts = []
-    for _ in range(3):
-        xs.zero_(); torch.cuda.synchronize()
-        t0 = time.perf_counter(); solver.solve(ls, xs); torch.cuda.synchronize()
-        ts.append((time.perf_counter() - t0) * 1e3 / iters)
-    ms = float(np.median(ts)); by = nnz * 12 + nC * 20 + 72 * nC
-    out["pcg_jacobi_iteration"] = {"ms": ms, "algorithmic_bytes": by, "achieved_gbs": by / ms / 1e6, "frac": by / ms / 1e6 / peak}
-    del gm, ls, T, solver
-    gmc = UnstructuredMesh(piso.cavity_desc(64, True))
-    app = piso.IcoFoam(gmc, nu=0.01, dt=1e-4 * 20 / 64, check_every=16)
-    for _ in range(2):
-        app.step()
-    torch.cuda.synchronize()
-    ts, its = [], []
-    for _ in range(5):
-        t0 = time.perf_counter(); st = app.step(); torch.cuda.synchronize()
-        ts.append((time.perf_counter() - t0) * 1e3); its.append(sum(s_.numIter for s_ in st))
-    out["piso_step_cavity3d_64"] = {"ms": float(np.median(ts)), "cg_iterations_per_step": its}
-    return out
-
-
 def run_native(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -253,26 +467,27 @@ def run_native(args, rank, world, local_rank):
     from foamadapter_b200.decomp import Comm, Decomposition, default_split
     from foamadapter_b200.mesh import MeshDesc, UnstructuredMesh
 
+    ctx = Ctx(rank, world, local_rank)
     n = args.mesh
-    dev = torch.device("cuda", local_rank)
-    comm, dec = None, None
+    dev = ctx.dev
+    comm, dec, G = None, None, None
+    rng = np.random.Generator(np.random.MT19937(42))
     if world == 1:
-        d, T_h, flux_h = host_workload(n)
+        d = MeshDesc.block(n, n, n, 0.1, 0.1, 0.01)
+        T_h = rng.uniform(1.0, 2.0, d.nCells)
+        flux_h = np.concatenate([np.arange(d.nInternalFaces, dtype=np.float64), np.zeros(d.nBoundaryFaces)])
         nF_global = d.nInternalFaces + d.nBoundaryFaces
-        phib_sel = None
     else:
         # weak scaling: every rank owns an n^3 block of the (n px, n py, n pz) mesh; same cell size as the 1-GPU case
         px, py, pz = default_split(world)
         G = MeshDesc.block(n * px, n * py, n * pz, 0.1 * px, 0.1 * py, 0.01 * pz)
         nF_global = G.nInternalFaces + G.nBoundaryFaces
-        rng = np.random.Generator(np.random.MT19937(42))
         Tg = rng.uniform(1.0, 2.0, G.nCells)
         dec = Decomposition(G, world, rank, n=(px, py, pz))
         d = dec.desc
         T_h = np.ascontiguousarray(Tg[dec.cellGlobal])
         fg = dec.faceGlobal.astype(np.float64)
         flux_h = np.where(dec.faceGlobal < G.nInternalFaces, fg, 0.0)  # phi[f] = global face id, 0 on the boundary
-        del Tg, G
         comm = Comm.from_torch()
     nC, nI, nB = d.nCells, d.nInternalFaces, d.nBoundaryFaces
     mesh = UnstructuredMesh(d)
@@ -309,6 +524,7 @@ def run_native(args, rank, world, local_rank):
     calls = ((L.fvk_div_s, a_div), (L.fvk_grad_s, a_grad), (L.fvk_laplacian_s, a_lap))
     cs = C.c_void_p(comm_stream.cuda_stream) if comm is not None else None
     calls_cs = tuple((fn, a[:-1] + (cs,)) for fn, a in calls)  # the same operator calls on the communication stream
+    launches = [0]
 
     def step(ev=None):
         rc = 0
@@ -317,6 +533,7 @@ def run_native(args, rank, world, local_rank):
                 if ev is not None:
                     ev[i].record(stream)
                 rc |= fn(*a)
+            launches[0] += 3
         else:
             # multi-GPU: the processor-boundary exchange of each operator's input field is part of the step.
             # Communication stream: exchange field i, then the operator's HALO phase (the boundary / cut-layer cells, which
@@ -337,40 +554,80 @@ def run_native(args, rank, world, local_rank):
                 rc |= fn(*a)
             mesh.set_tile_phase(0)
             stream.wait_event(ev_comm)
+            launches[0] += 12
         if ev is not None:
             ev[3].record(stream)
         if rc:
             raise RuntimeError(L.fvk_last_error().decode())
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     for _ in range(max(args.warmup, 3)):
         step()
-    barrier()
+    ctx.barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    ctx.barrier()
+    launches[0] = 0
     e_start.record(stream)
     for k in range(args.steps):
         step(evs[k])
     e_end.record(stream)
-    barrier()
-    total_ms = e_start.elapsed_time(e_end)
-    clocks = sampler.summary() if rank == 0 else None
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
+    ctx.barrier()
+    timed_launches = launches[0]
+    total_ms = float(ctx.max(e_start.elapsed_time(e_end))[0])
     ms_per_step = total_ms / args.steps
     value = 3.0 * nF_global / (ms_per_step * 1e-3)
     kern_ms = {name: float(np.mean([evs[k][i].elapsed_time(evs[k][i + 1]) for k in range(args.steps)]))
                for i, name in enumerate(("div", "grad", "laplacian"))}
+    # clock sampling: the timed region is milliseconds long at the driver's --steps, so the SAME step keeps running
+    # (untimed) until the 50 ms poller has seen >= 1.2 s of it
+    if rank == 0:
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < 1.2 and world == 1:
+            for _ in range(200):
+                step()
+            torch.cuda.synchronize()
+    if world > 1:
+        t0 = time.perf_counter()
+        flag = torch.zeros(1, device=dev)
+        while True:  # every rank runs the same number of extra steps (the exchange is collective)
+            for _ in range(100):
+                step()
+            flag.fill_(1.0 if time.perf_counter() - t0 < 1.2 else 0.0)
+            dist.broadcast(flag, 0)
+            if float(flag.item()) == 0.0:
+                break
+        torch.cuda.synchronize()
+    clocks = sampler.summary() if rank == 0 else None
+    parity = {}
+
+    # ---- parity of the headline step, outside the timed region -------------------------------------------
+    if world > 1:
+        nO = dec.nOwned
+        parts = [ctx.gather_to_root(t[:nO].contiguous()) for t in (out_div, out_grad, out_lap)]
+        gids = ctx.gather_to_root(torch.from_numpy(dec.cellGlobal[:nO].astype(np.int64)).to(dev))
+        if rank == 0:
+            gm = UnstructuredMesh(G)
+            Tg_d = torch.from_numpy(Tg).to(dev)
+            fT = fvcc.VolumeField(gm, "T", 1, bcs, device=dev)
+            fT.internal.copy_(Tg_d); fT.correctBoundaryConditions()
+            fl = torch.cat([torch.arange(G.nInternalFaces, dtype=torch.float64), torch.zeros(G.nBoundaryFaces, dtype=torch.float64)]).to(dev)
+            r_d = ops.div(gm, fl, fT.internal, fT.boundary.value, torch.zeros(G.nCells, dtype=torch.float64, device=dev))
+            r_g = ops.grad(gm, fT.internal, fT.boundary.value, torch.zeros((G.nCells, 3), dtype=torch.float64, device=dev))
+            r_l = ops.laplacian(gm, fT.internal, fT.boundary.value, torch.zeros(G.nCells, dtype=torch.float64, device=dev))
+            ok = True
+            for ref, part in zip((r_d, r_g, r_l), parts):
+                got = torch.empty_like(ref)
+                for p_, gi in zip(part, gids):
+                    got[gi] = p_
+                ok = ok and bool(torch.equal(got, ref))
+            parity["explicit_step"] = {"vs": f"single-domain GPU run of the global {'x'.join(str(n * q) for q in default_split(world))} mesh on rank 0",
+                                       "bit_identical": ok, "ok": ok}
+            del gm, fT, fl, r_d, r_g, r_l, Tg_d
+        del parts, gids
+        del Tg
 
     # ---- e2e: host (pinned) buffers in, results out, every step ---------------------------------
     pin = lambda a: torch.from_numpy(a).pin_memory()
@@ -411,8 +668,8 @@ def run_native(args, rank, world, local_rank):
                 a_lap=(mesh.handle, ptr(f.internal), ptr(f.boundary.value), one, None, ptr(ol), C.c_int(0), s),
                 in_ready=torch.cuda.Event(), comp_done=torch.cuda.Event(), out_copied=torch.cuda.Event()))
 
-        def run(n):
-            for k in range(n):
+        def run(nsteps):
+            for k in range(nsteps):
                 B = bufs[k % 2]
                 with torch.cuda.stream(s_in):
                     if k >= 2:
@@ -437,7 +694,7 @@ def run_native(args, rank, world, local_rank):
                     r_grad.copy_(B["outs"][1], non_blocking=True)
                     r_lap.copy_(B["outs"][2], non_blocking=True)
                     B["out_copied"].record(s_out)
-            for b in range(min(n, 2)):
+            for b in range(min(nsteps, 2)):
                 stream.wait_event(bufs[b]["out_copied"])  # the timed region ends when the last results are on the host
         return run, bufs
 
@@ -445,99 +702,110 @@ def run_native(args, rank, world, local_rank):
 
     def measure(run):
         run(2)
-        barrier()
+        ctx.barrier()
         e_start.record(stream)
         run(e2e_steps)
         e_end.record(stream)
-        barrier()
-        tt = torch.tensor([e_start.elapsed_time(e_end)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return tt
+        ctx.barrier()
+        return float(ctx.max(e_start.elapsed_time(e_end))[0])
 
-    def sequential(n):
-        for _ in range(n):
+    def sequential(nsteps):
+        for _ in range(nsteps):
             e2e_step()
 
     t = measure(sequential)
     e2e_mode = "sequential copies and operators on one stream"
     ref_host = (r_div.clone(), r_grad.clone(), r_lap.clone())
     try:
-        if world > 1:
-            raise RuntimeError("multi-GPU arm keeps the sequential e2e step")
         run_p, bufs = make_pipeline()
         t_p = measure(run_p)
         torch.cuda.synchronize()
         same = all(torch.equal(a, b) for a, b in zip(ref_host, (r_div, r_grad, r_lap))) and all(
             torch.equal(x, y) for x, y in zip(bufs[0]["outs"], bufs[1]["outs"]))
-        flag = torch.tensor([1 if same else 0], dtype=torch.int32, device=dev)
-        if world > 1:
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if int(flag.item()) == 1 and float(t_p.item()) < float(t.item()):
+        same = ctx.min_flag(same)
+        if same and t_p < t:
             t, e2e_mode = t_p, "double-buffered: H2D / operators / D2H of consecutive steps overlap on three streams (results verified on the host)"
-        elif int(flag.item()) != 1:
+        elif not same:
             print("bench.py: pipelined e2e results differ from the sequential path; reporting the sequential number", file=sys.stderr)
         del bufs
     except Exception as exc:  # the sequential measurement stands
-        if world == 1:
-            print(f"bench.py: pipelined e2e not available ({exc!r}); reporting the sequential number", file=sys.stderr)
-    e2e_ms = float(t.item()) / e2e_steps
+        print(f"bench.py: pipelined e2e not available ({exc!r}); reporting the sequential number", file=sys.stderr)
+    e2e_ms = t / e2e_steps
     e2e_value = 3.0 * nF_global / (e2e_ms * 1e-3)
 
+    peak, peak_kind = peaks()
+    line = None
     if rank == 0:
-        peak, peak_kind = peaks()
         ab = algorithmic_bytes(n)
         kernels = {k: {"ms": kern_ms[k], "algorithmic_bytes": ab[k], "achieved_gbs": ab[k] / (kern_ms[k] * 1e-3) / 1e9,
                        "frac": ab[k] / (kern_ms[k] * 1e-3) / 1e9 / peak} for k in kern_ms}
         dom = max(kern_ms, key=kern_ms.get)
-        traffic = None
-        tp = ROOT / "profiles" / "traffic.json"
-        if tp.exists():
-            try:
-                traffic = json.loads(tp.read_text()).get(f"{dom}_{n}")
-            except Exception:
-                traffic = None
-        halo_note = "" if world == 1 else (f"; {world} sub-domains ({'x'.join(map(str, default_split(world)))}) of one "
-                                           f"{'x'.join(str(n * q) for q in default_split(world))} mesh, halo exchange ({transport}) of each "
-                                           "operator's input inside the step on a second stream (followed there by the operator's halo phase), overlapped with the cells that read no ghost cell")
+        split = "x".join(map(str, default_split(world)))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"explicit div+grad+laplacian, {n}^3 block-hex mesh per GPU (BASELINE configs[1])" + halo_note,
+            "config": {"workload": workload_name(n),
                        "cells_per_gpu": mesh.nOwned, "internal_faces_per_gpu": nI, "boundary_faces_per_gpu": nB, "faces_global": nF_global,
-                       "l2": "inputs larger than L2: each operator streams 203/338/203 MB (>126 MB L2) and reads its own phi array",
-                       "parallelism": "1 GPU" if world == 1 else f"domain decomposition, {world} ranks, ghost cells + {transport}"},
+                       "l2": "inputs larger than L2: each operator streams 203/338/203 MB (>126 MB L2) and reads its own phi array; the kernels_256 "
+                             "section flushes L2 (256 MB write) before every launch",
+                       "parallelism": "1 GPU" if world == 1 else
+                       f"domain decomposition, {world} ranks ({split}) of one {'x'.join(str(n * q) for q in default_split(world))} mesh, ghost cells + {transport}; the "
+                       "exchange of each operator's input runs on a second stream (followed there by the operator's halo phase) beside the cells that read no ghost cell"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                         "frac": kernels[dom]["frac"], "traffic": traffic, "peak_kind": peak_kind},
+                         "frac": kernels[dom]["frac"], "traffic": None, "peak_kind": peak_kind,
+                         "traffic_note": "not measured in this run; ncu dram bytes per launch are committed in profiles/traffic.json and profiles/r2*_ncu_*.csv"},
             "kernels": kernels,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "mode": e2e_mode},
-            "gpu_launches": (3 if world == 1 else 12) * args.steps,
+            "gpu_launches": timed_launches,
             "clocks": clocks,
         }
-        if world == 1 and not args.no_cpu:
-            from oracle import cpu as ocpu
-            ocpu.lib().fvo_set_threads(C.c_int(len(os.sched_getaffinity(0))))
-            cores = ocpu.max_threads()
-            t_par = cpu_step_time(n, d, T_h, flux_h, par=1, reps=3)
-            t_ser = cpu_step_time(n, d, T_h, flux_h, par=0, reps=1)
-            line["cpu_baseline"] = {
-                "value": 3.0 * nF_global / t_par, "unit": UNIT, "cores": cores, "kind": "port",
-                "sample": f"full {n}^3 step (div+grad+laplacian), best of 3, OpenMP+atomics restatement of the NeoN CPU "
-                          f"executor on {cores} threads; Serial executor restatement on 1 core: {3.0 * nF_global / t_ser:.4g} {UNIT}",
-                "serial_value": 3.0 * nF_global / t_ser,
-            }
-        if world == 1 and not args.no_extras:
-            del fields, flux, out_div, out_grad, out_lap, mesh
-            torch.cuda.empty_cache()
-            try:
-                line["solver_path"] = solver_path_extras(n, peak)
-            except Exception as e:  # secondary numbers must never cost the headline line
-                line["solver_path"] = {"error": repr(e)}
-        print(json.dumps(line), flush=True)
+    if world == 1 and not args.no_cpu:
+        from oracle import cpu as ocpu
+        ocpu.lib().fvo_set_threads(C.c_int(len(os.sched_getaffinity(0))))
+        cores = ocpu.max_threads()
+        om, oT, oflux, ophib = oracle_workload(n)
+        t_par = min(cpu_step(om, oT, oflux, ophib, 1)[0] for _ in range(3))
+        t_ser, ref = cpu_step(om, oT, oflux, ophib, 0)
+        line["cpu_baseline"] = {
+            "value": 3.0 * nF_global / t_par, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"full {n}^3 step (div+grad+laplacian), best of 3, OpenMP+atomics restatement of the NeoN CPU "
+                      f"executor on {cores} threads; Serial executor restatement on 1 core: {3.0 * nF_global / t_ser:.4g} {UNIT}",
+            "serial_value": 3.0 * nF_global / t_ser,
+        }
+        step(); torch.cuda.synchronize()
+        ok = all(np.array_equal(a.cpu().numpy(), b) for a, b in zip((out_div, out_grad, out_lap), ref))
+        parity["explicit_step"] = {"vs": "Serial CPU oracle on the oracle's own mesh (cpu_baseline leg)", "bit_identical": bool(ok), "ok": bool(ok)}
+        del om, ref
+    # ---- the other BASELINE configs, at every N -----------------------------------------------------------
+    del fields, flux, out_div, out_grad, out_lap, mesh, f0
     if comm is not None:
-        barrier()
+        ctx.barrier()
         comm.close()
+    torch.cuda.empty_cache()
+    if not args.no_extras:
+        extras = {}
+        try:
+            p_out, k_out, p_par = piso_256(ctx, args.big, args.piso_steps, peak)
+            extras["piso_256"], extras["kernels_256"] = p_out, k_out
+            if p_par is not None:
+                parity["piso_256"] = p_par
+        except Exception as e:  # secondary numbers must never cost the headline line
+            extras["piso_256"] = {"error": repr(e)}
+        torch.cuda.empty_cache()
+        try:
+            a_out, a_par = advection_256(ctx, args.big, args.advection_steps, peak)
+            extras["advection_256"] = a_out
+            if a_par is not None:
+                parity["advection_256"] = a_par
+        except Exception as e:
+            extras["advection_256"] = {"error": repr(e)}
+        if rank == 0:
+            line.update(extras)
+    if rank == 0:
+        parity["ok"] = all(v.get("ok", False) for v in parity.values() if isinstance(v, dict)) if parity else None
+        line["parity"] = parity
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -549,12 +817,18 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--mesh", type=int, default=128)
+    ap.add_argument("--big", type=int, default=256, help="edge of the mesh of the kernels_256 / piso_256 / advection_256 sections")
+    ap.add_argument("--piso-steps", type=int, default=6)
+    ap.add_argument("--advection-steps", type=int, default=50)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-extras", action="store_true", help="skip the solver_path secondary measurements")
+    ap.add_argument("--no-extras", action="store_true", help="skip the kernels_256 / piso_256 / advection_256 sections")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and args.impl == "native":
+        # torchrun exports OMP_NUM_THREADS=1: the host-side mesh generator / decomposition of each rank get their share of the cores
+        os.environ["OMP_NUM_THREADS"] = str(max(1, len(os.sched_getaffinity(0)) // world))
     # stdout carries exactly ONE JSON line: everything native libraries print while we run (e.g. NCCL's version banner)
     # goes to stderr; the real stdout is restored just for the final print
     sys.stdout.flush()

@@ -18,7 +18,7 @@ _LIB = None
 
 def build(force: bool = False) -> Path:
     so = HERE / "libfvo.so"
-    if force or not so.exists() or so.stat().st_mtime < (HERE / "fvo.cpp").stat().st_mtime:
+    if force or not so.exists() or so.stat().st_mtime < max((HERE / f).stat().st_mtime for f in ("fvo.cpp", "blockmesh.cpp", "Makefile")):
         subprocess.run(["make", "-C", str(HERE), "-B" if force else "-s"], check=True, capture_output=True)
     return so
 
@@ -97,6 +97,28 @@ class Mesh:
         self.diagOffset = np.zeros(self.nC, np.uint8)
         call("fvo_sparsity", self.nC, self.nI, self.owner, self.neighbour, self.rowOffs, self.colIdxs,
              self.ownerOffset, self.neighbourOffset, self.diagOffset)
+
+    # block sides: 0 x-min, 1 x-max, 2 y-min, 3 y-max, 4 z-min, 5 z-max; patches = [(name, [sides], isEmpty)]
+    PATCHES_3DCUBE = [("top", [3], False), ("bottom", [2], False), ("sides", [0, 1, 4, 5], False)]
+
+    @classmethod
+    def block(cls, nx, ny, nz, lx=1.0, ly=1.0, lz=1.0, patches=None):
+        """Single hex block in blockMesh ordering with primitiveMesh geometry (oracle/blockmesh.cpp): the oracle's own
+        mesh generator, so the CPU arms of bench.py never load the product library."""
+        patches = patches or cls.PATCHES_3DCUBE
+        nSides = i32([len(p[1]) for p in patches])
+        sides = i32([s for p in patches for s in p[1]])
+        empty = i32([1 if p[2] else 0 for p in patches])
+        sz = np.zeros(4, np.int64)
+        call("fvo_blockmesh_sizes", nx, ny, nz, len(patches), nSides, sides, empty, sz)
+        nC, nI, nB, kept = (int(v) for v in sz)
+        a = dict(owner=np.zeros(nI + nB, np.int32), neighbour=np.zeros(nI, np.int32), faceCells=np.zeros(nB, np.int32),
+                 V=np.zeros(nC), C=np.zeros(nC * 3), Sf=np.zeros((nI + nB) * 3), Cf=np.zeros((nI + nB) * 3), magSf=np.zeros(nI + nB),
+                 bSf=np.zeros(nB * 3), bDeltaCoeffs=np.zeros(nB), bWeights=np.zeros(nB), patchOffsets=np.zeros(kept + 1, np.int32))
+        lib().fvo_blockmesh(C.c_int32(nx), C.c_int32(ny), C.c_int32(nz), C.c_double(lx), C.c_double(ly), C.c_double(lz),
+                            C.c_int32(len(patches)), _arg(nSides), _arg(sides), _arg(empty), *[_arg(a[k]) for k in
+                            ("owner", "neighbour", "faceCells", "V", "C", "Sf", "Cf", "magSf", "bSf", "bDeltaCoeffs", "bWeights", "patchOffsets")])
+        return cls(nCells=nC, **a)
 
     @classmethod
     def from_desc(cls, d):

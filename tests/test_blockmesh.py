@@ -57,3 +57,24 @@ def test_rejects_bad_patch_spec():
         MeshDesc.block(2, 2, 2, patches=[("a", [0, 1, 2, 3, 4], False)])  # side 5 missing
     with pytest.raises(FvkError):
         MeshDesc.block(2, 2, 2, patches=[("a", [0, 0, 1, 2, 3, 4, 5], False)])  # duplicate
+
+
+# ---- the oracle's own generator (oracle/blockmesh.cpp) vs the product's host generator: bit for bit ---------------------
+import pytest  # noqa: E402
+
+from foamadapter_b200.mesh import PATCHES_3DCUBE, PATCHES_CAVITY2D, PATCHES_CAVITY3D  # noqa: E402
+
+
+@pytest.mark.parametrize("dims,box,patches", [((5, 5, 1), (0.1, 0.1, 0.01), PATCHES_CAVITY2D), ((7, 5, 3), (0.1, 0.1, 0.01), PATCHES_3DCUBE),
+                                              ((4, 6, 5), (1.0, 2.0, 3.0), PATCHES_CAVITY3D), ((1, 1, 1), (1.0, 1.0, 1.0), PATCHES_3DCUBE),
+                                              ((3, 1, 2), (1.0, 1.0, 1.0), PATCHES_3DCUBE), ((33, 17, 9), (0.3, 0.2, 0.1), PATCHES_3DCUBE)])
+def test_oracle_generator_equals_product_generator(dims, box, patches):
+    import numpy as np
+    from foamadapter_b200.mesh import MeshDesc
+    from oracle.cpu import Mesh
+    a = Mesh.from_desc(MeshDesc.block(*dims, *box, patches=patches))
+    b = Mesh.block(*dims, *box, patches=[(n, list(s), e) for n, s, e in patches])
+    for k in ("owner", "neighbour", "faceCells", "V", "C", "Sf", "Cf", "magSf", "patchOffsets", "bSf", "bDeltaCoeffs", "bWeights", "w", "dc", "nodc",
+              "rowOffs", "colIdxs", "ownerOffset", "neighbourOffset", "diagOffset"):
+        x, y = np.ravel(getattr(a, k)), np.ravel(getattr(b, k))
+        assert x.shape == y.shape and np.array_equal(x, y), k
