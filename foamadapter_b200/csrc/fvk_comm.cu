@@ -122,7 +122,7 @@ k_halo_push(const FvkP2PCtx* __restrict__ ctxp, const int* __restrict__ cells, c
         int k = 0;
         while (i >= ctx.sendOff[k + 1]) ++k;
         double* dst = reinterpret_cast<double*>(ctx.win[ctx.nbrRank[k]] + FVK_P2P_HALO_OFF)
-                      + (seq & 1) * size_t(3) * ctx.peerGhost[k] + size_t(NC) * (ctx.peerRecvOff[k] + (i - ctx.sendOff[k]));
+                      + (seq & 1) * size_t(FVK_P2P_HALO_COMPS) * ctx.peerGhost[k] + size_t(NC) * (ctx.peerRecvOff[k] + (i - ctx.sendOff[k]));
         const int64_t c = cells[i];
 #pragma unroll
         for (int q = 0; q < NC; ++q) dst[q] = field[NC * c + q];
@@ -156,10 +156,67 @@ k_halo_wait_unpack(const FvkP2PCtx* __restrict__ ctxp, double* __restrict__ fiel
         while (ld_acquire_sys(flag) < seq) __nanosleep(40);
     }
     __syncthreads();
-    const double* src = reinterpret_cast<const double*>(ctx.win[ctx.rank] + FVK_P2P_HALO_OFF) + (seq & 1) * size_t(3) * ctx.nGhost;
+    const double* src = reinterpret_cast<const double*>(ctx.win[ctx.rank] + FVK_P2P_HALO_OFF) + (seq & 1) * size_t(FVK_P2P_HALO_COMPS) * ctx.nGhost;
     double* dst = field + size_t(NC) * ctx.nOwned;
     const int n = NC * ctx.nGhost;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = __ldcg(src + i); // L1 may hold the previous exchange
+}
+
+
+// several cell fields in ONE exchange (one push, one flag, one wait): ghost cell g of neighbour k carries the fields'
+// components back to back, TOT doubles per ghost
+struct HaloFields
+{
+    int n, tot;
+    double* f[4];
+    int nc[4], off[4];
+};
+__global__ void __launch_bounds__(256)
+k_halo_push_multi(const FvkP2PCtx* __restrict__ ctxp, const int* __restrict__ cells, HaloFields hf)
+{
+    const FvkP2PCtx& ctx = *ctxp;
+    const unsigned long long seq = ctx.state->haloSeq + 1;
+    const int nSend = ctx.sendOff[ctx.nNbr];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nSend; i += gridDim.x * blockDim.x)
+    {
+        int k = 0;
+        while (i >= ctx.sendOff[k + 1]) ++k;
+        double* dst = reinterpret_cast<double*>(ctx.win[ctx.nbrRank[k]] + FVK_P2P_HALO_OFF)
+                      + (seq & 1) * size_t(FVK_P2P_HALO_COMPS) * ctx.peerGhost[k] + size_t(hf.tot) * (ctx.peerRecvOff[k] + (i - ctx.sendOff[k]));
+        const int64_t c = cells[i];
+        for (int a = 0; a < hf.n; ++a)
+            for (int q = 0; q < hf.nc[a]; ++q) dst[hf.off[a] + q] = hf.f[a][hf.nc[a] * c + q];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        const unsigned t = atomicAdd(&ctx.state->pushCounter, 1u);
+        if (t == gridDim.x - 1)
+        {
+            __threadfence();
+            ctx.state->pushCounter = 0u;
+            for (int k = 0; k < ctx.nNbr; ++k)
+                st_release_sys(reinterpret_cast<unsigned long long*>(ctx.win[ctx.nbrRank[k]] + FVK_P2P_HALOFLAG_OFF) + ctx.rank, seq);
+            ctx.state->haloSeq = seq;
+        }
+    }
+}
+__global__ void __launch_bounds__(256)
+k_halo_wait_unpack_multi(const FvkP2PCtx* __restrict__ ctxp, HaloFields hf)
+{
+    const FvkP2PCtx& ctx = *ctxp;
+    const unsigned long long seq = ctx.state->haloSeq;
+    if (threadIdx.x < ctx.nNbr)
+    {
+        const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(ctx.win[ctx.rank] + FVK_P2P_HALOFLAG_OFF) + ctx.nbrRank[threadIdx.x];
+        while (ld_acquire_sys(flag) < seq) __nanosleep(40);
+    }
+    __syncthreads();
+    const double* src = reinterpret_cast<const double*>(ctx.win[ctx.rank] + FVK_P2P_HALO_OFF) + (seq & 1) * size_t(FVK_P2P_HALO_COMPS) * ctx.nGhost;
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < ctx.nGhost; g += gridDim.x * blockDim.x)
+        for (int a = 0; a < hf.n; ++a)
+            for (int q = 0; q < hf.nc[a]; ++q) hf.f[a][size_t(hf.nc[a]) * (ctx.nOwned + g) + q] = __ldcg(src + size_t(hf.tot) * g + hf.off[a] + q);
 }
 
 __global__ void k_allreduce_p2p(const FvkP2PCtx* __restrict__ ctx, double* data, int n)
@@ -337,6 +394,33 @@ int fvk_comm_allreduce_sum_impl(fvk_comm* c, double* data, int count, cudaStream
 extern "C" int fvk_comm_halo_exchange(fvk_comm* c, double* field, int ncomp, fvk_stream s)
 {
     return fvk_comm_halo_exchange_impl(c, field, ncomp, fvk_cu(s));
+}
+extern "C" int fvk_comm_halo_exchange_multi(fvk_comm* c, int nFields, const fvk_halo_field* fields_h, fvk_stream s)
+{
+    if (!c || nFields < 1 || nFields > 4 || !fields_h) return fvk_fail(FVK_EINVAL, "fvk_comm_halo_exchange_multi: bad argument");
+    HaloFields hf;
+    hf.n = nFields; hf.tot = 0;
+    for (int a = 0; a < nFields; ++a)
+    {
+        if (!fields_h[a].field || (fields_h[a].ncomp != 1 && fields_h[a].ncomp != 3)) return fvk_fail(FVK_EINVAL, "fvk_comm_halo_exchange_multi: bad field %d", a);
+        hf.f[a] = fields_h[a].field; hf.nc[a] = fields_h[a].ncomp; hf.off[a] = hf.tot; hf.tot += fields_h[a].ncomp;
+    }
+    if (hf.tot > FVK_P2P_HALO_COMPS) return fvk_fail(FVK_EINVAL, "fvk_comm_halo_exchange_multi: more than %d components", FVK_P2P_HALO_COMPS);
+    if (c->nRanks == 1 || c->nbrRank.empty()) return FVK_OK;
+    cudaStream_t st = fvk_cu(s);
+    if (!c->p2p || nFields == 1)
+    { // NCCL transport: one send/recv group per field
+        for (int a = 0; a < nFields; ++a)
+            if (int rc = fvk_comm_halo_exchange_impl(c, fields_h[a].field, fields_h[a].ncomp, st)) return rc;
+        return FVK_OK;
+    }
+    const int nS = c->sendOff.back(), nG = c->recvOff.back();
+    const int gp = nS > 0 ? ((nS + 255) / 256 < 64 ? (nS + 255) / 256 : 64) : 1;
+    const int gw = nG > 0 ? ((nG + 255) / 256 < 64 ? (nG + 255) / 256 : 64) : 1;
+    k_halo_push_multi<<<gp, 256, 0, st>>>(c->ctx_d, c->sendCells, hf);
+    k_halo_wait_unpack_multi<<<gw, 256, 0, st>>>(c->ctx_d, hf);
+    FVK_LAUNCH_CHECK();
+    return FVK_OK;
 }
 extern "C" int fvk_comm_allreduce_sum(fvk_comm* c, double* data_d, int count, fvk_stream s)
 {

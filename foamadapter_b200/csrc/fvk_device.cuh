@@ -58,15 +58,16 @@ __device__ __forceinline__ int ld_stream(const int* p)
 
 // ---- peer-memory windows (fvk_comm.cu; used by the CG kernels of fvk_la.cu) ----------------------------------------
 // Window layout (bytes): [0, 512) halo flags (u64 per sender rank) | [1024, ...) all-reduce flags u64[2][64] |
-// [4096, 12288) all-reduce words u64[2][64][8] ({32 data bits | 32-bit sequence} pairs) | [FVK_P2P_HALO_OFF, ...) halo data double[2][3 * nGhost]
+// [4096, 12288) all-reduce words u64[2][64][8] ({32 data bits | 32-bit sequence} pairs) | [FVK_P2P_HALO_OFF, ...) halo data double[2][FVK_P2P_HALO_COMPS * nGhost]
 #define FVK_P2P_MAX_RANKS 64
 #define FVK_P2P_MAX_NBR 32
 #define FVK_P2P_HALOFLAG_OFF 0
 #define FVK_P2P_ARFLAG_OFF 1024
 #define FVK_P2P_ARVAL_OFF 4096
 #define FVK_P2P_HALO_OFF 16384
+#define FVK_P2P_HALO_COMPS 8 // doubles per ghost cell one exchange can carry (e.g. rAU + HbyA + U = 7)
 // byte offset of the CG work area z[2][nOwned + nGhost] of a rank with nGhost ghost cells: behind its halo area
-#define FVK_P2P_Z_OFF(nGhost) (FVK_P2P_HALO_OFF + ((sizeof(double) * 2 * 3 * (size_t(nGhost) + 1) + 255) & ~size_t(255)))
+#define FVK_P2P_Z_OFF(nGhost) (FVK_P2P_HALO_OFF + ((sizeof(double) * 2 * FVK_P2P_HALO_COMPS * (size_t(nGhost) + 1) + 255) & ~size_t(255)))
 struct FvkP2PState // device memory of the owning rank only
 {
     unsigned long long haloSeq, arSeq;
@@ -172,7 +173,7 @@ __device__ __forceinline__ unsigned long long fvk_p2p_halo_push_block(const FvkP
     {
         int k = 0;
         while (i >= ctx.sendOff[k + 1]) ++k;
-        double* dst = reinterpret_cast<double*>(ctx.win[ctx.nbrRank[k]] + FVK_P2P_HALO_OFF) + (seq & 1) * size_t(3) * ctx.peerGhost[k]
+        double* dst = reinterpret_cast<double*>(ctx.win[ctx.nbrRank[k]] + FVK_P2P_HALO_OFF) + (seq & 1) * size_t(FVK_P2P_HALO_COMPS) * ctx.peerGhost[k]
                       + (ctx.peerRecvOff[k] + (i - ctx.sendOff[k]));
         *dst = __ldcg(field + ctx.sendCells[i]); // written by other blocks of this kernel: read through L2
     }
@@ -197,7 +198,7 @@ __device__ __forceinline__ void fvk_p2p_halo_wait_unpack_block(const FvkP2PCtx& 
         } while (v < seq);
     }
     __syncthreads();
-    const double* src = reinterpret_cast<const double*>(ctx.win[ctx.rank] + FVK_P2P_HALO_OFF) + (seq & 1) * size_t(3) * ctx.nGhost;
+    const double* src = reinterpret_cast<const double*>(ctx.win[ctx.rank] + FVK_P2P_HALO_OFF) + (seq & 1) * size_t(FVK_P2P_HALO_COMPS) * ctx.nGhost;
     for (int i = threadIdx.x; i < ctx.nGhost; i += blockDim.x) field[ctx.nOwned + i] = __ldcg(src + i);
     if (threadIdx.x == 0) ctx.state->haloSeq = seq;
 }

@@ -24,6 +24,8 @@ struct S1
     static constexpr int NC = 1;
     static __device__ __forceinline__ T zero() { return 0.0; }
     static __device__ __forceinline__ T splat(double s) { return s; } // s * one<T>()
+    static __device__ __forceinline__ T splatRaw(double s) { return s; }
+    static __device__ __forceinline__ double first(const T& v) { return v; }
     static __device__ __forceinline__ T ld(const double* __restrict__ p, int64_t i) { return p[i]; }
     static __device__ __forceinline__ void st(double* __restrict__ p, int64_t i, T v) { p[i] = v; }
     static __device__ __forceinline__ T add(T a, T b) { return a + b; }
@@ -36,6 +38,8 @@ struct S3
     static constexpr int NC = 3;
     static __device__ __forceinline__ T zero() { return Vec3d {0.0, 0.0, 0.0}; }
     static __device__ __forceinline__ T splat(double s) { return Vec3d {1.0 * s, 1.0 * s, 1.0 * s}; }
+    static __device__ __forceinline__ T splatRaw(double s) { return Vec3d {s, s, s}; }
+    static __device__ __forceinline__ double first(const T& v) { return v.x; }
     static __device__ __forceinline__ T ld(const double* __restrict__ p, int64_t i) { return ld3(p, i); }
     static __device__ __forceinline__ void st(double* __restrict__ p, int64_t i, T v) { st3(p, i, v); }
     static __device__ __forceinline__ T add(T a, T b) { return Vec3d {a.x + b.x, a.y + b.y, a.z + b.z}; }
@@ -92,7 +96,21 @@ __device__ __forceinline__ void face_coeffs(const fvk_term& t, const AsmMesh& m,
     }
 }
 
-template <class VT>
+// matrix value access: COMPACT (Vec3 systems only) stores the identical components of an entry once (values double[nnz])
+template <class VT, bool COMPACT>
+__device__ __forceinline__ typename VT::T ldval(const double* __restrict__ values, int64_t i)
+{
+    if (COMPACT) return VT::splatRaw(values[i]);
+    return VT::ld(values, i);
+}
+template <class VT, bool COMPACT>
+__device__ __forceinline__ void stval(double* __restrict__ values, int64_t i, const typename VT::T& v)
+{
+    if (COMPACT) values[i] = VT::first(v);
+    else VT::st(values, i, v);
+}
+
+template <class VT, bool COMPACT>
 __global__ void __launch_bounds__(256)
 k_assemble(Terms terms, AsmMesh m, fvk_bfield bd, double* __restrict__ values, double* __restrict__ rhs,
            double* __restrict__ bcMatrix, double* __restrict__ bcRhs, int accumulate)
@@ -110,7 +128,7 @@ k_assemble(Terms terms, AsmMesh m, fvk_bfield bd, double* __restrict__ values, d
         if (f >= m.nI) break; // boundary faces come last
         const int side = code & 1;
         const int slot = r0 + (side ? m.neiOffs[f] : m.ownOffs[f]);
-        T v = accumulate ? VT::ld(values, slot) : VT::zero();
+        T v = accumulate ? ldval<VT, COMPACT>(values, slot) : VT::zero();
         for (int k = 0; k < terms.n; ++k)
         {
             const fvk_term& t = terms.t[k];
@@ -119,11 +137,11 @@ k_assemble(Terms terms, AsmMesh m, fvk_bfield bd, double* __restrict__ values, d
             face_coeffs(t, m, f, lo, up);
             v = VT::add(v, VT::mul(term_scaling(t, c), VT::splat(side ? lo : up)));
         }
-        VT::st(values, slot, v);
+        stval<VT, COMPACT>(values, slot, v);
     }
     // ---- diagonal and rhs: term-major, faces ascending inside a term ------------------------------
     const int dslot = r0 + m.diagOffs[c];
-    T d = accumulate ? VT::ld(values, dslot) : VT::zero();
+    T d = accumulate ? ldval<VT, COMPACT>(values, dslot) : VT::zero();
     T r = accumulate ? VT::ld(rhs, c) : VT::zero();
     for (int k = 0; k < terms.n; ++k)
     {
@@ -183,7 +201,7 @@ k_assemble(Terms terms, AsmMesh m, fvk_bfield bd, double* __restrict__ values, d
             d = VT::add(d, VT::splat(os * t.cellField[c] * m.V[c]));
         }
     }
-    VT::st(values, dslot, d);
+    stval<VT, COMPACT>(values, dslot, d);
     VT::st(rhs, c, r);
 }
 
@@ -220,14 +238,14 @@ __device__ __forceinline__ void face_coeffs_k(const fvk_term& t, const AsmMesh& 
     }
 }
 
-template <class VT, int K0, int K1>
+template <class VT, int K0, int K1, bool COMPACT>
 __global__ void __launch_bounds__(256)
 k_assemble_fast(Terms terms, AsmMesh m, fvk_bfield bd, int ft0, int ft1, double* __restrict__ values,
                 double* __restrict__ rhs, double* __restrict__ bcMatrix, double* __restrict__ bcRhs,
                 const int* __restrict__ cellList = nullptr, int nList = 0, int tailFirst = 0, int nTail = 0)
 {
     using T = typename VT::T;
-    constexpr int NC = VT::NC;
+    constexpr int NC = COMPACT ? 1 : VT::NC; // doubles per stored matrix entry
     constexpr bool HAS1 = K1 != 0;
     extern __shared__ double stageAll[];
     const int lane = threadIdx.x & 31;
@@ -256,11 +274,11 @@ k_assemble_fast(Terms terms, AsmMesh m, fvk_bfield bd, int ft0, int ft1, double*
         if (staged)
         {
             double* q = stage + size_t(r0 - wbase + pos) * NC;
-            if (NC == 1) q[0] = reinterpret_cast<const double&>(v);
+            if (NC == 1) q[0] = VT::first(v);
             else { const double* pv = reinterpret_cast<const double*>(&v); q[0] = pv[0]; q[1] = pv[1]; q[2] = pv[2]; }
         }
         else
-            VT::st(values, r0 + pos, v);
+            stval<VT, COMPACT>(values, r0 + pos, v);
     };
 
     // ---- internal faces: coefficients once, off-diagonal entries out, diagonal contributions kept
@@ -395,12 +413,12 @@ struct AsmAffine
 };
 constexpr int AFF_LX = 32;
 
-template <class VT, int K0, int K1, int BY, int BZ, int MINB>
+template <class VT, int K0, int K1, int BY, int BZ, int MINB, bool COMPACT>
 __global__ void __launch_bounds__(AFF_LX * BY * BZ, MINB)
 k_assemble_affine(Terms terms, AsmMesh m, AsmAffine g, int ft0, int ft1, double* __restrict__ values, double* __restrict__ rhs)
 {
     using T = typename VT::T;
-    constexpr int NC = VT::NC;
+    constexpr int NC = COMPACT ? 1 : VT::NC; // doubles per stored matrix entry
     constexpr bool HAS1 = K1 != 0;
     constexpr int NCO = HAS1 ? 4 : 2; // doubles per face slot: {lo0, up0[, lo1, up1]}
     constexpr int TB = AFF_LX * BY * BZ;
@@ -583,7 +601,7 @@ k_rhs_sub_source(int nC, const double* __restrict__ V, const double* __restrict_
     VT::st(rhs, c, VT::sub(VT::ld(rhs, c), VT::mul(V[c], VT::ld(src, c))));
 }
 
-template <class VT>
+template <class VT, bool COMPACT = false>
 int assemble_impl(const fvk_mesh* m, int nTerms, const fvk_term* terms_h, const fvk_bfield* bd, double* values,
                   double* rhs, double* bcMatrix, double* bcRhs, int accumulate, fvk_stream s)
 {
@@ -639,7 +657,7 @@ int assemble_impl(const fvk_mesh* m, int nTerms, const fvk_term* terms_h, const 
     static const bool noFast = [] { const char* e = std::getenv("FVK_ASM_GENERIC"); return e && *e == '1'; }();
     if (!noFast && !accumulate && m->rowsInStencilOrder && nFace >= 1 && nFace <= 2)
     {
-        const size_t shm = sizeof(double) * 8 * ASM_CAPW * VT::NC;
+        const size_t shm = sizeof(double) * 8 * ASM_CAPW * (COMPACT ? 1 : VT::NC);
         const int k0 = terms_h[ft[0]].kind, k1 = nFace == 2 ? terms_h[ft[1]].kind : 0;
         // block-structured mesh with proven topology: index-free kernel for the regular rows + cell-list pass for the rest
         static const bool noAffine = [] { const char* e = std::getenv("FVK_ASM_NO_AFFINE"); return e && *e == '1'; }();
@@ -666,11 +684,11 @@ int assemble_impl(const fvk_mesh* m, int nTerms, const fvk_term* terms_h, const 
         const int nTilesA = ag.tdx * ag.tdy * ((bg.dims[2] + BZ - 1) / BZ);                                             \
         const size_t shmA = sizeof(double) * std::max(size_t(3 * TB + AFF_LX * BY + AFF_LX * BZ + BY * BZ) * (nFace == 2 ? 4 : 2), size_t(TB) * 7); \
         if (shmA > 48 * 1024)                                                                                           \
-            FVK_CUDA(cudaFuncSetAttribute(k_assemble_affine<VT, a, bb, BY, BZ, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(shmA))); \
-        k_assemble_affine<VT, a, bb, BY, BZ, MINB><<<nTilesA, TB, shmA, fvk_cu(s)>>>(T, am, ag, ft[0], ft[1], values, rhs); \
+            FVK_CUDA(cudaFuncSetAttribute(k_assemble_affine<VT, a, bb, BY, BZ, MINB, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(shmA))); \
+        k_assemble_affine<VT, a, bb, BY, BZ, MINB, COMPACT><<<nTilesA, TB, shmA, fvk_cu(s)>>>(T, am, ag, ft[0], ft[1], values, rhs); \
         FVK_LAUNCH_CHECK();                                                                                             \
         if (nListed > 0)                                                                                                \
-            k_assemble_fast<VT, a, bb><<<(nListed + 255) / 256, 256, 0, fvk_cu(s)>>>(T, am, b, ft[0], ft[1], values, rhs, bcMatrix, bcRhs, \
+            k_assemble_fast<VT, a, bb, COMPACT><<<(nListed + 255) / 256, 256, 0, fvk_cu(s)>>>(T, am, b, ft[0], ft[1], values, rhs, bcMatrix, bcRhs, \
                                                                                      m->bp.irrCells, m->bp.nIrr, m->nOwned, nTail); \
         FVK_LAUNCH_CHECK();                                                                                             \
         return FVK_OK;                                                                                                  \
@@ -691,8 +709,8 @@ int assemble_impl(const fvk_mesh* m, int nTerms, const fvk_term* terms_h, const 
     if (k0 == a && k1 == bb)                                                                                            \
     {                                                                                                                   \
         if (shm > 48 * 1024)                                                                                            \
-            FVK_CUDA(cudaFuncSetAttribute(k_assemble_fast<VT, a, bb>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(shm))); \
-        k_assemble_fast<VT, a, bb><<<grid, 256, shm, fvk_cu(s)>>>(T, am, b, ft[0], ft[1], values, rhs, bcMatrix, bcRhs); \
+            FVK_CUDA(cudaFuncSetAttribute(k_assemble_fast<VT, a, bb, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(shm))); \
+        k_assemble_fast<VT, a, bb, COMPACT><<<grid, 256, shm, fvk_cu(s)>>>(T, am, b, ft[0], ft[1], values, rhs, bcMatrix, bcRhs); \
         FVK_LAUNCH_CHECK();                                                                                             \
         return FVK_OK;                                                                                                  \
     }
@@ -701,7 +719,7 @@ int assemble_impl(const fvk_mesh* m, int nTerms, const fvk_term* terms_h, const 
         FVK_ASM_CASE(FVK_TERM_DIV, FVK_TERM_DIV) FVK_ASM_CASE(FVK_TERM_LAPLACIAN, FVK_TERM_LAPLACIAN)
 #undef FVK_ASM_CASE
     }
-    k_assemble<VT><<<grid, 256, 0, fvk_cu(s)>>>(T, am, b, values, rhs, bcMatrix, bcRhs, accumulate ? 1 : 0);
+    k_assemble<VT, COMPACT><<<grid, 256, 0, fvk_cu(s)>>>(T, am, b, values, rhs, bcMatrix, bcRhs, accumulate ? 1 : 0);
     FVK_LAUNCH_CHECK();
     return FVK_OK;
 }
@@ -716,6 +734,30 @@ extern "C" int fvk_assemble_v(const fvk_mesh* m, int nTerms, const fvk_term* ter
                               double* values, double* rhs, double* bcMatrix, double* bcRhs, int accumulate, fvk_stream s)
 {
     return assemble_impl<S3>(m, nTerms, terms_h, bd, values, rhs, bcMatrix, bcRhs, accumulate, s);
+}
+
+// Vec3 system whose matrix entries have identical components (every implicit operator multiplies by one<Vec3>()):
+// values double[nnz] holds each entry ONCE (a third of the HBM traffic of the Vec3 layout); rhs / bcMatrix / bcRhs stay Vec3.
+extern "C" int fvk_assemble_vc(const fvk_mesh* m, int nTerms, const fvk_term* terms_h, const fvk_bfield* bd,
+                               double* valuesCompact, double* rhs, double* bcMatrix, double* bcRhs, int accumulate, fvk_stream s)
+{
+    return assemble_impl<S3, true>(m, nTerms, terms_h, bd, valuesCompact, rhs, bcMatrix, bcRhs, accumulate, s);
+}
+namespace
+{
+__global__ void __launch_bounds__(256) k_expand_vec3(int64_t n, const double* __restrict__ in, double* __restrict__ out)
+{
+    for (int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x; i < 3 * n; i += int64_t(gridDim.x) * 256) out[i] = in[i / 3];
+}
+} // namespace
+extern "C" int fvk_expand_vec3(int64_t n, const double* compact, double* outV, fvk_stream s)
+{
+    if (n < 0 || (n && (!compact || !outV))) return fvk_fail(FVK_EINVAL, "fvk_expand_vec3: bad argument");
+    if (n == 0) return FVK_OK;
+    const int64_t g = (3 * n + 255) / 256;
+    k_expand_vec3<<<unsigned(g < 148 * 16 ? g : 148 * 16), 256, 0, fvk_cu(s)>>>(n, compact, outV);
+    FVK_LAUNCH_CHECK();
+    return FVK_OK;
 }
 
 extern "C" int fvk_bc_coeff_indices(const fvk_mesh* m, int32_t* matrixIdxs, int32_t* rhsIdxs, fvk_stream s)

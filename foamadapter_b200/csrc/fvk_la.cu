@@ -1184,16 +1184,24 @@ extern "C" int fvk_solver_solve_vec3(fvk_solver* sv, int64_t nnz, const int32_t*
         FVK_CUDA(cudaMalloc(reinterpret_cast<void**>(&sv->vals0), sizeof(double) * nnz));
         sv->vals0Cap = nnz;
     }
-    if (!sv->bC) FVK_CUDA(cudaMalloc(reinterpret_cast<void**>(&sv->bC), sizeof(double) * sv->nRows));
-    if (!sv->xC) FVK_CUDA(cudaMalloc(reinterpret_cast<void**>(&sv->xC), sizeof(double) * sv->nCols));
     k_take_component<<<stream_grid(nnz), TB, 0, st>>>(nnz, 0, valuesV, sv->vals0);
     FVK_LAUNCH_CHECK();
+    return fvk_solver_solve_vec3c(sv, rowOffs, colIdxs, sv->vals0, bV, xV, stats3_h, s);
+}
+
+extern "C" int fvk_solver_solve_vec3c(fvk_solver* sv, const int32_t* rowOffs, const int32_t* colIdxs, const double* valuesCompact,
+                                      const double* bV, double* xV, fvk_solver_stats* stats3_h, fvk_stream s)
+{
+    if (!sv || !rowOffs || !colIdxs || !valuesCompact || !bV || !xV || !stats3_h) return fvk_fail(FVK_EINVAL, "fvk_solver_solve_vec3c: bad argument");
+    cudaStream_t st = fvk_cu(s);
+    if (!sv->bC) FVK_CUDA(cudaMalloc(reinterpret_cast<void**>(&sv->bC), sizeof(double) * sv->nRows));
+    if (!sv->xC) FVK_CUDA(cudaMalloc(reinterpret_cast<void**>(&sv->xC), sizeof(double) * sv->nCols));
     for (int c = 0; c < 3; ++c)
     {
         k_take_component<<<stream_grid(sv->nRows), TB, 0, st>>>(sv->nRows, c, bV, sv->bC);
         k_take_component<<<stream_grid(sv->nCols), TB, 0, st>>>(sv->nCols, c, xV, sv->xC);
         FVK_LAUNCH_CHECK();
-        if (int rc = fvk_solver_solve(sv, rowOffs, colIdxs, sv->vals0, sv->bC, sv->xC, &stats3_h[c], nullptr, 0, s)) return rc;
+        if (int rc = fvk_solver_solve(sv, rowOffs, colIdxs, valuesCompact, sv->bC, sv->xC, &stats3_h[c], nullptr, 0, s)) return rc;
         k_put_component<<<stream_grid(sv->nRows), TB, 0, st>>>(sv->nRows, c, sv->xC, xV);
         FVK_LAUNCH_CHECK();
     }

@@ -616,6 +616,8 @@ extern "C" int fvk_mesh_size(const fvk_mesh* m, int field, int64_t* value)
         case FVK_N_PATCHES: *value = m->nPatches; break;
         case FVK_NNZ: *value = m->nnz; break;
         case FVK_N_OWNED_CELLS: *value = m->nOwned; break;
+        case FVK_ROWS_IN_STENCIL_ORDER: *value = m->rowsInStencilOrder ? 1 : 0; break;
+        case FVK_AFFINE_TOPOLOGY: *value = (m->bp.nTiles > 0 && m->bp.geom.affine) ? 1 : 0; break;
         default: return fvk_fail(FVK_EINVAL, "fvk_mesh_size: unknown field %d", field);
     }
     return FVK_OK;

@@ -45,6 +45,64 @@ k_rAU_HbyA(int nC, int nI, const int* __restrict__ seg, const int* __restrict__ 
     st3(HbyA, c, vscale(h, ra / vol));
 }
 
+
+// Row-walk variant for meshes whose CSR rows are laid out like the cell's stencil ([lower faces ascending | diag | upper faces
+// ascending], fvk_mesh::rowsInStencilOrder): "off-diagonals subtracted in ascending face order" is then simply the row in
+// entry order, so no stencil / owner / neighbour / offset array is read -- only the row itself. VS = doubles between matrix
+// entries: 3 for the reference's Vec3 layout (component [0] is read), 1 for the compact layout (fvk_assemble_vc). Block-
+// structured meshes with proven topology get the column indices of the regular rows from arithmetic (as k_spmv does).
+struct RowsAffine
+{
+    int on, nx, ny, nz;
+};
+template <int VS>
+__global__ void __launch_bounds__(256)
+k_rAU_HbyA_rows(int nC, const int* __restrict__ rowOffs, const int* __restrict__ colIdxs, const uint8_t* __restrict__ diagOffs,
+                const double* __restrict__ V, const double* __restrict__ values, const double* __restrict__ rhsV,
+                const double* __restrict__ U, double* __restrict__ rAU, double* __restrict__ HbyA, RowsAffine aff)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nC) return;
+    const int r0 = rowOffs[c], r1 = rowOffs[c + 1];
+    const double vol = V[c];
+    bool reg = false;
+    int i = 0, j = 0, kz = 0;
+    if (aff.on)
+    {
+        i = c % aff.nx; const int q = c / aff.nx; j = q % aff.ny; kz = q / aff.ny;
+        reg = i > 0 && i < aff.nx - 1 && j > 0 && j < aff.ny - 1 && kz > 0 && kz < aff.nz - 1 && r1 - r0 == 7;
+    }
+    if (reg)
+    {
+        const int nxy = aff.nx * aff.ny;
+        const int col[6] = {c - nxy, c - aff.nx, c - 1, c + 1, c + aff.nx, c + nxy};
+        double a[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) a[k] = values[int64_t(VS) * (r0 + k)];
+        const double ra = vol / a[3];
+        rAU[c] = ra;
+        if (!HbyA) return;
+        Vec3d u[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) u[k] = ld3(U, col[k]);
+        Vec3d h {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int k = 0; k < 6; ++k) h = vsub(h, vscale(u[k], a[k < 3 ? k : k + 1]));
+        h = vadd(h, ld3(rhsV, c));
+        st3(HbyA, c, vscale(h, ra / vol));
+        return;
+    }
+    const int dpos = r0 + diagOffs[c];
+    const double ra = vol / values[int64_t(VS) * dpos];
+    rAU[c] = ra;
+    if (!HbyA) return;
+    Vec3d h {0.0, 0.0, 0.0};
+    for (int k = r0; k < r1; ++k)
+        if (k != dpos) h = vsub(h, vscale(ld3(U, colIdxs[k]), values[int64_t(VS) * k]));
+    h = vadd(h, ld3(rhsV, c));
+    st3(HbyA, c, vscale(h, ra / vol));
+}
+
 // flux (:215-267)
 __global__ void __launch_bounds__(256)
 k_flux(int nI, int nF, const int* __restrict__ owner, const int* __restrict__ neighbour, const double* __restrict__ w,
@@ -150,10 +208,33 @@ k_copy_patches(PatchMask pm, int nB, const double* __restrict__ src, double* __r
 
 #define GRID(n) ((n) + 255) / 256, 256, 0, fvk_cu(s)
 
+static RowsAffine rows_affine(const fvk_mesh* m)
+{
+    const FvkBrickGeom& g = m->bp.geom;
+    if (fvk_no_affine() || !g.affine || m->bp.nTiles == 0 || int64_t(g.dims[0]) * g.dims[1] * g.dims[2] != m->nOwned) return RowsAffine {0, 0, 0, 0};
+    return RowsAffine {1, g.dims[0], g.dims[1], g.dims[2]};
+}
+
+extern "C" int fvk_rAU_HbyA_c(const fvk_mesh* m, const double* valuesCompact, const double* rhsV, const double* U, double* rAU,
+                              double* HbyA, fvk_stream s)
+{
+    if (!m || !valuesCompact || !rAU || (HbyA && (!rhsV || !U))) return fvk_fail(FVK_EINVAL, "fvk_rAU_HbyA_c: null argument");
+    if (!m->rowsInStencilOrder) return fvk_fail(FVK_EUNSUPPORTED, "fvk_rAU_HbyA_c: the mesh's CSR rows are not in stencil order");
+    k_rAU_HbyA_rows<1><<<GRID(m->nOwned)>>>(m->nOwned, m->rowOffs, m->colIdxs, m->diagOffset, m->V, valuesCompact, rhsV, U, rAU, HbyA, rows_affine(m));
+    FVK_LAUNCH_CHECK();
+    return FVK_OK;
+}
+
 extern "C" int fvk_rAU_HbyA(const fvk_mesh* m, const double* valuesV, const double* rhsV, const double* U, double* rAU,
                             double* HbyA, fvk_stream s)
 {
     if (!m || !valuesV || !rAU || (HbyA && (!rhsV || !U))) return fvk_fail(FVK_EINVAL, "fvk_rAU_HbyA: null argument");
+    if (m->rowsInStencilOrder && fvk_variant() == 0)
+    {
+        k_rAU_HbyA_rows<3><<<GRID(m->nOwned)>>>(m->nOwned, m->rowOffs, m->colIdxs, m->diagOffset, m->V, valuesV, rhsV, U, rAU, HbyA, rows_affine(m));
+        FVK_LAUNCH_CHECK();
+        return FVK_OK;
+    }
     k_rAU_HbyA<<<GRID(m->nOwned)>>>(m->nOwned, m->nInternalFaces, m->stencilSeg, m->gatherEnt, m->owner, m->neighbour, m->rowOffs,
                                     m->diagOffset, m->ownerOffset, m->neighbourOffset, m->V, valuesV, rhsV, U, rAU, HbyA);
     FVK_LAUNCH_CHECK();

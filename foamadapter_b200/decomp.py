@@ -158,6 +158,15 @@ class Comm:
         check(lib().fvk_comm_halo_exchange(self._h, C.c_void_p(field.data_ptr()), C.c_int(ncomp),
                                            C.c_void_p(torch.cuda.current_stream().cuda_stream)))
 
+    def halo_exchange_multi(self, fields):
+        """one exchange for several cell fields (fvk_comm_halo_exchange_multi)"""
+        import torch
+
+        class _HF(C.Structure):
+            _fields_ = [("field", C.c_void_p), ("ncomp", C.c_int32)]
+        arr = (_HF * len(fields))(*[_HF(f.data_ptr(), 3 if f.ndim == 2 else 1) for f in fields])
+        check(lib().fvk_comm_halo_exchange_multi(self._h, C.c_int(len(fields)), arr, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
     def allreduce_sum(self, t):
         import torch
         check(lib().fvk_comm_allreduce_sum(self._h, C.c_void_p(t.data_ptr()), C.c_int(t.numel()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))

@@ -202,19 +202,18 @@ class PDESolver:
     def setReference(self, pRefCell, pRefValue):
         self.needReference, self.pRefCell, self.pRefValue = True, int(pRefCell), float(pRefValue)
 
-    def prepare(self):
+    def prepare(self, exchange_guess=True):
         """Everything of `solve` before the linear solver runs: implicit assembly, rhs -= explicit*V, post-assembly
-        functors (SetReference), halo of the initial guess. Kernel launches only (CUDA-graph capturable)."""
-        if self.psi.ncomp != 1:
-            raise NotImplementedError("only the scalar (pressure) solve is on the hot path; momentumPredictor is 'no'")
+        functors (SetReference, scalar systems only: expression.hpp:120-132), halo of the initial guess. Kernel launches
+        only (CUDA-graph capturable)."""
         mesh = self.psi.mesh
         self.assemble()
         if self.expr.has_explicit():
             src = self.expr.explicitOperation(mesh, self.psi.ncomp)
             ops.rhs_sub_source(mesh, src, self.ls.rhs)
-        if self.needReference:
+        if self.needReference and self.psi.ncomp == 1:
             ops.set_reference(mesh, self.pRefCell, self.pRefValue, self.ls.values, self.ls.rhs)
-        if self.rt.comm is not None:
+        if exchange_guess and self.rt.comm is not None:
             self.rt.comm.halo_exchange(self.psi.internal)
 
     def solve(self, solver: la.Solver | None = None) -> la.SolverStats:

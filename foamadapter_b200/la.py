@@ -43,18 +43,31 @@ class SparsityPattern:
 class LinearSystem:
     """la::LinearSystem<scalar|Vec3, localIdx> + BoundaryCoefficients (linearSystem.hpp:36-186)."""
 
-    def __init__(self, mesh, ncomp=1, device="cuda", zero=True):
+    def __init__(self, mesh, ncomp=1, device="cuda", zero=True, compact=False):
+        """compact (Vec3 systems only; an HBM-layout choice of this implementation): the implicit operators give the three
+        components of every matrix entry the same value (SURVEY A.3), so `values` holds each entry once (double[nnz]);
+        `valuesVec3()` materialises the reference's Vec3[nnz] layout bit for bit. rhs / bcMatrix / bcRhs stay Vec3."""
         self.mesh, self.ncomp = mesh, ncomp
+        self.compact = bool(compact) and ncomp == 3
         self.sp = SparsityPattern.readOrCreate(mesh)
         mk = torch.zeros if zero else torch.empty
         shp = (lambda n: (n, 3)) if ncomp == 3 else (lambda n: (n,))
-        self.values = mk(shp(mesh.nnz), dtype=torch.float64, device=device)
+        self.values = mk((mesh.nnz,) if self.compact else shp(mesh.nnz), dtype=torch.float64, device=device)
         self.rhs = mk(shp(mesh.nCells), dtype=torch.float64, device=device)
         self.bcMatrix = torch.zeros(shp(mesh.nBoundaryFaces), dtype=torch.float64, device=device)
         self.bcRhs = torch.zeros(shp(mesh.nBoundaryFaces), dtype=torch.float64, device=device)
 
     def reset(self):
         self.values.zero_(); self.rhs.zero_()
+
+    def valuesVec3(self):
+        """LinearSystem<Vec3>::matrix().values() in the reference layout (a copy when the system is compact)."""
+        if not self.compact:
+            return self.values
+        out = torch.empty((self.mesh.nnz, 3), dtype=torch.float64, device=self.values.device)
+        check(lib().fvk_expand_vec3(C.c_int64(self.mesh.nnz), ptr(self.values), ptr(out), _stream()))
+        ops._count()
+        return out
 
 
 def createEmptyLinearSystem(mesh, ncomp=1):
@@ -232,8 +245,12 @@ class Solver:
         h = self._attach(m)
         if ls.ncomp == 3:
             st3 = (_Stats * 3)()
-            check(lib().fvk_solver_solve_vec3(h, C.c_int64(m.nnz), C.c_void_p(ls.sp.rowOffs_ptr), C.c_void_p(ls.sp.colIdxs_ptr),
-                                              ptr(ls.values), ptr(ls.rhs), ptr(x), st3, _stream()))
+            if ls.compact:
+                check(lib().fvk_solver_solve_vec3c(h, C.c_void_p(ls.sp.rowOffs_ptr), C.c_void_p(ls.sp.colIdxs_ptr),
+                                                   ptr(ls.values), ptr(ls.rhs), ptr(x), st3, _stream()))
+            else:
+                check(lib().fvk_solver_solve_vec3(h, C.c_int64(m.nnz), C.c_void_p(ls.sp.rowOffs_ptr), C.c_void_p(ls.sp.colIdxs_ptr),
+                                                  ptr(ls.values), ptr(ls.rhs), ptr(x), st3, _stream()))
             ops._count(sum(self._launches(s.numIter) + 3 for s in st3) + 1)
             return [SolverStats(s.numIter, s.initResNorm, s.finalResNorm) for s in st3]
         return self.solve_csr(m.nOwned, m.nCells, ls.sp.rowOffs_ptr, ls.sp.colIdxs_ptr, ls.values, ls.rhs, x, _mesh=m)

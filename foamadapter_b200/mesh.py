@@ -18,7 +18,7 @@ from ._capi import MeshDesc as _CDesc, check, lib
 XMIN, XMAX, YMIN, YMAX, ZMIN, ZMAX = range(6)
 
 # fvk_mesh_field
-N_CELLS, N_INTERNAL_FACES, N_BOUNDARY_FACES, N_PATCHES, NNZ, N_OWNED_CELLS = range(6)
+N_CELLS, N_INTERNAL_FACES, N_BOUNDARY_FACES, N_PATCHES, NNZ, N_OWNED_CELLS, ROWS_IN_STENCIL_ORDER, AFFINE_TOPOLOGY = range(8)
 (CELL_VOLUMES, CELL_CENTRES, FACE_AREAS, FACE_CENTRES, MAG_FACE_AREAS, FACE_OWNER, FACE_NEIGHBOUR,
  FACE_CELLS, B_CF, B_CN, B_SF, B_MAGSF, B_NF, B_DELTA, B_WEIGHTS, B_DELTACOEFFS) = range(16, 32)
 WEIGHTS, DELTACOEFFS, NONORTH_DELTACOEFFS = 48, 49, 50

@@ -149,8 +149,10 @@ def _p(t):
 
 def assemble(mesh, terms, boundary, values, rhs, bcMatrix=None, bcRhs=None, accumulate=False):
     """terms: list of dicts {kind, scheme?, coeff?, coeffView?, faceField?, cellField?, dt?} applied in order
-    (Expression::implicitOperation). boundary: BoundaryData of the unknown field (or None)."""
-    vec = values.ndim == 2
+    (Expression::implicitOperation). boundary: BoundaryData of the unknown field (or None). A Vec3 right-hand side with
+    1-D `values` selects the compact Vec3 system (la.LinearSystem(compact=True), fvk_assemble_vc)."""
+    vec = rhs.ndim == 2
+    compact = vec and values.ndim == 1
     arr = (_Term * len(terms))()
     keep = []
     for i, t in enumerate(terms):
@@ -160,7 +162,7 @@ def assemble(mesh, terms, boundary, values, rhs, bcMatrix=None, bcRhs=None, accu
     bf = None
     if boundary is not None:
         bf = C.byref(_BField(_p(boundary.value), _p(boundary.refValue), _p(boundary.valueFraction), _p(boundary.refGrad)))
-    fn = lib().fvk_assemble_v if vec else lib().fvk_assemble_s
+    fn = (lib().fvk_assemble_vc if compact else lib().fvk_assemble_v) if vec else lib().fvk_assemble_s
     check(fn(mesh.handle, C.c_int(len(terms)), arr, bf, ptr(values), ptr(rhs), ptr(bcMatrix), ptr(bcRhs),
              C.c_int(1 if accumulate else 0), _stream()))
     _count()
@@ -190,7 +192,9 @@ def bc_coeff_indices(mesh, matrixIdxs, rhsIdxs):
 
 # ---- PISO glue -----------------------------------------------------------------------------------
 def rAU_HbyA(mesh, valuesV, rhsV, U, rAU, HbyA=None):
-    check(lib().fvk_rAU_HbyA(mesh.handle, ptr(valuesV), ptr(rhsV), ptr(U), ptr(rAU), ptr(HbyA), _stream()))
+    """valuesV: Vec3[nnz] (reference layout) or double[nnz] (compact momentum matrix)"""
+    fn = lib().fvk_rAU_HbyA_c if valuesV.ndim == 1 else lib().fvk_rAU_HbyA
+    check(fn(mesh.handle, ptr(valuesV), ptr(rhsV), ptr(U), ptr(rAU), ptr(HbyA), _stream()))
     _count()
 
 

@@ -6,6 +6,7 @@ from __future__ import annotations
 import torch
 
 from . import dsl, fvcc, la, ops
+from . import mesh as _m
 from .mesh import MeshDesc, PATCHES_CAVITY2D, PATCHES_CAVITY3D, UnstructuredMesh
 
 
@@ -65,7 +66,8 @@ def updateVelocity(HbyA, rAU, p, U, gradP=None):
 # tutorials/cavity/system/{fvSchemes,fvSolution}
 CAVITY_FVSCHEMES = {"ddtSchemes": {"type": "backwardEuler"}, "divSchemes": {"div(phi,U)": "Gauss linear"},
                     "laplacianSchemes": {"laplacian(nu,U)": "Gauss linear uncorrected", "laplacian(rAUf,p)": "Gauss linear uncorrected"}}
-CAVITY_FVSOLUTION = {"solvers": {"p": {"solver": "PCG", "preconditioner": "DIC", "tolerance": 1e-6, "relTol": 0.0}},
+CAVITY_FVSOLUTION = {"solvers": {"p": {"solver": "PCG", "preconditioner": "DIC", "tolerance": 1e-6, "relTol": 0.0},
+                                 "U": {"solver": "smoothSolver", "smoother": "symGaussSeidel", "tolerance": 1e-5, "relTol": 0.0}},
                      "PISO": {"nCorrectors": 2, "nNonOrthogonalCorrectors": 0, "momentumPredictor": False, "pRefCell": 0, "pRefValue": 0.0}}
 
 
@@ -77,12 +79,17 @@ def cavity_desc(n, three_d=False, L=0.1):
     return MeshDesc.block(n, n, 1, L, L, 0.1 * L, patches=PATCHES_CAVITY2D)
 
 
+def mesh_rows_in_stencil_order(mesh) -> bool:
+    """the compact momentum matrix needs fvk_rAU_HbyA_c, i.e. CSR rows laid out like the stencil (any mesh in OpenFOAM face order)"""
+    return bool(mesh.size(_m.ROWS_IN_STENCIL_ORDER))
+
+
 class IcoFoam:
     """neoIcoFoam (examples/neoIcoFoam/neoIcoFoam.cpp) on a lid-driven cavity: U = (1 0 0) on movingWall, noSlip on
     fixedWalls, p zeroGradient everywhere (tutorials/cavity/0.orig/{U,p}), nu uniform, momentumPredictor no."""
 
     def __init__(self, mesh: UnstructuredMesh, nu=0.01, dt=1e-4, fvSolution=None, fvSchemes=None, comm=None,
-                 lid=(1.0, 0.0, 0.0), history=False, check_every=8, graphs=True):
+                 lid=(1.0, 0.0, 0.0), history=False, check_every=8, graphs=True, compact_momentum=True):
         self.mesh = mesh
         fvSolution = fvSolution or CAVITY_FVSOLUTION
         self.rt = dsl.RunTime(mesh, dt, 0.0, fvSchemes or CAVITY_FVSCHEMES, fvSolution, comm, check_every, history)
@@ -100,31 +107,48 @@ class IcoFoam:
         self.rAUf = fvcc.SurfaceField(mesh, "rAUf", 1)
         self.phiHbyA = fvcc.SurfaceField(mesh, "phiHbyA", 1)
         self.gradP = torch.empty((mesh.nCells, 3), dtype=torch.float64, device="cuda")
-        self.Uls = la.LinearSystem(mesh, 3, zero=False)
+        self.Uls = la.LinearSystem(mesh, 3, zero=False, compact=compact_momentum and mesh_rows_in_stencil_order(mesh))
         self.pls = la.LinearSystem(mesh, 1, zero=False)
         self.linear = fvcc.SurfaceInterpolation(mesh, "linear")
         self.solver = la.Solver(fvSolution["solvers"]["p"], comm=comm, check_every=check_every, history=history)
-        self.stats = []
+        # momentumPredictor yes (neoIcoFoam.cpp:100-103): the Vec3 momentum system, component by component, with the solver
+        # mapFvSolution gives for `U` (tutorials/cavity/system/fvSolution: smoothSolver -> solver::Bicgstab + scalar Jacobi)
+        self.Usolver = (la.Solver(fvSolution["solvers"]["U"], comm=comm, check_every=check_every)
+                        if self.piso.get("momentumPredictor", False) else None)
+        self.stats, self.Ustats = [], None
+        from ._capi import lib
+        self._co = torch.empty(2, dtype=torch.float64, device="cuda")
+        self._coScratch = torch.empty(lib().fvk_conum_scratch_bytes(mesh.handle) // 8, dtype=torch.float64, device="cuda")
         self.coNum = None
         self.graphs, self._captured, self._nsteps = bool(graphs), None, 0
 
-    def _halo(self, t):
-        if self.rt.comm is not None:
-            self.rt.comm.halo_exchange(t)
+    def _halo(self, *ts):
+        """processor-boundary exchange of one or several cell fields (one exchange for all of them)"""
+        comm = self.rt.comm
+        if comm is None:
+            return
+        if len(ts) == 1:
+            comm.halo_exchange(ts[0])
+        else:
+            comm.halo_exchange_multi(list(ts))
 
-    # ---- the step in three kinds of segments; everything except the linear solver is plain kernel launches ----------
-    def _pre(self, first: bool):
-        """neoIcoFoam.cpp:84-153 up to (not including) pEqn.solve's linear solver."""
-        rt, mesh, U, p, phi = self.rt, self.mesh, self.U, self.p, self.phi
-        if first:
-            U.oldTime().internal.copy_(U.internal)                         # neoIcoFoam.cpp:84-85
-            self.coNum = ops.conum(mesh, phi.internal, rt.dt)              # :87 (device scalars; no host sync here)
-            self._halo(U.internal)
-            self._UEqn = dsl.PDESolver(dsl.imp.ddt(U) + dsl.imp.div(phi, U) - dsl.imp.laplacian(self.nu, U), U, rt, ls=self.Uls)
-            self._UEqn.assemble()                                          # momentumPredictor no (:100-109)
+    # ---- the step in segments; everything except the linear solvers is plain kernel launches --------------------------
+    def _momentum(self):
+        """neoIcoFoam.cpp:84-109 up to the momentum solve: old time level, CoNum, UEqn assembly."""
+        rt, mesh, U, phi = self.rt, self.mesh, self.U, self.phi
+        U.oldTime().internal.copy_(U.internal)                             # neoIcoFoam.cpp:84-85
+        self.coNum = ops.conum(mesh, phi.internal, rt.dt, self._co, self._coScratch)  # :87 (device scalars; no host sync here)
+        if self._nsteps == 0:
+            self._halo(U.internal)  # later steps: the ghosts are current since the exchange that ended the previous step
+        self._UEqn = dsl.PDESolver(dsl.imp.ddt(U) + dsl.imp.div(phi, U) - dsl.imp.laplacian(self.nu, U), U, rt, ls=self.Uls)
+        self._UEqn.assemble()                                              # :94-98 / :105-108
+
+    def _pre(self):
+        """neoIcoFoam.cpp:112-153: one PISO corrector up to (not including) pEqn.solve's linear solver."""
+        U, p = self.U, self.p
         rAU, HbyA = computeRAUandHByA(self._UEqn, self.rAU, self.HbyA)     # :114
         constrainHbyA(U, p, HbyA)                                          # :115
-        self._halo(rAU.internal); self._halo(HbyA.internal)
+        self._halo(rAU.internal, HbyA.internal)
         self.linear.interpolate(rAU, self.rAUf)                            # :117-124
         flux(HbyA, self.phiHbyA)                                           # :126
         self._p_prepare()
@@ -135,7 +159,7 @@ class IcoFoam:
         self._pEqn = dsl.PDESolver(dsl.imp.laplacian(self.rAUf, p) - dsl.exp.div(self.phiHbyA), p, rt, ls=self.pls)
         if self.piso.get("pRefCell", -1) >= 0 and (rt.comm is None or rt.comm.rank == self.piso.get("pRefRank", 0)):
             self._pEqn.setReference(self.piso["pRefCell"], self.piso["pRefValue"])  # :150-153
-        self._pEqn.prepare()
+        self._pEqn.prepare(exchange_guess=False)  # the linear solver exchanges the ghosts of its initial guess itself
 
     def _post(self, last_nonorth: bool = True):
         """neoIcoFoam.cpp:156-167 after the linear solver."""
@@ -148,18 +172,25 @@ class IcoFoam:
             U.correctBoundaryConditions()                                  # :167
             self._halo(U.internal)
 
-    def _segments(self):
-        """The kernel-only parts of a step between the linear solves, merged: [pre] solve [post + pre] solve ... [post].
-        Each bracket is one CUDA graph once captured."""
+    def _plan(self):
+        """One time step as a list of kernel-only segments (each becomes one CUDA graph) separated by the linear solves:
+        [momentum] (solve U) [pre] solve p [post + pre] solve p ... [post]."""
         nC, nN = self.piso["nCorrectors"], self.piso["nNonOrthogonalCorrectors"]
-        segs, cur = [], []
+        plan, cur = [], [self._momentum]
+        if self.piso.get("momentumPredictor", False):
+            plan += [("kernels", cur), ("solveU",)]                        # :100-103
+            cur = [self._after_momentum_solve]
         for c in range(nC):
             for k in range(nN + 1):
-                cur.append((lambda c=c: self._pre(c == 0)) if k == 0 else self._p_prepare)
-                segs.append(cur)
+                cur.append(self._pre if k == 0 else self._p_prepare)
+                plan += [("kernels", cur), ("solveP",)]
                 cur = [lambda k=k: self._post(k == nN)]
-        segs.append(cur)
-        return [(lambda fs=fs: [f() for f in fs]) for fs in segs]
+        plan.append(("kernels", cur))
+        return plan
+
+    def _after_momentum_solve(self):
+        self.U.correctBoundaryConditions()
+        self._halo(self.U.internal)
 
     def _graphs_allowed(self):
         comm = self.rt.comm
@@ -172,7 +203,8 @@ class IcoFoam:
         the peer-memory halo kernels keep their sequence numbers on the device), which removes ~60 host-driven launches
         per step. `graphs=False` or the NCCL transport keep the eager path."""
         rt = self.rt
-        segs = self._segments()
+        plan = self._plan()
+        segs = [item[1] for item in plan if item[0] == "kernels"]
         use_graphs = self._graphs_allowed() and self._nsteps >= 2
         if use_graphs and self._captured is None:
             try:
@@ -181,7 +213,8 @@ class IcoFoam:
                 for seg in segs:
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g):
-                        seg()
+                        for f in seg:
+                            f()
                     captured.append(g)
                 self._captured = captured
             except Exception as e:  # not capturable on this setup: stay eager, loudly
@@ -189,12 +222,22 @@ class IcoFoam:
                 print(f"[piso] CUDA-graph capture failed ({e!r}); continuing without graphs", file=sys.stderr)
                 self.graphs, self._captured, use_graphs = False, None, False
                 torch.cuda.synchronize()
-        run = (lambda k: self._captured[k].replay()) if (use_graphs and self._captured) else (lambda k: segs[k]())
+        replay = use_graphs and self._captured
         self.stats.append([])
-        for k in range(len(segs) - 1):
-            run(k)
-            self.stats[-1].append(self.solver.solve(self.pls, self.p.internal))   # :155
-        run(len(segs) - 1)
+        self.Ustats = None
+        k = 0
+        for item in plan:
+            if item[0] == "kernels":
+                if replay:
+                    self._captured[k].replay()
+                else:
+                    for f in item[1]:
+                        f()
+                k += 1
+            elif item[0] == "solveU":
+                self.Ustats = self.Usolver.solve(self.Uls, self.U.internal)        # :102 UEqn.solve()
+            else:
+                self.stats[-1].append(self.solver.solve(self.pls, self.p.internal))   # :155
         rt.t += rt.dt
         self._nsteps += 1
         return self.stats[-1]

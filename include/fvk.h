@@ -178,6 +178,8 @@ int fvk_mesh_destroy(fvk_mesh* mesh);
 enum fvk_mesh_field {
     /* sizes */
     FVK_N_CELLS = 0, FVK_N_INTERNAL_FACES, FVK_N_BOUNDARY_FACES, FVK_N_PATCHES, FVK_NNZ, FVK_N_OWNED_CELLS,
+    /* plan properties (0 / 1): CSR rows laid out like the cell's stencil; block topology proven (index-free kernels) */
+    FVK_ROWS_IN_STENCIL_ORDER, FVK_AFFINE_TOPOLOGY,
     /* device arrays, reference order */
     FVK_CELL_VOLUMES = 16, FVK_CELL_CENTRES, FVK_FACE_AREAS, FVK_FACE_CENTRES, FVK_MAG_FACE_AREAS,
     FVK_FACE_OWNER, FVK_FACE_NEIGHBOUR, FVK_FACE_CELLS,
@@ -324,6 +326,14 @@ int fvk_assemble_s(const fvk_mesh* mesh, int nTerms, const fvk_term* terms_h, co
 int fvk_assemble_v(const fvk_mesh* mesh, int nTerms, const fvk_term* terms_h, const fvk_bfield* bd,
                    double* values, double* rhs, double* bcMatrix, double* bcRhs, int accumulate,
                    fvk_stream stream);
+/* Compact Vec3 system (new here; an HBM-layout choice, not a reference type): every implicit operator multiplies its
+ * coefficient by one<Vec3>() (gaussGreenDiv.cpp:200,209), so the three components of a matrix entry are
+ * identical -- valuesCompact double[nnz] stores each entry once (a third of the traffic of LinearSystem<Vec3>::values);
+ * rhs, bcMatrix and bcRhs stay Vec3. fvk_expand_vec3 materialises the reference layout Vec3[nnz] from it, bit for bit. */
+int fvk_assemble_vc(const fvk_mesh* mesh, int nTerms, const fvk_term* terms_h, const fvk_bfield* bd,
+                    double* valuesCompact, double* rhs, double* bcMatrix, double* bcRhs, int accumulate,
+                    fvk_stream stream);
+int fvk_expand_vec3(int64_t n, const double* compact, double* outV, fvk_stream stream);
 /* BoundaryCoefficients::matrixIdxs / rhsIdxs as createEmptyLinearSystem fills them
  * (linearSystem.hpp:163-174; matrixIdxs = celli + diagOffset[celli], sic). */
 int fvk_bc_coeff_indices(const fvk_mesh* mesh, int32_t* matrixIdxs, int32_t* rhsIdxs,
@@ -422,6 +432,9 @@ int fvk_solver_solve(fvk_solver* solver, const int32_t* rowOffs, const int32_t* 
  * of neoIcoFoam.cpp:100-103 needs). stats3_h receives one fvk_solver_stats per component. */
 int fvk_solver_solve_vec3(fvk_solver* solver, int64_t nnz, const int32_t* rowOffs, const int32_t* colIdxs, const double* valuesV,
                           const double* bV, double* xV, fvk_solver_stats* stats3_h, fvk_stream stream);
+/* same with the compact matrix of fvk_assemble_vc (double[nnz], used in place: no component extraction) */
+int fvk_solver_solve_vec3c(fvk_solver* solver, const int32_t* rowOffs, const int32_t* colIdxs, const double* valuesCompact,
+                           const double* bV, double* xV, fvk_solver_stats* stats3_h, fvk_stream stream);
 
 /* ------------------------------------------------------------------------------------------------
  * PISO pressure-velocity coupling (FoamAdapter src/algorithms/pressureVelocityCoupling.cpp) and the
@@ -434,6 +447,9 @@ int fvk_solver_solve_vec3(fvk_solver* solver, int64_t nnz, const int32_t* rowOff
  * Boundary values follow from fvk_correct_boundary_conditions with FVK_BC_EXTRAPOLATED. */
 int fvk_rAU_HbyA(const fvk_mesh* mesh, const double* valuesV, const double* rhsV, const double* U,
                  double* rAU, double* HbyA, fvk_stream stream);
+/* same, from the compact momentum matrix of fvk_assemble_vc (needs a mesh whose CSR rows are in stencil order) */
+int fvk_rAU_HbyA_c(const fvk_mesh* mesh, const double* valuesCompact, const double* rhsV, const double* U,
+                   double* rAU, double* HbyA, fvk_stream stream);
 /* constrainHbyA (:14-36): dstB = srcB on the patches with patchMask_h[p] != 0 (the non-assignable
  * patches of U). patchMask_h is HOST [nPatches]. */
 int fvk_copy_patches(const fvk_mesh* mesh, int ncomp, const int32_t* patchMask_h, const double* srcB,
@@ -475,6 +491,10 @@ int fvk_comm_set_halo(fvk_comm* comm, int32_t nOwned, int32_t nNeighbours, const
                       const int32_t* sendOffsets_h, const int32_t* sendCells_h, const int32_t* recvOffsets_h);
 /* pack + one NCCL send/recv group on `stream`; field has (nOwned + nGhost) * ncomp doubles */
 int fvk_comm_halo_exchange(fvk_comm* comm, double* field, int ncomp, fvk_stream stream);
+/* several cell fields (up to 4, at most 8 components together) in ONE exchange: one push kernel, one flag per neighbour, one
+ * wait (peer-memory transport; over NCCL it is one send/recv group per field). PISO exchanges rAU + HbyA this way. */
+typedef struct fvk_halo_field { double* field; int32_t ncomp; } fvk_halo_field;
+int fvk_comm_halo_exchange_multi(fvk_comm* comm, int nFields, const fvk_halo_field* fields_h, fvk_stream stream);
 int fvk_comm_allreduce_sum(fvk_comm* comm, double* data_d, int count, fvk_stream stream);
 int fvk_comm_allreduce_max(fvk_comm* comm, double* data_d, int count, fvk_stream stream);
 /* Peer-memory transport (NVLink/NVSwitch P2P through CUDA IPC), optional, after fvk_comm_set_halo: every rank exports

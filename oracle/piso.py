@@ -7,17 +7,18 @@ from __future__ import annotations
 
 import numpy as np
 
-from .cpu import Mesh, cg
+from .cpu import Mesh, bicgstab, cg
 
 FIXED_VALUE, FIXED_GRADIENT, EXTRAPOLATED = 1, 2, 3
 
 
 class IcoFoamOracle:
     def __init__(self, om: Mesh, nu=0.01, dt=1e-4, lid=(1.0, 0.0, 0.0), nCorrectors=2, tolerance=1e-6, relTol=0.0,
-                 maxIter=1000, pRefCell=0, pRefValue=0.0, jacobi=True):
+                 maxIter=1000, pRefCell=0, pRefValue=0.0, jacobi=True, momentumPredictor=False, Utolerance=1e-5):
         self.om, self.nu, self.dt = om, nu, dt
         self.nCorr, self.tol, self.relTol, self.maxIter, self.pRefCell, self.pRefValue, self.jacobi = (
             nCorrectors, tolerance, relTol, maxIter, pRefCell, pRefValue, jacobi)
+        self.momentumPredictor, self.Utol, self.Ustats = momentumPredictor, Utolerance, []
         nP = len(om.patchOffsets) - 1
         self.Ukinds = [FIXED_VALUE] * nP
         self.Uconsts = [list(lid)] + [[0.0, 0.0, 0.0]] * (nP - 1)
@@ -37,6 +38,17 @@ class IcoFoamOracle:
         om.div_imp(Uls, self.phi, self.Ubd, 0, 1.0, None)
         om.laplacian_imp(Uls, nuF, self.Ubd, -1.0, None)
         om.ddt_imp(Uls, oldU, dt, 1.0, None)
+        if self.momentumPredictor:
+            # neoIcoFoam.cpp:100-103 UEqn.solve(): the Vec3 system component by component (identical matrix components, A.3)
+            # with what mapFvSolution makes of fvSolution.solvers.U: solver::Bicgstab + scalar Jacobi, absolute norm 1e-5
+            vals0 = np.ascontiguousarray(Uls["values"][:, 0])
+            self.Ustats = []
+            for c in range(3):
+                x, st, _ = bicgstab(om.rowOffs, om.colIdxs, vals0, np.ascontiguousarray(Uls["rhs"][:, c]), np.ascontiguousarray(self.U[:, c]),
+                                    jacobi=True, max_iter=1000, rel_tol=0.0, abs_tol=self.Utol)
+                self.U[:, c] = x
+                self.Ustats.append(st)
+            self.Ubd = om.correct_bcs(self.Ukinds, self.Uconsts, self.U)
         out = []
         for _ in range(self.nCorr):
             rAU = om.rAU(Uls["values"])

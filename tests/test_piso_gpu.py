@@ -141,3 +141,69 @@ def test_pdesolver_matches_dsl_solve_sequence(case):
     xo, so, ho = om.cg(ls["values"], ls["rhs"], np.zeros(om.nC), jacobi=True, max_iter=1000, rel_tol=0.0, abs_tol=1e-10, max_hist=1002)
     assert abs(st.numIter - so["numIter"]) <= 1
     assert np.abs(host(p.internal) - xo).max() <= 1e-7 * max(np.abs(xo).max(), 1e-30)
+
+
+# ---- compact Vec3 momentum system (values stored once) ------------------------------------------------------------------
+@pytest.mark.parametrize("dims", [(7, 5, 4), (40, 11, 7), (33, 9, 3)])
+def test_compact_momentum_system_equals_the_vec3_layout(dims):
+    """fvk_assemble_vc / fvk_rAU_HbyA_c / valuesVec3 against the reference layout (fvk_assemble_v / fvk_rAU_HbyA) and the
+    oracle, bit for bit; both kernel families (index-free and stencil-driven) and the old face-walk kernel (variant 5)."""
+    import ctypes as C
+    from foamadapter_b200._capi import lib
+    d = M.MeshDesc.block(*dims, 0.7, 0.3, 0.9)
+    gm, om = M.UnstructuredMesh(d), OMesh.from_desc(d)
+    rng = np.random.default_rng(5)
+    U = fvcc.VolumeField(gm, "U", 3, [("fixedValue", (1.0, 0.0, 0.0)), ("noSlip", 0.0), ("zeroGradient", 0.0)])
+    U_h = rng.uniform(-1, 1, (om.nC, 3))
+    U.internal.copy_(dev(U_h)); U.correctBoundaryConditions()
+    flux, nu, old = rng.uniform(-1, 1, om.nF), rng.uniform(0.5, 1.5, om.nF), rng.uniform(-1, 1, (om.nC, 3))
+    terms = [dict(kind=ops.TERM_DIV, scheme=0, coeff=1.0, faceField=dev(flux)), dict(kind=ops.TERM_LAPLACIAN, coeff=-1.0, faceField=dev(nu)),
+             dict(kind=ops.TERM_DDT, coeff=1.0, cellField=dev(old), dt=0.01)]
+    ref = la.LinearSystem(gm, 3, zero=False)
+    ops.assemble(gm, terms, U.boundary, ref.values, ref.rhs, ref.bcMatrix, ref.bcRhs)
+    rAU0, H0 = torch.empty(om.nC, dtype=torch.float64, device="cuda"), torch.empty((om.nC, 3), dtype=torch.float64, device="cuda")
+    lib().fvk_set_variant(C.c_int(5))          # the face-walk kernel (any mesh)
+    ops.rAU_HbyA(gm, ref.values, ref.rhs, U.internal, rAU0, H0)
+    lib().fvk_set_variant(C.c_int(0))
+    Ho = om.HbyA(host(ref.values), host(ref.rhs), om.rAU(host(ref.values)), U_h)
+    assert np.array_equal(host(H0), Ho)
+    for affine in (1, 0):
+        lib().fvk_set_affine(C.c_int(affine))
+        cls = la.LinearSystem(gm, 3, zero=False, compact=True)
+        assert cls.values.shape == (gm.nnz,)
+        cls.values.fill_(float("nan"))
+        ops.assemble(gm, terms, U.boundary, cls.values, cls.rhs, cls.bcMatrix, cls.bcRhs)
+        assert torch.equal(cls.valuesVec3(), ref.values) and torch.equal(cls.rhs, ref.rhs)
+        assert torch.equal(cls.bcMatrix, ref.bcMatrix) and torch.equal(cls.bcRhs, ref.bcRhs)
+        for vals in (cls.values, ref.values):   # row-walk kernel on both layouts
+            rAU, H = torch.empty_like(rAU0), torch.empty_like(H0)
+            ops.rAU_HbyA(gm, vals, ref.rhs, U.internal, rAU, H)
+            assert torch.equal(rAU, rAU0) and torch.equal(H, H0)
+    lib().fvk_set_affine(C.c_int(1))
+
+
+def test_piso_step_is_identical_with_and_without_the_compact_momentum_matrix():
+    d = piso.cavity_desc(12, True)
+    a = piso.IcoFoam(M.UnstructuredMesh(d), nu=0.01, dt=5e-4, compact_momentum=True, graphs=False)
+    b = piso.IcoFoam(M.UnstructuredMesh(d), nu=0.01, dt=5e-4, compact_momentum=False, graphs=False)
+    assert a.Uls.compact and not b.Uls.compact
+    for _ in range(3):
+        a.step(); b.step()
+    assert torch.equal(a.U.internal, b.U.internal) and torch.equal(a.p.internal, b.p.internal) and torch.equal(a.phi.internal, b.phi.internal)
+
+
+def test_momentum_predictor_step_matches_the_oracle():
+    """momentumPredictor yes (neoIcoFoam.cpp:100-103): UEqn solved with BiCGStab + scalar Jacobi, component
+    by component, before the PISO correctors."""
+    import copy
+    d = piso.cavity_desc(10, True)
+    sol = copy.deepcopy(piso.CAVITY_FVSOLUTION)
+    sol["PISO"]["momentumPredictor"] = True
+    app = piso.IcoFoam(M.UnstructuredMesh(d), nu=0.01, dt=5e-3, fvSolution=sol, graphs=True)
+    ref = IcoFoamOracle(OMesh.from_desc(d), nu=0.01, dt=5e-3, momentumPredictor=True)
+    for step in range(4):   # steps 3 and 4 replay the CUDA-graph segments around the three linear solves
+        app.step(); ref.step()
+        assert [abs(a.numIter - b["numIter"]) <= 1 for a, b in zip(app.Ustats, ref.Ustats)] == [True] * 3
+    assert any(s["numIter"] > 0 for s in ref.Ustats)
+    assert np.abs(host(app.U.internal) - ref.U).max() <= 1e-7 * np.abs(ref.U).max()
+    assert np.abs(host(app.p.internal) - ref.p).max() <= 1e-6 * np.abs(ref.p).max()
