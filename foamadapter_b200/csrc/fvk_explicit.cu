@@ -237,12 +237,19 @@ struct SurfIntOp // surfaceIntegrate.cpp:26-41
 };
 
 // ---- scaling + store ---------------------------------------------------------------------------
+// internal epilogue modes (not part of the C ABI): the operator's result feeds the next cell-wise step without a round
+// trip through memory. FVK_EPI_UPDATE_VELOCITY (grad): out = epiA - (s * sum) * epiB   = updateVelocity's U = HbyA - rAU gradP
+// (pressureVelocityCoupling.cpp:199-213); FVK_EPI_RHS_SUB (surfaceIntegrate / div / laplacian): out -= (0 + s * sum) * V, i.e.
+// Operator::explicitOperation into a zeroed source followed by dsl::solve's rhs -= source * V (dsl/solver.hpp:73-77).
+enum { FVK_EPI_UPDATE_VELOCITY = 16, FVK_EPI_RHS_SUB = 17 };
 struct Scaling
 {
     const double* __restrict__ V;    // cell volumes
     const double* __restrict__ view; // Coeff view or nullptr
     double coeff;
     bool invVolOnly; // grad: res *= 1 / V
+    const double* epiA = nullptr;    // FVK_EPI_UPDATE_VELOCITY: HbyA (Vec3)
+    const double* epiB = nullptr;    // FVK_EPI_UPDATE_VELOCITY: rAU
     __device__ __forceinline__ double at(int c) const
     {
         if (invVolOnly) return 1 / V[c];
@@ -252,10 +259,14 @@ struct Scaling
 };
 
 template <class VT>
-__device__ __forceinline__ void finish(double* __restrict__ out, int c, typename VT::T acc, double s, int mode)
+__device__ __forceinline__ void finish(double* __restrict__ out, int c, typename VT::T acc, double s, int mode, const Scaling& sc)
 {
     if (mode == FVK_ADD)
         VT::st(out, c, VT::add(VT::ld(out, c), VT::mul(s, acc)));
+    else if (mode == FVK_EPI_UPDATE_VELOCITY)
+        VT::st(out, c, VT::sub(VT::ld(sc.epiA, c), VT::mul(sc.epiB[c], VT::mul(s, acc))));
+    else if (mode == FVK_EPI_RHS_SUB)
+        VT::st(out, c, VT::sub(VT::ld(out, c), VT::mul(sc.V[c], VT::add(VT::zero(), VT::mul(s, acc)))));
     else
         VT::st(out, c, VT::mul(s, acc));
 }
@@ -287,7 +298,7 @@ __device__ __forceinline__ void gather_cell(const Op& op, const Scaling& sc, int
             acc = VT::add(acc, op.boundary(f, f - nI, c));
         }
     }
-    finish<VT>(out, c, acc, sc.at(c), mode);
+    finish<VT>(out, c, acc, sc.at(c), mode, sc);
 }
 
 template <class Op>
@@ -344,7 +355,7 @@ k_gather_plan(Op op, Scaling sc, int nC, int nI, const int* __restrict__ seg, co
             if (e + k < e1) acc = VT::add(acc, v[k]);
         }
     }
-    finish<VT>(out, c, acc, s, mode);
+    finish<VT>(out, c, acc, s, mode, sc);
 }
 
 // ---- variant 6 (opt-in, owner-sorted meshes): TMA-staged tile kernel, optionally double-buffered -------------
@@ -573,7 +584,7 @@ k_gather_tile(Op op, Scaling sc, FvkTilePlan tp, int nI, double* __restrict__ ou
             double s;
             if (sc.invVolOnly) s = 1 / vol;
             else s = (sc.view ? sc.view[c] * sc.coeff : sc.coeff) / vol;
-            finish<VT>(out, c, acc, s, mode);
+            finish<VT>(out, c, acc, s, mode, sc);
         }
         __syncthreads(); // stage `cur` and sflux are free again
         if (NSTAGE == 1 && producer && t + G < tp.nTiles)
@@ -790,7 +801,7 @@ k_gather_brick(Op op, Scaling sc, FvkBrickPlan bp, int nI, const int* __restrict
     double s;
     if (sc.invVolOnly) s = 1 / vol;
     else s = (sc.view ? sc.view[cell] * sc.coeff : sc.coeff) / vol;
-    finish<VT>(out, cell, acc, s, mode);
+    finish<VT>(out, cell, acc, s, mode, sc);
 }
 
 // ---- affine kernel: block-structured meshes whose topology the plan proved (FvkBrickGeom) ----------------------------
@@ -909,7 +920,7 @@ k_gather_affine(Op op, Scaling sc, FvkBrickGeom g, double* __restrict__ out, int
     double s;
     if (sc.invVolOnly) s = 1 / vol;
     else s = (sc.view ? sc.view[cell] * sc.coeff : sc.coeff) / vol;
-    finish<VT>(out, cell, acc, s, mode);
+    finish<VT>(out, cell, acc, s, mode, sc);
 }
 
 template <class Op, int TB, int MINB, bool XDEFER>
@@ -990,7 +1001,7 @@ __host__ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr
 template <class Op>
 int launch_gather(const fvk_mesh* m, Op op, Scaling sc, double* out, int mode, fvk_stream stream)
 {
-    if (mode != FVK_SET && mode != FVK_ACC_SCALE && mode != FVK_ADD)
+    if (mode != FVK_SET && mode != FVK_ACC_SCALE && mode != FVK_ADD && mode != FVK_EPI_UPDATE_VELOCITY && mode != FVK_EPI_RHS_SUB)
         return fvk_fail(FVK_EINVAL, "bad mode %d", mode);
     const int nC = m->nOwned;
     const int nI = m->nInternalFaces;
@@ -1204,6 +1215,7 @@ static int div_impl(const fvk_mesh* m, int scheme, const double* faceFlux, const
 {
     if (!m || !faceFlux || !phi || !out || (m->nBoundaryFaces && !phiB))
         return fvk_fail(FVK_EINVAL, "fvk_div: null argument");
+    if (mode != FVK_SET && mode != FVK_ACC_SCALE && mode != FVK_ADD) return fvk_fail(FVK_EINVAL, "fvk_div: bad mode %d", mode);
     Scaling sc {m->V, view, coeff, false};
     if (scheme == FVK_LINEAR)
         return launch_gather(m, DivOp<VT, FVK_LINEAR> {faceFlux, m->weights, phi, phiB}, sc, out, mode, s);
@@ -1223,9 +1235,31 @@ extern "C" int fvk_div_v(const fvk_mesh* m, int scheme, const double* faceFlux, 
     return div_impl<S3>(m, scheme, faceFlux, phi, phiB, coeff, view, out, mode, s);
 }
 
+// updateVelocity (pressureVelocityCoupling.cpp:199-213) fused with the gradient it consumes: U = HbyA - rAU * grad(p), no gradP
+// round trip through memory; same arithmetic as fvk_grad_s followed by fvk_update_velocity
+extern "C" int fvk_update_velocity_grad(const fvk_mesh* m, const double* HbyA, const double* rAU, const double* p, const double* pB,
+                                        double* U, fvk_stream s)
+{
+    if (!m || !HbyA || !rAU || !p || !U || (m->nBoundaryFaces && !pB)) return fvk_fail(FVK_EINVAL, "fvk_update_velocity_grad: null argument");
+    Scaling sc {m->V, nullptr, 1.0, true};
+    sc.epiA = HbyA; sc.epiB = rAU;
+    return launch_gather(m, GradOp {m->Sf, m->weights, p, pB}, sc, U, FVK_EPI_UPDATE_VELOCITY, s);
+}
+// dsl::solve's explicit source of ONE surfaceIntegrate operator folded into the right-hand side: rhs -= (0 + op) * V
+// (Operator::explicitOperation into a zeroed source, then dsl/solver.hpp:73-77), no source vector in memory
+extern "C" int fvk_rhs_sub_surface_integrate_s(const fvk_mesh* m, const double* flux, double coeff, const double* view, double* rhs,
+                                               fvk_stream s)
+{
+    if (!m || !flux || !rhs) return fvk_fail(FVK_EINVAL, "fvk_rhs_sub_surface_integrate_s: null argument");
+    Scaling sc {m->V, view, coeff, false};
+    return launch_gather(m, SurfIntOp<S1> {flux}, sc, rhs, FVK_EPI_RHS_SUB, s);
+}
+
+#define FVK_PUBLIC_MODE(mode) do { if ((mode) != FVK_SET && (mode) != FVK_ACC_SCALE && (mode) != FVK_ADD) return fvk_fail(FVK_EINVAL, "%s: bad mode %d", __func__, (mode)); } while (0)
 extern "C" int fvk_grad_s(const fvk_mesh* m, const double* phi, const double* phiB, double* out, int mode, fvk_stream s)
 {
     if (!m || !phi || !out || (m->nBoundaryFaces && !phiB)) return fvk_fail(FVK_EINVAL, "fvk_grad_s: null argument");
+    FVK_PUBLIC_MODE(mode);
     if (mode == FVK_ADD) return fvk_fail(FVK_EINVAL, "fvk_grad_s: mode FVK_ADD not defined for grad");
     Scaling sc {m->V, nullptr, 1.0, true};
     return launch_gather(m, GradOp {m->Sf, m->weights, phi, phiB}, sc, out, mode, s);
@@ -1235,6 +1269,7 @@ extern "C" int fvk_laplacian_s(const fvk_mesh* m, const double* phi, const doubl
                                const double* view, double* out, int mode, fvk_stream s)
 {
     if (!m || !phi || !out || (m->nBoundaryFaces && !phiB)) return fvk_fail(FVK_EINVAL, "fvk_laplacian_s: null argument");
+    FVK_PUBLIC_MODE(mode);
     Scaling sc {m->V, view, coeff, false};
     return launch_gather(m, LaplacianOp<S1> {m->magSf, m->nonOrthDeltaCoeffs, phi, phiB}, sc, out, mode, s);
 }
@@ -1242,6 +1277,7 @@ extern "C" int fvk_laplacian_v(const fvk_mesh* m, const double* phi, const doubl
                                const double* view, double* out, int mode, fvk_stream s)
 {
     if (!m || !phi || !out || (m->nBoundaryFaces && !phiB)) return fvk_fail(FVK_EINVAL, "fvk_laplacian_v: null argument");
+    FVK_PUBLIC_MODE(mode);
     Scaling sc {m->V, view, coeff, false};
     return launch_gather(m, LaplacianOp<S3> {m->magSf, m->nonOrthDeltaCoeffs, phi, phiB}, sc, out, mode, s);
 }
@@ -1250,6 +1286,7 @@ extern "C" int fvk_surface_integrate_s(const fvk_mesh* m, const double* flux, do
                                        double* out, int mode, fvk_stream s)
 {
     if (!m || !flux || !out) return fvk_fail(FVK_EINVAL, "fvk_surface_integrate_s: null argument");
+    FVK_PUBLIC_MODE(mode);
     Scaling sc {m->V, view, coeff, false};
     return launch_gather(m, SurfIntOp<S1> {flux}, sc, out, mode, s);
 }
@@ -1257,6 +1294,7 @@ extern "C" int fvk_surface_integrate_v(const fvk_mesh* m, const double* flux, do
                                        double* out, int mode, fvk_stream s)
 {
     if (!m || !flux || !out) return fvk_fail(FVK_EINVAL, "fvk_surface_integrate_v: null argument");
+    FVK_PUBLIC_MODE(mode);
     Scaling sc {m->V, view, coeff, false};
     return launch_gather(m, SurfIntOp<S3> {flux}, sc, out, mode, s);
 }

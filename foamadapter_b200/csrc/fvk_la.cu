@@ -505,7 +505,12 @@ k_spmv(int nRows, const int* __restrict__ rowOffs, const int* __restrict__ colId
             const int r = r0 + threadIdx.x;
             if (MODE == 0) y[r] = sum;
             if (MODE == 1) y[r] = sum - b[r];
-            if (MODE == 2) y[r] = b[r] - sum;
+            if (MODE == 2)
+            {
+                const double br = b[r];
+                y[r] = br - sum;
+                acc[0] += br * br;
+            }
             if (MODE == 3)
             {
                 y[r] = sum;
@@ -530,6 +535,17 @@ k_spmv(int nRows, const int* __restrict__ rowOffs, const int* __restrict__ colId
                 acc[NV - 1] += sum * sum;
             }
         }
+    }
+    if (MODE == 2)
+    { // solver start-up: ||b||^2 next to r0 = b - A x (st == nullptr: plain residual)
+        if (!st) return;
+        double tot[NV];
+        if (grid_sum<NV>(acc, partial, counter, tot) && threadIdx.x == 0)
+        {
+            st->sums[3] = tot[0];
+            if (!distributed) st->normB = sqrt(tot[0]);
+        }
+        return;
     }
     if (MODE == 5 || MODE == 6)
     {
@@ -575,6 +591,15 @@ k_spmv(int nRows, const int* __restrict__ rowOffs, const int* __restrict__ colId
     }
 }
 
+// diagonal through the SparsityPattern's diagOffset (the attached mesh's own pattern): one entry per row instead of the row scan
+__global__ void __launch_bounds__(TB)
+k_extract_dinv_offs(int n, const int* __restrict__ rowOffs, const uint8_t* __restrict__ diagOffs, const double* __restrict__ values,
+                    double* __restrict__ dinv)
+{
+    const int r = blockIdx.x * TB + threadIdx.x;
+    if (r >= n) return;
+    dinv[r] = 1.0 / values[rowOffs[r] + diagOffs[r]];
+}
 __global__ void __launch_bounds__(TB)
 k_extract_dinv(int n, const int* __restrict__ rowOffs, const int* __restrict__ colIdxs, const double* __restrict__ values,
                double* __restrict__ dinv)
@@ -808,6 +833,7 @@ struct fvk_solver
     fvk_comm* comm = nullptr;
     SpmvAffine aff {0, 0, 0, 0}; // set by fvk_solver_attach_mesh
     const int32_t *affRowOffs = nullptr, *affColIdxs = nullptr; // the attached mesh's pattern: aff applies to these arrays only
+    const uint8_t* affDiagOffs = nullptr;                       // its diagOffset (Jacobi diagonal without a row scan)
     double *r2 = nullptr; // second residual buffer of the peer-memory mode
     double *rr = nullptr, *sB = nullptr, *tB = nullptr; // BiCGStab: shadow residual, s, t
     double *vals0 = nullptr, *bC = nullptr, *xC = nullptr; // Vec3 solves: component matrix / rhs / solution (lazy)
@@ -872,9 +898,21 @@ extern "C" int fvk_solver_attach_mesh(fvk_solver* sv, const fvk_mesh* m)
     sv->aff = (m && m->nOwned == sv->nRows && m->nCells == sv->nCols) ? mesh_affine(m) : SpmvAffine {0, 0, 0, 0};
     sv->affRowOffs = m ? m->rowOffs : nullptr;
     sv->affColIdxs = m ? m->colIdxs : nullptr;
+    sv->affDiagOffs = (m && m->nOwned == sv->nRows && m->nCells == sv->nCols) ? m->diagOffset : nullptr;
     return FVK_OK;
 }
 
+
+static int launch_dinv(fvk_solver* sv, const int32_t* rowOffs, const int32_t* colIdxs, const double* values, cudaStream_t st)
+{
+    const int n = sv->nRows;
+    if (sv->affDiagOffs && rowOffs == sv->affRowOffs && colIdxs == sv->affColIdxs)
+        k_extract_dinv_offs<<<(n + TB - 1) / TB, TB, 0, st>>>(n, rowOffs, sv->affDiagOffs, values, sv->dinv);
+    else
+        k_extract_dinv<<<(n + TB - 1) / TB, TB, 0, st>>>(n, rowOffs, colIdxs, values, sv->dinv);
+    FVK_LAUNCH_CHECK();
+    return FVK_OK;
+}
 
 // Pipelined stop polling shared by the solvers: check after 1, 2, 4, ... rounds up to `every`, then every `every`; the
 // state copy of check k is awaited only after the rounds up to check k+1 have been queued.
@@ -928,20 +966,17 @@ static int bicgstab_solve(fvk_solver* sv, const int32_t* rowOffs, const int32_t*
     FVK_CUDA(cudaMemsetAsync(p, 0, sizeof(double) * sv->nCols, st));
     FVK_CUDA(cudaMemsetAsync(v, 0, sizeof(double) * n, st));
     if (jacobi)
-    {
-        k_extract_dinv<<<(n + TB - 1) / TB, TB, 0, st>>>(n, rowOffs, colIdxs, values, sv->dinv);
-        FVK_LAUNCH_CHECK();
-    }
-    k_dot<false><<<gV, TB, 0, st>>>(n, b, b, &sv->state->sums[3], sv->partial, sv->counter);
+        if (int rc = launch_dinv(sv, rowOffs, colIdxs, values, st)) return rc;
+    if (dist)
+        if (int rc = fvk_comm_halo_exchange_impl(sv->comm, x, 1, st)) return rc;
+    // r = b - A x and ||b||^2 in one pass
+    k_spmv<2><<<gS, TB, 0, st>>>(n, rowOffs, colIdxs, values, x, b, r, sv->state, nullptr, nullptr, sv->partial, sv->counter, dm, nullptr, 0, sv->aff);
     FVK_LAUNCH_CHECK();
     if (dist)
     {
         if (int rc = fvk_comm_allreduce_sum_impl(sv->comm, &sv->state->sums[3], 1, st)) return rc;
-        if (int rc = fvk_comm_halo_exchange_impl(sv->comm, x, 1, st)) return rc;
+        k_set_normB<<<1, 1, 0, st>>>(sv->state);
     }
-    k_set_normB<<<1, 1, 0, st>>>(sv->state);
-    k_spmv<2><<<gS, TB, 0, st>>>(n, rowOffs, colIdxs, values, x, b, r, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0, sv->aff);
-    FVK_LAUNCH_CHECK();
     auto reduce = [&](int first, int count) -> int { return dist ? fvk_comm_allreduce_sum_impl(sv->comm, &sv->state->sums[first], count, st) : FVK_OK; };
     k_bicg_step3<true><<<gV, TB, 0, st>>>(n, sv->state, x, y, z, sB, tB, r, rr, sv->partial, sv->counter, sv->hist, dm);
     FVK_LAUNCH_CHECK();
@@ -1032,26 +1067,20 @@ extern "C" int fvk_solver_solve(fvk_solver* sv, const int32_t* rowOffs, const in
     init.maxIter = sv->cfg.maxIter; init.maxHist = wantHist;
     *sv->state_h = init;
     FVK_CUDA(cudaMemcpyAsync(sv->state, sv->state_h, sizeof(PcgState), cudaMemcpyHostToDevice, st));
+    // p of "iteration -1" is zero (p = z + beta p); p1 and q are fully written before they are read
     FVK_CUDA(cudaMemsetAsync(sv->p0, 0, sizeof(double) * sv->nCols, st));
-    FVK_CUDA(cudaMemsetAsync(sv->p1, 0, sizeof(double) * sv->nCols, st));
-    FVK_CUDA(cudaMemsetAsync(sv->q, 0, sizeof(double) * n, st));
     if (jacobi)
-    {
-        k_extract_dinv<<<(n + TB - 1) / TB, TB, 0, st>>>(n, rowOffs, colIdxs, values, sv->dinv);
-        FVK_LAUNCH_CHECK();
-    }
-    // ||b|| (the reference's "initial residual", ginkgo.hpp:143-144)
-    k_dot<false><<<gV, TB, 0, st>>>(n, b, b, &sv->state->sums[3], sv->partial, sv->counter);
+        if (int rc = launch_dinv(sv, rowOffs, colIdxs, values, st)) return rc;
+    if (dist)
+        if (int rc = fvk_comm_halo_exchange_impl(sv->comm, x, 1, st)) return rc;
+    // r = b - A x, fused with ||b||^2 (the reference's "initial residual" is ||b||, ginkgo.hpp:143-144)
+    k_spmv<2><<<gS, TB, 0, st>>>(n, rowOffs, colIdxs, values, x, b, sv->r, sv->state, nullptr, nullptr, sv->partial, sv->counter, dist ? 1 : 0, nullptr, 0, sv->aff);
     FVK_LAUNCH_CHECK();
     if (dist)
     {
         if (int rc = fvk_comm_allreduce_sum_impl(sv->comm, &sv->state->sums[3], 1, st)) return rc;
-        if (int rc = fvk_comm_halo_exchange_impl(sv->comm, x, 1, st)) return rc;
+        k_set_normB<<<1, 1, 0, st>>>(sv->state);
     }
-    k_set_normB<<<1, 1, 0, st>>>(sv->state);
-    // r = b - A x
-    k_spmv<2><<<gS, TB, 0, st>>>(n, rowOffs, colIdxs, values, x, b, sv->r, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0, sv->aff);
-    FVK_LAUNCH_CHECK();
 
     double* pCur = sv->p0;  // p of the previous iteration
     double* pNext = sv->p1;

@@ -209,8 +209,13 @@ class PDESolver:
         mesh = self.psi.mesh
         self.assemble()
         if self.expr.has_explicit():
-            src = self.expr.explicitOperation(mesh, self.psi.ncomp)
-            ops.rhs_sub_source(mesh, src, self.ls.rhs)
+            ex = [o for o in self.expr.spatial + self.expr.temporal if o.type == "explicit"]
+            if len(ex) == 1 and ex[0].kind == "surfaceIntegrate" and self.psi.ncomp == 1:
+                # the pressure equation's `- exp::div(phiHbyA)`: source and rhs update in one pass, same bits
+                ops.rhs_sub_surface_integrate(mesh, ex[0].faceField.internal, self.ls.rhs, ex[0].coeff.value, ex[0].coeff.view)
+            else:
+                src = self.expr.explicitOperation(mesh, self.psi.ncomp)
+                ops.rhs_sub_source(mesh, src, self.ls.rhs)
         if self.needReference and self.psi.ncomp == 1:
             ops.set_reference(mesh, self.pRefCell, self.pRefValue, self.ls.values, self.ls.rhs)
         if exchange_guess and self.rt.comm is not None:

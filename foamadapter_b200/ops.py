@@ -220,6 +220,18 @@ def update_velocity(mesh, HbyA, rAU, gradP, U):
     _count()
 
 
+def update_velocity_grad(mesh, HbyA, rAU, p, pB, U):
+    """U = HbyA - rAU * grad(p), fused (fvk_update_velocity_grad)"""
+    check(lib().fvk_update_velocity_grad(mesh.handle, ptr(HbyA), ptr(rAU), ptr(p), ptr(pB), ptr(U), _stream()))
+    _count()
+
+
+def rhs_sub_surface_integrate(mesh, flux, rhs, coeff=1.0, coeffView=None):
+    """rhs -= surfaceIntegrate(flux, coeff) * V, fused (fvk_rhs_sub_surface_integrate_s)"""
+    check(lib().fvk_rhs_sub_surface_integrate_s(mesh.handle, ptr(flux), C.c_double(coeff), ptr(coeffView), ptr(rhs), _stream()))
+    _count()
+
+
 def set_reference(mesh, refCell, refValue, values, rhs):
     check(lib().fvk_set_reference(mesh.handle, C.c_int32(refCell), C.c_double(refValue), ptr(values), ptr(rhs), _stream()))
     _count()

@@ -55,10 +55,12 @@ def updateFaceVelocity(predictedPhi: fvcc.SurfaceField, expr: dsl.PDESolver, phi
 
 
 def updateVelocity(HbyA, rAU, p, U, gradP=None):
-    """pressureVelocityCoupling.cpp:199-213"""
+    """pressureVelocityCoupling.cpp:199-213: U = HbyA - rAU * grad(p). One fused kernel (the gradient never goes to memory);
+    passing a gradP buffer keeps the two-kernel form (GaussGreenGrad::grad, then the cell loop) -- same bits either way."""
     mesh = U.mesh
     if gradP is None:
-        gradP = torch.empty((mesh.nCells, 3), dtype=torch.float64, device=U.internal.device)
+        ops.update_velocity_grad(mesh, HbyA.internal, rAU.internal, p.internal, p.boundary.value, U.internal)
+        return
     ops.grad(mesh, p.internal, p.boundary.value, gradP, ops.SET)
     ops.update_velocity(mesh, HbyA.internal, rAU.internal, gradP, U.internal)
 
@@ -106,7 +108,6 @@ class IcoFoam:
         self.HbyA = fvcc.VolumeField(mesh, "HbyA", 3, _extrapolated(mesh))
         self.rAUf = fvcc.SurfaceField(mesh, "rAUf", 1)
         self.phiHbyA = fvcc.SurfaceField(mesh, "phiHbyA", 1)
-        self.gradP = torch.empty((mesh.nCells, 3), dtype=torch.float64, device="cuda")
         self.Uls = la.LinearSystem(mesh, 3, zero=False, compact=compact_momentum and mesh_rows_in_stencil_order(mesh))
         self.pls = la.LinearSystem(mesh, 1, zero=False)
         self.linear = fvcc.SurfaceInterpolation(mesh, "linear")
@@ -168,7 +169,7 @@ class IcoFoam:
         p.correctBoundaryConditions()                                      # :156
         if last_nonorth:
             updateFaceVelocity(self.phiHbyA, self._pEqn, self.phi)         # :160
-            updateVelocity(self.HbyA, self.rAU, p, U, self.gradP)          # :166
+            updateVelocity(self.HbyA, self.rAU, p, U)                      # :166 (fused with the gradient)
             U.correctBoundaryConditions()                                  # :167
             self._halo(U.internal)
 

@@ -464,6 +464,15 @@ int fvk_update_face_velocity(const fvk_mesh* mesh, const double* values, const d
 /* updateVelocity (:199-213): U = HbyA - rAU * gradP (gradP from fvk_grad_s) */
 int fvk_update_velocity(const fvk_mesh* mesh, const double* HbyA, const double* rAU, const double* gradP,
                         double* U, fvk_stream stream);
+/* updateVelocity fused with the gradient it consumes: U = HbyA - rAU * grad(p) in one pass (no gradP array in memory); same
+ * arithmetic, bit for bit, as fvk_grad_s (FVK_SET) followed by fvk_update_velocity */
+int fvk_update_velocity_grad(const fvk_mesh* mesh, const double* HbyA, const double* rAU, const double* p, const double* pB,
+                             double* U, fvk_stream stream);
+/* dsl::solve's explicit source when it is ONE surfaceIntegrate operator (the pressure equation's `- exp::div(phiHbyA)`):
+ * rhs -= (0 + coeff/V * sum_f flux_f) * V in one pass = SurfaceIntegrate::explicitOperation into a zeroed source
+ * (operators/surfaceIntegrate.hpp) followed by dsl/solver.hpp:73-77, bit for bit, without the source vector */
+int fvk_rhs_sub_surface_integrate_s(const fvk_mesh* mesh, const double* flux, double coeff, const double* coeffView,
+                                    double* rhs, fvk_stream stream);
 /* PDESolver::SetReference (expression.hpp:86-112): rhs[r] += diag*value; diag += diag */
 int fvk_set_reference(const fvk_mesh* mesh, int32_t refCell, double refValue, double* values, double* rhs,
                       fvk_stream stream);

@@ -207,3 +207,33 @@ def test_momentum_predictor_step_matches_the_oracle():
     assert any(s["numIter"] > 0 for s in ref.Ustats)
     assert np.abs(host(app.U.internal) - ref.U).max() <= 1e-7 * np.abs(ref.U).max()
     assert np.abs(host(app.p.internal) - ref.p).max() <= 1e-6 * np.abs(ref.p).max()
+
+
+@pytest.mark.parametrize("dims", [(7, 5, 4), (40, 11, 7)])
+def test_fused_epilogues_equal_the_two_kernel_forms(dims):
+    """fvk_update_velocity_grad == fvk_grad_s + fvk_update_velocity; fvk_rhs_sub_surface_integrate_s == surfaceIntegrate into a
+    zeroed source + rhs -= source * V; both on the index-free and the stencil-driven kernels."""
+    import ctypes as C
+    from foamadapter_b200._capi import lib
+    d = M.MeshDesc.block(*dims, 0.7, 0.3, 0.9)
+    gm = M.UnstructuredMesh(d)
+    rng = np.random.default_rng(9)
+    nC, nB, nF = gm.nCells, gm.nBoundaryFaces, gm.nFaces
+    p, pB = dev(rng.uniform(-1, 1, nC)), dev(rng.uniform(-1, 1, nB))
+    H, rAU = dev(rng.uniform(-1, 1, (nC, 3))), dev(rng.uniform(0.5, 2, nC))
+    flux, rhs0, view = dev(rng.uniform(-1, 1, nF)), dev(rng.uniform(-1, 1, nC)), dev(rng.uniform(0.5, 2, nC))
+    g = torch.empty((nC, 3), dtype=torch.float64, device="cuda")
+    ops.grad(gm, p, pB, g)
+    U_ref = torch.empty_like(g); ops.update_velocity(gm, H, rAU, g, U_ref)
+    src = torch.zeros(nC, dtype=torch.float64, device="cuda")
+    ops.surface_integrate(gm, flux, src, -1.0, view, ops.ADD)
+    rhs_ref = rhs0.clone(); ops.rhs_sub_source(gm, src, rhs_ref)
+    for affine in (1, 0):
+        lib().fvk_set_affine(C.c_int(affine))
+        U = torch.full_like(g, float("nan"))
+        ops.update_velocity_grad(gm, H, rAU, p, pB, U)
+        assert torch.equal(U, U_ref)
+        rhs = rhs0.clone()
+        ops.rhs_sub_surface_integrate(gm, flux, rhs, -1.0, view)
+        assert torch.equal(rhs, rhs_ref)
+    lib().fvk_set_affine(C.c_int(1))
