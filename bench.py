@@ -660,7 +660,8 @@ def run_native(args, rank, world, local_rank):
         for b in range(2):
             f = fields[b]
             fl = flux if b == 0 else torch.empty_like(flux)
-            od, og, ol = (out_div, out_grad, out_lap) if b == 0 else (torch.empty_like(out_div), torch.empty_like(out_grad), torch.empty_like(out_lap))
+            # zeros: the operators write owned cells only, the ghost slots of a decomposed field keep their initial value
+            od, og, ol = (out_div, out_grad, out_lap) if b == 0 else (torch.zeros_like(out_div), torch.zeros_like(out_grad), torch.zeros_like(out_lap))
             bufs.append(dict(
                 f=f, flux=fl, outs=(od, og, ol),
                 a_div=(mesh.handle, C.c_int(0), ptr(fl), ptr(f.internal), ptr(f.boundary.value), one, None, ptr(od), C.c_int(0), s),
