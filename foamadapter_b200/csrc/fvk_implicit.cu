@@ -601,6 +601,30 @@ k_rhs_sub_source(int nC, const double* __restrict__ V, const double* __restrict_
     VT::st(rhs, c, VT::sub(VT::ld(rhs, c), VT::mul(V[c], VT::ld(src, c))));
 }
 
+// per-device auxiliary stream + events for the forked irregular-row pass (FVK_ASM_NO_FORK=1: same stream)
+bool side_stream(cudaStream_t* st, cudaEvent_t* evFork, cudaEvent_t* evJoin)
+{
+    static const bool off = [] { const char* e = std::getenv("FVK_ASM_NO_FORK"); return e && *e == '1'; }();
+    if (off) return false;
+    struct Side { cudaStream_t st = nullptr; cudaEvent_t a = nullptr, b = nullptr; bool ok = false, tried = false; };
+    static Side tab[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+    Side& sd = tab[dev];
+    if (!sd.tried)
+    {
+        sd.tried = true;
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        sd.ok = cudaStreamCreateWithPriority(&sd.st, cudaStreamNonBlocking, hi) == cudaSuccess
+                && cudaEventCreateWithFlags(&sd.a, cudaEventDisableTiming) == cudaSuccess
+                && cudaEventCreateWithFlags(&sd.b, cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (!sd.ok) return false;
+    *st = sd.st; *evFork = sd.a; *evJoin = sd.b;
+    return true;
+}
+
 template <class VT, bool COMPACT = false>
 int assemble_impl(const fvk_mesh* m, int nTerms, const fvk_term* terms_h, const fvk_bfield* bd, double* values,
                   double* rhs, double* bcMatrix, double* bcRhs, int accumulate, fvk_stream s)
@@ -685,12 +709,26 @@ int assemble_impl(const fvk_mesh* m, int nTerms, const fvk_term* terms_h, const 
         const size_t shmA = sizeof(double) * std::max(size_t(3 * TB + AFF_LX * BY + AFF_LX * BZ + BY * BZ) * (nFace == 2 ? 4 : 2), size_t(TB) * 7); \
         if (shmA > 48 * 1024)                                                                                           \
             FVK_CUDA(cudaFuncSetAttribute(k_assemble_affine<VT, a, bb, BY, BZ, MINB, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(shmA))); \
-        k_assemble_affine<VT, a, bb, BY, BZ, MINB, COMPACT><<<nTilesA, TB, shmA, fvk_cu(s)>>>(T, am, ag, ft[0], ft[1], values, rhs); \
-        FVK_LAUNCH_CHECK();                                                                                             \
+        /* the irregular rows (boundary / cut layers, ghost rows: latency-bound per-row walk) run BESIDE the streaming tiles on a \
+           forked stream (events: also valid inside a stream capture) */                                               \
+        cudaStream_t side = nullptr; cudaEvent_t evFork = nullptr, evJoin = nullptr;                                    \
+        const bool forked = nListed > 0 && side_stream(&side, &evFork, &evJoin);                                        \
+        if (forked)                                                                                                     \
+        {                                                                                                               \
+            FVK_CUDA(cudaEventRecord(evFork, fvk_cu(s)));                                                               \
+            FVK_CUDA(cudaStreamWaitEvent(side, evFork, 0));                                                             \
+        }                                                                                                               \
         if (nListed > 0)                                                                                                \
-            k_assemble_fast<VT, a, bb, COMPACT><<<(nListed + 255) / 256, 256, 0, fvk_cu(s)>>>(T, am, b, ft[0], ft[1], values, rhs, bcMatrix, bcRhs, \
+            k_assemble_fast<VT, a, bb, COMPACT><<<(nListed + 255) / 256, 256, 0, forked ? side : fvk_cu(s)>>>(T, am, b, ft[0], ft[1], values, rhs, bcMatrix, bcRhs, \
                                                                                      m->bp.irrCells, m->bp.nIrr, m->nOwned, nTail); \
         FVK_LAUNCH_CHECK();                                                                                             \
+        k_assemble_affine<VT, a, bb, BY, BZ, MINB, COMPACT><<<nTilesA, TB, shmA, fvk_cu(s)>>>(T, am, ag, ft[0], ft[1], values, rhs); \
+        FVK_LAUNCH_CHECK();                                                                                             \
+        if (forked)                                                                                                     \
+        {                                                                                                               \
+            FVK_CUDA(cudaEventRecord(evJoin, side));                                                                    \
+            FVK_CUDA(cudaStreamWaitEvent(fvk_cu(s), evJoin, 0));                                                        \
+        }                                                                                                               \
         return FVK_OK;                                                                                                  \
     }
 #define FVK_ASMA_CASE(a, bb)                                                                                            \

@@ -843,6 +843,12 @@ struct fvk_solver
     unsigned* counter = nullptr;
     PcgState* state = nullptr;
     PcgState* state_h = nullptr; // pinned, [2]: double-buffered stop checks
+    // stream-capture mode (fvk_solver_solve on a capturing stream): the iteration is a conditional WHILE node of the graph
+    // being captured -- no host round trip; every captured solve copies its final state into its own pinned slot
+    PcgState* init_h = nullptr;  // pinned start state the graph's memcpy node reads
+    PcgState* cap_h = nullptr;   // pinned [FVK_MAX_CAPTURED_SOLVES]
+    int nCaptured = 0;
+    cudaStream_t bodyStream = nullptr;
     cudaEvent_t checkEv[2] = {nullptr, nullptr};
     int32_t histCap = 0;
 };
@@ -856,6 +862,9 @@ extern "C" int fvk_solver_destroy(fvk_solver* sv)
                       (void*) sv->partial, (void*) sv->hist, (void*) sv->counter, (void*) sv->state})
         if (ptr) cudaFree(ptr);
     if (sv->state_h) cudaFreeHost(sv->state_h);
+    if (sv->init_h) cudaFreeHost(sv->init_h);
+    if (sv->cap_h) cudaFreeHost(sv->cap_h);
+    if (sv->bodyStream) cudaStreamDestroy(sv->bodyStream);
     for (auto& e : sv->checkEv)
         if (e) cudaEventDestroy(e);
     delete sv;
@@ -1042,6 +1051,106 @@ static int bicgstab_solve(fvk_solver* sv, const int32_t* rowOffs, const int32_t*
     return FVK_OK;
 }
 
+
+// ---- CG inside a stream capture: one conditional WHILE node, zero host round trips ---------------------------------------
+constexpr int FVK_MAX_CAPTURED_SOLVES = 64;
+__global__ void k_loop_cond(const PcgState* __restrict__ st, cudaGraphConditionalHandle h)
+{
+    if (st->done) cudaGraphSetConditional(h, 0);
+}
+
+static int cg_solve_captured(fvk_solver* sv, const int32_t* rowOffs, const int32_t* colIdxs, const double* values, const double* b,
+                             double* x, fvk_solver_stats* stats_h, cudaStream_t st)
+{
+    const int n = sv->nRows;
+    const bool dist = sv->comm != nullptr;
+    const FvkP2PCtx* p2p = fvk_comm_p2p_ctx(sv->comm);
+    if (dist && !p2p) return fvk_fail(FVK_EUNSUPPORTED, "fvk_solver_solve: stream capture needs the peer-memory transport (or one GPU)");
+    if (sv->nCaptured >= FVK_MAX_CAPTURED_SOLVES) return fvk_fail(FVK_EUNSUPPORTED, "fvk_solver_solve: more than %d captured solves", FVK_MAX_CAPTURED_SOLVES);
+    const int dmode = dist ? 2 : 0;
+    const bool jacobi = sv->cfg.preconditioner == FVK_PRECOND_JACOBI;
+    const int gV = stream_grid(n), gS = spmv_grid(n);
+    if (!sv->init_h) FVK_CUDA(cudaMallocHost(reinterpret_cast<void**>(&sv->init_h), sizeof(PcgState)));
+    if (!sv->cap_h) FVK_CUDA(cudaMallocHost(reinterpret_cast<void**>(&sv->cap_h), sizeof(PcgState) * FVK_MAX_CAPTURED_SOLVES));
+    if (!sv->bodyStream) FVK_CUDA(cudaStreamCreateWithFlags(&sv->bodyStream, cudaStreamNonBlocking));
+    PcgState init;
+    std::memset(&init, 0, sizeof(init));
+    init.rhoPrev = 1.0;
+    init.relTol = sv->cfg.relTol; init.absTol = sv->cfg.absTol; init.maxIter = sv->cfg.maxIter;
+    *sv->init_h = init; // identical for every captured solve of this solver
+    // the graph being captured, for the conditional handle
+    cudaStreamCaptureStatus status;
+    cudaGraph_t graph = nullptr;
+    const cudaGraphNode_t* deps = nullptr;
+    size_t nDeps = 0;
+    FVK_CUDA(cudaStreamGetCaptureInfo(st, &status, nullptr, &graph, &deps, &nDeps));
+    cudaGraphConditionalHandle handle;
+    FVK_CUDA(cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault));
+    // ---- start-up (same kernels as the eager path)
+    FVK_CUDA(cudaMemcpyAsync(sv->state, sv->init_h, sizeof(PcgState), cudaMemcpyHostToDevice, st));
+    FVK_CUDA(cudaMemsetAsync(sv->p0, 0, sizeof(double) * sv->nCols, st));
+    if (jacobi)
+        if (int rc = launch_dinv(sv, rowOffs, colIdxs, values, st)) return rc;
+    if (dist)
+        if (int rc = fvk_comm_halo_exchange_impl(sv->comm, x, 1, st)) return rc;
+    k_spmv<2><<<gS, TB, 0, st>>>(n, rowOffs, colIdxs, values, x, b, sv->r, sv->state, nullptr, nullptr, sv->partial, sv->counter, dist ? 1 : 0, nullptr, 0, sv->aff);
+    FVK_LAUNCH_CHECK();
+    if (dist)
+    {
+        if (int rc = fvk_comm_allreduce_sum_impl(sv->comm, &sv->state->sums[3], 1, st)) return rc;
+        k_set_normB<<<1, 1, 0, st>>>(sv->state);
+    }
+    double *rA = sv->r, *rB = dmode == 2 ? sv->r2 : sv->r;
+    auto K1 = [&](cudaStream_t q, bool first, double* rIn, double* rOut, double* pCur) {
+        if (first)
+        {
+            if (jacobi) k_cg_update<true, true><<<gV, TB, 0, q>>>(n, sv->state, x, pCur, sv->q, rIn, rIn, sv->dinv, sv->z, sv->partial, sv->counter, nullptr, dmode, p2p);
+            else k_cg_update<true, false><<<gV, TB, 0, q>>>(n, sv->state, x, pCur, sv->q, rIn, rIn, sv->dinv, sv->z, sv->partial, sv->counter, nullptr, dmode, p2p);
+        }
+        else
+        {
+            if (jacobi) k_cg_update<false, true><<<gV, TB, 0, q>>>(n, sv->state, x, pCur, sv->q, rIn, rOut, sv->dinv, sv->z, sv->partial, sv->counter, nullptr, dmode, p2p);
+            else k_cg_update<false, false><<<gV, TB, 0, q>>>(n, sv->state, x, pCur, sv->q, rIn, rOut, sv->dinv, sv->z, sv->partial, sv->counter, nullptr, dmode, p2p);
+        }
+    };
+    auto K2 = [&](cudaStream_t q, double* pCur, double* pNext) {
+        k_spmv<4><<<gS, TB, 0, q>>>(n, rowOffs, colIdxs, values, pCur, nullptr, sv->q, sv->state, sv->z, pNext, sv->partial, sv->counter, dmode, p2p, sv->nCols, sv->aff);
+    };
+    K1(st, true, rA, rA, sv->p0);
+    K2(st, sv->p0, sv->p1);
+    k_loop_cond<<<1, 1, 0, st>>>(sv->state, handle);
+    FVK_LAUNCH_CHECK();
+    // ---- WHILE (not done): two iterations per pass, so the double-buffered p (and r) are back where they started
+    FVK_CUDA(cudaStreamGetCaptureInfo(st, &status, nullptr, &graph, &deps, &nDeps));
+    cudaGraphNodeParams cp = {};
+    cp.type = cudaGraphNodeTypeConditional;
+    cp.conditional.handle = handle;
+    cp.conditional.type = cudaGraphCondTypeWhile;
+    cp.conditional.size = 1;
+    cudaGraphNode_t node;
+    FVK_CUDA(cudaGraphAddNode(&node, graph, deps, nDeps, &cp));
+    cudaGraph_t body = cp.conditional.phGraph_out[0];
+    FVK_CUDA(cudaStreamUpdateCaptureDependencies(st, &node, 1, cudaStreamSetCaptureDependencies));
+    FVK_CUDA(cudaStreamBeginCaptureToGraph(sv->bodyStream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+    K1(sv->bodyStream, false, rA, rB, sv->p1);
+    K2(sv->bodyStream, sv->p1, sv->p0);
+    K1(sv->bodyStream, false, rB, rA, sv->p0);
+    K2(sv->bodyStream, sv->p0, sv->p1);
+    k_loop_cond<<<1, 1, 0, sv->bodyStream>>>(sv->state, handle);
+    cudaError_t le = cudaGetLastError();
+    cudaGraph_t bodyOut = nullptr;
+    cudaError_t ee = cudaStreamEndCapture(sv->bodyStream, &bodyOut);
+    if (le != cudaSuccess || ee != cudaSuccess)
+        return fvk_fail(FVK_ECUDA, "fvk_solver_solve: capturing the iteration body failed: %s", cudaGetErrorString(le != cudaSuccess ? le : ee));
+    // ---- final state into this solve's pinned slot
+    const int slot = sv->nCaptured++;
+    FVK_CUDA(cudaMemcpyAsync(&sv->cap_h[slot], sv->state, sizeof(PcgState), cudaMemcpyDeviceToHost, st));
+    stats_h->numIter = -(slot + 1); // not known at capture time: fvk_solver_captured_stats(slot) after a replay
+    stats_h->initResNorm = stats_h->finalResNorm = 0.0;
+    stats_h->nHistory = 0;
+    return FVK_OK;
+}
+
 extern "C" int fvk_solver_solve(fvk_solver* sv, const int32_t* rowOffs, const int32_t* colIdxs, const double* values,
                                 const double* b, double* x, fvk_solver_stats* stats_h, double* history_h,
                                 int32_t maxHistory, fvk_stream s)
@@ -1050,8 +1159,17 @@ extern "C" int fvk_solver_solve(fvk_solver* sv, const int32_t* rowOffs, const in
     // the structured SpMV computes columns from the attached mesh's dimensions: only valid for that mesh's own pattern
     struct AffGuard { fvk_solver* s; SpmvAffine saved; ~AffGuard() { s->aff = saved; } } guard {sv, sv->aff};
     if (rowOffs != sv->affRowOffs || colIdxs != sv->affColIdxs) sv->aff = SpmvAffine {0, 0, 0, 0};
-    if (sv->cfg.solverType == FVK_SOLVER_BICGSTAB) return bicgstab_solve(sv, rowOffs, colIdxs, values, b, x, stats_h, history_h, maxHistory, s);
     cudaStream_t st = fvk_cu(s);
+    {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (st != nullptr && cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusActive)
+        {
+            if (sv->cfg.solverType != FVK_SOLVER_CG) return fvk_fail(FVK_EUNSUPPORTED, "fvk_solver_solve: only solver::Cg can be captured into a CUDA graph");
+            if (history_h) return fvk_fail(FVK_EUNSUPPORTED, "fvk_solver_solve: residual histories are not available inside a stream capture");
+            return cg_solve_captured(sv, rowOffs, colIdxs, values, b, x, stats_h, st);
+        }
+    }
+    if (sv->cfg.solverType == FVK_SOLVER_BICGSTAB) return bicgstab_solve(sv, rowOffs, colIdxs, values, b, x, stats_h, history_h, maxHistory, s);
     const int n = sv->nRows;
     const bool dist = sv->comm != nullptr;
     const FvkP2PCtx* p2p = fvk_comm_p2p_ctx(sv->comm);
@@ -1234,5 +1352,25 @@ extern "C" int fvk_solver_solve_vec3c(fvk_solver* sv, const int32_t* rowOffs, co
         k_put_component<<<stream_grid(sv->nRows), TB, 0, st>>>(sv->nRows, c, sv->xC, xV);
         FVK_LAUNCH_CHECK();
     }
+    return FVK_OK;
+}
+
+// Stream-capture mode: statistics of captured solve `slot` (the order of the fvk_solver_solve calls during the capture, as
+// returned in stats.numIter = -(slot + 1)), valid after a replay of the graph has completed. fvk_solver_reset_captures
+// forgets the slots (before capturing again).
+extern "C" int fvk_solver_captured_stats(const fvk_solver* sv, int32_t slot, fvk_solver_stats* stats_h)
+{
+    if (!sv || !stats_h || slot < 0 || slot >= sv->nCaptured || !sv->cap_h) return fvk_fail(FVK_EINVAL, "fvk_solver_captured_stats: bad slot");
+    const PcgState& fin = sv->cap_h[slot];
+    stats_h->numIter = fin.iter;
+    stats_h->initResNorm = fin.normB;
+    stats_h->finalResNorm = fin.normR;
+    stats_h->nHistory = 0;
+    return fin.done ? FVK_OK : fvk_fail(FVK_ECUDA, "fvk_solver_captured_stats: the solve has not finished (replay not complete?)");
+}
+extern "C" int fvk_solver_reset_captures(fvk_solver* sv)
+{
+    if (!sv) return fvk_fail(FVK_EINVAL, "fvk_solver_reset_captures: null");
+    sv->nCaptured = 0;
     return FVK_OK;
 }

@@ -115,6 +115,32 @@ class SolverStats:
         print(f"Solver: {name} , Initial residual = {self.initResNorm} , Final residual = {self.finalResNorm} , No Iterations = {self.numIter}")
 
 
+class CapturedSolverStats:
+    """Statistics of a solve that was captured into a CUDA graph (fvk_solver_solve on a capturing stream): read from the
+    solver's pinned slot after a replay; attribute access waits for the device (the replay must have been launched)."""
+
+    def __init__(self, solver, slot):
+        self._solver, self._slot = solver, slot
+        self.history = None
+
+    def _read(self):
+        torch.cuda.current_stream().synchronize()
+        st = _Stats()
+        check(lib().fvk_solver_captured_stats(self._solver._h, C.c_int32(self._slot), C.byref(st)))
+        return st
+
+    @property
+    def numIter(self): return self._read().numIter
+    @property
+    def initResNorm(self): return self._read().initResNorm
+    @property
+    def finalResNorm(self): return self._read().finalResNorm
+
+    def snapshot(self):
+        st = self._read()
+        return SolverStats(st.numIter, st.initResNorm, st.finalResNorm)
+
+
 class _Cfg(C.Structure):
     _fields_ = [("maxIter", C.c_int32), ("relTol", C.c_double), ("absTol", C.c_double), ("preconditioner", C.c_int32),
                 ("checkEvery", C.c_int32), ("solverType", C.c_int32)]
@@ -209,6 +235,11 @@ class Solver:
             lib().fvk_solver_destroy(self._h)
             self._h = None
 
+    def reset_captures(self):
+        """forget the slots of earlier captured solves (before capturing a new graph)"""
+        if self._h is not None:
+            check(lib().fvk_solver_reset_captures(self._h))
+
     def __del__(self):
         try:
             self.close()
@@ -229,6 +260,8 @@ class Solver:
         hist = np.zeros(max(nh, 1))
         check(lib().fvk_solver_solve(h, C.c_void_p(rowOffs_ptr), C.c_void_p(colIdxs_ptr), ptr(values), ptr(b), ptr(x),
                                      C.byref(st), hist.ctypes.data_as(C.c_void_p) if nh else None, C.c_int32(nh), _stream()))
+        if st.numIter < 0:  # captured into a CUDA graph: the iteration is a conditional node, statistics come after a replay
+            return CapturedSolverStats(self, -st.numIter - 1)
         ops._count(self._launches(st.numIter))
         return SolverStats(st.numIter, st.initResNorm, st.finalResNorm, hist[:st.nHistory] if nh else None)
 

@@ -91,7 +91,7 @@ class IcoFoam:
     fixedWalls, p zeroGradient everywhere (tutorials/cavity/0.orig/{U,p}), nu uniform, momentumPredictor no."""
 
     def __init__(self, mesh: UnstructuredMesh, nu=0.01, dt=1e-4, fvSolution=None, fvSchemes=None, comm=None,
-                 lid=(1.0, 0.0, 0.0), history=False, check_every=8, graphs=True, compact_momentum=True):
+                 lid=(1.0, 0.0, 0.0), history=False, check_every=8, graphs=True, compact_momentum=True, whole_step_graph=True):
         self.mesh = mesh
         fvSolution = fvSolution or CAVITY_FVSOLUTION
         self.rt = dsl.RunTime(mesh, dt, 0.0, fvSchemes or CAVITY_FVSCHEMES, fvSolution, comm, check_every, history)
@@ -122,6 +122,8 @@ class IcoFoam:
         self._coScratch = torch.empty(lib().fvk_conum_scratch_bytes(mesh.handle) // 8, dtype=torch.float64, device="cuda")
         self.coNum = None
         self.graphs, self._captured, self._nsteps = bool(graphs), None, 0
+        self.timing, self.segment_ms = False, None
+        self.whole_step_graph, self._whole, self._whole_stats, self._whole_failed = bool(whole_step_graph), None, None, False
 
     def _halo(self, *ts):
         """processor-boundary exchange of one or several cell fields (one exchange for all of them)"""
@@ -207,6 +209,37 @@ class IcoFoam:
         plan = self._plan()
         segs = [item[1] for item in plan if item[0] == "kernels"]
         use_graphs = self._graphs_allowed() and self._nsteps >= 2
+        # whole-step graph: the pressure solves are captured too (conditional WHILE nodes, device-side stopping test), so a
+        # time step is ONE graph launch with no host round trip. Needs solver::Cg, no residual history, no momentum solve.
+        whole = (use_graphs and self.whole_step_graph and not self.timing and self.solver.type == "solver::Cg" and not self.solver.history
+                 and not self.piso.get("momentumPredictor", False))
+        if whole and self._whole is None and self._whole_failed is False:
+            try:
+                torch.cuda.synchronize()
+                self.solver._attach(self.mesh)
+                self.solver.reset_captures()
+                g = torch.cuda.CUDAGraph()
+                lazy = []
+                with torch.cuda.graph(g):
+                    for item in plan:
+                        if item[0] == "kernels":
+                            for f in item[1]:
+                                f()
+                        else:
+                            lazy.append(self.solver.solve(self.pls, self.p.internal))
+                self._whole, self._whole_stats = g, lazy
+            except Exception as e:
+                import sys
+                print(f"[piso] whole-step CUDA-graph capture failed ({e!r}); using per-segment graphs", file=sys.stderr)
+                self._whole, self._whole_failed = None, True
+                torch.cuda.synchronize()
+        if whole and self._whole is not None:
+            self._whole.replay()
+            self.stats.append(list(self._whole_stats))
+            self.Ustats = None
+            rt.t += rt.dt
+            self._nsteps += 1
+            return self.stats[-1]
         if use_graphs and self._captured is None:
             try:
                 torch.cuda.synchronize()
@@ -227,7 +260,10 @@ class IcoFoam:
         self.stats.append([])
         self.Ustats = None
         k = 0
+        evs = [] if self.timing else None
         for item in plan:
+            if evs is not None:
+                e = torch.cuda.Event(enable_timing=True); e.record(); evs.append((item[0], e))
             if item[0] == "kernels":
                 if replay:
                     self._captured[k].replay()
@@ -239,6 +275,10 @@ class IcoFoam:
                 self.Ustats = self.Usolver.solve(self.Uls, self.U.internal)        # :102 UEqn.solve()
             else:
                 self.stats[-1].append(self.solver.solve(self.pls, self.p.internal))   # :155
+        if evs is not None:  # per-segment device times of this step (diagnostics: profiles/r2_piso_segments.jsonl)
+            e = torch.cuda.Event(enable_timing=True); e.record(); evs.append(("end", e))
+            torch.cuda.synchronize()
+            self.segment_ms = [(evs[i][0], evs[i][1].elapsed_time(evs[i + 1][1])) for i in range(len(evs) - 1)]
         rt.t += rt.dt
         self._nsteps += 1
         return self.stats[-1]

@@ -427,6 +427,13 @@ int fvk_solver_solve(fvk_solver* solver, const int32_t* rowOffs, const int32_t* 
                      const double* values, const double* b, double* x, fvk_solver_stats* stats_h,
                      double* history_h, int32_t maxHistory, fvk_stream stream);
 
+/* fvk_solver_solve on a CAPTURING stream (cudaStreamBeginCapture / torch.cuda.graph): solver::Cg on one GPU or over the
+ * peer-memory transport becomes part of the graph being captured -- the start-up kernels, then a conditional WHILE node whose
+ * body is two CG iterations and whose condition a device kernel clears when the stopping criterion fires. No host round trip:
+ * a whole PISO step (assembly, both pressure solves, correctors) is ONE graph launch. stats.numIter = -(slot + 1) at capture
+ * time; the real statistics of a replay are read with fvk_solver_captured_stats(slot) once the replay has completed. */
+int fvk_solver_captured_stats(const fvk_solver* solver, int32_t slot, fvk_solver_stats* stats_h);
+int fvk_solver_reset_captures(fvk_solver* solver);
 /* Vec3 LinearSystem (values Vec3[nnz] with identical components; rhs / x Vec3[nRows] / [nCols]): three scalar
  * solves over the component matrix (NeoN's la::Solver has no Vec3 overload, solver.hpp:52; this is what `momentumPredictor yes`
  * of neoIcoFoam.cpp:100-103 needs). stats3_h receives one fvk_solver_stats per component. */

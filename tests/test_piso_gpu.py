@@ -110,7 +110,7 @@ def test_cuda_graph_segments_equal_eager_steps():
     """From the third step on IcoFoam replays the kernel-only segments between the linear solves as CUDA graphs: the
     fields must be bit-identical to the eager time loop, step after step."""
     d = piso.cavity_desc(12, True)
-    a = piso.IcoFoam(M.UnstructuredMesh(d), nu=0.01, dt=5e-4, check_every=4, graphs=True)
+    a = piso.IcoFoam(M.UnstructuredMesh(d), nu=0.01, dt=5e-4, check_every=4, graphs=True, whole_step_graph=False)
     b = piso.IcoFoam(M.UnstructuredMesh(d), nu=0.01, dt=5e-4, check_every=4, graphs=False)
     for step in range(6):
         sa, sb = a.step(), b.step()
@@ -118,6 +118,27 @@ def test_cuda_graph_segments_equal_eager_steps():
         for x, y in ((a.U.internal, b.U.internal), (a.p.internal, b.p.internal), (a.phi.internal, b.phi.internal)):
             assert torch.equal(x, y), step
     assert a._captured is not None and len(a._captured) == 3 and b._captured is None
+
+
+def test_whole_step_graph_with_captured_solves_equals_eager_steps():
+    """Default mode: from the third step on a time step is ONE CUDA graph -- the pressure solves are conditional WHILE nodes
+    whose stopping test runs on the device (no host round trip). Fields and iteration counts must equal the eager loop's, bit
+    for bit, step after step (the graph runs the same kernels in the same order; iterations past the stop are no-ops)."""
+    d = piso.cavity_desc(14, True)
+    a = piso.IcoFoam(M.UnstructuredMesh(d), nu=0.01, dt=5e-4, check_every=4, graphs=True)
+    b = piso.IcoFoam(M.UnstructuredMesh(d), nu=0.01, dt=5e-4, check_every=4, graphs=False)
+    iters = []
+    for step in range(8):
+        sa, sb = a.step(), b.step()
+        ia, ib = [s.numIter for s in sa], [s.numIter for s in sb]
+        assert ia == ib, (step, ia, ib)
+        iters.append(ia)
+        for x, y in ((a.U.internal, b.U.internal), (a.p.internal, b.p.internal), (a.phi.internal, b.phi.internal)):
+            assert torch.equal(x, y), step
+        if step >= 2:
+            assert abs(sa[0].finalResNorm - sb[0].finalResNorm) <= 1e-15 + 1e-12 * sb[0].finalResNorm
+    assert a._whole is not None and a._captured is None
+    assert len({tuple(i) for i in iters[2:]}) > 1 and max(max(i) for i in iters[2:]) >= 3   # the loop really iterates, differently per step
 
 
 def test_pdesolver_matches_dsl_solve_sequence(case):

@@ -67,7 +67,7 @@ def main():
     if rank == 0:
         tot_it = [int(sum(i)) for i in its]
         print("PISO " + json.dumps({"n": args.size, "cells": args.size ** 3, "n_gpus": world, "transport": ("peer-memory windows" if (comm and comm.p2p) else ("NCCL" if comm else "none")),
-                                    "ms_per_step": [round(float(x), 3) for x in ms], "median_ms": float(np.median(ms)), "cg_iterations": its, "cuda_graphs": bool(app._captured),
+                                    "ms_per_step": [round(float(x), 3) for x in ms], "median_ms": float(np.median(ms)), "cg_iterations": its, "cuda_graphs": ("whole step" if app._whole is not None else ("segments" if app._captured else "none")),
                                     "ms_per_cg_iteration_upper_bound": float(np.median(ms / np.maximum(tot_it, 1))), "setup_s": round(setup_s, 1)}), flush=True)
     if comm is not None:
         comm.close()
