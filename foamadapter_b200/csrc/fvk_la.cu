@@ -890,6 +890,10 @@ extern "C" int fvk_solver_create(int32_t nRows, int32_t nCols, const fvk_solver_
     if (e == cudaSuccess) e = cudaMemset(sv->counter, 0, sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&sv->state), sizeof(PcgState));
     if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&sv->state_h), 2 * sizeof(PcgState));
+    // stream-capture mode needs these before a capture starts (allocations are not allowed while a stream captures)
+    if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&sv->init_h), sizeof(PcgState));
+    if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&sv->cap_h), sizeof(PcgState) * 64);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sv->bodyStream, cudaStreamNonBlocking);
     for (auto& ev : sv->checkEv)
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     if (e != cudaSuccess)
@@ -1053,7 +1057,7 @@ static int bicgstab_solve(fvk_solver* sv, const int32_t* rowOffs, const int32_t*
 
 
 // ---- CG inside a stream capture: one conditional WHILE node, zero host round trips ---------------------------------------
-constexpr int FVK_MAX_CAPTURED_SOLVES = 64;
+constexpr int FVK_MAX_CAPTURED_SOLVES = 64; // = the pinned slots allocated by fvk_solver_create
 __global__ void k_loop_cond(const PcgState* __restrict__ st, cudaGraphConditionalHandle h)
 {
     if (st->done) cudaGraphSetConditional(h, 0);
@@ -1070,9 +1074,7 @@ static int cg_solve_captured(fvk_solver* sv, const int32_t* rowOffs, const int32
     const int dmode = dist ? 2 : 0;
     const bool jacobi = sv->cfg.preconditioner == FVK_PRECOND_JACOBI;
     const int gV = stream_grid(n), gS = spmv_grid(n);
-    if (!sv->init_h) FVK_CUDA(cudaMallocHost(reinterpret_cast<void**>(&sv->init_h), sizeof(PcgState)));
-    if (!sv->cap_h) FVK_CUDA(cudaMallocHost(reinterpret_cast<void**>(&sv->cap_h), sizeof(PcgState) * FVK_MAX_CAPTURED_SOLVES));
-    if (!sv->bodyStream) FVK_CUDA(cudaStreamCreateWithFlags(&sv->bodyStream, cudaStreamNonBlocking));
+    if (!sv->init_h || !sv->cap_h || !sv->bodyStream) return fvk_fail(FVK_ECUDA, "fvk_solver_solve: capture buffers missing");
     PcgState init;
     std::memset(&init, 0, sizeof(init));
     init.rhoPrev = 1.0;
