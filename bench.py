@@ -552,8 +552,8 @@ def run_native(args, rank, world, local_rank):
             with torch.cuda.stream(comm_stream):
                 comm_stream.wait_event(ev_begin)
                 mesh.set_tile_phase(2)
+                comm.halo_exchange_multi([f.internal for f in fields])  # ONE exchange for the three inputs
                 for i, (fn, a) in enumerate(calls_cs):
-                    comm.halo_exchange(fields[i].internal)
                     rc |= fn(*a)
                 ev_comm.record(comm_stream)
             mesh.set_tile_phase(1)
@@ -563,7 +563,7 @@ def run_native(args, rank, world, local_rank):
                 rc |= fn(*a)
             mesh.set_tile_phase(0)
             stream.wait_event(ev_comm)
-            launches[0] += 12
+            launches[0] += 8
         if ev is not None:
             ev[3].record(stream)
         if rc:
@@ -761,7 +761,7 @@ def run_native(args, rank, world, local_rank):
                              "section flushes L2 (256 MB write) before every launch",
                        "parallelism": "1 GPU" if world == 1 else
                        f"domain decomposition, {world} ranks ({split}) of one {'x'.join(str(n * q) for q in default_split(world))} mesh, ghost cells + {transport}; the "
-                       "exchange of each operator's input runs on a second stream (followed there by the operator's halo phase) beside the cells that read no ghost cell"},
+                       "one exchange for the three operators' inputs runs on a second stream (followed there by the operators' halo phases) beside the cells that read no ghost cell"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                          "frac": kernels[dom]["frac"], "traffic": None, "peak_kind": peak_kind,
                          "traffic_note": "not measured in this run; ncu dram bytes per launch are committed in profiles/traffic.json and profiles/r2*_ncu_*.csv"},

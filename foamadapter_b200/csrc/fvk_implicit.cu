@@ -67,7 +67,23 @@ struct AsmMesh
     const double* __restrict__ nodc;  // nonOrthDeltaCoeffs
     const double* __restrict__ magSf;
     const double* __restrict__ bDeltaCoeffs;
+    const int* __restrict__ owner;     // only read by laplacian terms whose gamma is interpolated on the fly (gammaCell)
+    const int* __restrict__ neighbour;
 };
+
+// gamma of a laplacian term at internal face f (owner own, neighbour nei): the given face field, or -- gammaCell set -- the
+// linear interpolate of a cell field evaluated on the fly with computeLinearInterpolation's arithmetic
+// (interpolation/linear.cpp:30-45: w phi_P + (1 - w) phi_N), so `laplacian(interpolate(rAU), p)` needs no face-sized temporary
+__device__ __forceinline__ double lap_gamma(const fvk_term& t, const AsmMesh& m, int f, int own, int nei)
+{
+    if (!t.gammaCell) return t.faceField[f];
+    const double wf = m.w[f];
+    return wf * t.gammaCell[own] + (1 - wf) * t.gammaCell[nei];
+}
+__device__ __forceinline__ double lap_gamma_boundary(const fvk_term& t, const AsmMesh& m, int f, int b)
+{
+    return t.gammaCell ? m.w[f] * t.gammaBoundary[b] : t.faceField[f]; // linear.cpp: boundary weight (= 1) x boundary value
+}
 
 __device__ __forceinline__ double term_scaling(const fvk_term& t, int c)
 {
@@ -78,7 +94,7 @@ __device__ __forceinline__ double term_scaling(const fvk_term& t, int c)
 // A[c][nei]; side 1: c is the neighbour -> lower entry A[c][own]) and, negated, to the diagonal of the
 // OTHER role. div: value1 = -w F (lower, and subtracted from the owner's diag), value2 = F (1 - w)
 // (upper, and subtracted from the neighbour's diag); laplacian: flux for all four.
-__device__ __forceinline__ void face_coeffs(const fvk_term& t, const AsmMesh& m, int f, double& lowerAndOwnDiag,
+__device__ __forceinline__ void face_coeffs(const fvk_term& t, const AsmMesh& m, int f, int c, bool side, double& lowerAndOwnDiag,
                                             double& upperAndNeiDiag)
 {
     if (t.kind == FVK_TERM_DIV)
@@ -90,7 +106,8 @@ __device__ __forceinline__ void face_coeffs(const fvk_term& t, const AsmMesh& m,
     }
     else
     {
-        const double flux = m.nodc[f] * t.faceField[f] * m.magSf[f];
+        const double g = t.gammaCell ? lap_gamma(t, m, f, side ? m.owner[f] : c, side ? c : m.neighbour[f]) : t.faceField[f];
+        const double flux = m.nodc[f] * g * m.magSf[f];
         lowerAndOwnDiag = flux;
         upperAndNeiDiag = flux;
     }
@@ -134,7 +151,7 @@ k_assemble(Terms terms, AsmMesh m, fvk_bfield bd, double* __restrict__ values, d
             const fvk_term& t = terms.t[k];
             if (t.kind != FVK_TERM_DIV && t.kind != FVK_TERM_LAPLACIAN) continue;
             double lo, up;
-            face_coeffs(t, m, f, lo, up);
+            face_coeffs(t, m, f, c, side, lo, up);
             v = VT::add(v, VT::mul(term_scaling(t, c), VT::splat(side ? lo : up)));
         }
         stval<VT, COMPACT>(values, slot, v);
@@ -156,7 +173,7 @@ k_assemble(Terms terms, AsmMesh m, fvk_bfield bd, double* __restrict__ values, d
                 if (f < m.nI)
                 {
                     double lo, up;
-                    face_coeffs(t, m, f, lo, up);
+                    face_coeffs(t, m, f, c, code & 1, lo, up);
                     // owner's diag -= value1 * os ; neighbour's diag -= value2 * os
                     d = VT::sub(d, VT::mul(os, VT::splat((code & 1) ? up : lo)));
                 }
@@ -176,7 +193,7 @@ k_assemble(Terms terms, AsmMesh m, fvk_bfield bd, double* __restrict__ values, d
                     }
                     else
                     { // gaussGreenLaplacian.cpp:156-175
-                        const double flux = t.faceField[f] * m.magSf[f];
+                        const double flux = lap_gamma_boundary(t, m, f, b) * m.magSf[f];
                         const double dcf = m.nodc[f];
                         valueMat = VT::splat(flux * os * vf1 * dcf);
                         d = VT::sub(d, valueMat);
@@ -220,7 +237,7 @@ constexpr int ASM_E = 6;      // stencil entries handled in registers
 constexpr int ASM_CAPW = 288; // staged entries per warp (32 rows x 9)
 
 template <int KIND>
-__device__ __forceinline__ void face_coeffs_k(const fvk_term& t, const AsmMesh& m, int f, double& lowerAndOwnDiag,
+__device__ __forceinline__ void face_coeffs_k(const fvk_term& t, const AsmMesh& m, int f, int own, int nei, double& lowerAndOwnDiag,
                                               double& upperAndNeiDiag)
 {
     if (KIND == FVK_TERM_DIV)
@@ -232,9 +249,19 @@ __device__ __forceinline__ void face_coeffs_k(const fvk_term& t, const AsmMesh& 
     }
     else
     {
-        const double flux = m.nodc[f] * t.faceField[f] * m.magSf[f];
+        const double flux = m.nodc[f] * lap_gamma(t, m, f, own, nei) * m.magSf[f];
         lowerAndOwnDiag = flux;
         upperAndNeiDiag = flux;
+    }
+}
+// own / nei of stencil entry (f, side) of cell c; the arrays are only read when a term interpolates its gamma on the fly
+__device__ __forceinline__ void face_cells(const fvk_term& t0, const fvk_term& t1, const AsmMesh& m, int f, int c, bool side, int& own, int& nei)
+{
+    own = nei = c;
+    if (t0.gammaCell || t1.gammaCell)
+    {
+        if (side) own = m.owner[f];
+        else nei = m.neighbour[f];
     }
 }
 
@@ -287,8 +314,10 @@ k_assemble_fast(Terms terms, AsmMesh m, fvk_bfield bd, int ft0, int ft1, double*
     for (int k = 0; k < ASM_E; ++k)
     {
         const int f = code[k] >> 1; // face 0 on padded lanes: valid address, value unused
-        face_coeffs_k<K0>(t0, m, f, lo0[k], up0[k]);
-        if (HAS1) face_coeffs_k<K1>(t1, m, f, lo1[k], up1[k]);
+        int own, nei;
+        face_cells(t0, t1, m, f, active ? c : 0, code[k] & 1, own, nei);
+        face_coeffs_k<K0>(t0, m, f, own, nei, lo0[k], up0[k]);
+        if (HAS1) face_coeffs_k<K1>(t1, m, f, own, nei, lo1[k], up1[k]);
     }
     double dc0[ASM_E], dc1[ASM_E];
 #pragma unroll
@@ -308,11 +337,13 @@ k_assemble_fast(Terms terms, AsmMesh m, fvk_bfield bd, int ft0, int ft1, double*
         const bool side = cd & 1;
         double lo, up;
         T v = VT::zero();
-        face_coeffs_k<K0>(t0, m, f, lo, up);
+        int own, nei;
+        face_cells(t0, t1, m, f, c, side, own, nei);
+        face_coeffs_k<K0>(t0, m, f, own, nei, lo, up);
         v = VT::add(v, VT::mul(os0, VT::splat(side ? lo : up)));
         if (HAS1)
         {
-            face_coeffs_k<K1>(t1, m, f, lo, up);
+            face_coeffs_k<K1>(t1, m, f, own, nei, lo, up);
             v = VT::add(v, VT::mul(os1, VT::splat(side ? lo : up)));
         }
         put(side ? k : k + 1, v);
@@ -334,7 +365,7 @@ k_assemble_fast(Terms terms, AsmMesh m, fvk_bfield bd, int ft0, int ft1, double*
                 {
                     const int cd = m.ent[s0 + k];
                     double lo, up;
-                    face_coeffs(t, m, cd >> 1, lo, up);
+                    face_coeffs(t, m, cd >> 1, c, cd & 1, lo, up);
                     d = VT::sub(d, VT::mul(os, VT::splat((cd & 1) ? up : lo)));
                 }
                 for (int e = s0 + nInt; e < s1; ++e)
@@ -354,7 +385,7 @@ k_assemble_fast(Terms terms, AsmMesh m, fvk_bfield bd, int ft0, int ft1, double*
                     }
                     else
                     { // gaussGreenLaplacian.cpp:156-175
-                        const double flux = t.faceField[f] * m.magSf[f];
+                        const double flux = lap_gamma_boundary(t, m, f, b) * m.magSf[f];
                         const double dcf = m.nodc[f];
                         valueMat = VT::splat(flux * os * vf1 * dcf);
                         d = VT::sub(d, valueMat);
@@ -448,8 +479,9 @@ k_assemble_affine(Terms terms, AsmMesh m, AsmAffine g, int ft0, int ft1, double*
 #pragma unroll
         for (int f = 0; f < 3; ++f)
         {
-            face_coeffs_k<K0>(t0, m, int(fs) + f, lo0[f], up0[f]);
-            if (HAS1) face_coeffs_k<K1>(t1, m, int(fs) + f, lo1[f], up1[f]);
+            const int nb = int(cell) + (f == 0 ? 1 : (f == 1 ? nx : int(nxy)));
+            face_coeffs_k<K0>(t0, m, int(fs) + f, int(cell), nb, lo0[f], up0[f]);
+            if (HAS1) face_coeffs_k<K1>(t1, m, int(fs) + f, int(cell), nb, lo1[f], up1[f]);
         }
 #pragma unroll
         for (int f = 0; f < 3; ++f)
@@ -473,17 +505,17 @@ k_assemble_affine(Terms terms, AsmMesh m, AsmAffine g, int ft0, int ft1, double*
     for (int e = tid; e < nCross; e += TB)
     {
         int co, ca, cb;
-        int64_t dFace;
-        if (e < nZ) { co = e % rl; ca = e / rl; cb = 0; dFace = -3 * nxy + int64_t(g.tx) * ny + int64_t(g.ty) * nx + 2; }
-        else if (e < nZ + nY) { const int e1 = e - nZ; co = e1 % rl; cb = e1 / rl; ca = 0; dFace = -3 * int64_t(nx) + g.tx + 1; }
-        else { const int e1 = e - nZ - nY; ca = e1 % ry; cb = e1 / ry; co = 0; dFace = -3; }
+        int64_t dFace, dOwner;
+        if (e < nZ) { co = e % rl; ca = e / rl; cb = 0; dFace = -3 * nxy + int64_t(g.tx) * ny + int64_t(g.ty) * nx + 2; dOwner = nxy; }
+        else if (e < nZ + nY) { const int e1 = e - nZ; co = e1 % rl; cb = e1 / rl; ca = 0; dFace = -3 * int64_t(nx) + g.tx + 1; dOwner = nx; }
+        else { const int e1 = e - nZ - nY; ca = e1 % ry; cb = e1 / ry; co = 0; dFace = -3; dOwner = 1; }
         const int ci = x0 + co, cj = y0 + ca, ck = z0 + cb;
         if (!(ci > 0 && ci < nx - 1 && cj > 0 && cj < ny - 1 && ck > 0 && ck < nz - 1)) continue; // consumer not regular
         const int64_t cc = ci + int64_t(nx) * cj + nxy * ck;
         const int64_t xf = 3 * cc - int64_t(g.tx) * (cj + int64_t(ny) * ck) - int64_t(g.ty) * ck * nx + dFace;
         double* s = coef + size_t(XB + e) * NCO;
-        face_coeffs_k<K0>(t0, m, int(xf), s[0], s[1]);
-        if (HAS1) face_coeffs_k<K1>(t1, m, int(xf), s[2], s[3]);
+        face_coeffs_k<K0>(t0, m, int(xf), int(cc - dOwner), int(cc), s[0], s[1]);
+        if (HAS1) face_coeffs_k<K1>(t1, m, int(xf), int(cc - dOwner), int(cc), s[2], s[3]);
     }
     __syncthreads();
     // ---- regular rows: [zL, yL, xL | diag | x, y, z]
@@ -645,7 +677,8 @@ int assemble_impl(const fvk_mesh* m, int nTerms, const fvk_term* terms_h, const 
                 needsBoundary = true;
                 break;
             case FVK_TERM_LAPLACIAN:
-                if (!t.faceField) return fvk_fail(FVK_EINVAL, "fvk_assemble: term %d: laplacian needs gamma", k);
+                if (!t.faceField && !(t.gammaCell && (t.gammaBoundary || m->nBoundaryFaces == 0)))
+                    return fvk_fail(FVK_EINVAL, "fvk_assemble: term %d: laplacian needs gamma (a face field, or gammaCell + gammaBoundary)", k);
                 needsBoundary = true;
                 break;
             case FVK_TERM_DDT:
@@ -668,7 +701,7 @@ int assemble_impl(const fvk_mesh* m, int nTerms, const fvk_term* terms_h, const 
     }
     // all rows incl. ghost rows: a ghost row's off-diagonals over the cut faces are read by updateFaceVelocity
     AsmMesh am {m->nCells, m->nInternalFaces, m->stencilSeg, m->gatherEnt, m->rowOffs, m->diagOffset, m->ownerOffset,
-                m->neighbourOffset, m->V, m->weights, m->nonOrthDeltaCoeffs, m->magSf, m->bDeltaCoeffs};
+                m->neighbourOffset, m->V, m->weights, m->nonOrthDeltaCoeffs, m->magSf, m->bDeltaCoeffs, m->owner, m->neighbour};
     const int grid = (m->nCells + 255) / 256;
     // fast path (k_assemble_fast): fresh system, rows in stencil order, one or two face terms
     int ft[2] = {-1, -1}, nFace = 0;

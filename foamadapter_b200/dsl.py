@@ -86,7 +86,11 @@ class Expression:
             if o.kind == "div":
                 terms.append(dict(kind=ops.TERM_DIV, scheme=o.scheme or 0, coeff=c.value, coeffView=c.view, faceField=o.faceField.internal))
             elif o.kind == "laplacian":
-                terms.append(dict(kind=ops.TERM_LAPLACIAN, coeff=c.value, coeffView=c.view, faceField=o.faceField.internal))
+                if isinstance(o.faceField, fvcc.InterpolatedSurfaceField):   # gamma interpolated on the fly
+                    src = o.faceField.src
+                    terms.append(dict(kind=ops.TERM_LAPLACIAN, coeff=c.value, coeffView=c.view, gammaCell=src.internal, gammaBoundary=src.boundary.value))
+                else:
+                    terms.append(dict(kind=ops.TERM_LAPLACIAN, coeff=c.value, coeffView=c.view, faceField=o.faceField.internal))
             elif o.kind == "source":
                 terms.append(dict(kind=ops.TERM_SOURCE, coeff=c.value, coeffView=c.view, cellField=o.cellField))
             elif o.kind == "ddt":

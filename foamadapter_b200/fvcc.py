@@ -102,6 +102,21 @@ class SurfaceField:
         return self.internal
 
 
+class InterpolatedSurfaceField:
+    """A surface field DEFINED as the linear interpolate of a volume field and never materialised:
+    `imp.laplacian(InterpolatedSurfaceField(rAU, "rAUf"), p)` makes the assembly kernel evaluate gamma_f = w rAU_P + (1 - w) rAU_N
+    on the fly with computeLinearInterpolation's arithmetic (interpolation/linear.cpp:30-45) -- same bits as
+    SurfaceInterpolation("linear").interpolate(rAU) followed by the laplacian, without the face-sized temporary."""
+
+    def __init__(self, src: "VolumeField", name: str):
+        if src.ncomp != 1:
+            raise ValueError("only scalar fields can be used as an interpolated diffusivity")
+        self.src, self.name, self.mesh, self.ncomp = src, name, src.mesh, 1
+
+    def materialise(self):
+        return SurfaceInterpolation(self.mesh, "linear").interpolate(self.src)
+
+
 class SurfaceInterpolation:
     """interpolation/surfaceInterpolation.hpp:54-69; keys "linear" | "upwind"."""
 

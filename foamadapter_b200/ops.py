@@ -136,7 +136,7 @@ TERM_DDT, TERM_DIV, TERM_LAPLACIAN, TERM_SOURCE = range(4)
 
 class _Term(C.Structure):
     _fields_ = [("kind", C.c_int32), ("scheme", C.c_int32), ("coeff", C.c_double), ("coeffView", C.c_void_p),
-                ("faceField", C.c_void_p), ("cellField", C.c_void_p), ("dt", C.c_double)]
+                ("faceField", C.c_void_p), ("cellField", C.c_void_p), ("dt", C.c_double), ("gammaCell", C.c_void_p), ("gammaBoundary", C.c_void_p)]
 
 
 class _BField(C.Structure):
@@ -158,7 +158,7 @@ def assemble(mesh, terms, boundary, values, rhs, bcMatrix=None, bcRhs=None, accu
     for i, t in enumerate(terms):
         keep += [t.get("coeffView"), t.get("faceField"), t.get("cellField")]
         arr[i] = _Term(int(t["kind"]), int(t.get("scheme", 0)), float(t.get("coeff", 1.0)), _p(t.get("coeffView")),
-                       _p(t.get("faceField")), _p(t.get("cellField")), float(t.get("dt", 0.0)))
+                       _p(t.get("faceField")), _p(t.get("cellField")), float(t.get("dt", 0.0)), _p(t.get("gammaCell")), _p(t.get("gammaBoundary")))
     bf = None
     if boundary is not None:
         bf = C.byref(_BField(_p(boundary.value), _p(boundary.refValue), _p(boundary.valueFraction), _p(boundary.refGrad)))

@@ -91,7 +91,7 @@ class IcoFoam:
     fixedWalls, p zeroGradient everywhere (tutorials/cavity/0.orig/{U,p}), nu uniform, momentumPredictor no."""
 
     def __init__(self, mesh: UnstructuredMesh, nu=0.01, dt=1e-4, fvSolution=None, fvSchemes=None, comm=None,
-                 lid=(1.0, 0.0, 0.0), history=False, check_every=8, graphs=True, compact_momentum=True, whole_step_graph=True):
+                 lid=(1.0, 0.0, 0.0), history=False, check_every=8, graphs=True, compact_momentum=True, whole_step_graph=True, fuse_interpolate=True):
         self.mesh = mesh
         fvSolution = fvSolution or CAVITY_FVSOLUTION
         self.rt = dsl.RunTime(mesh, dt, 0.0, fvSchemes or CAVITY_FVSCHEMES, fvSolution, comm, check_every, history)
@@ -106,7 +106,9 @@ class IcoFoam:
         # persistent work fields (the reference allocates these every corrector)
         self.rAU = fvcc.VolumeField(mesh, "rAU", 1, _extrapolated(mesh))
         self.HbyA = fvcc.VolumeField(mesh, "HbyA", 3, _extrapolated(mesh))
-        self.rAUf = fvcc.SurfaceField(mesh, "rAUf", 1)
+        # rAUf = linearInterpolate(rAU) (neoIcoFoam.cpp:117-124) is only ever the pressure laplacian's diffusivity: it is
+        # interpolated inside the assembly kernel instead of being written and re-read (fuse_interpolate=False: materialised)
+        self.rAUf = fvcc.InterpolatedSurfaceField(self.rAU, "rAUf") if fuse_interpolate else fvcc.SurfaceField(mesh, "rAUf", 1)
         self.phiHbyA = fvcc.SurfaceField(mesh, "phiHbyA", 1)
         self.Uls = la.LinearSystem(mesh, 3, zero=False, compact=compact_momentum and mesh_rows_in_stencil_order(mesh))
         self.pls = la.LinearSystem(mesh, 1, zero=False)
@@ -152,7 +154,8 @@ class IcoFoam:
         rAU, HbyA = computeRAUandHByA(self._UEqn, self.rAU, self.HbyA)     # :114
         constrainHbyA(U, p, HbyA)                                          # :115
         self._halo(rAU.internal, HbyA.internal)
-        self.linear.interpolate(rAU, self.rAUf)                            # :117-124
+        if not isinstance(self.rAUf, fvcc.InterpolatedSurfaceField):
+            self.linear.interpolate(rAU, self.rAUf)                        # :117-124
         flux(HbyA, self.phiHbyA)                                           # :126
         self._p_prepare()
 

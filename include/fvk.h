@@ -292,7 +292,7 @@ int fvk_correct_boundary_conditions(const fvk_mesh* mesh, int ncomp, const int32
  *   FVK_TERM_DIV        computeDivImp                    (operators/gaussGreenDiv.cpp:155-262)
  *                       faceField = faceFlux [nFaces], scheme = FVK_LINEAR | FVK_UPWIND
  *   FVK_TERM_LAPLACIAN  computeLaplacianImpl             (operators/gaussGreenLaplacian.cpp:76-177)
- *                       faceField = gamma [nFaces]
+ *                       faceField = gamma [nFaces] (or gammaCell / gammaBoundary, see fvk_term)
  *   FVK_TERM_SOURCE     SourceTerm::implicitOperation    (operators/sourceTerm.cpp:37-55)
  *                       cellField = coefficients (double[nCells])
  * coeff/coeffView = the operator's dsl::Coeff (a subtracted operator carries coeff = -1,
@@ -312,6 +312,11 @@ typedef struct fvk_term {
     const double* faceField; /* div: faceFlux, laplacian: gamma; [nFaces] */
     const double* cellField; /* ddt: old field T[nCells]; source: coefficients double[nCells] */
     double dt;
+    /* laplacian only, faceField == NULL: gamma is the LINEAR INTERPOLATE of this cell field [nCells] / its boundary values
+     * [nBoundaryFaces], evaluated on the fly with the arithmetic of computeLinearInterpolation (interpolation/linear.cpp:30-45)
+     * -- neoIcoFoam's laplacian(interpolate(rAU), p) (neoIcoFoam.cpp:117-124,141) without the face-sized rAUf temporary */
+    const double* gammaCell;
+    const double* gammaBoundary;
 } fvk_term;
 /* BoundaryData of the unknown field (fields/boundaryData.hpp:32-215), device pointers */
 typedef struct fvk_bfield {

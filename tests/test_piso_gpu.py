@@ -258,3 +258,34 @@ def test_fused_epilogues_equal_the_two_kernel_forms(dims):
         ops.rhs_sub_surface_integrate(gm, flux, rhs, -1.0, view)
         assert torch.equal(rhs, rhs_ref)
     lib().fvk_set_affine(C.c_int(1))
+
+
+def test_piso_step_is_identical_with_gamma_interpolated_inside_the_assembly():
+    """laplacian(interpolate(rAU), p): the assembly kernels (index-free, stencil-driven, generic) evaluate the linear
+    interpolate on the fly -- bit-identical to the materialised rAUf."""
+    import ctypes as C
+    from foamadapter_b200._capi import lib
+    d = piso.cavity_desc(12, True)
+    gm = M.UnstructuredMesh(d)
+    rng = np.random.default_rng(2)
+    rAU = fvcc.VolumeField(gm, "rAU", 1, [("extrapolated", 0.0)] * gm.nPatches)
+    rAU.internal.copy_(dev(rng.uniform(0.5, 1.5, gm.nCells))); rAU.correctBoundaryConditions()
+    p = fvcc.VolumeField(gm, "p", 1, [("fixedValue", 1.0)] + [("zeroGradient", 0.0)] * (gm.nPatches - 1)); p.correctBoundaryConditions()
+    rAUf = fvcc.SurfaceInterpolation(gm, "linear").interpolate(rAU)
+    ref = la.LinearSystem(gm, 1, zero=False)
+    ops.assemble(gm, [dict(kind=ops.TERM_LAPLACIAN, coeff=1.0, faceField=rAUf.internal)], p.boundary, ref.values, ref.rhs, ref.bcMatrix, ref.bcRhs)
+    lazy = [dict(kind=ops.TERM_LAPLACIAN, coeff=1.0, gammaCell=rAU.internal, gammaBoundary=rAU.boundary.value)]
+    for affine in (1, 0):
+        lib().fvk_set_affine(C.c_int(affine))
+        ls = la.LinearSystem(gm, 1, zero=False); ls.values.fill_(float("nan"))
+        ops.assemble(gm, lazy, p.boundary, ls.values, ls.rhs, ls.bcMatrix, ls.bcRhs)
+        assert torch.equal(ls.values, ref.values) and torch.equal(ls.rhs, ref.rhs) and torch.equal(ls.bcMatrix, ref.bcMatrix)
+    lib().fvk_set_affine(C.c_int(1))
+    ls = la.LinearSystem(gm, 1, zero=True)     # accumulate = generic kernel
+    ops.assemble(gm, lazy, p.boundary, ls.values, ls.rhs, ls.bcMatrix, ls.bcRhs, accumulate=True)
+    assert torch.equal(ls.values, ref.values)
+    a = piso.IcoFoam(M.UnstructuredMesh(d), nu=0.01, dt=5e-4, fuse_interpolate=True, graphs=False)
+    b = piso.IcoFoam(M.UnstructuredMesh(d), nu=0.01, dt=5e-4, fuse_interpolate=False, graphs=False)
+    for _ in range(3):
+        a.step(); b.step()
+    assert torch.equal(a.U.internal, b.U.internal) and torch.equal(a.p.internal, b.p.internal) and torch.equal(a.phi.internal, b.phi.internal)
