@@ -142,6 +142,28 @@ class MeshDesc:
         self.patch_names = list(patch_names or [f"patch{i}" for i in range(c.nPatches)])
         return self
 
+    def renumbered(self, method="morton", cellOldToNew=None):
+        """(new MeshDesc, cellOldToNew, faceOldToNew, faceFlipped): the mesh with its cells in reverse Cuthill-McKee ("rcm") or
+        Morton ("morton") order (or a given permutation), faces re-sorted into upper-triangular order (fvk_renumber_*) -- what
+        OpenFOAM's `renumberMesh` does to a case before the solver runs. A cell field moves as new[cellOldToNew] = old; a face
+        field as new[faceOldToNew] = old, negated where faceFlipped (face fluxes)."""
+        if cellOldToNew is None:
+            cellOldToNew = np.zeros(self.nCells, dtype=np.int32)
+            check(lib().fvk_renumber_order(C.byref(self._c), C.c_int({"rcm": 0, "morton": 1}[method]), cellOldToNew.ctypes.data_as(C.c_void_p)))
+        cellOldToNew = np.ascontiguousarray(cellOldToNew, dtype=np.int32)
+        out = C.POINTER(_CDesc)()
+        check(lib().fvk_renumber_apply(C.byref(self._c), cellOldToNew.ctypes.data_as(C.c_void_p), C.byref(out)))
+        new = MeshDesc()
+        new._c = out.contents
+        new._owned_ptr, new._owned_kind = out, "renumbered"
+        new.patch_names = list(self.patch_names)
+        pf, pflip = C.POINTER(C.c_int32)(), C.POINTER(C.c_uint8)()
+        check(lib().fvk_renumber_maps(out, C.byref(pf), C.byref(pflip)))
+        nF = self.nFaces
+        faceMap = np.ctypeslib.as_array(pf, shape=(nF,)).copy() if nF else np.zeros(0, np.int32)
+        flipped = np.ctypeslib.as_array(pflip, shape=(nF,)).copy().astype(bool) if nF else np.zeros(0, bool)
+        return new, cellOldToNew, faceMap, flipped
+
     @classmethod
     def uniform_1d(cls, nCells: int):
         """NeoN::create1DUniformMesh (src/NeoN/src/mesh/unstructured/unstructuredMesh.cpp:112-220):
@@ -172,6 +194,8 @@ class MeshDesc:
         if getattr(self, "_owned_ptr", None) is not None and _capi is not None and _capi._lib is not None:
             if getattr(self, "_owned_kind", "block") == "polymesh":
                 _capi._lib.fvk_polymesh_destroy(self._owned_ptr)
+            elif getattr(self, "_owned_kind", "block") == "renumbered":
+                _capi._lib.fvk_renumber_destroy(self._owned_ptr)
             else:
                 _capi._lib.fvk_blockmesh_destroy(self._owned_ptr)
             self._owned_ptr = None

@@ -165,6 +165,21 @@ int fvk_fieldfile_write(const char* path, const char* objectName, int32_t ncomp,
                         const int32_t* patchHasValue, const double* patchValues);
 
 /* ------------------------------------------------------------------------------------------------
+ * Cell renumbering for coalescing (HOST; BASELINE north_star "renumbered (RCM / space-filling) cell order"). The reference reads
+ * whatever order the polyMesh has (meshAdapter.cpp:59-136); OpenFOAM cases are renumbered beforehand with `renumberMesh`. This
+ * is that step for mesh descriptions: fvk_renumber_order computes cellOldToNew [nCells] (reverse Cuthill-McKee on the cell-cell
+ * graph, or Morton order of the cell centres); fvk_renumber_apply builds the renumbered description (arrays owned by the
+ * returned object): cells permuted, internal faces re-sorted into upper-triangular order (owner < neighbour; a face whose
+ * owner and neighbour swap gets -Sf), boundary faces and patches unchanged. fvk_renumber_maps gives faceOldToNew [nFaces] and
+ * faceFlipped [nFaces] (0/1: a face flux changes sign) to carry fields across. Renumber BEFORE decomposing.
+ * ---------------------------------------------------------------------------------------------- */
+enum { FVK_RENUMBER_RCM = 0, FVK_RENUMBER_MORTON = 1 };
+int fvk_renumber_order(const fvk_mesh_desc* desc_h, int method, int32_t* cellOldToNew);
+int fvk_renumber_apply(const fvk_mesh_desc* desc_h, const int32_t* cellOldToNew, fvk_mesh_desc** out);
+int fvk_renumber_maps(const fvk_mesh_desc* renumbered, const int32_t** faceOldToNew, const uint8_t** faceFlipped);
+int fvk_renumber_destroy(fvk_mesh_desc* renumbered);
+
+/* ------------------------------------------------------------------------------------------------
  * Device mesh handle. Uploads the description and builds, once per mesh:
  *   - BasicGeometryScheme weights / deltaCoeffs / nonOrthDeltaCoeffs
  *     (src/NeoN/src/finiteVolume/cellCentred/stencil/basicGeometryScheme.cpp:15-136),
