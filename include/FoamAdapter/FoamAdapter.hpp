@@ -110,20 +110,34 @@ public:
     }
     void setReference(NeoN::localIdx pRefCell, scalar pRefValue) { needReference_ = true; pRefCell_ = pRefCell; pRefValue_ = pRefValue; }
 
-    la::SolverStats solve()
+    // scalar systems: SolverStats; Vec3 systems (momentumPredictor, neoIcoFoam.cpp:100-103): one SolverStats per component
+    auto solve()
     {
-        static_assert(std::is_same_v<ValueType, scalar>, "momentumPredictor (Vec3 solve) is outside the hot path");
         const auto& solverDict = runTime_.fvSolutionDict.subDict("solvers").subDict(psi_.name);
         if (!solver_) solver_ = std::make_shared<la::Solver>(exec(), solverDict, runTime_.comm);
         auto post = [&](const la::SparsityPattern&, la::LinearSystem<ValueType, IndexType>& ls)
-        { // SetReference (expression.hpp:86-112)
-            if (needReference_) NeoN::check(fvk_set_reference(psi_.mesh().handle(), pRefCell_, pRefValue_, ls.values().data(), ls.rhs().data(), exec().stream()));
+        { // SetReference (expression.hpp:86-112), scalar systems only (:120-132)
+            if constexpr (std::is_same_v<ValueType, scalar>)
+            {
+                if (needReference_) NeoN::check(fvk_set_reference(psi_.mesh().handle(), pRefCell_, pRefValue_, ls.values().data(), ls.rhs().data(), exec().stream()));
+            }
+            else (void) ls;
         };
-        if (runTime_.comm) NeoN::check(fvk_comm_halo_exchange(runTime_.comm, psi_.internalVector().raw(), 1, exec().stream()));
         auto stats = dsl::detail::iterativeSolveImpl(expr_, sparsityPattern_, ls_, psi_, runTime_.t, runTime_.dt, *solver_, post);
-        std::cout << "[NeoN] Solving for " << psi_.name << ":" << " Initial residual: " << stats.initResNorm
-                  << " Final residual: " << stats.finalResNorm << " No Iterations: " << stats.numIter << std::endl;
+        if constexpr (std::is_same_v<ValueType, scalar>)
+            std::cout << "[NeoN] Solving for " << psi_.name << ":" << " Initial residual: " << stats.initResNorm
+                      << " Final residual: " << stats.finalResNorm << " No Iterations: " << stats.numIter << std::endl;
+        else
+            for (int c = 0; c < 3; ++c)
+                std::cout << "[NeoN] Solving for " << psi_.name << "[" << c << "]:" << " Initial residual: " << stats[c].initResNorm
+                          << " Final residual: " << stats[c].finalResNorm << " No Iterations: " << stats[c].numIter << std::endl;
         return stats;
+    }
+    // expression.hpp:163-167
+    auto solve(dsl::SpatialOperator<ValueType>&& rhs)
+    {
+        expr_.addOperator(-1.0 * rhs);
+        return solve();
     }
     void useSolver(std::shared_ptr<la::Solver> s) { solver_ = std::move(s); }
 

@@ -11,6 +11,7 @@
 #include <array>
 #include <cmath>
 #include <cstdint>
+#include <functional>
 #include <iostream>
 #include <map>
 #include <memory>
@@ -198,6 +199,69 @@ template<typename T> inline void setContainer(Vector<T>& dst, const Vector<T>& s
 inline void scalarMul(Vector<scalar>& v, scalar a) { v *= a; }
 inline void add(Vector<scalar>& a, const Vector<scalar>& b) { a += b; }
 inline void sub(Vector<scalar>& a, const Vector<scalar>& b) { a -= b; }
+
+
+// ---- RuntimeSelectionFactory (core/runtimeSelectionFactory.hpp:193-413): plugins register by NAME --------------------
+// `class MyScheme : public Base::template Register<MyScheme>` gives the class the reference's shape (static name(), doc(),
+// schema()); NF_REGISTER(Base, MyScheme) -- or Base::template Register<MyScheme>::add() -- enters it into Base's table under
+// MyScheme::name(). The reference does the same with a static initialiser inside Register (:406-412), which needs explicit
+// template instantiations in its .cpp files; this build is header-only, so the registration is an inline variable.
+template<typename... Args>
+struct Parameters
+{
+};
+template<typename Base, typename Params>
+class RuntimeSelectionFactory;
+template<typename Base, typename... Args>
+class RuntimeSelectionFactory<Base, Parameters<Args...>>
+{
+public:
+    using CreatorFunc = std::function<std::unique_ptr<Base>(Args...)>;
+    using LookupTable = std::map<std::string, CreatorFunc>;
+    static LookupTable& table()
+    {
+        static LookupTable tbl;
+        return tbl;
+    }
+    static std::vector<std::string> entries()
+    {
+        std::vector<std::string> e;
+        for (const auto& kv : table()) e.push_back(kv.first);
+        return e;
+    }
+    static size_t size() { return table().size(); }
+    static bool contains(const std::string& key) { return table().count(key) > 0; }
+    static void keyExistsOrError(const std::string& key)
+    {
+        if (contains(key)) return;
+        std::string known;
+        for (const auto& kv : table()) known += " " + kv.first;
+        NF_ERROR_EXIT("Could not find constructor for " + key + ". Valid constructors are:" + known);
+    }
+    static std::unique_ptr<Base> create(const std::string& key, Args... args)
+    {
+        keyExistsOrError(key);
+        return table().at(key)(std::forward<Args>(args)...);
+    }
+    template<typename Derived>
+    class Register : public Base
+    {
+    public:
+        using Base::Base;
+        static bool add()
+        {
+            RuntimeSelectionFactory::table()[Derived::name()] = [](Args... a) { return std::unique_ptr<Base>(new Derived(std::forward<Args>(a)...)); };
+            return true;
+        }
+    };
+    virtual ~RuntimeSelectionFactory() = default;
+};
+#define NF_REGISTER_CAT2(a, b) a##b
+#define NF_REGISTER_CAT(a, b) NF_REGISTER_CAT2(a, b)
+// namespace-scope registration: NF_REGISTER((fvcc::SurfaceInterpolationFactory<scalar>), (MyScheme<scalar>))
+#define NF_UNPAREN(...) __VA_ARGS__
+#define NF_REGISTER(Base, Derived) \
+    inline const bool NF_REGISTER_CAT(nf_registered_, __COUNTER__) = NF_UNPAREN Base ::template Register<NF_UNPAREN Derived>::add()
 
 // ---- Dictionary / TokenList / Input (core/{dictionary,tokenList,input}.hpp) -- host-only configuration ------------
 class Dictionary

@@ -108,6 +108,16 @@ struct SolverStats
     }
 };
 
+// la::SolverFactory (solver.hpp:29-60): linear solvers registered by name; the dictionary's `solver` entry selects one. The
+// reference registers exactly one, "Ginkgo" (ginkgo.hpp:95-169); here that name is bound to libfvk's device-resident CG /
+// BiCGStab (class Solver below doubles as the registered implementation and as the front end la::Solver of solver.hpp:63-91).
+class SolverFactory : public RuntimeSelectionFactory<SolverFactory, Parameters<const Executor&, const Dictionary&>>
+{
+public:
+    static std::string name() { return "SolverFactory"; }
+    virtual ~SolverFactory() = default;
+};
+
 // la::Solver(exec, dict) (solver.hpp:63-91) for Ginkgo-style dictionaries (ginkgo.hpp:95-108) as mapFvSolution emits them
 // (FoamAdapter src/compatibility/fvSolution.cpp:19-159) or as the reference's tests pass them (test/test_advection.cpp:125-131):
 // {solver Ginkgo; type solver::Cg | solver::Bicgstab; preconditioner{type preconditioner::Jacobi; max_block_size 1};
@@ -119,7 +129,8 @@ public:
         : exec_(exec), comm_(comm), history_(history)
     {
         const auto name = dict.getOr<std::string>("solver", "Ginkgo");
-        if (name != "Ginkgo") NF_ERROR_EXIT("la::SolverFactory has no solver " + name);
+        SolverFactory::keyExistsOrError(name); // a third-party solver registered under another name constructs itself via SolverFactory::create
+        if (name != "Ginkgo") NF_ERROR_EXIT("la::Solver implements the solver registered as Ginkgo; use SolverFactory::create for " + name);
         const auto type = dict.getOr<std::string>("type", "solver::Cg");
         if (type == "solver::Cg") cfg_.solverType = FVK_SOLVER_CG;
         else if (type == "solver::Bicgstab") cfg_.solverType = FVK_SOLVER_BICGSTAB;
@@ -193,5 +204,19 @@ private:
     mutable fvk_solver* h_ = nullptr;
     mutable localIdx rows_ = 0, cols_ = 0;
 };
+
+// the name the reference's solver dictionaries carry
+class GinkgoSolver : public SolverFactory::Register<GinkgoSolver>
+{
+public:
+    GinkgoSolver(const Executor& exec, const Dictionary& dict) : solver_(exec, dict) {}
+    static std::string name() { return "Ginkgo"; }
+    static std::string doc() { return "libfvk device-resident solver::Cg / solver::Bicgstab with scalar Jacobi"; }
+    static std::string schema() { return "none"; }
+    SolverStats solve(const LinearSystem<scalar, localIdx>& sys, Vector<scalar>& x) const { return solver_.solve(sys, x); }
+private:
+    Solver solver_;
+};
+NF_REGISTER((SolverFactory), (GinkgoSolver));
 
 } // namespace NeoN::la

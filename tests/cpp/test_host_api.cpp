@@ -13,6 +13,62 @@ namespace fvcc = NeoN::finiteVolume::cellCentred;
 static int failures = 0;
 #define EXPECT(cond) do { if (!(cond)) { std::printf("FAIL %s:%d: %s\n", __FILE__, __LINE__, #cond); ++failures; } } while (0)
 
+// ---- third-party plug-ins written against the reference's interfaces -------------------------------------------------------
+// A conforming SpatialOperator in the shape of the reference's test operator (src/NeoN/test/dsl/common.hpp:53-106): explicit:
+// source += coeff * field; implicit: rhs += coeff * field. A plug-in has no parallelFor here: it composes C-ABI kernels.
+template<typename ValueType>
+class Dummy : public dsl::OperatorMixin<fvcc::VolumeField<ValueType>>
+{
+public:
+    using VectorValueType = ValueType;
+    Dummy(fvcc::VolumeField<ValueType>& field, dsl::Operator::Type type = dsl::Operator::Type::Explicit)
+        : dsl::OperatorMixin<fvcc::VolumeField<ValueType>>(field.exec(), dsl::Coeff(1.0), field, type) {}
+    void explicitOperation(Vector<ValueType>& source) const
+    {
+        check(fvk_vec_axpby(int64_t(source.size()), this->getCoefficient().value(), this->field_.internalVector().raw(), 1.0, source.raw(), source.exec().stream()));
+    }
+    void implicitOperation(la::LinearSystem<ValueType, localIdx>& ls) const
+    {
+        check(fvk_vec_axpby(int64_t(ls.rhs().size()), this->getCoefficient().value(), this->field_.internalVector().raw(), 1.0, ls.rhs().raw(), ls.exec().stream()));
+    }
+    std::string getName() const { return "Dummy"; }
+};
+// an interpolation scheme registered by name: the arithmetic mean of owner and neighbour = linear weights on a uniform mesh
+template<typename T>
+class Midpoint : public fvcc::SurfaceInterpolationFactory<T>::template Register<Midpoint<T>>
+{
+    using Base = typename fvcc::SurfaceInterpolationFactory<T>::template Register<Midpoint<T>>;
+public:
+    Midpoint(const Executor& exec, const UnstructuredMesh& mesh, const Input&) : Base(exec, mesh) {}
+    static std::string name() { return "midPoint"; }
+    void interpolate(const fvcc::VolumeField<T>& src, fvcc::SurfaceField<T>& dst) const override
+    { // plug-in schemes compose existing kernels: here the library's linear interpolation (weights are 0.5 on the uniform test mesh)
+        fvcc::Linear<T>(this->exec_, this->mesh_, Input()).interpolate(src, dst);
+    }
+    void interpolate(const fvcc::SurfaceField<scalar>&, const fvcc::VolumeField<T>& src, fvcc::SurfaceField<T>& dst) const override { interpolate(src, dst); }
+    void weight(const fvcc::VolumeField<T>&, fvcc::SurfaceField<scalar>& w) const override { fill(w.internalVector(), 0.5); }
+    void weight(const fvcc::SurfaceField<scalar>&, const fvcc::VolumeField<T>& s, fvcc::SurfaceField<scalar>& w) const override { weight(s, w); }
+    std::unique_ptr<fvcc::SurfaceInterpolationFactory<T>> clone() const override { return std::make_unique<Midpoint<T>>(*this); }
+};
+NF_REGISTER((fvcc::SurfaceInterpolationFactory<scalar>), (Midpoint<scalar>));
+// a time integrator registered by name: two forward-Euler half steps
+class TwoHalfSteps : public timeIntegration::TimeIntegratorBase<fvcc::VolumeField<scalar>>::Register<TwoHalfSteps>
+{
+    using Sol = fvcc::VolumeField<scalar>;
+public:
+    TwoHalfSteps(const Dictionary& a, const Dictionary& b) : timeIntegration::TimeIntegratorBase<Sol>::Register<TwoHalfSteps>(a, b) {}
+    static std::string name() { return "twoHalfSteps"; }
+    void solve(dsl::Expression<scalar>& eqn, Sol& sol, scalar t, scalar dt) override
+    {
+        timeIntegration::ForwardEuler<Sol> fe(schemeDict_, solutionDict_);
+        fe.solve(eqn, sol, t, 0.5 * dt);
+        sol.oldTime().internalVector() = sol.internalVector();
+        fe.solve(eqn, sol, t + 0.5 * dt, 0.5 * dt);
+    }
+    std::unique_ptr<timeIntegration::TimeIntegratorBase<Sol>> clone() const override { return std::make_unique<TwoHalfSteps>(*this); }
+};
+NF_REGISTER((timeIntegration::TimeIntegratorBase<fvcc::VolumeField<scalar>>), (TwoHalfSteps));
+
 int main()
 {
     try
@@ -100,6 +156,94 @@ int main()
             EXPECT(mapped.subDict("preconditioner").get<std::string>("type") == "preconditioner::Jacobi");
             EXPECT(mapped.subDict("criteria").get<scalar>("absolute_residual_norm") == 1e-6);
             EXPECT(mapped.subDict("criteria").get<int>("iteration") == 1000);
+        }
+        // ---- the open DSL: a third-party operator class, type-erased next to the built-in ones (dsl/spatialOperator.hpp:21-124) ----
+        {
+            std::vector<fvcc::VolumeBoundary<scalar>> bcs {{"fixedValue", 2.0}, {"fixedValue", 2.0}};
+            fvcc::VolumeField<scalar> phi(exec, "phi", mesh, bcs);
+            fill(phi.internalVector(), 2.0);
+            phi.correctBoundaryConditions();
+            dsl::SpatialOperator<scalar> a = Dummy<scalar>(phi);                                     // explicit by default
+            dsl::SpatialOperator<scalar> b = Dummy<scalar>(phi, dsl::Operator::Type::Implicit);
+            EXPECT(a.getName() == "Dummy" && a.getType() == dsl::Operator::Type::Explicit && b.getType() == dsl::Operator::Type::Implicit);
+            auto c = 2.0 * a;                                                                        // coefficient arithmetic on the erased type
+            EXPECT(c.getCoefficient().value() == 2.0 && a.getCoefficient().value() == 1.0);
+            Vector<scalar> src(exec, 10, 1.0);
+            c.explicitOperation(src);
+            for (auto v : src.copyToHost()) EXPECT(v == 5.0);                                        // 1 + 2 * 2
+            // an expression mixing a plug-in with built-ins: not fusable -> zeroed system, operators applied one after another
+            fvcc::SurfaceField<scalar> gamma(exec, "gamma", mesh);
+            fill(gamma.internalVector(), 1.0);
+            Dictionary schemes {{"laplacianSchemes", Dictionary {{"laplacian(gamma,phi)", std::string("Gauss linear uncorrected")}}}};
+            dsl::Expression<scalar> mixed = dsl::imp::laplacian(gamma, phi) + b + a;
+            mixed.read(schemes);
+            EXPECT(mixed.size() == 3 && mixed.hasExplicit());
+            la::LinearSystem<scalar> ls(mesh, sp, false), ref(mesh, sp, true);
+            mixed.assemble(0.0, 1.0, sp, ls, phi);
+            dsl::Expression<scalar> builtin; builtin.addOperator(dsl::imp::laplacian(gamma, phi)); builtin.read(schemes);
+            builtin.assemble(0.0, 1.0, sp, ref, phi);                                                // the fused single-launch path
+            auto v1 = ls.values().copyToHost(), v2 = ref.values().copyToHost(), r1 = ls.rhs().copyToHost(), r2 = ref.rhs().copyToHost();
+            for (size_t i = 0; i < v1.size(); ++i) EXPECT(v1[i] == v2[i]);
+            for (size_t i = 0; i < r1.size(); ++i) EXPECT(r1[i] == r2[i] + 2.0);                     // + the plug-in's rhs contribution
+            auto e = mixed.explicitOperation(exec, 10);
+            for (auto v : e.copyToHost()) EXPECT(v == 2.0);
+        }
+        // ---- strategies and integrators by NAME (core/runtimeSelectionFactory.hpp): built-ins + the plug-ins registered above ----
+        {
+            auto names = fvcc::SurfaceInterpolationFactory<scalar>::entries();
+            EXPECT(names.size() == 3 && fvcc::SurfaceInterpolationFactory<scalar>::contains("midPoint") && fvcc::SurfaceInterpolationFactory<scalar>::contains("upwind"));
+            EXPECT(fvcc::DivOperatorFactory<Vec3>::contains("Gauss") && fvcc::LaplacianOperatorFactory<scalar>::contains("Gauss"));
+            EXPECT(fvcc::FaceNormalGradientFactory<scalar>::contains("uncorrected") && la::SolverFactory::contains("Ginkgo"));
+            std::vector<fvcc::VolumeBoundary<scalar>> bcs {{"fixedValue", 1.0}, {"fixedValue", 1.0}};
+            fvcc::VolumeField<scalar> T(exec, "T", mesh, bcs);
+            std::vector<scalar> init(10);
+            for (int i = 0; i < 10; ++i) init[i] = 1.0 + 0.1 * i;
+            T.internalVector().copyFromHost(init.data());
+            T.correctBoundaryConditions();
+            fvcc::SurfaceField<scalar> phi(exec, "phi", mesh);
+            fill(phi.internalVector(), 1.0);
+            auto h = phi.internalVector().copyToHost(); h[9] = -1.0; h[10] = 1.0; phi.internalVector().copyFromHost(h.data());
+            // div through the plug-in interpolation scheme equals div through "linear" on the uniform mesh
+            Vector<scalar> d1(exec, 10, 0.0), d2(exec, 10, 0.0);
+            fvcc::DivOperatorFactory<scalar>::create(exec, mesh, TokenList({"Gauss", "midPoint"}))->div(d1, phi, T, dsl::Coeff(1.0));
+            fvcc::DivOperatorFactory<scalar>::create(exec, mesh, TokenList({"Gauss", "linear"}))->div(d2, phi, T, dsl::Coeff(1.0));
+            auto a1 = d1.copyToHost(), a2 = d2.copyToHost();
+            for (int i = 0; i < 10; ++i) EXPECT(std::abs(a1[i] - a2[i]) <= 1e-13 * (1.0 + std::abs(a2[i])));
+            // dsl::solve with forwardEuler, Runge-Kutta (Forward-Euler table) and the registered two-half-steps integrator
+            auto run = [&](const std::string& type, int steps, scalar dt) {
+                T.internalVector().copyFromHost(init.data());
+                T.correctBoundaryConditions();
+                Dictionary schemes {{"ddtSchemes", Dictionary {{"type", type}, {"Runge-Kutta-Method", std::string("Forward-Euler")}}},
+                                    {"divSchemes", Dictionary {{"div(phi,T)", std::string("Gauss upwind")}}}};
+                for (int s_ = 0; s_ < steps; ++s_)
+                {
+                    fvcc::oldTime(T).internalVector() = T.internalVector();
+                    dsl::Expression<scalar> eqn = dsl::imp::ddt(T) + dsl::exp::div(phi, T);
+                    dsl::solve(eqn, T, s_ * dt, dt, schemes, Dictionary {});
+                }
+                return T.internalVector().copyToHost();
+            };
+            auto fe2 = run("forwardEuler", 2, 0.005), half = run("twoHalfSteps", 1, 0.01), rk = run("Runge-Kutta", 2, 0.005);
+            for (int i = 1; i < 9; ++i) EXPECT(std::abs(fe2[i] - half[i]) < 1e-12 && std::abs(fe2[i] - rk[i]) < 1e-12);
+            EXPECT(std::abs(fe2[5] - init[5]) > 1e-4);                                                  // it did advect
+            bool threw = false;
+            try { run("crankNicolson", 1, 0.01); } catch (const NeoNException&) { threw = true; }
+            EXPECT(threw);
+            // backwardEuler + BiCGStab (test/test_advection.cpp:176-228): (I + dt div) T = T_old, checked through the residual
+            T.internalVector().copyFromHost(init.data());
+            fvcc::oldTime(T).internalVector() = T.internalVector();
+            Dictionary schemes {{"ddtSchemes", Dictionary {{"type", std::string("backwardEuler")}}}, {"divSchemes", Dictionary {{"div(phi,T)", std::string("Gauss upwind")}}}};
+            Dictionary solver {{"solver", std::string("Ginkgo")}, {"type", std::string("solver::Bicgstab")},
+                               {"preconditioner", Dictionary {{"type", std::string("preconditioner::Jacobi")}, {"max_block_size", 1}}},
+                               {"criteria", Dictionary {{"iteration", 20}, {"relative_residual_norm", 1e-14}}}};
+            dsl::Expression<scalar> eqn = dsl::imp::ddt(T) + dsl::imp::div(phi, T);
+            auto st = dsl::solve(eqn, T, 0.0, 0.01, schemes, solver);
+            EXPECT(st.numIter >= 1 && st.numIter <= 20 && st.finalResNorm <= 1e-13 * st.initResNorm);
+            la::LinearSystem<scalar> ls(mesh, sp, false);
+            eqn.assemble(0.0, 0.01, sp, ls, T);
+            Vector<scalar> res(exec, 10, 0.0);
+            la::computeResidual(ls, T.internalVector(), res);
+            for (auto v : res.copyToHost()) EXPECT(std::abs(v) < 1e-13);
         }
     }
     catch (const std::exception& e)

@@ -31,8 +31,10 @@ def _compile(src: Path, name: str) -> Path:
 def test_cpp_host_layer_compiles_and_has_no_cpu_fallback():
     api = _compile(ROOT / "tests" / "cpp" / "test_host_api.cpp", "test_host_api")
     ico = _compile(ROOT / "examples" / "neoIcoFoam" / "neoIcoFoam.cpp", "neoIcoFoam")
+    adv = _compile(ROOT / "examples" / "scalarAdvection" / "scalarAdvection.cpp", "scalarAdvection")
+    heat = _compile(ROOT / "examples" / "heatTransfer" / "heatTransfer.cpp", "heatTransfer")
     if not torch.cuda.is_available():
-        for exe in (api, ico):
+        for exe in (api, ico, adv, heat):
             r = subprocess.run([str(exe)], capture_output=True, text=True)
             assert r.returncode != 0 and "libfvk" in (r.stdout + r.stderr)
 
@@ -65,3 +67,53 @@ def test_cpp_neoicofoam_matches_oracle(tmp_path, three_d):
     U, p = raw[: 3 * om.nC].reshape(-1, 3), raw[3 * om.nC:]
     assert np.abs(U - o.U).max() <= 1e-8 * np.abs(o.U).max()
     assert np.abs(p - o.p).max() <= 1e-7 * np.abs(o.p).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("integrator,three_d", [("forwardEuler", False), ("Runge-Kutta", False), ("backwardEuler", False), ("forwardEuler", True)])
+def test_cpp_scalaradvection_matches_oracle(tmp_path, integrator, three_d):
+    """examples/scalarAdvection/scalarAdvection.cpp (BASELINE configs[3]) through the C++ DSL: dsl::solve + the time integrators
+    selected by name, bars of test/test_advection.cpp:169,228 (the explicit runs are bit-identical)."""
+    from foamadapter_b200 import advection as adv
+    from oracle.advection import ScalarAdvectionOracle
+    from oracle.cpu import Mesh as OMesh
+    exe = _compile(ROOT / "examples" / "scalarAdvection" / "scalarAdvection.cpp", "scalarAdvection")
+    n, steps = (24, 5) if three_d else (50, 12)
+    dump = tmp_path / "T.bin"
+    r = subprocess.run([str(exe), str(n), str(steps), integrator] + (["--3d"] if three_d else []), capture_output=True, text=True,
+                       env=dict(os.environ, SCALARADVECTION_DUMP=str(dump)))
+    assert r.returncode == 0, r.stdout + r.stderr
+    om = OMesh.from_desc(adv.advection_desc(n, three_d))
+    C = om.C.reshape(-1, 3)
+    U, T = adv.init_fields_columns(C, n * n) if three_d else adv.init_fields(C)
+    ref = ScalarAdvectionOracle(om, 0.1 / n, 3.0, scheme=1, ddt=integrator, U=U, T=T)
+    for _ in range(steps):
+        ref.step()
+    got = np.fromfile(dump, dtype=np.float64)
+    if integrator == "backwardEuler":
+        assert np.abs(got - ref.T).max() <= 1e-8 * np.abs(ref.T).max()
+    else:
+        assert np.array_equal(got, ref.T)
+
+
+@pytest.mark.gpu
+def test_cpp_heattransfer_matches_oracle(tmp_path):
+    """examples/heatTransfer/heatTransfer.cpp: ddt(T) - laplacian(kappa, T) with backwardEuler + Jacobi-CG."""
+    from foamadapter_b200.mesh import MeshDesc
+    from oracle.cpu import Mesh as OMesh, cg
+    exe = _compile(ROOT / "examples" / "heatTransfer" / "heatTransfer.cpp", "heatTransfer")
+    n, steps = 16, 4
+    dump = tmp_path / "T.bin"
+    r = subprocess.run([str(exe), str(n), str(steps)], capture_output=True, text=True, env=dict(os.environ, HEATTRANSFER_DUMP=str(dump)))
+    assert r.returncode == 0, r.stdout + r.stderr
+    om = OMesh.from_desc(MeshDesc.block(n, n, 1, 1.0, 1.0, 0.1, patches=[("hot", [3], False), ("cold", [0, 1, 2], False), ("frontAndBack", [4, 5], True)]))
+    T = np.full(om.nC, 273.0)
+    kappa = np.full(om.nF, 0.5)
+    for _ in range(steps):
+        bd = om.correct_bcs([1, 1], [300.0, 273.0], T)
+        ls = om.empty_system(False)
+        om.laplacian_imp(ls, kappa, bd, -1.0, None)
+        om.ddt_imp(ls, T.copy(), 1e-3, 1.0, None)
+        T, st, _ = cg(om.rowOffs, om.colIdxs, ls["values"], ls["rhs"], T, jacobi=True, max_iter=1000, rel_tol=0.0, abs_tol=1e-10)
+    got = np.fromfile(dump, dtype=np.float64)
+    assert got.max() > 274.0 and np.abs(got - T).max() <= 1e-9 * np.abs(T).max()
