@@ -114,7 +114,11 @@ int main()
             for (auto v : out.copyToHost()) EXPECT(std::abs(v) < 1e-8);
             // implicit: A phi - b == 0
             auto op = dsl::imp::laplacian(gamma, phi);
+            bool threw = false;
             la::LinearSystem<scalar> ls(mesh, sp, true);
+            try { op.implicitOperation(ls); } catch (const NeoNException&) { threw = true; }   // no strategy before read(), as in the reference
+            EXPECT(threw);
+            op.read(Dictionary {{"laplacianSchemes", Dictionary {{"laplacian(gamma,phi)", std::string("Gauss linear uncorrected")}}}});
             op.implicitOperation(ls);
             Vector<scalar> res(exec, 10, 0.0);
             la::computeResidual(ls, phi.internalVector(), res);

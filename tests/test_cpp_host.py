@@ -90,10 +90,11 @@ def test_cpp_scalaradvection_matches_oracle(tmp_path, integrator, three_d):
     for _ in range(steps):
         ref.step()
     got = np.fromfile(dump, dtype=np.float64)
-    if integrator == "backwardEuler":
-        assert np.abs(got - ref.T).max() <= 1e-8 * np.abs(ref.T).max()
-    else:
-        assert np.array_equal(got, ref.T)
+    # the reference's own bars (test_advection.cpp:169,228). Not bit-equality here: the example evaluates createFields.H with the
+    # C++ compiler's sin / pow / exp (g++ folds pow(x, 2.0) into x * x), the oracle with Python's libm calls -- the INPUT fields
+    # differ in the last bit of a few cells; with identical inputs the explicit path is bit-identical (tests/test_advection_gpu.py)
+    tol = 1e-8 if integrator == "backwardEuler" else 1e-10
+    assert np.abs(got - ref.T).max() <= tol * np.abs(ref.T).max()
 
 
 @pytest.mark.gpu
