@@ -204,4 +204,13 @@ struct fvk_mesh
     // halo overlap (fvk_mesh_set_tile_phase): 0 = operators compute every cell, 1 = only tiles that read no ghost
     // cell, 2 = only tiles that do
     int tilePhase = 0;
+    // multicolour ordering of the cells for the DIC preconditioner (fvk_mesh_ensure_colors, built on first use): color [nCells]
+    // (device), the owned cells sorted by colour (device) and the colour segments (host)
+    mutable uint8_t* dicColor = nullptr;
+    mutable int32_t* dicCells = nullptr;
+    mutable int32_t dicOff[66] = {0};
+    mutable int32_t dicNColors = 0;
 };
+// greedy colouring of the owned rows of the mesh's own sparsity pattern in natural cell order (no two coupled cells share a
+// colour); cached in the handle. Returns an FVK_* code.
+int fvk_mesh_ensure_colors(const fvk_mesh* m);

@@ -138,7 +138,7 @@ __global__ void k_decide_after_spmv(PcgState* st)
 __global__ void k_set_normB(PcgState* st) { st->normB = sqrt(st->sums[3]); }
 
 // ---- K1: x += alpha p; r -= alpha q; z = M^-1 r; r.z; r.r ------------------------------------------
-template <bool FIRST, bool JACOBI>
+template <bool FIRST, int JACOBI /* 0 none, 1 scalar Jacobi, 2 external (DIC): z and r.z are produced by the kernels that follow */>
 __global__ void __launch_bounds__(TB)
 k_cg_update(int n, PcgState* __restrict__ st, double* __restrict__ x, const double* __restrict__ p,
             const double* __restrict__ q, const double* rIn, double* rOut, const double* __restrict__ dinv,
@@ -166,7 +166,7 @@ k_cg_update(int n, PcgState* __restrict__ st, double* __restrict__ x, const doub
             const int c = ctx.sendCells[i];
             double ri = rIn[c];
             if (!FIRST) ri = ri - alpha * q[c];
-            const double zi = JACOBI ? ri * dinv[c] : ri;
+            const double zi = JACOBI == 1 ? ri * dinv[c] : ri;
             // the neighbour's ghost entry of ITS z (same parity): it reads it like any other column
             double* dst = reinterpret_cast<double*>(ctx.win[ctx.nbrRank[k]] + FVK_P2P_Z_OFF(ctx.peerGhost[k]))
                           + (hseq & 1) * size_t(ctx.peerOwned[k] + ctx.peerGhost[k]) + ctx.peerOwned[k] + ctx.peerRecvOff[k] + (i - ctx.sendOff[k]);
@@ -183,9 +183,12 @@ k_cg_update(int n, PcgState* __restrict__ st, double* __restrict__ x, const doub
             ri = ri - alpha * q[i];
             rOut[i] = ri;
         }
-        const double zi = JACOBI ? ri * dinv[i] : ri;
-        z[i] = zi;
-        acc[0] += ri * zi;
+        const double zi = JACOBI == 1 ? ri * dinv[i] : ri;
+        if (JACOBI != 2)
+        {
+            z[i] = zi;
+            acc[0] += ri * zi;
+        }
         acc[1] += ri * ri;
     }
     double tot[2];
@@ -226,7 +229,81 @@ k_cg_update(int n, PcgState* __restrict__ st, double* __restrict__ x, const doub
     {
         st->sums[0] = tot[0];
         st->sums[1] = tot[1];
-        if (!distributed) decide_after_update(st, hist);
+        if (!distributed && JACOBI != 2) decide_after_update(st, hist);
+    }
+}
+
+// ---- multicolour DIC (diagonal incomplete Cholesky, OpenFOAM's DIC recurrences applied in COLOUR order) ---------------------
+// Extension (the reference maps DIC to scalar Jacobi, fvSolution.cpp:51-55): M = (D* + L) D*^-1 (D* + U) with L / U
+// the couplings to cells of lower / higher colour and D* chosen so that diag(M) = diag(A). Cells of one colour are not
+// coupled, so every step is one fully parallel kernel over that colour's cells (a hex block needs 2 colours: apply = 3 kernels).
+__global__ void __launch_bounds__(TB)
+k_dic_diag(int n0, int n1, const int* __restrict__ cells, const int* __restrict__ rowOffs, const int* __restrict__ colIdxs,
+           const double* __restrict__ values, const uint8_t* __restrict__ color, int c, int nRows, double* __restrict__ dinvStar)
+{
+    const int idx = n0 + blockIdx.x * TB + threadIdx.x;
+    if (idx >= n1) return;
+    const int i = cells[idx];
+    double d = 0.0;
+    for (int k = rowOffs[i]; k < rowOffs[i + 1]; ++k)
+    {
+        const int j = colIdxs[k];
+        const double a = values[k];
+        if (j == i) d += a;
+        else if (j < nRows && color[j] < c) d -= a * a * dinvStar[j];
+    }
+    dinvStar[i] = 1.0 / d;
+}
+// forward substitution of colour c: z_i = (r_i - sum_{colour(j) < c} a_ij z_j) / D*_i
+__global__ void __launch_bounds__(TB)
+k_dic_fwd(int n0, int n1, const PcgState* __restrict__ st, const int* __restrict__ cells, const int* __restrict__ rowOffs,
+          const int* __restrict__ colIdxs, const double* __restrict__ values, const uint8_t* __restrict__ color, int c, int nRows,
+          const double* __restrict__ dinvStar, const double* __restrict__ r, double* __restrict__ z)
+{
+    if (st->done) return;
+    const int idx = n0 + blockIdx.x * TB + threadIdx.x;
+    if (idx >= n1) return;
+    const int i = cells[idx];
+    double s = r[i];
+    if (c > 0)
+        for (int k = rowOffs[i]; k < rowOffs[i + 1]; ++k)
+        {
+            const int j = colIdxs[k];
+            if (j != i && j < nRows && color[j] < c) s -= values[k] * z[j];
+        }
+    z[i] = s * dinvStar[i];
+}
+// backward substitution of colour c: z_i -= (sum_{colour(j) > c} a_ij z_j) / D*_i
+__global__ void __launch_bounds__(TB)
+k_dic_bwd(int n0, int n1, const PcgState* __restrict__ st, const int* __restrict__ cells, const int* __restrict__ rowOffs,
+          const int* __restrict__ colIdxs, const double* __restrict__ values, const uint8_t* __restrict__ color, int c, int nRows,
+          const double* __restrict__ dinvStar, double* __restrict__ z)
+{
+    if (st->done) return;
+    const int idx = n0 + blockIdx.x * TB + threadIdx.x;
+    if (idx >= n1) return;
+    const int i = cells[idx];
+    double s = 0.0;
+    for (int k = rowOffs[i]; k < rowOffs[i + 1]; ++k)
+    {
+        const int j = colIdxs[k];
+        if (j != i && j < nRows && color[j] > c) s += values[k] * z[j];
+    }
+    z[i] = z[i] - dinvStar[i] * s;
+}
+// r.z after an external preconditioner, then the stopping test / beta (the tail of k_cg_update)
+__global__ void __launch_bounds__(TB)
+k_cg_rz_decide(int n, PcgState* __restrict__ st, const double* __restrict__ r, const double* __restrict__ z, double* __restrict__ partial,
+               unsigned* __restrict__ counter, double* __restrict__ hist)
+{
+    if (st->done) return;
+    double acc[1] = {0.0};
+    for (int i = blockIdx.x * TB + threadIdx.x; i < n; i += gridDim.x * TB) acc[0] += r[i] * z[i];
+    double tot[1];
+    if (grid_sum<1>(acc, partial, counter, tot) && threadIdx.x == 0)
+    {
+        st->sums[0] = tot[0];
+        decide_after_update(st, hist);
     }
 }
 
@@ -834,6 +911,7 @@ struct fvk_solver
     SpmvAffine aff {0, 0, 0, 0}; // set by fvk_solver_attach_mesh
     const int32_t *affRowOffs = nullptr, *affColIdxs = nullptr; // the attached mesh's pattern: aff applies to these arrays only
     const uint8_t* affDiagOffs = nullptr;                       // its diagOffset (Jacobi diagonal without a row scan)
+    const fvk_mesh* attached = nullptr;                         // the attached mesh (DIC needs its colouring)
     double *r2 = nullptr; // second residual buffer of the peer-memory mode
     double *rr = nullptr, *sB = nullptr, *tB = nullptr; // BiCGStab: shadow residual, s, t
     double *vals0 = nullptr, *bC = nullptr, *xC = nullptr; // Vec3 solves: component matrix / rhs / solution (lazy)
@@ -874,7 +952,8 @@ extern "C" int fvk_solver_destroy(fvk_solver* sv)
 extern "C" int fvk_solver_create(int32_t nRows, int32_t nCols, const fvk_solver_config* cfg, fvk_comm* comm, fvk_solver** out)
 {
     if (!cfg || !out || nRows <= 0 || nCols < nRows) return fvk_fail(FVK_EINVAL, "fvk_solver_create: bad argument");
-    if (cfg->maxIter < 0 || cfg->checkEvery < 1 || (cfg->preconditioner != FVK_PRECOND_NONE && cfg->preconditioner != FVK_PRECOND_JACOBI)
+    if (cfg->maxIter < 0 || cfg->checkEvery < 1 || cfg->preconditioner < FVK_PRECOND_NONE || cfg->preconditioner > FVK_PRECOND_DIC
+        || (cfg->preconditioner == FVK_PRECOND_DIC && (cfg->solverType != FVK_SOLVER_CG || comm))
         || (cfg->solverType != FVK_SOLVER_CG && cfg->solverType != FVK_SOLVER_BICGSTAB))
         return fvk_fail(FVK_EINVAL, "fvk_solver_create: bad configuration");
     *out = nullptr;
@@ -912,6 +991,7 @@ extern "C" int fvk_solver_attach_mesh(fvk_solver* sv, const fvk_mesh* m)
     sv->affRowOffs = m ? m->rowOffs : nullptr;
     sv->affColIdxs = m ? m->colIdxs : nullptr;
     sv->affDiagOffs = (m && m->nOwned == sv->nRows && m->nCells == sv->nCols) ? m->diagOffset : nullptr;
+    sv->attached = (m && m->nOwned == sv->nRows && m->nCells == sv->nCols) ? m : nullptr;
     return FVK_OK;
 }
 
@@ -1168,6 +1248,7 @@ extern "C" int fvk_solver_solve(fvk_solver* sv, const int32_t* rowOffs, const in
         {
             if (sv->cfg.solverType != FVK_SOLVER_CG) return fvk_fail(FVK_EUNSUPPORTED, "fvk_solver_solve: only solver::Cg can be captured into a CUDA graph");
             if (history_h) return fvk_fail(FVK_EUNSUPPORTED, "fvk_solver_solve: residual histories are not available inside a stream capture");
+            if (sv->cfg.preconditioner == FVK_PRECOND_DIC) return fvk_fail(FVK_EUNSUPPORTED, "fvk_solver_solve: the DIC preconditioner cannot be captured yet");
             return cg_solve_captured(sv, rowOffs, colIdxs, values, b, x, stats_h, st);
         }
     }
@@ -1191,6 +1272,35 @@ extern "C" int fvk_solver_solve(fvk_solver* sv, const int32_t* rowOffs, const in
     FVK_CUDA(cudaMemsetAsync(sv->p0, 0, sizeof(double) * sv->nCols, st));
     if (jacobi)
         if (int rc = launch_dinv(sv, rowOffs, colIdxs, values, st)) return rc;
+    const bool dic = sv->cfg.preconditioner == FVK_PRECOND_DIC;
+    const fvk_mesh* cm = sv->attached;
+    if (dic)
+    { // D* colour by colour (sv->dinv holds 1 / D*)
+        if (!cm || rowOffs != sv->affRowOffs || colIdxs != sv->affColIdxs)
+            return fvk_fail(FVK_EUNSUPPORTED, "fvk_solver_solve: the DIC preconditioner needs fvk_solver_attach_mesh and that mesh's own sparsity pattern");
+        if (int rc = fvk_mesh_ensure_colors(cm)) return rc;
+        for (int c = 0; c < cm->dicNColors; ++c)
+        {
+            const int n0 = cm->dicOff[c], n1 = cm->dicOff[c + 1];
+            if (n1 > n0) k_dic_diag<<<(n1 - n0 + TB - 1) / TB, TB, 0, st>>>(n0, n1, cm->dicCells, rowOffs, colIdxs, values, cm->dicColor, c, n, sv->dinv);
+        }
+        FVK_LAUNCH_CHECK();
+    }
+    auto dic_apply = [&](const double* rr) -> int {
+        for (int c = 0; c < cm->dicNColors; ++c)
+        {
+            const int n0 = cm->dicOff[c], n1 = cm->dicOff[c + 1];
+            if (n1 > n0) k_dic_fwd<<<(n1 - n0 + TB - 1) / TB, TB, 0, st>>>(n0, n1, sv->state, cm->dicCells, rowOffs, colIdxs, values, cm->dicColor, c, n, sv->dinv, rr, sv->z);
+        }
+        for (int c = cm->dicNColors - 2; c >= 0; --c) // the highest colour has no higher neighbours
+        {
+            const int n0 = cm->dicOff[c], n1 = cm->dicOff[c + 1];
+            if (n1 > n0) k_dic_bwd<<<(n1 - n0 + TB - 1) / TB, TB, 0, st>>>(n0, n1, sv->state, cm->dicCells, rowOffs, colIdxs, values, cm->dicColor, c, n, sv->dinv, sv->z);
+        }
+        k_cg_rz_decide<<<gV, TB, 0, st>>>(n, sv->state, rr, sv->z, sv->partial, sv->counter, sv->hist);
+        FVK_LAUNCH_CHECK();
+        return FVK_OK;
+    };
     if (dist)
         if (int rc = fvk_comm_halo_exchange_impl(sv->comm, x, 1, st)) return rc;
     // r = b - A x, fused with ||b||^2 (the reference's "initial residual" is ||b||, ginkgo.hpp:143-144)
@@ -1220,7 +1330,14 @@ extern "C" int fvk_solver_solve(fvk_solver* sv, const int32_t* rowOffs, const in
     {
         if (timing && it >= 1 && it <= NT) cudaEventRecord(tev[it - 1][0], st);
         // K1
-        if (it == 0)
+        if (dic)
+        {
+            if (it == 0) k_cg_update<true, 2><<<gV, TB, 0, st>>>(n, sv->state, x, pCur, sv->q, rIn, rIn, sv->dinv, sv->z, sv->partial, sv->counter, sv->hist, dmode, p2p);
+            else k_cg_update<false, 2><<<gV, TB, 0, st>>>(n, sv->state, x, pCur, sv->q, rIn, rOut, sv->dinv, sv->z, sv->partial, sv->counter, sv->hist, dmode, p2p);
+            FVK_LAUNCH_CHECK();
+            if (int rc = dic_apply(it == 0 ? rIn : rOut)) return rc;
+        }
+        else if (it == 0)
         {
             if (jacobi) k_cg_update<true, true><<<gV, TB, 0, st>>>(n, sv->state, x, pCur, sv->q, rIn, rIn, sv->dinv, sv->z, sv->partial, sv->counter, sv->hist, dmode, p2p);
             else k_cg_update<true, false><<<gV, TB, 0, st>>>(n, sv->state, x, pCur, sv->q, rIn, rIn, sv->dinv, sv->z, sv->partial, sv->counter, sv->hist, dmode, p2p);

@@ -250,7 +250,8 @@ extern "C" int fvk_mesh_destroy(fvk_mesh* m)
                     m->gatherEnt, m->gatherPlan, m->rowOffs, m->colIdxs, m->ownerOffset, m->neighbourOffset,
                     m->diagOffset, m->ownStart, m->lowSeg, m->lowFace, m->lowOwner, m->bndCell,
                     m->bndSeg, m->bndFace, m->hasBnd, m->tp.hdr, m->tp.blob, m->bp.hdr, m->bp.rec, m->bp.codes,
-                    m->bp.xFace, m->bp.xOwner, m->bp.xNei, m->bp.bFace, m->bp.bCell, m->bp.recF, m->bp.codes4, m->bp.tileInfo, m->bp.irrCells};
+                    m->bp.xFace, m->bp.xOwner, m->bp.xNei, m->bp.bFace, m->bp.bCell, m->bp.recF, m->bp.codes4, m->bp.tileInfo, m->bp.irrCells,
+                    m->dicColor, m->dicCells};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete m;
@@ -602,6 +603,48 @@ extern "C" int fvk_mesh_create(const fvk_mesh_desc* d, fvk_mesh** out)
     }
     tm.lap("geometry scheme");
     *out = m;
+    return FVK_OK;
+}
+
+int fvk_mesh_ensure_colors(const fvk_mesh* m)
+{
+    if (!m) return fvk_fail(FVK_EINVAL, "fvk_mesh_ensure_colors: null mesh");
+    if (m->dicNColors > 0) return FVK_OK;
+    const int32_t n = m->nOwned;
+    std::vector<int32_t> ro(size_t(m->nCells) + 1);
+    std::vector<int32_t> col;
+    col.resize(size_t(m->nnz));
+    FVK_CUDA(cudaMemcpy(ro.data(), m->rowOffs, sizeof(int32_t) * ro.size(), cudaMemcpyDeviceToHost));
+    FVK_CUDA(cudaMemcpy(col.data(), m->colIdxs, sizeof(int32_t) * col.size(), cudaMemcpyDeviceToHost));
+    std::vector<uint8_t> color(size_t(m->nCells), 255);
+    int32_t nColors = 0;
+    for (int32_t c = 0; c < n; ++c)
+    {
+        uint64_t used = 0;
+        for (int32_t k = ro[c]; k < ro[size_t(c) + 1]; ++k)
+        {
+            const int32_t j = col[k];
+            if (j != c && j < n && color[j] != 255) used |= uint64_t(1) << color[j];
+        }
+        int32_t cc = 0;
+        while (cc < 64 && (used >> cc & 1)) ++cc;
+        if (cc >= 64) return fvk_fail(FVK_EUNSUPPORTED, "fvk_mesh_ensure_colors: more than 64 colours");
+        color[c] = uint8_t(cc);
+        nColors = std::max(nColors, cc + 1);
+    }
+    std::vector<int32_t> off(size_t(nColors) + 1, 0);
+    std::vector<int32_t> cells;
+    cells.resize(size_t(n));
+    for (int32_t c = 0; c < n; ++c) ++off[size_t(color[c]) + 1];
+    for (int32_t k = 0; k < nColors; ++k) off[size_t(k) + 1] += off[k];
+    std::vector<int32_t> pos(off.begin(), off.end() - 1);
+    for (int32_t c = 0; c < n; ++c) cells[pos[color[c]]++] = c;
+    FVK_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->dicColor), color.size()));
+    FVK_CUDA(cudaMemcpy(m->dicColor, color.data(), color.size(), cudaMemcpyHostToDevice));
+    FVK_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->dicCells), sizeof(int32_t) * std::max<size_t>(cells.size(), 1)));
+    FVK_CUDA(cudaMemcpy(m->dicCells, cells.data(), sizeof(int32_t) * cells.size(), cudaMemcpyHostToDevice));
+    for (int32_t k = 0; k <= nColors; ++k) m->dicOff[k] = off[k];
+    m->dicNColors = nColors;
     return FVK_OK;
 }
 

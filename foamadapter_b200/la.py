@@ -213,8 +213,12 @@ class Solver:
             precond = 0
         elif isinstance(pre, dict) and pre.get("type") == "preconditioner::Jacobi" and int(pre.get("max_block_size", 1)) == 1:
             precond = 1
+        elif isinstance(pre, dict) and pre.get("type") == "preconditioner::Ic":
+            # extension: Ginkgo's name for incomplete Cholesky selects the multicolour DIC of libfvk
+            # (FVK_PRECOND_DIC; solver::Cg, one GPU). mapFvSolution never emits it: OpenFOAM's DIC maps to Jacobi like the reference.
+            precond = 2
         else:
-            raise KeyError(f"preconditioner {pre!r} is not supported (scalar preconditioner::Jacobi only)")
+            raise KeyError(f"preconditioner {pre!r} is not supported (scalar preconditioner::Jacobi, or preconditioner::Ic = multicolour DIC)")
         self.cfg = _Cfg(int(crit.get("iteration", 1000)), float(crit.get("relative_residual_norm", 0.0)),
                         float(crit.get("absolute_residual_norm", 0.0)), precond, int(check_every), SOLVER_TYPES[cfg["type"]])
         self.type = cfg["type"]

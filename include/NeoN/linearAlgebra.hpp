@@ -149,6 +149,7 @@ public:
             const auto& pd = dict.subDict("preconditioner");
             const auto ptype = pd.getOr<std::string>("type", "");
             if (ptype == "preconditioner::Jacobi" && pd.getOr<int>("max_block_size", 1) == 1) cfg_.preconditioner = FVK_PRECOND_JACOBI;
+            else if (ptype == "preconditioner::Ic") cfg_.preconditioner = FVK_PRECOND_DIC; // extension: multicolour DIC (fvk.h)
             else NF_ERROR_EXIT("preconditioner " + ptype + " not supported (scalar preconditioner::Jacobi only)");
         }
     }

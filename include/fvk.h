@@ -413,7 +413,11 @@ int fvk_norm2(int64_t n, const double* x, double* result_d, fvk_stream stream);
  * `checkEvery` iterations (kernels after the stop are no-ops, so results equal a per-iteration check). */
 typedef struct fvk_solver fvk_solver;
 typedef struct fvk_comm fvk_comm;
-enum { FVK_PRECOND_NONE = 0, FVK_PRECOND_JACOBI = 1 };
+/* FVK_PRECOND_DIC (extension; the reference maps OpenFOAM's DIC to scalar Jacobi, fvSolution.cpp:51-55): diagonal
+ * incomplete Cholesky, OpenFOAM's DIC recurrences applied in a MULTICOLOUR order of the cells (greedy colouring of the mesh's own
+ * pattern; a hex block needs two colours), so every substitution step is one fully parallel kernel. solver::Cg on one GPU, needs
+ * fvk_solver_attach_mesh. Changes iteration counts by construction: compared with the oracle's restatement of the same ordering. */
+enum { FVK_PRECOND_NONE = 0, FVK_PRECOND_JACOBI = 1, FVK_PRECOND_DIC = 2 };
 /* solver::Cg (PCG) | solver::Bicgstab (PBiCGStab, smoothSolver: src/compatibility/fvSolution.cpp:22-28). BiCGStab follows
  * Ginkgo 1.10's published loop (two stopping checks per iteration, on ||r|| and on the half-step residual ||s||; a stop at
  * the half step adds alpha*y to x and does not count as an iteration); five kernels per iteration, scalars on the device. */

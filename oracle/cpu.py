@@ -30,6 +30,7 @@ def lib() -> C.CDLL:
         _LIB.fvo_max_threads.restype = C.c_int
         _LIB.fvo_cg.restype = C.c_int
         _LIB.fvo_bicgstab.restype = C.c_int
+        _LIB.fvo_cg_dic.restype = C.c_int
     return _LIB
 
 
@@ -308,3 +309,12 @@ def cg(rowOffs, colIdxs, values, b, x0, jacobi=True, max_iter=1000, rel_tol=0.0,
 def bicgstab(rowOffs, colIdxs, values, b, x0, jacobi=True, max_iter=1000, rel_tol=0.0, abs_tol=0.0, par=0, max_hist=0):
     """Ginkgo solver::Bicgstab restated (fvo_bicgstab); history holds every checked norm (||r|| and ||s|| alternate)."""
     return cg(rowOffs, colIdxs, values, b, x0, jacobi, max_iter, rel_tol, abs_tol, par, max_hist, fn="fvo_bicgstab")
+
+
+def cg_dic(rowOffs, colIdxs, values, b, x0, max_iter=1000, rel_tol=0.0, abs_tol=1e-6, max_hist=0):
+    """EXTENSION: CG with the multicolour DIC preconditioner (fvo_cg_dic). Returns (x, stats, history, colours)."""
+    x = f64(x0).copy()
+    stats, hist, colors = np.zeros(3), np.zeros(max(max_hist, 1)), np.zeros(len(x), np.int32)
+    nh = lib().fvo_cg_dic(C.c_int32(len(x)), _arg(i32(rowOffs)), _arg(i32(colIdxs)), _arg(f64(values)), _arg(f64(b)), _arg(x), C.c_int(max_iter),
+                          C.c_double(rel_tol), C.c_double(abs_tol), _arg(stats), _arg(hist) if max_hist else C.c_void_p(0), C.c_int(max_hist), _arg(colors))
+    return x, dict(numIter=int(stats[0]), initResNorm=stats[1], finalResNorm=stats[2]), hist[:nh], colors

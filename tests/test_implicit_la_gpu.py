@@ -235,3 +235,44 @@ def test_solver_rejects_unknown_configuration():
         la.Solver({"solver": "Ginkgo", "type": "solver::Bicg"})
     with pytest.raises(KeyError):  # DILU -> preconditioner::Ilu (fvSolution.cpp:56-62) is not on the hot path: no silent downgrade
         la.Solver({"solver": "PBiCGStab", "preconditioner": "DILU", "tolerance": 1e-6})
+
+
+# ---- extension: multicolour DIC preconditioner -------------------------------------------------------
+@pytest.mark.parametrize("dims", [(24, 16, 12), (17, 9, 5)])
+def test_multicolour_dic_cg_tracks_the_oracle_and_beats_jacobi(dims):
+    from oracle.cpu import cg_dic
+    d = M.MeshDesc.block(*dims)
+    gm, om = M.UnstructuredMesh(d), OMesh.from_desc(d)
+    rng = np.random.default_rng(2)
+    ls = _poisson(om, rng)
+    b = rng.uniform(-1, 1, om.nC)
+    tol = 1e-9 * np.linalg.norm(b)
+    xo, so, ho, colors = cg_dic(om.rowOffs, om.colIdxs, ls["values"], b, np.zeros(om.nC), max_iter=500, rel_tol=0.0, abs_tol=tol, max_hist=600)
+    assert colors.max() == 1                                        # a hex block is two-colourable
+    _, sj, _ = oracle_cg(om.rowOffs, om.colIdxs, ls["values"], b, np.zeros(om.nC), jacobi=True, max_iter=500, rel_tol=0.0, abs_tol=tol)
+    assert so["numIter"] < 0.8 * sj["numIter"]                      # what the preconditioner is for
+    gls = la.LinearSystem(gm); gls.values.copy_(dev(ls["values"])); gls.rhs.copy_(dev(b))
+    x = torch.zeros(om.nC, dtype=torch.float64, device="cuda")
+    cfg = {"solver": "Ginkgo", "type": "solver::Cg", "preconditioner": {"type": "preconditioner::Ic"},
+           "criteria": {"iteration": 500, "relative_residual_norm": 0.0, "absolute_residual_norm": tol}}
+    st = la.Solver(cfg, check_every=3, history=True).solve(gls, x)
+    assert abs(st.numIter - so["numIter"]) <= 1
+    n = min(len(st.history), len(ho))
+    sig = ho[:n] > 1e-8 * ho[0]
+    assert np.allclose(st.history[:n][sig], ho[:n][sig], rtol=1e-7)
+    assert np.allclose(host(x), xo, rtol=1e-7, atol=1e-9 * np.abs(xo).max())
+    r = om.residual(ls["values"], b, host(x))
+    assert np.linalg.norm(r) <= 1.01 * tol
+
+
+def test_dic_needs_the_mesh_pattern_and_one_gpu():
+    d = M.MeshDesc.block(6, 5, 4)
+    gm, om = M.UnstructuredMesh(d), OMesh.from_desc(d)
+    cfg = {"solver": "Ginkgo", "type": "solver::Cg", "preconditioner": {"type": "preconditioner::Ic"}, "criteria": {"iteration": 10}}
+    s = la.Solver(cfg)
+    ls = _poisson(om, np.random.default_rng(0))
+    ro, ci = dev(om.rowOffs.copy()), dev(om.colIdxs.copy())      # a foreign copy of the pattern: no colouring for it
+    x = torch.zeros(om.nC, dtype=torch.float64, device="cuda")
+    from foamadapter_b200._capi import FvkError
+    with pytest.raises(FvkError):
+        s.solve_csr(om.nC, om.nC, ro.data_ptr(), ci.data_ptr(), dev(ls["values"]), dev(ls["rhs"] + 1.0), x)
