@@ -1117,17 +1117,41 @@ __device__ __forceinline__ double warp_max(double v)
     return v;
 }
 
+// aff.on: block topology proven by the plan -- a REGULAR cell's six faces are [zL, yL, xL | x, y, z] with arithmetic ids (same
+// order as its stencil), so no index array is read for it
+struct CoNumAffine
+{
+    int on, nx, ny, nz, tx, ty;
+};
 __global__ void __launch_bounds__(256)
 k_conum_stage1(CoNumOp op, int nC, const int* __restrict__ seg, const int* __restrict__ ent,
-               const double* __restrict__ V, double* __restrict__ partial /* [3*gridDim.x] */)
+               const double* __restrict__ V, double* __restrict__ partial /* [3*gridDim.x] */, CoNumAffine aff)
 {
     __shared__ double sMax[8], sPhi[8], sVol[8];
     double lmax = -1.7976931348623157e308, lphi = 0.0, lvol = 0.0;
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nC; c += gridDim.x * blockDim.x)
     {
         double acc = 0.0;
-        const int e1 = seg[c + 1];
-        for (int e = seg[c]; e < e1; ++e) acc += op.at(ent[e] >> 1);
+        bool reg = false;
+        if (aff.on)
+        {
+            const int i = c % aff.nx, q = c / aff.nx, j = q % aff.ny, k = q / aff.ny;
+            reg = i > 0 && i < aff.nx - 1 && j > 0 && j < aff.ny - 1 && k > 0 && k < aff.nz - 1;
+            if (reg)
+            {
+                const int64_t nxy = int64_t(aff.nx) * aff.ny;
+                const int64_t fs = 3 * int64_t(c) - int64_t(aff.tx) * (j + int64_t(aff.ny) * k) - int64_t(aff.ty) * k * aff.nx;
+                const int64_t f[6] = {fs - 3 * nxy + int64_t(aff.tx) * aff.ny + int64_t(aff.ty) * aff.nx + 2, fs - 3 * int64_t(aff.nx) + aff.tx + 1, fs - 3,
+                                      fs, fs + 1, fs + 2};
+                double a[6];
+#pragma unroll
+                for (int e = 0; e < 6; ++e) a[e] = op.at(int(f[e]));
+#pragma unroll
+                for (int e = 0; e < 6; ++e) acc += a[e];
+            }
+        }
+        const int e1 = reg ? 0 : seg[c + 1];
+        for (int e = reg ? 0 : seg[c]; e < e1; ++e) acc += op.at(ent[e] >> 1);
         const double v = V[c];
         lmax = fmax(lmax, acc / v);
         lphi += acc;
@@ -1383,7 +1407,10 @@ extern "C" int fvk_conum(const fvk_mesh* m, const double* faceFlux, double dt, d
     if (!m || !faceFlux || !result_d || !scratch_d) return fvk_fail(FVK_EINVAL, "fvk_conum: null argument");
     const int grid = conum_grid(m);
     double* partial = static_cast<double*>(scratch_d);
-    k_conum_stage1<<<grid, 256, 0, fvk_cu(s)>>>(CoNumOp {faceFlux}, m->nOwned, m->stencilSeg, m->gatherEnt, m->V, partial);
+    const FvkBrickGeom& bg = m->bp.geom;
+    const bool affine = !fvk_no_affine() && m->bp.nTiles > 0 && bg.affine && int64_t(bg.dims[0]) * bg.dims[1] * bg.dims[2] == m->nOwned;
+    const CoNumAffine ca {affine ? 1 : 0, bg.dims[0], bg.dims[1], bg.dims[2], bg.tUp[0], bg.tUp[1]};
+    k_conum_stage1<<<grid, 256, 0, fvk_cu(s)>>>(CoNumOp {faceFlux}, m->nOwned, m->stencilSeg, m->gatherEnt, m->V, partial, ca);
     FVK_LAUNCH_CHECK();
     k_conum_stage2<<<1, 256, 0, fvk_cu(s)>>>(grid, partial, dt, result_d);
     FVK_LAUNCH_CHECK();

@@ -691,6 +691,11 @@ k_extract_dinv(int n, const int* __restrict__ rowOffs, const int* __restrict__ c
 
 // ---- BLAS-1 --------------------------------------------------------------------------------------
 enum { OP_FILL, OP_SCALE, OP_ADD, OP_SUB, OP_MUL, OP_AXPBY, OP_SCALED_COPY };
+// w = a x + b y (three-array form of axpby: forwardEuler's solution = old - source * dt without the copy of `old`)
+__global__ void __launch_bounds__(TB) k_waxpby(int64_t n, double a, const double* __restrict__ x, double b, const double* __restrict__ y, double* __restrict__ w)
+{
+    for (int64_t i = int64_t(blockIdx.x) * TB + threadIdx.x; i < n; i += int64_t(gridDim.x) * TB) w[i] = a * x[i] + b * y[i];
+}
 template <int OP>
 __global__ void __launch_bounds__(TB)
 k_vec(int64_t n, double a, double bb, double* __restrict__ x, const double* __restrict__ y)
@@ -875,6 +880,15 @@ extern "C" int fvk_vec_axpby(int64_t n, double a, const double* x, double b, dou
 {
     if (n && !x) return fvk_fail(FVK_EINVAL, "fvk_vec_axpby: null");
     VEC_OP(OP_AXPBY, a, b, y, x);
+}
+
+extern "C" int fvk_vec_waxpby(int64_t n, double a, const double* x, double b, const double* y, double* w, fvk_stream s)
+{
+    if (n < 0 || (n && (!x || !y || !w))) return fvk_fail(FVK_EINVAL, "fvk_vec_waxpby: bad argument");
+    if (n == 0) return FVK_OK;
+    k_waxpby<<<stream_grid(n), TB, 0, fvk_cu(s)>>>(n, a, x, b, y, w);
+    FVK_LAUNCH_CHECK();
+    return FVK_OK;
 }
 
 extern "C" int fvk_vec_scaled_copy(int64_t n, double a, const double* x, double* out, fvk_stream s)

@@ -127,21 +127,29 @@ class Expression:
                 raise NotImplementedError("explicit ddt needs dt; use ops.ddt_explicit")
         return src
 
-    def explicitOperationInto(self, mesh, src):
+    def explicitOperationInto(self, mesh, src, fresh=False):
         """Expression::explicitOperation(source) (dsl/expression.hpp:55-65): the explicit SPATIAL operators added to an
-        existing source vector (each operator: tmp = 0; op(tmp); source += tmp -- fused into one ADD-mode launch)."""
+        existing source vector (each operator: tmp = 0; op(tmp); source += tmp -- fused into one ADD-mode launch).
+        fresh=True: `src` is the zero vector of explicitOperation(nCells) and has NOT been filled -- the first gather operator
+        writes it (SET mode: 0 + x without the zero-fill and the read-back), the others add."""
+        mode = ops.SET if fresh else ops.ADD
         for o in self.spatial:
             if o.type != "explicit":
                 continue
             c = o.coeff
             if o.kind == "surfaceIntegrate":
-                ops.surface_integrate(mesh, o.faceField.internal, src, c.value, c.view, ops.ADD)
+                ops.surface_integrate(mesh, o.faceField.internal, src, c.value, c.view, mode)
             elif o.kind == "div":
-                ops.div(mesh, o.faceField.internal, o.field.internal, o.field.boundary.value, src, o.scheme or 0, c.value, c.view, ops.ADD)
+                ops.div(mesh, o.faceField.internal, o.field.internal, o.field.boundary.value, src, o.scheme or 0, c.value, c.view, mode)
             elif o.kind == "laplacian":
-                ops.laplacian(mesh, o.field.internal, o.field.boundary.value, src, c.value, c.view, ops.ADD)
+                ops.laplacian(mesh, o.field.internal, o.field.boundary.value, src, c.value, c.view, mode)
             elif o.kind == "source":
+                if mode == ops.SET:
+                    src.zero_()
                 ops.source_explicit(mesh, o.cellField, o.field.internal, src, c.value, c.view)
+            mode = ops.ADD
+        if mode == ops.SET:  # no explicit operator at all
+            src.zero_()
         return src
 
 
@@ -264,9 +272,8 @@ class TimeIntegratorBase:
         the work vector is kept with the field instead of being allocated every step"""
         src = getattr(sol, "_tiSource", None)
         if src is None:
-            src = sol._tiSource = torch.empty_like(sol.internal)
-        src.zero_()
-        return eqn.explicitOperationInto(sol.mesh, src)
+            src = sol._tiSource = torch.zeros_like(sol.internal)   # ghost slots stay zero: the operators write owned cells
+        return eqn.explicitOperationInto(sol.mesh, src, fresh=True)
 
 
 class ForwardEuler(TimeIntegratorBase):
@@ -276,9 +283,7 @@ class ForwardEuler(TimeIntegratorBase):
     def solve(self, eqn, sol, t, dt):
         src = self._source(eqn, sol)
         old = sol.oldTime()
-        if old.internal.data_ptr() != sol.internal.data_ptr():
-            sol.internal.copy_(old.internal)
-        la.axpby(-dt, src, 1.0, sol.internal)   # old - source*dt, bit for bit
+        la.waxpby(-dt, src, 1.0, old.internal, sol.internal)   # old - source*dt, bit for bit, in one pass
         sol.correctBoundaryConditions()
 
 
@@ -301,8 +306,7 @@ class RungeKutta(TimeIntegratorBase):
     def solve(self, eqn, sol, t, dt):
         old = sol.oldTime()
         src = self._source(eqn, sol)
-        sol.internal.copy_(old.internal)
-        la.axpby(-dt, src, 1.0, sol.internal)
+        la.waxpby(-dt, src, 1.0, old.internal, sol.internal)
         old.internal.copy_(sol.internal)
 
 

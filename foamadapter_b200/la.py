@@ -303,6 +303,11 @@ def mul(x, y): check(lib().fvk_vec_mul(_n(x), ptr(x), ptr(y), _stream())); ops._
 def axpby(a, x, b, y): check(lib().fvk_vec_axpby(_n(y), C.c_double(a), ptr(x), C.c_double(b), ptr(y), _stream())); ops._count(); return y
 
 
+def waxpby(a, x, b, y, w):
+    """w = a*x + b*y"""
+    check(lib().fvk_vec_waxpby(_n(w), C.c_double(a), ptr(x), C.c_double(b), ptr(y), ptr(w), _stream())); ops._count(); return w
+
+
 def scaledCopy(a, x, out):
     """out = x * a"""
     check(lib().fvk_vec_scaled_copy(_n(x), C.c_double(a), ptr(x), ptr(out), _stream())); ops._count(); return out

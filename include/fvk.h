@@ -393,6 +393,8 @@ int fvk_vec_sub(int64_t n, double* x, const double* y, fvk_stream stream);
 int fvk_vec_mul(int64_t n, double* x, const double* y, fvk_stream stream);
 /* y = a*x + b*y */
 int fvk_vec_axpby(int64_t n, double a, const double* x, double b, double* y, fvk_stream stream);
+/* w = a*x + b*y (w may alias x or y): forwardEuler.hpp:48 `solution = old - source * dt` in one pass */
+int fvk_vec_waxpby(int64_t n, double a, const double* x, double b, const double* y, double* w, fvk_stream stream);
 /* out = x * a: the temporary `Vector operator*(Vector, scalar)` creates (vector.hpp; scalarAdvection.cpp:66-67
  * nfPhi = nfPhi0 * cos(...)), written straight to its destination */
 int fvk_vec_scaled_copy(int64_t n, double a, const double* x, double* out, fvk_stream stream);
