@@ -39,7 +39,9 @@ extern "C" int fvk_decomp_simple_map(const fvk_mesh_desc* g, int px, int py, int
 {
     if (!g || !cellRank || px < 1 || py < 1 || pz < 1 || !g->cellCentres) return fvk_fail(FVK_EINVAL, "fvk_decomp_simple_map: bad argument");
     const int32_t nC = g->nCells;
+    if (nC <= 0) return FVK_OK;
     std::vector<int32_t> idx(nC), grp(nC);
+    std::vector<int64_t> key(nC);
     std::fill(cellRank, cellRank + nC, 0);
     const int p[3] = {px, py, pz};
     int stride = 1;
@@ -50,11 +52,10 @@ extern "C" int fvk_decomp_simple_map(const fvk_mesh_desc* g, int px, int py, int
         // quantise to suppress last-bit noise in equal coordinates, ties broken by cell id (stable)
         double lo = C[axis], hi = C[axis];
         for (int32_t c = 0; c < nC; ++c) { lo = std::min(lo, C[3 * size_t(c) + axis]); hi = std::max(hi, C[3 * size_t(c) + axis]); }
+        // integer keys: a tolerance comparison (xa < xb - eps) is not a strict weak ordering
         const double eps = (hi - lo) * 1e-9 + 1e-300;
-        std::stable_sort(idx.begin(), idx.end(), [&](int32_t a, int32_t b) {
-            const double xa = C[3 * size_t(a) + axis], xb = C[3 * size_t(b) + axis];
-            return xa < xb - eps;
-        });
+        for (int32_t c = 0; c < nC; ++c) key[c] = std::llround((C[3 * size_t(c) + axis] - lo) / eps);
+        std::stable_sort(idx.begin(), idx.end(), [&](int32_t a, int32_t b) { return key[a] < key[b]; });
         for (int32_t k = 0; k < nC; ++k) grp[idx[k]] = int32_t((int64_t(k) * p[axis]) / nC);
         for (int32_t c = 0; c < nC; ++c) cellRank[c] += stride * grp[c];
         stride *= p[axis];
@@ -75,6 +76,13 @@ extern "C" int fvk_decompose(const fvk_mesh_desc* g, const int32_t* cellRank, in
     const int32_t nC = g->nCells, nI = g->nInternalFaces, nB = g->nBoundaryFaces;
     for (int32_t c = 0; c < nC; ++c)
         if (cellRank[c] < 0 || cellRank[c] >= nRanks) return fvk_fail(FVK_EINVAL, "fvk_decompose: cell %d has rank %d", c, cellRank[c]);
+    if (!g->faceOwner || (nI && !g->faceNeighbour) || (nB && (!g->faceCells || !g->patchOffsets))) return fvk_fail(FVK_EINVAL, "fvk_decompose: missing array");
+    for (int32_t f = 0; f < nI; ++f)
+        if (g->faceOwner[f] < 0 || g->faceOwner[f] >= nC || g->faceNeighbour[f] < 0 || g->faceNeighbour[f] >= nC)
+            return fvk_fail(FVK_EINVAL, "fvk_decompose: face %d has bad owner/neighbour", f);
+    for (int32_t b = 0; b < nB; ++b)
+        if (g->faceCells[b] < 0 || g->faceCells[b] >= nC) return fvk_fail(FVK_EINVAL, "fvk_decompose: boundary face %d has bad faceCell", b);
+    if (nB && (g->patchOffsets[0] != 0 || g->patchOffsets[g->nPatches] != nB)) return fvk_fail(FVK_EINVAL, "fvk_decompose: patchOffsets do not cover the boundary faces");
     fvk_decomp* d = new fvk_decomp;
     std::vector<int32_t> g2l(nC, -1);
     for (int32_t c = 0; c < nC; ++c)

@@ -169,6 +169,7 @@ extern "C" int fvk_fieldfile_read_patch(const char* path, const char* patchName,
     const size_t pk = findKey(s, patchName, open + 1, close, 0);
     if (pk == std::string::npos) return fvk_fail(FVK_EINVAL, "fvk_fieldfile_read_patch: %s has no patch '%s'", path, patchName);
     const size_t po = s.find('{', pk);
+    if (po == std::string::npos || po >= close) return fvk_fail(FVK_EINVAL, "fvk_fieldfile_read_patch: patch '%s' has no dictionary", patchName);
     size_t pc = po;
     for (depth = 0; pc < close; ++pc)
     {

@@ -4,7 +4,10 @@
 // which need OpenFOAM: the files are parsed here, the geometry follows OpenFOAM's primitiveMesh (triangle-fan face
 // centres / areas about the vertex average, pyramid cell centres / volumes about the face-centre average -- the same
 // arithmetic as fvk_blockmesh.cpp, for arbitrary polygons / polyhedra), and the boundary is flattened like the reference's
-// converter: patches concatenated in file order, `empty` patches contribute no faces (fvPatch::size() == 0).
+// converter: patches concatenated in file order, `empty` patches contribute no faces (fvPatch::size() == 0). NOTE (deviation
+// from meshAdapter.cpp:33-45,63, which keeps an empty patch as a zero-size entry that still occupies a patch index): here an
+// `empty` patch is dropped from the patch list altogether, so patch indices are those of the KEPT patches in file order;
+// fvk_polymesh_patch gives each kept patch's name and type, fvk_polymesh_patch_file_index its index in the boundary file.
 // The result is an fvk_mesh_desc that fvk_mesh_create / fvk_decompose take like a generated block mesh.
 #include "fvk_internal.hpp"
 
@@ -471,6 +474,21 @@ extern "C" int fvk_polymesh_destroy(fvk_mesh_desc* desc)
     st->magic[0] = 0;
     delete st;
     return FVK_OK;
+}
+
+// index of kept patch `patch` in the case's `boundary` file (= OpenFOAM's patch id, which counts the dropped `empty` patches)
+extern "C" int fvk_polymesh_patch_file_index(const fvk_mesh_desc* desc, int32_t patch, int32_t* fileIndex)
+{
+    const PolyStore* st = storeOf(desc);
+    if (!st || !fileIndex) return fvk_fail(FVK_EINVAL, "fvk_polymesh_patch_file_index: not a mesh from fvk_polymesh_read");
+    if (patch < 0 || patch >= int32_t(st->patchName.size())) return fvk_fail(FVK_EINVAL, "fvk_polymesh_patch_file_index: patch %d out of range", patch);
+    int32_t kept = -1;
+    for (size_t i = 0; i < st->allName.size(); ++i)
+    {
+        if (st->allType[i] != "empty") ++kept;
+        if (kept == patch) { *fileIndex = int32_t(i); return FVK_OK; }
+    }
+    return fvk_fail(FVK_EINVAL, "fvk_polymesh_patch_file_index: patch %d not found", patch);
 }
 
 extern "C" int fvk_polymesh_patch(const fvk_mesh_desc* desc, int32_t patch, char* name, int32_t nameCap, char* type, int32_t typeCap)

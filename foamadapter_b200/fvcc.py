@@ -208,33 +208,60 @@ def read_field_file(path, nCells: int):
     return out[:nCells].copy() if nc.value == 1 else out[: 3 * nCells].reshape(nCells, 3).copy()
 
 
-def read_patch_conditions(path, patch_names):
-    """[(type, uniform value or None)] per patch from the boundaryField of an OpenFOAM ASCII field file: the (type,
-    constant) list VolumeField takes (readers.hpp:43-95 of the reference maps the same dictionaries)."""
+def read_patch_conditions(path, patch_names, patch_sizes=None):
+    """[(type, value)] per patch from the boundaryField of an OpenFOAM ASCII field file (readers.hpp:43-95 of the reference
+    maps the same dictionaries). value: None (no `value` entry), a constant (uniform, or a nonuniform list whose entries are all
+    equal), or -- with patch_sizes given -- the per-face array [n] / [n, 3] of a `value nonuniform List<...>` entry, which is
+    what OpenFOAM itself writes into time directories."""
     import ctypes as C
     import numpy as np
     from ._capi import check, lib
     bcs = []
-    for name in patch_names:
+    for i, name in enumerate(patch_names):
+        n = int(patch_sizes[i]) if patch_sizes is not None else 1
         typ, has, nc = C.create_string_buffer(128), C.c_int32(0), C.c_int32(0)
-        val = np.zeros(3)
-        check(lib().fvk_fieldfile_read_patch(str(path).encode(), name.encode(), typ, C.c_int32(128), C.c_int32(1), C.byref(has), C.byref(nc),
-                                             val.ctypes.data_as(C.c_void_p), C.c_int64(3)))
-        v = None if not has.value else (float(val[0]) if nc.value == 1 else tuple(float(x) for x in val))
+        val = np.zeros(3 * max(n, 1))
+        check(lib().fvk_fieldfile_read_patch(str(path).encode(), name.encode(), typ, C.c_int32(128), C.c_int32(n if patch_sizes is not None else 1),
+                                             C.byref(has), C.byref(nc), val.ctypes.data_as(C.c_void_p), C.c_int64(val.size)))
+        v = None
+        if has.value and n > 0:
+            a = val[:n].copy() if nc.value == 1 else val[: 3 * n].reshape(n, 3).copy()
+            if (a == a[0]).all():
+                v = float(a[0]) if nc.value == 1 else tuple(float(x) for x in a[0])
+            else:
+                v = a
         bcs.append((typ.value.decode(), v))
     return bcs
 
 
 def read_volume_field(mesh, path, name=None, device="cuda"):
-    """VolumeField from an OpenFOAM ASCII field file on a mesh whose patches carry names (e.g. MeshDesc.from_polymesh)."""
+    """VolumeField from an OpenFOAM ASCII field file on a mesh whose patches carry names (e.g. MeshDesc.from_polymesh).
+    Patches whose `value` is a genuinely nonuniform list keep their per-face values: the patch becomes `calculated` (the BC
+    kernel leaves it alone) with value / refValue = the list and, for fixedValue, valueFraction = 1 (fixedValue.hpp:21-43)."""
     import os
+    import numpy as np
     internal = read_field_file(path, mesh.nOwned)
     ncomp = 3 if internal.ndim == 2 else 1
     zero = (0.0, 0.0, 0.0) if ncomp == 3 else 0.0
-    bcs = [(t, v if v is not None else zero) for t, v in read_patch_conditions(path, mesh.patch_names)]
+    off = mesh.patch_offsets
+    raw = read_patch_conditions(path, mesh.patch_names, [off[i + 1] - off[i] for i in range(mesh.nPatches)])
+    bcs, perFace = [], []
+    for i, (t, v) in enumerate(raw):
+        if isinstance(v, np.ndarray):
+            perFace.append((i, t, v))
+            bcs.append(("calculated", zero))
+        else:
+            bcs.append((t, v if v is not None else zero))
     f = VolumeField(mesh, name or os.path.basename(str(path)), ncomp, bcs, device)
     f.internal[: mesh.nOwned].copy_(torch.from_numpy(internal))
     f.correctBoundaryConditions()
+    for i, t, v in perFace:
+        sl = slice(off[i], off[i + 1])
+        tv = torch.from_numpy(np.ascontiguousarray(v)).to(f.internal.device)
+        f.boundary.value[sl] = tv
+        if t in ("fixedValue", "noSlip"):
+            f.boundary.refValue[sl] = tv
+            f.boundary.valueFraction[sl] = 1.0
     return f
 
 

@@ -139,6 +139,10 @@ int fvk_polymesh_read(const char* polyMeshDir, fvk_mesh_desc** out);
 int fvk_polymesh_destroy(fvk_mesh_desc* desc);
 /* name / type of kept (non-empty) patch `patch` of a mesh from fvk_polymesh_read, NUL-terminated into the buffers */
 int fvk_polymesh_patch(const fvk_mesh_desc* desc, int32_t patch, char* name, int32_t nameCap, char* type, int32_t typeCap);
+/* NOTE: an `empty` patch is dropped from the patch list (the reference keeps it as a zero-size entry that still occupies a
+ * patch index, meshAdapter.cpp:33-45,63), so patch indices here count the KEPT patches; this gives kept patch `patch`'s index
+ * in the case's boundary file, i.e. the OpenFOAM patch id per-patch lists of a case are keyed by. */
+int fvk_polymesh_patch_file_index(const fvk_mesh_desc* desc, int32_t patch, int32_t* fileIndex);
 /* write the five files into an existing directory. Faces: faceOffsets [nFaces+1] into facePoints; faces [0, nInternalFaces)
  * are internal, then the patches in order with patchSizes[p] faces each (all patches, `empty` ones included). */
 int fvk_polymesh_write(const char* polyMeshDir, int32_t nPoints, const double* points, int32_t nFaces,

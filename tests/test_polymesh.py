@@ -279,3 +279,34 @@ def test_reader_tolerates_formatting_variants(tmp_path):
     assert r.patch_names == ref.patch_names and r.patch_types == ref.patch_types
     for name in ARRAYS:
         assert np.array_equal(r.array(name), ref.array(name)), name
+
+
+def test_nonuniform_patch_values_are_read_per_face(tmp_path):
+    """OpenFOAM writes `value nonuniform List<...>` into time directories; read_patch_conditions must take the real
+    patch size and return the per-face values (a list whose entries are all equal collapses to a constant)."""
+    import numpy as np
+    from foamadapter_b200 import fvcc
+    f = tmp_path / "T"
+    f.write_text("""FoamFile { version 2.0; format ascii; class volScalarField; object T; }
+dimensions [0 0 0 1 0 0 0];
+internalField uniform 1;
+boundaryField
+{
+    inlet { type fixedValue; value nonuniform List<scalar> 3 ( 1.5 2.5 3.5 ); }
+    wall { type calculated; value nonuniform List<scalar> 2 ( 4 4 ); }
+    outlet { type zeroGradient; }
+}
+""")
+    bcs = fvcc.read_patch_conditions(f, ["inlet", "wall", "outlet"], [3, 2, 5])
+    assert bcs[0][0] == "fixedValue" and np.array_equal(bcs[0][1], [1.5, 2.5, 3.5])
+    assert bcs[1] == ("calculated", 4.0) and bcs[2] == ("zeroGradient", None)
+    u = tmp_path / "U"
+    u.write_text("""FoamFile { version 2.0; format ascii; class volVectorField; object U; }
+internalField uniform (0 0 0);
+boundaryField { inlet { type fixedValue; value nonuniform List<vector> 2 ( (1 0 0) (2 0 0.5) ); } }
+""")
+    (t, v), = fvcc.read_patch_conditions(u, ["inlet"], [2])
+    assert t == "fixedValue" and np.array_equal(v, [[1, 0, 0], [2, 0, 0.5]])
+    from foamadapter_b200._capi import FvkError
+    with pytest.raises(FvkError):
+        fvcc.read_patch_conditions(f, ["inlet"], [4])      # wrong patch size: loud
