@@ -1103,7 +1103,13 @@ k_weights(int scheme, int nI, int nF, const double* __restrict__ geomW, const do
 struct CoNumOp
 {
     const double* __restrict__ faceFlux;
-    __device__ __forceinline__ double at(int f) const { const double F = faceFlux[f]; return sqrt(F * F); }
+    // coNum.cpp:43,53 takes sqrt(F * F). In binary floating point with correctly rounded * and sqrt that is exactly |F| whenever
+    // F * F neither underflows nor overflows (Boldo 2015), so the (slow, multi-instruction) fp64 sqrt only runs outside that range
+    __device__ __forceinline__ double at(int f) const
+    {
+        const double F = faceFlux[f], a = fabs(F);
+        return (a > 1e-150 && a < 1e150) ? a : sqrt(F * F);
+    }
 };
 
 __device__ __forceinline__ double warp_sum(double v)
