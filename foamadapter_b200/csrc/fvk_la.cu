@@ -11,6 +11,7 @@
 // a fixed order), so a solve is bit-reproducible run to run and needs no host round trip per iteration.
 #include "fvk_device.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -941,6 +942,10 @@ struct fvk_solver
     PcgState* cap_h = nullptr;   // pinned [FVK_MAX_CAPTURED_SOLVES]
     int nCaptured = 0;
     cudaStream_t bodyStream = nullptr;
+    // device-side log of the captured solves' iteration counts (one entry per executed solve, in execution order), so that
+    // back-to-back graph replays need no host synchronisation to keep their statistics
+    int32_t* capLog = nullptr;   // [FVK_CAPTURE_LOG]
+    unsigned* capLogCount = nullptr;
     cudaEvent_t checkEv[2] = {nullptr, nullptr};
     int32_t histCap = 0;
 };
@@ -957,6 +962,8 @@ extern "C" int fvk_solver_destroy(fvk_solver* sv)
     if (sv->init_h) cudaFreeHost(sv->init_h);
     if (sv->cap_h) cudaFreeHost(sv->cap_h);
     if (sv->bodyStream) cudaStreamDestroy(sv->bodyStream);
+    if (sv->capLog) cudaFree(sv->capLog);
+    if (sv->capLogCount) cudaFree(sv->capLogCount);
     for (auto& e : sv->checkEv)
         if (e) cudaEventDestroy(e);
     delete sv;
@@ -987,6 +994,9 @@ extern "C" int fvk_solver_create(int32_t nRows, int32_t nCols, const fvk_solver_
     if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&sv->init_h), sizeof(PcgState));
     if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&sv->cap_h), sizeof(PcgState) * 64);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sv->bodyStream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&sv->capLog), sizeof(int32_t) * 8192);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&sv->capLogCount), sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMemset(sv->capLogCount, 0, sizeof(unsigned));
     for (auto& ev : sv->checkEv)
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     if (e != cudaSuccess)
@@ -1156,6 +1166,12 @@ __global__ void k_loop_cond(const PcgState* __restrict__ st, cudaGraphConditiona
 {
     if (st->done) cudaGraphSetConditional(h, 0);
 }
+constexpr unsigned FVK_CAPTURE_LOG = 8192;
+__global__ void k_log_captured(const PcgState* __restrict__ st, int32_t* __restrict__ log, unsigned* __restrict__ count)
+{
+    const unsigned i = (*count)++;
+    if (i < FVK_CAPTURE_LOG) log[i] = st->iter;
+}
 
 static int cg_solve_captured(fvk_solver* sv, const int32_t* rowOffs, const int32_t* colIdxs, const double* values, const double* b,
                              double* x, fvk_solver_stats* stats_h, cudaStream_t st)
@@ -1238,7 +1254,9 @@ static int cg_solve_captured(fvk_solver* sv, const int32_t* rowOffs, const int32
     cudaError_t ee = cudaStreamEndCapture(sv->bodyStream, &bodyOut);
     if (le != cudaSuccess || ee != cudaSuccess)
         return fvk_fail(FVK_ECUDA, "fvk_solver_solve: capturing the iteration body failed: %s", cudaGetErrorString(le != cudaSuccess ? le : ee));
-    // ---- final state into this solve's pinned slot
+    // ---- iteration count into the device log, final state into this solve's pinned slot
+    k_log_captured<<<1, 1, 0, st>>>(sv->state, sv->capLog, sv->capLogCount);
+    FVK_LAUNCH_CHECK();
     const int slot = sv->nCaptured++;
     FVK_CUDA(cudaMemcpyAsync(&sv->cap_h[slot], sv->state, sizeof(PcgState), cudaMemcpyDeviceToHost, st));
     stats_h->numIter = -(slot + 1); // not known at capture time: fvk_solver_captured_stats(slot) after a replay
@@ -1500,6 +1518,19 @@ extern "C" int fvk_solver_captured_stats(const fvk_solver* sv, int32_t slot, fvk
     stats_h->finalResNorm = fin.normR;
     stats_h->nHistory = 0;
     return fin.done ? FVK_OK : fvk_fail(FVK_ECUDA, "fvk_solver_captured_stats: the solve has not finished (replay not complete?)");
+}
+// iteration counts of the captured solves executed since the last call, in execution order (synchronises the device)
+extern "C" int fvk_solver_captured_log(fvk_solver* sv, int32_t* out_h, int32_t capacity, int32_t* n_h)
+{
+    if (!sv || !n_h || capacity < 0 || (capacity && !out_h)) return fvk_fail(FVK_EINVAL, "fvk_solver_captured_log: bad argument");
+    FVK_CUDA(cudaDeviceSynchronize());
+    unsigned cnt = 0;
+    FVK_CUDA(cudaMemcpy(&cnt, sv->capLogCount, sizeof(unsigned), cudaMemcpyDeviceToHost));
+    const unsigned take = std::min<unsigned>(std::min<unsigned>(cnt, FVK_CAPTURE_LOG), unsigned(capacity));
+    if (take) FVK_CUDA(cudaMemcpy(out_h, sv->capLog, sizeof(int32_t) * take, cudaMemcpyDeviceToHost));
+    FVK_CUDA(cudaMemset(sv->capLogCount, 0, sizeof(unsigned)));
+    *n_h = int32_t(take);
+    return FVK_OK;
 }
 extern "C" int fvk_solver_reset_captures(fvk_solver* sv)
 {

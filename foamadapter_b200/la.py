@@ -239,6 +239,13 @@ class Solver:
             lib().fvk_solver_destroy(self._h)
             self._h = None
 
+    def captured_log(self):
+        """iteration counts of the captured solves executed since the last call, in execution order (device-side log)"""
+        out = (C.c_int32 * 8192)()
+        n = C.c_int32(0)
+        check(lib().fvk_solver_captured_log(self._h, out, C.c_int32(8192), C.byref(n)))
+        return list(out[: n.value])
+
     def reset_captures(self):
         """forget the slots of earlier captured solves (before capturing a new graph)"""
         if self._h is not None:

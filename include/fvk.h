@@ -464,6 +464,9 @@ int fvk_solver_solve(fvk_solver* solver, const int32_t* rowOffs, const int32_t* 
  * time; the real statistics of a replay are read with fvk_solver_captured_stats(slot) once the replay has completed. */
 int fvk_solver_captured_stats(const fvk_solver* solver, int32_t slot, fvk_solver_stats* stats_h);
 int fvk_solver_reset_captures(fvk_solver* solver);
+/* iteration counts of the captured solves executed since the last call, in execution order (a device-side log, so that graph
+ * replays issued back to back need no host synchronisation to keep their statistics); synchronises the device */
+int fvk_solver_captured_log(fvk_solver* solver, int32_t* out_h, int32_t capacity, int32_t* n_h);
 /* Vec3 LinearSystem (values Vec3[nnz] with identical components; rhs / x Vec3[nRows] / [nCols]): three scalar
  * solves over the component matrix (NeoN's la::Solver has no Vec3 overload, solver.hpp:52; this is what `momentumPredictor yes`
  * of neoIcoFoam.cpp:100-103 needs). stats3_h receives one fvk_solver_stats per component. */

@@ -28,6 +28,8 @@ def main():
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"])
     ap.add_argument("--check-every", type=int, default=16)
     ap.add_argument("--graphs", type=int, default=1)
+    ap.add_argument("--no-comm", action="store_true", help="diagnostic: every rank steps its sub-domain WITHOUT a communicator (stale ghosts, "
+                    "pressure solve capped at 3 iterations): the kernel-only time of a rank's share, to separate it from the communication cost")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -39,13 +41,19 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         dec = Decomposition(g, world, rank, n=default_split(world))
         mesh = UnstructuredMesh(dec.desc)
-        comm = Comm.from_torch()
-        comm.set_halo(dec, p2p=args.transport == "p2p")
+        if not args.no_comm:
+            comm = Comm.from_torch()
+            comm.set_halo(dec, p2p=args.transport == "p2p")
         del g
     else:
         mesh = UnstructuredMesh(g)
     setup_s = time.perf_counter() - t0
-    app = piso.IcoFoam(mesh, nu=0.01, dt=1e-4 * 20 / args.size, comm=comm, check_every=args.check_every, graphs=bool(args.graphs))
+    sol = None
+    if args.no_comm and world > 1:
+        import copy
+        sol = copy.deepcopy(piso.CAVITY_FVSOLUTION)
+        sol["solvers"]["p"] = {"solver": "PCG", "preconditioner": "DIC", "tolerance": 0.0, "relTol": 0.0, "maxIter": 3}
+    app = piso.IcoFoam(mesh, nu=0.01, dt=1e-4 * 20 / args.size, comm=comm, check_every=args.check_every, graphs=bool(args.graphs), fvSolution=sol)
     for _ in range(args.warmup):
         app.step()
     torch.cuda.synchronize()
@@ -60,15 +68,31 @@ def main():
         torch.cuda.synchronize()
         ms.append(e0.elapsed_time(e1))
         its.append([s.numIter for s in st])
+    b2b = None
+    if app._whole is not None:   # sustained rate: steps back to back, iteration counts from the solver's device-side log
+        nb = 2 * args.steps
+        app.solver.captured_log()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(nb):
+            app.step()
+        e1.record(); torch.cuda.synchronize()
+        tb = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        log = app.solver.captured_log()
+        b2b = {"steps": nb, "ms_per_step": float(tb.item()) / nb, "cg_iterations_total": int(sum(log))}
     t = torch.tensor(ms, dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = t.cpu().numpy()
     if rank == 0:
         tot_it = [int(sum(i)) for i in its]
-        print("PISO " + json.dumps({"n": args.size, "cells": args.size ** 3, "n_gpus": world, "transport": ("peer-memory windows" if (comm and comm.p2p) else ("NCCL" if comm else "none")),
+        print("PISO " + json.dumps({"n": args.size, "cells": args.size ** 3, "n_gpus": world, "transport": ("peer-memory windows" if (comm and comm.p2p) else ("NCCL" if comm else ("none (diagnostic: no communicator)" if world > 1 else "none"))),
                                     "ms_per_step": [round(float(x), 3) for x in ms], "median_ms": float(np.median(ms)), "cg_iterations": its, "cuda_graphs": ("whole step" if app._whole is not None else ("segments" if app._captured else "none")),
-                                    "ms_per_cg_iteration_upper_bound": float(np.median(ms / np.maximum(tot_it, 1))), "setup_s": round(setup_s, 1)}), flush=True)
+                                    "ms_per_cg_iteration_upper_bound": float(np.median(ms / np.maximum(tot_it, 1))), "setup_s": round(setup_s, 1), "back_to_back": b2b}), flush=True)
     if comm is not None:
         comm.close()
         dist.destroy_process_group()
