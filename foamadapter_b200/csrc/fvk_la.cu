@@ -173,6 +173,10 @@ k_cg_update(int n, PcgState* __restrict__ st, double* __restrict__ x, const doub
                           + (hseq & 1) * size_t(ctx.peerOwned[k] + ctx.peerGhost[k]) + ctx.peerOwned[k] + ctx.peerRecvOff[k] + (i - ctx.sendOff[k]);
             *dst = zi;
         }
+        // the ghost entries of x follow the same update (p's ghost entries were formed by the previous SpMV from the exchanged
+        // z, alpha is global): the solution leaves the solver with current ghosts, no exchange of x afterwards
+        if (!FIRST)
+            for (int g = n + blockIdx.x * TB + threadIdx.x; g < ctx.nOwned + ctx.nGhost; g += gridDim.x * TB) x[g] = x[g] + alpha * p[g];
     }
     double acc[2] = {0.0, 0.0};
     for (int i = blockIdx.x * TB + threadIdx.x; i < n; i += gridDim.x * TB)
@@ -204,10 +208,10 @@ k_cg_update(int n, PcgState* __restrict__ st, double* __restrict__ x, const doub
         __threadfence(); // every block fenced its window stores at system scope before checking in (grid_sum, sysFence)
         if (threadIdx.x < ctx.nNbr)
             st_release_sys_u64(reinterpret_cast<unsigned long long*>(ctx.win[ctx.nbrRank[threadIdx.x]] + FVK_P2P_HALOFLAG_OFF) + ctx.rank, hseq);
-        if (threadIdx.x == 0) { shv[0] = tot[0]; shv[1] = tot[1]; }
+        if (threadIdx.x == 0) { shv[0] = tot[0]; shv[1] = tot[1]; if (FIRST) shv[2] = st->sums[3]; }
         __syncthreads();
         const unsigned long long t1 = fvk_gtime();
-        fvk_p2p_allreduce_sum(ctx, shv, 2);
+        fvk_p2p_allreduce_sum(ctx, shv, FIRST ? 3 : 2); // start-up: ||b||^2 (local part left by the r0 SpMV) rides along
         const unsigned long long t2 = fvk_gtime();
         if (threadIdx.x < ctx.nNbr)
         {
@@ -222,6 +226,7 @@ k_cg_update(int n, PcgState* __restrict__ st, double* __restrict__ x, const doub
             ctx.state->haloSeq = hseq;
             st->sums[0] = shv[0];
             st->sums[1] = shv[1];
+            if (FIRST) { st->sums[3] = shv[2]; st->normB = sqrt(shv[2]); }
             decide_after_update(st, hist);
         }
         return;
@@ -923,6 +928,7 @@ struct fvk_solver
     int32_t nRows = 0, nCols = 0;
     fvk_solver_config cfg {};
     fvk_comm* comm = nullptr;
+    bool guessGhostsCurrent = false; // fvk_solver_set_ghosts_current: skip the exchange of the initial guess
     SpmvAffine aff {0, 0, 0, 0}; // set by fvk_solver_attach_mesh
     const int32_t *affRowOffs = nullptr, *affColIdxs = nullptr; // the attached mesh's pattern: aff applies to these arrays only
     const uint8_t* affDiagOffs = nullptr;                       // its diagOffset (Jacobi diagonal without a row scan)
@@ -1203,15 +1209,11 @@ static int cg_solve_captured(fvk_solver* sv, const int32_t* rowOffs, const int32
     FVK_CUDA(cudaMemsetAsync(sv->p0, 0, sizeof(double) * sv->nCols, st));
     if (jacobi)
         if (int rc = launch_dinv(sv, rowOffs, colIdxs, values, st)) return rc;
-    if (dist)
+    if (dist && !sv->guessGhostsCurrent)
         if (int rc = fvk_comm_halo_exchange_impl(sv->comm, x, 1, st)) return rc;
+    // distributed: ||b||^2 is all-reduced together with (r.z, r.r) inside the first update kernel
     k_spmv<2><<<gS, TB, 0, st>>>(n, rowOffs, colIdxs, values, x, b, sv->r, sv->state, nullptr, nullptr, sv->partial, sv->counter, dist ? 1 : 0, nullptr, 0, sv->aff);
     FVK_LAUNCH_CHECK();
-    if (dist)
-    {
-        if (int rc = fvk_comm_allreduce_sum_impl(sv->comm, &sv->state->sums[3], 1, st)) return rc;
-        k_set_normB<<<1, 1, 0, st>>>(sv->state);
-    }
     double *rA = sv->r, *rB = dmode == 2 ? sv->r2 : sv->r;
     auto K1 = [&](cudaStream_t q, bool first, double* rIn, double* rOut, double* pCur) {
         if (first)
@@ -1333,13 +1335,13 @@ extern "C" int fvk_solver_solve(fvk_solver* sv, const int32_t* rowOffs, const in
         FVK_LAUNCH_CHECK();
         return FVK_OK;
     };
-    if (dist)
+    if (dist && !sv->guessGhostsCurrent)
         if (int rc = fvk_comm_halo_exchange_impl(sv->comm, x, 1, st)) return rc;
     // r = b - A x, fused with ||b||^2 (the reference's "initial residual" is ||b||, ginkgo.hpp:143-144)
     k_spmv<2><<<gS, TB, 0, st>>>(n, rowOffs, colIdxs, values, x, b, sv->r, sv->state, nullptr, nullptr, sv->partial, sv->counter, dist ? 1 : 0, nullptr, 0, sv->aff);
     FVK_LAUNCH_CHECK();
-    if (dist)
-    {
+    if (dmode == 1)
+    { // NCCL transport; the peer-memory transport all-reduces ||b||^2 inside the first update kernel
         if (int rc = fvk_comm_allreduce_sum_impl(sv->comm, &sv->state->sums[3], 1, st)) return rc;
         k_set_normB<<<1, 1, 0, st>>>(sv->state);
     }
@@ -1530,6 +1532,18 @@ extern "C" int fvk_solver_captured_log(fvk_solver* sv, int32_t* out_h, int32_t c
     if (take) FVK_CUDA(cudaMemcpy(out_h, sv->capLog, sizeof(int32_t) * take, cudaMemcpyDeviceToHost));
     FVK_CUDA(cudaMemset(sv->capLogCount, 0, sizeof(unsigned)));
     *n_h = int32_t(take);
+    return FVK_OK;
+}
+extern "C" int fvk_solver_set_ghosts_current(fvk_solver* sv, int32_t on)
+{
+    if (!sv) return fvk_fail(FVK_EINVAL, "fvk_solver_set_ghosts_current: null");
+    sv->guessGhostsCurrent = on != 0;
+    return FVK_OK;
+}
+extern "C" int fvk_solver_keeps_ghosts(const fvk_solver* sv, int32_t* out_h)
+{
+    if (!sv || !out_h) return fvk_fail(FVK_EINVAL, "fvk_solver_keeps_ghosts: null");
+    *out_h = (!sv->comm || (sv->cfg.solverType == FVK_SOLVER_CG && fvk_comm_p2p_ctx(sv->comm))) ? 1 : 0;
     return FVK_OK;
 }
 extern "C" int fvk_solver_reset_captures(fvk_solver* sv)

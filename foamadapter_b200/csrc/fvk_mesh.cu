@@ -508,8 +508,11 @@ extern "C" int fvk_mesh_create(const fvk_mesh_desc* d, fvk_mesh** out)
     // ---- sparsity pattern: row = [lower (face order) | diag | upper (face order)] (sparsityPattern.cpp:21-143). The
     // reference's three serial passes over the faces place, in row r, the lower entries in ascending face id, the diagonal,
     // then the upper entries in ascending face id; built here row by row in parallel from the cell's stencil (sorted by
-    // LOCAL face id, which is what the passes visit -- a decomposed mesh's stencil is ordered by the global key instead).
+    // LOCAL face id, which is what the passes visit). A decomposed mesh (faceOrder key; the reference has no such path) sorts
+    // each half by the GLOBAL face id instead: the ghost-owned faces, which the sub-domain numbers last, then sit where the
+    // undecomposed mesh has them, the rows stay in stencil order and the index-free kernels serve every rank's sub-domain.
     {
+        const int32_t* fkey = d->faceOrder;
         std::vector<int32_t> rowOffs(size_t(nC) + 1, 0);
         int tooLong = -1;
 #pragma omp parallel for schedule(static) reduction(max : tooLong)
@@ -541,8 +544,17 @@ extern "C" int fvk_mesh_create(const fvk_mesh_desc* d, fvk_mesh** out)
                     if (f >= nI) continue;
                     ((sth.ent[e] & 1) ? lower : upper).push_back(f);
                 }
-                std::sort(lower.begin(), lower.end());
-                std::sort(upper.begin(), upper.end());
+                if (fkey)
+                {
+                    auto byKey = [fkey](int32_t a, int32_t b) { return fkey[a] < fkey[b]; };
+                    std::sort(lower.begin(), lower.end(), byKey);
+                    std::sort(upper.begin(), upper.end(), byKey);
+                }
+                else
+                {
+                    std::sort(lower.begin(), lower.end());
+                    std::sort(upper.begin(), upper.end());
+                }
                 const size_t r0 = size_t(rowOffs[c]);
                 int32_t k = 0;
                 for (int32_t f : lower) { neiOff[f] = uint8_t(k); col[r0 + k] = own[f]; ++k; }

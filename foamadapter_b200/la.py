@@ -223,7 +223,7 @@ class Solver:
                         float(crit.get("absolute_residual_norm", 0.0)), precond, int(check_every), SOLVER_TYPES[cfg["type"]])
         self.type = cfg["type"]
         self.comm, self.history = comm, history
-        self._h, self._shape = None, None
+        self._h, self._shape, self._ghosts_current = None, None, False
 
     def _handle(self, nRows, nCols):
         if self._shape != (nRows, nCols):
@@ -232,6 +232,8 @@ class Solver:
             check(lib().fvk_solver_create(C.c_int32(nRows), C.c_int32(nCols), C.byref(self.cfg),
                                           self.comm.handle if self.comm is not None else None, C.byref(h)))
             self._h, self._shape, self._attached = h, (nRows, nCols), None
+            if self._ghosts_current:
+                check(lib().fvk_solver_set_ghosts_current(h, C.c_int32(1)))
         return self._h
 
     def close(self):
@@ -245,6 +247,21 @@ class Solver:
         n = C.c_int32(0)
         check(lib().fvk_solver_captured_log(self._h, out, C.c_int32(8192), C.byref(n)))
         return list(out[: n.value])
+
+    def set_ghosts_current(self, on: bool = True):
+        """fvk_solver_set_ghosts_current: every initial guess passed from now on has current ghost entries (skip that exchange)"""
+        self._ghosts_current = bool(on)
+        if self._h is not None:
+            check(lib().fvk_solver_set_ghosts_current(self._h, C.c_int32(1 if on else 0)))
+
+    @property
+    def keeps_ghosts(self) -> bool:
+        """fvk_solver_keeps_ghosts: the solution leaves the solver with current ghost entries (no exchange needed afterwards)"""
+        if self._h is None:  # same rule as the library's, before the handle exists
+            return self.comm is None or (self.type == "solver::Cg" and bool(getattr(self.comm, "p2p", False)))
+        out = C.c_int32(0)
+        check(lib().fvk_solver_keeps_ghosts(self._h, C.byref(out)))
+        return bool(out.value)
 
     def reset_captures(self):
         """forget the slots of earlier captured solves (before capturing a new graph)"""

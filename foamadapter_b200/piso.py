@@ -144,7 +144,10 @@ class IcoFoam:
         U.oldTime().internal.copy_(U.internal)                             # neoIcoFoam.cpp:84-85
         self.coNum = ops.conum(mesh, phi.internal, rt.dt, self._co, self._coScratch)  # :87 (device scalars; no host sync here)
         if self._nsteps == 0:
-            self._halo(U.internal)  # later steps: the ghosts are current since the exchange that ended the previous step
+            # later steps: U's ghosts are current since the exchange that ended the previous step, p's since its last solve
+            self._halo(U.internal, self.p.internal)
+            if self.rt.comm is not None and self.solver.keeps_ghosts:
+                self.solver.set_ghosts_current(True)  # p is only ever written by this solver: its guesses keep current ghosts
         self._UEqn = dsl.PDESolver(dsl.imp.ddt(U) + dsl.imp.div(phi, U) - dsl.imp.laplacian(self.nu, U), U, rt, ls=self.Uls)
         self._UEqn.assemble()                                              # :94-98 / :105-108
 
@@ -170,7 +173,8 @@ class IcoFoam:
     def _post(self, last_nonorth: bool = True):
         """neoIcoFoam.cpp:156-167 after the linear solver."""
         U, p = self.U, self.p
-        self._halo(p.internal)
+        if not self.solver.keeps_ghosts:
+            self._halo(p.internal)  # (solver::Cg over peer memory hands the solution back with current ghosts)
         p.correctBoundaryConditions()                                      # :156
         if last_nonorth:
             updateFaceVelocity(self.phiHbyA, self._pEqn, self.phi)         # :160

@@ -467,6 +467,14 @@ int fvk_solver_reset_captures(fvk_solver* solver);
 /* iteration counts of the captured solves executed since the last call, in execution order (a device-side log, so that graph
  * replays issued back to back need no host synchronisation to keep their statistics); synchronises the device */
 int fvk_solver_captured_log(fvk_solver* solver, int32_t* out_h, int32_t capacity, int32_t* n_h);
+/* Ghost entries around a distributed solve (a solver created with a communicator; no-ops without one).
+ * fvk_solver_set_ghosts_current(on): the caller guarantees that the ghost entries of every initial guess passed from now on are
+ * current (e.g. the previous solution of the same field, untouched since), so the solver skips its start-up exchange of x.
+ * fvk_solver_keeps_ghosts: *out_h = 1 when the solver leaves the ghost entries of its SOLUTION current (solver::Cg over the
+ * peer-memory transport: the ghost entries follow x += alpha p with the exchanged search direction, bit-identical to the
+ * owners' values), so no exchange of x is needed after the solve; 0 otherwise (NCCL transport, BiCGStab). */
+int fvk_solver_set_ghosts_current(fvk_solver* solver, int32_t on);
+int fvk_solver_keeps_ghosts(const fvk_solver* solver, int32_t* out_h);
 /* Vec3 LinearSystem (values Vec3[nnz] with identical components; rhs / x Vec3[nRows] / [nCols]): three scalar
  * solves over the component matrix (NeoN's la::Solver has no Vec3 overload, solver.hpp:52; this is what `momentumPredictor yes`
  * of neoIcoFoam.cpp:100-103 needs). stats3_h receives one fvk_solver_stats per component. */

@@ -145,8 +145,19 @@ def check(rank, world, p2p):
     x = torch.zeros(lm.nCells, dtype=torch.float64, device="cuda")
     cfg = {"solver": "Ginkgo", "type": "solver::Cg", "preconditioner": {"type": "preconditioner::Jacobi", "max_block_size": 1},
            "criteria": {"iteration": 500, "relative_residual_norm": 0.0, "absolute_residual_norm": tol}}
-    st = la.Solver(cfg, comm=comm, check_every=4, history=True).solve(ls, x)
+    cg = la.Solver(cfg, comm=comm, check_every=4, history=True)
+    st = cg.solve(ls, x)
     assert abs(st.numIter - so["numIter"]) <= 1, (st.numIter, so["numIter"])
+    assert cg.keeps_ghosts == p2p
+    if p2p:  # the solution's ghost entries followed the owners' updates bit for bit: an exchange changes nothing
+        x2 = x.clone()
+        comm.halo_exchange(x2)
+        torch.cuda.synchronize()
+        assert torch.equal(x2, x), "CG keeps the ghost entries of x current"
+        cg.set_ghosts_current(True)  # and a second solve from that guess needs no start-up exchange
+        st2 = cg.solve(ls, x2)
+        assert st2.numIter <= 1, st2.numIter
+        cg.set_ghosts_current(False)
     assert abs(st.initResNorm - so["initResNorm"]) <= 1e-12 * so["initResNorm"]
     n = min(len(st.history), len(ho))
     sig = ho[:n] > 1e-8 * ho[0]

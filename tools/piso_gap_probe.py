@@ -20,6 +20,7 @@ from foamadapter_b200.mesh import UnstructuredMesh  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--size", type=int, default=128)
 ap.add_argument("--iters", type=int, default=0)
+ap.add_argument("--all-ranks", action="store_true", help="probe every rank's sub-domain (whole-step graph only), not only rank 0's")
 args = ap.parse_args()
 n = args.size
 sol = copy.deepcopy(piso.CAVITY_FVSOLUTION)
@@ -50,7 +51,12 @@ standalone = UnstructuredMesh(piso.cavity_desc(n, True))
 for g in (True, False):
     run(standalone, f"standalone {n}^3", g)
 del standalone
-dec = Decomposition(piso.cavity_desc(2 * n, True), 8, 0, n=(2, 2, 2))
-sub = UnstructuredMesh(dec.desc)
-for g in (True, False):
-    run(sub, f"rank 0 of 8 of {2 * n}^3, no communicator", g)
+big = piso.cavity_desc(2 * n, True)
+for r in (range(8) if args.all_ranks else (0,)):
+    dec = Decomposition(big, 8, r, n=(2, 2, 2))
+    sub = UnstructuredMesh(dec.desc)
+    from foamadapter_b200 import mesh as _m
+    flags = {"rowsInStencilOrder": sub.size(_m.ROWS_IN_STENCIL_ORDER), "affine": sub.size(_m.AFFINE_TOPOLOGY)}
+    for g in ((True,) if args.all_ranks else (True, False)):
+        run(sub, f"rank {r} of 8 of {2 * n}^3, no communicator, flags {flags}", g)
+    del sub, dec
