@@ -150,12 +150,14 @@ k_halo_wait_unpack(const FvkP2PCtx* __restrict__ ctxp, double* __restrict__ fiel
 {
     const FvkP2PCtx& ctx = *ctxp;
     const unsigned long long seq = ctx.state->haloSeq;
+    const unsigned long long t0 = (blockIdx.x == 0 && threadIdx.x == 0) ? fvk_gtime() : 0ull;
     if (threadIdx.x < ctx.nNbr)
     {
         const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(ctx.win[ctx.rank] + FVK_P2P_HALOFLAG_OFF) + ctx.nbrRank[threadIdx.x];
         while (ld_acquire_sys(flag) < seq) __nanosleep(40);
     }
     __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) { ctx.state->dbg[6] += fvk_gtime() - t0; ctx.state->dbg[7] += 1; } // time spent waiting for the neighbours
     const double* src = reinterpret_cast<const double*>(ctx.win[ctx.rank] + FVK_P2P_HALO_OFF) + (seq & 1) * size_t(FVK_P2P_HALO_COMPS) * ctx.nGhost;
     double* dst = field + size_t(NC) * ctx.nOwned;
     const int n = NC * ctx.nGhost;
@@ -207,12 +209,14 @@ k_halo_wait_unpack_multi(const FvkP2PCtx* __restrict__ ctxp, HaloFields hf)
 {
     const FvkP2PCtx& ctx = *ctxp;
     const unsigned long long seq = ctx.state->haloSeq;
+    const unsigned long long t0 = (blockIdx.x == 0 && threadIdx.x == 0) ? fvk_gtime() : 0ull;
     if (threadIdx.x < ctx.nNbr)
     {
         const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(ctx.win[ctx.rank] + FVK_P2P_HALOFLAG_OFF) + ctx.nbrRank[threadIdx.x];
         while (ld_acquire_sys(flag) < seq) __nanosleep(40);
     }
     __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) { ctx.state->dbg[6] += fvk_gtime() - t0; ctx.state->dbg[7] += 1; } // time spent waiting for the neighbours
     const double* src = reinterpret_cast<const double*>(ctx.win[ctx.rank] + FVK_P2P_HALO_OFF) + (seq & 1) * size_t(FVK_P2P_HALO_COMPS) * ctx.nGhost;
     for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < ctx.nGhost; g += gridDim.x * blockDim.x)
         for (int a = 0; a < hf.n; ++a)
@@ -540,7 +544,8 @@ extern "C" int fvk_comm_p2p_disable(fvk_comm* c)
 }
 
 /* accumulated nanoseconds of the in-kernel communication phases (diagnostics): [0] flag raise + system fence, [1] all-reduce
- * (r.z, r.r), [2] wait for the halo flags, [3] count; [4] all-reduce p.q, [5] count */
+ * (r.z, r.r), [2] wait for the halo flags, [3] count; [4] all-reduce p.q, [5] count; [6] field exchanges: wait for the neighbours'
+ * flags (block 0), [7] count */
 extern "C" int fvk_comm_p2p_debug(const fvk_comm* c, uint64_t* out8)
 {
     if (!c || !out8 || !c->state_d) return fvk_fail(FVK_EINVAL, "fvk_comm_p2p_debug: not connected");

@@ -1108,7 +1108,7 @@ struct CoNumOp
     __device__ __forceinline__ double at(int f) const
     {
         const double F = faceFlux[f], a = fabs(F);
-        return (a > 1e-150 && a < 1e150) ? a : sqrt(F * F);
+        return (a < 1e150 && (a > 1e-150 || a == 0.0)) ? a : sqrt(F * F); // (a fluid at rest has F == 0 on most faces)
     }
 };
 

@@ -503,7 +503,7 @@ k_spmv(int nRows, const int* __restrict__ rowOffs, const int* __restrict__ colId
        const double* __restrict__ x, const double* __restrict__ b, double* __restrict__ y, PcgState* __restrict__ st,
        const double* __restrict__ z, double* __restrict__ pNew, double* __restrict__ partial,
        unsigned* __restrict__ counter, int distributed, const FvkP2PCtx* __restrict__ p2p = nullptr, int nCols = 0,
-       SpmvAffine aff = SpmvAffine {0, 0, 0, 0})
+       SpmvAffine aff = SpmvAffine {0, 0, 0, 0}, const uint8_t* __restrict__ diagOffs = nullptr, double* __restrict__ dinvOut = nullptr)
 {
     __shared__ double prod[SPMV_CAP];
     __shared__ int ro[SPMV_ROWS + 1];
@@ -593,6 +593,8 @@ k_spmv(int nRows, const int* __restrict__ rowOffs, const int* __restrict__ colId
                 const double br = b[r];
                 y[r] = br - sum;
                 acc[0] += br * br;
+                // solver start-up: the scalar Jacobi preconditioner's 1 / a_rr from the row just streamed (k_extract_dinv_offs)
+                if (dinvOut) dinvOut[r] = 1.0 / values[ro[threadIdx.x] + diagOffs[r]];
             }
             if (MODE == 3)
             {
@@ -1026,6 +1028,11 @@ extern "C" int fvk_solver_attach_mesh(fvk_solver* sv, const fvk_mesh* m)
 }
 
 
+// the CG start-up SpMV (r0 = b - A x) can write 1 / a_rr itself when the diagonal's slot in every row is known
+static bool dinv_fusable(const fvk_solver* sv, const int32_t* rowOffs, const int32_t* colIdxs)
+{
+    return sv->affDiagOffs && rowOffs == sv->affRowOffs && colIdxs == sv->affColIdxs;
+}
 static int launch_dinv(fvk_solver* sv, const int32_t* rowOffs, const int32_t* colIdxs, const double* values, cudaStream_t st)
 {
     const int n = sv->nRows;
@@ -1207,12 +1214,14 @@ static int cg_solve_captured(fvk_solver* sv, const int32_t* rowOffs, const int32
     // ---- start-up (same kernels as the eager path)
     FVK_CUDA(cudaMemcpyAsync(sv->state, sv->init_h, sizeof(PcgState), cudaMemcpyHostToDevice, st));
     FVK_CUDA(cudaMemsetAsync(sv->p0, 0, sizeof(double) * sv->nCols, st));
-    if (jacobi)
+    const bool fuseDinv = jacobi && dinv_fusable(sv, rowOffs, colIdxs);
+    if (jacobi && !fuseDinv)
         if (int rc = launch_dinv(sv, rowOffs, colIdxs, values, st)) return rc;
     if (dist && !sv->guessGhostsCurrent)
         if (int rc = fvk_comm_halo_exchange_impl(sv->comm, x, 1, st)) return rc;
     // distributed: ||b||^2 is all-reduced together with (r.z, r.r) inside the first update kernel
-    k_spmv<2><<<gS, TB, 0, st>>>(n, rowOffs, colIdxs, values, x, b, sv->r, sv->state, nullptr, nullptr, sv->partial, sv->counter, dist ? 1 : 0, nullptr, 0, sv->aff);
+    k_spmv<2><<<gS, TB, 0, st>>>(n, rowOffs, colIdxs, values, x, b, sv->r, sv->state, nullptr, nullptr, sv->partial, sv->counter, dist ? 1 : 0, nullptr, 0, sv->aff,
+                                 fuseDinv ? sv->affDiagOffs : nullptr, fuseDinv ? sv->dinv : nullptr);
     FVK_LAUNCH_CHECK();
     double *rA = sv->r, *rB = dmode == 2 ? sv->r2 : sv->r;
     auto K1 = [&](cudaStream_t q, bool first, double* rIn, double* rOut, double* pCur) {
@@ -1304,7 +1313,8 @@ extern "C" int fvk_solver_solve(fvk_solver* sv, const int32_t* rowOffs, const in
     FVK_CUDA(cudaMemcpyAsync(sv->state, sv->state_h, sizeof(PcgState), cudaMemcpyHostToDevice, st));
     // p of "iteration -1" is zero (p = z + beta p); p1 and q are fully written before they are read
     FVK_CUDA(cudaMemsetAsync(sv->p0, 0, sizeof(double) * sv->nCols, st));
-    if (jacobi)
+    const bool fuseDinv = jacobi && dinv_fusable(sv, rowOffs, colIdxs);
+    if (jacobi && !fuseDinv)
         if (int rc = launch_dinv(sv, rowOffs, colIdxs, values, st)) return rc;
     const bool dic = sv->cfg.preconditioner == FVK_PRECOND_DIC;
     const fvk_mesh* cm = sv->attached;
@@ -1338,7 +1348,8 @@ extern "C" int fvk_solver_solve(fvk_solver* sv, const int32_t* rowOffs, const in
     if (dist && !sv->guessGhostsCurrent)
         if (int rc = fvk_comm_halo_exchange_impl(sv->comm, x, 1, st)) return rc;
     // r = b - A x, fused with ||b||^2 (the reference's "initial residual" is ||b||, ginkgo.hpp:143-144)
-    k_spmv<2><<<gS, TB, 0, st>>>(n, rowOffs, colIdxs, values, x, b, sv->r, sv->state, nullptr, nullptr, sv->partial, sv->counter, dist ? 1 : 0, nullptr, 0, sv->aff);
+    k_spmv<2><<<gS, TB, 0, st>>>(n, rowOffs, colIdxs, values, x, b, sv->r, sv->state, nullptr, nullptr, sv->partial, sv->counter, dist ? 1 : 0, nullptr, 0, sv->aff,
+                                 fuseDinv ? sv->affDiagOffs : nullptr, fuseDinv ? sv->dinv : nullptr);
     FVK_LAUNCH_CHECK();
     if (dmode == 1)
     { // NCCL transport; the peer-memory transport all-reduces ||b||^2 inside the first update kernel

@@ -167,6 +167,12 @@ class Comm:
         arr = (_HF * len(fields))(*[_HF(f.data_ptr(), 3 if f.ndim == 2 else 1) for f in fields])
         check(lib().fvk_comm_halo_exchange_multi(self._h, C.c_int(len(fields)), arr, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
 
+    def p2p_debug(self):
+        """fvk_comm_p2p_debug: accumulated ns / counts of the in-kernel communication phases (diagnostics)"""
+        out = (C.c_uint64 * 8)()
+        check(lib().fvk_comm_p2p_debug(self._h, out))
+        return list(out)
+
     def allreduce_sum(self, t):
         import torch
         check(lib().fvk_comm_allreduce_sum(self._h, C.c_void_p(t.data_ptr()), C.c_int(t.numel()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))

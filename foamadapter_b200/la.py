@@ -275,8 +275,11 @@ class Solver:
             pass
 
     def _launches(self, numIter):
-        # CG: K1 + K2 per completed iteration, + the final K1, + dinv / ||b|| / normB / r0; BiCGStab: 5 per iteration
-        return (2 * numIter + 5) if self.cfg.solverType == 0 else (5 * numIter + 10)
+        # CG: K1 + K2 per completed iteration, + the final K1 and the no-op K2 behind it, + the start-up SpMV (r0, ||b||^2 and, with
+        # the mesh attached, 1 / diag; else one more kernel for it); BiCGStab: 5 per iteration
+        if self.cfg.solverType == 0:
+            return 2 * numIter + 3 + (0 if getattr(self, "_attached", None) is not None or self.cfg.preconditioner != 1 else 1)
+        return 5 * numIter + 10
 
     def solve_csr(self, nRows, nCols, rowOffs_ptr, colIdxs_ptr, values, b, x, _mesh=None) -> SolverStats:
         h = self._handle(nRows, nCols)

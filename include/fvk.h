@@ -568,7 +568,7 @@ int fvk_comm_p2p_enabled(const fvk_comm* comm);
 /* back to NCCL; the transport must be the same on every rank, so call it everywhere when any rank failed to connect */
 int fvk_comm_p2p_disable(fvk_comm* comm);
 /* diagnostics: accumulated ns spent by the CG kernels' last blocks in [0] flag raise, [1] all-reduce (r.z, r.r), [2] halo
- * flag wait, [3] count, [4] all-reduce p.q, [5] count */
+ * flag wait, [3] count, [4] all-reduce p.q, [5] count; [6] ns the field exchanges waited for their neighbours' flags, [7] count */
 int fvk_comm_p2p_debug(const fvk_comm* comm, uint64_t* out8_h);
 
 /* ------------------------------------------------------------------------------------------------

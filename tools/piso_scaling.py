@@ -75,6 +75,7 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        d0 = comm.p2p_debug() if (comm and comm.p2p) else None
         e0.record()
         for _ in range(nb):
             app.step()
@@ -84,6 +85,14 @@ def main():
             dist.all_reduce(tb, op=dist.ReduceOp.MAX)
         log = app.solver.captured_log()
         b2b = {"steps": nb, "ms_per_step": float(tb.item()) / nb, "cg_iterations_total": int(sum(log))}
+        if d0 is not None:  # time this rank's kernels spent WAITING for neighbours (exchange flags, in-kernel all-reduces), per step
+            d1 = comm.p2p_debug()
+            dd = [b - a for a, b in zip(d0, d1)]
+            mine = torch.tensor([dd[6] / 1e6 / nb, dd[7] / nb, (dd[1] + dd[2] + dd[4]) / 1e6 / nb, (dd[3] + dd[5]) / nb], dtype=torch.float64, device="cuda")
+            allr = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allr, mine)
+            b2b["comm_wait_per_rank"] = [{"exchange_wait_ms": round(float(t[0]), 4), "exchanges": round(float(t[1]), 1),
+                                          "cg_sync_ms": round(float(t[2]), 4), "cg_syncs": round(float(t[3]), 1)} for t in allr]
     t = torch.tensor(ms, dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
