@@ -1105,11 +1105,13 @@ struct CoNumOp
     const double* __restrict__ faceFlux;
     // coNum.cpp:43,53 takes sqrt(F * F). In binary floating point with correctly rounded * and sqrt that is exactly |F| whenever
     // F * F neither underflows nor overflows (Boldo 2015), so the (slow, multi-instruction) fp64 sqrt only runs outside that range
-    __device__ __forceinline__ double at(int f) const
+    static __device__ __forceinline__ bool abs_is_exact(double F)
     {
-        const double F = faceFlux[f], a = fabs(F);
-        return (a < 1e150 && (a > 1e-150 || a == 0.0)) ? a : sqrt(F * F); // (a fluid at rest has F == 0 on most faces)
+        const double a = fabs(F);
+        return a < 1e150 && (a > 1e-150 || a == 0.0); // (a fluid at rest has F == 0 on most faces)
     }
+    static __device__ __forceinline__ double mag(double F) { return abs_is_exact(F) ? fabs(F) : sqrt(F * F); }
+    __device__ __forceinline__ double at(int f) const { return mag(faceFlux[f]); }
 };
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -1149,11 +1151,24 @@ k_conum_stage1(CoNumOp op, int nC, const int* __restrict__ seg, const int* __res
                 const int64_t fs = 3 * int64_t(c) - int64_t(aff.tx) * (j + int64_t(aff.ny) * k) - int64_t(aff.ty) * k * aff.nx;
                 const int64_t f[6] = {fs - 3 * nxy + int64_t(aff.tx) * aff.ny + int64_t(aff.ty) * aff.nx + 2, fs - 3 * int64_t(aff.nx) + aff.tx + 1, fs - 3,
                                       fs, fs + 1, fs + 2};
-                double a[6];
+                // all six loads first (a branch on a loaded value between them would serialise six DRAM round trips), then one
+                // test for the exact-|F| range; the sqrt(F * F) form only runs for a cell that has a face outside it
+                double F[6];
 #pragma unroll
-                for (int e = 0; e < 6; ++e) a[e] = op.at(int(f[e]));
+                for (int e = 0; e < 6; ++e) F[e] = op.faceFlux[f[e]];
+                bool exact = true;
 #pragma unroll
-                for (int e = 0; e < 6; ++e) acc += a[e];
+                for (int e = 0; e < 6; ++e) exact = exact && CoNumOp::abs_is_exact(F[e]);
+                if (exact)
+                {
+#pragma unroll
+                    for (int e = 0; e < 6; ++e) acc += fabs(F[e]);
+                }
+                else
+                {
+#pragma unroll 1
+                    for (int e = 0; e < 6; ++e) acc += CoNumOp::mag(F[e]);
+                }
             }
         }
         const int e1 = reg ? 0 : seg[c + 1];

@@ -1255,10 +1255,16 @@ static int cg_solve_captured(fvk_solver* sv, const int32_t* rowOffs, const int32
     cudaGraph_t body = cp.conditional.phGraph_out[0];
     FVK_CUDA(cudaStreamUpdateCaptureDependencies(st, &node, 1, cudaStreamSetCaptureDependencies));
     FVK_CUDA(cudaStreamBeginCaptureToGraph(sv->bodyStream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
-    K1(sv->bodyStream, false, rA, rB, sv->p1);
-    K2(sv->bodyStream, sv->p1, sv->p0);
-    K1(sv->bodyStream, false, rB, rA, sv->p0);
-    K2(sv->bodyStream, sv->p0, sv->p1);
+    // iterations per pass: an even number (the double-buffered p and r are back where they started); once the stop flag is up
+    // the rest of a pass is no-op kernels, so longer passes trade fewer loop turns against a few idle launches at the end
+    static const int passPairs = [] { const char* e = std::getenv("FVK_CG_PASS_ITERS"); const int v = e ? std::atoi(e) : 2; return v >= 2 && v <= 16 ? v / 2 : 1; }();
+    for (int pp = 0; pp < passPairs; ++pp)
+    {
+        K1(sv->bodyStream, false, rA, rB, sv->p1);
+        K2(sv->bodyStream, sv->p1, sv->p0);
+        K1(sv->bodyStream, false, rB, rA, sv->p0);
+        K2(sv->bodyStream, sv->p0, sv->p1);
+    }
     k_loop_cond<<<1, 1, 0, sv->bodyStream>>>(sv->state, handle);
     cudaError_t le = cudaGetLastError();
     cudaGraph_t bodyOut = nullptr;

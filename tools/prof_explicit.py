@@ -36,5 +36,9 @@ for v in args.variants:
         ops.grad(gm, T.internal, T.boundary.value, out3)
         ops.laplacian(gm, T.internal, T.boundary.value, out)
         ops.surface_integrate(gm, flux, out)
+        ops.div(gm, flux, T.internal, T.boundary.value, out, scheme=ops.UPWIND)
+        co = torch.empty(2, dtype=torch.float64, device="cuda")
+        scratch = torch.empty(_capi.lib().fvk_conum_scratch_bytes(gm.handle) // 8, dtype=torch.float64, device="cuda")
+        ops.conum(gm, flux, 1e-3, co, scratch)
 torch.cuda.synchronize()
 print("done")
