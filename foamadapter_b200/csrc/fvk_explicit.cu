@@ -923,6 +923,126 @@ k_gather_affine(Op op, Scaling sc, FvkBrickGeom g, double* __restrict__ out, int
     finish<VT>(out, cell, acc, s, mode, sc);
 }
 
+// The same kernel with CPT cells per thread: the tile is CPT bricks stacked in z (thread t owns the cells t, t + TB, ...), every
+// load of all its cells is issued before the first use. For the operators with ONE face operand (surfaceIntegrate, upwind div:
+// 40-60 registers) a thread of the kernel above has too few bytes in flight to keep HBM busy (ncu: 40 % of DRAM peak at 75 %
+// occupancy, profiles/r2z_ncu_explicit_256.csv); two cells per thread raise that by half at the register budget of the others.
+template <class Op, int TB, int MINB, int CPT>
+__global__ void __launch_bounds__(TB, MINB)
+k_gather_affine_n(Op op, Scaling sc, FvkBrickGeom g, double* __restrict__ out, int mode, AffineTail tail)
+{
+    if (int(blockIdx.x) < tail.nBlocks)
+    {
+        const int idx = blockIdx.x * TB + threadIdx.x;
+        if (idx < tail.nIrr) gather_cell(op, sc, tail.irrCells[idx], tail.nI, tail.seg, tail.ent, tail.owner, tail.neighbour, out, mode);
+        return;
+    }
+    const int tileId = blockIdx.x - tail.nBlocks;
+    using VT = typename Op::V;
+    using T = typename VT::T;
+    using CL = CellLd<typename Op::CV>;
+    using CT = typename CL::T;
+    constexpr int W0 = Op::W0, W1 = Op::W1 ? Op::W1 : 1;
+    extern __shared__ __align__(16) unsigned char smem[];
+    T* sflux = reinterpret_cast<T*>(smem);
+    const double* __restrict__ S0 = op.s0();
+    const double* __restrict__ S1 = op.s1();
+    const double* __restrict__ cellsG = op.cells();
+    const int tid = threadIdx.x;
+    const int nx = g.dims[0], ny = g.dims[1], nz = g.dims[2];
+    const int64_t nxy = int64_t(nx) * ny;
+    const int tx = g.tUp[0], ty = g.tUp[1];
+    const int bz = g.brick[2] * CPT;
+    const int ix = tileId % g.tdim[0], q = tileId / g.tdim[0], iy = q % g.tdim[1], iz = q / g.tdim[1];
+    const int x0 = ix * g.brick[0], y0 = iy * g.brick[1], z0 = iz * bz;
+    const int rl = min(g.brick[0], nx - x0), ry = min(g.brick[1], ny - y0), rz = min(bz, nz - z0);
+    const bool full = rl == g.brick[0] && ry == g.brick[1] && g.shiftL >= 0 && g.shiftBy >= 0;
+    const int nc = rl * ry * rz;
+    int off[CPT], a[CPT], b[CPT];
+    bool upper[CPT], regular[CPT];
+    int64_t cell[CPT];
+    double fa[CPT][3][W0], fb[CPT][3][W1], vol[CPT];
+    CT pc[CPT], pn[CPT][3];
+#pragma unroll
+    for (int u = 0; u < CPT; ++u)
+    {
+        const int lc = tid + u * TB;
+        if (full) { off[u] = lc & (rl - 1); const int r = lc >> g.shiftL; a[u] = r & (ry - 1); b[u] = r >> g.shiftBy; }
+        else { off[u] = lc % rl; const int r = lc / rl; a[u] = r % ry; b[u] = r / ry; }
+        const int i = x0 + off[u], j = y0 + a[u], k = z0 + b[u];
+        upper[u] = lc < nc && i < nx - 1 && j < ny - 1 && k < nz - 1;
+        regular[u] = upper[u] && i > 0 && j > 0 && k > 0;
+        cell[u] = i + int64_t(nx) * j + nxy * k;
+        const int64_t fs = 3 * cell[u] - int64_t(tx) * (j + int64_t(ny) * k) - int64_t(ty) * k * nx;
+        pc[u] = CL::ld(cellsG, 0); pn[u][0] = pn[u][1] = pn[u][2] = pc[u];
+        vol[u] = 1.0;
+        if (upper[u])
+        {
+#pragma unroll
+            for (int f = 0; f < 3; ++f)
+            {
+#pragma unroll
+                for (int c = 0; c < W0; ++c) fa[u][f][c] = S0[int64_t(W0) * (fs + f) + c];
+                fb[u][f][0] = Op::W1 ? S1[fs + f] : 0.0;
+            }
+            pc[u] = CL::ld(cellsG, cell[u]);
+            pn[u][0] = CL::ld(cellsG, cell[u] + 1); pn[u][1] = CL::ld(cellsG, cell[u] + nx); pn[u][2] = CL::ld(cellsG, cell[u] + nxy);
+            vol[u] = sc.V[cell[u]];
+        }
+    }
+    // ---- cross faces: e < nZ: z side (b = 0) | < nZ + nY: y side (a = 0) | x side (off = 0); only for regular consumers
+    const int nZ = rl * ry, nY = rl * rz, nX = ry * rz, nCross = nZ + nY + nX;
+    constexpr int XB = 3 * TB * CPT;
+    for (int e = tid; e < nCross; e += TB)
+    {
+        int co, ca, cb, e1;
+        int64_t dOwner, dFace;
+        if (e < nZ) { e1 = e; cb = 0; dOwner = nxy; dFace = -3 * nxy + int64_t(tx) * ny + int64_t(ty) * nx + 2; }
+        else if (e < nZ + nY) { e1 = e - nZ; ca = 0; dOwner = nx; dFace = -3 * int64_t(nx) + tx + 1; }
+        else { e1 = e - nZ - nY; co = 0; dOwner = 1; dFace = -3; }
+        if (e < nZ) { if (full) { co = e1 & (rl - 1); ca = e1 >> g.shiftL; } else { co = e1 % rl; ca = e1 / rl; } }
+        else if (e < nZ + nY) { if (full) { co = e1 & (rl - 1); cb = e1 >> g.shiftL; } else { co = e1 % rl; cb = e1 / rl; } }
+        else { if (full) { ca = e1 & (ry - 1); cb = e1 >> g.shiftBy; } else { ca = e1 % ry; cb = e1 / ry; } }
+        const int ci = x0 + co, cj = y0 + ca, ck = z0 + cb;
+        if (!(ci > 0 && ci < nx - 1 && cj > 0 && cj < ny - 1 && ck > 0 && ck < nz - 1)) continue; // consumer not regular
+        const int64_t cc = ci + int64_t(nx) * cj + nxy * ck;
+        const int64_t xf = 3 * cc - int64_t(tx) * (cj + int64_t(ny) * ck) - int64_t(ty) * ck * nx + dFace;
+        double xa[W0], xb[W1];
+#pragma unroll
+        for (int c = 0; c < W0; ++c) xa[c] = S0[int64_t(W0) * xf + c];
+        xb[0] = Op::W1 ? S1[xf] : 0.0;
+        const CT po = CL::ld(cellsG, cc - dOwner), pnn = CL::ld(cellsG, cc);
+        sflux[XB + e] = op.fluxv(xa, xb, po, pnn);
+    }
+#pragma unroll
+    for (int u = 0; u < CPT; ++u)
+        if (upper[u])
+        {
+            const int lc = tid + u * TB;
+            sflux[3 * lc + 0] = op.fluxv(fa[u][0], fb[u][0], pc[u], pn[u][0]);
+            sflux[3 * lc + 1] = op.fluxv(fa[u][1], fb[u][1], pc[u], pn[u][1]);
+            sflux[3 * lc + 2] = op.fluxv(fa[u][2], fb[u][2], pc[u], pn[u][2]);
+        }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < CPT; ++u)
+    {
+        if (!regular[u]) continue;
+        const int lc = tid + u * TB;
+        T acc = (mode == FVK_ACC_SCALE) ? VT::ld(out, cell[u]) : VT::zero();
+        acc = VT::sub(acc, b[u] > 0 ? sflux[3 * (lc - rl * ry) + 2] : sflux[XB + off[u] + rl * a[u]]);
+        acc = VT::sub(acc, a[u] > 0 ? sflux[3 * (lc - rl) + 1] : sflux[XB + nZ + off[u] + rl * b[u]]);
+        acc = VT::sub(acc, off[u] > 0 ? sflux[3 * (lc - 1)] : sflux[XB + nZ + nY + a[u] + ry * b[u]]);
+        acc = VT::add(acc, sflux[3 * lc + 0]);
+        acc = VT::add(acc, sflux[3 * lc + 1]);
+        acc = VT::add(acc, sflux[3 * lc + 2]);
+        double s;
+        if (sc.invVolOnly) s = 1 / vol[u];
+        else s = (sc.view ? sc.view[cell[u]] * sc.coeff : sc.coeff) / vol[u];
+        finish<VT>(out, cell[u], acc, s, mode, sc);
+    }
+}
+
 template <class Op, int TB, int MINB, bool XDEFER>
 int launch_brick_n(const fvk_mesh* m, Op op, Scaling sc, double* out, int mode, cudaStream_t st)
 {
@@ -954,6 +1074,28 @@ int launch_affine_n(const fvk_mesh* m, Op op, Scaling sc, double* out, int mode,
     if (ab > 48 * 1024) return -1;
     const int listBlocks = m->tilePhase == 0 ? (m->bp.nIrr + TB - 1) / TB : 0;
     AffineTail tail {listBlocks, m->bp.nIrr, m->nInternalFaces, m->bp.irrCells, m->stencilSeg, m->gatherEnt, m->owner, m->neighbour};
+    // one-operand scalar operators: two cells per thread (k_gather_affine_n); FVK_AFFINE_CPT="cpt,minb" overrides for sweeps
+    constexpr bool oneOperand = sizeof(T) == 8 && Op::W0 == 1 && Op::W1 == 0;
+    int cpt = oneOperand ? 2 : 1, minb2 = 8;
+    {
+        static const char* env = std::getenv("FVK_AFFINE_CPT");
+        int a1 = 0, a2 = 0;
+        if (env && std::sscanf(env, "%d,%d", &a1, &a2) == 2) { cpt = oneOperand ? a1 : 1; minb2 = a2; }
+    }
+    if constexpr (oneOperand && TB == 128)
+    if (m->tilePhase != 2 && cpt == 2)
+    {
+        const int bz = g.brick[2] * 2, tz = (g.dims[2] + bz - 1) / bz;
+        const int nTiles2 = g.tdim[0] * g.tdim[1] * tz;
+        const size_t ab2 = (size_t(3) * TB * 2 + size_t(g.brick[0]) * g.brick[1] + size_t(g.brick[0]) * bz + size_t(g.brick[1]) * bz) * sizeof(T);
+        if (ab2 <= 48 * 1024)
+        {
+            if (minb2 >= 8) k_gather_affine_n<Op, 128, 8, 2><<<listBlocks + nTiles2, 128, ab2, st>>>(op, sc, g, out, mode, tail);
+            else k_gather_affine_n<Op, 128, 6, 2><<<listBlocks + nTiles2, 128, ab2, st>>>(op, sc, g, out, mode, tail);
+            FVK_LAUNCH_CHECK();
+            return FVK_OK;
+        }
+    }
     if (m->tilePhase != 2) // phase 0: one launch, list blocks + tiles
         k_gather_affine<Op, TB, MINB><<<listBlocks + m->bp.nTiles, TB, ab, st>>>(op, sc, g, out, mode, tail);
     else if (m->bp.nIrr > 0)
@@ -1130,7 +1272,27 @@ __device__ __forceinline__ double warp_max(double v)
 struct CoNumAffine
 {
     int on, nx, ny, nz, tx, ty;
+    int nIrr;            // on: the irregular cells (boundary / cut layers) are taken from this list, spread over ALL threads
+    const int* irrCells;
 };
+// one cell through its stencil: the face ids of up to eight entries, then their fluxes, then the sums -- three dependent round
+// trips instead of one per face
+__device__ __forceinline__ double conum_cell_generic(const CoNumOp& op, int c, const int* __restrict__ seg, const int* __restrict__ ent)
+{
+    double acc = 0.0;
+    const int e0 = seg[c], e1 = seg[c + 1];
+    int ids[8];
+    double F[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) ids[q] = (e0 + q < e1) ? (ent[e0 + q] >> 1) : -1;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) F[q] = ids[q] >= 0 ? op.faceFlux[ids[q]] : 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        if (e0 + q < e1) acc += CoNumOp::mag(F[q]);
+    for (int e = e0 + 8; e < e1; ++e) acc += op.at(ent[e] >> 1);
+    return acc;
+}
 __global__ void __launch_bounds__(256)
 k_conum_stage1(CoNumOp op, int nC, const int* __restrict__ seg, const int* __restrict__ ent,
                const double* __restrict__ V, double* __restrict__ partial /* [3*gridDim.x] */, CoNumAffine aff)
@@ -1140,44 +1302,53 @@ k_conum_stage1(CoNumOp op, int nC, const int* __restrict__ seg, const int* __res
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nC; c += gridDim.x * blockDim.x)
     {
         double acc = 0.0;
-        bool reg = false;
         if (aff.on)
         {
             const int i = c % aff.nx, q = c / aff.nx, j = q % aff.ny, k = q / aff.ny;
-            reg = i > 0 && i < aff.nx - 1 && j > 0 && j < aff.ny - 1 && k > 0 && k < aff.nz - 1;
-            if (reg)
+            // an irregular cell costs three dependent round trips and would hold up its warp in EVERY pass of this loop (the
+            // grid stride is a multiple of nx: the same lanes meet the block's outer layer each time): they come from the
+            // plan's list below, spread over all threads
+            if (!(i > 0 && i < aff.nx - 1 && j > 0 && j < aff.ny - 1 && k > 0 && k < aff.nz - 1)) continue;
+            const int64_t nxy = int64_t(aff.nx) * aff.ny;
+            const int64_t fs = 3 * int64_t(c) - int64_t(aff.tx) * (j + int64_t(aff.ny) * k) - int64_t(aff.ty) * k * aff.nx;
+            const int64_t f[6] = {fs - 3 * nxy + int64_t(aff.tx) * aff.ny + int64_t(aff.ty) * aff.nx + 2, fs - 3 * int64_t(aff.nx) + aff.tx + 1, fs - 3,
+                                  fs, fs + 1, fs + 2};
+            // all six loads first (a branch on a loaded value between them would serialise six DRAM round trips), then one
+            // test for the exact-|F| range; the sqrt(F * F) form only runs for a cell that has a face outside it
+            double F[6];
+#pragma unroll
+            for (int e = 0; e < 6; ++e) F[e] = op.faceFlux[f[e]];
+            bool exact = true;
+#pragma unroll
+            for (int e = 0; e < 6; ++e) exact = exact && CoNumOp::abs_is_exact(F[e]);
+            if (exact)
             {
-                const int64_t nxy = int64_t(aff.nx) * aff.ny;
-                const int64_t fs = 3 * int64_t(c) - int64_t(aff.tx) * (j + int64_t(aff.ny) * k) - int64_t(aff.ty) * k * aff.nx;
-                const int64_t f[6] = {fs - 3 * nxy + int64_t(aff.tx) * aff.ny + int64_t(aff.ty) * aff.nx + 2, fs - 3 * int64_t(aff.nx) + aff.tx + 1, fs - 3,
-                                      fs, fs + 1, fs + 2};
-                // all six loads first (a branch on a loaded value between them would serialise six DRAM round trips), then one
-                // test for the exact-|F| range; the sqrt(F * F) form only runs for a cell that has a face outside it
-                double F[6];
 #pragma unroll
-                for (int e = 0; e < 6; ++e) F[e] = op.faceFlux[f[e]];
-                bool exact = true;
-#pragma unroll
-                for (int e = 0; e < 6; ++e) exact = exact && CoNumOp::abs_is_exact(F[e]);
-                if (exact)
-                {
-#pragma unroll
-                    for (int e = 0; e < 6; ++e) acc += fabs(F[e]);
-                }
-                else
-                {
+                for (int e = 0; e < 6; ++e) acc += fabs(F[e]);
+            }
+            else
+            {
 #pragma unroll 1
-                    for (int e = 0; e < 6; ++e) acc += CoNumOp::mag(F[e]);
-                }
+                for (int e = 0; e < 6; ++e) acc += CoNumOp::mag(F[e]);
             }
         }
-        const int e1 = reg ? 0 : seg[c + 1];
-        for (int e = reg ? 0 : seg[c]; e < e1; ++e) acc += op.at(ent[e] >> 1);
+        else
+            acc = conum_cell_generic(op, c, seg, ent);
         const double v = V[c];
         lmax = fmax(lmax, acc / v);
         lphi += acc;
         lvol += v;
     }
+    if (aff.on)
+        for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < aff.nIrr; idx += gridDim.x * blockDim.x)
+        {
+            const int c = aff.irrCells[idx];
+            const double acc = conum_cell_generic(op, c, seg, ent);
+            const double v = V[c];
+            lmax = fmax(lmax, acc / v);
+            lphi += acc;
+            lvol += v;
+        }
     lmax = warp_max(lmax); lphi = warp_sum(lphi); lvol = warp_sum(lvol);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (lane == 0) { sMax[wid] = lmax; sPhi[wid] = lphi; sVol[wid] = lvol; }
@@ -1430,7 +1601,7 @@ extern "C" int fvk_conum(const fvk_mesh* m, const double* faceFlux, double dt, d
     double* partial = static_cast<double*>(scratch_d);
     const FvkBrickGeom& bg = m->bp.geom;
     const bool affine = !fvk_no_affine() && m->bp.nTiles > 0 && bg.affine && int64_t(bg.dims[0]) * bg.dims[1] * bg.dims[2] == m->nOwned;
-    const CoNumAffine ca {affine ? 1 : 0, bg.dims[0], bg.dims[1], bg.dims[2], bg.tUp[0], bg.tUp[1]};
+    const CoNumAffine ca {affine ? 1 : 0, bg.dims[0], bg.dims[1], bg.dims[2], bg.tUp[0], bg.tUp[1], m->bp.nIrr, m->bp.irrCells};
     k_conum_stage1<<<grid, 256, 0, fvk_cu(s)>>>(CoNumOp {faceFlux}, m->nOwned, m->stencilSeg, m->gatherEnt, m->V, partial, ca);
     FVK_LAUNCH_CHECK();
     k_conum_stage2<<<1, 256, 0, fvk_cu(s)>>>(grid, partial, dt, result_d);
