@@ -135,11 +135,18 @@ extern "C" int fvk_blockmesh_create(int32_t nx, int32_t ny, int32_t nz, double l
                     p[2] = lz * (double(k) / nz);
                 }
 
-        // ---- poly faces -------------------------------------------------------------------
-        st->polyFaces.resize(4 * int64_t(nPoly));
-        st->polyOwner.resize(nPoly);
+        // ---- faces ------------------------------------------------------------------------
+        // Everything below is CELL-CENTRIC and parallel over cells (or over a side's faces): the block's topology is closed
+        // form, so a cell finds its own faces and its lower neighbours' faces by arithmetic. The per-cell sums keep the order
+        // of OpenFOAM's face loops (all faces the cell owns in ascending poly id, then the faces it is neighbour of in
+        // ascending id), so the geometry is bit-identical to the serial face-loop formulation (and to oracle/blockmesh.cpp).
         st->neighbour.resize(nI);
-        st->nPolyFaces = nPoly;
+        st->nPolyFaces = withPoints ? nPoly : 0;
+        if (withPoints)
+        {
+            st->polyFaces.resize(4 * int64_t(nPoly));
+            st->polyOwner.resize(nPoly);
+        }
         // internal faces: owner ascending, then +x, +y, +z. First face id of each cell by scan.
         std::vector<int32_t> ownStart(size_t(nC) + 1);
         {
@@ -158,42 +165,12 @@ extern "C" int fvk_blockmesh_create(int32_t nx, int32_t ny, int32_t nz, double l
                 }
             ownStart[nC] = int32_t(run);
         }
-#pragma omp parallel for schedule(static)
-        for (int64_t k = 0; k < nz; ++k)
-            for (int64_t j = 0; j < ny; ++j)
-                for (int64_t i = 0; i < nx; ++i)
-                {
-                    const int32_t c = cell(i, j, k);
-                    int32_t f = ownStart[c];
-                    if (i < nx - 1)
-                    {
-                        int32_t* q = &st->polyFaces[4 * int64_t(f)];
-                        q[0] = vtx(i + 1, j, k); q[1] = vtx(i + 1, j + 1, k);
-                        q[2] = vtx(i + 1, j + 1, k + 1); q[3] = vtx(i + 1, j, k + 1);
-                        st->polyOwner[f] = c; st->neighbour[f] = cell(i + 1, j, k); ++f;
-                    }
-                    if (j < ny - 1)
-                    {
-                        int32_t* q = &st->polyFaces[4 * int64_t(f)];
-                        q[0] = vtx(i, j + 1, k); q[1] = vtx(i, j + 1, k + 1);
-                        q[2] = vtx(i + 1, j + 1, k + 1); q[3] = vtx(i + 1, j + 1, k);
-                        st->polyOwner[f] = c; st->neighbour[f] = cell(i, j + 1, k); ++f;
-                    }
-                    if (k < nz - 1)
-                    {
-                        int32_t* q = &st->polyFaces[4 * int64_t(f)];
-                        q[0] = vtx(i, j, k + 1); q[1] = vtx(i + 1, j, k + 1);
-                        q[2] = vtx(i + 1, j + 1, k + 1); q[3] = vtx(i, j + 1, k + 1);
-                        st->polyOwner[f] = c; st->neighbour[f] = cell(i, j, k + 1); ++f;
-                    }
-                }
-        // boundary faces: patches in dictionary order, sides in listed order
-        // (blockMesh block::createBoundary loop nests)
-        std::vector<int32_t> keepStart; // poly start of each kept (non-empty-type) side run
-        std::vector<int32_t> keepSize;
+        // boundary faces: patches in dictionary order, sides in listed order (blockMesh block::createBoundary loop nests);
+        // sideStart = poly id of the side's first face, -> its index in the kept (non-empty-type) boundary list or -1
+        int64_t sideStart[6] = {0, 0, 0, 0, 0, 0}, sideKept[6] = {-1, -1, -1, -1, -1, -1};
         st->patchOffsets.assign(1, 0);
         {
-            int64_t f = nI;
+            int64_t f = nI, kept = 0;
             int s = 0;
             for (int p = 0; p < nPatches; ++p)
             {
@@ -202,126 +179,166 @@ extern "C" int fvk_blockmesh_create(int32_t nx, int32_t ny, int32_t nz, double l
                 for (int q = 0; q < patchNSides[p]; ++q, ++s)
                 {
                     const int side = patchSides[s];
-                    const int64_t f0 = f;
-                    auto put = [&](int32_t a, int32_t b, int32_t c, int32_t d, int32_t own) {
-                        int32_t* r = &st->polyFaces[4 * f];
-                        r[0] = a; r[1] = b; r[2] = c; r[3] = d;
-                        st->polyOwner[f] = own;
-                        ++f;
-                    };
-                    switch (side)
-                    {
-                        case 0:
-                            for (int64_t k = 0; k < nz; ++k) for (int64_t j = 0; j < ny; ++j)
-                                put(vtx(0, j, k), vtx(0, j, k + 1), vtx(0, j + 1, k + 1), vtx(0, j + 1, k), cell(0, j, k));
-                            break;
-                        case 1:
-                            for (int64_t k = 0; k < nz; ++k) for (int64_t j = 0; j < ny; ++j)
-                                put(vtx(nx, j, k), vtx(nx, j + 1, k), vtx(nx, j + 1, k + 1), vtx(nx, j, k + 1), cell(nx - 1, j, k));
-                            break;
-                        case 2:
-                            for (int64_t i = 0; i < nx; ++i) for (int64_t k = 0; k < nz; ++k)
-                                put(vtx(i, 0, k), vtx(i + 1, 0, k), vtx(i + 1, 0, k + 1), vtx(i, 0, k + 1), cell(i, 0, k));
-                            break;
-                        case 3:
-                            for (int64_t i = 0; i < nx; ++i) for (int64_t k = 0; k < nz; ++k)
-                                put(vtx(i, ny, k), vtx(i, ny, k + 1), vtx(i + 1, ny, k + 1), vtx(i + 1, ny, k), cell(i, ny - 1, k));
-                            break;
-                        case 4:
-                            for (int64_t i = 0; i < nx; ++i) for (int64_t j = 0; j < ny; ++j)
-                                put(vtx(i, j, 0), vtx(i, j + 1, 0), vtx(i + 1, j + 1, 0), vtx(i + 1, j, 0), cell(i, j, 0));
-                            break;
-                        default:
-                            for (int64_t i = 0; i < nx; ++i) for (int64_t j = 0; j < ny; ++j)
-                                put(vtx(i, j, nz), vtx(i + 1, j, nz), vtx(i + 1, j + 1, nz), vtx(i, j + 1, nz), cell(i, j, nz - 1));
-                            break;
-                    }
+                    sideStart[side] = f;
+                    f += sideSize[side];
                     if (!isEmpty)
                     {
-                        keepStart.push_back(int32_t(f0));
-                        keepSize.push_back(int32_t(f - f0));
-                        patchSize += int32_t(f - f0);
+                        sideKept[side] = kept;
+                        kept += sideSize[side];
+                        patchSize += int32_t(sideSize[side]);
                     }
                 }
                 if (!isEmpty) st->patchOffsets.push_back(st->patchOffsets.back() + patchSize);
             }
         }
         const int32_t nKeptPatches = int32_t(st->patchOffsets.size()) - 1;
-
-        // ---- geometry on all poly faces ---------------------------------------------------
-        std::vector<double> pCf(3 * size_t(nPoly)), pSf(3 * size_t(nPoly));
-#pragma omp parallel for schedule(static)
-        for (int64_t f = 0; f < nPoly; ++f)
-            quadGeometry(st->points.data(), &st->polyFaces[4 * f], &pCf[3 * f], &pSf[3 * f]);
-
-        // cell centre estimate = mean of face centres (own faces then nei faces, OpenFOAM order)
-        std::vector<double> cEst(3 * size_t(nC), 0.0);
-        std::vector<int32_t> cnt(nC, 0);
-        for (int64_t f = 0; f < nPoly; ++f)
-        {
-            const int32_t o = st->polyOwner[f];
-            for (int d = 0; d < 3; ++d) cEst[3 * size_t(o) + d] += pCf[3 * f + d];
-            ++cnt[o];
-        }
-        for (int64_t f = 0; f < nI; ++f)
-        {
-            const int32_t n = st->neighbour[f];
-            for (int d = 0; d < 3; ++d) cEst[3 * size_t(n) + d] += pCf[3 * f + d];
-            ++cnt[n];
-        }
-#pragma omp parallel for schedule(static)
-        for (int64_t c = 0; c < nC; ++c)
-            for (int d = 0; d < 3; ++d) cEst[3 * c + d] /= cnt[c];
-
-        st->C.assign(3 * size_t(nC), 0.0);
-        st->V.assign(nC, 0.0);
-        for (int64_t f = 0; f < nPoly; ++f)
-        {
-            const size_t o = size_t(st->polyOwner[f]);
-            double pyr3 = 0.0;
-            for (int d = 0; d < 3; ++d) pyr3 += pSf[3 * f + d] * (pCf[3 * f + d] - cEst[3 * o + d]);
-            for (int d = 0; d < 3; ++d)
-                st->C[3 * o + d] += pyr3 * ((3.0 / 4.0) * pCf[3 * f + d] + (1.0 / 4.0) * cEst[3 * o + d]);
-            st->V[o] += pyr3;
-        }
-        for (int64_t f = 0; f < nI; ++f)
-        {
-            const size_t n = size_t(st->neighbour[f]);
-            double pyr3 = 0.0;
-            for (int d = 0; d < 3; ++d) pyr3 += pSf[3 * f + d] * (cEst[3 * n + d] - pCf[3 * f + d]);
-            for (int d = 0; d < 3; ++d)
-                st->C[3 * n + d] += pyr3 * ((3.0 / 4.0) * pCf[3 * f + d] + (1.0 / 4.0) * cEst[3 * n + d]);
-            st->V[n] += pyr3;
-        }
-#pragma omp parallel for schedule(static)
-        for (int64_t c = 0; c < nC; ++c)
-        {
-            for (int d = 0; d < 3; ++d) st->C[3 * c + d] /= st->V[c];
-            st->V[c] *= (1.0 / 3.0);
-        }
-        std::vector<double>().swap(cEst);
-        std::vector<int32_t>().swap(cnt);
-
-        // ---- NeoN view: internal faces + kept boundary faces ------------------------------
+        // index of a cell's face inside a side's loop nest, and the inverse
+        auto sideIndex = [=](int side, int64_t i, int64_t j, int64_t k) -> int64_t {
+            return side < 2 ? k * ny + j : (side < 4 ? i * nz + k : i * ny + j);
+        };
+        const int64_t nPolyBnd = nPolyB;
+        std::vector<double> bndCf(3 * size_t(nPolyBnd)), bndSf(3 * size_t(nPolyBnd)); // geometry of ALL boundary poly faces (incl. empty patches)
         st->owner.resize(nF);
         st->Sf.resize(3 * size_t(nF));
         st->Cf.resize(3 * size_t(nF));
         st->magSf.resize(nF);
-        std::memcpy(st->owner.data(), st->polyOwner.data(), sizeof(int32_t) * size_t(nI));
-        std::memcpy(st->Sf.data(), pSf.data(), sizeof(double) * 3 * size_t(nI));
-        std::memcpy(st->Cf.data(), pCf.data(), sizeof(double) * 3 * size_t(nI));
+        const double* pts = st->points.data();
+        for (int side = 0; side < 6; ++side)
         {
-            int64_t dst = nI;
-            for (size_t r = 0; r < keepStart.size(); ++r)
+            const int64_t n = sideSize[side], f0 = sideStart[side];
+#pragma omp parallel for schedule(static)
+            for (int64_t idx = 0; idx < n; ++idx)
             {
-                std::memcpy(&st->owner[dst], &st->polyOwner[keepStart[r]], sizeof(int32_t) * size_t(keepSize[r]));
-                std::memcpy(&st->Sf[3 * dst], &pSf[3 * size_t(keepStart[r])], sizeof(double) * 3 * size_t(keepSize[r]));
-                std::memcpy(&st->Cf[3 * dst], &pCf[3 * size_t(keepStart[r])], sizeof(double) * 3 * size_t(keepSize[r]));
-                dst += keepSize[r];
+                int64_t i, j, k;
+                int32_t q[4];
+                switch (side)
+                {
+                    case 0: k = idx / ny; j = idx % ny; i = 0;
+                        q[0] = vtx(0, j, k); q[1] = vtx(0, j, k + 1); q[2] = vtx(0, j + 1, k + 1); q[3] = vtx(0, j + 1, k); break;
+                    case 1: k = idx / ny; j = idx % ny; i = nx - 1;
+                        q[0] = vtx(nx, j, k); q[1] = vtx(nx, j + 1, k); q[2] = vtx(nx, j + 1, k + 1); q[3] = vtx(nx, j, k + 1); break;
+                    case 2: i = idx / nz; k = idx % nz; j = 0;
+                        q[0] = vtx(i, 0, k); q[1] = vtx(i + 1, 0, k); q[2] = vtx(i + 1, 0, k + 1); q[3] = vtx(i, 0, k + 1); break;
+                    case 3: i = idx / nz; k = idx % nz; j = ny - 1;
+                        q[0] = vtx(i, ny, k); q[1] = vtx(i, ny, k + 1); q[2] = vtx(i + 1, ny, k + 1); q[3] = vtx(i + 1, ny, k); break;
+                    case 4: i = idx / ny; j = idx % ny; k = 0;
+                        q[0] = vtx(i, j, 0); q[1] = vtx(i, j + 1, 0); q[2] = vtx(i + 1, j + 1, 0); q[3] = vtx(i + 1, j, 0); break;
+                    default: i = idx / ny; j = idx % ny; k = nz - 1;
+                        q[0] = vtx(i, j, nz); q[1] = vtx(i + 1, j, nz); q[2] = vtx(i + 1, j + 1, nz); q[3] = vtx(i, j + 1, nz); break;
+                }
+                const int64_t f = f0 + idx, fb = f - nI;
+                quadGeometry(pts, q, &bndCf[3 * fb], &bndSf[3 * fb]);
+                if (withPoints)
+                {
+                    for (int d = 0; d < 4; ++d) st->polyFaces[4 * f + d] = q[d];
+                    st->polyOwner[f] = cell(i, j, k);
+                }
+                if (sideKept[side] >= 0)
+                { // NeoN view: the kept boundary faces follow the internal ones
+                    const int64_t g = nI + sideKept[side] + idx;
+                    st->owner[g] = cell(i, j, k);
+                    for (int d = 0; d < 3; ++d) { st->Cf[3 * g + d] = bndCf[3 * fb + d]; st->Sf[3 * g + d] = bndSf[3 * fb + d]; }
+                }
             }
         }
-        std::vector<double>().swap(pSf);
-        std::vector<double>().swap(pCf);
+        // internal faces: labels and geometry straight into the NeoN arrays (poly id == NeoN id for them)
+#pragma omp parallel for schedule(static)
+        for (int64_t k = 0; k < nz; ++k)
+            for (int64_t j = 0; j < ny; ++j)
+                for (int64_t i = 0; i < nx; ++i)
+                {
+                    const int32_t c = cell(i, j, k);
+                    int64_t f = ownStart[c];
+                    int32_t q[4];
+                    auto emit = [&](int32_t nei) {
+                        quadGeometry(pts, q, &st->Cf[3 * f], &st->Sf[3 * f]);
+                        st->owner[f] = c; st->neighbour[f] = nei;
+                        if (withPoints)
+                        {
+                            for (int d = 0; d < 4; ++d) st->polyFaces[4 * f + d] = q[d];
+                            st->polyOwner[f] = c;
+                        }
+                        ++f;
+                    };
+                    if (i < nx - 1)
+                    {
+                        q[0] = vtx(i + 1, j, k); q[1] = vtx(i + 1, j + 1, k); q[2] = vtx(i + 1, j + 1, k + 1); q[3] = vtx(i + 1, j, k + 1);
+                        emit(cell(i + 1, j, k));
+                    }
+                    if (j < ny - 1)
+                    {
+                        q[0] = vtx(i, j + 1, k); q[1] = vtx(i, j + 1, k + 1); q[2] = vtx(i + 1, j + 1, k + 1); q[3] = vtx(i + 1, j + 1, k);
+                        emit(cell(i, j + 1, k));
+                    }
+                    if (k < nz - 1)
+                    {
+                        q[0] = vtx(i, j, k + 1); q[1] = vtx(i + 1, j, k + 1); q[2] = vtx(i + 1, j + 1, k + 1); q[3] = vtx(i, j + 1, k + 1);
+                        emit(cell(i, j, k + 1));
+                    }
+                }
+
+        // ---- cell centres and volumes (primitiveMeshCellCentresAndVols.C), per cell ---------------------------------
+        // a cell's faces: owned = its internal faces [ownStart[c], ownStart[c+1]) then its boundary faces in ascending poly id;
+        // neighbour-of = the z, y, x faces of the cells below / in front / left (ascending ids)
+        st->C.resize(3 * size_t(nC));
+        st->V.resize(nC);
+        const int64_t nxy = int64_t(nx) * ny;
+#pragma omp parallel for schedule(static)
+        for (int64_t k = 0; k < nz; ++k)
+            for (int64_t j = 0; j < ny; ++j)
+                for (int64_t i = 0; i < nx; ++i)
+                {
+                    const int64_t c = cell(i, j, k);
+                    const double* own[9];
+                    const double* ownS[9];
+                    int nOwn = 0;
+                    for (int64_t f = ownStart[c]; f < ownStart[c + 1]; ++f) { own[nOwn] = &st->Cf[3 * f]; ownS[nOwn] = &st->Sf[3 * f]; ++nOwn; }
+                    int64_t bf[6];
+                    int nb = 0;
+                    if (i == 0) bf[nb++] = sideStart[0] + sideIndex(0, i, j, k);
+                    if (i == nx - 1) bf[nb++] = sideStart[1] + sideIndex(1, i, j, k);
+                    if (j == 0) bf[nb++] = sideStart[2] + sideIndex(2, i, j, k);
+                    if (j == ny - 1) bf[nb++] = sideStart[3] + sideIndex(3, i, j, k);
+                    if (k == 0) bf[nb++] = sideStart[4] + sideIndex(4, i, j, k);
+                    if (k == nz - 1) bf[nb++] = sideStart[5] + sideIndex(5, i, j, k);
+                    for (int x = 1; x < nb; ++x) // ascending poly id (at most six)
+                        for (int y = x; y > 0 && bf[y] < bf[y - 1]; --y) { const int64_t t = bf[y]; bf[y] = bf[y - 1]; bf[y - 1] = t; }
+                    for (int x = 0; x < nb; ++x) { own[nOwn] = &bndCf[3 * (bf[x] - nI)]; ownS[nOwn] = &bndSf[3 * (bf[x] - nI)]; ++nOwn; }
+                    const double* low[3];
+                    const double* lowS[3];
+                    int nLow = 0;
+                    if (k > 0) { const int64_t f = ownStart[c - nxy] + (i < nx - 1) + (j < ny - 1); low[nLow] = &st->Cf[3 * f]; lowS[nLow] = &st->Sf[3 * f]; ++nLow; }
+                    if (j > 0) { const int64_t f = ownStart[c - nx] + (i < nx - 1); low[nLow] = &st->Cf[3 * f]; lowS[nLow] = &st->Sf[3 * f]; ++nLow; }
+                    if (i > 0) { const int64_t f = ownStart[c - 1]; low[nLow] = &st->Cf[3 * f]; lowS[nLow] = &st->Sf[3 * f]; ++nLow; }
+                    // cell centre estimate = mean of face centres (own faces then nei faces, OpenFOAM order)
+                    double est[3] = {0.0, 0.0, 0.0};
+                    for (int x = 0; x < nOwn; ++x)
+                        for (int d = 0; d < 3; ++d) est[d] += own[x][d];
+                    for (int x = 0; x < nLow; ++x)
+                        for (int d = 0; d < 3; ++d) est[d] += low[x][d];
+                    const int cnt = nOwn + nLow;
+                    for (int d = 0; d < 3; ++d) est[d] /= cnt;
+                    double Cc[3] = {0.0, 0.0, 0.0}, Vc = 0.0;
+                    for (int x = 0; x < nOwn; ++x)
+                    {
+                        double pyr3 = 0.0;
+                        for (int d = 0; d < 3; ++d) pyr3 += ownS[x][d] * (own[x][d] - est[d]);
+                        for (int d = 0; d < 3; ++d) Cc[d] += pyr3 * ((3.0 / 4.0) * own[x][d] + (1.0 / 4.0) * est[d]);
+                        Vc += pyr3;
+                    }
+                    for (int x = 0; x < nLow; ++x)
+                    {
+                        double pyr3 = 0.0;
+                        for (int d = 0; d < 3; ++d) pyr3 += lowS[x][d] * (est[d] - low[x][d]);
+                        for (int d = 0; d < 3; ++d) Cc[d] += pyr3 * ((3.0 / 4.0) * low[x][d] + (1.0 / 4.0) * est[d]);
+                        Vc += pyr3;
+                    }
+                    for (int d = 0; d < 3; ++d) st->C[3 * c + d] = Cc[d] / Vc;
+                    st->V[c] = Vc * (1.0 / 3.0);
+                }
+        std::vector<double>().swap(bndCf);
+        std::vector<double>().swap(bndSf);
+        std::vector<int32_t>().swap(ownStart);
 #pragma omp parallel for schedule(static)
         for (int64_t f = 0; f < nF; ++f)
         {
@@ -355,13 +372,7 @@ extern "C" int fvk_blockmesh_create(int32_t nx, int32_t ny, int32_t nz, double l
             st->bWeights[b] = 1.0;
             st->bDeltaCoeffs[b] = 1.0 / std::sqrt(d2);
         }
-        if (!withPoints)
-        {
-            std::vector<double>().swap(st->points);
-            std::vector<int32_t>().swap(st->polyFaces);
-            std::vector<int32_t>().swap(st->polyOwner);
-            st->nPolyFaces = 0;
-        }
+        if (!withPoints) std::vector<double>().swap(st->points);
 
         fvk_mesh_desc& d = st->desc;
         d.nCells = nC; d.nInternalFaces = nI; d.nBoundaryFaces = nB; d.nPatches = nKeptPatches;
