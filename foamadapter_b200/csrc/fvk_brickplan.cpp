@@ -12,35 +12,78 @@
 #include <map>
 #include <utility>
 
-void fvk_build_stencil(const fvk_mesh_desc* d, FvkStencilHost& st)
+void fvk_build_stencil(const fvk_mesh_desc* d, FvkStencilHost& st, bool withPlan)
 {
     const int32_t nC = d->nCells, nI = d->nInternalFaces, nB = d->nBoundaryFaces;
     const int32_t* own = d->faceOwner;
     const int32_t* nei = d->faceNeighbour;
     std::vector<int32_t>& seg = st.seg;
     seg.assign(size_t(nC) + 1, 0);
-    for (int32_t f = 0; f < nI; ++f) { ++seg[size_t(own[f]) + 1]; ++seg[size_t(nei[f]) + 1]; }
-    for (int32_t b = 0; b < nB; ++b) ++seg[size_t(d->faceCells[b]) + 1];
+    // counting sort of the (cell, face) incidences, every pass parallel: count, scan, scatter in any order, then each cell
+    // sorts its handful of entries by face id -- the order a serial visit of the faces in ascending id would append them in
+    // (cellToFaceStencil.cpp:82-93 sorts too). A boundary face's key (nI + b) << 1 puts it behind the internal faces.
+#pragma omp parallel for schedule(static)
+    for (int32_t f = 0; f < nI; ++f)
+    {
+#pragma omp atomic
+        ++seg[size_t(own[f]) + 1];
+#pragma omp atomic
+        ++seg[size_t(nei[f]) + 1];
+    }
+#pragma omp parallel for schedule(static)
+    for (int32_t b = 0; b < nB; ++b)
+    {
+#pragma omp atomic
+        ++seg[size_t(d->faceCells[b]) + 1];
+    }
     for (int32_t c = 0; c < nC; ++c) seg[size_t(c) + 1] += seg[c];
     const size_t nEnt = size_t(seg[nC]);
     std::vector<int32_t>&val = st.val, &ent = st.ent, &plan = st.plan;
-    val.resize(nEnt); ent.resize(nEnt); plan.resize(2 * nEnt);
-    std::vector<int32_t> pos(seg.begin(), seg.end() - 1);
-    // visiting faces in ascending id appends ascending ids (cellToFaceStencil.cpp:82-93 sorts; same result)
-    for (int32_t f = 0; f < nI; ++f)
+    val.resize(nEnt); ent.resize(nEnt);
+    if (withPlan) plan.resize(2 * nEnt); else plan.clear();
     {
-        int32_t k = pos[own[f]]++;
-        val[k] = f; ent[k] = f << 1;
-        plan[2 * size_t(k)] = f << 1; plan[2 * size_t(k) + 1] = nei[f];
-        k = pos[nei[f]]++;
-        val[k] = f; ent[k] = (f << 1) | 1;
-        plan[2 * size_t(k)] = (f << 1) | 1; plan[2 * size_t(k) + 1] = own[f];
+        std::vector<int32_t> pos(seg.begin(), seg.end() - 1);
+#pragma omp parallel for schedule(static)
+        for (int32_t f = 0; f < nI; ++f)
+        {
+            int32_t k;
+#pragma omp atomic capture
+            k = pos[own[f]]++;
+            ent[k] = f << 1;
+#pragma omp atomic capture
+            k = pos[nei[f]]++;
+            ent[k] = (f << 1) | 1;
+        }
+#pragma omp parallel for schedule(static)
+        for (int32_t b = 0; b < nB; ++b)
+        {
+            int32_t k;
+#pragma omp atomic capture
+            k = pos[d->faceCells[b]]++;
+            ent[k] = (nI + b) << 1;
+        }
     }
-    for (int32_t b = 0; b < nB; ++b)
+#pragma omp parallel for schedule(static)
+    for (int32_t c = 0; c < nC; ++c)
     {
-        const int32_t k = pos[d->faceCells[b]]++;
-        val[k] = nI + b; ent[k] = (nI + b) << 1;
-        plan[2 * size_t(k)] = -(b + 1); plan[2 * size_t(k) + 1] = d->faceCells[b];
+        const int32_t b0 = seg[c], b1 = seg[size_t(c) + 1];
+        for (int32_t x = b0 + 1; x < b1; ++x) // insertion sort: a cell has a handful of faces
+        {
+            const int32_t v = ent[x];
+            int32_t y = x;
+            for (; y > b0 && ent[y - 1] > v; --y) ent[y] = ent[y - 1];
+            ent[y] = v;
+        }
+        for (int32_t k = b0; k < b1; ++k)
+        {
+            const int32_t f = ent[k] >> 1;
+            val[k] = f;
+            if (withPlan)
+            {
+                if (f < nI) { plan[2 * size_t(k)] = ent[k]; plan[2 * size_t(k) + 1] = (ent[k] & 1) ? own[f] : nei[f]; }
+                else { plan[2 * size_t(k)] = -(f - nI + 1); plan[2 * size_t(k) + 1] = d->faceCells[f - nI]; }
+            }
+        }
     }
     if (d->faceOrder)
     {
@@ -64,12 +107,12 @@ void fvk_build_stencil(const fvk_mesh_desc* d, FvkStencilHost& st)
                 for (size_t i = 0; i < tmp.size(); ++i)
                 {
                     e2[i] = ent[tmp[i].second];
-                    p2[2 * i] = plan[2 * size_t(tmp[i].second)]; p2[2 * i + 1] = plan[2 * size_t(tmp[i].second) + 1];
+                    if (withPlan) { p2[2 * i] = plan[2 * size_t(tmp[i].second)]; p2[2 * i + 1] = plan[2 * size_t(tmp[i].second) + 1]; }
                 }
                 for (size_t i = 0; i < tmp.size(); ++i)
                 {
                     ent[b0 + i] = e2[i];
-                    plan[2 * (size_t(b0) + i)] = p2[2 * i]; plan[2 * (size_t(b0) + i) + 1] = p2[2 * i + 1];
+                    if (withPlan) { plan[2 * (size_t(b0) + i)] = p2[2 * i]; plan[2 * (size_t(b0) + i) + 1] = p2[2 * i + 1]; }
                 }
             }
         }
@@ -106,21 +149,38 @@ int32_t log2_exact(int32_t v)
 // Purely a tiling hint: any partition of the cells gives a correct plan.
 bool detect_dims(int32_t nOwned, int32_t nI, const int32_t* own, const int32_t* nei, int32_t dims[3])
 {
-    std::map<int32_t, int64_t> diffs;
-    int32_t last = 0;
-    for (int32_t f = 0; f < nI; ++f)
+    // at most three distinct owner->neighbour strides (kept in a 3-entry table: this loop visits every face)
+    int32_t known[3] = {0, 0, 0};
+    int nKnown = 0;
+    int tooMany = 0, nonPositive = 0;
+#pragma omp parallel
     {
-        if (own[f] >= nOwned || nei[f] >= nOwned) continue;
-        const int32_t dlt = nei[f] - own[f];
-        if (dlt == last) continue;
-        if (dlt <= 0) return false;
-        last = dlt;
-        if (diffs.find(dlt) == diffs.end())
+        int32_t mine[3] = {0, 0, 0};
+        int nMine = 0, bad = 0, neg = 0;
+#pragma omp for schedule(static) nowait
+        for (int32_t f = 0; f < nI; ++f)
         {
-            if (diffs.size() == 3) return false;
-            diffs[dlt] = 1;
+            if (own[f] >= nOwned || nei[f] >= nOwned) continue;
+            const int32_t dlt = nei[f] - own[f];
+            if (dlt <= 0) { neg = 1; continue; }
+            if ((nMine > 0 && dlt == mine[0]) || (nMine > 1 && dlt == mine[1]) || (nMine > 2 && dlt == mine[2])) continue;
+            if (nMine == 3) { bad = 1; continue; }
+            mine[nMine++] = dlt;
+        }
+#pragma omp critical
+        {
+            tooMany |= bad; nonPositive |= neg;
+            for (int q = 0; q < nMine; ++q)
+            {
+                bool have = false;
+                for (int r = 0; r < nKnown; ++r) have = have || known[r] == mine[q];
+                if (!have) { if (nKnown == 3) tooMany = 1; else known[nKnown++] = mine[q]; }
+            }
         }
     }
+    if (tooMany || nonPositive) return false;
+    std::map<int32_t, int64_t> diffs;
+    for (int r = 0; r < nKnown; ++r) diffs[known[r]] = 1;
     if (diffs.empty()) { dims[0] = nOwned; dims[1] = dims[2] = 1; return true; }
     std::vector<int32_t> s;
     for (auto& kv : diffs) s.push_back(kv.first);

@@ -12,9 +12,9 @@ struct FvkStencilHost
     std::vector<int32_t> seg;  // [nC+1]
     std::vector<int32_t> val;  // ascending local face id per cell (the reference's stencil values)
     std::vector<int32_t> ent;  // (face << 1) | (cell is the face's neighbour), accumulation order
-    std::vector<int32_t> plan; // 2 per entry: {ent, other cell}; boundary face b: {-(b + 1), own cell}
+    std::vector<int32_t> plan; // 2 per entry: {ent, other cell}; boundary face b: {-(b + 1), own cell} (only withPlan)
 };
-void fvk_build_stencil(const fvk_mesh_desc* d, FvkStencilHost& st);
+void fvk_build_stencil(const fvk_mesh_desc* d, FvkStencilHost& st, bool withPlan = false);
 
 struct FvkBrickPlanHost
 {

@@ -20,6 +20,7 @@
 #include <cstring>
 #include <map>
 #include <numeric>
+#include <parallel/algorithm>
 #include <vector>
 
 struct fvk_decomp
@@ -51,12 +52,17 @@ extern "C" int fvk_decomp_simple_map(const fvk_mesh_desc* g, int px, int py, int
         const double* C = g->cellCentres;
         // quantise to suppress last-bit noise in equal coordinates, ties broken by cell id (stable)
         double lo = C[axis], hi = C[axis];
+#pragma omp parallel for schedule(static) reduction(min : lo) reduction(max : hi)
         for (int32_t c = 0; c < nC; ++c) { lo = std::min(lo, C[3 * size_t(c) + axis]); hi = std::max(hi, C[3 * size_t(c) + axis]); }
         // integer keys: a tolerance comparison (xa < xb - eps) is not a strict weak ordering
         const double eps = (hi - lo) * 1e-9 + 1e-300;
+#pragma omp parallel for schedule(static)
         for (int32_t c = 0; c < nC; ++c) key[c] = std::llround((C[3 * size_t(c) + axis] - lo) / eps);
-        std::stable_sort(idx.begin(), idx.end(), [&](int32_t a, int32_t b) { return key[a] < key[b]; });
+        // (multi-threaded merge sort; stable, so the result is the serial std::stable_sort's)
+        __gnu_parallel::stable_sort(idx.begin(), idx.end(), [&](int32_t a, int32_t b) { return key[a] < key[b]; });
+#pragma omp parallel for schedule(static)
         for (int32_t k = 0; k < nC; ++k) grp[idx[k]] = int32_t((int64_t(k) * p[axis]) / nC);
+#pragma omp parallel for schedule(static)
         for (int32_t c = 0; c < nC; ++c) cellRank[c] += stride * grp[c];
         stride *= p[axis];
     }

@@ -351,7 +351,7 @@ extern "C" int fvk_mesh_create(const fvk_mesh_desc* d, fvk_mesh** out)
     const int32_t* own = d->faceOwner;
     const int32_t* nei = d->faceNeighbour;
     FvkStencilHost sth;
-    fvk_build_stencil(d, sth);
+    fvk_build_stencil(d, sth, experiment_plans());
     tm.lap("cell->face stencil");
     {
         std::vector<int32_t>&seg = sth.seg, &val = sth.val, &ent = sth.ent, &plan = sth.plan;

@@ -3,6 +3,12 @@
 decomposed over the ranks. Run plain (1 GPU) or under torchrun:
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29520 tools/piso_scaling.py --size 256
 Prints one JSON line on rank 0: ms per step (max over ranks, CUDA events), CG iterations, transport."""
+import os as _os
+if "LOCAL_WORLD_SIZE" in _os.environ and _os.environ.get("OMP_NUM_THREADS") == "1":
+    # torchrun pins every rank to ONE OpenMP thread unless told otherwise; the once-per-mesh host setup (block generator, stencil,
+    # plans, decomposition) is multi-threaded: give each rank its share of the host cores
+    _os.environ["OMP_NUM_THREADS"] = str(max(1, (_os.cpu_count() or 1) // int(_os.environ["LOCAL_WORLD_SIZE"])))
+
 import argparse
 import json
 import os
