@@ -493,6 +493,8 @@ def run_native(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    from foamadapter_b200.decomp import bind_host_to_device
+    host_cpus = bind_host_to_device(local_rank)  # NUMA-local pinned buffers for the e2e leg
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from foamadapter_b200 import fvcc, ops
@@ -790,7 +792,8 @@ def run_native(args, rank, world, local_rank):
                          "frac": kernels[dom]["frac"], "traffic": None, "peak_kind": peak_kind,
                          "traffic_note": "not measured in this run; ncu dram bytes per launch are committed in profiles/traffic.json and profiles/r2*_ncu_*.csv"},
             "kernels": kernels,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "mode": e2e_mode},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "mode": e2e_mode,
+                    "host_cpus": (f"{host_cpus[0]}-{host_cpus[-1]} ({len(host_cpus)} CPUs local to the GPU, NVML)" if host_cpus else "not bound")},
             "gpu_launches": timed_launches,
             "clocks": clocks,
         }

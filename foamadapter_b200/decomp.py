@@ -185,3 +185,31 @@ class Comm:
         if self._h is not None:
             lib().fvk_comm_destroy(self._h)
             self._h = None
+
+
+def bind_host_to_device(device_index: int):
+    """Pin this process to the CPUs NVML reports as local to CUDA device `device_index` (its PCIe root / NUMA node), so that the
+    pinned host buffers allocated afterwards are first-touched on that node and host<->device copies do not cross the socket
+    interconnect. One process per GPU: call it right after choosing the device. Returns the CPU set used, or None when NVML is
+    unavailable, reports nothing, or the set does not intersect the CPUs this process may use (containers): nothing changes then."""
+    import os
+
+    import torch
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(device_index)
+        bus = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        n = (os.cpu_count() or 1024) // 64 + 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, n)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if not use or use == allowed:
+            return None if not use else sorted(use)
+        os.sched_setaffinity(0, use)
+        return sorted(use)
+    except Exception:
+        return None
+
