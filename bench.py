@@ -19,13 +19,14 @@ The same line carries, at EVERY N, the measurements the other BASELINE configs a
                 in the cpu_baseline leg) or with a single-domain GPU run of the same global mesh (N > 1); PISO / advection
                 fields of the decomposed run compared with a single-domain run
 """
+
+from __future__ import annotations
+
 import os as _os
 if "LOCAL_WORLD_SIZE" in _os.environ and _os.environ.get("OMP_NUM_THREADS") == "1":
     # torchrun pins every rank to ONE OpenMP thread unless told otherwise; the once-per-mesh host setup (block generator, stencil,
     # plans, decomposition) is multi-threaded: give each rank its share of the host cores
     _os.environ["OMP_NUM_THREADS"] = str(max(1, (_os.cpu_count() or 1) // int(_os.environ["LOCAL_WORLD_SIZE"])))
-
-from __future__ import annotations
 
 import argparse
 import ctypes as C

@@ -9,6 +9,7 @@ if "LOCAL_WORLD_SIZE" in _os.environ and _os.environ.get("OMP_NUM_THREADS") == "
     # plans, decomposition) is multi-threaded: give each rank its share of the host cores
     _os.environ["OMP_NUM_THREADS"] = str(max(1, (_os.cpu_count() or 1) // int(_os.environ["LOCAL_WORLD_SIZE"])))
 
+
 import argparse
 import json
 import os
