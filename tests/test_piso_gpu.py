@@ -138,6 +138,12 @@ def test_whole_step_graph_with_captured_solves_equals_eager_steps():
         if step >= 2:
             assert abs(sa[0].finalResNorm - sb[0].finalResNorm) <= 1e-15 + 1e-12 * sb[0].finalResNorm
     assert a._whole is not None and a._captured is None
+    # the solver's device-side log holds the iteration counts of the replayed solves in execution order (read without having
+    # synchronised after every step); the first two steps run eagerly and are not in it
+    log = a.solver.captured_log()
+    flat = [n for i in iters[2:] for n in i]
+    assert log == flat, (log, flat)
+    assert a.solver.captured_log() == []   # reading resets it
     assert len({tuple(i) for i in iters[2:]}) > 1 and max(max(i) for i in iters[2:]) >= 3   # the loop really iterates, differently per step
 
 
