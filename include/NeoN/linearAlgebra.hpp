@@ -165,6 +165,7 @@ public:
             if (h_) fvk_solver_destroy(h_);
             h_ = nullptr;
             check(fvk_solver_create(m.nOwnedCells(), m.nCells(), &cfg_, comm_, &h_));
+            if (ghostsCurrent_) check(fvk_solver_set_ghosts_current(h_, 1));
             rows_ = m.nOwnedCells(); cols_ = m.nCells();
         }
         // structured SpMV inside the solver when the mesh plan proved a block topology; re-attached on every solve (host-only,
@@ -187,6 +188,7 @@ public:
             if (h_) fvk_solver_destroy(h_);
             h_ = nullptr;
             check(fvk_solver_create(m.nOwnedCells(), m.nCells(), &cfg_, comm_, &h_));
+            if (ghostsCurrent_) check(fvk_solver_set_ghosts_current(h_, 1));
             rows_ = m.nOwnedCells(); cols_ = m.nCells();
         }
         check(fvk_solver_attach_mesh(h_, m.handle()));
@@ -197,10 +199,35 @@ public:
         return {SolverStats {st[0].numIter, st[0].initResNorm, st[0].finalResNorm, {}}, SolverStats {st[1].numIter, st[1].initResNorm, st[1].finalResNorm, {}},
                 SolverStats {st[2].numIter, st[2].initResNorm, st[2].finalResNorm, {}}};
     }
+    // ---- distributed solves: ghost entries of the unknown (fvk.h "Ghost entries around a distributed solve") -----------------
+    // the initial guesses passed from now on already have current ghost entries (skip the start-up exchange)
+    void setGhostsCurrent(bool on) const
+    {
+        ghostsCurrent_ = on;
+        if (h_) check(fvk_solver_set_ghosts_current(h_, on ? 1 : 0));
+    }
+    // does the solution come back with current ghost entries (no exchange of x needed after solve)?
+    bool keepsGhosts() const
+    {
+        if (!h_) return comm_ == nullptr || (cfg_.solverType == FVK_SOLVER_CG && fvk_comm_p2p_enabled(comm_) == 1);
+        int32_t yes = 0;
+        check(fvk_solver_keeps_ghosts(h_, &yes));
+        return yes != 0;
+    }
+    // iteration counts of the solves that ran inside replayed CUDA graphs since the last call (device-side log)
+    std::vector<int32_t> capturedLog() const
+    {
+        std::vector<int32_t> out(8192);
+        int32_t n = 0;
+        if (h_) check(fvk_solver_captured_log(h_, out.data(), int32_t(out.size()), &n));
+        out.resize(size_t(n));
+        return out;
+    }
 private:
     Executor exec_;
     fvk_comm* comm_;
     bool history_;
+    mutable bool ghostsCurrent_ = false;
     fvk_solver_config cfg_ {};
     mutable fvk_solver* h_ = nullptr;
     mutable localIdx rows_ = 0, cols_ = 0;
