@@ -1293,62 +1293,9 @@ __device__ __forceinline__ double conum_cell_generic(const CoNumOp& op, int c, c
     for (int e = e0 + 8; e < e1; ++e) acc += op.at(ent[e] >> 1);
     return acc;
 }
-__global__ void __launch_bounds__(256)
-k_conum_stage1(CoNumOp op, int nC, const int* __restrict__ seg, const int* __restrict__ ent,
-               const double* __restrict__ V, double* __restrict__ partial /* [3*gridDim.x] */, CoNumAffine aff)
+__device__ __forceinline__ void conum_block_partials(double lmax, double lphi, double lvol, double* __restrict__ partial)
 {
     __shared__ double sMax[8], sPhi[8], sVol[8];
-    double lmax = -1.7976931348623157e308, lphi = 0.0, lvol = 0.0;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nC; c += gridDim.x * blockDim.x)
-    {
-        double acc = 0.0;
-        if (aff.on)
-        {
-            const int i = c % aff.nx, q = c / aff.nx, j = q % aff.ny, k = q / aff.ny;
-            // an irregular cell costs three dependent round trips and would hold up its warp in EVERY pass of this loop (the
-            // grid stride is a multiple of nx: the same lanes meet the block's outer layer each time): they come from the
-            // plan's list below, spread over all threads
-            if (!(i > 0 && i < aff.nx - 1 && j > 0 && j < aff.ny - 1 && k > 0 && k < aff.nz - 1)) continue;
-            const int64_t nxy = int64_t(aff.nx) * aff.ny;
-            const int64_t fs = 3 * int64_t(c) - int64_t(aff.tx) * (j + int64_t(aff.ny) * k) - int64_t(aff.ty) * k * aff.nx;
-            const int64_t f[6] = {fs - 3 * nxy + int64_t(aff.tx) * aff.ny + int64_t(aff.ty) * aff.nx + 2, fs - 3 * int64_t(aff.nx) + aff.tx + 1, fs - 3,
-                                  fs, fs + 1, fs + 2};
-            // all six loads first (a branch on a loaded value between them would serialise six DRAM round trips), then one
-            // test for the exact-|F| range; the sqrt(F * F) form only runs for a cell that has a face outside it
-            double F[6];
-#pragma unroll
-            for (int e = 0; e < 6; ++e) F[e] = op.faceFlux[f[e]];
-            bool exact = true;
-#pragma unroll
-            for (int e = 0; e < 6; ++e) exact = exact && CoNumOp::abs_is_exact(F[e]);
-            if (exact)
-            {
-#pragma unroll
-                for (int e = 0; e < 6; ++e) acc += fabs(F[e]);
-            }
-            else
-            {
-#pragma unroll 1
-                for (int e = 0; e < 6; ++e) acc += CoNumOp::mag(F[e]);
-            }
-        }
-        else
-            acc = conum_cell_generic(op, c, seg, ent);
-        const double v = V[c];
-        lmax = fmax(lmax, acc / v);
-        lphi += acc;
-        lvol += v;
-    }
-    if (aff.on)
-        for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < aff.nIrr; idx += gridDim.x * blockDim.x)
-        {
-            const int c = aff.irrCells[idx];
-            const double acc = conum_cell_generic(op, c, seg, ent);
-            const double v = V[c];
-            lmax = fmax(lmax, acc / v);
-            lphi += acc;
-            lvol += v;
-        }
     lmax = warp_max(lmax); lphi = warp_sum(lphi); lvol = warp_sum(lvol);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (lane == 0) { sMax[wid] = lmax; sPhi[wid] = lphi; sVol[wid] = lvol; }
@@ -1358,6 +1305,85 @@ k_conum_stage1(CoNumOp op, int nC, const int* __restrict__ seg, const int* __res
         for (int i = 1; i < 8; ++i) { lmax = fmax(lmax, sMax[i]); lphi += sPhi[i]; lvol += sVol[i]; }
         partial[3 * blockIdx.x] = lmax; partial[3 * blockIdx.x + 1] = lphi; partial[3 * blockIdx.x + 2] = lvol;
     }
+}
+// stage 1a, block topology proven: the REGULAR cells, index-free, two cells per pass of the grid-stride loop (fourteen
+// independent loads in flight per thread). The irregular cells are skipped here: they cost three dependent round trips and would
+// hold up their warp in EVERY pass (the grid stride is a multiple of nx: the same lanes meet the block's outer layer each time).
+__global__ void __launch_bounds__(256, 4)
+k_conum_regular(CoNumOp op, int nC, const double* __restrict__ V, double* __restrict__ partial, CoNumAffine aff)
+{
+    double lmax = -1.7976931348623157e308, lphi = 0.0, lvol = 0.0;
+    const int stride = gridDim.x * blockDim.x;
+    const int64_t nxy = int64_t(aff.nx) * aff.ny;
+    for (int c0 = blockIdx.x * blockDim.x + threadIdx.x; c0 < nC; c0 += 2 * stride)
+    {
+        double F[2][6], v[2];
+        bool reg[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+        {
+            const int c = c0 + u * stride;
+            reg[u] = false;
+            v[u] = 1.0;
+            if (c < nC)
+            {
+                const int i = c % aff.nx, q = c / aff.nx, j = q % aff.ny, k = q / aff.ny;
+                reg[u] = i > 0 && i < aff.nx - 1 && j > 0 && j < aff.ny - 1 && k > 0 && k < aff.nz - 1;
+                if (reg[u])
+                {
+                    const int64_t fs = 3 * int64_t(c) - int64_t(aff.tx) * (j + int64_t(aff.ny) * k) - int64_t(aff.ty) * k * aff.nx;
+                    const int64_t f[6] = {fs - 3 * nxy + int64_t(aff.tx) * aff.ny + int64_t(aff.ty) * aff.nx + 2, fs - 3 * int64_t(aff.nx) + aff.tx + 1,
+                                          fs - 3, fs, fs + 1, fs + 2};
+                    // all loads first (a branch on a loaded value between them would serialise the DRAM round trips)
+#pragma unroll
+                    for (int e = 0; e < 6; ++e) F[u][e] = op.faceFlux[f[e]];
+                    v[u] = V[c];
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+        {
+            if (!reg[u]) continue;
+            // one test for the exact-|F| range; the sqrt(F * F) form only runs for a cell that has a face outside it
+            bool exact = true;
+#pragma unroll
+            for (int e = 0; e < 6; ++e) exact = exact && CoNumOp::abs_is_exact(F[u][e]);
+            double acc = 0.0;
+            if (exact)
+            {
+#pragma unroll
+                for (int e = 0; e < 6; ++e) acc += fabs(F[u][e]);
+            }
+            else
+            {
+#pragma unroll
+                for (int e = 0; e < 6; ++e) acc += CoNumOp::mag(F[u][e]); // (unrolled: a runtime index would put F in local memory)
+            }
+            lmax = fmax(lmax, acc / v[u]);
+            lphi += acc;
+            lvol += v[u];
+        }
+    }
+    conum_block_partials(lmax, lphi, lvol, partial);
+}
+// stage 1b: cells through their stencil -- the plan's irregular-cell list (spread over all threads) next to k_conum_regular, or
+// every cell of a mesh without the affine proof (list == nullptr)
+__global__ void __launch_bounds__(256)
+k_conum_list(CoNumOp op, int n, const int* __restrict__ list, const int* __restrict__ seg, const int* __restrict__ ent,
+             const double* __restrict__ V, double* __restrict__ partial)
+{
+    double lmax = -1.7976931348623157e308, lphi = 0.0, lvol = 0.0;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x)
+    {
+        const int c = list ? list[idx] : idx;
+        const double acc = conum_cell_generic(op, c, seg, ent);
+        const double v = V[c];
+        lmax = fmax(lmax, acc / v);
+        lphi += acc;
+        lvol += v;
+    }
+    conum_block_partials(lmax, lphi, lvol, partial);
 }
 
 __global__ void __launch_bounds__(256)
@@ -1583,28 +1609,48 @@ extern "C" int fvk_face_normal_grad_v(const fvk_mesh* m, const double* phi, cons
     return sngrad_impl<S3>(m, phi, phiB, outFace, s);
 }
 
-static int conum_grid(const fvk_mesh* m)
+static int conum_grid(int n, int perSm)
 {
-    const int want = (m->nOwned + 255) / 256;
-    const int cap = fvk_sm_count() * 8;
+    const int want = (n + 255) / 256;
+    const int cap = fvk_sm_count() * perSm;
     return want < cap ? (want > 0 ? want : 1) : cap;
 }
 extern "C" size_t fvk_conum_scratch_bytes(const fvk_mesh* m)
 {
     if (!m) return 0;
-    return sizeof(double) * 3 * size_t(148 * 8 > conum_grid(m) ? 148 * 8 : conum_grid(m));
+    return sizeof(double) * 3 * size_t(148 * 16 > 2 * conum_grid(m->nOwned, 8) ? 148 * 16 : 2 * conum_grid(m->nOwned, 8));
 }
 extern "C" int fvk_conum(const fvk_mesh* m, const double* faceFlux, double dt, double* result_d, void* scratch_d, fvk_stream s)
 {
     if (!m || !faceFlux || !result_d || !scratch_d) return fvk_fail(FVK_EINVAL, "fvk_conum: null argument");
-    const int grid = conum_grid(m);
     double* partial = static_cast<double*>(scratch_d);
     const FvkBrickGeom& bg = m->bp.geom;
     const bool affine = !fvk_no_affine() && m->bp.nTiles > 0 && bg.affine && int64_t(bg.dims[0]) * bg.dims[1] * bg.dims[2] == m->nOwned;
-    const CoNumAffine ca {affine ? 1 : 0, bg.dims[0], bg.dims[1], bg.dims[2], bg.tUp[0], bg.tUp[1], m->bp.nIrr, m->bp.irrCells};
-    k_conum_stage1<<<grid, 256, 0, fvk_cu(s)>>>(CoNumOp {faceFlux}, m->nOwned, m->stencilSeg, m->gatherEnt, m->V, partial, ca);
-    FVK_LAUNCH_CHECK();
-    k_conum_stage2<<<1, 256, 0, fvk_cu(s)>>>(grid, partial, dt, result_d);
+    const CoNumOp op {faceFlux};
+    int nPartial = 0;
+    if (affine)
+    {
+        const CoNumAffine ca {1, bg.dims[0], bg.dims[1], bg.dims[2], bg.tUp[0], bg.tUp[1], m->bp.nIrr, m->bp.irrCells};
+        const int gA = conum_grid((m->nOwned + 1) / 2, 4); // two cells per thread and pass, 4 resident blocks per SM
+        k_conum_regular<<<gA, 256, 0, fvk_cu(s)>>>(op, m->nOwned, m->V, partial, ca);
+        FVK_LAUNCH_CHECK();
+        nPartial = gA;
+        if (m->bp.nIrr > 0)
+        {
+            const int gB = conum_grid(m->bp.nIrr, 4);
+            k_conum_list<<<gB, 256, 0, fvk_cu(s)>>>(op, m->bp.nIrr, m->bp.irrCells, m->stencilSeg, m->gatherEnt, m->V, partial + 3 * size_t(gA));
+            FVK_LAUNCH_CHECK();
+            nPartial += gB;
+        }
+    }
+    else
+    {
+        const int g = conum_grid(m->nOwned, 8);
+        k_conum_list<<<g, 256, 0, fvk_cu(s)>>>(op, m->nOwned, nullptr, m->stencilSeg, m->gatherEnt, m->V, partial);
+        FVK_LAUNCH_CHECK();
+        nPartial = g;
+    }
+    k_conum_stage2<<<1, 256, 0, fvk_cu(s)>>>(nPartial, partial, dt, result_d);
     FVK_LAUNCH_CHECK();
     return FVK_OK;
 }

@@ -13,10 +13,13 @@ for r in csv.reader(open(sys.argv[1], errors="ignore")):
         continue
     if hdr and len(r) == len(hdr):
         rows.append(dict(zip(hdr, r)))
-marker = sys.argv[2] if len(sys.argv) > 2 else "k_conum_stage1"
+marker = sys.argv[2] if len(sys.argv) > 2 else "k_conum_regular"
 names = [re.sub(r"^void ", "", re.sub(r"\(.*", "", r["Kernel Name"])).replace("<unnamed>::", "") for r in rows]
 dur = [float(r["Metric Value"].replace(",", "")) / 1e3 for r in rows]
 starts = [i for i, n in enumerate(names) if marker in n]
+if len(starts) < 2 and len(sys.argv) <= 2:  # lists captured before CoNum was split into two kernels
+    marker = "k_conum_stage1"
+    starts = [i for i, n in enumerate(names) if marker in n]
 if len(starts) >= 2:
     a, b = starts[-2], starts[-1]
 else:

@@ -15,7 +15,7 @@ PEAK = 6541.8  # MEASURED_PEAKS.json hbm_gbs
 def alg_bytes(nC, nI, nB):
     nF, nnz = nI + nB, nC + 2 * nI
     return OrderedDict([
-        ("k_conum_stage1", ("CoNum: |phi| over the faces of every cell, V", 8 * nF + 8 * nC)),
+        ("k_conum_regular|k_conum_list|k_conum_stage1", ("CoNum: |phi| over the faces of every cell, V", 8 * nF + 8 * nC)),
         ("k_assemble_affine<S3|k_assemble_fast<S3", ("UEqn = ddt + div(phi) - laplacian(nu), compact Vec3 matrix (values once, rhs Vec3)",
                                                       50 * nI + (4 + 1 + 8 + 24 + 24 + 7 * 8) * nC + 52 * nB)),
         ("k_rAU_HbyA_rows", ("rAU = 1/diag, HbyA = rAU (b - H(U)): matrix values + columns, rhs, U, V in; rAU, HbyA out", 12 * nnz + 88 * nC)),
@@ -43,7 +43,7 @@ def main():
             rows.append(dict(zip(hdr, r)))
     names = [re.sub(r"^void ", "", re.sub(r"\(.*", "", r["Kernel Name"])).replace("<unnamed>::", "") for r in rows]
     dur = [float(r["Metric Value"].replace(",", "")) / 1e3 for r in rows]
-    starts = [i for i, n in enumerate(names) if "k_conum_stage1" in n]
+    starts = [i for i, n in enumerate(names) if "k_conum_regular" in n] or [i for i, n in enumerate(names) if "k_conum_stage1" in n]
     a, b = starts[-2], starts[-1]
     step = list(zip(names[a:b], dur[a:b]))
     total = sum(d for _, d in step)
