@@ -111,7 +111,10 @@ def conum(mesh, faceFlux, dt, result=None, scratch=None):
     if scratch is None:
         scratch = torch.empty(lib().fvk_conum_scratch_bytes(mesh.handle) // 8, dtype=torch.float64, device=faceFlux.device)
     check(lib().fvk_conum(mesh.handle, ptr(faceFlux), C.c_double(dt), ptr(result), ptr(scratch), _stream()))
-    _count(2)
+    if getattr(mesh, "_conum_launches", None) is None:  # block topology proven: regular-cell kernel + irregular-cell list + fold
+        from . import mesh as _m
+        mesh._conum_launches = 3 if mesh.size(_m.AFFINE_TOPOLOGY) else 2
+    _count(mesh._conum_launches)
     return result
 
 
