@@ -57,7 +57,7 @@ def init_fields_columns(C: np.ndarray, nxy: int):
 
 class ScalarAdvection:
     def __init__(self, mesh: UnstructuredMesh, dt, endTime, fvSchemes=None, fvSolution=None, comm=None, U=None, T=None,
-                 adjustTimeStep=False, maxCo=0.1, maxDeltaT=1.0, check_every=8):
+                 adjustTimeStep=False, maxCo=0.1, maxDeltaT=1.0, check_every=8, fuse_euler=True):
         self.mesh, self.dt, self.endTime, self.t = mesh, float(dt), float(endTime), 0.0
         self.fvSchemes = fvSchemes or ADVECTION_FVSCHEMES
         self.fvSolution = fvSolution or ADVECTION_FVSOLUTION
@@ -85,6 +85,10 @@ class ScalarAdvection:
         self.eqn = dsl.imp.ddt(self.T) + make(self.phi, self.T)
         self.eqn.read(self.fvSchemes)
         self.stats = None
+        # forwardEuler of `ddt(T) + div(phi, T)`: the old-time copy made at the top of the step IS the operand, so the div kernel can
+        # write T = old - dt * div itself (fvk_div_forward_euler_s; no source vector, no separate update pass). fuse_euler=False keeps
+        # the generic dsl::solve sequence -- same bits (tests/test_advection_gpu.py).
+        self.fuse_euler = fuse_euler and self.fvSchemes["ddtSchemes"]["type"] == "forwardEuler"
 
     def step(self):
         t, dt = self.t, self.dt
@@ -99,7 +103,15 @@ class ScalarAdvection:
             co = float(self._max_conum())
             fact = self.maxCo / (co + 1e-15)
             self.dt = min(min(min(fact, 1.0 + 0.1 * fact), 1.2) * dt, self.maxDeltaT)
-        self.stats = dsl.solve(self.eqn, self.T, t, dt, self.fvSchemes, self.fvSolution, comm=self.comm, check_every=self.check_every)
+        if self.fuse_euler:
+            if self.comm is not None:
+                self.comm.halo_exchange(old.internal)   # the operand's ghosts (dsl::solve would exchange T's)
+            o = self.eqn.spatial[0]
+            ops.div_forward_euler(self.mesh, self.phi.internal, old.internal, self.T.boundary.value, dt, self.T.internal, o.scheme or 0, o.coeff.value, o.coeff.view)
+            self.T.correctBoundaryConditions()
+            self.stats = None
+        else:
+            self.stats = dsl.solve(self.eqn, self.T, t, dt, self.fvSchemes, self.fvSolution, comm=self.comm, check_every=self.check_every)
         self.t = t + dt
         return self.stats
 

@@ -241,7 +241,7 @@ struct SurfIntOp // surfaceIntegrate.cpp:26-41
 // trip through memory. FVK_EPI_UPDATE_VELOCITY (grad): out = epiA - (s * sum) * epiB   = updateVelocity's U = HbyA - rAU gradP
 // (pressureVelocityCoupling.cpp:199-213); FVK_EPI_RHS_SUB (surfaceIntegrate / div / laplacian): out -= (0 + s * sum) * V, i.e.
 // Operator::explicitOperation into a zeroed source followed by dsl::solve's rhs -= source * V (dsl/solver.hpp:73-77).
-enum { FVK_EPI_UPDATE_VELOCITY = 16, FVK_EPI_RHS_SUB = 17 };
+enum { FVK_EPI_UPDATE_VELOCITY = 16, FVK_EPI_RHS_SUB = 17, FVK_EPI_AXPY = 18 /* out = epiScale * (s * sum) + epiA: forwardEuler */ };
 struct Scaling
 {
     const double* __restrict__ V;    // cell volumes
@@ -250,6 +250,7 @@ struct Scaling
     bool invVolOnly; // grad: res *= 1 / V
     const double* epiA = nullptr;    // FVK_EPI_UPDATE_VELOCITY: HbyA (Vec3)
     const double* epiB = nullptr;    // FVK_EPI_UPDATE_VELOCITY: rAU
+    double epiScale = 0.0;           // FVK_EPI_AXPY: -dt (epiA = the old-time field)
     __device__ __forceinline__ double at(int c) const
     {
         if (invVolOnly) return 1 / V[c];
@@ -267,6 +268,8 @@ __device__ __forceinline__ void finish(double* __restrict__ out, int c, typename
         VT::st(out, c, VT::sub(VT::ld(sc.epiA, c), VT::mul(sc.epiB[c], VT::mul(s, acc))));
     else if (mode == FVK_EPI_RHS_SUB)
         VT::st(out, c, VT::sub(VT::ld(out, c), VT::mul(sc.V[c], VT::add(VT::zero(), VT::mul(s, acc)))));
+    else if (mode == FVK_EPI_AXPY) // a * source + 1 * old, the products and the sum of fvk_vec_waxpby(-dt, source, 1, old)
+        VT::st(out, c, VT::add(VT::mul(sc.epiScale, VT::mul(s, acc)), VT::ld(sc.epiA, c)));
     else
         VT::st(out, c, VT::mul(s, acc));
 }
@@ -1143,7 +1146,7 @@ __host__ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr
 template <class Op>
 int launch_gather(const fvk_mesh* m, Op op, Scaling sc, double* out, int mode, fvk_stream stream)
 {
-    if (mode != FVK_SET && mode != FVK_ACC_SCALE && mode != FVK_ADD && mode != FVK_EPI_UPDATE_VELOCITY && mode != FVK_EPI_RHS_SUB)
+    if (mode != FVK_SET && mode != FVK_ACC_SCALE && mode != FVK_ADD && mode != FVK_EPI_UPDATE_VELOCITY && mode != FVK_EPI_RHS_SUB && mode != FVK_EPI_AXPY)
         return fvk_fail(FVK_EINVAL, "bad mode %d", mode);
     const int nC = m->nOwned;
     const int nI = m->nInternalFaces;
@@ -1475,6 +1478,20 @@ extern "C" int fvk_div_v(const fvk_mesh* m, int scheme, const double* faceFlux, 
                          const double* phiB, double coeff, const double* view, double* out, int mode, fvk_stream s)
 {
     return div_impl<S3>(m, scheme, faceFlux, phi, phiB, coeff, view, out, mode, s);
+}
+
+// forwardEuler (timeIntegration/forwardEuler.hpp:38-56) of `ddt(phi) + div(faceFlux, phi) = 0` in ONE pass: out = phiOld - dt * div, the
+// source vector never goes to memory. phiOld must not alias out (neighbours' old values are read while out is written).
+extern "C" int fvk_div_forward_euler_s(const fvk_mesh* m, int scheme, const double* faceFlux, const double* phiOld, const double* phiB,
+                                       double coeff, const double* view, double dt, double* out, fvk_stream s)
+{
+    if (!m || !faceFlux || !phiOld || !out || (m->nBoundaryFaces && !phiB)) return fvk_fail(FVK_EINVAL, "fvk_div_forward_euler_s: null argument");
+    if (phiOld == out) return fvk_fail(FVK_EINVAL, "fvk_div_forward_euler_s: phiOld and out must be different arrays");
+    Scaling sc {m->V, view, coeff, false};
+    sc.epiA = phiOld; sc.epiScale = -dt;
+    if (scheme == FVK_LINEAR) return launch_gather(m, DivOp<S1, FVK_LINEAR> {faceFlux, m->weights, phiOld, phiB}, sc, out, FVK_EPI_AXPY, s);
+    if (scheme == FVK_UPWIND) return launch_gather(m, DivOp<S1, FVK_UPWIND> {faceFlux, m->weights, phiOld, phiB}, sc, out, FVK_EPI_AXPY, s);
+    return fvk_fail(FVK_EINVAL, "fvk_div_forward_euler_s: unknown scheme %d", scheme);
 }
 
 // updateVelocity (pressureVelocityCoupling.cpp:199-213) fused with the gradient it consumes: U = HbyA - rAU * grad(p), no gradP

@@ -48,6 +48,16 @@ def div(mesh: UnstructuredMesh, faceFlux, phi, phiB, out, scheme=LINEAR, coeff=1
     return out
 
 
+def div_forward_euler(mesh: UnstructuredMesh, faceFlux, phiOld, phiB, dt, out, scheme=LINEAR, coeff=1.0, coeffView=None):
+    """fvk_div_forward_euler_s: out = phiOld - dt * div(faceFlux, phiOld) in one pass (forwardEuler of ddt + div, scalar)"""
+    _chk(faceFlux, mesh.nFaces, "faceFlux", 1); _chk(phiOld, mesh.nCells, "phiOld", 1)
+    _chk(phiB, mesh.nBoundaryFaces, "phiB", 1); _chk(out, mesh.nCells, "out", 1); _chk(coeffView, mesh.nCells, "coeffView", 1)
+    check(lib().fvk_div_forward_euler_s(mesh.handle, C.c_int(scheme), ptr(faceFlux), ptr(phiOld), ptr(phiB), C.c_double(coeff), ptr(coeffView),
+                                        C.c_double(dt), ptr(out), _stream()))
+    _count()
+    return out
+
+
 def grad(mesh, phi, phiB, out, mode=SET):
     _chk(phi, mesh.nCells, "phi", 1); _chk(phiB, mesh.nBoundaryFaces, "phiB", 1); _chk(out, mesh.nCells, "out", 3)
     check(lib().fvk_grad_s(mesh.handle, ptr(phi), ptr(phiB), ptr(out), C.c_int(mode), _stream()))

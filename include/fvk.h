@@ -516,6 +516,12 @@ int fvk_update_velocity(const fvk_mesh* mesh, const double* HbyA, const double* 
  * arithmetic, bit for bit, as fvk_grad_s (FVK_SET) followed by fvk_update_velocity */
 int fvk_update_velocity_grad(const fvk_mesh* mesh, const double* HbyA, const double* rAU, const double* p, const double* pB,
                              double* U, fvk_stream stream);
+/* forwardEuler (timeIntegration/forwardEuler.hpp:38-56: solution = old - source * dt) of `ddt(phi) + div(faceFlux, phi)` with the div
+ * as its only spatial operator (examples/scalarAdvection/scalarAdvection.cpp:77-83) in ONE pass: out = phiOld - dt * (coeff / V) *
+ * sum_f flux_f phi_f, bit for bit fvk_div_s (FVK_SET) into a source followed by fvk_vec_waxpby(-dt, source, 1, phiOld, out), without
+ * the source vector. phiOld (owned + ghost entries) and out must be different arrays. */
+int fvk_div_forward_euler_s(const fvk_mesh* mesh, int scheme, const double* faceFlux, const double* phiOld, const double* phiB,
+                            double coeff, const double* coeffView, double dt, double* out, fvk_stream stream);
 /* dsl::solve's explicit source when it is ONE surfaceIntegrate operator (the pressure equation's `- exp::div(phiHbyA)`):
  * rhs -= (0 + coeff/V * sum_f flux_f) * V in one pass = SurfaceIntegrate::explicitOperation into a zeroed source
  * (operators/surfaceIntegrate.hpp) followed by dsl/solver.hpp:73-77, bit for bit, without the source vector */

@@ -130,6 +130,23 @@ def test_forward_euler_advection_64_cubed():
     assert np.array_equal(host(app.T.internal), ref.T)
 
 
+def test_fused_forward_euler_step_equals_the_dsl_sequence():
+    """fvk_div_forward_euler_s (T = old - dt * div written by the div kernel) vs dsl::solve's div -> source -> waxpby: same bits."""
+    d = adv.advection_desc(24, True)
+    C = OMesh.from_desc(d).C.reshape(-1, 3)
+    U, T = adv.init_fields_columns(C, 24 * 24)
+    for scheme in ("upwind", "linear"):
+        schemes = {"ddtSchemes": {"type": "forwardEuler"}, "divSchemes": {"div(phi,nfT)": f"Gauss {scheme}"}}
+        a = adv.ScalarAdvection(M.UnstructuredMesh(d), 5e-4, 0.1, fvSchemes=schemes, U=U, T=T)
+        b = adv.ScalarAdvection(M.UnstructuredMesh(d), 5e-4, 0.1, fvSchemes=schemes, U=U, T=T, fuse_euler=False)
+        assert a.fuse_euler and not b.fuse_euler
+        for _ in range(6):
+            a.step(); b.step()
+            assert torch.equal(a.T.internal, b.T.internal) and torch.equal(a.T.boundary.value, b.T.boundary.value)
+    with pytest.raises(Exception):   # in place is a race: rejected
+        ops.div_forward_euler(a.mesh, a.phi.internal, a.T.internal, a.T.boundary.value, 1e-3, a.T.internal, ops.UPWIND)
+
+
 def test_adjust_time_step_follows_setDeltaT():
     d = adv.advection_desc(32)
     gm, om = M.UnstructuredMesh(d), OMesh.from_desc(d)
