@@ -9,20 +9,24 @@
 
 #include <cmath>
 #include <cstring>
+#include <memory>
 #include <new>
+#include <utility>
 #include <vector>
 
 namespace
 {
+template <class T> using RawVec = FvkRawVec<T>; // (fvk_internal.hpp: no serial zero-fill; every element below is written by the parallel loops)
 
 struct BlockMeshStore
 {
     fvk_mesh_desc desc {};
-    std::vector<double> points, V, C, Sf, Cf, magSf;
-    std::vector<int32_t> owner, neighbour, faceCells, patchOffsets;
-    std::vector<double> bCf, bCn, bSf, bMagSf, bNf, bDelta, bWeights, bDeltaCoeffs;
+    RawVec<double> points, V, C, Sf, Cf, magSf;
+    RawVec<int32_t> owner, neighbour, faceCells;
+    std::vector<int32_t> patchOffsets;
+    RawVec<double> bCf, bCn, bSf, bMagSf, bNf, bDelta, bWeights, bDeltaCoeffs;
     // poly (all faces incl. empty patches)
-    std::vector<int32_t> polyFaces, polyOwner;
+    RawVec<int32_t> polyFaces, polyOwner;
     int32_t nPolyFaces = 0;
 };
 
@@ -148,7 +152,7 @@ extern "C" int fvk_blockmesh_create(int32_t nx, int32_t ny, int32_t nz, double l
             st->polyOwner.resize(nPoly);
         }
         // internal faces: owner ascending, then +x, +y, +z. First face id of each cell by scan.
-        std::vector<int32_t> ownStart(size_t(nC) + 1);
+        RawVec<int32_t> ownStart(size_t(nC) + 1);
         {
             // faces owned by cell (i,j,k) = (i<nx-1)+(j<ny-1)+(k<nz-1); closed form per row
             int64_t run = 0;
@@ -197,7 +201,7 @@ extern "C" int fvk_blockmesh_create(int32_t nx, int32_t ny, int32_t nz, double l
             return side < 2 ? k * ny + j : (side < 4 ? i * nz + k : i * ny + j);
         };
         const int64_t nPolyBnd = nPolyB;
-        std::vector<double> bndCf(3 * size_t(nPolyBnd)), bndSf(3 * size_t(nPolyBnd)); // geometry of ALL boundary poly faces (incl. empty patches)
+        RawVec<double> bndCf(3 * size_t(nPolyBnd)), bndSf(3 * size_t(nPolyBnd)); // geometry of ALL boundary poly faces (incl. empty patches)
         st->owner.resize(nF);
         st->Sf.resize(3 * size_t(nF));
         st->Cf.resize(3 * size_t(nF));
@@ -336,9 +340,9 @@ extern "C" int fvk_blockmesh_create(int32_t nx, int32_t ny, int32_t nz, double l
                     for (int d = 0; d < 3; ++d) st->C[3 * c + d] = Cc[d] / Vc;
                     st->V[c] = Vc * (1.0 / 3.0);
                 }
-        std::vector<double>().swap(bndCf);
-        std::vector<double>().swap(bndSf);
-        std::vector<int32_t>().swap(ownStart);
+        RawVec<double>().swap(bndCf);
+        RawVec<double>().swap(bndSf);
+        RawVec<int32_t>().swap(ownStart);
 #pragma omp parallel for schedule(static)
         for (int64_t f = 0; f < nF; ++f)
         {
@@ -372,7 +376,7 @@ extern "C" int fvk_blockmesh_create(int32_t nx, int32_t ny, int32_t nz, double l
             st->bWeights[b] = 1.0;
             st->bDeltaCoeffs[b] = 1.0 / std::sqrt(d2);
         }
-        if (!withPoints) std::vector<double>().swap(st->points);
+        if (!withPoints) RawVec<double>().swap(st->points);
 
         fvk_mesh_desc& d = st->desc;
         d.nCells = nC; d.nInternalFaces = nI; d.nBoundaryFaces = nB; d.nPatches = nKeptPatches;

@@ -38,7 +38,7 @@ void fvk_build_stencil(const fvk_mesh_desc* d, FvkStencilHost& st, bool withPlan
     }
     for (int32_t c = 0; c < nC; ++c) seg[size_t(c) + 1] += seg[c];
     const size_t nEnt = size_t(seg[nC]);
-    std::vector<int32_t>&val = st.val, &ent = st.ent, &plan = st.plan;
+    FvkRawVec<int32_t>&val = st.val, &ent = st.ent, &plan = st.plan;
     val.resize(nEnt); ent.resize(nEnt);
     if (withPlan) plan.resize(2 * nEnt); else plan.clear();
     {
@@ -301,7 +301,10 @@ bool fvk_build_brick_plan(const fvk_mesh_desc* d, const FvkStencilHost& st, FvkB
     make_tiles(nOwned, out.dims, structured, out.brick, tiles);
     const int32_t nT = int32_t(tiles.size());
 
-    std::vector<int32_t> cellTile(size_t(nC), -1), cellFaceStart(size_t(nC), 0), cellSlotBase(size_t(nC), 0);
+    FvkRawVec<int32_t> cellTile, cellFaceStart, cellSlotBase; // (filled in parallel below)
+    cellTile.resize(size_t(nC)); cellFaceStart.resize(size_t(nC)); cellSlotBase.resize(size_t(nC));
+#pragma omp parallel for schedule(static)
+    for (int32_t c = 0; c < nC; ++c) { cellTile[c] = -1; cellFaceStart[c] = 0; cellSlotBase[c] = 0; }
     std::vector<int32_t> tSlots(nT, 0), tCodes(nT, 0), tX(nT, 0), tB(nT, 0), tC(nT, 0);
     int bad = 0;
     // pass 1: per-cell order check, own-slot numbering
@@ -366,7 +369,8 @@ bool fvk_build_brick_plan(const fvk_mesh_desc* d, const FvkStencilHost& st, FvkB
         out.maxCells = std::max(out.maxCells, tC[t]);
     }
     out.rec.resize(size_t(recBase));
-    out.codes.assign(size_t(codeBase) + 8, kPad); // every list is a multiple of 4 codes (codeBase too), padded with kPad
+    out.codes.resize(size_t(codeBase) + 8);       // every list is a multiple of 4 codes (codeBase too), padded with kPad by pass 2
+    for (int q = 0; q < 8; ++q) out.codes[size_t(codeBase) + q] = kPad;
     out.xFace.resize(size_t(xBase)); out.xOwner.resize(size_t(xBase)); out.xNei.resize(size_t(xBase));
     out.bFace.resize(size_t(bBase)); out.bCell.resize(size_t(bBase));
     // pass 2: fill
@@ -425,8 +429,8 @@ bool fvk_build_brick_plan(const fvk_mesh_desc* d, const FvkStencilHost& st, FvkB
     }
     else
         g.brick[0] = g.cap; // tiles of `cap` consecutive cells (make_tiles used the same size)
-    out.recF.assign(size_t(nT) * (g.cap + 1), FvkBrickRec {0, 0});
-    out.codes4.assign(size_t(nT) * g.cap, make_uint2(0xffffffffu, 0xffffffffu));
+    out.recF.resize(size_t(nT) * (g.cap + 1));    // the entries behind a ragged tile's cells are padded in the loop below
+    out.codes4.resize(size_t(nT) * g.cap);
     out.tileInfo.resize(nT);
     int geomBad = 0;
 #pragma omp parallel for schedule(static) reduction(| : geomBad)
@@ -435,6 +439,8 @@ bool fvk_build_brick_plan(const fvk_mesh_desc* d, const FvkStencilHost& st, FvkB
         const FvkBrickHdr& h = out.hdr[t];
         bool ghost = false;
         for (int32_t lc = 0; lc <= h.nc; ++lc) out.recF[size_t(t) * (g.cap + 1) + lc] = out.rec[size_t(h.recBase) + lc];
+        for (int32_t lc = h.nc + 1; lc <= g.cap; ++lc) out.recF[size_t(t) * (g.cap + 1) + lc] = FvkBrickRec {0, 0};
+        for (int32_t lc = h.nc; lc < g.cap; ++lc) out.codes4[size_t(t) * g.cap + lc] = make_uint2(0xffffffffu, 0xffffffffu);
         for_tile_cells(tiles[t], [&](int32_t c, int32_t lc) {
             int32_t nc = 0;
             if (fvk_brick_cell(g, t, lc, nc) != c || nc != h.nc) geomBad |= 1;
@@ -460,8 +466,9 @@ bool fvk_build_brick_plan(const fvk_mesh_desc* d, const FvkStencilHost& st, FvkB
     if (!noAffine && structured && g.dims[0] >= 3 && g.dims[1] >= 3 && g.dims[2] >= 3 && int64_t(3) * nOwned + 8 < (int64_t(1) << 31))
     {
         const int64_t nx = g.dims[0], ny = g.dims[1], nz = g.dims[2], nxy = nx * ny;
-        for (int combo = 0; combo < 8 && !g.affine; ++combo)
+        for (int cq = 7; cq >= 0 && !g.affine; --cq) // (1,1,1) -- a whole block, the common case -- first
         {
+            const int combo = cq;
             const int64_t tx = combo & 1, ty = (combo >> 1) & 1, tz = (combo >> 2) & 1;
             auto fsOf = [&](int64_t c) {
                 const int64_t i = c % nx, j = (c / nx) % ny, k = c / nxy;
@@ -505,11 +512,20 @@ bool fvk_build_brick_plan(const fvk_mesh_desc* d, const FvkStencilHost& st, FvkB
             }
         }
         if (g.affine)
-            for (int32_t c = 0; c < nOwned; ++c)
+        { // the irregular cells in ascending id: count per z-plane, scan, fill (parallel)
+            std::vector<int64_t> planeOff(size_t(nz) + 1, 0);
+            for (int64_t k = 0; k < nz; ++k)
+                planeOff[size_t(k) + 1] = planeOff[k] + ((k == 0 || k == nz - 1) ? nxy : nxy - std::max<int64_t>(nx - 2, 0) * std::max<int64_t>(ny - 2, 0));
+            out.irrCells.resize(size_t(planeOff[nz]));
+#pragma omp parallel for schedule(static)
+            for (int64_t k = 0; k < nz; ++k)
             {
-                const int64_t i = c % nx, j = (c / nx) % ny, k = c / nxy;
-                if (!(i > 0 && i < nx - 1 && j > 0 && j < ny - 1 && k > 0 && k < nz - 1)) out.irrCells.push_back(c);
+                int64_t w = planeOff[k];
+                for (int64_t j = 0; j < ny; ++j)
+                    for (int64_t i = 0; i < nx; ++i)
+                        if (!(i > 0 && i < nx - 1 && j > 0 && j < ny - 1 && k > 0 && k < nz - 1)) out.irrCells[size_t(w++)] = int32_t(i + nx * j + nxy * k);
             }
+        }
     }
     return true;
 }

@@ -10,23 +10,23 @@
 struct FvkStencilHost
 {
     std::vector<int32_t> seg;  // [nC+1]
-    std::vector<int32_t> val;  // ascending local face id per cell (the reference's stencil values)
-    std::vector<int32_t> ent;  // (face << 1) | (cell is the face's neighbour), accumulation order
-    std::vector<int32_t> plan; // 2 per entry: {ent, other cell}; boundary face b: {-(b + 1), own cell} (only withPlan)
+    FvkRawVec<int32_t> val;  // ascending local face id per cell (the reference's stencil values)
+    FvkRawVec<int32_t> ent;  // (face << 1) | (cell is the face's neighbour), accumulation order
+    FvkRawVec<int32_t> plan; // 2 per entry: {ent, other cell}; boundary face b: {-(b + 1), own cell} (only withPlan)
 };
 void fvk_build_stencil(const fvk_mesh_desc* d, FvkStencilHost& st, bool withPlan = false);
 
 struct FvkBrickPlanHost
 {
     std::vector<FvkBrickHdr> hdr;
-    std::vector<FvkBrickRec> rec;
-    std::vector<uint16_t> codes;
-    std::vector<int32_t> xFace, xOwner, xNei, bFace, bCell;
+    FvkRawVec<FvkBrickRec> rec;      // (raw: every entry is written by the parallel fill passes)
+    FvkRawVec<uint16_t> codes;
+    FvkRawVec<int32_t> xFace, xOwner, xNei, bFace, bCell;
     int32_t maxSlots = 0, maxCells = 0;
     // direct-indexed copies + tiling geometry (see FvkBrickPlan)
     FvkBrickGeom geom;
-    std::vector<FvkBrickRec> recF;
-    std::vector<uint2> codes4;
+    FvkRawVec<FvkBrickRec> recF;
+    FvkRawVec<uint2> codes4;
     std::vector<int4> tileInfo;
     std::vector<int32_t> irrCells;
     int32_t dims[3] = {0, 0, 0};  // detected block-structured numbering (0,0,0: none -> runs of consecutive cells)

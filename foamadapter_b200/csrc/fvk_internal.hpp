@@ -4,6 +4,23 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <memory>
+#include <utility>
+#include <vector>
+
+// Host work arrays that are FULLY written by parallel loops: std::vector::resize would value-initialise them on one thread first
+// (gigabytes of zero pages at 256^3); with this allocator resize leaves them default-initialised and the pages are first touched
+// by the threads that fill them.
+template <class T>
+struct FvkRawAllocator : std::allocator<T>
+{
+    template <class U> struct rebind { using other = FvkRawAllocator<U>; };
+    FvkRawAllocator() = default;
+    template <class U> FvkRawAllocator(const FvkRawAllocator<U>&) {}
+    template <class U> void construct(U* p) { ::new (static_cast<void*>(p)) U; }
+    template <class U, class... A> void construct(U* p, A&&... a) { ::new (static_cast<void*>(p)) U(std::forward<A>(a)...); }
+};
+template <class T> using FvkRawVec = std::vector<T, FvkRawAllocator<T>>;
 
 
 // record an error message (thread-local) and return `code`
