@@ -154,6 +154,12 @@ int main()
             EXPECT(std::abs(st.initResNorm - 3.741657386) < 1e-8);
             EXPECT(st.finalResNorm < 1e-4);
             EXPECT(std::abs(xh[0] - 1.24489796) < 1e-8 && std::abs(xh[1] - 2.44897959) < 1e-8 && std::abs(xh[2] - 3.24489796) < 1e-8);
+            // single-GPU solver: the solution trivially "keeps its ghosts"; no solve ran inside a CUDA graph, so the device log is empty
+            EXPECT(solver.keepsGhosts());
+            EXPECT(solver.capturedLog().empty());
+            solver.setGhostsCurrent(true);   // a no-op without a communicator: same answer
+            Vector<scalar> x2(exec, 3, 0.0);
+            EXPECT(solver.solve(ls, x2).numIter == 3);
             // mapFvSolution: PCG + DIC -> Cg + scalar Jacobi, tolerance -> absolute_residual_norm
             auto mapped = FoamAdapter::mapFvSolution(Dictionary {{"solver", std::string("PCG")}, {"preconditioner", std::string("DIC")}, {"tolerance", 1e-6}, {"relTol", 0.0}});
             EXPECT(mapped.get<std::string>("type") == "solver::Cg");
