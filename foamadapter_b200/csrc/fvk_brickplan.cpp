@@ -625,6 +625,129 @@ int64_t fvk_verify_brick_plan(const fvk_mesh_desc* d, const FvkStencilHost& st, 
     return badCells;
 }
 
+// ---- sparsity pattern: row = [lower (face order) | diag | upper (face order)] (sparsityPattern.cpp:21-143). The reference's three
+// serial passes over the faces place, in row r, the lower entries in ascending face id, the diagonal, then the upper entries in
+// ascending face id; built here row by row in parallel from the cell's stencil (sorted by LOCAL face id, which is what the passes
+// visit). A decomposed mesh (faceOrder key; the reference has no such path) sorts each half by the GLOBAL face id instead: the
+// ghost-owned faces, which the sub-domain numbers last, then sit where the undecomposed mesh has them, the rows stay in stencil
+// order and the index-free kernels serve every rank's sub-domain.
+bool fvk_build_sparsity(const fvk_mesh_desc* d, const FvkStencilHost& sth, FvkSparsityHost& out)
+{
+    const int32_t nC = d->nCells, nI = d->nInternalFaces;
+    const int32_t* own = d->faceOwner;
+    const int32_t* nei = d->faceNeighbour;
+    const int32_t* fkey = d->faceOrder;
+    std::vector<int32_t>& rowOffs = out.rowOffs;
+    rowOffs.assign(size_t(nC) + 1, 0);
+    int tooLong = -1;
+#pragma omp parallel for schedule(static) reduction(max : tooLong)
+    for (int32_t c = 0; c < nC; ++c)
+    {
+        int32_t n = 1;
+        for (int32_t e = sth.seg[c]; e < sth.seg[size_t(c) + 1]; ++e) n += (sth.ent[e] >> 1) < nI;
+        if (n > 255) tooLong = std::max(tooLong, c);
+        rowOffs[size_t(c) + 1] = n;
+    }
+    out.tooLongCell = tooLong;
+    if (tooLong >= 0) return false;
+    for (int32_t c = 0; c < nC; ++c) rowOffs[size_t(c) + 1] += rowOffs[c];
+    FvkRawVec<int32_t>& col = out.col;          // every entry / offset below is written by the per-row loop
+    FvkRawVec<uint8_t>&ownOff = out.ownOff, &neiOff = out.neiOff, &diagOff = out.diagOff;
+    col.resize(size_t(rowOffs[nC]));
+    ownOff.resize(size_t(nI)); neiOff.resize(size_t(nI)); diagOff.resize(size_t(nC));
+#pragma omp parallel
+    {
+        std::vector<int32_t> lower, upper;
+#pragma omp for schedule(static)
+        for (int32_t c = 0; c < nC; ++c)
+        {
+            lower.clear(); upper.clear();
+            for (int32_t e = sth.seg[c]; e < sth.seg[size_t(c) + 1]; ++e)
+            {
+                const int32_t f = sth.ent[e] >> 1;
+                if (f >= nI) continue;
+                ((sth.ent[e] & 1) ? lower : upper).push_back(f);
+            }
+            if (fkey)
+            {
+                auto byKey = [fkey](int32_t a, int32_t b) { return fkey[a] < fkey[b]; };
+                std::sort(lower.begin(), lower.end(), byKey);
+                std::sort(upper.begin(), upper.end(), byKey);
+            }
+            else
+            {
+                std::sort(lower.begin(), lower.end());
+                std::sort(upper.begin(), upper.end());
+            }
+            const size_t r0 = size_t(rowOffs[c]);
+            int32_t k = 0;
+            for (int32_t f : lower) { neiOff[f] = uint8_t(k); col[r0 + k] = own[f]; ++k; }
+            diagOff[c] = uint8_t(k);
+            col[r0 + k] = c;
+            ++k;
+            for (int32_t f : upper) { ownOff[f] = uint8_t(k); col[r0 + k] = nei[f]; ++k; }
+        }
+    }
+    // rows in stencil order? (k_assemble_fast / k_rAU_HbyA_rows derive slots from stencil positions)
+    int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+    for (int32_t c = 0; c < nC; ++c)
+    {
+        int32_t k = 0;
+        for (int32_t e = sth.seg[c]; e < sth.seg[size_t(c) + 1]; ++e, ++k)
+        {
+            const int32_t f = sth.ent[e] >> 1;
+            if (f >= nI) break;
+            const bool side = sth.ent[e] & 1;
+            if (side ? (neiOff[f] != k || k >= diagOff[c]) : (ownOff[f] != k + 1 || k < diagOff[c])) bad |= 1;
+        }
+    }
+    out.rowsInStencilOrder = !bad;
+    return true;
+}
+
+// diagnostics (host only): the SparsityPattern exactly as fvk_mesh_create builds it. result[4] = {rows, nnz, every row in stencil
+// order (0/1), rows that are NOT [lower columns | own id | upper columns] with the diagonal where diagOffset says (must be 0)}
+extern "C" int fvk_sparsity_selftest(const fvk_mesh_desc* d, int64_t* result /* [4] */)
+{
+    if (!d || !result) return fvk_fail(FVK_EINVAL, "fvk_sparsity_selftest: null");
+    FvkStencilHost st;
+    fvk_build_stencil(d, st);
+    FvkSparsityHost sp;
+    if (!fvk_build_sparsity(d, st, sp)) return fvk_fail(FVK_EUNSUPPORTED, "fvk_sparsity_selftest: cell %d has > 255 row entries", sp.tooLongCell);
+    const int32_t nC = d->nCells, nI = d->nInternalFaces;
+    int64_t badRows = 0;
+    for (int32_t c = 0; c < nC; ++c)
+        if (sp.col[size_t(sp.rowOffs[c]) + sp.diagOff[c]] != c) ++badRows;
+    for (int32_t f = 0; f < nI; ++f)
+        if (sp.col[size_t(sp.rowOffs[d->faceOwner[f]]) + sp.ownOff[f]] != d->faceNeighbour[f]
+            || sp.col[size_t(sp.rowOffs[d->faceNeighbour[f]]) + sp.neiOff[f]] != d->faceOwner[f])
+            ++badRows;
+    if (!d->faceOrder)
+    { // single-domain mesh: the reference's own three serial passes over the faces (sparsityPattern.cpp:21-143) must give the same
+      // column array as the row-parallel builder
+        std::vector<int64_t> ro(size_t(nC) + 1, 0);
+        for (int32_t c = 0; c < nC; ++c) ro[size_t(c) + 1] = 1;
+        for (int32_t f = 0; f < nI; ++f) { ++ro[size_t(d->faceOwner[f]) + 1]; ++ro[size_t(d->faceNeighbour[f]) + 1]; }
+        for (int32_t c = 0; c < nC; ++c) ro[size_t(c) + 1] += ro[c];
+        std::vector<int32_t> col, cnt;
+        col.resize(size_t(ro[nC])); cnt.assign(size_t(nC), 0);
+        for (int32_t f = 0; f < nI; ++f) { const int32_t n = d->faceNeighbour[f]; col[size_t(ro[n]) + cnt[n]++] = d->faceOwner[f]; }
+        for (int32_t c = 0; c < nC; ++c) col[size_t(ro[c]) + cnt[c]++] = c;
+        for (int32_t f = 0; f < nI; ++f) { const int32_t o = d->faceOwner[f]; col[size_t(ro[o]) + cnt[o]++] = d->faceNeighbour[f]; }
+        if (ro[nC] != sp.rowOffs[nC]) ++badRows;
+        else
+            for (int32_t c = 0; c < nC; ++c)
+            {
+                bool same = ro[c] == sp.rowOffs[c];
+                for (int64_t k = ro[c]; same && k < ro[size_t(c) + 1]; ++k) same = col[size_t(k)] == sp.col[size_t(k)];
+                if (!same) ++badRows;
+            }
+    }
+    result[0] = nC; result[1] = sp.rowOffs[nC]; result[2] = sp.rowsInStencilOrder ? 1 : 0; result[3] = badRows;
+    return FVK_OK;
+}
+
 // diagnostics entry (host only, no device needed): build stencil + brick plan for a mesh description and replay it
 extern "C" int fvk_brick_plan_selftest(const fvk_mesh_desc* d, int32_t* info /* [8] */, int64_t* badCells)
 {

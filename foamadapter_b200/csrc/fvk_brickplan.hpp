@@ -16,6 +16,18 @@ struct FvkStencilHost
 };
 void fvk_build_stencil(const fvk_mesh_desc* d, FvkStencilHost& st, bool withPlan = false);
 
+// SparsityPattern on the host (sparsityPattern.cpp:21-143): row = [lower (face order) | diag | upper (face order)], built row by row in
+// parallel from the cell's stencil. A decomposed mesh (faceOrder key) orders each half by the GLOBAL face id -- see fvk_build_sparsity.
+struct FvkSparsityHost
+{
+    std::vector<int32_t> rowOffs;            // [nC + 1]
+    FvkRawVec<int32_t> col;                  // [nnz]
+    FvkRawVec<uint8_t> ownOff, neiOff, diagOff; // [nI], [nI], [nC]
+    bool rowsInStencilOrder = false;         // every row's entries sit at their stencil positions (+1 behind the diagonal)
+    int32_t tooLongCell = -1;                // a row with > 255 entries (uint8 offsets): pattern not built
+};
+bool fvk_build_sparsity(const fvk_mesh_desc* d, const FvkStencilHost& st, FvkSparsityHost& out);
+
 struct FvkBrickPlanHost
 {
     std::vector<FvkBrickHdr> hdr;

@@ -567,87 +567,21 @@ extern "C" int fvk_mesh_create(const fvk_mesh_desc* d, fvk_mesh** out)
         if (experiment_plans()) UP(gatherPlan, plan.data(), 2 * nEnt); // packed-plan gathers (fvk_set_variant 1-4)
         tm.lap("upload stencil");
     }
-    // ---- sparsity pattern: row = [lower (face order) | diag | upper (face order)] (sparsityPattern.cpp:21-143). The
-    // reference's three serial passes over the faces place, in row r, the lower entries in ascending face id, the diagonal,
-    // then the upper entries in ascending face id; built here row by row in parallel from the cell's stencil (sorted by
-    // LOCAL face id, which is what the passes visit). A decomposed mesh (faceOrder key; the reference has no such path) sorts
-    // each half by the GLOBAL face id instead: the ghost-owned faces, which the sub-domain numbers last, then sit where the
-    // undecomposed mesh has them, the rows stay in stencil order and the index-free kernels serve every rank's sub-domain.
+    // ---- sparsity pattern (host builder shared with the CPU self-test: fvk_build_sparsity, fvk_brickplan.cpp)
     {
-        const int32_t* fkey = d->faceOrder;
-        std::vector<int32_t> rowOffs(size_t(nC) + 1, 0);
-        int tooLong = -1;
-#pragma omp parallel for schedule(static) reduction(max : tooLong)
-        for (int32_t c = 0; c < nC; ++c)
+        FvkSparsityHost sph;
+        if (!fvk_build_sparsity(d, sth, sph))
         {
-            int32_t n = 1;
-            for (int32_t e = sth.seg[c]; e < sth.seg[size_t(c) + 1]; ++e) n += (sth.ent[e] >> 1) < nI;
-            if (n > 255) tooLong = std::max(tooLong, c);
-            rowOffs[size_t(c) + 1] = n;
-        }
-        if (tooLong >= 0)
-        {
+            const int32_t cell = sph.tooLongCell;
             fvk_mesh_destroy(m);
-            return fvk_fail(FVK_EUNSUPPORTED, "fvk_mesh_create: cell %d has > 255 row entries (uint8 offsets)", tooLong);
+            return fvk_fail(FVK_EUNSUPPORTED, "fvk_mesh_create: cell %d has > 255 row entries (uint8 offsets)", cell);
         }
-        for (int32_t c = 0; c < nC; ++c) rowOffs[size_t(c) + 1] += rowOffs[c];
-        FvkRawVec<int32_t> col(size_t(m->nnz));          // every entry / offset below is written by the per-row loop
-        FvkRawVec<uint8_t> ownOff(nI), neiOff(nI), diagOff(nC);
-#pragma omp parallel
-        {
-            std::vector<int32_t> lower, upper;
-#pragma omp for schedule(static)
-            for (int32_t c = 0; c < nC; ++c)
-            {
-                lower.clear(); upper.clear();
-                for (int32_t e = sth.seg[c]; e < sth.seg[size_t(c) + 1]; ++e)
-                {
-                    const int32_t f = sth.ent[e] >> 1;
-                    if (f >= nI) continue;
-                    ((sth.ent[e] & 1) ? lower : upper).push_back(f);
-                }
-                if (fkey)
-                {
-                    auto byKey = [fkey](int32_t a, int32_t b) { return fkey[a] < fkey[b]; };
-                    std::sort(lower.begin(), lower.end(), byKey);
-                    std::sort(upper.begin(), upper.end(), byKey);
-                }
-                else
-                {
-                    std::sort(lower.begin(), lower.end());
-                    std::sort(upper.begin(), upper.end());
-                }
-                const size_t r0 = size_t(rowOffs[c]);
-                int32_t k = 0;
-                for (int32_t f : lower) { neiOff[f] = uint8_t(k); col[r0 + k] = own[f]; ++k; }
-                diagOff[c] = uint8_t(k);
-                col[r0 + k] = c;
-                ++k;
-                for (int32_t f : upper) { ownOff[f] = uint8_t(k); col[r0 + k] = nei[f]; ++k; }
-            }
-        }
-        {
-            // rows in stencil order? (k_assemble_fast derives slots from stencil positions)
-            int bad = 0;
-#pragma omp parallel for schedule(static) reduction(| : bad)
-            for (int32_t c = 0; c < nC; ++c)
-            {
-                int32_t k = 0;
-                for (int32_t e = sth.seg[c]; e < sth.seg[size_t(c) + 1]; ++e, ++k)
-                {
-                    const int32_t f = sth.ent[e] >> 1;
-                    if (f >= nI) break;
-                    const bool side = sth.ent[e] & 1;
-                    if (side ? (neiOff[f] != k || k >= diagOff[c]) : (ownOff[f] != k + 1 || k < diagOff[c])) bad |= 1;
-                }
-            }
-            m->rowsInStencilOrder = !bad;
-        }
-        UP(rowOffs, rowOffs.data(), rowOffs.size());
-        UP(colIdxs, col.data(), col.size());
-        UP(ownerOffset, ownOff.data(), nI);
-        UP(neighbourOffset, neiOff.data(), nI);
-        UP(diagOffset, diagOff.data(), nC);
+        m->rowsInStencilOrder = sph.rowsInStencilOrder;
+        UP(rowOffs, sph.rowOffs.data(), sph.rowOffs.size());
+        UP(colIdxs, sph.col.data(), sph.col.size());
+        UP(ownerOffset, sph.ownOff.data(), nI);
+        UP(neighbourOffset, sph.neiOff.data(), nI);
+        UP(diagOffset, sph.diagOff.data(), nC);
         tm.lap("sparsity pattern + upload");
     }
     {

@@ -642,6 +642,10 @@ int fvk_brick_plan_affine_info(const fvk_mesh_desc* desc_h, int32_t* info_h);
  * and every regular row of the SparsityPattern is [c-nx*ny, c-nx, c-1, c, c+1, c+nx, c+nx*ny], 0 when the topology is not
  * affine (generic SpMV is used), -1 on a violation; result_h[1] = rows checked. */
 int fvk_brick_plan_structured_rows(const fvk_mesh_desc* desc_h, int64_t* result_h);
+/* HOST only: the SparsityPattern exactly as fvk_mesh_create builds it (same host function). result_h[4] = {rows, nnz, every row in
+ * stencil order (0/1: what lets the index-free assembly / rAU,HbyA kernels run; holds on every sub-domain of a decomposed block
+ * because each half of a row follows the GLOBAL face order), number of offset / diagonal inconsistencies (must be 0)}. */
+int fvk_sparsity_selftest(const fvk_mesh_desc* desc_h, int64_t* result_h);
 
 #ifdef __cplusplus
 }
